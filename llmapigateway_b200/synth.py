@@ -1,0 +1,148 @@
+"""Seeded synthetic upstreams (BASELINE.json north_star: "upstream providers are replaced
+in-bench by a local synthetic SSE generator").  Workload shapes follow SURVEY.md section 8(d).
+
+Everything here is host-side numpy; it produces the packed step layout the engine takes
+(see include/llmgw_b200.h): one byte buffer, chunk offsets, and per-stream segments.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+DELTA_HEAD = b'data: {"choices":[{"index":0,"delta":{"content":"'
+DELTA_TAIL = b'"}}]}\n\n'
+DELTA_CONTENT = 8
+DELTA_EVENT_BYTES = len(DELTA_HEAD) + DELTA_CONTENT + len(DELTA_TAIL)  # 64
+DONE_EVENT = b"data: [DONE]\n\n"
+
+# printable ASCII without '"' and '\\' 
+_ALPHABET = np.array([c for c in range(0x20, 0x7F) if c not in (0x22, 0x5C)], dtype=np.uint8)
+
+MODEL_NAMES = ["deepseek/deepseek-chat-v3-0324", "google/gemini-2.5-pro", "grok-3-mini-beta",
+               "openai/gpt-4.1-mini", "deepseek-ai/DeepSeek-V3-0324", "anthropic/claude-sonnet"]
+PROVIDER_NAMES = ["Chutes", "Targon", "DeepInfra", "Lambda", "Nebius AI Studio"]
+
+
+@dataclass
+class UsageTruth:
+    prompt_tokens: int
+    completion_tokens: int      # as reported upstream (before the reasoning subtraction)
+    total_tokens: int
+    reasoning_tokens: int
+    cached_tokens: int
+    cost_text: str
+    model: str
+    provider: str
+
+    def expected_row(self) -> dict:
+        """What chat_logging.py:233-272 makes of this usage event."""
+        comp = self.completion_tokens - self.reasoning_tokens if self.reasoning_tokens > 0 else self.completion_tokens
+        return {"prompt_tokens": self.prompt_tokens, "completion_tokens": comp,
+                "total_tokens": self.total_tokens, "reasoning_tokens": self.reasoning_tokens,
+                "cached_tokens": self.cached_tokens, "cost": float(self.cost_text),
+                "provider": self.provider, "model": self.model}
+
+
+def usage_event(u: UsageTruth) -> bytes:
+    return (b'data: {"choices":[],"usage":{"prompt_tokens":%d,"completion_tokens":%d,"total_tokens":%d,'
+            b'"cost":%s,"completion_tokens_details":{"reasoning_tokens":%d},'
+            b'"prompt_tokens_details":{"cached_tokens":%d}},"model":"%s","provider":"%s"}\n\n'
+            % (u.prompt_tokens, u.completion_tokens, u.total_tokens, u.cost_text.encode(),
+               u.reasoning_tokens, u.cached_tokens, u.model.encode(), u.provider.encode()))
+
+
+def _usage_truths(n_streams: int, seed: int) -> list[UsageTruth]:
+    rng = np.random.default_rng([seed, 0xC3])
+    p = rng.integers(1, 2**31 - 1, n_streams)
+    r = rng.integers(0, 2**20, n_streams)
+    c = r + rng.integers(1, 2**30, n_streams)
+    h = rng.integers(0, 2**20, n_streams)
+    k = rng.integers(0, 10**6, n_streams)
+    mi = rng.integers(0, len(MODEL_NAMES), n_streams)
+    pi = rng.integers(0, len(PROVIDER_NAMES), n_streams)
+    out = []
+    for i in range(n_streams):
+        out.append(UsageTruth(int(p[i]), int(c[i]), int(min(p[i] + c[i], 2**31 - 1)), int(r[i]), int(h[i]),
+                              "%.6f" % (int(k[i]) / 1e6), MODEL_NAMES[mi[i]], PROVIDER_NAMES[pi[i]]))
+    return out
+
+
+@dataclass
+class PackedBatch:
+    """One engine step worth of upstream bytes, grouped per stream (segment)."""
+    data: np.ndarray            # uint8 [total_bytes]
+    chunk_off: np.ndarray       # uint32 [n_chunks + 1]
+    seg_chunk: np.ndarray       # uint32 [n_segs + 1]  chunk range of each segment
+    seg_slot: np.ndarray        # uint32 [n_segs]      engine stream slot of each segment
+    n_delta_events: int         # the events BASELINE.json's chunks/s counts
+    truths: list[UsageTruth]
+
+    @property
+    def n_chunks(self) -> int:
+        return int(self.chunk_off.shape[0] - 1)
+
+    def stream_chunks(self, seg: int) -> list[bytes]:
+        c0, c1 = int(self.seg_chunk[seg]), int(self.seg_chunk[seg + 1])
+        raw = self.data
+        return [raw[int(self.chunk_off[c]):int(self.chunk_off[c + 1])].tobytes() for c in range(c0, c1)]
+
+
+def sse_batch(n_streams: int = 4096, n_events: int = 512, seed: int = 3,
+              events_per_chunk: int = 1, with_usage: bool = True, with_done: bool = True,
+              slot_base: int = 0) -> PackedBatch:
+    """n_streams x n_events delta events of exactly 64 B, then (not counted)
+    one usage event and `data: [DONE]`, one event per network chunk (or `events_per_chunk`)."""
+    assert n_events % events_per_chunk == 0
+    rng = np.random.default_rng([seed, n_streams, n_events])
+    truths = _usage_truths(n_streams, seed)
+    head = np.frombuffer(DELTA_HEAD, dtype=np.uint8)
+    tail = np.frombuffer(DELTA_TAIL, dtype=np.uint8)
+    tails = [usage_event(t) if with_usage else b"" for t in truths]
+    done = DONE_EVENT if with_done else b""
+    tail_lens = np.array([len(t) for t in tails], dtype=np.int64)
+    delta_bytes = n_events * DELTA_EVENT_BYTES
+    seg_bytes = delta_bytes + tail_lens + len(done)
+    seg_start = np.concatenate([[0], np.cumsum(seg_bytes)])
+    data = np.empty(int(seg_start[-1]), dtype=np.uint8)
+    chunks_per_seg = n_events // events_per_chunk + (1 if with_usage else 0) + (1 if with_done else 0)
+    chunk_off = np.empty(n_streams * chunks_per_seg + 1, dtype=np.int64)
+    delta_chunk = DELTA_EVENT_BYTES * events_per_chunk
+    n_delta_chunks = n_events // events_per_chunk
+    for s in range(n_streams):
+        b = int(seg_start[s])
+        ev = data[b:b + delta_bytes].reshape(n_events, DELTA_EVENT_BYTES)
+        ev[:, :len(head)] = head
+        ev[:, len(head):len(head) + DELTA_CONTENT] = _ALPHABET[rng.integers(0, len(_ALPHABET), (n_events, DELTA_CONTENT))]
+        ev[:, len(head) + DELTA_CONTENT:] = tail
+        pos = b + delta_bytes
+        co = s * chunks_per_seg
+        chunk_off[co:co + n_delta_chunks] = b + delta_chunk * np.arange(n_delta_chunks)
+        k = co + n_delta_chunks
+        if with_usage:
+            t = tails[s]
+            data[pos:pos + len(t)] = np.frombuffer(t, dtype=np.uint8)
+            chunk_off[k] = pos; k += 1; pos += len(t)
+        if with_done:
+            data[pos:pos + len(done)] = np.frombuffer(done, dtype=np.uint8)
+            chunk_off[k] = pos; k += 1; pos += len(done)
+    chunk_off[-1] = seg_start[-1]
+    assert chunk_off[-1] < 2**32
+    seg_chunk = (np.arange(n_streams + 1, dtype=np.int64) * chunks_per_seg).astype(np.uint32)
+    return PackedBatch(data, chunk_off.astype(np.uint32), seg_chunk,
+                       (slot_base + np.arange(n_streams)).astype(np.uint32),
+                       n_streams * n_events, truths)
+
+
+def pack_streams(streams: list[list[bytes]], slots: list[int] | None = None) -> PackedBatch:
+    """Pack arbitrary per-stream chunk lists (tests, adversarial cases) into a step."""
+    offs, segc, blobs = [0], [0], []
+    for chunks in streams:
+        for c in chunks:
+            blobs.append(c)
+            offs.append(offs[-1] + len(c))
+        segc.append(segc[-1] + len(chunks))
+    data = np.frombuffer(b"".join(blobs), dtype=np.uint8).copy() if blobs else np.zeros(0, np.uint8)
+    slots = list(range(len(streams))) if slots is None else slots
+    return PackedBatch(data, np.array(offs, dtype=np.uint32), np.array(segc, dtype=np.uint32),
+                       np.array(slots, dtype=np.uint32), 0, [])
