@@ -1,0 +1,189 @@
+/* llmgw_b200 -- C ABI of the B200 streaming chat-completions transform engine.
+ *
+ * Drop-in boundary for the per-request hot path of fabiojbg/LLMApiGateway.
+ * The reference exposes no FFI for this path (it is inline Python); each entry point below
+ * names the reference code whose per-byte work it replaces.  Paths are relative to the
+ * reference root.  INTEGRATION.md shows the ctypes binding a maintainer adds on the Python side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer it passes in;
+ *   - every function returns 0 on success or a negative lgw_status; nothing throws across the
+ *     boundary; lgw_last_error() gives a human-readable reason;
+ *   - data errors (bad JSON, failed attempt, ...) are VALUES in the outputs, like the
+ *     reference's (None, error_detail) returns -- never a non-zero status;
+ *   - there is no CPU fallback: without a CUDA device lgw_engine_create fails;
+ *   - an engine handle is not thread-safe (one batcher thread per GPU owns it).
+ */
+#ifndef LLMGW_B200_H
+#define LLMGW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGW_ABI_VERSION 1
+
+typedef enum lgw_status {
+    LGW_OK = 0,
+    LGW_ERR_ARG = -1,        /* bad argument (null pointer, unsorted offsets, unknown slot ...) */
+    LGW_ERR_CUDA = -2,       /* a CUDA runtime call failed */
+    LGW_ERR_CAPACITY = -3,   /* step larger than the limits given at create time */
+    LGW_ERR_NO_DEVICE = -4   /* no usable CUDA device: the engine never computes on the CPU */
+} lgw_status;
+
+/* ---- value model ---------------------------------------------------------------------------
+ * JSON values copied "untyped" by chat_logging.py:248-267 keep their Python type, so every
+ * extracted field is a tagged value. */
+enum lgw_kind {
+    LGW_KIND_ABSENT = 0, LGW_KIND_INT = 1, LGW_KIND_FLOAT = 2, LGW_KIND_NULL = 3, LGW_KIND_TRUE = 4,
+    LGW_KIND_FALSE = 5, LGW_KIND_STR = 6, LGW_KIND_BIGINT = 7, LGW_KIND_OBJECT = 8, LGW_KIND_ARRAY = 9,
+    LGW_KIND_FLOAT_INEXACT = 10
+};
+
+typedef struct lgw_val {
+    int64_t bits;            /* INT: the value; FLOAT: IEEE-754 binary64 bit pattern */
+    uint8_t kind;            /* enum lgw_kind */
+    uint8_t _pad[7];
+} lgw_val;
+
+#define LGW_STR_CAP 120
+
+/* The dict get_token_usage returns (chat_logging.py:233-272), after its reasoning-token
+ * subtraction (:262-263).  model_val/provider_val.kind == ABSENT means the key is not in the dict. */
+typedef struct lgw_usage_rec {
+    lgw_val prompt_tokens, completion_tokens, total_tokens, reasoning_tokens, cached_tokens, cost;
+    lgw_val model_val, provider_val;
+    uint8_t model_len, provider_len;
+    uint8_t str_flags;       /* bit0/1: model truncated / lone surrogate; bit2/3: provider */
+    uint8_t exotic;          /* 1: some value is not representable here (big int, string where a number goes ...) */
+    char model[LGW_STR_CAP];
+    char provider[LGW_STR_CAP];
+} lgw_usage_rec;
+
+/* stream phases and verdicts (request_handler.py:65-98) */
+enum lgw_phase { LGW_PHASE_FREE = 0, LGW_PHASE_PRIMING = 1, LGW_PHASE_COMMITTED = 2, LGW_PHASE_FAILED = 3 };
+enum lgw_verdict {
+    LGW_VERDICT_NONE = 0,
+    LGW_VERDICT_OK = 1,          /* first real event accepted (:89-90) */
+    LGW_VERDICT_FAIL_EVENT = 2,  /* first real event carries top-level "error"/"detail" (:50-54,:86-88) */
+    LGW_VERDICT_FAIL_PARSE = 3,  /* first real event is not JSON (:85 -> :183-187) */
+    LGW_VERDICT_FAIL_HTTP = 4    /* upstream status >= 400 (:25-30) */
+};
+enum lgw_stream_flag {
+    LGW_SF_A_USAGE_BOUND = 1 << 0,   /* request_handler.py:134 ran (otherwise :144 raises UnboundLocalError) */
+    LGW_SF_EMITTED_ANY = 1 << 1,     /* a chunk was relayed => a tap thread / DB row exists (chat_logging.py:200) */
+    LGW_SF_CARRY_OVERFLOW = 1 << 2,  /* an unterminated event outgrew carry_cap (engine limit, reported) */
+    LGW_SF_EXOTIC_SEEN = 1 << 3,
+    LGW_SF_SYNCED = 1 << 4,
+    LGW_SF_REC_VALID = 1 << 5,
+    LGW_SF_DETAIL_TRUNC = 1 << 6,
+    LGW_SF_ROWQ_OVERFLOW = 1 << 7
+};
+
+typedef struct lgw_stream_state {
+    uint8_t phase, verdict;
+    uint16_t flags;
+    uint32_t carry_a_len, carry_b_len, detail_len;
+    uint32_t n_events_a, n_events_b, n_usage_b, n_exotic, n_error_rows;
+    uint32_t n_chunks_in, n_chunks_emitted;
+    uint64_t bytes_in, bytes_emitted;
+    lgw_usage_rec rec;       /* current tap record (valid when LGW_SF_REC_VALID, else the defaults) */
+} lgw_stream_state;
+
+/* a write_log call that happened mid-stream: tap saw a top-level "error" (chat_logging.py:137-139) */
+typedef struct lgw_row_event {
+    uint32_t slot, seq;
+    lgw_usage_rec rec;
+} lgw_row_event;
+
+typedef struct lgw_seg_result {
+    uint32_t emit_chunk_begin;   /* first chunk of the segment that is relayed this step; the relayed
+                                    chunks are [emit_chunk_begin, segment end): always a suffix */
+    uint8_t phase, verdict;
+    uint16_t flags;
+    uint32_t detail_len;         /* > 0 with a FAIL_* verdict: fetch with lgw_stream_detail */
+} lgw_seg_result;
+
+typedef struct lgw_limits {
+    uint32_t max_streams;        /* stream slots resident on the device */
+    uint32_t carry_cap;          /* bytes of unterminated event kept per stream between steps */
+    uint32_t detail_cap;         /* bytes of error detail kept per stream */
+    uint32_t rowq_cap;           /* mid-stream row events per step */
+    uint32_t max_step_chunks;    /* chunks per step (host-buffer entry points stage this much) */
+    uint64_t max_step_bytes;     /* bytes per step */
+} lgw_limits;
+
+typedef struct lgw_engine lgw_engine;
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+int lgw_abi_version(void);
+int lgw_engine_create(int device, const lgw_limits* limits, lgw_engine** out);
+int lgw_engine_destroy(lgw_engine* e);
+const char* lgw_last_error(const lgw_engine* e);    /* e may be NULL: error of the last failed create */
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the engine's own stream */
+int lgw_engine_set_stream(lgw_engine* e, void* cuda_stream);
+
+/* ---- streams ------------------------------------------------------------------------------------
+ * One slot = one upstream attempt of make_llm_request(..., is_streaming=True)
+ * (llm_gateway_core/services/request_handler.py:8).  http_status is the upstream response status
+ * (:25-30): >= 400 marks the attempt failed at once and the host keeps the body as error detail. */
+int lgw_streams_open(lgw_engine* e, const uint32_t* slots, const int32_t* http_status, uint32_t n);
+int lgw_streams_state(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* out);
+/* error detail of a failed attempt: the text the reference stores at request_handler.py:51,87
+ * (the whole first event, "data: " included) */
+int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uint32_t cap, uint32_t* len);
+/* end of upstream: final state (the last DB row of chat_logging.py:150 is `rec` when
+ * LGW_SF_EMITTED_ANY), slot returns to FREE */
+int lgw_streams_close(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* final_out);
+
+/* ---- the hot path ---------------------------------------------------------------------------------
+ * One batched pass over the newly arrived upstream chunks of many streams.  Replaces, per chunk,
+ *   request_handler.py:34-63   stream_generator   (decode, split on "\n\n", "data: {" test, first-event sniff)
+ *   request_handler.py:69-98   priming loop        (keep/drop, error/detail verdict)
+ *   request_handler.py:109-142 combined_generator  (parse, "code"/"usage" keys, relay bytes)
+ *   chat_logging.py:90-147     ChunkProcessorThread.run (parse again, choices walk, usage extraction)
+ *   chat_logging.py:233-272    get_token_usage
+ *
+ * Layout: chunk_bytes holds every chunk back to back; chunk c is bytes [chunk_off[c], chunk_off[c+1]).
+ * Chunks are grouped per stream in arrival order: segment s is chunks [seg_chunk[s], seg_chunk[s+1])
+ * of stream slot seg_slot[s]; a slot appears in at most one segment per step.
+ *
+ * out_bytes (same size as chunk_bytes) receives the re-emitted stream: for every relayed chunk
+ * the bytes at the same offsets (the reference relays original bytes, :141-142); bytes of dropped
+ * chunks are unspecified.  seg_out[s].emit_chunk_begin says where relaying starts in segment s.
+ * rows_out/n_rows: mid-stream row events of this step, in no particular order across streams
+ * (seq orders them within a stream).
+ *
+ * lgw_sse_step takes HOST pointers and performs the H2D/D2H copies itself (synchronous).
+ * lgw_sse_step_device takes DEVICE pointers for the five input arrays and out_bytes/seg_out, is
+ * asynchronous on the engine stream, and leaves row events on the device until lgw_fetch_rows. */
+int lgw_sse_step(lgw_engine* e,
+                 const uint8_t* chunk_bytes, uint64_t n_bytes,
+                 const uint32_t* chunk_off, uint32_t n_chunks,
+                 const uint32_t* seg_chunk, const uint32_t* seg_slot, uint32_t n_segs,
+                 uint8_t* out_bytes, lgw_seg_result* seg_out,
+                 lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows);
+int lgw_sse_step_device(lgw_engine* e,
+                        const uint8_t* d_chunk_bytes, uint64_t n_bytes,
+                        const uint32_t* d_chunk_off, uint32_t n_chunks,
+                        const uint32_t* d_seg_chunk, const uint32_t* d_seg_slot, uint32_t n_segs,
+                        uint8_t* d_out_bytes, lgw_seg_result* d_seg_out);
+int lgw_fetch_rows(lgw_engine* e, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows);
+int lgw_sync(lgw_engine* e);
+
+/* device time of the kernels of the last step (CUDA events on the launching stream), milliseconds:
+ * [0] prime  [1] relay (bulk parse + re-emit)  [2] commit  [3] whole step incl. copies (host entry only) */
+int lgw_last_step_ms(lgw_engine* e, float ms[4]);
+/* number of kernels launched by this engine since creation */
+int lgw_launch_count(lgw_engine* e, uint64_t* out);
+
+/* ---- pinned staging buffers (SURVEY 8(b) ownership) -------------------------------------------- */
+int lgw_alloc_pinned(lgw_engine* e, uint64_t bytes, void** out);
+int lgw_free_pinned(lgw_engine* e, void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMGW_B200_H */

@@ -1,0 +1,77 @@
+"""Loader for the TEST-AID host build of the device machines (tests/support/host_machine.cpp).
+CPU-only helper: lets the CPU suite fuzz the exact device code paths without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from llmapigateway_b200 import _abi
+
+SUP = Path(__file__).resolve().parent / "support"
+SRC = SUP / "host_machine.cpp"
+LIB = SUP / "_host_machine.so"
+CSRC = Path(__file__).resolve().parent.parent / "llmapigateway_b200" / "csrc"
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [SRC] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [CSRC.parent.parent / "include" / "llmgw_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if _stale():
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", str(LIB), str(SRC)])
+        _lib = C.CDLL(str(LIB))
+        _lib.lgwt_parse_part.restype = C.c_uint32
+    return _lib
+
+
+def parse_part(text: bytes):
+    rec = _abi.UsageRec()
+    cls = C.c_int(0)
+    f = lib().lgwt_parse_part(text, len(text), C.byref(rec), C.byref(cls))
+    return f, cls.value, rec
+
+
+def utf8_valid(b: bytes) -> bool:
+    return bool(lib().lgwt_utf8_valid(b, len(b)))
+
+
+def dec_to_double(man: int, exp10: int):
+    out = C.c_uint64(0)
+    ok = lib().lgwt_dec_to_double(C.c_uint64(man), C.c_int(exp10), C.byref(out))
+    return bool(ok), out.value
+
+
+def run_stream(chunks: list[bytes], steps: list[int] | None = None, http_status: int = 200,
+               carry_cap: int = 4096, detail_cap: int = 4096, rows_cap: int = 64):
+    """steps = chunk indices where a new step starts (first must be 0); default: one step."""
+    data = b"".join(chunks)
+    off = np.zeros(len(chunks) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(c) for c in chunks])
+    steps = [0] if steps is None else steps
+    step_chunk = np.array(list(steps) + [len(chunks)], dtype=np.uint32)
+    n_steps = len(step_chunk) - 1
+    segs = (_abi.SegResult * n_steps)()
+    st = _abi.StreamState()
+    detail = C.create_string_buffer(detail_cap + 1)
+    rows = (_abi.RowEvent * rows_cap)()
+    n_rows = C.c_uint32(0)
+    buf = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+    lib().lgwt_run_stream(buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                          step_chunk.ctypes.data_as(C.c_void_p), C.c_uint32(n_steps), C.c_int(http_status),
+                          C.c_uint32(carry_cap), C.c_uint32(detail_cap), segs, C.byref(st), detail,
+                          rows, C.c_uint32(rows_cap), C.byref(n_rows))
+    return dict(segs=list(segs), state=st, detail=detail.raw[:st.detail_len],
+                rows=[rows[i] for i in range(n_rows.value)], step_chunk=step_chunk)

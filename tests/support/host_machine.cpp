@@ -1,0 +1,64 @@
+// TEST AID ONLY: compiles the device-side machines (json_machine.cuh / stream_machine.cuh) for
+// the host so the CPU test-suite can fuzz them against CPython and the oracle without a GPU.
+// Never linked into the product library; the product has no CPU path.
+#include <stddef.h>
+#include <string.h>
+#include <vector>
+#include "../../include/llmgw_b200.h"
+#include "../../llmapigateway_b200/csrc/stream_machine.cuh"
+
+using namespace lgw;
+
+static_assert(sizeof(Val) == sizeof(lgw_val), "Val");
+static_assert(sizeof(UsageRec) == sizeof(lgw_usage_rec), "UsageRec");
+static_assert(sizeof(StreamState) == sizeof(lgw_stream_state), "StreamState");
+static_assert(sizeof(RowEvent) == sizeof(lgw_row_event), "RowEvent");
+static_assert(sizeof(SegResult) == sizeof(lgw_seg_result), "SegResult");
+
+extern "C" {
+
+// parse one event text exactly as the stream machine would (cls: 1 = "data: {" part, 2 = "{" part;
+// `text` is the whole part).  Returns TopKey|PartFlag bits, fills the normalised record.
+uint32_t lgwt_parse_part(const uint8_t* text, uint32_t n, lgw_usage_rec* rec_out, int* cls_out) {
+    Rope r{nullptr, 0, text, n};
+    const uint8_t cls = classify_part(r, 0, n);
+    *cls_out = cls;
+    if (cls == PC_NONE) return 0;
+    UsageRaw raw;
+    const uint32_t f = parse_part<true>(r, 0, n, cls, &raw);
+    const uint32_t f2 = parse_part<false>(r, 0, n, cls, nullptr);
+    if (f != f2) return 0xFFFFFFFFu;       // the flags-only machine must agree with the extracting one
+    UsageRec rec;
+    normalise_usage(raw, f, rec);
+    memcpy(rec_out, &rec, sizeof(rec));
+    return f;
+}
+
+int lgwt_utf8_valid(const uint8_t* p, uint32_t n) { return utf8_valid(p, n) ? 1 : 0; }
+
+int lgwt_dec_to_double(uint64_t man, int exp10, uint64_t* bits) { return dec_to_double(man, exp10, *bits) ? 1 : 0; }
+
+// run one stream through `n_steps` steps; step k covers chunks [step_chunk[k], step_chunk[k+1])
+int lgwt_run_stream(const uint8_t* data, const uint32_t* chunk_off, const uint32_t* step_chunk, uint32_t n_steps,
+                    int http_status, uint32_t carry_cap, uint32_t detail_cap,
+                    lgw_seg_result* seg_out, lgw_stream_state* final_state,
+                    uint8_t* detail_out, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
+    StreamState st;
+    init_stream(st, http_status);
+    std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1);
+    std::vector<RowEvent> rq(rows_cap + 1);
+    uint32_t rcount = 0;
+    StepIO io{&st, ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
+    for (uint32_t k = 0; k < n_steps; ++k) {
+        SegResult res;
+        run_segment(io, data, chunk_off, step_chunk[k], step_chunk[k + 1], res);
+        memcpy(&seg_out[k], &res, sizeof(res));
+    }
+    memcpy(final_state, &st, sizeof(st));
+    memcpy(detail_out, det.data(), st.detail_len);
+    *n_rows = rcount < rows_cap ? rcount : rows_cap;
+    memcpy(rows_out, rq.data(), sizeof(RowEvent) * (*n_rows));
+    return 0;
+}
+
+}  // extern "C"
