@@ -1,0 +1,292 @@
+"""bench.py -- BASELINE.json metric: SSE chunks/sec & JSON GB/s at 4096 streams x 512 deltas (64 B).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch (4096 streams x 512 delta
+events of 64 B + a usage event + [DONE] per stream, one event per network chunk).  Under torchrun
+every rank runs its own 4096-stream batch on its own GPU (streams shard with no cross-GPU
+dependency: weak scaling, no collective on the data path).
+
+value   : chunks/s with inputs resident in HBM (kernels only, CUDA events on the launching stream)
+e2e     : the same through the host-buffer C-ABI call (pinned host -> device -> host inside the
+          timed region) plus the read-back of the usage records
+roofline: algorithmic bytes (128 B per 64-B event) / summed kernel time, vs MEASURED_PEAKS.json
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_STREAMS, N_EVENTS, EVENT_BYTES = 4096, 512, 64
+ALGO_BYTES_PER_EVENT = 128          # 64 read + 64 re-emitted
+METRIC, UNIT = "sse_chunks_per_sec", "chunks/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU reference arm ------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_streams, n_events = args
+    from llmapigateway_b200.synth import sse_batch
+    from oracle.sse_oracle import run_stream
+    b = sse_batch(n_streams=n_streams, n_events=n_events, seed=seed)
+    streams = [b.stream_chunks(s) for s in range(n_streams)]
+    t0 = time.perf_counter()
+    for chunks in streams:
+        relay, tap = run_stream(chunks)
+        assert not relay.failed and len(tap.rows) == 1
+    return time.perf_counter() - t0
+
+
+def cpu_reference(n_streams_per_proc: int, n_events: int, procs: int, seed: int = 3):
+    """Oracle port of the reference path (relay loop A + tap loop B, stdlib json standing in for
+    json5 = the GENEROUS variant B2 of BASELINE.md) on `procs` processes."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(seed + i, n_streams_per_proc, n_events) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    events = procs * n_streams_per_proc * n_events
+    return events / max(times), max(times), wall
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.stop_ev = gpu_index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_ev.wait(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    per_proc = 48
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, tmax, _ = cpu_reference(per_proc, N_EVENTS, procs, seed=3 + 100 * i)
+        if i >= args.warmup:
+            vals.append((v, tmax))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([t for _, t in vals])) * 1e3
+    sample = f"{procs} procs x {per_proc} streams x {N_EVENTS} events of {EVENT_BYTES} B per step (oracle port, stdlib json for json5, relay+tap loops)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C3: SSE delta parse/normalise/re-emit, 64 B events, 1 event per chunk (bounded sample of 4096x512)",
+                       "streams": procs * per_proc, "events_per_stream": N_EVENTS},
+            "json_gbs": value * EVENT_BYTES / 1e9,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--streams", type=int, default=N_STREAMS)
+    ap.add_argument("--events", type=int, default=N_EVENTS)
+    ap.add_argument("--mode", type=int, default=0, help="0 bulk kernel (default), 1 exact sequential path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import llmapigateway_b200 as L
+    from llmapigateway_b200 import _abi
+    from llmapigateway_b200.engine import SEG_DTYPE
+    from llmapigateway_b200.synth import sse_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    S, E = args.streams, args.events
+    W, K = max(args.warmup, 3), args.steps
+
+    eng = L.Engine(device=local, max_streams=S, max_step_chunks=S * (E + 2) + 8, max_step_bytes=S * (E * EVENT_BYTES + 512))
+    eng.set_mode(args.mode)
+    # two alternating input sets: every step touches 2 x 128 MiB of HBM that the previous step evicted from L2
+    sets = []
+    for k in range(2):
+        b = sse_batch(n_streams=S, n_events=E, seed=3 + 1000 * k + rank)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        h = {"data": pin(b.data), "chunk_off": pin(b.chunk_off), "seg_chunk": pin(b.seg_chunk), "seg_slot": pin(b.seg_slot)}
+        d = {n: t.to(dev) for n, t in h.items()}
+        d["out"] = torch.empty_like(d["data"])
+        d["segs"] = torch.empty(S * SEG_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        h["out"] = torch.empty(b.data.size, dtype=torch.uint8).pin_memory()
+        sets.append((b, h, d))
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    status = np.full(S, 200, dtype=np.int32)
+    n_chunks = sets[0][0].n_chunks
+    n_bytes = int(sets[0][0].data.size)
+
+    def device_step(k):
+        b, h, d = sets[k % 2]
+        eng.open(b.seg_slot, status)           # stream table reset (tiny kernel)
+        eng.step_device(d["data"].data_ptr(), n_bytes, d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
+                        d["seg_slot"].data_ptr(), S, d["out"].data_ptr(), d["segs"].data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident ------------------------------------------------------------------
+    for k in range(W):
+        device_step(k); eng.sync()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = eng.launch_count()
+    kern = {"prime": 0.0, "relay": 0.0, "commit": 0.0}
+    step_ms = []
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b, h, d = sets[k % 2]
+        eng.open(b.seg_slot, status)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            eng.step_device(d["data"].data_ptr(), n_bytes, d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
+                            d["seg_slot"].data_ptr(), S, d["out"].data_ptr(), d["segs"].data_ptr())
+            e1.record(stream)
+        eng.sync()
+        step_ms.append(e0.elapsed_time(e1))
+        ms = eng.last_step_ms()
+        for n in kern:
+            kern[n] += ms[n]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.launch_count() - l0
+    sampler.stop_ev.set(); sampler.join(timeout=2)
+    dev_ms = float(np.sum(step_ms))
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
+    ms_per_step = dev_ms / K
+    events_total = world * S * E
+    value = events_total / (ms_per_step / 1e3)
+
+    # correctness spot check of the timed configuration (not timed)
+    b, h, d = sets[(K - 1) % 2]
+    torch.cuda.synchronize(dev)
+    assert torch.equal(d["out"], d["data"]), "re-emitted bytes differ from the input of committed streams"
+    st = eng.state(b.seg_slot[:4])
+    for s in range(4):
+        assert _abi.usage_rec_to_dict(st[s].rec) == b.truths[s].expected_row()
+
+    # ---- e2e: host buffers through the C-ABI call ---------------------------------------------------
+    e2e_ms = []
+    for k in range(2 + min(K, 5)):
+        b, h, d = sets[k % 2]
+        barrier()
+        t0 = time.perf_counter()
+        eng.open(b.seg_slot, status)
+        res = eng.step(h["data"].numpy(), h["chunk_off"].numpy(), h["seg_chunk"].numpy(), h["seg_slot"].numpy(), out=h["out"].numpy())
+        states = eng.close(b.seg_slot)
+        barrier()
+        if k >= 2:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_step = float(np.mean(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_step], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_step = float(t.item())
+    e2e_value = events_total / (e2e_step / 1e3)
+    h2d = n_bytes + 4 * (n_chunks + 1) + 4 * (S + 1) + 4 * S + 8 * S
+    d2h = n_bytes + S * SEG_DTYPE.itemsize + S * 440
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    kern_step = {n: v / K for n, v in kern.items()}
+    kernel_ms = sum(kern_step.values())
+    algo = S * E * ALGO_BYTES_PER_EVENT
+    achieved = algo / (kernel_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C3: 4096 concurrent SSE streams x 512 data: deltas (64 B each), parse/normalise/re-emit",
+                   "streams_per_gpu": S, "events_per_stream": E, "event_bytes": EVENT_BYTES, "events_per_chunk": 1,
+                   "extra_chunks_per_stream": "1 usage event + data: [DONE] (not counted)", "parallelism": f"streams sharded x{world}, no collective",
+                   "l2": "two alternating input/output sets; each step touches 268 MB of HBM evicted by the previous step (L2 = 126 MB)",
+                   "mode": "bulk" if args.mode == 0 else "sequential"},
+        "json_gbs": value * EVENT_BYTES / 1e9,
+        "kernel_ms": kern_step,
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "json_gbs": e2e_value * EVENT_BYTES / 1e9},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_prime + k_relay + k_commit (summed; 128 B algorithmic per 64-B event)"},
+        "wall_s_timed_loop": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        procs = os.cpu_count() or 1
+        v, tmax, _ = cpu_reference(64, E, procs)
+        v1, t1, _ = cpu_reference(96, E, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                                "sample": f"{procs} procs x 64 streams x {E} events (oracle port of request_handler.py relay + chat_logging.py tap; stdlib json stands in for json5 = generous)",
+                                "single_core_value": v1}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+"""Loads the C-ABI shared library (include/llmgw_b200.h).  There is deliberately no fallback:
+if the CUDA library is missing or no device is usable, importing/creating raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _abi
+
+LIB_PATH = Path(__file__).resolve().parent / "_native" / "libllmgw_b200.so"
+
+EXPORTS = [
+    "lgw_abi_version", "lgw_engine_create", "lgw_engine_destroy", "lgw_last_error", "lgw_engine_set_stream",
+    "lgw_streams_open", "lgw_streams_state", "lgw_stream_detail", "lgw_streams_close",
+    "lgw_sse_step", "lgw_sse_step_device", "lgw_fetch_rows", "lgw_sync", "lgw_last_step_ms",
+    "lgw_launch_count", "lgw_alloc_pinned", "lgw_free_pinned",
+]
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This package has no CPU implementation.")
+    lib = C.CDLL(str(LIB_PATH))
+    missing = [n for n in EXPORTS if not hasattr(lib, n)]
+    if missing:
+        raise NativeLibraryMissing(f"{LIB_PATH} lacks symbols {missing}")
+    lib.lgw_last_error.restype = C.c_char_p
+    lib.lgw_last_error.argtypes = [C.c_void_p]
+    lib.lgw_engine_create.argtypes = [C.c_int, C.POINTER(_abi.Limits), C.POINTER(C.c_void_p)]
+    lib.lgw_engine_destroy.argtypes = [C.c_void_p]
+    lib.lgw_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lgw_streams_open.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.lgw_streams_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.lgw_streams_close.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.lgw_stream_detail.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    step_args = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.lgw_sse_step.argtypes = step_args + [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.lgw_sse_step_device.argtypes = step_args
+    lib.lgw_fetch_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.lgw_sync.argtypes = [C.c_void_p]
+    lib.lgw_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
+    lib.lgw_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.lgw_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lgw_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
+    if hasattr(lib, "lgw_engine_set_mode"):
+        lib.lgw_engine_set_mode.argtypes = [C.c_void_p, C.c_int]
+    if lib.lgw_abi_version() != 1:
+        raise NativeLibraryMissing("ABI version mismatch")
+    _lib = lib
+    return lib

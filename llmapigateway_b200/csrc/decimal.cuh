@@ -22,15 +22,17 @@ namespace lgw {
 
 struct U128 { uint64_t lo, hi; };
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 __device__ __constant__ U128 g_pow10_dev[] = {
 #include "pow10_table.inc"
 };
-#define LGW_POW10(i) g_pow10_dev[i]
-#else
+#endif
 static const U128 g_pow10_host[] = {
 #include "pow10_table.inc"
 };
+#if defined(__CUDA_ARCH__)
+#define LGW_POW10(i) g_pow10_dev[i]
+#else
 #define LGW_POW10(i) g_pow10_host[i]
 #endif
 #define LGW_POW10_QMIN (-348)

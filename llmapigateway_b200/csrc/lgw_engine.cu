@@ -1,0 +1,273 @@
+// llmgw_b200 engine: C ABI (include/llmgw_b200.h) over the sm_100a kernels.
+// No CPU fallback anywhere in this file: every entry point either runs on the device or fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/llmgw_b200.h"
+#include "stream_machine.cuh"
+#include "sse_kernels.cuh"
+
+using namespace lgw;
+
+static_assert(sizeof(Val) == sizeof(lgw_val), "lgw_val layout");
+static_assert(sizeof(UsageRec) == sizeof(lgw_usage_rec), "lgw_usage_rec layout");
+static_assert(sizeof(StreamState) == sizeof(lgw_stream_state), "lgw_stream_state layout");
+static_assert(sizeof(RowEvent) == sizeof(lgw_row_event), "lgw_row_event layout");
+static_assert(sizeof(SegResult) == sizeof(lgw_seg_result), "lgw_seg_result layout");
+
+static thread_local std::string g_create_error;
+
+struct lgw_engine {
+    int device = 0;
+    lgw_limits lim{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    DeviceTables t{};               // persistent per-slot state
+    uint32_t* d_rowq_count = nullptr;
+    RowEvent* d_rowq = nullptr;
+    StepScratch scratch{};          // per-step scratch (sized by max_step_chunks / max_streams)
+    // staging for the host-pointer entry points
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint32_t *d_chunk_off = nullptr, *d_seg_chunk = nullptr, *d_seg_slot = nullptr;
+    SegResult* d_seg_out = nullptr;
+    uint32_t* d_slots = nullptr; int32_t* d_status = nullptr; StreamState* d_state_stage = nullptr;
+    cudaEvent_t ev[6]{};
+    float ms[4]{0, 0, 0, 0};
+    bool timed = false;
+    uint64_t launches = 0;
+    int mode = 0;                   // 0: fast path + general fix-up, 1: general path only
+    int sm_count = 148;
+    std::string err;
+};
+
+#define CK(e, call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { \
+    (e)->err = std::string(#call) + ": " + cudaGetErrorString(_r); return LGW_ERR_CUDA; } } while (0)
+
+extern "C" int lgw_abi_version(void) { return LGW_ABI_VERSION; }
+
+extern "C" const char* lgw_last_error(const lgw_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engine** out) {
+    if (!out || !limits) { g_create_error = "null argument"; return LGW_ERR_ARG; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        g_create_error = "no usable CUDA device (this engine has no CPU path)";
+        return LGW_ERR_NO_DEVICE;
+    }
+    lgw_engine* e = new lgw_engine();
+    e->device = device; e->lim = *limits;
+    if (e->lim.max_streams == 0 || e->lim.carry_cap < 64 || e->lim.detail_cap < 64 || e->lim.max_step_chunks == 0 || e->lim.max_step_bytes == 0) {
+        g_create_error = "limits out of range"; delete e; return LGW_ERR_ARG;
+    }
+    auto fail = [&](const char* what, cudaError_t r) { g_create_error = std::string(what) + ": " + cudaGetErrorString(r); lgw_engine_destroy(e); return LGW_ERR_CUDA; };
+    cudaError_t r;
+    if ((r = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", r);
+    cudaDeviceProp prop;
+    if ((r = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", r);
+    e->sm_count = prop.multiProcessorCount;
+    if ((r = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", r);
+    e->stream = e->own_stream;
+    for (auto& ev : e->ev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
+    const size_t S = e->lim.max_streams, C = e->lim.max_step_chunks, B = e->lim.max_step_bytes;
+#define ALLOC(ptr, bytes) if ((r = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return fail("cudaMalloc " #ptr, r)
+    ALLOC(e->t.state, S * sizeof(StreamState));
+    ALLOC(e->t.carry_a, S * (size_t)e->lim.carry_cap);
+    ALLOC(e->t.carry_b, S * (size_t)e->lim.carry_cap);
+    ALLOC(e->t.detail, S * (size_t)e->lim.detail_cap);
+    e->t.carry_cap = e->lim.carry_cap; e->t.detail_cap = e->lim.detail_cap; e->t.max_streams = e->lim.max_streams;
+    ALLOC(e->d_rowq, (size_t)(e->lim.rowq_cap + 1) * sizeof(RowEvent));
+    ALLOC(e->d_rowq_count, 16);
+    ALLOC(e->d_in, B + 64); ALLOC(e->d_out, B + 64);
+    ALLOC(e->d_chunk_off, (C + 1) * 4); ALLOC(e->d_seg_chunk, (S + 1) * 4); ALLOC(e->d_seg_slot, S * 4);
+    ALLOC(e->d_seg_out, S * sizeof(SegResult));
+    ALLOC(e->d_slots, S * 4); ALLOC(e->d_status, S * 4); ALLOC(e->d_state_stage, S * sizeof(StreamState));
+    if ((r = scratch_alloc(e->scratch, S, C, B)) != cudaSuccess) return fail("scratch_alloc", r);
+#undef ALLOC
+    if ((r = cudaMemset(e->t.state, 0, S * sizeof(StreamState))) != cudaSuccess) return fail("cudaMemset", r);
+    if ((r = cudaMemset(e->d_rowq_count, 0, 16)) != cudaSuccess) return fail("cudaMemset", r);
+    const char* m = getenv("LGW_FORCE_GENERAL");
+    e->mode = (m && m[0] == '1') ? 1 : 0;
+    *out = e;
+    return LGW_OK;
+}
+
+extern "C" int lgw_engine_destroy(lgw_engine* e) {
+    if (!e) return LGW_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->t.state); cudaFree(e->t.carry_a); cudaFree(e->t.carry_b); cudaFree(e->t.detail);
+    cudaFree(e->d_rowq); cudaFree(e->d_rowq_count); cudaFree(e->d_in); cudaFree(e->d_out);
+    cudaFree(e->d_chunk_off); cudaFree(e->d_seg_chunk); cudaFree(e->d_seg_slot); cudaFree(e->d_seg_out);
+    cudaFree(e->d_slots); cudaFree(e->d_status); cudaFree(e->d_state_stage);
+    scratch_free(e->scratch);
+    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return LGW_OK;
+}
+
+extern "C" int lgw_engine_set_stream(lgw_engine* e, void* s) {
+    if (!e) return LGW_ERR_ARG;
+    e->stream = s ? (cudaStream_t)s : e->own_stream;
+    return LGW_OK;
+}
+
+extern "C" int lgw_engine_set_mode(lgw_engine* e, int mode) {     // 0 fast+fix-up, 1 general only (tests)
+    if (!e) return LGW_ERR_ARG;
+    e->mode = mode;
+    return LGW_OK;
+}
+
+extern "C" int lgw_streams_open(lgw_engine* e, const uint32_t* slots, const int32_t* http_status, uint32_t n) {
+    if (!e || !slots || !http_status) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    if (n > e->lim.max_streams) { e->err = "more slots than max_streams"; return LGW_ERR_CAPACITY; }
+    for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->lim.max_streams) { e->err = "slot out of range"; return LGW_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(e->d_slots, slots, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_status, http_status, n * 4, cudaMemcpyHostToDevice, e->stream));
+    k_streams_open<<<(n + 127) / 128, 128, 0, e->stream>>>(e->t, e->d_slots, e->d_status, n);
+    ++e->launches;
+    CK(e, cudaGetLastError());
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+static int gather_states(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* out, int free_after) {
+    if (!e || !slots || !out) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    if (n > e->lim.max_streams) { e->err = "more slots than max_streams"; return LGW_ERR_CAPACITY; }
+    for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->lim.max_streams) { e->err = "slot out of range"; return LGW_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(e->d_slots, slots, n * 4, cudaMemcpyHostToDevice, e->stream));
+    k_streams_gather<<<(n + 127) / 128, 128, 0, e->stream>>>(e->t, e->d_slots, n, e->d_state_stage, free_after);
+    ++e->launches;
+    CK(e, cudaGetLastError());
+    CK(e, cudaMemcpyAsync(out, e->d_state_stage, n * sizeof(StreamState), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_streams_state(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* out) { return gather_states(e, slots, n, out, 0); }
+extern "C" int lgw_streams_close(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* out) { return gather_states(e, slots, n, out, 1); }
+
+extern "C" int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uint32_t cap, uint32_t* len) {
+    if (!e || !buf || !len || slot >= e->lim.max_streams) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    StreamState st;
+    CK(e, cudaMemcpyAsync(&st, e->t.state + slot, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    uint32_t n = st.detail_len < cap ? st.detail_len : cap;
+    if (n) CK(e, cudaMemcpyAsync(buf, e->t.detail + (size_t)slot * e->lim.detail_cap, n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    *len = n;
+    return LGW_OK;
+}
+
+// ---- the step ------------------------------------------------------------------------------------
+static int step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint32_t* d_chunk_off, uint32_t n_chunks,
+                       const uint32_t* d_seg_chunk, const uint32_t* d_seg_slot, uint32_t n_segs,
+                       uint8_t* d_out, SegResult* d_seg_out) {
+    if (n_segs > e->lim.max_streams || n_chunks > e->lim.max_step_chunks || n_bytes > e->lim.max_step_bytes) {
+        e->err = "step exceeds the limits given to lgw_engine_create"; return LGW_ERR_CAPACITY;
+    }
+    if (n_bytes >= 0xFFFFFFF0ull) { e->err = "step larger than 4 GiB"; return LGW_ERR_CAPACITY; }
+    StepArgs a{};
+    a.t = e->t; a.data = d_bytes; a.n_bytes = (uint32_t)n_bytes; a.chunk_off = d_chunk_off; a.n_chunks = n_chunks;
+    a.seg_chunk = d_seg_chunk; a.seg_slot = d_seg_slot; a.n_segs = n_segs; a.out = d_out; a.seg_out = d_seg_out;
+    a.rowq = e->d_rowq; a.rowq_count = e->d_rowq_count; a.rowq_cap = e->lim.rowq_cap; a.s = e->scratch;
+    CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
+    int launched = 0;
+    cudaError_t r = launch_step(a, e->mode, e->sm_count, e->stream, e->ev, &launched);
+    e->launches += (uint64_t)launched;
+    if (r != cudaSuccess) { e->err = std::string("step launch: ") + cudaGetErrorString(r); return LGW_ERR_CUDA; }
+    e->timed = true;
+    return LGW_OK;
+}
+
+extern "C" int lgw_sse_step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint32_t* d_chunk_off, uint32_t n_chunks,
+                                   const uint32_t* d_seg_chunk, const uint32_t* d_seg_slot, uint32_t n_segs,
+                                   uint8_t* d_out, lgw_seg_result* d_seg_out) {
+    if (!e || (!d_bytes && n_bytes) || !d_chunk_off || !d_seg_chunk || !d_seg_slot || (!d_out && n_bytes) || !d_seg_out) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    return step_device(e, d_bytes, n_bytes, d_chunk_off, n_chunks, d_seg_chunk, d_seg_slot, n_segs, d_out, (SegResult*)d_seg_out);
+}
+
+extern "C" int lgw_fetch_rows(lgw_engine* e, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
+    if (!e || !n_rows || (!rows_out && rows_cap)) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    uint32_t cnt = 0;
+    CK(e, cudaMemcpyAsync(&cnt, e->d_rowq_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (cnt > e->lim.rowq_cap) cnt = e->lim.rowq_cap;
+    if (cnt > rows_cap) cnt = rows_cap;
+    if (cnt) CK(e, cudaMemcpyAsync(rows_out, e->d_rowq, (size_t)cnt * sizeof(RowEvent), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    *n_rows = cnt;
+    return LGW_OK;
+}
+
+extern "C" int lgw_sync(lgw_engine* e) {
+    if (!e) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_bytes, const uint32_t* chunk_off, uint32_t n_chunks,
+                            const uint32_t* seg_chunk, const uint32_t* seg_slot, uint32_t n_segs,
+                            uint8_t* out_bytes, lgw_seg_result* seg_out, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
+    if (!e || (!bytes && n_bytes) || !chunk_off || !seg_chunk || !seg_slot || (!out_bytes && n_bytes) || !seg_out || !n_rows) return LGW_ERR_ARG;
+    if (n_segs > e->lim.max_streams || n_chunks > e->lim.max_step_chunks || n_bytes > e->lim.max_step_bytes) {
+        e->err = "step exceeds the limits given to lgw_engine_create"; return LGW_ERR_CAPACITY;
+    }
+    // cheap host-side validation of the layout (offsets sorted, segments cover chunks in order)
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_bytes) { e->err = "chunk_off must start at 0 and end at n_bytes"; return LGW_ERR_ARG; }
+    if (n_segs && (seg_chunk[0] != 0 || seg_chunk[n_segs] != n_chunks)) { e->err = "seg_chunk must cover all chunks"; return LGW_ERR_ARG; }
+    for (uint32_t s = 0; s < n_segs; ++s) if (seg_chunk[s] > seg_chunk[s + 1] || seg_slot[s] >= e->lim.max_streams) { e->err = "bad segment table"; return LGW_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaEventRecord(e->ev[4], e->stream));
+    if (n_bytes) CK(e, cudaMemcpyAsync(e->d_in, bytes, n_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_chunk_off, chunk_off, (size_t)(n_chunks + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_seg_chunk, seg_chunk, (size_t)(n_segs + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    if (n_segs) CK(e, cudaMemcpyAsync(e->d_seg_slot, seg_slot, (size_t)n_segs * 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = step_device(e, e->d_in, n_bytes, e->d_chunk_off, n_chunks, e->d_seg_chunk, e->d_seg_slot, n_segs, e->d_out, e->d_seg_out);
+    if (rc != LGW_OK) return rc;
+    if (n_bytes) CK(e, cudaMemcpyAsync(out_bytes, e->d_out, n_bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (n_segs) CK(e, cudaMemcpyAsync(seg_out, e->d_seg_out, (size_t)n_segs * sizeof(SegResult), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaEventRecord(e->ev[5], e->stream));
+    rc = lgw_fetch_rows(e, rows_out, rows_cap, n_rows);
+    if (rc != LGW_OK) return rc;
+    float t = 0; if (cudaEventElapsedTime(&t, e->ev[4], e->ev[5]) == cudaSuccess) e->ms[3] = t;
+    return LGW_OK;
+}
+
+extern "C" int lgw_last_step_ms(lgw_engine* e, float ms[4]) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    if (e->timed) {
+        CK(e, cudaSetDevice(e->device));
+        CK(e, cudaEventSynchronize(e->ev[3]));
+        for (int i = 0; i < 3; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->ms[i] = t; }
+    }
+    for (int i = 0; i < 4; ++i) ms[i] = e->ms[i];
+    return LGW_OK;
+}
+
+extern "C" int lgw_launch_count(lgw_engine* e, uint64_t* out) {
+    if (!e || !out) return LGW_ERR_ARG;
+    *out = e->launches;
+    return LGW_OK;
+}
+
+extern "C" int lgw_alloc_pinned(lgw_engine* e, uint64_t bytes, void** out) {
+    if (!e || !out) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return LGW_OK;
+}
+extern "C" int lgw_free_pinned(lgw_engine* e, void* p) {
+    if (!e) return LGW_ERR_ARG;
+    CK(e, cudaFreeHost(p));
+    return LGW_OK;
+}

@@ -1,0 +1,127 @@
+// Kernels of the SSE step (sm_100a).  See DESIGN.md for the data layout and the roofline of each.
+//
+//   k_prime    one thread per segment: streams still PRIMING walk their chunks with the exact
+//              sequential machine until they commit or fail (a handful of chunks per stream);
+//              writes the per-segment plan the bulk kernel reads.
+//   k_relay    bulk kernel: every block copies one byte tile in -> out with 16-byte vector
+//              accesses (the re-emit) and parses the events of the chunks that start in it.
+//   k_commit   one thread per segment: folds the bulk kernel's findings into the persistent
+//              stream state; streams the bulk kernel flagged irregular are redone sequentially
+//              with the exact machine.
+//   k_general  (mode 1 / fix-up) the exact sequential machine over whole segments.
+#pragma once
+#include <cuda_runtime.h>
+#include "stream_machine.cuh"
+
+namespace lgw {
+
+struct DeviceTables {
+    StreamState* state;
+    uint8_t* carry_a; uint8_t* carry_b; uint8_t* detail;
+    uint32_t carry_cap, detail_cap, max_streams;
+};
+
+struct SegPlan {
+    uint32_t resume_chunk;     // first chunk not yet consumed by k_prime
+    uint32_t relay_begin;      // byte offset where the regular (bulk) relay text starts; seg end when none
+    uint32_t seg_end;          // byte offset of the end of the segment
+    uint32_t emit_chunk_begin;
+    uint32_t irregular;        // 1: the bulk kernel's findings are void, k_commit redoes [resume_chunk, end)
+    uint32_t last_usage_pos;   // 1 + byte offset of the last usage-bearing event the tap accepts (atomicMax)
+    uint32_t a_usage;          // handler bound `tokens_usage` (request_handler.py:134)
+    uint32_t n_events_a, n_events_b, n_usage_b;
+    uint32_t _pad[2];
+};
+
+struct StepScratch {
+    SegPlan* plan;             // [max_streams]
+    uint32_t* tile_chunk;      // [max tiles + 2] first chunk starting at or after each tile
+    uint32_t max_tiles;
+};
+
+struct StepArgs {
+    DeviceTables t;
+    const uint8_t* data; uint32_t n_bytes;
+    const uint32_t* chunk_off; uint32_t n_chunks;
+    const uint32_t* seg_chunk; const uint32_t* seg_slot; uint32_t n_segs;
+    uint8_t* out; SegResult* seg_out;
+    RowEvent* rowq; uint32_t* rowq_count; uint32_t rowq_cap;
+    StepScratch s;
+};
+
+#define LGW_TILE_BYTES 16384u
+
+static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size_t max_chunks, size_t max_bytes) {
+    cudaError_t r;
+    if ((r = cudaMalloc((void**)&s.plan, max_streams * sizeof(SegPlan))) != cudaSuccess) return r;
+    s.max_tiles = (uint32_t)((max_bytes + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES);
+    if ((r = cudaMalloc((void**)&s.tile_chunk, ((size_t)s.max_tiles + 2) * 4)) != cudaSuccess) return r;
+    return cudaSuccess;
+}
+static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); s.plan = nullptr; s.tile_chunk = nullptr; }
+
+__device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot) {
+    StepIO io;
+    io.st = a.t.state + slot;
+    io.carry_a = a.t.carry_a + (size_t)slot * a.t.carry_cap;
+    io.carry_b = a.t.carry_b + (size_t)slot * a.t.carry_cap;
+    io.detail = a.t.detail + (size_t)slot * a.t.detail_cap;
+    io.carry_cap = a.t.carry_cap; io.detail_cap = a.t.detail_cap;
+    io.rowq = a.rowq; io.rowq_count = a.rowq_count; io.rowq_cap = a.rowq_cap; io.slot = slot;
+    return io;
+}
+
+// ---- stream table maintenance -------------------------------------------------------------------
+__global__ void k_streams_open(DeviceTables t, const uint32_t* slots, const int32_t* status, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    init_stream(t.state[slots[i]], status[i]);
+}
+
+__global__ void k_streams_gather(DeviceTables t, const uint32_t* slots, uint32_t n, StreamState* out, int free_after) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StreamState* s = t.state + slots[i];
+    out[i] = *s;
+    if (free_after) s->phase = PH_FREE;
+}
+
+// ---- exact sequential path ------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_general(StepArgs a) {
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= a.n_segs) return;
+    const StepIO io = make_io(a, a.seg_slot[seg]);
+    SegResult res;
+    run_segment(io, a.data, a.chunk_off, a.seg_chunk[seg], a.seg_chunk[seg + 1], res);
+    a.seg_out[seg] = res;
+}
+
+// ---- plain re-emit (used with k_general): out[i] = in[i], 16 bytes per thread per trip ---------------
+__global__ void __launch_bounds__(256) k_copy(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t n) {
+    const uint32_t nvec = n >> 4;
+    const uint4* __restrict__ vi = reinterpret_cast<const uint4*>(in);
+    uint4* __restrict__ vo = reinterpret_cast<uint4*>(out);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) vo[i] = __ldg(vi + i);
+    const uint32_t tail = nvec << 4;
+    if (blockIdx.x == 0 && threadIdx.x < (n - tail)) out[tail + threadIdx.x] = in[tail + threadIdx.x];
+}
+
+#include "relay_kernels.cuh"
+
+// Launch one step on `stream`.  ev[0..3] bracket prime / relay / commit.
+static inline cudaError_t launch_step(const StepArgs& a, int mode, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
+    *launched = 0;
+    cudaError_t r;
+    if ((r = cudaEventRecord(ev[0], stream)) != cudaSuccess) return r;
+    if (mode == 1) {
+        if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
+        if (a.n_bytes) { k_copy<<<sm_count * 8, 256, 0, stream>>>(a.data, a.out, a.n_bytes); ++*launched; }
+        if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
+        if (a.n_segs) { k_general<<<(a.n_segs + 63) / 64, 64, 0, stream>>>(a); ++*launched; }
+        if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
+        return cudaGetLastError();
+    }
+    return launch_step_fast(a, sm_count, stream, ev, launched);
+}
+
+}  // namespace lgw

@@ -1,0 +1,146 @@
+"""Python face of the engine: thin ctypes calls into the C ABI, numpy in / numpy out.
+
+Mirrors the seams of the reference:
+  Engine.step      <- the per-chunk bodies of request_handler.py:34-63, :69-98, :109-142 and
+                      chat_logging.py:90-147 for every stream at once
+  Engine.close     <- end of stream: the final tokens_usage row of chat_logging.py:150
+  Engine.detail    <- error_detail of a failed attempt (request_handler.py:51,87,98)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi, _native
+
+SEG_DTYPE = np.dtype([("emit_chunk_begin", "<u4"), ("phase", "u1"), ("verdict", "u1"), ("flags", "<u2"), ("detail_len", "<u4")])
+assert SEG_DTYPE.itemsize == C.sizeof(_abi.SegResult)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+@dataclass
+class StepResult:
+    out: np.ndarray            # uint8, same size as the input bytes (re-emitted stream)
+    segs: np.ndarray           # SEG_DTYPE per segment
+    rows: list                 # list[_abi.RowEvent] mid-stream row events
+
+    def keep_mask(self, seg_chunk: np.ndarray, n_chunks: int) -> np.ndarray:
+        """Per-chunk keep flags derived from the per-segment suffix rule."""
+        keep = np.zeros(n_chunks, dtype=bool)
+        for s in range(len(self.segs)):
+            keep[int(self.segs["emit_chunk_begin"][s]):int(seg_chunk[s + 1])] = True
+        return keep
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_streams: int = 8192, carry_cap: int = 4096, detail_cap: int = 4096,
+                 rowq_cap: int = 4096, max_step_chunks: int = 1 << 22, max_step_bytes: int = 1 << 28):
+        self._lib = _native.load()
+        self.limits = _abi.Limits(max_streams, carry_cap, detail_cap, rowq_cap, max_step_chunks, max_step_bytes)
+        h = C.c_void_p()
+        rc = self._lib.lgw_engine_create(device, C.byref(self.limits), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"lgw_engine_create failed ({rc}): {self._lib.lgw_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self._lib.lgw_last_error(self._h).decode()}")
+
+    def close_engine(self):
+        if getattr(self, "_h", None):
+            self._lib.lgw_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close_engine()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._ck(self._lib.lgw_engine_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "set_stream")
+
+    def set_mode(self, mode: int):
+        """0: bulk kernel + fix-up (default); 1: exact sequential path only (tests)."""
+        self._ck(self._lib.lgw_engine_set_mode(self._h, mode), "set_mode")
+
+    # -- streams ----------------------------------------------------------------------------------
+    def open(self, slots, http_status=None):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        st = np.full(len(slots), 200, dtype=np.int32) if http_status is None else np.ascontiguousarray(http_status, dtype=np.int32)
+        self._ck(self._lib.lgw_streams_open(self._h, _ptr(slots), _ptr(st), len(slots)), "streams_open")
+
+    def _states(self, fn, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        out = (_abi.StreamState * max(1, len(slots)))()
+        self._ck(fn(self._h, _ptr(slots), len(slots), out), "streams_state")
+        return [out[i] for i in range(len(slots))]
+
+    def state(self, slots):
+        return self._states(self._lib.lgw_streams_state, slots)
+
+    def close(self, slots):
+        return self._states(self._lib.lgw_streams_close, slots)
+
+    def detail(self, slot: int) -> bytes:
+        buf = C.create_string_buffer(self.limits.detail_cap)
+        n = C.c_uint32(0)
+        self._ck(self._lib.lgw_stream_detail(self._h, slot, buf, self.limits.detail_cap, C.byref(n)), "stream_detail")
+        return buf.raw[:n.value]
+
+    # -- the hot path --------------------------------------------------------------------------------
+    def step(self, data: np.ndarray, chunk_off: np.ndarray, seg_chunk: np.ndarray, seg_slot: np.ndarray,
+             out: np.ndarray | None = None) -> StepResult:
+        """Host-buffer step: H2D, kernels, D2H inside the call."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        chunk_off = np.ascontiguousarray(chunk_off, dtype=np.uint32)
+        seg_chunk = np.ascontiguousarray(seg_chunk, dtype=np.uint32)
+        seg_slot = np.ascontiguousarray(seg_slot, dtype=np.uint32)
+        n_bytes, n_chunks, n_segs = data.size, chunk_off.size - 1, seg_slot.size
+        if out is None:
+            out = np.empty(max(n_bytes, 1), dtype=np.uint8)
+        segs = np.zeros(max(n_segs, 1), dtype=SEG_DTYPE)
+        cap = self.limits.rowq_cap
+        rows = (_abi.RowEvent * max(cap, 1))()
+        n_rows = C.c_uint32(0)
+        self._ck(self._lib.lgw_sse_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot),
+                                        n_segs, _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows)), "sse_step")
+        return StepResult(out[:n_bytes], segs[:n_segs], [rows[i] for i in range(n_rows.value)])
+
+    def step_device(self, d_data: int, n_bytes: int, d_chunk_off: int, n_chunks: int, d_seg_chunk: int, d_seg_slot: int,
+                    n_segs: int, d_out: int, d_segs: int):
+        """Device-pointer step (asynchronous on the engine stream)."""
+        self._ck(self._lib.lgw_sse_step_device(self._h, d_data, n_bytes, d_chunk_off, n_chunks, d_seg_chunk, d_seg_slot,
+                                               n_segs, d_out, d_segs), "sse_step_device")
+
+    def fetch_rows(self):
+        cap = self.limits.rowq_cap
+        rows = (_abi.RowEvent * max(cap, 1))()
+        n_rows = C.c_uint32(0)
+        self._ck(self._lib.lgw_fetch_rows(self._h, rows, cap, C.byref(n_rows)), "fetch_rows")
+        return [rows[i] for i in range(n_rows.value)]
+
+    def sync(self):
+        self._ck(self._lib.lgw_sync(self._h), "sync")
+
+    def last_step_ms(self):
+        ms = (C.c_float * 4)()
+        self._ck(self._lib.lgw_last_step_ms(self._h, C.byref(ms)), "last_step_ms")
+        return dict(prime=ms[0], relay=ms[1], commit=ms[2], host_step=ms[3])
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self._lib.lgw_launch_count(self._h, C.byref(n)), "launch_count")
+        return n.value

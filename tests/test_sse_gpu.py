@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path through the C ABI against the golden fixtures (outputs of the
+unmodified reference) and against the oracle on seeded synthetic streams.  Byte-exact."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+from golden_io import canon_rows, load_sse_cases
+from llmapigateway_b200 import _abi
+from llmapigateway_b200.synth import pack_streams, sse_batch
+from stream_compare import check_stream
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_sse_cases()
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import llmapigateway_b200 as L
+    e = L.Engine(max_streams=8192, max_step_chunks=1 << 20, max_step_bytes=64 << 20)
+    yield e
+    e.close_engine()
+
+
+def _expect(case):
+    return dict(failed=case["failed"], error_detail=case["error_detail"], emitted=case["emitted"],
+                end_raises=case["end_raises"], rows=case["rows"], http_status=case["http_status"])
+
+
+class _SegView:
+    def __init__(self, row):
+        self.emit_chunk_begin = int(row["emit_chunk_begin"])
+
+
+def _run_cases(engine, cases, schedule, mode):
+    """schedule(case) -> list of step boundaries (chunk indices where a step starts)."""
+    engine.set_mode(mode)
+    n = len(cases)
+    slots = np.arange(n, dtype=np.uint32)
+    engine.open(slots, [c["http_status"] for c in cases])
+    bounds = [list(schedule(c)) + [len(c["chunks"])] for c in cases]
+    n_steps = max(len(b) - 1 for b in bounds)
+    seg_views = [[] for _ in cases]       # per case: list of (local step_chunk, seg)
+    step_chunks = [[0] for _ in cases]
+    rows = []
+    emitted_bytes = [[] for _ in cases]
+    for k in range(n_steps):
+        streams, who = [], []
+        for i, c in enumerate(cases):
+            b = bounds[i]
+            if k < len(b) - 1:
+                streams.append(c["chunks"][b[k]:b[k + 1]]); who.append(i)
+        pb = pack_streams(streams, slots=who)
+        res = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot)
+        rows += res.rows
+        for s, i in enumerate(who):
+            c0, c1 = int(pb.seg_chunk[s]), int(pb.seg_chunk[s + 1])
+            eb = int(res.segs["emit_chunk_begin"][s])
+            assert c0 <= eb <= c1
+            # byte-exact re-emit of the kept chunks
+            for ch in range(eb, c1):
+                o0, o1 = int(pb.chunk_off[ch]), int(pb.chunk_off[ch + 1])
+                if o1 > o0:
+                    emitted_bytes[i].append(res.out[o0:o1].tobytes())
+    states = engine.close(slots)
+    details = {}
+    for i, st in enumerate(states):
+        pass
+    return states, rows, emitted_bytes
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["general", "fast"])
+@pytest.mark.parametrize("stepping", ["one_step", "step_per_chunk", "random_steps"])
+def test_golden_cases_batched(engine, mode, stepping):
+    def schedule(c):
+        n = len(c["chunks"])
+        if stepping == "one_step" or n <= 1:
+            return [0]
+        if stepping == "step_per_chunk":
+            return list(range(n))
+        rng = random.Random(len(c["name"]) * 7919 + n)
+        return [0] + sorted(set(rng.randrange(1, n) for _ in range(rng.randrange(0, 4))))
+
+    engine.set_mode(mode)
+    n = len(CASES)
+    slots = np.arange(n, dtype=np.uint32)
+    engine.open(slots, [c["http_status"] for c in CASES])
+    bounds = [list(schedule(c)) + [len(c["chunks"])] for c in CASES]
+    n_steps = max(len(b) - 1 for b in bounds)
+    rows, emitted = [], [[] for _ in CASES]
+    details = {}
+    for k in range(n_steps):
+        streams, who = [], []
+        for i, c in enumerate(CASES):
+            b = bounds[i]
+            if k < len(b) - 1:
+                streams.append(c["chunks"][b[k]:b[k + 1]]); who.append(i)
+        pb = pack_streams(streams, slots=who)
+        res = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot)
+        rows += res.rows
+        for s, i in enumerate(who):
+            c0, c1 = int(pb.seg_chunk[s]), int(pb.seg_chunk[s + 1])
+            eb = int(res.segs["emit_chunk_begin"][s])
+            assert c0 <= eb <= c1
+            for ch in range(eb, c1):
+                o0, o1 = int(pb.chunk_off[ch]), int(pb.chunk_off[ch + 1])
+                if o1 > o0:
+                    emitted[i].append(res.out[o0:o1].tobytes())
+            if res.segs["verdict"][s] in (_abi.VERDICT_FAIL_EVENT, _abi.VERDICT_FAIL_PARSE) and i not in details:
+                details[i] = engine.detail(i)
+    states = engine.close(slots)
+    n_exotic = 0
+    for i, (c, st) in enumerate(zip(CASES, states)):
+        label = f"{c['name']} mode={mode} {stepping}"
+        failed = st.phase == _abi.PHASE_FAILED
+        assert failed == c["failed"], label
+        assert emitted[i] == c["emitted"], label
+        if failed:
+            if c["http_status"] >= 400:
+                assert st.verdict == _abi.VERDICT_FAIL_HTTP, label
+            elif c["error_detail"].startswith("Unexpected error during request to"):
+                assert st.verdict == _abi.VERDICT_FAIL_PARSE, label
+            else:
+                assert st.verdict == _abi.VERDICT_FAIL_EVENT and details[i].decode() == c["error_detail"], label
+            continue
+        assert (not (st.flags & _abi.SF_A_USAGE_BOUND)) == c["end_raises"], label
+        if st.n_exotic:
+            n_exotic += 1
+            continue
+        got = [_abi.usage_rec_to_dict(ev.rec) for ev in sorted((r for r in rows if r.slot == i), key=lambda r: r.seq)]
+        if st.flags & _abi.SF_EMITTED_ANY:
+            got.append(_abi.usage_rec_to_dict(st.rec))
+        assert canon_rows(got) == c["rows"], label
+    assert n_exotic <= 6
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["general", "fast"])
+@pytest.mark.parametrize("events_per_chunk", [1, 8])
+def test_c3_small_vs_oracle(engine, mode, events_per_chunk):
+    """SURVEY 8(d) C3 shape at a size the oracle finishes in seconds: bytes, verdicts, usage rows."""
+    from oracle.sse_oracle import run_stream
+    engine.set_mode(mode)
+    b = sse_batch(n_streams=96, n_events=64, seed=3, events_per_chunk=events_per_chunk)
+    engine.open(b.seg_slot)
+    res = engine.step(b.data, b.chunk_off, b.seg_chunk, b.seg_slot)
+    states = engine.close(b.seg_slot)
+    assert np.array_equal(res.out, b.data)                       # every chunk relayed verbatim
+    assert (res.segs["emit_chunk_begin"] == b.seg_chunk[:-1]).all()
+    for s in range(96):
+        relay, tap = run_stream(b.stream_chunks(s))
+        assert not relay.failed and not relay.end_raises
+        st = states[s]
+        assert st.phase == _abi.PHASE_COMMITTED and (st.flags & _abi.SF_A_USAGE_BOUND)
+        assert canon_rows([_abi.usage_rec_to_dict(st.rec)]) == canon_rows(tap.rows)
+        assert tap.rows[0] == b.truths[s].expected_row()
+        assert st.n_chunks_emitted == len(relay.emitted) and st.bytes_emitted == sum(map(len, relay.emitted))
+
+
+def test_c3_two_steps_with_mid_event_cut(engine):
+    """A step boundary in the middle of an event: the carry must survive between launches."""
+    from oracle.sse_oracle import run_stream
+    engine.set_mode(0)
+    b = sse_batch(n_streams=8, n_events=32, seed=5, events_per_chunk=1)
+    streams = []
+    for s in range(8):
+        blob = b"".join(b.stream_chunks(s))
+        cuts = list(range(37 + s, len(blob), 97 + s))
+        streams.append([blob[i:j] for i, j in zip([0] + cuts, cuts + [len(blob)])])
+    half = [len(x) // 2 for x in streams]
+    engine.open(np.arange(8))
+    outs = [[] for _ in range(8)]
+    for part in (0, 1):
+        pb = pack_streams([x[:h] if part == 0 else x[h:] for x, h in zip(streams, half)])
+        res = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot)
+        for s in range(8):
+            for ch in range(int(res.segs["emit_chunk_begin"][s]), int(pb.seg_chunk[s + 1])):
+                outs[s].append(res.out[int(pb.chunk_off[ch]):int(pb.chunk_off[ch + 1])].tobytes())
+    states = engine.close(np.arange(8))
+    for s in range(8):
+        relay, tap = run_stream(streams[s])
+        assert outs[s] == relay.emitted
+        assert canon_rows([_abi.usage_rec_to_dict(states[s].rec)]) == canon_rows(tap.rows)
+
+
+@pytest.mark.parametrize("mode", [0], ids=["fast"])
+def test_c3_full_size_properties(engine, mode):
+    """BASELINE.json config 3 at full size (4096 x 512 x 64 B): size-independent properties."""
+    import llmapigateway_b200 as L
+    e = L.Engine(max_streams=4096, max_step_chunks=(4096 * 514) + 8, max_step_bytes=160 << 20)
+    try:
+        e.set_mode(mode)
+        b = sse_batch(n_streams=4096, n_events=512, seed=3)
+        e.open(b.seg_slot)
+        res = e.step(b.data, b.chunk_off, b.seg_chunk, b.seg_slot)
+        states = e.close(b.seg_slot)
+        assert np.array_equal(res.out, b.data)                    # relay is the identity on committed streams
+        assert (res.segs["emit_chunk_begin"] == b.seg_chunk[:-1]).all()
+        assert (res.segs["phase"] == _abi.PHASE_COMMITTED).all()
+        for s in range(0, 4096, 97):
+            assert _abi.usage_rec_to_dict(states[s].rec) == b.truths[s].expected_row()
+        assert sum(st.n_events_b for st in states) == 4096 * 513   # 512 deltas + usage event; [DONE] is not JSON
+        assert sum(st.n_chunks_emitted for st in states) == b.n_chunks
+        assert all(st.flags & _abi.SF_A_USAGE_BOUND for st in states)
+    finally:
+        e.close_engine()
