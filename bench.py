@@ -71,29 +71,45 @@ def cpu_reference(n_streams_per_proc: int, n_events: int, procs: int, seed: int 
 
 
 class ClockSampler(threading.Thread):
+    """nvidia-smi polled every 20 ms by ONE child process for the whole measured part of the run."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
-        self.idx, self.samples, self.reasons, self.stop_ev = gpu_index, [], set(), threading.Event()
-        self.max_mhz = None
+        self.idx, self.samples, self.loaded, self.reasons = gpu_index, [], [], set()
+        self.max_mhz, self.proc = None, None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_ev.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    mhz = float(f[0]); self.max_mhz = float(f[1])
+                except Exception:
+                    continue
+                self.samples.append(mhz)
+                if len(f) > 6 and f[6].isdigit() and int(f[6]) > 0:
+                    self.loaded.append(mhz)
+                for n, v in zip(self.NAMES, f[2:6]):
+                    if v.lower().startswith("active"):
                         self.reasons.add(n)
-            except Exception:
-                pass
-            self.stop_ev.wait(0.05)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        s = sorted(self.loaded or self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "samples_under_load": len(self.loaded)}
 
 
 def run_reference_arm(args):
@@ -171,12 +187,11 @@ def main():
     eng.set_stream(stream.cuda_stream)
     status = np.full(S, 200, dtype=np.int32)
     n_chunks = sets[0][0].n_chunks
-    n_bytes = int(sets[0][0].data.size)
 
     def device_step(k):
         b, h, d = sets[k % 2]
         eng.open(b.seg_slot, status)           # stream table reset (tiny kernel)
-        eng.step_device(d["data"].data_ptr(), n_bytes, d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
+        eng.step_device(d["data"].data_ptr(), int(b.data.size), d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
                         d["seg_slot"].data_ptr(), S, d["out"].data_ptr(), d["segs"].data_ptr())
 
     def barrier():
@@ -200,7 +215,7 @@ def main():
         eng.open(b.seg_slot, status)
         with torch.cuda.stream(stream):
             e0.record(stream)
-            eng.step_device(d["data"].data_ptr(), n_bytes, d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
+            eng.step_device(d["data"].data_ptr(), int(b.data.size), d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
                             d["seg_slot"].data_ptr(), S, d["out"].data_ptr(), d["segs"].data_ptr())
             e1.record(stream)
         eng.sync()
@@ -211,7 +226,6 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count() - l0
-    sampler.stop_ev.set(); sampler.join(timeout=2)
     dev_ms = float(np.sum(step_ms))
     if world > 1:
         t = torch.tensor([dev_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
@@ -243,9 +257,11 @@ def main():
     if world > 1:
         t = torch.tensor([e2e_step], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_step = float(t.item())
     e2e_value = events_total / (e2e_step / 1e3)
+    n_bytes = int(sets[0][0].data.size)
     h2d = n_bytes + 4 * (n_chunks + 1) + 4 * (S + 1) + 4 * S + 8 * S
     d2h = n_bytes + S * SEG_DTYPE.itemsize + S * 440
 
+    sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

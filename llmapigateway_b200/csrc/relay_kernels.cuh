@@ -1,10 +1,275 @@
-// placeholder until the bulk kernel lands: fast mode == exact sequential path
+// Bulk path of the SSE step: k_prime -> k_relay -> k_commit.   (included from sse_kernels.cuh)
+//
+// Regular streams -- committed, carries empty and equal at the start of the bulk region, every
+// chunk valid UTF-8 and non-empty, no run of three or more LFs, no event the tap turns into an
+// extra row ("error") or that has an unmodelled shape -- are exactly the streams for which the
+// reference's chunk-by-chunk split (request_handler.py:111-115, chat_logging.py:108-112) equals a
+// split of the CONCATENATED text on every LF LF pair.  For those, events are independent: the
+// chunk in which an event completes owns it, parses it, and posts its findings with atomics.
+// Everything else is flagged irregular and redone by k_commit with the exact sequential machine,
+// so the result never depends on which path ran (tests run both and compare with the oracle).
+
+#define LGW_RELAY_THREADS 256
+
+// 16 KB tile in shared memory, swizzled so that 32 lanes reading the same byte position of 32
+// consecutive 64-byte rows (the 64-byte-event pattern) hit 32 different banks, while a 16-byte
+// vector store stays one STS.128 (the four words are permuted inside their own vector).
+__device__ __forceinline__ uint32_t swz(uint32_t off) {
+    const uint32_t r = off >> 6;
+    return (off & ~63u) | ((((off >> 4) & 3u) ^ ((r >> 1) & 3u)) << 4) | ((((off >> 2) & 3u) ^ ((r >> 3) & 3u)) << 2) | (off & 3u);
+}
+
+struct TileReader {
+    const uint8_t* smem;          // swizzled tile
+    const uint8_t* __restrict__ g; // whole packed buffer
+    uint32_t t0;                  // tile start offset
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const {
+        const uint32_t d = pos - t0;
+        return d < LGW_TILE_BYTES ? (uint32_t)smem[swz(d)] : (uint32_t)__ldg(g + pos);
+    }
+};
+
+// flags-only parse of the event text [s, e) read through the tile reader
+__device__ __forceinline__ uint32_t parse_event_flags(const TileReader& rd, uint32_t s, uint32_t e, bool data_prefix) {
+    JsonMachine<false> m;
+    m.reset(nullptr, data_prefix);
+    for (uint32_t i = s + (data_prefix ? 6u : 0u); i < e; ++i) {
+        m.feed(rd.at(i));
+        if (m.failed()) break;
+    }
+    return m.finish();
+}
+
+__device__ __forceinline__ uint8_t classify_event(const TileReader& rd, uint32_t s, uint32_t e) {
+    if (e <= s) return PC_NONE;
+    const uint32_t c0 = rd.at(s);
+    if (c0 == '{') return PC_BRACE;
+    if (c0 != 'd' || e - s < 7) return PC_NONE;
+    return (rd.at(s + 1) == 'a' && rd.at(s + 2) == 't' && rd.at(s + 3) == 'a' && rd.at(s + 4) == ':' &&
+            rd.at(s + 5) == ' ' && rd.at(s + 6) == '{') ? PC_DATA : PC_NONE;
+}
+
+// ---- k_prime ---------------------------------------------------------------------------------------
+// thread i: (a) tile table entry i = first chunk that starts at or after byte i*TILE;
+//           (b) segment i: finish priming with the exact machine, then plan the bulk region.
+__global__ void __launch_bounds__(64) k_prime(StepArgs a, uint32_t n_tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_tiles) {
+        const uint32_t target = i * LGW_TILE_BYTES;
+        uint32_t lo = 0, hi = a.n_chunks;                 // first c in [0, n_chunks] with chunk_off[c] >= target
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.chunk_off[mid] < target) lo = mid + 1; else hi = mid; }
+        a.s.tile_chunk[i] = lo;
+    }
+    if (i >= a.n_segs) return;
+    const uint32_t seg = i, c0 = a.seg_chunk[seg], c1 = a.seg_chunk[seg + 1];
+    const StepIO io = make_io(a, a.seg_slot[seg]);
+    StreamState& st = *io.st;
+    SegPlan p;
+    p.seg_end = a.chunk_off[c1]; p.relay_begin = p.seg_end; p.irregular = 0; p.last_usage_pos = 0; p.a_usage = 0;
+    p.n_events_a = p.n_events_b = p.n_usage_b = 0; p._pad[0] = p._pad[1] = 0;
+    uint32_t emit_begin = (st.phase == PH_COMMITTED) ? c0 : c1;
+    uint32_t resume = c0;
+    if (st.phase == PH_PRIMING) resume = run_chunks(io, a.data, a.chunk_off, c0, c1, emit_begin, true);
+    if (st.phase == PH_COMMITTED && resume < c1) {
+        if ((st.flags & SF_SYNCED) && st.carry_a_len == 0) p.relay_begin = a.chunk_off[resume];
+        else p.irregular = 1;
+    }
+    p.resume_chunk = resume; p.emit_chunk_begin = emit_begin;
+    a.s.plan[seg] = p;
+}
+
+// ---- k_relay ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LGW_RELAY_THREADS) k_relay(StepArgs a) {
+    __shared__ __align__(16) uint8_t tile[LGW_TILE_BYTES];
+    const uint32_t t0 = blockIdx.x * LGW_TILE_BYTES;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_bytes = a.n_bytes;
+
+    // (1) re-emit: position-preserving 16-byte copy of the tile, staged into shared memory on the way
+    {
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
+#pragma unroll
+        for (uint32_t k = 0; k < LGW_TILE_BYTES / 16 / LGW_RELAY_THREADS; ++k) {
+            const uint32_t v = k * LGW_RELAY_THREADS + tid;
+            const uint32_t pos = t0 + v * 16;
+            if (pos + 16 <= n_bytes) {
+                uint4 x = __ldg(src + v);
+                dst[v] = x;
+                const uint32_t r = (v * 16) >> 6;
+                const uint32_t kx = (r >> 3) & 3u;          // word permutation inside the vector
+                uint4 y;
+                y.x = kx == 0 ? x.x : kx == 1 ? x.y : kx == 2 ? x.z : x.w;
+                y.y = kx == 0 ? x.y : kx == 1 ? x.x : kx == 2 ? x.w : x.z;
+                y.z = kx == 0 ? x.z : kx == 1 ? x.w : kx == 2 ? x.x : x.y;
+                y.w = kx == 0 ? x.w : kx == 1 ? x.z : kx == 2 ? x.y : x.x;
+                const uint32_t slot16 = ((v * 16) & ~63u) | ((((v * 16) >> 4 & 3u) ^ ((r >> 1) & 3u)) << 4);
+                *reinterpret_cast<uint4*>(tile + slot16) = y;
+            } else if (pos < n_bytes) {
+                for (uint32_t b = pos; b < n_bytes; ++b) { const uint8_t c = a.data[b]; a.out[b] = c; tile[swz(b - t0)] = c; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // (2) events of the chunks that START in this tile
+    TileReader rd{tile, a.data, t0};
+    const uint32_t c_lo = a.s.tile_chunk[blockIdx.x], c_hi = a.s.tile_chunk[blockIdx.x + 1];
+    for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
+        // segment of chunk c: last seg with seg_chunk[seg] <= c (empty segments never match)
+        uint32_t lo = 0, hi = a.n_segs;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+        const uint32_t seg = lo;
+        SegPlan* pl = a.s.plan + seg;
+        const uint32_t relay_begin = pl->relay_begin, seg_end = pl->seg_end;
+        const uint32_t o = __ldg(a.chunk_off + c), e = __ldg(a.chunk_off + c + 1);
+        if (o < relay_begin || pl->irregular) continue;
+        if (e == o) { pl->irregular = 1; continue; }
+
+        // chunk-level UTF-8 check (request_handler.py:111 decodes each chunk on its own)
+        bool has_high = false;
+        for (uint32_t p = o; p < e; ++p) has_high |= rd.at(p) >= 0x80;
+        if (has_high) {
+            // walk the DFA over this chunk only
+            uint32_t p = o; bool ok = true;
+            while (p < e && ok) {
+                const uint32_t ch = rd.at(p);
+                if (ch < 0x80) { ++p; continue; }
+                uint32_t need, l = 0x80, h = 0xBF;
+                if (ch >= 0xC2 && ch <= 0xDF) need = 1;
+                else if (ch == 0xE0) { need = 2; l = 0xA0; }
+                else if (ch >= 0xE1 && ch <= 0xEC) need = 2;
+                else if (ch == 0xED) { need = 2; h = 0x9F; }
+                else if (ch >= 0xEE && ch <= 0xEF) need = 2;
+                else if (ch == 0xF0) { need = 3; l = 0x90; }
+                else if (ch >= 0xF1 && ch <= 0xF3) need = 3;
+                else if (ch == 0xF4) { need = 3; h = 0x8F; }
+                else { ok = false; break; }
+                if (p + need >= e) { ok = false; break; }
+                uint32_t b = rd.at(p + 1);
+                if (b < l || b > h) { ok = false; break; }
+                for (uint32_t k = 2; k <= need; ++k) { b = rd.at(p + k); if (b < 0x80 || b > 0xBF) ok = false; }
+                p += need + 1;
+            }
+            if (!ok) { pl->irregular = 1; continue; }
+        }
+
+        // where does the event that is open at the start of this chunk begin?
+        uint32_t b = o;
+        if (o != relay_begin) {
+            uint32_t k = o;
+            bool found = false;
+            const uint32_t limit = (o - relay_begin > a.t.carry_cap + 2) ? o - a.t.carry_cap - 2 : relay_begin;
+            while (k >= limit + 2) {
+                if (rd.at(k - 1) == '\n' && rd.at(k - 2) == '\n') { found = true; break; }
+                --k;
+            }
+            if (found) {
+                b = k;
+                if (k >= relay_begin + 3 && rd.at(k - 3) == '\n') { pl->irregular = 1; continue; }   // LF run >= 3
+            } else {
+                b = relay_begin;
+                if (limit != relay_begin) { pl->irregular = 1; continue; }     // open event longer than the carry capacity
+            }
+            if (o - b > a.t.carry_cap) { pl->irregular = 1; continue; }
+            if (found && rd.at(b) == '\n' && b < seg_end) { pl->irregular = 1; continue; }            // LF run >= 3
+        }
+
+        // events that complete inside this chunk
+        uint32_t ev_a = 0, ev_b = 0, us_b = 0, a_usage = 0, last_usage = 0;
+        bool irregular = false;
+        uint32_t ps = b;
+        uint32_t i = (b > o) ? b : o;          // the second LF must lie in [o, e)
+        if (i > 0 && i == o && o > b) --i;      // a separator may straddle the chunk start
+        while (i + 1 < e) {
+            if (rd.at(i) == '\n' && rd.at(i + 1) == '\n') {
+                if (i + 2 < seg_end && rd.at(i + 2) == '\n') { irregular = true; break; }
+                const uint8_t cls = classify_event(rd, ps, i);
+                if (cls != PC_NONE) {
+                    const uint32_t f = parse_event_flags(rd, ps, i, cls == PC_DATA);
+                    if (cls == PC_DATA) {                                   // handler loop, request_handler.py:122-134
+                        ++ev_a;
+                        if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
+                    }
+                    if (f & PF_VALID_B) {                                   // tap loop, chat_logging.py:123-141
+                        if ((f & PF_EXOTIC) || (f & TK_ERROR)) {
+                            if (!((f & TK_CHOICES) && (f & PF_TYPE_ERROR)) || (f & PF_EXOTIC)) { irregular = true; break; }
+                        }
+                        if (!((f & TK_CHOICES) && (f & PF_TYPE_ERROR))) {
+                            ++ev_b;
+                            if (f & TK_USAGE) { ++us_b; last_usage = ps + 1; }
+                        }
+                    }
+                }
+                ps = i + 2; i += 2;
+            } else ++i;
+        }
+        if (irregular) { pl->irregular = 1; continue; }
+        if (ev_a) atomicAdd(&pl->n_events_a, ev_a);
+        if (ev_b) atomicAdd(&pl->n_events_b, ev_b);
+        if (us_b) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage_pos, last_usage); }
+        if (a_usage) pl->a_usage = 1;
+    }
+}
+
+// ---- k_commit --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_commit(StepArgs a) {
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= a.n_segs) return;
+    const uint32_t c1 = a.seg_chunk[seg + 1];
+    const StepIO io = make_io(a, a.seg_slot[seg]);
+    StreamState& st = *io.st;
+    const SegPlan p = a.s.plan[seg];
+    uint32_t emit_begin = p.emit_chunk_begin;
+    if (st.phase == PH_COMMITTED && p.resume_chunk < c1) {
+        if (p.irregular) {
+            run_chunks(io, a.data, a.chunk_off, p.resume_chunk, c1, emit_begin, false);
+        } else {
+            const uint32_t nch = c1 - p.resume_chunk, nby = p.seg_end - p.relay_begin;
+            st.n_chunks_in += nch; st.n_chunks_emitted += nch; st.bytes_in += nby; st.bytes_emitted += nby;
+            st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b; st.n_usage_b += p.n_usage_b;
+            if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
+            const uint8_t* d = a.data;
+            if (p.last_usage_pos) {                 // the last usage-bearing event wins (chat_logging.py:134-135)
+                const uint32_t ps = p.last_usage_pos - 1;
+                uint32_t pe = ps;
+                while (pe + 1 < p.seg_end && !(d[pe] == '\n' && d[pe + 1] == '\n')) ++pe;
+                Rope r{nullptr, 0, d + ps, pe - ps};
+                const uint8_t cls = classify_part(r, 0, pe - ps);
+                UsageRaw raw;
+                const uint32_t f = parse_part<true>(r, 0, pe - ps, cls, &raw);
+                normalise_usage(raw, f, st.rec);
+                st.flags |= SF_REC_VALID;
+                if (st.rec.exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+            }
+            // new carry = text after the last separator (both loops: SF_SYNCED)
+            uint32_t tail = p.relay_begin;
+            if (nby >= 2 && d[p.seg_end - 1] == '\n' && d[p.seg_end - 2] == '\n') tail = p.seg_end;
+            else {
+                const uint32_t limit = nby > a.t.carry_cap + 2 ? p.seg_end - a.t.carry_cap - 2 : p.relay_begin;
+                for (uint32_t k = p.seg_end; k >= limit + 2; --k)
+                    if (d[k - 1] == '\n' && d[k - 2] == '\n') { tail = k; break; }
+            }
+            const uint32_t n = p.seg_end - tail;
+            if (n > a.t.carry_cap) { st.carry_a_len = 0; st.flags |= SF_CARRY_OVERFLOW; }
+            else { for (uint32_t k = 0; k < n; ++k) io.carry_a[k] = d[tail + k]; st.carry_a_len = n; }
+        }
+    }
+    SegResult res;
+    fill_seg_result(st, emit_begin, c1, res);
+    a.seg_out[seg] = res;
+}
+
 static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
+    (void)sm_count;
     cudaError_t r;
+    const uint32_t n_tiles = (a.n_bytes + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
+    const uint32_t n_prime = (a.n_segs > n_tiles + 1 ? a.n_segs : n_tiles + 1);
+    k_prime<<<(n_prime + 63) / 64, 64, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
-    if (a.n_bytes) { k_copy<<<sm_count * 8, 256, 0, stream>>>(a.data, a.out, a.n_bytes); ++*launched; }
+    if (n_tiles) { k_relay<<<n_tiles, LGW_RELAY_THREADS, 0, stream>>>(a); ++*launched; }
     if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
-    if (a.n_segs) { k_general<<<(a.n_segs + 63) / 64, 64, 0, stream>>>(a); ++*launched; }
+    if (a.n_segs) { k_commit<<<(a.n_segs + 63) / 64, 64, 0, stream>>>(a); ++*launched; }
     if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
     return cudaGetLastError();
 }

@@ -371,17 +371,17 @@ LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
     return kept;
 }
 
-// A whole segment (this step's chunks of one stream), sequentially.
-LGW_HD void run_segment(const StepIO& io, const uint8_t* data, const uint32_t* chunk_off,
-                        uint32_t c0, uint32_t c1, SegResult& res) {
+// Chunks [c_from, c_to) of one stream, sequentially.  `emit_begin` tracks the first relayed chunk.
+// With stop_at_commit the walk returns right after the kept chunk (the stream has just committed);
+// the return value is the first chunk not consumed.
+LGW_HD uint32_t run_chunks(const StepIO& io, const uint8_t* data, const uint32_t* chunk_off,
+                           uint32_t c_from, uint32_t c_to, uint32_t& emit_begin, bool stop_at_commit) {
     StreamState& st = *io.st;
-    uint32_t emit_begin = c1;
-    if (st.phase == PH_COMMITTED) emit_begin = c0;
-    for (uint32_t c = c0; c < c1; ++c) {
+    for (uint32_t c = c_from; c < c_to; ++c) {
         const uint32_t o = chunk_off[c], n = chunk_off[c + 1] - o;
         if (n == 0) continue;                                   // never yielded (request_handler.py:60-63)
-        ++st.n_chunks_in; st.bytes_in += n;
         if (st.phase == PH_PRIMING) {
+            ++st.n_chunks_in; st.bytes_in += n;
             if (prime_chunk(io, data + o, n)) {
                 emit_begin = c;
                 st.flags |= SF_EMITTED_ANY;
@@ -390,15 +390,30 @@ LGW_HD void run_segment(const StepIO& io, const uint8_t* data, const uint32_t* c
                 ++st.n_chunks_emitted; st.bytes_emitted += n;
                 relay_chunk(io, data + o, n, true);             // the tap sees the kept chunk
                 if (st.carry_b_len == 0) st.flags |= SF_SYNCED; // kept chunk ended on a separator
+                if (stop_at_commit) return c + 1;
             }
         } else if (st.phase == PH_COMMITTED) {
+            ++st.n_chunks_in; st.bytes_in += n;
             ++st.n_chunks_emitted; st.bytes_emitted += n;
             relay_chunk(io, data + o, n, false);
+        } else {
+            return c_to;      // PH_FAILED / PH_FREE: the generator is gone; nothing is read or relayed
         }
-        // PH_FAILED / PH_FREE: the generator is gone; nothing is read or relayed
     }
+    return c_to;
+}
+
+LGW_HD void fill_seg_result(const StreamState& st, uint32_t emit_begin, uint32_t c1, SegResult& res) {
     res.emit_chunk_begin = (st.phase == PH_COMMITTED) ? emit_begin : c1;
     res.phase = st.phase; res.verdict = st.verdict; res.flags = st.flags; res.detail_len = st.detail_len;
+}
+
+// A whole segment (this step's chunks of one stream), sequentially.
+LGW_HD void run_segment(const StepIO& io, const uint8_t* data, const uint32_t* chunk_off,
+                        uint32_t c0, uint32_t c1, SegResult& res) {
+    uint32_t emit_begin = (io.st->phase == PH_COMMITTED) ? c0 : c1;
+    run_chunks(io, data, chunk_off, c0, c1, emit_begin, false);
+    fill_seg_result(*io.st, emit_begin, c1, res);
 }
 
 LGW_HD void init_stream(StreamState& st, int http_status) {
