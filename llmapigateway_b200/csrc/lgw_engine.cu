@@ -158,7 +158,7 @@ extern "C" int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uin
     StreamState st;
     CK(e, cudaMemcpyAsync(&st, e->t.state + slot, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    uint32_t n = st.detail_len < cap ? st.detail_len : cap;
+    uint32_t n = st.h.detail_len < cap ? st.h.detail_len : cap;
     if (n) CK(e, cudaMemcpyAsync(buf, e->t.detail + (size_t)slot * e->lim.detail_cap, n, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     *len = n;

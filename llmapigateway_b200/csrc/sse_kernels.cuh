@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "stream_machine.cuh"
+#include "lean_json.cuh"
 
 namespace lgw {
 
@@ -60,9 +61,10 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size
 }
 static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); s.plan = nullptr; s.tile_chunk = nullptr; }
 
-__device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot) {
+__device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot, StreamHdr* local_hdr) {
     StepIO io;
-    io.st = a.t.state + slot;
+    io.st = local_hdr;
+    io.rec = &a.t.state[slot].rec;
     io.carry_a = a.t.carry_a + (size_t)slot * a.t.carry_cap;
     io.carry_b = a.t.carry_b + (size_t)slot * a.t.carry_cap;
     io.detail = a.t.detail + (size_t)slot * a.t.detail_cap;
@@ -83,16 +85,19 @@ __global__ void k_streams_gather(DeviceTables t, const uint32_t* slots, uint32_t
     if (i >= n) return;
     StreamState* s = t.state + slots[i];
     out[i] = *s;
-    if (free_after) s->phase = PH_FREE;
+    if (free_after) s->h.phase = PH_FREE;
 }
 
 // ---- exact sequential path ------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_general(StepArgs a) {
     const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= a.n_segs) return;
-    const StepIO io = make_io(a, a.seg_slot[seg]);
+    const uint32_t slot = a.seg_slot[seg];
+    StreamHdr st = a.t.state[slot].h;
+    const StepIO io = make_io(a, slot, &st);
     SegResult res;
     run_segment(io, a.data, a.chunk_off, a.seg_chunk[seg], a.seg_chunk[seg + 1], res);
+    a.t.state[slot].h = st;
     a.seg_out[seg] = res;
 }
 

@@ -48,19 +48,24 @@ struct UsageRec {
     char provider[LGW_STR_CAP];
 };
 
-struct StreamState {
+struct StreamHdr {            // the 64 hot bytes of a stream's state (kernels work on a local copy)
     uint8_t phase, verdict;
     uint16_t flags;
     uint32_t carry_a_len, carry_b_len, detail_len;
     uint32_t n_events_a;       // real events parsed by the handler loop
-    uint32_t n_events_b;       // events the tap parsed successfully
-    uint32_t n_usage_b;        // of those, how many carried usage
+    uint32_t n_events_b;       // events the tap parsed as JSON
+    uint32_t n_usage_b;        // of those, how many updated the usage record
     uint32_t n_exotic;
     uint32_t n_error_rows;     // tap "error" events => extra rows (chat_logging.py:137-139)
     uint32_t n_chunks_in, n_chunks_emitted;
+    uint32_t _pad;
     uint64_t bytes_in, bytes_emitted;
+};
+struct StreamState {          // == lgw_stream_state
+    StreamHdr h;
     UsageRec rec;
 };
+static_assert(sizeof(StreamHdr) == 64, "StreamHdr must be 64 bytes");
 
 struct RowEvent {            // one write_log call that happened mid-stream (chat_logging.py:139)
     uint32_t slot, seq;
@@ -247,7 +252,8 @@ LGW_HD bool store_carry(uint8_t* carry, uint32_t& carry_len, uint32_t cap, const
 }
 
 struct StepIO {                 // where one stream's step reads and writes
-    StreamState* st;
+    StreamHdr* st;              // usually a local copy, written back by the caller
+    UsageRec* rec;              // the stream's tap record (global memory)
     uint8_t* carry_a; uint8_t* carry_b; uint8_t* detail;
     uint32_t carry_cap, detail_cap;
     RowEvent* rowq; uint32_t* rowq_count; uint32_t rowq_cap;
@@ -262,7 +268,7 @@ LGW_HD void save_detail(const StepIO& io, const Rope& r, uint32_t s, uint32_t e)
 }
 
 LGW_HD void push_row(const StepIO& io) {
-    StreamState& st = *io.st;
+    StreamHdr& st = *io.st;
     ++st.n_error_rows;
 #if defined(__CUDA_ARCH__)
     const uint32_t k = atomicAdd(io.rowq_count, 1u);
@@ -272,25 +278,27 @@ LGW_HD void push_row(const StepIO& io) {
     if (k >= io.rowq_cap) { st.flags |= SF_ROWQ_OVERFLOW; return; }
     RowEvent& ev = io.rowq[k];
     ev.slot = io.slot; ev.seq = st.n_error_rows;
-    if (st.flags & SF_REC_VALID) ev.rec = st.rec; else default_usage(ev.rec);
+    if (st.flags & SF_REC_VALID) ev.rec = *io.rec; else default_usage(ev.rec);
 }
 
-// tap handling of one parsed part (chat_logging.py:123-141)
+// tap handling of one parsed part (chat_logging.py:123-141).  The choices walk (and any shape of it
+// the device does not model) is observable only through events that also carry "usage" or "error".
 LGW_HD void tap_part(const StepIO& io, uint32_t f, const UsageRaw& raw) {
-    StreamState& st = *io.st;
+    StreamHdr& st = *io.st;
     if (!(f & PF_VALID_B)) return;
+    ++st.n_events_b;
+    if (!(f & (TK_USAGE | TK_ERROR))) return;
     if (f & PF_EXOTIC) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; return; }
     if ((f & TK_CHOICES) && (f & PF_TYPE_ERROR)) return;
-    ++st.n_events_b;
     if (f & TK_USAGE) {
-        normalise_usage(raw, f, st.rec);
+        normalise_usage(raw, f, *io.rec);
         st.flags |= SF_REC_VALID; ++st.n_usage_b;
-        if (st.rec.exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+        if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
     }
     if (f & TK_ERROR) push_row(io);
 }
 
-LGW_HD void handler_part(StreamState& st, uint32_t f) {       // request_handler.py:122-134
+LGW_HD void handler_part(StreamHdr& st, uint32_t f) {       // request_handler.py:122-134
     ++st.n_events_a;
     if (!(f & PF_VALID_A)) return;
     if (f & TK_CODE) return;                                   // Appendix A.1 item 9
@@ -302,7 +310,7 @@ LGW_HD void handler_part(StreamState& st, uint32_t f) {       // request_handler
 // While the two carries differ (SF_SYNCED clear) each loop scans with its own carry; they become
 // equal for good as soon as both loops end a chunk on the same separator.
 LGW_HD void relay_chunk(const StepIO& io, const uint8_t* p, uint32_t n, bool tap_only) {
-    StreamState& st = *io.st;
+    StreamHdr& st = *io.st;
     if (!utf8_valid(p, n)) return;            // both loops swallow the decode error; carries unchanged
     UsageRaw raw;
     bool stopped;
@@ -349,7 +357,7 @@ LGW_HD void relay_chunk(const StepIO& io, const uint8_t* p, uint32_t n, bool tap
 // One chunk while priming (request_handler.py:34-58 and :69-95).  Returns true when this chunk
 // is the kept one (the stream committed on it).
 LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
-    StreamState& st = *io.st;
+    StreamHdr& st = *io.st;
     if (!utf8_valid(p, n)) return false;                     // sniffer swallows, priming drops (:94-95)
     Rope r{io.carry_a, st.carry_a_len, p, n};
     bool stopped;
@@ -376,7 +384,7 @@ LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
 // the return value is the first chunk not consumed.
 LGW_HD uint32_t run_chunks(const StepIO& io, const uint8_t* data, const uint32_t* chunk_off,
                            uint32_t c_from, uint32_t c_to, uint32_t& emit_begin, bool stop_at_commit) {
-    StreamState& st = *io.st;
+    StreamHdr& st = *io.st;
     for (uint32_t c = c_from; c < c_to; ++c) {
         const uint32_t o = chunk_off[c], n = chunk_off[c + 1] - o;
         if (n == 0) continue;                                   // never yielded (request_handler.py:60-63)
@@ -403,7 +411,7 @@ LGW_HD uint32_t run_chunks(const StepIO& io, const uint8_t* data, const uint32_t
     return c_to;
 }
 
-LGW_HD void fill_seg_result(const StreamState& st, uint32_t emit_begin, uint32_t c1, SegResult& res) {
+LGW_HD void fill_seg_result(const StreamHdr& st, uint32_t emit_begin, uint32_t c1, SegResult& res) {
     res.emit_chunk_begin = (st.phase == PH_COMMITTED) ? emit_begin : c1;
     res.phase = st.phase; res.verdict = st.verdict; res.flags = st.flags; res.detail_len = st.detail_len;
 }
@@ -416,13 +424,14 @@ LGW_HD void run_segment(const StepIO& io, const uint8_t* data, const uint32_t* c
     fill_seg_result(*io.st, emit_begin, c1, res);
 }
 
-LGW_HD void init_stream(StreamState& st, int http_status) {
+LGW_HD void init_stream(StreamState& s, int http_status) {
+    StreamHdr& st = s.h;
     st.phase = http_status >= 400 ? PH_FAILED : PH_PRIMING;
     st.verdict = http_status >= 400 ? VD_FAIL_HTTP : VD_NONE;
     st.flags = 0; st.carry_a_len = st.carry_b_len = st.detail_len = 0;
     st.n_events_a = st.n_events_b = st.n_usage_b = st.n_exotic = st.n_error_rows = 0;
-    st.n_chunks_in = st.n_chunks_emitted = 0; st.bytes_in = st.bytes_emitted = 0;
-    default_usage(st.rec);
+    st.n_chunks_in = st.n_chunks_emitted = 0; st._pad = 0; st.bytes_in = st.bytes_emitted = 0;
+    default_usage(s.rec);
 }
 
 }  // namespace lgw

@@ -44,6 +44,11 @@ def parse_part(text: bytes):
     return f, cls.value, rec
 
 
+def lean_parse(text: bytes) -> int:
+    lib().lgwt_lean_parse.restype = C.c_uint32
+    return lib().lgwt_lean_parse(text, len(text))
+
+
 def utf8_valid(b: bytes) -> bool:
     return bool(lib().lgwt_utf8_valid(b, len(b)))
 

@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../include/llmgw_b200.h"
 #include "../../llmapigateway_b200/csrc/stream_machine.cuh"
+#include "../../llmapigateway_b200/csrc/lean_json.cuh"
 
 using namespace lgw;
 
@@ -34,6 +35,14 @@ uint32_t lgwt_parse_part(const uint8_t* text, uint32_t n, lgw_usage_rec* rec_out
     return f;
 }
 
+// the bulk kernel's lean recogniser on the same text (flags subset)
+uint32_t lgwt_lean_parse(const uint8_t* text, uint32_t n) {
+    Rope r{nullptr, 0, text, n};
+    const uint8_t cls = classify_part(r, 0, n);
+    if (cls == PC_NONE) return 0;
+    return lean_parse(r, cls == PC_DATA ? 6u : 0u, n, cls == PC_DATA, g_lean_tables_host.cls, g_lean_tables_host.trans);
+}
+
 int lgwt_utf8_valid(const uint8_t* p, uint32_t n) { return utf8_valid(p, n) ? 1 : 0; }
 
 int lgwt_dec_to_double(uint64_t man, int exp10, uint64_t* bits) { return dec_to_double(man, exp10, *bits) ? 1 : 0; }
@@ -48,14 +57,14 @@ int lgwt_run_stream(const uint8_t* data, const uint32_t* chunk_off, const uint32
     std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1);
     std::vector<RowEvent> rq(rows_cap + 1);
     uint32_t rcount = 0;
-    StepIO io{&st, ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
+    StepIO io{&st.h, &st.rec, ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
     for (uint32_t k = 0; k < n_steps; ++k) {
         SegResult res;
         run_segment(io, data, chunk_off, step_chunk[k], step_chunk[k + 1], res);
         memcpy(&seg_out[k], &res, sizeof(res));
     }
     memcpy(final_state, &st, sizeof(st));
-    memcpy(detail_out, det.data(), st.detail_len);
+    memcpy(detail_out, det.data(), st.h.detail_len);
     *n_rows = rcount < rows_cap ? rcount : rows_cap;
     memcpy(rows_out, rq.data(), sizeof(RowEvent) * (*n_rows));
     return 0;

@@ -158,6 +158,8 @@ def test_part_parser_matches_cpython():
             continue
         f, cls, rec = hm.parse_part(text.encode("utf-8"))
         assert f != 0xFFFFFFFF, text            # flags-only machine == extracting machine
+        lean_mask = _abi.PF_VALID_A | _abi.PF_VALID_B | _abi.TK_ERROR | _abi.TK_DETAIL | _abi.TK_CODE | _abi.TK_USAGE | _abi.PF_TOO_DEEP
+        assert hm.lean_parse(text.encode("utf-8")) == (f & lean_mask), text      # the bulk kernel's lean recogniser
         assert cls == 1
         py = _py_view(text)
         assert bool(f & _abi.PF_VALID_A) == py["valid_a"], text
@@ -189,6 +191,21 @@ def test_part_parser_matches_cpython():
         n_checked += 1
     assert n_valid > 15000 and n_usage > 3000
     assert n_exotic < 0.3 * n_valid      # the generator aims at odd shapes on purpose
+
+
+def test_lean_recogniser_on_golden_events():
+    """Every complete event of every golden stream: lean flags == full-machine flags (subset)."""
+    lean_mask = _abi.PF_VALID_A | _abi.PF_VALID_B | _abi.TK_ERROR | _abi.TK_DETAIL | _abi.TK_CODE | _abi.TK_USAGE | _abi.PF_TOO_DEEP
+    n = 0
+    for case in CASES:
+        blob = b"".join(case["chunks"])
+        for part in blob.split(b"\n\n"):
+            f, cls, _ = hm.parse_part(part)
+            if cls == 0:
+                continue
+            assert hm.lean_parse(part) == (f & lean_mask), part
+            n += 1
+    assert n > 500
 
 
 def test_utf8_validator_matches_cpython():

@@ -29,48 +29,6 @@ def _expect(case):
                 end_raises=case["end_raises"], rows=case["rows"], http_status=case["http_status"])
 
 
-class _SegView:
-    def __init__(self, row):
-        self.emit_chunk_begin = int(row["emit_chunk_begin"])
-
-
-def _run_cases(engine, cases, schedule, mode):
-    """schedule(case) -> list of step boundaries (chunk indices where a step starts)."""
-    engine.set_mode(mode)
-    n = len(cases)
-    slots = np.arange(n, dtype=np.uint32)
-    engine.open(slots, [c["http_status"] for c in cases])
-    bounds = [list(schedule(c)) + [len(c["chunks"])] for c in cases]
-    n_steps = max(len(b) - 1 for b in bounds)
-    seg_views = [[] for _ in cases]       # per case: list of (local step_chunk, seg)
-    step_chunks = [[0] for _ in cases]
-    rows = []
-    emitted_bytes = [[] for _ in cases]
-    for k in range(n_steps):
-        streams, who = [], []
-        for i, c in enumerate(cases):
-            b = bounds[i]
-            if k < len(b) - 1:
-                streams.append(c["chunks"][b[k]:b[k + 1]]); who.append(i)
-        pb = pack_streams(streams, slots=who)
-        res = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot)
-        rows += res.rows
-        for s, i in enumerate(who):
-            c0, c1 = int(pb.seg_chunk[s]), int(pb.seg_chunk[s + 1])
-            eb = int(res.segs["emit_chunk_begin"][s])
-            assert c0 <= eb <= c1
-            # byte-exact re-emit of the kept chunks
-            for ch in range(eb, c1):
-                o0, o1 = int(pb.chunk_off[ch]), int(pb.chunk_off[ch + 1])
-                if o1 > o0:
-                    emitted_bytes[i].append(res.out[o0:o1].tobytes())
-    states = engine.close(slots)
-    details = {}
-    for i, st in enumerate(states):
-        pass
-    return states, rows, emitted_bytes
-
-
 @pytest.mark.parametrize("mode", [1, 0], ids=["general", "fast"])
 @pytest.mark.parametrize("stepping", ["one_step", "step_per_chunk", "random_steps"])
 def test_golden_cases_batched(engine, mode, stepping):
@@ -205,3 +163,93 @@ def test_c3_full_size_properties(engine, mode):
         assert all(st.flags & _abi.SF_A_USAGE_BOUND for st in states)
     finally:
         e.close_engine()
+
+
+def _random_streams(n, seed):
+    """Mostly well-formed streams (so the bulk path is exercised) with a share of odd ones."""
+    import sse_cases as sc
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        k = rng.random()
+        n_ev = rng.randrange(1, 40)
+        if k < 0.6:      # clean: deltas, usage, done
+            evs = [sc.delta(rng.choice(["a", "hello", "\u00e9t\u00e9", "x" * rng.randrange(1, 200)])) for _ in range(n_ev)]
+            if rng.random() < 0.8:
+                u = dict(sc.USAGE); u["prompt_tokens"] = rng.randrange(10**6)
+                evs.append(sc.ev({"choices": [], "usage": u, "model": "m%d" % i, "provider": "P"}))
+            if rng.random() < 0.8:
+                evs.append(sc.DONE)
+        else:            # anything from the adversarial pool
+            evs = [sc._random_event(rng) for _ in range(n_ev)]
+            if rng.random() < 0.7:
+                evs.insert(0, sc.delta("lead"))
+        blob = b"".join(evs)
+        m = rng.random()
+        if m < 0.5:
+            chunks = evs
+        elif m < 0.75:
+            chunks = sc.rechunk(blob, [rng.randrange(1, max(2, len(blob))) for _ in range(rng.randrange(0, 12))])
+        else:
+            step = rng.randrange(3, 150)
+            chunks = sc.rechunk(blob, list(range(step, len(blob), step)))
+        out.append([c for c in chunks if c])
+    return out
+
+
+def _run_all(engine, streams, mode, n_steps, seed):
+    engine.set_mode(mode)
+    n = len(streams)
+    slots = np.arange(n, dtype=np.uint32)
+    engine.open(slots)
+    rng = random.Random(seed)
+    bounds = []
+    for st in streams:
+        cuts = sorted(set(rng.randrange(0, len(st) + 1) for _ in range(n_steps - 1)))
+        bounds.append([0] + cuts + [len(st)])
+    emitted = [[] for _ in streams]
+    rows = []
+    for k in range(n_steps):
+        parts, who = [], []
+        for i, st in enumerate(streams):
+            b = bounds[i]
+            if k < len(b) - 1 and b[k + 1] > b[k]:
+                parts.append(st[b[k]:b[k + 1]]); who.append(i)
+        if not parts:
+            continue
+        pb = pack_streams(parts, slots=who)
+        res = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot)
+        rows += [(r.slot, r.seq, canon_rows([_abi.usage_rec_to_dict(r.rec)]) if not r.rec.exotic else 'exotic') for r in res.rows]
+        for s, i in enumerate(who):
+            for ch in range(int(res.segs["emit_chunk_begin"][s]), int(pb.seg_chunk[s + 1])):
+                emitted[i].append(res.out[int(pb.chunk_off[ch]):int(pb.chunk_off[ch + 1])].tobytes())
+    states = engine.close(slots)
+    return states, sorted(rows), emitted
+
+
+@pytest.mark.parametrize("n_steps", [1, 3])
+def test_bulk_path_equals_sequential_path_and_oracle(engine, n_steps):
+    """Differential: bulk kernel (+ fix-up) vs the exact sequential kernel vs the oracle, on
+    random streams with random chunking and random step boundaries."""
+    from oracle.sse_oracle import run_stream
+    streams = _random_streams(1500, seed=77 + n_steps)
+    s_fast, r_fast, e_fast = _run_all(engine, streams, 0, n_steps, seed=5)
+    s_seq, r_seq, e_seq = _run_all(engine, streams, 1, n_steps, seed=5)
+    assert e_fast == e_seq
+    assert r_fast == r_seq
+    n_regular = 0
+    for i, (a, b) in enumerate(zip(s_fast, s_seq)):
+        assert bytes(a)[:64] == bytes(b)[:64], (i, streams[i][:3])          # header: phase, flags, carries, counters
+        if a.flags & _abi.SF_REC_VALID:
+            assert a.rec.exotic == b.rec.exotic and (a.rec.exotic or _abi.usage_rec_to_dict(a.rec) == _abi.usage_rec_to_dict(b.rec) or canon_rows([_abi.usage_rec_to_dict(a.rec)]) == canon_rows([_abi.usage_rec_to_dict(b.rec)])), i
+        relay, tap = run_stream(streams[i])
+        assert e_fast[i] == relay.emitted, i
+        assert (a.phase == _abi.PHASE_FAILED) == relay.failed
+        if not relay.failed and not a.n_exotic:
+            got = [json.loads(r[2])[0] for r in r_fast if r[0] == i]
+            if a.flags & _abi.SF_EMITTED_ANY:
+                got.append(json.loads(canon_rows([_abi.usage_rec_to_dict(a.rec)]))[0])
+            assert canon_rows(got) == canon_rows(tap.rows), i
+            assert (not (a.flags & _abi.SF_A_USAGE_BOUND)) == relay.end_raises
+            n_regular += 1
+    assert n_regular > 1000
