@@ -79,7 +79,8 @@ enum lgw_stream_flag {
     LGW_SF_SYNCED = 1 << 4,
     LGW_SF_REC_VALID = 1 << 5,
     LGW_SF_DETAIL_TRUNC = 1 << 6,
-    LGW_SF_ROWQ_OVERFLOW = 1 << 7
+    LGW_SF_ROWQ_OVERFLOW = 1 << 7,
+    LGW_SF_PENDING = 1 << 8          /* internal: usage event stashed, extracted when the state is read */
 };
 
 typedef struct lgw_stream_state {
@@ -88,6 +89,7 @@ typedef struct lgw_stream_state {
     uint32_t carry_a_len, carry_b_len, detail_len;
     uint32_t n_events_a, n_events_b, n_usage_b, n_exotic, n_error_rows;
     uint32_t n_chunks_in, n_chunks_emitted;
+    uint32_t pending_len;        /* internal (see LGW_SF_PENDING); always 0 in states returned to the host */
     uint64_t bytes_in, bytes_emitted;
     lgw_usage_rec rec;       /* current tap record (valid when LGW_SF_REC_VALID, else the defaults) */
 } lgw_stream_state;

@@ -7,7 +7,7 @@ import struct
 KIND_ABSENT, KIND_INT, KIND_FLOAT, KIND_NULL, KIND_TRUE, KIND_FALSE, KIND_STR, KIND_BIGINT, KIND_OBJECT, KIND_ARRAY, KIND_FLOAT_INEXACT = range(11)
 PHASE_FREE, PHASE_PRIMING, PHASE_COMMITTED, PHASE_FAILED = range(4)
 VERDICT_NONE, VERDICT_OK, VERDICT_FAIL_EVENT, VERDICT_FAIL_PARSE, VERDICT_FAIL_HTTP = range(5)
-SF_A_USAGE_BOUND, SF_EMITTED_ANY, SF_CARRY_OVERFLOW, SF_EXOTIC_SEEN, SF_SYNCED, SF_REC_VALID, SF_DETAIL_TRUNC, SF_ROWQ_OVERFLOW = (1 << i for i in range(8))
+SF_A_USAGE_BOUND, SF_EMITTED_ANY, SF_CARRY_OVERFLOW, SF_EXOTIC_SEEN, SF_SYNCED, SF_REC_VALID, SF_DETAIL_TRUNC, SF_ROWQ_OVERFLOW, SF_PENDING = (1 << i for i in range(9))
 
 # TopKey | PartFlag bits returned by the part parser (json_machine.cuh)
 TK_ERROR, TK_DETAIL, TK_CODE, TK_USAGE, TK_CHOICES, TK_MODEL, TK_PROVIDER = (1 << i for i in range(7))
@@ -33,7 +33,7 @@ class StreamState(C.Structure):
                 ("carry_a_len", C.c_uint32), ("carry_b_len", C.c_uint32), ("detail_len", C.c_uint32),
                 ("n_events_a", C.c_uint32), ("n_events_b", C.c_uint32), ("n_usage_b", C.c_uint32),
                 ("n_exotic", C.c_uint32), ("n_error_rows", C.c_uint32),
-                ("n_chunks_in", C.c_uint32), ("n_chunks_emitted", C.c_uint32),
+                ("n_chunks_in", C.c_uint32), ("n_chunks_emitted", C.c_uint32), ("pending_len", C.c_uint32),
                 ("bytes_in", C.c_uint64), ("bytes_emitted", C.c_uint64), ("rec", UsageRec)]
 
 

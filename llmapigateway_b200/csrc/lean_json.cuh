@@ -142,8 +142,9 @@ struct LeanMachine {
         else if (n == 4 && k == lit_word("code")) flags |= TK_CODE;
     }
 
+    // R provides at(pos) (event bytes, for key matching), cls(byte) and trans(index) (the tables)
     template <class R>
-    LGW_HD void step(uint32_t c, uint32_t pos, const R& rd, const uint8_t* cls_tab, const uint8_t* trans_tab) {
+    LGW_HD void step(uint32_t c, uint32_t pos, const R& rd) {
         if (st == L_STR) {
             if (c == '"') {
                 if (in_key) {
@@ -155,8 +156,8 @@ struct LeanMachine {
             return;
         }
         if (st < LGW_LEAN_ROWS) {
-            const uint32_t cl = cls_tab[c];
-            const uint32_t e = trans_tab[st * 32 + cl];
+            const uint32_t cl = rd.cls(c);
+            const uint32_t e = rd.trans(st * 32 + cl);
             const uint32_t act = e >> 5;
             const uint32_t prev = st;
             st = e & 31u;
@@ -216,12 +217,30 @@ struct LeanMachine {
     }
 };
 
-// reference implementation of the byte loop (host tests; the bulk kernel has its own word-wise loop)
+// byte source + tables for host code and for device code that reads plain memory
+struct PlainEnv {
+    const uint8_t* a; uint32_t na;          // two-piece rope (carry, chunk)
+    const uint8_t* b; uint32_t nb;
+    const uint8_t* cls_tab; const uint8_t* trans_tab;
+    LGW_HD uint32_t at(uint32_t i) const { return i < na ? a[i] : b[i - na]; }
+    LGW_HD uint32_t cls(uint32_t c) const { return cls_tab[c]; }
+    LGW_HD uint32_t trans(uint32_t i) const { return trans_tab[i]; }
+};
+
+LGW_HD const LeanTables& lean_tables() {
+#if defined(__CUDA_ARCH__)
+    return g_lean_tables_dev;
+#else
+    return g_lean_tables_host;
+#endif
+}
+
+// reference byte loop over [s, e) of an env (the bulk kernel has its own word-wise loop)
 template <class R>
-LGW_HD uint32_t lean_parse(const R& rd, uint32_t s, uint32_t e, bool strip, const uint8_t* cls_tab, const uint8_t* trans_tab) {
+LGW_HD uint32_t lean_parse(const R& rd, uint32_t s, uint32_t e, bool strip) {
     LeanMachine m;
     m.reset(strip);
-    for (uint32_t i = s; i < e; ++i) m.step(rd.at(i), i, rd, cls_tab, trans_tab);
+    for (uint32_t i = s; i < e; ++i) m.step(rd.at(i), i, rd);
     return m.finish();
 }
 

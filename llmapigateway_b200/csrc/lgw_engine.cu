@@ -76,6 +76,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     ALLOC(e->t.carry_a, S * (size_t)e->lim.carry_cap);
     ALLOC(e->t.carry_b, S * (size_t)e->lim.carry_cap);
     ALLOC(e->t.detail, S * (size_t)e->lim.detail_cap);
+    ALLOC(e->t.pending, S * (size_t)LGW_PENDING_CAP);
     e->t.carry_cap = e->lim.carry_cap; e->t.detail_cap = e->lim.detail_cap; e->t.max_streams = e->lim.max_streams;
     ALLOC(e->d_rowq, (size_t)(e->lim.rowq_cap + 1) * sizeof(RowEvent));
     ALLOC(e->d_rowq_count, 16);
@@ -96,7 +97,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
 extern "C" int lgw_engine_destroy(lgw_engine* e) {
     if (!e) return LGW_OK;
     cudaSetDevice(e->device);
-    cudaFree(e->t.state); cudaFree(e->t.carry_a); cudaFree(e->t.carry_b); cudaFree(e->t.detail);
+    cudaFree(e->t.state); cudaFree(e->t.carry_a); cudaFree(e->t.carry_b); cudaFree(e->t.detail); cudaFree(e->t.pending);
     cudaFree(e->d_rowq); cudaFree(e->d_rowq_count); cudaFree(e->d_in); cudaFree(e->d_out);
     cudaFree(e->d_chunk_off); cudaFree(e->d_seg_chunk); cudaFree(e->d_seg_slot); cudaFree(e->d_seg_out);
     cudaFree(e->d_slots); cudaFree(e->d_status); cudaFree(e->d_state_stage);

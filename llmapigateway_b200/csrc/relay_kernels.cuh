@@ -15,60 +15,47 @@
 
 // 16 KB tile in shared memory, swizzled so that 32 lanes reading the same byte position of 32
 // consecutive 64-byte rows (the 64-byte-event pattern) hit 32 different banks, while a 16-byte
-// vector store stays one STS.128 (the four words are permuted inside their own vector).
-__device__ __forceinline__ uint32_t swz(uint32_t off) {
-    const uint32_t r = off >> 6;
-    return (off & ~63u) | ((((off >> 4) & 3u) ^ ((r >> 1) & 3u)) << 4) | ((((off >> 2) & 3u) ^ ((r >> 3) & 3u)) << 2) | (off & 3u);
-}
+// vector store stays one STS.128 (the four words are permuted inside their own vector):
+//   physical offset = d ^ X(d),  X(d) = ((d >> 3) & 0x30) | ((d >> 7) & 0x0c)
+__device__ __forceinline__ uint32_t swz(uint32_t d) { return d ^ (((d >> 3) & 0x30u) | ((d >> 7) & 0x0cu)); }
 
-// per-byte equality of a 32-bit word with a repeated byte -> 4-bit mask (bit k = byte k equal)
-__device__ __forceinline__ uint32_t eq4(uint32_t x, uint32_t pat4) {
-    const uint32_t y = x ^ pat4;
-    const uint32_t t = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);     // 0x80 where the byte is zero
-    return ((t >> 7) * 0x01020408u) >> 24;
-}
-__device__ __forceinline__ uint32_t lf_mask16(const uint4& x) {
-    return eq4(x.x, 0x0a0a0a0au) | (eq4(x.y, 0x0a0a0a0au) << 4) | (eq4(x.z, 0x0a0a0a0au) << 8) | (eq4(x.w, 0x0a0a0a0au) << 12);
-}
+// Shared memory of k_relay, declared at file scope so that device functions index it by name
+// (LDS with an immediate base; a pointer would be rebuilt from the CTA's shared window per access).
+__shared__ __align__(16) uint8_t sh_tile[LGW_TILE_BYTES];
+__shared__ __align__(4) uint8_t sh_cls[256];
+__shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
+__shared__ uint32_t sh_seg_lo, sh_seg_hi;
 
-struct TileReader {
-    const uint8_t* smem;           // swizzled tile
-    const uint32_t* vinfo;         // per 16-byte vector: LF mask | (has byte >= 0x80) << 16
-    const uint8_t* __restrict__ g; // whole packed buffer
+// shared-memory loads by 32-bit shared-window address held in a register (the compiler otherwise
+// rebuilds the CTA's shared-window base -- S2UR SR_CgaCtaId + ULEA -- in front of every access)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+
+// byte source + tables of the bulk kernel: the staged tile, global memory outside it
+struct TileEnv {
+    uint32_t tile_s, cls_s, trans_s;   // shared-window addresses (opaque registers)
+    const uint8_t* __restrict__ g;     // whole packed buffer
     uint32_t t0, n_bytes;
-    __device__ __forceinline__ uint32_t at(uint32_t pos) const {
-        const uint32_t d = pos - t0;
-        return d < LGW_TILE_BYTES ? (uint32_t)smem[swz(d)] : (uint32_t)__ldg(g + pos);
-    }
     // aligned 32-bit word containing byte `pos` (little endian); bytes past n_bytes read as 0
     __device__ __forceinline__ uint32_t word(uint32_t pos) const {
         const uint32_t p4 = pos & ~3u, d = p4 - t0;
-        if (d < LGW_TILE_BYTES) return *reinterpret_cast<const uint32_t*>(smem + swz(d));
+        if (d < LGW_TILE_BYTES) return lds_u32(tile_s + swz(d));
+        return word_global(p4);
+    }
+    __device__ __noinline__ uint32_t word_global(uint32_t p4) const {
         if (p4 + 4 <= n_bytes) return __ldg(reinterpret_cast<const uint32_t*>(g + p4));
         uint32_t w = 0;
         for (uint32_t k = 0; k < 4 && p4 + k < n_bytes; ++k) w |= (uint32_t)__ldg(g + p4 + k) << (8 * k);
         return w;
     }
-    // LF mask / high flag of the 16-byte vector number V (= byte offset >> 4)
-    __device__ __forceinline__ uint32_t vec_info(uint32_t V) const {
-        const uint32_t d = V - (t0 >> 4);
-        if (d < LGW_TILE_VECS) return vinfo[d];
-        const uint32_t p = V << 4;
-        if (p >= n_bytes) return 0;
-        uint32_t m = 0, hi = 0;
-        if (p + 16 <= n_bytes) {
-            const uint4 x = __ldg(reinterpret_cast<const uint4*>(g + p));
-            m = lf_mask16(x); hi = ((x.x | x.y | x.z | x.w) & 0x80808080u) ? 1u : 0u;
-        } else {
-            for (uint32_t k = 0; p + k < n_bytes; ++k) { const uint32_t c = __ldg(g + p + k); if (c == '\n') m |= 1u << k; if (c >= 0x80) hi = 1; }
-        }
-        return m | (hi << 16);
-    }
-    __device__ __forceinline__ bool lf_at(uint32_t pos) const { return (vec_info(pos >> 4) >> (pos & 15)) & 1u; }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (word(pos) >> (8 * (pos & 3u))) & 0xffu; }
+    __device__ __forceinline__ uint32_t cls(uint32_t c) const { return lds_u8(cls_s + c); }
+    __device__ __forceinline__ uint32_t trans(uint32_t i) const { return lds_u8(trans_s + i); }
 };
 
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
-__device__ __noinline__ bool chunk_utf8_ok(const TileReader* rd, uint32_t o, uint32_t e) {
+__device__ __noinline__ bool chunk_utf8_ok(const TileEnv* rd, uint32_t o, uint32_t e) {
     uint32_t p = o;
     while (p < e) {
         const uint32_t ch = rd->at(p);
@@ -94,7 +81,7 @@ __device__ __noinline__ bool chunk_utf8_ok(const TileReader* rd, uint32_t o, uin
 
 // rare path: where does the event that is open at byte o begin?  (o is not right after a separator)
 // returns false when the stream must go to the sequential path
-__device__ __noinline__ bool find_open_event_start(const TileReader* rd, uint32_t o, uint32_t relay_begin, uint32_t seg_end, uint32_t carry_cap, uint32_t* out_b) {
+__device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o, uint32_t relay_begin, uint32_t seg_end, uint32_t carry_cap, uint32_t* out_b) {
     uint32_t k = o;
     bool found = false;
     const uint32_t limit = (o - relay_begin > carry_cap + 2) ? o - carry_cap - 2 : relay_begin;
@@ -151,29 +138,24 @@ __global__ void __launch_bounds__(64) k_prime(StepArgs a, uint32_t n_tiles) {
 
 // ---- k_relay ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a) {
-    __shared__ __align__(16) uint8_t tile[LGW_TILE_BYTES];
-    __shared__ uint32_t vinfo[LGW_TILE_VECS];
-    __shared__ __align__(4) uint8_t s_cls[256];
-    __shared__ __align__(4) uint8_t s_trans[LGW_LEAN_ROWS * 32];
-    __shared__ uint32_t s_seg_lo, s_seg_hi;
-
     const uint32_t t0 = blockIdx.x * LGW_TILE_BYTES;
     const uint32_t tid = threadIdx.x;
     const uint32_t n_bytes = a.n_bytes;
     const uint32_t c_lo = a.s.tile_chunk[blockIdx.x], c_hi = a.s.tile_chunk[blockIdx.x + 1];
 
     // (0) tables + segment range of this tile's chunks
-    if (tid < 64) reinterpret_cast<uint32_t*>(s_cls)[tid] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[tid];
-    else if (tid < 64 + LGW_LEAN_ROWS * 8) reinterpret_cast<uint32_t*>(s_trans)[tid - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[tid - 64];
+    if (tid < 64) reinterpret_cast<uint32_t*>(sh_cls)[tid] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[tid];
+    else if (tid < 64 + LGW_LEAN_ROWS * 8) reinterpret_cast<uint32_t*>(sh_trans)[tid - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[tid - 64];
     if (tid >= 224 && tid < 226 && c_hi > c_lo) {
         const uint32_t c = tid == 224 ? c_lo : c_hi - 1;
         uint32_t lo = 0, hi = a.n_segs;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
-        if (tid == 224) s_seg_lo = lo; else s_seg_hi = lo;
+        if (tid == 224) sh_seg_lo = lo; else sh_seg_hi = lo;
     }
 
-    // (1) re-emit: position-preserving 16-byte copy of the tile, staged into shared memory on the
-    //     way; LF bit mask and high-byte flag of every vector for the event discovery below
+    // (1) re-emit: position-preserving 16-byte copy of the tile, staged (swizzled) into shared memory
+    //     on the way; note whether the tile has any byte >= 0x80 (UTF-8 checks are skipped otherwise)
+    uint32_t high = 0;
     {
         const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
         uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
@@ -190,10 +172,15 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a) {
             if (pos + 16 <= n_bytes) {
                 dst[v] = x[k];
             } else if (pos < n_bytes) {                        // ragged end of the buffer
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (uint32_t b = pos; b < n_bytes; ++b) { const uint32_t c = a.data[b]; a.out[b] = (uint8_t)c; w[(b - pos) >> 2] |= c << (8 * ((b - pos) & 3)); }
-                x[k] = make_uint4(w[0], w[1], w[2], w[3]);
+                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                for (uint32_t b = pos; b < n_bytes; ++b) {
+                    const uint32_t c = a.data[b]; a.out[b] = (uint8_t)c;
+                    const uint32_t sh = c << (8 * ((b - pos) & 3)), wi = (b - pos) >> 2;
+                    if (wi == 0) w0 |= sh; else if (wi == 1) w1 |= sh; else if (wi == 2) w2 |= sh; else w3 |= sh;
+                }
+                x[k] = make_uint4(w0, w1, w2, w3);
             }
+            high |= x[k].x | x[k].y | x[k].z | x[k].w;
             const uint32_t r = v >> 2;                          // 64-byte row
             const uint32_t kx = (r >> 3) & 3u;                  // word permutation inside the vector
             uint4 y;
@@ -202,15 +189,18 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a) {
             y.z = kx == 0 ? x[k].z : kx == 1 ? x[k].w : kx == 2 ? x[k].x : x[k].y;
             y.w = kx == 0 ? x[k].w : kx == 1 ? x[k].z : kx == 2 ? x[k].y : x[k].x;
             const uint32_t slot16 = (r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4);
-            *reinterpret_cast<uint4*>(tile + slot16) = y;
-            vinfo[v] = lf_mask16(x[k]) | ((((x[k].x | x[k].y | x[k].z | x[k].w) & 0x80808080u) ? 1u : 0u) << 16);
+            *reinterpret_cast<uint4*>(sh_tile + slot16) = y;
         }
     }
-    __syncthreads();
+    const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
 
     // (2) events of the chunks that START in this tile
-    const TileReader rd{tile, vinfo, a.data, t0, n_bytes};
-    const uint32_t seg_lo = s_seg_lo, seg_hi = s_seg_hi;
+    TileEnv env;
+    env.tile_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tile));
+    env.cls_s = opaque((uint32_t)__cvta_generic_to_shared(sh_cls));
+    env.trans_s = opaque((uint32_t)__cvta_generic_to_shared(sh_trans));
+    env.g = a.data; env.t0 = t0; env.n_bytes = n_bytes;
+    const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
     uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
 
     for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
@@ -230,79 +220,71 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a) {
             acc_seg = seg; ev_a = ev_b = 0;
         }
 
-        // chunk-level UTF-8: only when some vector of the chunk has a byte >= 0x80
-        {
-            uint32_t hi_any = 0;
-            for (uint32_t V = o >> 4; V <= (e - 1) >> 4; ++V) hi_any |= rd.vec_info(V) >> 16;
-            if (hi_any && !chunk_utf8_ok(&rd, o, e)) { pl->irregular = 1; continue; }
-        }
+        // chunk-level UTF-8: ASCII tiles need no check for chunks that end inside the tile
+        if ((tile_high || e > t0 + LGW_TILE_BYTES) && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
 
         // where does the event that is open at the start of this chunk begin?
         uint32_t b = o;
         if (o != relay_begin) {
-            const bool sep_before = o >= relay_begin + 2 && rd.lf_at(o - 1) && rd.lf_at(o - 2);
+            const bool sep_before = o >= relay_begin + 2 && env.at(o - 1) == '\n' && env.at(o - 2) == '\n';
             if (sep_before) {
-                if ((o >= relay_begin + 3 && rd.lf_at(o - 3)) || rd.lf_at(o)) { pl->irregular = 1; continue; }   // LF run >= 3
-            } else if (!find_open_event_start(&rd, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; continue; }
+                if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; continue; }   // LF run >= 3
+            } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; continue; }
         }
 
-        // separators whose second LF lies in [o, e): first LF i in [max(b, o-1), e-2]
+        // walk the events that complete inside this chunk (second LF of the separator in [o, e))
         bool irregular = false;
         uint32_t us_b = 0, a_usage = 0, last_usage = 0;
         uint32_t ps = b;
-        const uint32_t i_min = (o > b) ? o - 1 : b;
-        if (e >= 2 && i_min + 2 <= e) {
-            const uint32_t i_max = e - 2;
-            for (uint32_t V = i_min >> 4; V <= (i_max >> 4) && !irregular; ++V) {
-                const uint32_t m = (rd.vec_info(V) & 0xFFFFu) | ((rd.vec_info(V + 1) & 3u) << 16);
-                uint32_t pairs = m & (m >> 1) & 0xFFFFu;
-                const uint32_t base = V << 4;
-                if (base < i_min) pairs &= ~((1u << (i_min - base)) - 1u);
-                if (base + 15 > i_max) pairs &= (2u << (i_max - base)) - 1u;
-                const uint32_t triples = pairs & (m >> 2);
-                while (pairs) {
-                    const uint32_t k = __ffs(pairs) - 1; pairs &= pairs - 1;
-                    const uint32_t i = base + k;
-                    if (((triples >> k) & 1u) && i + 2 < seg_end) { irregular = true; break; }
-                    if (i < ps) continue;                       // second half of an overlapping pair cannot happen without a triple
-                    // ---- one complete event [ps, i) ----
-                    const uint32_t len = i - ps;
-                    uint32_t cls = PC_NONE;
-                    if (len >= 1) {
-                        const uint32_t w0 = rd.word(ps) >> (8 * (ps & 3));
-                        if ((w0 & 0xff) == '{') cls = PC_BRACE;
-                        else if ((w0 & 0xff) == 'd' && len >= 7) {
-                            if ((ps & 3) == 0) cls = (w0 == 0x61746164u && (rd.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
-                            else cls = (rd.at(ps + 1) == 'a' && rd.at(ps + 2) == 't' && rd.at(ps + 3) == 'a' && rd.at(ps + 4) == ':' && rd.at(ps + 5) == ' ' && rd.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
-                        }
-                    }
-                    if (cls != PC_NONE) {
-                        LeanMachine lm;
-                        lm.reset(cls == PC_DATA);
-                        uint32_t pos = ps + (cls == PC_DATA ? 6u : 0u);
-                        while (pos < i) {                        // word-wise byte loop
-                            uint32_t w = rd.word(pos) >> (8 * (pos & 3));
-                            uint32_t nb = 4 - (pos & 3);
-                            if (nb > i - pos) nb = i - pos;
-#pragma unroll 1
-                            for (uint32_t q = 0; q < nb; ++q, ++pos, w >>= 8) lm.step(w & 0xffu, pos, rd, s_cls, s_trans);
-                        }
-                        uint32_t f = lm.finish();
-                        if (cls == PC_DATA) {                    // handler loop, request_handler.py:122-134
-                            ++ev_a;
-                            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
-                        }
-                        if (f & PF_VALID_B) {                    // tap loop, chat_logging.py:123-141
-                            ++ev_b;
-                            // events with "error" (extra DB row) go to the sequential path; a "usage" event is
-                            // a candidate that k_commit validates with the full machine (choices walk)
-                            if (f & TK_ERROR) { irregular = true; break; }
-                            if (f & TK_USAGE) { ++us_b; last_usage = ps + 1; }
-                        }
-                    }
-                    ps = i + 2;
+        while (ps < e) {
+            // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
+            uint32_t cls = PC_NONE;
+            {
+                const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
+                if ((w0 & 0xffu) == '{') cls = PC_BRACE;
+                else if ((w0 & 0xffu) == 'd') {
+                    if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
+                    else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
                 }
             }
+            LeanMachine lm;
+            lm.reset(cls == PC_DATA);
+            uint32_t pos = ps + (cls == PC_DATA ? 6u : 0u);      // "data: " holds no LF
+            bool ended = false;
+            while (pos < e && !ended) {                          // word-wise byte loop
+                uint32_t w = env.word(pos) >> (8 * (pos & 3u));
+                uint32_t nb = 4 - (pos & 3u);
+                if (nb > e - pos) nb = e - pos;
+#pragma unroll 1
+                for (; nb; --nb, w >>= 8, ++pos) {
+                    const uint32_t ch = w & 0xffu;
+                    // hot path: a plain byte inside a string changes nothing
+                    if (lm.st == L_STR && ch >= 0x20u && ch != '"' && ch != '\\') continue;
+                    if (ch == '\n') {
+                        if (pos + 1 >= e) { pos = e; break; }     // a separator starting on the last byte completes later
+                        if (env.at(pos + 1) == '\n') { ended = true; break; }
+                    }
+                    if (cls != PC_NONE) lm.step(ch, pos, env);
+                }
+            }
+            if (!ended) break;                                   // the open event completes in a later chunk
+            // ---- one complete event [ps, pos) ----
+            if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
+            if (cls != PC_NONE) {
+                const uint32_t f = lm.finish();
+                if (cls == PC_DATA) {                            // handler loop, request_handler.py:122-134
+                    ++ev_a;
+                    if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
+                }
+                if (f & PF_VALID_B) {                            // tap loop, chat_logging.py:123-141
+                    ++ev_b;
+                    // events with "error" (extra DB row) go to the sequential path; a "usage" event is
+                    // a candidate that k_commit validates with the full machine (choices walk)
+                    if (f & TK_ERROR) { irregular = true; break; }
+                    if (f & TK_USAGE) { ++us_b; last_usage = ps + 1; }
+                }
+            }
+            ps = pos + 2;
         }
         if (irregular) { pl->irregular = 1; continue; }
         if (us_b) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage_pos, last_usage); }
@@ -339,27 +321,23 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
     if (st.phase == PH_COMMITTED && p.resume_chunk < c1) {
         const uint8_t* __restrict__ d = a.data;
         bool sequential = p.irregular || p.n_usage_b > 1;      // several usage candidates: let the exact path count them
-        UsageRaw raw; uint32_t uf = 0;
-        if (!sequential && p.last_usage_pos) {                  // validate the candidate with the full machine
-            const uint32_t ps = p.last_usage_pos - 1;
-            uint32_t pe = ps;
-            while (pe + 1 < p.seg_end && !(__ldg(d + pe) == '\n' && __ldg(d + pe + 1) == '\n')) ++pe;
-            Rope r{nullptr, 0, d + ps, pe - ps};
-            const uint8_t cls = classify_part(r, 0, pe - ps);
-            uf = parse_part<true>(r, 0, pe - ps, cls, &raw);
-            if ((uf & PF_EXOTIC) || ((uf & TK_CHOICES) && (uf & PF_TYPE_ERROR))) sequential = true;
+        uint32_t ups = 0, upe = 0;
+        if (!sequential && p.last_usage_pos) {                  // the winning usage event: [ups, upe)
+            ups = p.last_usage_pos - 1; upe = ups;
+            while (upe + 1 < p.seg_end && !(__ldg(d + upe) == '\n' && __ldg(d + upe + 1) == '\n')) ++upe;
+            if (upe - ups > LGW_PENDING_CAP) sequential = true;
         }
         if (sequential) {
             run_chunks(io, a.data, a.chunk_off, p.resume_chunk, c1, emit_begin, false);
         } else {
             const uint32_t nch = c1 - p.resume_chunk, nby = p.seg_end - p.relay_begin;
             st.n_chunks_in += nch; st.n_chunks_emitted += nch; st.bytes_in += nby; st.bytes_emitted += nby;
-            st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b; st.n_usage_b += p.n_usage_b;
+            st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b;
             if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
-            if (p.last_usage_pos) {                 // the last usage-bearing event wins (chat_logging.py:134-135)
-                normalise_usage(raw, uf, *io.rec);
-                st.flags |= SF_REC_VALID;
-                if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+            if (p.last_usage_pos) {                 // the last usage-bearing event wins (chat_logging.py:134-135):
+                if (st.flags & SF_PENDING) resolve_pending(io);     // an older stash must be settled first
+                for (uint32_t k = 0; k < upe - ups; ++k) io.pending[k] = __ldg(d + ups + k);    // stash its text;
+                st.pending_len = upe - ups; st.flags |= SF_PENDING; ++st.n_usage_b;               // values on demand
             }
             // new carry = text after the last separator (both loops: SF_SYNCED)
             uint32_t tail = p.relay_begin;

@@ -18,7 +18,7 @@ namespace lgw {
 
 struct DeviceTables {
     StreamState* state;
-    uint8_t* carry_a; uint8_t* carry_b; uint8_t* detail;
+    uint8_t* carry_a; uint8_t* carry_b; uint8_t* detail; uint8_t* pending;
     uint32_t carry_cap, detail_cap, max_streams;
 };
 
@@ -65,6 +65,7 @@ __device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot, Stre
     StepIO io;
     io.st = local_hdr;
     io.rec = &a.t.state[slot].rec;
+    io.pending = a.t.pending + (size_t)slot * LGW_PENDING_CAP;
     io.carry_a = a.t.carry_a + (size_t)slot * a.t.carry_cap;
     io.carry_b = a.t.carry_b + (size_t)slot * a.t.carry_cap;
     io.detail = a.t.detail + (size_t)slot * a.t.detail_cap;
@@ -83,7 +84,17 @@ __global__ void k_streams_open(DeviceTables t, const uint32_t* slots, const int3
 __global__ void k_streams_gather(DeviceTables t, const uint32_t* slots, uint32_t n, StreamState* out, int free_after) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    StreamState* s = t.state + slots[i];
+    const uint32_t slot = slots[i];
+    StreamState* s = t.state + slot;
+    if (s->h.flags & SF_PENDING) {            // extract the stashed usage event now (deferred by the bulk path)
+        StreamHdr st = s->h;
+        StepIO io;
+        io.st = &st; io.rec = &s->rec; io.pending = t.pending + (size_t)slot * LGW_PENDING_CAP;
+        io.carry_a = io.carry_b = io.detail = nullptr; io.carry_cap = io.detail_cap = 0;
+        io.rowq = nullptr; io.rowq_count = nullptr; io.rowq_cap = 0; io.slot = slot;
+        resolve_pending(io);
+        s->h = st;
+    }
     out[i] = *s;
     if (free_after) s->h.phase = PH_FREE;
 }

@@ -15,8 +15,11 @@
 // Host/device portable (tests compile it with g++ as a test aid; the product has no CPU path).
 #pragma once
 #include "json_machine.cuh"
+#include "lean_json.cuh"
 
 namespace lgw {
+
+#define LGW_PENDING_CAP 1024u
 
 enum Phase : uint8_t { PH_FREE = 0, PH_PRIMING = 1, PH_COMMITTED = 2, PH_FAILED = 3 };
 enum Verdict : uint8_t {
@@ -34,7 +37,8 @@ enum StreamFlag : uint16_t {
     SF_SYNCED = 1 << 4,          // carry A == carry B (only carry A is stored)
     SF_REC_VALID = 1 << 5,       // `rec` holds a get_token_usage result
     SF_DETAIL_TRUNC = 1 << 6,
-    SF_ROWQ_OVERFLOW = 1 << 7
+    SF_ROWQ_OVERFLOW = 1 << 7,
+    SF_PENDING = 1 << 8          // a usage event's text is stashed; its values are extracted on demand
 };
 
 // get_token_usage's result (chat_logging.py:233-272).  Absent model/provider => key not in dict.
@@ -58,7 +62,7 @@ struct StreamHdr {            // the 64 hot bytes of a stream's state (kernels w
     uint32_t n_exotic;
     uint32_t n_error_rows;     // tap "error" events => extra rows (chat_logging.py:137-139)
     uint32_t n_chunks_in, n_chunks_emitted;
-    uint32_t _pad;
+    uint32_t pending_len;      // bytes of stashed usage event (SF_PENDING)
     uint64_t bytes_in, bytes_emitted;
 };
 struct StreamState {          // == lgw_stream_state
@@ -123,9 +127,9 @@ LGW_HD uint8_t classify_part(const Rope& r, uint32_t s, uint32_t e) {
             r.at(s + 5) == ' ' && r.at(s + 6) == '{') ? PC_DATA : PC_NONE;
 }
 
-// parse one classified part; returns TopKey|PartFlag bits
+// full machine over one classified part; returns TopKey|PartFlag bits
 template <bool EXTRACT>
-LGW_HD uint32_t parse_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, UsageRaw* raw) {
+LGW_HD_NOINLINE uint32_t parse_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, UsageRaw* raw) {
     JsonMachine<EXTRACT> m;
     m.reset(raw, cls == PC_DATA);
     uint32_t i = s + (cls == PC_DATA ? 6u : 0u);
@@ -134,6 +138,21 @@ LGW_HD uint32_t parse_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, U
         if (m.failed()) break;
     }
     return m.finish();
+}
+
+// lean recogniser over one classified part: validity + error/detail/code/usage (lean_json.cuh)
+LGW_HD uint32_t lean_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls) {
+    const LeanTables& t = lean_tables();
+    PlainEnv env{r.a, r.na, r.b, r.nb, t.cls, t.trans};
+    return lean_parse(env, s + (cls == PC_DATA ? 6u : 0u), e, cls == PC_DATA);
+}
+
+// what the tap needs of one part: lean first; the full machine (choices walk, usage values) only
+// for the rare events that carry "usage" or "error"
+LGW_HD uint32_t tap_parse(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, UsageRaw* raw) {
+    uint32_t f = lean_part(r, s, e, cls);
+    if ((f & PF_VALID_B) && (f & (TK_USAGE | TK_ERROR))) f = parse_part<true>(r, s, e, cls, raw);
+    return f;
 }
 
 // ---- get_token_usage arithmetic (chat_logging.py:246-267) --------------------------------------
@@ -254,6 +273,7 @@ LGW_HD bool store_carry(uint8_t* carry, uint32_t& carry_len, uint32_t cap, const
 struct StepIO {                 // where one stream's step reads and writes
     StreamHdr* st;              // usually a local copy, written back by the caller
     UsageRec* rec;              // the stream's tap record (global memory)
+    uint8_t* pending;           // stashed usage event text (LGW_PENDING_CAP bytes)
     uint8_t* carry_a; uint8_t* carry_b; uint8_t* detail;
     uint32_t carry_cap, detail_cap;
     RowEvent* rowq; uint32_t* rowq_count; uint32_t rowq_cap;
@@ -298,6 +318,25 @@ LGW_HD void tap_part(const StepIO& io, uint32_t f, const UsageRaw& raw) {
     if (f & TK_ERROR) push_row(io);
 }
 
+// The bulk path stashes the text of the stream's winning usage event instead of extracting its
+// values on the spot (k_commit); this is the deferred chat_logging.py:134-135 for that event.
+LGW_HD_NOINLINE void resolve_pending(const StepIO& io) {
+    StreamHdr& st = *io.st;
+    if (!(st.flags & SF_PENDING)) return;
+    st.flags &= ~(uint16_t)SF_PENDING;
+    const uint32_t n = st.pending_len;
+    st.pending_len = 0;
+    Rope r{nullptr, 0, io.pending, n};
+    const uint8_t cls = classify_part(r, 0, n);
+    UsageRaw raw;
+    const uint32_t f = parse_part<true>(r, 0, n, cls, &raw);
+    if (f & PF_EXOTIC) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; --st.n_usage_b; return; }
+    if ((f & TK_CHOICES) && (f & PF_TYPE_ERROR)) { --st.n_usage_b; return; }
+    normalise_usage(raw, f, *io.rec);
+    st.flags |= SF_REC_VALID;
+    if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+}
+
 LGW_HD void handler_part(StreamHdr& st, uint32_t f) {       // request_handler.py:122-134
     ++st.n_events_a;
     if (!(f & PF_VALID_A)) return;
@@ -319,7 +358,7 @@ LGW_HD void relay_chunk(const StepIO& io, const uint8_t* p, uint32_t n, bool tap
         const uint32_t tail = split_scan(r, [&](uint32_t s, uint32_t e) {
             const uint8_t cls = classify_part(r, s, e);
             if (cls == PC_NONE) return true;
-            const uint32_t f = parse_part<true>(r, s, e, cls, &raw);
+            const uint32_t f = tap_parse(r, s, e, cls, &raw);
             if (cls == PC_DATA) handler_part(st, f);
             tap_part(io, f, raw);
             return true; }, stopped);
@@ -333,7 +372,7 @@ LGW_HD void relay_chunk(const StepIO& io, const uint8_t* p, uint32_t n, bool tap
         const uint32_t tail = split_scan(r, [&](uint32_t s, uint32_t e) {
             const uint8_t cls = classify_part(r, s, e);
             if (cls != PC_DATA) return true;
-            handler_part(st, parse_part<false>(r, s, e, cls, nullptr));
+            handler_part(st, lean_part(r, s, e, cls));
             return true; }, stopped);
         if (tail != 0) qa = tail - st.carry_a_len;
         if (!store_carry(io.carry_a, st.carry_a_len, io.carry_cap, r, tail)) st.flags |= SF_CARRY_OVERFLOW;
@@ -345,7 +384,7 @@ LGW_HD void relay_chunk(const StepIO& io, const uint8_t* p, uint32_t n, bool tap
         const uint32_t tail = split_scan(r, [&](uint32_t s, uint32_t e) {
             const uint8_t cls = classify_part(r, s, e);
             if (cls == PC_NONE) return true;
-            const uint32_t f = parse_part<true>(r, s, e, cls, &raw);
+            const uint32_t f = tap_parse(r, s, e, cls, &raw);
             tap_part(io, f, raw);
             return true; }, stopped);
         if (tail != 0) qb = tail - st.carry_b_len;
@@ -365,7 +404,7 @@ LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
     const uint32_t tail = split_scan(r, [&](uint32_t s, uint32_t e) {
         const uint8_t cls = classify_part(r, s, e);
         if (cls != PC_DATA) return true;
-        const uint32_t f = parse_part<false>(r, s, e, cls, nullptr);
+        const uint32_t f = lean_part(r, s, e, cls);
         ++st.n_events_a;
         if (!(f & PF_VALID_A)) { st.phase = PH_FAILED; st.verdict = VD_FAIL_PARSE; save_detail(io, r, s, e); }
         else if (f & (TK_ERROR | TK_DETAIL)) { st.phase = PH_FAILED; st.verdict = VD_FAIL_EVENT; save_detail(io, r, s, e); }
@@ -385,6 +424,7 @@ LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
 LGW_HD uint32_t run_chunks(const StepIO& io, const uint8_t* data, const uint32_t* chunk_off,
                            uint32_t c_from, uint32_t c_to, uint32_t& emit_begin, bool stop_at_commit) {
     StreamHdr& st = *io.st;
+    if (st.flags & SF_PENDING) resolve_pending(io);          // the sequential path works on extracted records
     for (uint32_t c = c_from; c < c_to; ++c) {
         const uint32_t o = chunk_off[c], n = chunk_off[c + 1] - o;
         if (n == 0) continue;                                   // never yielded (request_handler.py:60-63)
@@ -430,7 +470,7 @@ LGW_HD void init_stream(StreamState& s, int http_status) {
     st.verdict = http_status >= 400 ? VD_FAIL_HTTP : VD_NONE;
     st.flags = 0; st.carry_a_len = st.carry_b_len = st.detail_len = 0;
     st.n_events_a = st.n_events_b = st.n_usage_b = st.n_exotic = st.n_error_rows = 0;
-    st.n_chunks_in = st.n_chunks_emitted = 0; st._pad = 0; st.bytes_in = st.bytes_emitted = 0;
+    st.n_chunks_in = st.n_chunks_emitted = 0; st.pending_len = 0; st.bytes_in = st.bytes_emitted = 0;
     default_usage(s.rec);
 }
 

@@ -6,7 +6,6 @@
 #include <vector>
 #include "../../include/llmgw_b200.h"
 #include "../../llmapigateway_b200/csrc/stream_machine.cuh"
-#include "../../llmapigateway_b200/csrc/lean_json.cuh"
 
 using namespace lgw;
 
@@ -40,7 +39,8 @@ uint32_t lgwt_lean_parse(const uint8_t* text, uint32_t n) {
     Rope r{nullptr, 0, text, n};
     const uint8_t cls = classify_part(r, 0, n);
     if (cls == PC_NONE) return 0;
-    return lean_parse(r, cls == PC_DATA ? 6u : 0u, n, cls == PC_DATA, g_lean_tables_host.cls, g_lean_tables_host.trans);
+    PlainEnv env{nullptr, 0, text, n, g_lean_tables_host.cls, g_lean_tables_host.trans};
+    return lean_parse(env, cls == PC_DATA ? 6u : 0u, n, cls == PC_DATA);
 }
 
 int lgwt_utf8_valid(const uint8_t* p, uint32_t n) { return utf8_valid(p, n) ? 1 : 0; }
@@ -54,10 +54,10 @@ int lgwt_run_stream(const uint8_t* data, const uint32_t* chunk_off, const uint32
                     uint8_t* detail_out, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
     StreamState st;
     init_stream(st, http_status);
-    std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1);
+    std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1), pend(LGW_PENDING_CAP);
     std::vector<RowEvent> rq(rows_cap + 1);
     uint32_t rcount = 0;
-    StepIO io{&st.h, &st.rec, ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
+    StepIO io{&st.h, &st.rec, pend.data(), ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
     for (uint32_t k = 0; k < n_steps; ++k) {
         SegResult res;
         run_segment(io, data, chunk_off, step_chunk[k], step_chunk[k + 1], res);
