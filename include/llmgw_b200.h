@@ -181,6 +181,50 @@ int lgw_last_step_ms(lgw_engine* e, float ms[4]);
 /* number of kernels launched by this engine since creation */
 int lgw_launch_count(lgw_engine* e, uint64_t* out);
 
+/* ---- usage-stats rollup -----------------------------------------------------------------------------
+ * Replaces the scan inside TokensUsageDB.get_aggregated_usage (llm_gateway_core/db/tokens_usage_db.py:222-304,
+ * SQL at :268-286): GROUP BY strftime(fmt, timestamp), model; SUM of the five token columns, SUM(cost),
+ * COUNT(*); optional window on timestamp (:255-266).  Records are device-resident SoA columns
+ * (40 B per record): ts_us = microseconds of the naive local timestamp the reference stores
+ * (:135), model_rank = 0 for NULL else 1 + rank of the model name in byte order.
+ * period: 0 hour, 1 day, 2 week ('%Y-W%W'), 3 month.  Bucket numbering: see lgw_rollup_row.bucket.
+ *
+ * lgw_usage_rollup_accum adds the records into a dense table of 64-bit integer cells
+ * [n_buckets][n_models][LGW_ROLLUP_CELLS] (d_table, zeroed by the caller) -- every cell is an
+ * integer sum, so tables from several GPUs merge with an element-wise add (ncclAllReduce sum) --
+ * and lgw_usage_rollup_emit turns a table into rows ordered like the SQL (time_period DESC, model ASC). */
+#define LGW_ROLLUP_CELLS 10
+typedef struct lgw_rollup_row {
+    int64_t bucket;          /* hour: hours since 1970-01-01T00; day: days since 1970-01-01;
+                                week: year*64 + %W; month: year*12 + month-1 */
+    int32_t model_rank;
+    uint32_t inexact;        /* 1: some cost in the group had bits below 2^-80 (sum not exact) */
+    int64_t prompt_tokens, completion_tokens, total_tokens, reasoning_tokens, cached_tokens;
+    double cost;
+    int64_t count;
+} lgw_rollup_row;
+
+int lgw_usage_rollup_accum(lgw_engine* e, const int64_t* d_ts_us, const int32_t* d_model_rank,
+                           const int32_t* d_prompt, const int32_t* d_completion, const int32_t* d_total,
+                           const int32_t* d_reasoning, const int32_t* d_cached, const double* d_cost, uint64_t n,
+                           int period, int has_start, int64_t start_us, int has_end, int64_t end_us,
+                           int64_t bucket0, uint32_t n_buckets, uint32_t n_models,
+                           uint64_t* d_table, uint32_t* d_inexact, uint32_t* d_out_of_table);
+int lgw_usage_rollup_emit(lgw_engine* e, const uint64_t* d_table, const uint32_t* d_inexact,
+                          int64_t bucket0, uint32_t n_buckets, uint32_t n_models,
+                          lgw_rollup_row* rows_out /* host */, uint64_t rows_cap, uint64_t* n_rows);
+/* bucket index of one timestamp (host helper, same arithmetic as the kernel) */
+int64_t lgw_rollup_bucket_of(int64_t ts_us, int period);
+/* device time of the last accum / emit kernels, milliseconds */
+int lgw_rollup_last_ms(lgw_engine* e, float ms[2]);
+
+/* ---- device memory helpers for callers without their own CUDA allocator ----------------------------- */
+int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out);
+int lgw_device_free(lgw_engine* e, void* p);
+int lgw_device_upload(lgw_engine* e, void* d_dst, const void* h_src, uint64_t bytes);
+int lgw_device_download(lgw_engine* e, void* h_dst, const void* d_src, uint64_t bytes);
+int lgw_device_zero(lgw_engine* e, void* d_dst, uint64_t bytes);
+
 /* ---- pinned staging buffers (SURVEY 8(b) ownership) -------------------------------------------- */
 int lgw_alloc_pinned(lgw_engine* e, uint64_t bytes, void** out);
 int lgw_free_pinned(lgw_engine* e, void* p);

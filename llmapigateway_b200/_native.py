@@ -14,6 +14,8 @@ EXPORTS = [
     "lgw_streams_open", "lgw_streams_state", "lgw_stream_detail", "lgw_streams_close",
     "lgw_sse_step", "lgw_sse_step_device", "lgw_fetch_rows", "lgw_sync", "lgw_last_step_ms",
     "lgw_launch_count", "lgw_alloc_pinned", "lgw_free_pinned",
+    "lgw_usage_rollup_accum", "lgw_usage_rollup_emit", "lgw_rollup_bucket_of", "lgw_rollup_last_ms",
+    "lgw_device_alloc", "lgw_device_free", "lgw_device_upload", "lgw_device_download", "lgw_device_zero",
 ]
 
 _lib = None
@@ -53,6 +55,17 @@ def load():
     lib.lgw_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.lgw_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lgw_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lgw_usage_rollup_accum.argtypes = [C.c_void_p] + [C.c_void_p] * 8 + [C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64,
+                                           C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lgw_usage_rollup_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.lgw_rollup_bucket_of.argtypes = [C.c_int64, C.c_int]
+    lib.lgw_rollup_bucket_of.restype = C.c_int64
+    lib.lgw_rollup_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 2)]
+    lib.lgw_device_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lgw_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lgw_device_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lgw_device_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lgw_device_zero.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     if hasattr(lib, "lgw_engine_set_mode"):
         lib.lgw_engine_set_mode.argtypes = [C.c_void_p, C.c_int]
     if lib.lgw_abi_version() != 1:

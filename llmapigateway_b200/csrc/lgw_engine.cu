@@ -9,6 +9,7 @@
 #include "../../include/llmgw_b200.h"
 #include "stream_machine.cuh"
 #include "sse_kernels.cuh"
+#include "rollup.cuh"
 
 using namespace lgw;
 
@@ -17,6 +18,7 @@ static_assert(sizeof(UsageRec) == sizeof(lgw_usage_rec), "lgw_usage_rec layout")
 static_assert(sizeof(StreamState) == sizeof(lgw_stream_state), "lgw_stream_state layout");
 static_assert(sizeof(RowEvent) == sizeof(lgw_row_event), "lgw_row_event layout");
 static_assert(sizeof(SegResult) == sizeof(lgw_seg_result), "lgw_seg_result layout");
+static_assert(sizeof(RollupRow) == sizeof(lgw_rollup_row), "lgw_rollup_row layout");
 
 static thread_local std::string g_create_error;
 
@@ -34,6 +36,9 @@ struct lgw_engine {
     SegResult* d_seg_out = nullptr;
     uint32_t* d_slots = nullptr; int32_t* d_status = nullptr; StreamState* d_state_stage = nullptr;
     cudaEvent_t ev[6]{};
+    cudaEvent_t rev[4]{};
+    float rms[2]{0, 0};
+    RollupRow* d_rows = nullptr; uint64_t d_rows_cap = 0; unsigned long long* d_nrows = nullptr;
     float ms[4]{0, 0, 0, 0};
     bool timed = false;
     uint64_t launches = 0;
@@ -70,6 +75,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     if ((r = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", r);
     e->stream = e->own_stream;
     for (auto& ev : e->ev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
+    for (auto& ev : e->rev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
     const size_t S = e->lim.max_streams, C = e->lim.max_step_chunks, B = e->lim.max_step_bytes;
 #define ALLOC(ptr, bytes) if ((r = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return fail("cudaMalloc " #ptr, r)
     ALLOC(e->t.state, S * sizeof(StreamState));
@@ -103,6 +109,8 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     cudaFree(e->d_slots); cudaFree(e->d_status); cudaFree(e->d_state_stage);
     scratch_free(e->scratch);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->rev) if (ev) cudaEventDestroy(ev);
+    cudaFree(e->d_rows); cudaFree(e->d_nrows);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return LGW_OK;
@@ -270,5 +278,100 @@ extern "C" int lgw_alloc_pinned(lgw_engine* e, uint64_t bytes, void** out) {
 extern "C" int lgw_free_pinned(lgw_engine* e, void* p) {
     if (!e) return LGW_ERR_ARG;
     CK(e, cudaFreeHost(p));
+    return LGW_OK;
+}
+
+// ---- usage-stats rollup ----------------------------------------------------------------------------
+extern "C" int64_t lgw_rollup_bucket_of(int64_t ts_us, int period) { return bucket_of(ts_us, period); }
+
+extern "C" int lgw_usage_rollup_accum(lgw_engine* e, const int64_t* d_ts_us, const int32_t* d_model_rank,
+                                      const int32_t* d_prompt, const int32_t* d_completion, const int32_t* d_total,
+                                      const int32_t* d_reasoning, const int32_t* d_cached, const double* d_cost, uint64_t n,
+                                      int period, int has_start, int64_t start_us, int has_end, int64_t end_us,
+                                      int64_t bucket0, uint32_t n_buckets, uint32_t n_models,
+                                      uint64_t* d_table, uint32_t* d_inexact, uint32_t* d_oob) {
+    if (!e || !d_table || !d_inexact || !d_oob || period < 0 || period > 3 || n_buckets == 0 || n_models == 0) return LGW_ERR_ARG;
+    if (n && (!d_ts_us || !d_model_rank || !d_prompt || !d_completion || !d_total || !d_reasoning || !d_cached || !d_cost)) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    RollupArgs a{};
+    a.ts_us = d_ts_us; a.model_rank = d_model_rank; a.tok[0] = d_prompt; a.tok[1] = d_completion; a.tok[2] = d_total;
+    a.tok[3] = d_reasoning; a.tok[4] = d_cached; a.cost = d_cost; a.n = n; a.period = period;
+    a.start_us = start_us; a.end_us = end_us; a.has_start = has_start; a.has_end = has_end;
+    a.bucket0 = bucket0; a.n_buckets = n_buckets; a.n_models = n_models;
+    a.table = (unsigned long long*)d_table; a.inexact = d_inexact; a.oob = d_oob;
+    CK(e, cudaEventRecord(e->rev[0], e->stream));
+    if (n) {
+        const uint64_t want = (n + 255) / 256;
+        const unsigned grid = (unsigned)(want < (uint64_t)e->sm_count * 16 ? want : (uint64_t)e->sm_count * 16);
+        k_rollup_accum<<<grid, 256, 0, e->stream>>>(a);
+        ++e->launches;
+    }
+    CK(e, cudaEventRecord(e->rev[1], e->stream));
+    CK(e, cudaGetLastError());
+    return LGW_OK;
+}
+
+extern "C" int lgw_usage_rollup_emit(lgw_engine* e, const uint64_t* d_table, const uint32_t* d_inexact,
+                                     int64_t bucket0, uint32_t n_buckets, uint32_t n_models,
+                                     lgw_rollup_row* rows_out, uint64_t rows_cap, uint64_t* n_rows) {
+    if (!e || !d_table || !d_inexact || !n_rows || (!rows_out && rows_cap) || n_buckets == 0 || n_models == 0) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    const uint64_t groups = (uint64_t)n_buckets * n_models;
+    const uint64_t cap = rows_cap < groups ? rows_cap : groups;
+    if (cap > e->d_rows_cap) {
+        cudaFree(e->d_rows); e->d_rows = nullptr; e->d_rows_cap = 0;
+        CK(e, cudaMalloc((void**)&e->d_rows, (cap ? cap : 1) * sizeof(RollupRow)));
+        e->d_rows_cap = cap;
+    }
+    if (!e->d_nrows) CK(e, cudaMalloc((void**)&e->d_nrows, 8));
+    CK(e, cudaEventRecord(e->rev[2], e->stream));
+    k_rollup_compact<<<1, 1024, 0, e->stream>>>((const unsigned long long*)d_table, d_inexact, n_buckets, n_models, bucket0, e->d_rows, cap, e->d_nrows);
+    ++e->launches;
+    CK(e, cudaEventRecord(e->rev[3], e->stream));
+    CK(e, cudaGetLastError());
+    unsigned long long cnt = 0;
+    CK(e, cudaMemcpyAsync(&cnt, e->d_nrows, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    *n_rows = cnt;
+    const uint64_t take = cnt < cap ? cnt : cap;
+    if (take) CK(e, cudaMemcpyAsync(rows_out, e->d_rows, take * sizeof(RollupRow), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_rollup_last_ms(lgw_engine* e, float ms[2]) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    cudaEventSynchronize(e->rev[1]); cudaEventSynchronize(e->rev[3]);
+    float t = 0;
+    if (cudaEventElapsedTime(&t, e->rev[0], e->rev[1]) == cudaSuccess) e->rms[0] = t;
+    if (cudaEventElapsedTime(&t, e->rev[2], e->rev[3]) == cudaSuccess) e->rms[1] = t;
+    ms[0] = e->rms[0]; ms[1] = e->rms[1];
+    return LGW_OK;
+}
+
+extern "C" int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out) {
+    if (!e || !out) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMalloc(out, bytes ? bytes : 1));
+    return LGW_OK;
+}
+extern "C" int lgw_device_free(lgw_engine* e, void* p) { if (!e) return LGW_ERR_ARG; CK(e, cudaSetDevice(e->device)); CK(e, cudaFree(p)); return LGW_OK; }
+extern "C" int lgw_device_upload(lgw_engine* e, void* d, const void* h, uint64_t bytes) {
+    if (!e || (bytes && (!d || !h))) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream)); CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+extern "C" int lgw_device_download(lgw_engine* e, void* h, const void* d, uint64_t bytes) {
+    if (!e || (bytes && (!d || !h))) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, e->stream)); CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+extern "C" int lgw_device_zero(lgw_engine* e, void* d, uint64_t bytes) {
+    if (!e || (bytes && !d)) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemsetAsync(d, 0, bytes, e->stream));
     return LGW_OK;
 }

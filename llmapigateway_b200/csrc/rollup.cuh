@@ -1,0 +1,233 @@
+// Usage-stats rollup: GROUP BY strftime(fmt, timestamp), model with SUM x5,
+// SUM(cost), COUNT(*) -- llm_gateway_core/db/tokens_usage_db.py:222-304 (SQL at :268-286).
+//
+// Records are SoA in HBM, 40 B each: int64 timestamp (microseconds of the naive local datetime the
+// reference writes at :135), int32 model rank (0 = NULL, else 1 + rank of the name in byte order,
+// so ascending rank == SQL "model ASC"), 5 x int32 token counts, fp64 cost.
+//
+// Every accumulator is an integer, so partial tables from several GPUs merge with a plain sum in
+// any order: token sums/count are int64; cost is summed EXACTLY as a 128-bit fixed-point number
+// (LSB 2^-80) held as four 32-bit limbs in 64-bit cells, then rounded once to double.  SQLite's
+// own SUM(REAL) is a compensated sum, so the two agree to an ulp or so (tests allow 4 ulp).
+//
+// Bucket index (monotone in time, so descending index == "time_period DESC"):
+//   hour  : day * 24 + hour-of-day          day : days since 1970-01-01   (day: see date_days)
+//   week  : year * 64 + %W  (%W = week of year, Monday first, 00-53: SQLite/C strftime)
+//   month : year * 12 + (month - 1)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LGW_RHD __host__ __device__ __forceinline__
+#else
+#define LGW_RHD inline
+#endif
+
+namespace lgw {
+
+enum RollupPeriod : int { RP_HOUR = 0, RP_DAY = 1, RP_WEEK = 2, RP_MONTH = 3 };
+#define LGW_ROLLUP_CELLS 10          /* 5 token sums, count, 4 cost limbs */
+
+// floor division for possibly negative numerators
+LGW_RHD int64_t fdiv(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+// civil date from days since 1970-01-01 (proleptic Gregorian; H. Hinnant's algorithm)
+LGW_RHD void civil_from_days(int64_t z, int64_t& y, int& m, int& d) {
+    z += 719468;
+    const int64_t era = fdiv(z, 146097);
+    const int64_t doe = z - era * 146097;
+    const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    y = yoe + era * 400;
+    const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const int64_t mp = (5 * doy + 2) / 153;
+    d = (int)(doy - (153 * mp + 2) / 5 + 1);
+    m = (int)(mp < 10 ? mp + 3 : mp - 9);
+    if (m <= 2) ++y;
+}
+LGW_RHD int64_t days_from_civil(int64_t y, int m, int d) {
+    y -= m <= 2;
+    const int64_t era = fdiv(y, 400);
+    const int64_t yoe = y - era * 400;
+    const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + doe - 719468;
+}
+
+// SQLite 3.45 date.c quirks, reproduced on purpose (the oracle IS SQLite, same library on the GPU box):
+//  * the seconds field is rounded to milliseconds inside the Julian-day value, (int64)(s*1000 + 0.5),
+//    so 23:59:59.9995+ becomes 24:00:00.000 of the same parsed date ("roll");
+//  * Y-M-D stay as parsed unless D > 28, in which case isDate() re-derives them from the Julian day
+//    (normalisation of dates like Feb 31) -- a rolled 31st becomes the 1st of the next month;
+//  * %H is always the parsed hour;  %W takes the weekday from the (rolled) Julian day but the day of
+//    year from the parsed date relative to Jan 1 of the year in use.
+// '1999-12-31T23:59:59.999999' therefore formats as '2000-01-01 23:00:00' / '2000-W00', while
+// '2026-03-01T23:59:59.999999' (a Sunday) stays '2026-03-01 23:00:00' but gets '2026-W09'.
+LGW_RHD int64_t bucket_of(int64_t ts_us, int period) {
+    const int64_t secs = fdiv(ts_us, 1000000);
+    const int64_t us = ts_us - secs * 1000000;
+    const int64_t pdays = fdiv(secs, 86400);                          // parsed date
+    const int64_t tod = secs - pdays * 86400;                         // parsed time of day, seconds
+    const int64_t sec_in_min = tod % 60;
+    const double s = (double)(sec_in_min * 1000000 + us) / 1e6;      // what the parser makes of "SS.ffffff"
+    const int64_t ms = (int64_t)(s * 1000.0 + 0.5);
+    const bool roll = (tod - sec_in_min) * 1000 + ms >= 86400000;
+    int64_t y; int m, d;
+    civil_from_days(pdays, y, m, d);
+    int64_t udays = pdays;                                            // date in use for %Y %m %d
+    if (roll && d > 28) { udays = pdays + 1; civil_from_days(udays, y, m, d); }
+    if (period == RP_HOUR) return udays * 24 + tod / 3600;
+    if (period == RP_DAY) return udays;
+    if (period == RP_MONTH) return y * 12 + (m - 1);
+    int64_t nday = pdays - days_from_civil(y, 1, 1);                  // trunc((x.iJD - jan1.iJD + 12h) / 1d)
+    if (nday < 0) nday = 0;
+    const int64_t wdays = pdays + (roll ? 1 : 0);
+    const int wd = (int)((((wdays % 7) + 7) % 7 + 3) % 7);            // Monday = 0; 1970-01-01 was a Thursday
+    return y * 64 + (nday + 7 - wd) / 7;
+}
+
+// ---- exact cost accumulation ---------------------------------------------------------------------
+// double -> signed 128-bit fixed point with LSB 2^-80, as four 32-bit limbs (two's complement).
+// returns false when the value cannot be represented exactly (tiny bits lost, huge, NaN/Inf).
+LGW_RHD bool cost_to_limbs(double c, uint32_t limb[4]) {
+    uint64_t b; memcpy(&b, &c, 8);
+    const int E = (int)((b >> 52) & 0x7FF);
+    uint64_t M = b & 0x000FFFFFFFFFFFFFull;
+    const bool neg = b >> 63;
+    limb[0] = limb[1] = limb[2] = limb[3] = 0;
+    if (E == 0x7FF) return false;
+    if (E == 0) { if (M == 0) return true; return false; }            // subnormals: far below 2^-80
+    M |= 1ull << 52;
+    const int shift = E - 1075 + 80;                                  // value * 2^80 = M * 2^shift
+    bool exact = true;
+    uint64_t lo, hi;
+    if (shift >= 0) {
+        if (shift > 74) return false;                                 // |value| >= 2^47
+        if (shift >= 64) { lo = 0; hi = M << (shift - 64); }
+        else if (shift == 0) { lo = M; hi = 0; }
+        else { lo = M << shift; hi = M >> (64 - shift); }
+    } else {
+        const int r = -shift;
+        if (r >= 53) { lo = 0; hi = 0; exact = false; }
+        else { exact = (M & ((1ull << r) - 1)) == 0; lo = M >> r; hi = 0; }
+    }
+    if (neg) { lo = ~lo + 1; hi = ~hi + (lo == 0 ? 1 : 0); }
+    limb[0] = (uint32_t)lo; limb[1] = (uint32_t)(lo >> 32); limb[2] = (uint32_t)hi; limb[3] = (uint32_t)(hi >> 32);
+    return exact;
+}
+
+// four 64-bit cells of summed limbs -> one double, rounded half-to-even
+LGW_RHD double limbs_to_cost(const uint64_t cell[4]) {
+    // carry-propagate into a 128-bit two's complement value (mod 2^128)
+    uint64_t c0 = cell[0];
+    uint64_t c1 = cell[1] + (c0 >> 32);
+    uint64_t c2 = cell[2] + (c1 >> 32);
+    uint64_t c3 = cell[3] + (c2 >> 32);
+    uint64_t lo = (c0 & 0xFFFFFFFFull) | (c1 << 32);
+    uint64_t hi = (c2 & 0xFFFFFFFFull) | (c3 << 32);
+    const bool neg = hi >> 63;
+    if (neg) { lo = ~lo + 1; hi = ~hi + (lo == 0 ? 1 : 0); }
+    if ((lo | hi) == 0) return 0.0;
+    // top 64 significant bits + sticky
+    int top;                      // index of the highest set bit (0..127)
+    if (hi) { top = 127; while (!((hi >> (top - 64)) & 1)) --top; }
+    else { top = 63; while (!((lo >> top) & 1)) --top; }
+    uint64_t sig; bool sticky = false;
+    if (top >= 64) {
+        const int s = top - 63;                                       // drop s low bits (1..64)
+        sig = s == 64 ? hi : (hi << (64 - s)) | (lo >> s);
+        sticky = s == 64 ? lo != 0 : (lo & ((1ull << s) - 1)) != 0;
+    } else sig = lo << (63 - top);
+    // sig has its top bit at 63; value = sig * 2^(top - 63 - 80)
+    uint64_t kept = sig >> 11;
+    const uint64_t half = (sig >> 10) & 1, rest = sig & 0x3FF;
+    int e2 = top - 80;                                                // exponent of the leading bit
+    if (half && (rest || sticky || (kept & 1))) { ++kept; if (kept >> 53) { kept >>= 1; ++e2; } }
+    const uint64_t bits = ((uint64_t)(e2 + 1023) << 52) | (kept & 0x000FFFFFFFFFFFFFull) | (neg ? 1ull << 63 : 0);
+    double d; memcpy(&d, &bits, 8);
+    return d;
+}
+
+struct RollupRow {               // == lgw_rollup_row
+    int64_t bucket;
+    int32_t model_rank; uint32_t inexact;
+    int64_t prompt_tokens, completion_tokens, total_tokens, reasoning_tokens, cached_tokens;
+    double cost;
+    int64_t count;
+};
+
+#if defined(__CUDACC__)
+struct RollupArgs {
+    const int64_t* ts_us; const int32_t* model_rank;
+    const int32_t* tok[5]; const double* cost;
+    uint64_t n;
+    int period; int64_t start_us, end_us; int has_start, has_end;
+    int64_t bucket0; uint32_t n_buckets, n_models;       // dense table geometry: [n_buckets][n_models][CELLS]
+    unsigned long long* table; uint32_t* inexact;        // inexact: per group flag (cost bits lost)
+    uint32_t* oob;                                        // records whose bucket fell outside the table (must stay 0)
+};
+
+// one record per thread per trip; all table updates are 64-bit integer reductions (RED.ADD, no return)
+__global__ void __launch_bounds__(256) k_rollup_accum(RollupArgs a) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t ts = __ldg(a.ts_us + i);
+        if ((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us)) continue;     // tokens_usage_db.py:255-266
+        const int64_t b = bucket_of(ts, a.period) - a.bucket0;
+        const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
+        if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) { atomicAdd(a.oob, 1u); continue; }
+        const uint64_t g = (uint64_t)b * a.n_models + mr;
+        unsigned long long* cell = a.table + g * LGW_ROLLUP_CELLS;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(cell + k, (unsigned long long)(long long)__ldg(a.tok[k] + i));
+        atomicAdd(cell + 5, 1ull);
+        uint32_t limb[4];
+        if (!cost_to_limbs(__ldg(a.cost + i), limb)) a.inexact[g] = 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (limb[k]) atomicAdd(cell + 6 + k, (unsigned long long)limb[k]);
+    }
+}
+
+// groups with count > 0, in "time_period DESC, model ASC" order.  One block scans the table in
+// output order with a running offset (the table is small next to the record stream).
+__global__ void __launch_bounds__(1024) k_rollup_compact(const unsigned long long* table, const uint32_t* inexact, uint32_t n_buckets, uint32_t n_models,
+                                                         int64_t bucket0, RollupRow* rows, unsigned long long rows_cap, unsigned long long* n_rows) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ unsigned long long base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const uint64_t total = (uint64_t)n_buckets * n_models;
+    for (uint64_t start = 0; start < total; start += blockDim.x) {
+        const uint64_t j = start + threadIdx.x;                       // output-order position
+        uint32_t has = 0; uint64_t g = 0;
+        if (j < total) {
+            const uint64_t bdesc = j / n_models, mr = j % n_models;
+            g = (uint64_t)(n_buckets - 1 - bdesc) * n_models + mr;
+            has = table[g * LGW_ROLLUP_CELLS + 5] != 0;
+        }
+        // block exclusive scan of `has`
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
+        const uint32_t in_warp = __popc(ballot & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t before = 0, block_total = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) { const uint32_t s = warp_sums[w]; if (w < warp) before += s; block_total += s; }
+        const unsigned long long pos = base + before + in_warp;
+        if (has && pos < rows_cap) {
+            const unsigned long long* c = table + g * LGW_ROLLUP_CELLS;
+            RollupRow r;
+            r.bucket = bucket0 + (int64_t)(g / n_models); r.model_rank = (int32_t)(g % n_models); r.inexact = inexact[g];
+            r.prompt_tokens = (int64_t)c[0]; r.completion_tokens = (int64_t)c[1]; r.total_tokens = (int64_t)c[2];
+            r.reasoning_tokens = (int64_t)c[3]; r.cached_tokens = (int64_t)c[4]; r.count = (int64_t)c[5];
+            uint64_t cells[4] = {c[6], c[7], c[8], c[9]};
+            r.cost = limbs_to_cost(cells);
+            rows[pos] = r;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += block_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_rows = base;
+}
+#endif
+
+}  // namespace lgw
