@@ -86,8 +86,11 @@ def usage_rec_to_dict(rec: UsageRec) -> dict:
     """The dict chat_logging.py:233-272 (get_token_usage) would have returned."""
     out = {name: val_to_py(getattr(rec, name)) for name in
            ("prompt_tokens", "completion_tokens", "total_tokens", "reasoning_tokens", "cached_tokens", "cost")}
-    for name, val, ln in (("provider", rec.provider_val, rec.provider_len), ("model", rec.model_val, rec.model_len)):
+    for name, val, ln, shift in (("provider", rec.provider_val, rec.provider_len, 2), ("model", rec.model_val, rec.model_len, 0)):
         if val.kind == KIND_ABSENT:
             continue
-        out[name] = _rec_text(rec, name, ln) if val.kind == KIND_STR else val_to_py(val)
+        if val.kind == KIND_STR and (rec.str_flags >> shift) & 3:      # truncated / lone surrogate: reported, not guessed
+            out[name] = Unrepresentable(KIND_STR)
+        else:
+            out[name] = _rec_text(rec, name, ln) if val.kind == KIND_STR else val_to_py(val)
     return out

@@ -1,0 +1,62 @@
+"""CPU stand-in for llmapigateway_b200.Engine used ONLY by host-logic tests (batcher, gateway seam,
+gloo sharding): it replays each stream through the host build of the device machine
+(tests/support, test aid).  It keeps every stream's history and re-runs it per step."""
+from __future__ import annotations
+
+import numpy as np
+
+import host_machine as hm
+from llmapigateway_b200 import _abi
+from llmapigateway_b200.engine import SEG_DTYPE, StepResult
+
+
+class _Limits:
+    def __init__(self, max_streams):
+        self.max_streams = max_streams
+        self.detail_cap = 4096
+        self.rowq_cap = 64
+
+
+class FakeEngine:
+    def __init__(self, max_streams=64):
+        self.limits = _Limits(max_streams)
+        self.hist = {}
+
+    def open(self, slots, http_status=None):
+        for i, s in enumerate(slots):
+            self.hist[int(s)] = dict(chunks=[], steps=[], status=200 if http_status is None else int(http_status[i]), rows_seen=0, last=None)
+
+    def _run(self, h):
+        return hm.run_stream(h["chunks"], h["steps"] or [0], h["status"])
+
+    def step(self, data, chunk_off, seg_chunk, seg_slot, out=None):
+        data = np.asarray(data, dtype=np.uint8)
+        segs = np.zeros(len(seg_slot), dtype=SEG_DTYPE)
+        rows = []
+        for k, slot in enumerate(seg_slot):
+            h = self.hist[int(slot)]
+            c0, c1 = int(seg_chunk[k]), int(seg_chunk[k + 1])
+            h["steps"].append(len(h["chunks"]))
+            base = len(h["chunks"])
+            h["chunks"] += [data[int(chunk_off[c]):int(chunk_off[c + 1])].tobytes() for c in range(c0, c1)]
+            r = self._run(h)
+            seg = r["segs"][-1]
+            segs[k] = (c0 + (int(seg.emit_chunk_begin) - base), seg.phase, seg.verdict, seg.flags, seg.detail_len)
+            for ev in r["rows"][h["rows_seen"]:]:
+                ev.slot = int(slot)
+                rows.append(ev)
+            h["rows_seen"] = len(r["rows"])
+            h["last"] = r
+        return StepResult(data.copy(), segs, rows)
+
+    def detail(self, slot):
+        return self.hist[int(slot)]["last"]["detail"]
+
+    def state(self, slots):
+        return [self._run(self.hist[int(s)])["state"] for s in slots]
+
+    def close(self, slots):
+        out = self.state(slots)
+        for s in slots:
+            self.hist.pop(int(s), None)
+        return out

@@ -253,3 +253,27 @@ def test_bulk_path_equals_sequential_path_and_oracle(engine, n_steps):
             assert (not (a.flags & _abi.SF_A_USAGE_BOUND)) == relay.end_raises
             n_regular += 1
     assert n_regular > 1000
+
+
+def test_gateway_seam_on_the_real_engine(engine):
+    """make_llm_request + StreamBatcher over the CUDA engine against the reference goldens."""
+    import asyncio
+    from test_gateway_cpu import _Sink, _drive
+    from llmapigateway_b200.gateway import StreamBatcher
+    engine.set_mode(0)
+
+    async def go():
+        sink = _Sink()
+        batcher = StreamBatcher(engine, window_s=0.0005, usage_sink=sink)
+        picks = CASES[:150]
+        results = await asyncio.gather(*[_drive(c, batcher, _Sink()) for c in picks])
+        n_rows_ok = 0
+        for c, r in zip(picks, results):
+            assert r["failed"] == c["failed"], c["name"]
+            if c["failed"]:
+                if not c["error_detail"].startswith("Unexpected error during request to"):
+                    assert r["error_detail"] == c["error_detail"], c["name"]
+                continue
+            assert r["emitted"] == c["emitted"], c["name"]
+        assert batcher.steps > 0
+    asyncio.run(go())
