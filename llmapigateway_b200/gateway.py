@@ -13,6 +13,7 @@ and are left to the reference's own code.
 from __future__ import annotations
 
 import asyncio
+import concurrent.futures
 import zlib
 from dataclasses import dataclass, field
 
@@ -54,19 +55,21 @@ class StreamBatcher:
         self._task: asyncio.Task | None = None
         self._closed = False
         self.steps = 0
+        # the engine handle is not thread-safe: every call into it goes through this one worker thread
+        self._worker = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="lgw-engine")
 
     # -- slots ---------------------------------------------------------------------------------------
     async def open_stream(self, http_status: int = 200) -> int:
         if not self._free:
             raise RuntimeError("no free stream slot on this engine")
         slot = self._free.pop()
-        await asyncio.get_running_loop().run_in_executor(None, self.eng.open, [slot], [http_status])
+        await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.open, [slot], [http_status])
         return slot
 
     async def close_stream(self, slot: int):
         """End of upstream: returns (final StreamState, usage dict or None).  The usage dict is the
         last DB row of chat_logging.py:150 and goes to the usage sink (TokensUsageDB.insert_usage seam)."""
-        st = (await asyncio.get_running_loop().run_in_executor(None, self.eng.close, [slot]))[0]
+        st = (await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.close, [slot]))[0]
         self._free.append(slot)
         usage = None
         if st.flags & _abi.SF_EMITTED_ANY:
@@ -75,8 +78,9 @@ class StreamBatcher:
                 self.usage_sink.insert_usage(usage)
         return st, usage
 
-    def detail(self, slot: int) -> str:
-        return self.eng.detail(slot).decode("utf-8", errors="replace")
+    async def detail(self, slot: int) -> str:
+        raw = await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.detail, slot)
+        return raw.decode("utf-8", errors="replace")
 
     # -- data ------------------------------------------------------------------------------------------
     async def feed(self, slot: int, chunk: bytes) -> FeedResult:
@@ -104,7 +108,7 @@ class StreamBatcher:
                 segc.append(segc[-1] + len(by_slot[s]))
             data = np.frombuffer(b"".join(blobs), dtype=np.uint8) if blobs else np.zeros(0, np.uint8)
             try:
-                res = await loop.run_in_executor(None, self.eng.step, data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32))
+                res = await loop.run_in_executor(self._worker, self.eng.step, data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32))
             except Exception as exc:                      # engine failure: the endpoint answers 500/503 like chat.py:26,198
                 for p in batch:
                     if not p.fut.done():
@@ -149,7 +153,7 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
         async for chunk in chunks:                                        # priming: request_handler.py:69-95
             r = await batcher.feed(slot, chunk)
             if r.phase == _abi.PHASE_FAILED:
-                detail = batcher.detail(slot)
+                detail = await batcher.detail(slot)
                 if r.verdict == _abi.VERDICT_FAIL_PARSE:                  # :183-187 (message tail is the JSON library's text: unpinned)
                     detail = f"Unexpected error during request to {target_url}: first event is not valid JSON: {detail[:200]}"
                 await batcher.close_stream(slot)
