@@ -82,7 +82,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     ALLOC(e->t.carry_a, S * (size_t)e->lim.carry_cap);
     ALLOC(e->t.carry_b, S * (size_t)e->lim.carry_cap);
     ALLOC(e->t.detail, S * (size_t)e->lim.detail_cap);
-    ALLOC(e->t.pending, S * (size_t)LGW_PENDING_CAP);
+    ALLOC(e->t.pending, S * (size_t)LGW_PENDING_STRIDE);
     e->t.carry_cap = e->lim.carry_cap; e->t.detail_cap = e->lim.detail_cap; e->t.max_streams = e->lim.max_streams;
     ALLOC(e->d_rowq, (size_t)(e->lim.rowq_cap + 1) * sizeof(RowEvent));
     ALLOC(e->d_rowq_count, 16);

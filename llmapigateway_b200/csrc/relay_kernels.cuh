@@ -1,17 +1,26 @@
 // Bulk path of the SSE step: k_prime -> k_relay -> k_commit.   (included from sse_kernels.cuh)
 //
-// Regular streams -- committed, carries empty and equal at the start of the bulk region, every
-// chunk valid UTF-8 and non-empty, no run of three or more LFs, no event the tap turns into an
-// extra row ("error") or that has an unmodelled shape -- are exactly the streams for which the
-// reference's chunk-by-chunk split (request_handler.py:111-115, chat_logging.py:108-112) equals a
-// split of the CONCATENATED text on every LF LF pair.  For those, events are independent: the
-// chunk in which an event completes owns it, parses it, and posts its findings with atomics.
-// Everything else is flagged irregular and redone by k_commit with the exact sequential machine,
-// so the result never depends on which path ran (tests run both and compare with the oracle).
-
+// Regular streams -- committed (or committing on their first chunk), carries empty and equal at the
+// start of the bulk region, every chunk valid UTF-8 and non-empty, no run of three or more LFs, no
+// event the tap turns into an extra row ("error"), at most one usage event per step -- are exactly
+// the streams for which the reference's chunk-by-chunk split (request_handler.py:111-115,
+// chat_logging.py:108-112) equals a split of the CONCATENATED text on every LF LF pair.  For those,
+// events are independent: the chunk in which an event completes owns it, recognises it, and posts its
+// findings with atomics.  Everything else is flagged irregular and redone by k_commit with the exact
+// sequential machine, so the result never depends on which path ran (tests run both and the oracle).
+//
+// Event templates.  SSE deltas of a stream are the same JSON skeleton over and over with one string
+// value changing.  Each persistent block keeps ONE validated event as a template (bytes + for every
+// byte position whether the recogniser is inside a string VALUE there).  An event B that equals the
+// template A up to a position inside a value string, continues with plain string bytes up to a
+// closing quote, and from there equals A's text after that string's closing quote, drives the
+// recogniser through the same states as A: same validity, same top-level keys -- no byte of it needs
+// to be re-validated beyond the comparison.  Anything else takes the byte-wise recogniser.
 
 #define LGW_RELAY_THREADS 256
 #define LGW_TILE_VECS (LGW_TILE_BYTES / 16)
+#define LGW_TPL_MAX 248u            /* longest event kept as a template */
+#define LGW_TPL_IDS 32u
 
 // 16 KB tile in shared memory, swizzled so that 32 lanes reading the same byte position of 32
 // consecutive 64-byte rows (the 64-byte-event pattern) hit 32 different banks, while a 16-byte
@@ -19,12 +28,15 @@
 //   physical offset = d ^ X(d),  X(d) = ((d >> 3) & 0x30) | ((d >> 7) & 0x0c)
 __device__ __forceinline__ uint32_t swz(uint32_t d) { return d ^ (((d >> 3) & 0x30u) | ((d >> 7) & 0x0cu)); }
 
-// Shared memory of k_relay, declared at file scope so that device functions index it by name
-// (LDS with an immediate base; a pointer would be rebuilt from the CTA's shared window per access).
 __shared__ __align__(16) uint8_t sh_tile[LGW_TILE_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
+// the block's event template
+__shared__ __align__(4) uint8_t sh_tpl_bytes[LGW_TPL_MAX + 16];   // zero padded
+__shared__ __align__(4) uint8_t sh_tpl_strid[LGW_TPL_MAX + 8];    // value-string id per position (0xff: not inside one)
+__shared__ uint16_t sh_tpl_end[LGW_TPL_IDS];                      // position of each value string's closing quote
+__shared__ uint32_t sh_tpl_len, sh_tpl_flags, sh_tpl_cls, sh_tpl_valid, sh_tpl_cand;
 
 // shared-memory loads by 32-bit shared-window address held in a register (the compiler otherwise
 // rebuilds the CTA's shared-window base -- S2UR SR_CgaCtaId + ULEA -- in front of every access)
@@ -34,7 +46,7 @@ __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(
 
 // byte source + tables of the bulk kernel: the staged tile, global memory outside it
 struct TileEnv {
-    uint32_t tile_s, cls_s, trans_s;   // shared-window addresses (opaque registers)
+    uint32_t tile_s, cls_s, trans_s, tpl_s, strid_s;   // shared-window addresses (opaque registers)
     const uint8_t* __restrict__ g;     // whole packed buffer
     uint32_t t0, n_bytes;
     // aligned 32-bit word containing byte `pos` (little endian); bytes past n_bytes read as 0
@@ -44,15 +56,117 @@ struct TileEnv {
         return word_global(p4);
     }
     __device__ __noinline__ uint32_t word_global(uint32_t p4) const {
+        if (p4 >= n_bytes) return 0;
         if (p4 + 4 <= n_bytes) return __ldg(reinterpret_cast<const uint32_t*>(g + p4));
         uint32_t w = 0;
         for (uint32_t k = 0; k < 4 && p4 + k < n_bytes; ++k) w |= (uint32_t)__ldg(g + p4 + k) << (8 * k);
         return w;
     }
+    // the four bytes at pos .. pos+3 (any alignment)
+    __device__ __forceinline__ uint32_t wordu(uint32_t pos) const {
+        const uint32_t lo = word(pos);
+        if ((pos & 3u) == 0) return lo;
+        return __funnelshift_r(lo, word(pos + 4), 8 * (pos & 3u));
+    }
     __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (word(pos) >> (8 * (pos & 3u))) & 0xffu; }
     __device__ __forceinline__ uint32_t cls(uint32_t c) const { return lds_u8(cls_s + c); }
     __device__ __forceinline__ uint32_t trans(uint32_t i) const { return lds_u8(trans_s + i); }
+    // template text: the four bytes at k .. k+3
+    __device__ __forceinline__ uint32_t tplu(uint32_t k) const {
+        const uint32_t lo = lds_u32(tpl_s + (k & ~3u));
+        if ((k & 3u) == 0) return lo;
+        return __funnelshift_r(lo, lds_u32(tpl_s + (k & ~3u) + 4), 8 * (k & 3u));
+    }
 };
+
+// first byte of w (little endian) that is '"', '\\' or < 0x20: index 0..3, or 4 when none
+__device__ __forceinline__ uint32_t first_special(uint32_t w) {
+    const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5c5c5c5cu, c = w & 0xe0e0e0e0u;
+    const uint32_t m = (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((c - 0x01010101u) & ~c)) & 0x80808080u;
+    return m ? (uint32_t)(__ffs(m) - 1) >> 3 : 4u;      // the lowest flagged byte is exact (borrows only travel upward)
+}
+
+// Does the event starting at ps follow the block's template?  On success *end = position of the first
+// LF of its LF LF separator (which is verified to be there).
+__device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t ps, uint32_t* end) {
+    const uint32_t lenA = sh_tpl_len;
+    // common prefix
+    uint32_t i = 0, x = 0;
+    const uint32_t sh = 8 * (ps & 3u);
+    uint32_t lo = env.word(ps);
+    while (i < lenA) {
+        const uint32_t hi = env.word(ps + i + 4);
+        const uint32_t wb = sh ? __funnelshift_r(lo, hi, sh) : lo;
+        lo = hi;
+        x = wb ^ lds_u32(env.tpl_s + i);
+        if (x) break;
+        i += 4;
+    }
+    uint32_t L1 = x ? i + ((uint32_t)(__ffs(x) - 1) >> 3) : i;
+    uint32_t q_end;
+    if (L1 >= lenA) q_end = ps + lenA;                         // B starts with all of A
+    else {
+        const uint32_t id = lds_u8(env.strid_s + L1);
+        if (id == 0xffu) return false;                          // the texts part outside a string value
+        uint32_t q = ps + L1;                                   // B: plain string bytes up to the closing quote
+        for (;;) {
+            const uint32_t k = first_special(env.wordu(q));
+            q += k;
+            if (k < 4) break;
+            if (q - ps > 4096u) return false;
+        }
+        if (env.at(q) != '"') return false;
+        const uint32_t ve = sh_tpl_end[id];                     // A: closing quote of that string
+        if (ve >= lenA) return false;
+        const uint32_t rem = lenA - ve;
+        for (uint32_t j = 0; j < rem; j += 4) {
+            uint32_t d = env.wordu(q + j) ^ env.tplu(ve + j);
+            if (rem - j < 4) d &= (1u << (8 * (rem - j))) - 1u;
+            if (d) return false;
+        }
+        q_end = q + rem;
+    }
+    const uint32_t t = env.wordu(q_end);
+    if ((t & 0xffffu) != 0x0a0au) return false;                 // LF LF must follow
+    *end = q_end;
+    return true;
+}
+
+// One thread validates the event at ps and installs it as the block's template (or leaves the
+// template invalid).  limit = end of the segment.
+__device__ __noinline__ void build_template(const TileEnv* env, uint32_t ps, uint32_t limit) {
+    uint32_t cls = PC_NONE;
+    const uint32_t c0 = env->at(ps);
+    if (c0 == '{') cls = PC_BRACE;
+    else if (c0 == 'd' && env->at(ps + 1) == 'a' && env->at(ps + 2) == 't' && env->at(ps + 3) == 'a' && env->at(ps + 4) == ':' && env->at(ps + 5) == ' ' && env->at(ps + 6) == '{') cls = PC_DATA;
+    if (cls == PC_NONE) return;
+    LeanMachine lm;
+    lm.reset(cls == PC_DATA);
+    const uint32_t skip = cls == PC_DATA ? 6u : 0u;
+    for (uint32_t k = 0; k < skip; ++k) sh_tpl_strid[k] = 0xff;
+    uint32_t pos = ps + skip, n_ids = 0, cur = 0xff;
+    for (;;) {
+        if (pos + 1 >= limit || pos - ps >= LGW_TPL_MAX) return;
+        const uint32_t c = env->at(pos);
+        if (c == '\n' && env->at(pos + 1) == '\n') break;
+        const bool in_val = lm.st == L_STR && !lm.in_key;
+        sh_tpl_strid[pos - ps] = in_val ? (uint8_t)cur : (uint8_t)0xff;
+        if (in_val && c == '"' && cur != 0xff) sh_tpl_end[cur] = (uint16_t)(pos - ps);
+        const uint32_t prev = lm.st;
+        lm.step(c, pos, *env);
+        // a string VALUE opens (table state -> L_STR); returning from an escape keeps the id
+        if (prev < LGW_LEAN_ROWS && lm.st == L_STR && !lm.in_key) cur = n_ids < LGW_TPL_IDS ? n_ids++ : 0xffu;
+        ++pos;
+    }
+    const uint32_t f = lm.finish();
+    if (!(f & PF_VALID_A) || (f & (TK_USAGE | TK_ERROR | TK_DETAIL | TK_CODE))) return;    // plain events only
+    if (pos + 2 < limit && env->at(pos + 2) == '\n') return;
+    const uint32_t len = pos - ps;
+    for (uint32_t k = 0; k < LGW_TPL_MAX + 16; ++k) sh_tpl_bytes[k] = k < len ? (uint8_t)env->at(ps + k) : (uint8_t)0;
+    sh_tpl_len = len; sh_tpl_flags = f; sh_tpl_cls = cls;
+    __threadfence_block();
+    sh_tpl_valid = 1;
+}
 
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
 __device__ __noinline__ bool chunk_utf8_ok(const TileEnv* rd, uint32_t o, uint32_t e) {
@@ -105,8 +219,9 @@ __device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o
 
 // ---- k_prime ---------------------------------------------------------------------------------------
 // thread i: (a) tile table entry i = first chunk that starts at or after byte i*TILE;
-//           (b) segment i: finish priming with the exact machine, then plan the bulk region.
-__global__ void __launch_bounds__(64) k_prime(StepArgs a, uint32_t n_tiles) {
+//           (b) segment i: the plan the bulk kernel works to.  Fresh streams are SPECULATED to commit on
+//               their first non-empty chunk; the bulk kernel verifies, k_commit applies or falls back.
+__global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n_tiles) {
         const uint32_t target = i * LGW_TILE_BYTES;
@@ -117,193 +232,244 @@ __global__ void __launch_bounds__(64) k_prime(StepArgs a, uint32_t n_tiles) {
     if (i >= a.n_segs) return;
     const uint32_t seg = i, c0 = a.seg_chunk[seg], c1 = a.seg_chunk[seg + 1];
     const uint32_t slot = a.seg_slot[seg];
-    StreamHdr st = a.t.state[slot].h;                      // local copy of the 64 hot bytes
+    const StreamHdr st = a.t.state[slot].h;
     SegPlan p;
-    p.seg_end = a.chunk_off[c1]; p.relay_begin = p.seg_end; p.irregular = 0; p.last_usage_pos = 0; p.a_usage = 0;
+    p.seg_end = a.chunk_off[c1]; p.relay_begin = p.seg_end; p.irregular = 0; p.last_usage = 0; p.a_usage = 0;
     p.n_events_a = p.n_events_b = p.n_usage_b = 0; p._pad[0] = p._pad[1] = 0;
-    uint32_t emit_begin = (st.phase == PH_COMMITTED) ? c0 : c1;
-    uint32_t resume = c0;
-    if (st.phase == PH_PRIMING) {
-        const StepIO io = make_io(a, slot, &st);
-        resume = run_chunks(io, a.data, a.chunk_off, c0, c1, emit_begin, true);
-        a.t.state[slot].h = st;
-    }
-    if (st.phase == PH_COMMITTED && resume < c1) {
-        if ((st.flags & SF_SYNCED) && st.carry_a_len == 0) p.relay_begin = a.chunk_off[resume];
+    p.kept_chunk = 0xFFFFFFFFu; p.kept_end = 0; p.prime_ok = 0;
+    p.resume_chunk = c0; p.emit_chunk_begin = (st.phase == PH_COMMITTED) ? c0 : c1;
+    if (st.phase == PH_COMMITTED && c0 < c1) {
+        if ((st.flags & SF_SYNCED) && st.carry_a_len == 0) p.relay_begin = a.chunk_off[c0];
         else p.irregular = 1;
+    } else if (st.phase == PH_PRIMING && c0 < c1) {
+        uint32_t c = c0;
+        while (c < c1 && a.chunk_off[c + 1] == a.chunk_off[c]) ++c;          // empty chunks are never yielded (:60-63)
+        if (c < c1 && st.carry_a_len == 0) {
+            p.kept_chunk = c; p.kept_end = a.chunk_off[c + 1]; p.relay_begin = a.chunk_off[c]; p.emit_chunk_begin = c;
+        } else if (c < c1) p.irregular = 1;                                    // an event is open from an earlier step
     }
-    p.resume_chunk = resume; p.emit_chunk_begin = emit_begin;
     a.s.plan[seg] = p;
 }
 
 // ---- k_relay ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a) {
-    const uint32_t t0 = blockIdx.x * LGW_TILE_BYTES;
+// Persistent blocks: block b handles tiles [b*tiles_per_block, ...) so that its template carries over.
+__global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint32_t n_tiles, uint32_t tiles_per_block) {
     const uint32_t tid = threadIdx.x;
     const uint32_t n_bytes = a.n_bytes;
-    const uint32_t c_lo = a.s.tile_chunk[blockIdx.x], c_hi = a.s.tile_chunk[blockIdx.x + 1];
-
-    // (0) tables + segment range of this tile's chunks
     if (tid < 64) reinterpret_cast<uint32_t*>(sh_cls)[tid] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[tid];
     else if (tid < 64 + LGW_LEAN_ROWS * 8) reinterpret_cast<uint32_t*>(sh_trans)[tid - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[tid - 64];
-    if (tid >= 224 && tid < 226 && c_hi > c_lo) {
-        const uint32_t c = tid == 224 ? c_lo : c_hi - 1;
-        uint32_t lo = 0, hi = a.n_segs;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
-        if (tid == 224) sh_seg_lo = lo; else sh_seg_hi = lo;
-    }
+    if (tid == 0) { sh_tpl_valid = 0; sh_tpl_len = 0; }
 
-    // (1) re-emit: position-preserving 16-byte copy of the tile, staged (swizzled) into shared memory
-    //     on the way; note whether the tile has any byte >= 0x80 (UTF-8 checks are skipped otherwise)
-    uint32_t high = 0;
-    {
-        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
-        uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
-        uint4 x[LGW_TILE_VECS / LGW_RELAY_THREADS];
-#pragma unroll
-        for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
-            const uint32_t v = k * LGW_RELAY_THREADS + tid;
-            x[k] = (t0 + v * 16 + 16 <= n_bytes) ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
-            const uint32_t v = k * LGW_RELAY_THREADS + tid;
-            const uint32_t pos = t0 + v * 16;
-            if (pos + 16 <= n_bytes) {
-                dst[v] = x[k];
-            } else if (pos < n_bytes) {                        // ragged end of the buffer
-                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                for (uint32_t b = pos; b < n_bytes; ++b) {
-                    const uint32_t c = a.data[b]; a.out[b] = (uint8_t)c;
-                    const uint32_t sh = c << (8 * ((b - pos) & 3)), wi = (b - pos) >> 2;
-                    if (wi == 0) w0 |= sh; else if (wi == 1) w1 |= sh; else if (wi == 2) w2 |= sh; else w3 |= sh;
-                }
-                x[k] = make_uint4(w0, w1, w2, w3);
-            }
-            high |= x[k].x | x[k].y | x[k].z | x[k].w;
-            const uint32_t r = v >> 2;                          // 64-byte row
-            const uint32_t kx = (r >> 3) & 3u;                  // word permutation inside the vector
-            uint4 y;
-            y.x = kx == 0 ? x[k].x : kx == 1 ? x[k].y : kx == 2 ? x[k].z : x[k].w;
-            y.y = kx == 0 ? x[k].y : kx == 1 ? x[k].x : kx == 2 ? x[k].w : x[k].z;
-            y.z = kx == 0 ? x[k].z : kx == 1 ? x[k].w : kx == 2 ? x[k].x : x[k].y;
-            y.w = kx == 0 ? x[k].w : kx == 1 ? x[k].z : kx == 2 ? x[k].y : x[k].x;
-            const uint32_t slot16 = (r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4);
-            *reinterpret_cast<uint4*>(sh_tile + slot16) = y;
-        }
-    }
-    const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
-
-    // (2) events of the chunks that START in this tile
     TileEnv env;
     env.tile_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tile));
     env.cls_s = opaque((uint32_t)__cvta_generic_to_shared(sh_cls));
     env.trans_s = opaque((uint32_t)__cvta_generic_to_shared(sh_trans));
-    env.g = a.data; env.t0 = t0; env.n_bytes = n_bytes;
-    const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
-    uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
+    env.tpl_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tpl_bytes));
+    env.strid_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tpl_strid));
+    env.g = a.data; env.n_bytes = n_bytes;
 
-    for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
-        uint32_t seg = seg_lo;
-        if (seg_lo != seg_hi) {                                // segment of chunk c: last seg with seg_chunk[seg] <= c
-            uint32_t lo = seg_lo, hi = seg_hi;
+    const uint32_t tile_first = blockIdx.x * tiles_per_block;
+    const uint32_t tile_last = min(n_tiles, tile_first + tiles_per_block);
+    for (uint32_t tile = tile_first; tile < tile_last; ++tile) {
+        const uint32_t t0 = tile * LGW_TILE_BYTES;
+        env.t0 = t0;
+        const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
+        __syncthreads();                                       // the previous tile's readers are done
+
+        // (0) segment range of this tile's chunks
+        if (tid >= 224 && tid < 226 && c_hi > c_lo) {
+            const uint32_t c = tid == 224 ? c_lo : c_hi - 1;
+            uint32_t lo = 0, hi = a.n_segs;
             while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
-            seg = lo;
+            if (tid == 224) sh_seg_lo = lo; else sh_seg_hi = lo;
         }
-        SegPlan* pl = a.s.plan + seg;
-        const uint32_t relay_begin = pl->relay_begin, seg_end = pl->seg_end;
-        const uint32_t o = __ldg(a.chunk_off + c), e = __ldg(a.chunk_off + c + 1);
-        if (o < relay_begin || pl->irregular) continue;
-        if (e == o) { pl->irregular = 1; continue; }
-        if (seg != acc_seg) {
-            if (acc_seg != 0xFFFFFFFFu) { if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a); if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b); }
-            acc_seg = seg; ev_a = ev_b = 0;
-        }
+        if (tid == 0) sh_tpl_cand = 0xFFFFFFFFu;
 
-        // chunk-level UTF-8: ASCII tiles need no check for chunks that end inside the tile
-        if ((tile_high || e > t0 + LGW_TILE_BYTES) && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
-
-        // where does the event that is open at the start of this chunk begin?
-        uint32_t b = o;
-        if (o != relay_begin) {
-            const bool sep_before = o >= relay_begin + 2 && env.at(o - 1) == '\n' && env.at(o - 2) == '\n';
-            if (sep_before) {
-                if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; continue; }   // LF run >= 3
-            } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; continue; }
-        }
-
-        // walk the events that complete inside this chunk (second LF of the separator in [o, e))
-        bool irregular = false;
-        uint32_t us_b = 0, a_usage = 0, last_usage = 0;
-        uint32_t ps = b;
-        while (ps < e) {
-            // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
-            uint32_t cls = PC_NONE;
-            {
-                const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
-                if ((w0 & 0xffu) == '{') cls = PC_BRACE;
-                else if ((w0 & 0xffu) == 'd') {
-                    if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
-                    else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
-                }
+        // (1) re-emit: position-preserving 16-byte copy of the tile, staged (swizzled) into shared memory
+        //     on the way; note whether the tile has any byte >= 0x80 (UTF-8 checks are skipped otherwise)
+        uint32_t high = 0;
+        {
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
+            uint4 x[LGW_TILE_VECS / LGW_RELAY_THREADS];
+#pragma unroll
+            for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
+                const uint32_t v = k * LGW_RELAY_THREADS + tid;
+                x[k] = (t0 + v * 16 + 16 <= n_bytes) ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
             }
-            LeanMachine lm;
-            lm.reset(cls == PC_DATA);
-            uint32_t pos = ps + (cls == PC_DATA ? 6u : 0u);      // "data: " holds no LF
-            bool ended = false;
-            while (pos < e && !ended) {                          // word-wise byte loop
-                uint32_t w = env.word(pos) >> (8 * (pos & 3u));
-                uint32_t nb = 4 - (pos & 3u);
-                if (nb > e - pos) nb = e - pos;
-#pragma unroll 1
-                for (; nb; --nb, w >>= 8, ++pos) {
-                    const uint32_t ch = w & 0xffu;
-                    // hot path: a plain byte inside a string changes nothing
-                    if (lm.st == L_STR && ch >= 0x20u && ch != '"' && ch != '\\') continue;
-                    if (ch == '\n') {
-                        if (pos + 1 >= e) { pos = e; break; }     // a separator starting on the last byte completes later
-                        if (env.at(pos + 1) == '\n') { ended = true; break; }
+#pragma unroll
+            for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
+                const uint32_t v = k * LGW_RELAY_THREADS + tid;
+                const uint32_t pos = t0 + v * 16;
+                if (pos + 16 <= n_bytes) {
+                    dst[v] = x[k];
+                } else if (pos < n_bytes) {                        // ragged end of the buffer
+                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                    for (uint32_t b = pos; b < n_bytes; ++b) {
+                        const uint32_t c = a.data[b]; a.out[b] = (uint8_t)c;
+                        const uint32_t sh = c << (8 * ((b - pos) & 3)), wi = (b - pos) >> 2;
+                        if (wi == 0) w0 |= sh; else if (wi == 1) w1 |= sh; else if (wi == 2) w2 |= sh; else w3 |= sh;
                     }
-                    if (cls != PC_NONE) lm.step(ch, pos, env);
+                    x[k] = make_uint4(w0, w1, w2, w3);
                 }
+                high |= x[k].x | x[k].y | x[k].z | x[k].w;
+                const uint32_t r = v >> 2;                          // 64-byte row
+                const uint32_t kx = (r >> 3) & 3u;                  // word permutation inside the vector
+                uint4 y;
+                y.x = kx == 0 ? x[k].x : kx == 1 ? x[k].y : kx == 2 ? x[k].z : x[k].w;
+                y.y = kx == 0 ? x[k].y : kx == 1 ? x[k].x : kx == 2 ? x[k].w : x[k].z;
+                y.z = kx == 0 ? x[k].z : kx == 1 ? x[k].w : kx == 2 ? x[k].x : x[k].y;
+                y.w = kx == 0 ? x[k].w : kx == 1 ? x[k].z : kx == 2 ? x[k].y : x[k].x;
+                const uint32_t slot16 = (r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4);
+                *reinterpret_cast<uint4*>(sh_tile + slot16) = y;
             }
-            if (!ended) break;                                   // the open event completes in a later chunk
-            // ---- one complete event [ps, pos) ----
-            if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
-            if (cls != PC_NONE) {
-                const uint32_t f = lm.finish();
-                if (cls == PC_DATA) {                            // handler loop, request_handler.py:122-134
-                    ++ev_a;
-                    if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
-                }
-                if (f & PF_VALID_B) {                            // tap loop, chat_logging.py:123-141
-                    ++ev_b;
-                    // events with "error" (extra DB row) go to the sequential path; a "usage" event is
-                    // a candidate that k_commit validates with the full machine (choices walk)
-                    if (f & TK_ERROR) { irregular = true; break; }
-                    if (f & TK_USAGE) { ++us_b; last_usage = ps + 1; }
-                }
-            }
-            ps = pos + 2;
         }
-        if (irregular) { pl->irregular = 1; continue; }
-        if (us_b) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage_pos, last_usage); }
-        if (a_usage) pl->a_usage = 1;
-    }
+        const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
+        const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
 
-    // (3) post the event counters: one atomic per warp when the whole warp worked on one segment
-    {
-        const uint32_t full = 0xFFFFFFFFu;
-        const uint32_t seg0 = __shfl_sync(full, acc_seg, 0);
-        const bool uniform = __all_sync(full, acc_seg == seg0);
-        if (uniform) {
-            if (seg0 != 0xFFFFFFFFu) {
-                const uint32_t sa = __reduce_add_sync(full, ev_a), sb = __reduce_add_sync(full, ev_b);
-                if ((tid & 31) == 0) { if (sa) atomicAdd(&a.s.plan[seg0].n_events_a, sa); if (sb) atomicAdd(&a.s.plan[seg0].n_events_b, sb); }
+        // (1b) no template yet: the lowest thread whose chunk starts with an event builds one
+        if (!sh_tpl_valid) {
+            uint32_t cand_ps = 0, cand_limit = 0;
+            if (c_lo + tid < c_hi) {
+                const uint32_t c = c_lo + tid;
+                uint32_t lo = seg_lo, hi = seg_hi;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+                const SegPlan* pl = a.s.plan + lo;
+                const uint32_t o = __ldg(a.chunk_off + c);
+                const uint32_t begin = (pl->kept_chunk != 0xFFFFFFFFu && c > pl->kept_chunk) ? pl->kept_end : pl->relay_begin;
+                if (!pl->irregular && o >= begin && o + 8 < pl->seg_end && (o == begin || (o >= begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au))) {
+                    const uint32_t w = env.wordu(o);
+                    if ((w & 0xffu) == '{' || w == 0x61746164u) { cand_ps = o; cand_limit = pl->seg_end; atomicMin(&sh_tpl_cand, tid); }
+                }
             }
-        } else if (acc_seg != 0xFFFFFFFFu) {
-            if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a);
-            if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b);
+            __syncthreads();
+            if (sh_tpl_cand == tid) build_template(&env, cand_ps, cand_limit);
+            __syncthreads();
+        }
+        const bool have_tpl = sh_tpl_valid != 0;
+        const uint32_t tpl_flags = sh_tpl_flags, tpl_cls = sh_tpl_cls;
+
+        // (2) events of the chunks that START in this tile
+        uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
+        for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
+            uint32_t seg = seg_lo;
+            if (seg_lo != seg_hi) {                                // segment of chunk c: last seg with seg_chunk[seg] <= c
+                uint32_t lo = seg_lo, hi = seg_hi;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+                seg = lo;
+            }
+            SegPlan* pl = a.s.plan + seg;
+            const uint32_t seg_end = pl->seg_end, kept_chunk = pl->kept_chunk;
+            const bool is_kept = c == kept_chunk;
+            // text visible to both loops starts after the kept chunk; the kept chunk itself is tap-only
+            const uint32_t relay_begin = (kept_chunk != 0xFFFFFFFFu && !is_kept) ? pl->kept_end : pl->relay_begin;
+            const uint32_t o = __ldg(a.chunk_off + c), e = __ldg(a.chunk_off + c + 1);
+            if (o < relay_begin || pl->irregular) continue;
+            if (e == o) { pl->irregular = 1; continue; }
+            if (seg != acc_seg) {
+                if (acc_seg != 0xFFFFFFFFu) { if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a); if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b); }
+                acc_seg = seg; ev_a = ev_b = 0;
+            }
+
+            // chunk-level UTF-8: ASCII tiles need no check for chunks that end inside the tile
+            if ((tile_high || e > t0 + LGW_TILE_BYTES) && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
+
+            // where does the event that is open at the start of this chunk begin?
+            uint32_t b = o;
+            if (o != relay_begin) {
+                const bool sep_before = o >= relay_begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au;
+                if (sep_before) {
+                    if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; continue; }   // LF run >= 3
+                } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; continue; }
+            }
+
+            // walk the events that complete inside this chunk (second LF of the separator in [o, e))
+            bool irregular = false, primed = false;
+            uint32_t us_b = 0, a_usage = 0; unsigned long long last_usage = 0;
+            uint32_t ps = b;
+            while (ps < e) {
+                uint32_t cls = PC_NONE, f = 0, pos = 0;
+                bool ended = false;
+                if (have_tpl && match_template(env, ps, &pos)) {
+                    if (pos + 1 >= e) break;                         // the separator completes in a later chunk
+                    ended = true; cls = tpl_cls; f = tpl_flags;
+                } else {
+                    // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
+                    const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
+                    if ((w0 & 0xffu) == '{') cls = PC_BRACE;
+                    else if ((w0 & 0xffu) == 'd') {
+                        if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
+                        else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
+                    }
+                    LeanMachine lm;
+                    lm.reset(cls == PC_DATA);
+                    pos = ps + (cls == PC_DATA ? 6u : 0u);          // "data: " holds no LF
+                    while (pos < e && !ended) {                      // word-wise byte loop
+                        uint32_t w = env.word(pos) >> (8 * (pos & 3u));
+                        uint32_t nb = 4 - (pos & 3u);
+                        if (nb > e - pos) nb = e - pos;
+#pragma unroll 1
+                        for (; nb; --nb, w >>= 8, ++pos) {
+                            const uint32_t ch = w & 0xffu;
+                            // hot path: a plain byte inside a string changes nothing
+                            if (lm.st == L_STR && ch >= 0x20u && ch != '"' && ch != '\\') continue;
+                            if (ch == '\n') {
+                                if (pos + 1 >= e) { pos = e; break; }     // a separator starting on the last byte completes later
+                                if (env.at(pos + 1) == '\n') { ended = true; break; }
+                            }
+                            if (cls != PC_NONE) lm.step(ch, pos, env);
+                        }
+                    }
+                    if (!ended) break;                               // the open event completes in a later chunk
+                    f = lm.finish();
+                }
+                // ---- one complete event [ps, pos) ----
+                if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
+                if (cls != PC_NONE) {
+                    if (cls == PC_DATA) {
+                        if (is_kept) {                               // priming loop on the kept chunk, request_handler.py:82-91
+                            if (!primed) {
+                                if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) { irregular = true; break; }   // attempt fails: exact path
+                                primed = true;
+                            }
+                        } else {                                     // handler loop, request_handler.py:122-134
+                            ++ev_a;
+                            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
+                        }
+                    }
+                    if (f & PF_VALID_B) {                            // tap loop, chat_logging.py:123-141
+                        ++ev_b;
+                        // events with "error" (extra DB row) go to the sequential path; a "usage" event is
+                        // a candidate whose values k_commit stashes for extraction on demand
+                        if (f & TK_ERROR) { irregular = true; break; }
+                        if (f & TK_USAGE) { ++us_b; last_usage = ((unsigned long long)(ps + 1) << 32) | (pos - ps); }
+                    }
+                }
+                ps = pos + 2;
+            }
+            if (is_kept && !irregular) {
+                // the speculation holds when a real event was accepted and the chunk ends on a separator
+                if (primed && ps == e) pl->prime_ok = 1; else irregular = true;
+            }
+            if (irregular) { pl->irregular = 1; continue; }
+            if (us_b) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage, last_usage); }
+            if (a_usage) pl->a_usage = 1;
+        }
+
+        // (3) post the event counters: one atomic per warp when the whole warp worked on one segment
+        {
+            const uint32_t full = 0xFFFFFFFFu;
+            const uint32_t seg0 = __shfl_sync(full, acc_seg, 0);
+            const bool uniform = __all_sync(full, acc_seg == seg0);
+            if (uniform) {
+                if (seg0 != 0xFFFFFFFFu) {
+                    const uint32_t sa = __reduce_add_sync(full, ev_a), sb = __reduce_add_sync(full, ev_b);
+                    if ((tid & 31) == 0) { if (sa) atomicAdd(&a.s.plan[seg0].n_events_a, sa); if (sb) atomicAdd(&a.s.plan[seg0].n_events_b, sb); }
+                }
+            } else if (acc_seg != 0xFFFFFFFFu) {
+                if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a);
+                if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b);
+            }
         }
     }
 }
@@ -318,32 +484,46 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
     const StepIO io = make_io(a, slot, &st);
     const SegPlan p = a.s.plan[seg];
     uint32_t emit_begin = p.emit_chunk_begin;
-    if (st.phase == PH_COMMITTED && p.resume_chunk < c1) {
+    const bool speculated = p.kept_chunk != 0xFFFFFFFFu;
+    if ((st.phase == PH_COMMITTED || st.phase == PH_PRIMING) && p.resume_chunk < c1) {
         const uint8_t* __restrict__ d = a.data;
         bool sequential = p.irregular || p.n_usage_b > 1;      // several usage candidates: let the exact path count them
-        uint32_t ups = 0, upe = 0;
-        if (!sequential && p.last_usage_pos) {                  // the winning usage event: [ups, upe)
-            ups = p.last_usage_pos - 1; upe = ups;
-            while (upe + 1 < p.seg_end && !(__ldg(d + upe) == '\n' && __ldg(d + upe + 1) == '\n')) ++upe;
-            if (upe - ups > LGW_PENDING_CAP) sequential = true;
-        }
+        if (st.phase == PH_PRIMING && !(speculated && p.prime_ok)) sequential = true;
+        const uint32_t ups = (uint32_t)(p.last_usage >> 32) - 1u, ulen = (uint32_t)p.last_usage;   // the winning usage event
+        if (!sequential && p.last_usage && ulen > LGW_PENDING_CAP) sequential = true;
         if (sequential) {
+            emit_begin = (st.phase == PH_COMMITTED) ? p.resume_chunk : c1;
             run_chunks(io, a.data, a.chunk_off, p.resume_chunk, c1, emit_begin, false);
         } else {
-            const uint32_t nch = c1 - p.resume_chunk, nby = p.seg_end - p.relay_begin;
+            uint32_t first = p.resume_chunk;
+            if (speculated) {                       // apply the verified commit (request_handler.py:89-90, chat_logging.py:200)
+                st.phase = PH_COMMITTED; st.verdict = VD_OK;
+                st.flags |= SF_EMITTED_ANY | SF_SYNCED;
+                st.carry_a_len = st.carry_b_len = 0;
+                ++st.n_events_a;                    // the priming parse of the first real event
+                first = p.kept_chunk;
+            }
+            const uint32_t nch = c1 - first, nby = p.seg_end - p.relay_begin;
             st.n_chunks_in += nch; st.n_chunks_emitted += nch; st.bytes_in += nby; st.bytes_emitted += nby;
             st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b;
             if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
-            if (p.last_usage_pos) {                 // the last usage-bearing event wins (chat_logging.py:134-135):
+            if (p.last_usage) {                     // the last usage-bearing event wins (chat_logging.py:134-135):
                 if (st.flags & SF_PENDING) resolve_pending(io);     // an older stash must be settled first
-                for (uint32_t k = 0; k < upe - ups; ++k) io.pending[k] = __ldg(d + ups + k);    // stash its text;
-                st.pending_len = upe - ups; st.flags |= SF_PENDING; ++st.n_usage_b;               // values on demand
+                // stash its text as whole 16-byte vectors; the values are extracted on demand
+                const uint32_t off = ups & 15u, nv = (off + ulen + 15u) >> 4;
+                const uint4* src = reinterpret_cast<const uint4*>(d + (ups - off));
+                uint4* dst = reinterpret_cast<uint4*>(io.pending);
+                if (((size_t)(ups - off) + ((size_t)nv << 4)) <= a.n_bytes) { for (uint32_t k = 0; k < nv; ++k) dst[k] = __ldg(src + k); }
+                else { for (uint32_t k = 0; k < ulen; ++k) io.pending[off + k] = __ldg(d + ups + k); }
+                st.pending_len = ulen | (off << 16); st.flags |= SF_PENDING; ++st.n_usage_b;
             }
             // new carry = text after the last separator (both loops: SF_SYNCED)
-            uint32_t tail = p.relay_begin;
-            if (nby >= 2 && __ldg(d + p.seg_end - 1) == '\n' && __ldg(d + p.seg_end - 2) == '\n') tail = p.seg_end;
+            const uint32_t text_begin = speculated ? p.kept_end : p.relay_begin;
+            const uint32_t tby = p.seg_end - text_begin;
+            uint32_t tail = text_begin;
+            if (tby == 0 || (tby >= 2 && __ldg(d + p.seg_end - 1) == '\n' && __ldg(d + p.seg_end - 2) == '\n')) tail = p.seg_end;
             else {
-                const uint32_t limit = nby > a.t.carry_cap + 2 ? p.seg_end - a.t.carry_cap - 2 : p.relay_begin;
+                const uint32_t limit = tby > a.t.carry_cap + 2 ? p.seg_end - a.t.carry_cap - 2 : text_begin;
                 for (uint32_t k = p.seg_end; k >= limit + 2; --k)
                     if (__ldg(d + k - 1) == '\n' && __ldg(d + k - 2) == '\n') { tail = k; break; }
             }
@@ -359,13 +539,17 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
 }
 
 static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
-    (void)sm_count;
     cudaError_t r;
     const uint32_t n_tiles = (a.n_bytes + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
     const uint32_t n_prime = (a.n_segs > n_tiles + 1 ? a.n_segs : n_tiles + 1);
-    k_prime<<<(n_prime + 63) / 64, 64, 0, stream>>>(a, n_tiles); ++*launched;
+    k_prime<<<(n_prime + 127) / 128, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
-    if (n_tiles) { k_relay<<<n_tiles, LGW_RELAY_THREADS, 0, stream>>>(a); ++*launched; }
+    if (n_tiles) {
+        const uint32_t max_blocks = (uint32_t)sm_count * 4u;
+        const uint32_t tpb = (n_tiles + max_blocks - 1) / max_blocks;
+        const uint32_t blocks = (n_tiles + tpb - 1) / tpb;
+        k_relay<<<blocks, LGW_RELAY_THREADS, 0, stream>>>(a, n_tiles, tpb); ++*launched;
+    }
     if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
     if (a.n_segs) { k_commit<<<(a.n_segs + 63) / 64, 64, 0, stream>>>(a); ++*launched; }
     if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;

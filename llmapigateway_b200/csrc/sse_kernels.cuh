@@ -23,16 +23,22 @@ struct DeviceTables {
 };
 
 struct SegPlan {
-    uint32_t resume_chunk;     // first chunk not yet consumed by k_prime
-    uint32_t relay_begin;      // byte offset where the regular (bulk) relay text starts; seg end when none
+    uint32_t resume_chunk;     // first chunk the sequential path would have to (re)do
+    uint32_t relay_begin;      // byte offset where the bulk region starts (tap view); seg end when none
     uint32_t seg_end;          // byte offset of the end of the segment
     uint32_t emit_chunk_begin;
     uint32_t irregular;        // 1: the bulk kernel's findings are void, k_commit redoes [resume_chunk, end)
-    uint32_t last_usage_pos;   // 1 + byte offset of the last usage-bearing event the tap accepts (atomicMax)
     uint32_t a_usage;          // handler bound `tokens_usage` (request_handler.py:134)
+    unsigned long long last_usage;   // (1 + byte offset) << 32 | length of the last usage-bearing event (atomicMax)
     uint32_t n_events_a, n_events_b, n_usage_b;
+    // priming by speculation: a fresh stream is assumed to commit on its first non-empty chunk
+    // (request_handler.py:69-95); that chunk's own thread verifies it in the bulk kernel
+    uint32_t kept_chunk;       // 0xFFFFFFFF: no speculation (stream was already committed)
+    uint32_t kept_end;         // byte offset of the end of the kept chunk = where the handler's text starts
+    uint32_t prime_ok;         // set by the kept chunk's thread when the speculation holds
     uint32_t _pad[2];
 };
+static_assert(sizeof(SegPlan) == 64, "SegPlan");
 
 struct StepScratch {
     SegPlan* plan;             // [max_streams]
@@ -65,7 +71,7 @@ __device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot, Stre
     StepIO io;
     io.st = local_hdr;
     io.rec = &a.t.state[slot].rec;
-    io.pending = a.t.pending + (size_t)slot * LGW_PENDING_CAP;
+    io.pending = a.t.pending + (size_t)slot * LGW_PENDING_STRIDE;
     io.carry_a = a.t.carry_a + (size_t)slot * a.t.carry_cap;
     io.carry_b = a.t.carry_b + (size_t)slot * a.t.carry_cap;
     io.detail = a.t.detail + (size_t)slot * a.t.detail_cap;
@@ -89,7 +95,7 @@ __global__ void k_streams_gather(DeviceTables t, const uint32_t* slots, uint32_t
     if (s->h.flags & SF_PENDING) {            // extract the stashed usage event now (deferred by the bulk path)
         StreamHdr st = s->h;
         StepIO io;
-        io.st = &st; io.rec = &s->rec; io.pending = t.pending + (size_t)slot * LGW_PENDING_CAP;
+        io.st = &st; io.rec = &s->rec; io.pending = t.pending + (size_t)slot * LGW_PENDING_STRIDE;
         io.carry_a = io.carry_b = io.detail = nullptr; io.carry_cap = io.detail_cap = 0;
         io.rowq = nullptr; io.rowq_count = nullptr; io.rowq_cap = 0; io.slot = slot;
         resolve_pending(io);

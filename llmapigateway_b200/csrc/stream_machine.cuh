@@ -20,6 +20,7 @@
 namespace lgw {
 
 #define LGW_PENDING_CAP 1024u
+#define LGW_PENDING_STRIDE (LGW_PENDING_CAP + 32u)     /* whole 16-byte vectors around the event text */
 
 enum Phase : uint8_t { PH_FREE = 0, PH_PRIMING = 1, PH_COMMITTED = 2, PH_FAILED = 3 };
 enum Verdict : uint8_t {
@@ -324,9 +325,9 @@ LGW_HD_NOINLINE void resolve_pending(const StepIO& io) {
     StreamHdr& st = *io.st;
     if (!(st.flags & SF_PENDING)) return;
     st.flags &= ~(uint16_t)SF_PENDING;
-    const uint32_t n = st.pending_len;
+    const uint32_t n = st.pending_len & 0xFFFFu, off = st.pending_len >> 16;     // k_commit stores whole 16-byte vectors
     st.pending_len = 0;
-    Rope r{nullptr, 0, io.pending, n};
+    Rope r{nullptr, 0, io.pending + off, n};
     const uint8_t cls = classify_part(r, 0, n);
     UsageRaw raw;
     const uint32_t f = parse_part<true>(r, 0, n, cls, &raw);
@@ -418,6 +419,29 @@ LGW_HD bool prime_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
     return kept;
 }
 
+// One chunk (n > 0 bytes at p) of a PRIMING or COMMITTED stream.  Returns true when the stream
+// committed on this chunk (it is the kept one).
+LGW_HD bool step_chunk(const StepIO& io, const uint8_t* p, uint32_t n) {
+    StreamHdr& st = *io.st;
+    if (st.phase == PH_PRIMING) {
+        ++st.n_chunks_in; st.bytes_in += n;
+        if (prime_chunk(io, p, n)) {
+            st.flags |= SF_EMITTED_ANY;
+            st.flags &= ~(uint16_t)SF_SYNCED;
+            st.carry_b_len = 0;
+            ++st.n_chunks_emitted; st.bytes_emitted += n;
+            relay_chunk(io, p, n, true);                    // the tap sees the kept chunk
+            if (st.carry_b_len == 0) st.flags |= SF_SYNCED; // kept chunk ended on a separator
+            return true;
+        }
+    } else if (st.phase == PH_COMMITTED) {
+        ++st.n_chunks_in; st.bytes_in += n;
+        ++st.n_chunks_emitted; st.bytes_emitted += n;
+        relay_chunk(io, p, n, false);
+    }
+    return false;
+}
+
 // Chunks [c_from, c_to) of one stream, sequentially.  `emit_begin` tracks the first relayed chunk.
 // With stop_at_commit the walk returns right after the kept chunk (the stream has just committed);
 // the return value is the first chunk not consumed.
@@ -428,24 +452,10 @@ LGW_HD uint32_t run_chunks(const StepIO& io, const uint8_t* data, const uint32_t
     for (uint32_t c = c_from; c < c_to; ++c) {
         const uint32_t o = chunk_off[c], n = chunk_off[c + 1] - o;
         if (n == 0) continue;                                   // never yielded (request_handler.py:60-63)
-        if (st.phase == PH_PRIMING) {
-            ++st.n_chunks_in; st.bytes_in += n;
-            if (prime_chunk(io, data + o, n)) {
-                emit_begin = c;
-                st.flags |= SF_EMITTED_ANY;
-                st.flags &= ~(uint16_t)SF_SYNCED;
-                st.carry_b_len = 0;
-                ++st.n_chunks_emitted; st.bytes_emitted += n;
-                relay_chunk(io, data + o, n, true);             // the tap sees the kept chunk
-                if (st.carry_b_len == 0) st.flags |= SF_SYNCED; // kept chunk ended on a separator
-                if (stop_at_commit) return c + 1;
-            }
-        } else if (st.phase == PH_COMMITTED) {
-            ++st.n_chunks_in; st.bytes_in += n;
-            ++st.n_chunks_emitted; st.bytes_emitted += n;
-            relay_chunk(io, data + o, n, false);
-        } else {
-            return c_to;      // PH_FAILED / PH_FREE: the generator is gone; nothing is read or relayed
+        if (st.phase != PH_PRIMING && st.phase != PH_COMMITTED) return c_to;   // the generator is gone
+        if (step_chunk(io, data + o, n)) {
+            emit_begin = c;
+            if (stop_at_commit) return c + 1;
         }
     }
     return c_to;

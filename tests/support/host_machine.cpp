@@ -54,7 +54,7 @@ int lgwt_run_stream(const uint8_t* data, const uint32_t* chunk_off, const uint32
                     uint8_t* detail_out, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
     StreamState st;
     init_stream(st, http_status);
-    std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1), pend(LGW_PENDING_CAP);
+    std::vector<uint8_t> ca(carry_cap + 1), cb(carry_cap + 1), det(detail_cap + 1), pend(LGW_PENDING_STRIDE);
     std::vector<RowEvent> rq(rows_cap + 1);
     uint32_t rcount = 0;
     StepIO io{&st.h, &st.rec, pend.data(), ca.data(), cb.data(), det.data(), carry_cap, detail_cap, rq.data(), &rcount, rows_cap, 0};
