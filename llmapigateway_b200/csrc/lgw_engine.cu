@@ -181,7 +181,7 @@ static int step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, 
     if (n_segs > e->lim.max_streams || n_chunks > e->lim.max_step_chunks || n_bytes > e->lim.max_step_bytes) {
         e->err = "step exceeds the limits given to lgw_engine_create"; return LGW_ERR_CAPACITY;
     }
-    if (n_bytes >= 0xFFFFFFF0ull) { e->err = "step larger than 4 GiB"; return LGW_ERR_CAPACITY; }
+    if (n_bytes >= 0xFFFF0000ull) { e->err = "step larger than 4 GiB - 64 KiB"; return LGW_ERR_CAPACITY; }
     StepArgs a{};
     a.t = e->t; a.data = d_bytes; a.n_bytes = (uint32_t)n_bytes; a.chunk_off = d_chunk_off; a.n_chunks = n_chunks;
     a.seg_chunk = d_seg_chunk; a.seg_slot = d_seg_slot; a.n_segs = n_segs; a.out = d_out; a.seg_out = d_seg_out;

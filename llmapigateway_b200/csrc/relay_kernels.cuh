@@ -19,7 +19,7 @@
 
 #define LGW_RELAY_THREADS 256
 #define LGW_TILE_VECS (LGW_TILE_BYTES / 16)
-#define LGW_TPL_MAX 248u            /* longest event kept as a template */
+#define LGW_TPL_MAX 504u            /* longest event kept as a template */
 #define LGW_TPL_IDS 32u
 
 // 16 KB tile in shared memory, swizzled so that 32 lanes reading the same byte position of 32
@@ -32,11 +32,22 @@ __shared__ __align__(16) uint8_t sh_tile[LGW_TILE_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
-// the block's event template
-__shared__ __align__(4) uint8_t sh_tpl_bytes[LGW_TPL_MAX + 16];   // zero padded
-__shared__ __align__(4) uint8_t sh_tpl_strid[LGW_TPL_MAX + 8];    // value-string id per position (0xff: not inside one)
-__shared__ uint16_t sh_tpl_end[LGW_TPL_IDS];                      // position of each value string's closing quote
-__shared__ uint32_t sh_tpl_len, sh_tpl_flags, sh_tpl_cls, sh_tpl_valid, sh_tpl_cand;
+// the block's event templates (two slots): validated events kept as skeletons
+#define LGW_TPL_SLOTS 2u
+#define LGW_TPL_STRIDE (LGW_TPL_MAX + 16u)
+#define LGW_TPL_MAPSTRIDE (LGW_TPL_MAX + 8u)
+__shared__ __align__(4) uint8_t sh_tpl_bytes[LGW_TPL_SLOTS * LGW_TPL_STRIDE];      // zero padded text
+__shared__ __align__(4) uint8_t sh_tpl_strid[LGW_TPL_SLOTS * LGW_TPL_MAPSTRIDE];   // value-span id per position (0xff: literal)
+__shared__ uint16_t sh_tpl_sstart[LGW_TPL_SLOTS][LGW_TPL_IDS];                     // span start (numbers: first char)
+__shared__ uint16_t sh_tpl_send[LGW_TPL_SLOTS][LGW_TPL_IDS];                       // strings: closing quote; numbers: terminator
+__shared__ uint8_t sh_tpl_skind[LGW_TPL_SLOTS][LGW_TPL_IDS];                       // 0 string value, 1 number value
+__shared__ uint32_t sh_tpl_len[LGW_TPL_SLOTS], sh_tpl_flags[LGW_TPL_SLOTS], sh_tpl_cls[LGW_TPL_SLOTS], sh_tpl_valid[LGW_TPL_SLOTS];
+__shared__ uint32_t sh_tpl_cand;                  // slot 0: lowest thread with a candidate event in this tile
+__shared__ uint32_t sh_tpl_cand1, sh_tpl_cand1_limit;   // slot 1: position of the first event that missed slot 0
+__shared__ uint32_t sh_tpl_tries1;                        // failed attempts to build slot 1 (give up after a few)
+// block-staged copy of a second-template candidate (its tile is gone; one thread walking global
+// memory byte by byte would stall the whole block)
+__shared__ __align__(16) uint8_t sh_stage[LGW_TPL_STRIDE + 16];
 
 // shared-memory loads by 32-bit shared-window address held in a register (the compiler otherwise
 // rebuilds the CTA's shared-window base -- S2UR SR_CgaCtaId + ULEA -- in front of every access)
@@ -71,11 +82,11 @@ struct TileEnv {
     __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (word(pos) >> (8 * (pos & 3u))) & 0xffu; }
     __device__ __forceinline__ uint32_t cls(uint32_t c) const { return lds_u8(cls_s + c); }
     __device__ __forceinline__ uint32_t trans(uint32_t i) const { return lds_u8(trans_s + i); }
-    // template text: the four bytes at k .. k+3
-    __device__ __forceinline__ uint32_t tplu(uint32_t k) const {
-        const uint32_t lo = lds_u32(tpl_s + (k & ~3u));
+    // template text (shared address tb): the four bytes at k .. k+3
+    __device__ __forceinline__ uint32_t tplu(uint32_t tb, uint32_t k) const {
+        const uint32_t lo = lds_u32(tb + (k & ~3u));
         if ((k & 3u) == 0) return lo;
-        return __funnelshift_r(lo, lds_u32(tpl_s + (k & ~3u) + 4), 8 * (k & 3u));
+        return __funnelshift_r(lo, lds_u32(tb + (k & ~3u) + 4), 8 * (k & 3u));
     }
 };
 
@@ -86,86 +97,120 @@ __device__ __forceinline__ uint32_t first_special(uint32_t w) {
     return m ? (uint32_t)(__ffs(m) - 1) >> 3 : 4u;      // the lowest flagged byte is exact (borrows only travel upward)
 }
 
-// Does the event starting at ps follow the block's template?  On success *end = position of the first
-// LF of its LF LF separator (which is verified to be there).
-__device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t ps, uint32_t* end) {
-    const uint32_t lenA = sh_tpl_len;
-    // common prefix
-    uint32_t i = 0, x = 0;
-    const uint32_t sh = 8 * (ps & 3u);
-    uint32_t lo = env.word(ps);
-    while (i < lenA) {
-        const uint32_t hi = env.word(ps + i + 4);
-        const uint32_t wb = sh ? __funnelshift_r(lo, hi, sh) : lo;
-        lo = hi;
-        x = wb ^ lds_u32(env.tpl_s + i);
-        if (x) break;
-        i += 4;
-    }
-    uint32_t L1 = x ? i + ((uint32_t)(__ffs(x) - 1) >> 3) : i;
-    uint32_t q_end;
-    if (L1 >= lenA) q_end = ps + lenA;                         // B starts with all of A
-    else {
-        const uint32_t id = lds_u8(env.strid_s + L1);
-        if (id == 0xffu) return false;                          // the texts part outside a string value
-        uint32_t q = ps + L1;                                   // B: plain string bytes up to the closing quote
-        for (;;) {
-            const uint32_t k = first_special(env.wordu(q));
-            q += k;
-            if (k < 4) break;
-            if (q - ps > 4096u) return false;
+// Does the event starting at ps follow template `slot`?  The event may differ from the template in
+// any number of VALUE spans: inside a string value it may hold any plain bytes (no quote, backslash
+// or control byte) up to its closing quote; a number value may be any valid JSON number (checked
+// with the number rows of the recogniser's table).  Everything else must be byte-identical, so the
+// recogniser would walk the same states: same validity, same top-level keys.
+// On success *end = position of the first LF of the event's LF LF separator (verified to be there).
+__device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot, uint32_t ps, uint32_t* end) {
+    const uint32_t lenA = sh_tpl_len[slot];
+    const uint32_t tb = env.tpl_s + slot * LGW_TPL_STRIDE, sb = env.strid_s + slot * LGW_TPL_MAPSTRIDE;
+    uint32_t ia = 0, ib = ps;
+    bool fresh = false;                      // a span was just skipped: the next bytes must agree
+    for (;;) {
+        while (ia < lenA) {                  // equal run
+            uint32_t x = env.wordu(ib) ^ env.tplu(tb, ia);
+            const uint32_t left = lenA - ia;
+            if (left < 4) x &= (1u << (8 * left)) - 1u;
+            if (x) {
+                const uint32_t k = (uint32_t)(__ffs(x) - 1) >> 3;
+                if (k == 0 && fresh) return false;
+                ia += k; ib += k;
+                break;
+            }
+            fresh = false;
+            const uint32_t adv = left < 4 ? left : 4u;
+            ia += adv; ib += adv;
         }
-        if (env.at(q) != '"') return false;
-        const uint32_t ve = sh_tpl_end[id];                     // A: closing quote of that string
-        if (ve >= lenA) return false;
-        const uint32_t rem = lenA - ve;
-        for (uint32_t j = 0; j < rem; j += 4) {
-            uint32_t d = env.wordu(q + j) ^ env.tplu(ve + j);
-            if (rem - j < 4) d &= (1u << (8 * (rem - j))) - 1u;
-            if (d) return false;
+        if (ia >= lenA) break;
+        const uint32_t id = lds_u8(sb + ia);
+        if (id == 0xffu) return false;       // the texts part at a literal position
+        if (sh_tpl_skind[slot][id] == 0) {   // string value: plain bytes up to the closing quote
+            for (;;) {
+                const uint32_t k = first_special(env.wordu(ib));
+                ib += k;
+                if (k < 4) break;
+                if (ib - ps > 8192u) return false;
+            }
+            if (env.at(ib) != '"') return false;
+        } else {                             // number value: re-validate the event's own number
+            uint32_t bs = ib - (ia - sh_tpl_sstart[slot][id]);
+            uint32_t st = L_VALUE;
+            for (;;) {
+                const uint32_t cl = env.cls(env.at(bs));
+                if (cl < C_MINUS || cl > C_EXP) break;
+                st = env.trans(st * 32 + cl) & 31u;
+                if (st == L_ERR || bs - ps > 8192u) return false;
+                ++bs;
+            }
+            if (!(st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP)) return false;
+            ib = bs;
         }
-        q_end = q + rem;
+        ia = sh_tpl_send[slot][id];
+        fresh = true;
     }
-    const uint32_t t = env.wordu(q_end);
-    if ((t & 0xffffu) != 0x0a0au) return false;                 // LF LF must follow
-    *end = q_end;
+    if ((env.wordu(ib) & 0xffffu) != 0x0a0au) return false;     // LF LF must follow
+    *end = ib;
     return true;
 }
 
-// One thread validates the event at ps and installs it as the block's template (or leaves the
-// template invalid).  limit = end of the segment.
-__device__ __noinline__ void build_template(const TileEnv* env, uint32_t ps, uint32_t limit) {
+// reader over the block-staged copy [base, base + LGW_TPL_STRIDE)
+struct StageEnv {
+    uint32_t base, cls_s, trans_s;
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { const uint32_t d = pos - base; return d < LGW_TPL_STRIDE ? (uint32_t)sh_stage[d] : 0u; }
+    __device__ __forceinline__ uint32_t cls(uint32_t c) const { return lds_u8(cls_s + c); }
+    __device__ __forceinline__ uint32_t trans(uint32_t i) const { return lds_u8(trans_s + i); }
+};
+
+// One thread validates the event at ps and installs it as template `slot` (or leaves the slot
+// invalid).  limit = end of the segment.
+template <class ENV>
+__device__ __noinline__ void build_template(const ENV* env, uint32_t slot, uint32_t ps, uint32_t limit) {
     uint32_t cls = PC_NONE;
     const uint32_t c0 = env->at(ps);
     if (c0 == '{') cls = PC_BRACE;
     else if (c0 == 'd' && env->at(ps + 1) == 'a' && env->at(ps + 2) == 't' && env->at(ps + 3) == 'a' && env->at(ps + 4) == ':' && env->at(ps + 5) == ' ' && env->at(ps + 6) == '{') cls = PC_DATA;
     if (cls == PC_NONE) return;
+    uint8_t* map = sh_tpl_strid + slot * LGW_TPL_MAPSTRIDE;
     LeanMachine lm;
     lm.reset(cls == PC_DATA);
     const uint32_t skip = cls == PC_DATA ? 6u : 0u;
-    for (uint32_t k = 0; k < skip; ++k) sh_tpl_strid[k] = 0xff;
-    uint32_t pos = ps + skip, n_ids = 0, cur = 0xff;
+    for (uint32_t k = 0; k < skip; ++k) map[k] = 0xff;
+    uint32_t pos = ps + skip, n_ids = 0, cur_s = 0xff, cur_n = 0xff;
     for (;;) {
         if (pos + 1 >= limit || pos - ps >= LGW_TPL_MAX) return;
         const uint32_t c = env->at(pos);
         if (c == '\n' && env->at(pos + 1) == '\n') break;
-        const bool in_val = lm.st == L_STR && !lm.in_key;
-        sh_tpl_strid[pos - ps] = in_val ? (uint8_t)cur : (uint8_t)0xff;
-        if (in_val && c == '"' && cur != 0xff) sh_tpl_end[cur] = (uint16_t)(pos - ps);
         const uint32_t prev = lm.st;
+        const bool in_val = prev == L_STR && !lm.in_key;
+        const bool in_num = prev >= L_NUM_MINUS && prev <= L_NUM_EXP;
+        map[pos - ps] = in_val ? (uint8_t)cur_s : in_num ? (uint8_t)cur_n : (uint8_t)0xff;
+        if (in_val && c == '"' && cur_s != 0xff) sh_tpl_send[slot][cur_s] = (uint16_t)(pos - ps);
         lm.step(c, pos, *env);
-        // a string VALUE opens (table state -> L_STR); returning from an escape keeps the id
-        if (prev < LGW_LEAN_ROWS && lm.st == L_STR && !lm.in_key) cur = n_ids < LGW_TPL_IDS ? n_ids++ : 0xffu;
+        const bool now_num = lm.st >= L_NUM_MINUS && lm.st <= L_NUM_EXP;
+        if (in_num && !now_num && cur_n != 0xff) sh_tpl_send[slot][cur_n] = (uint16_t)(pos - ps);      // the terminator
+        if (prev < LGW_LEAN_ROWS && lm.st == L_STR && !lm.in_key) {           // a string VALUE opens (returning from an escape keeps the id)
+            cur_s = n_ids < LGW_TPL_IDS ? n_ids++ : 0xffu;
+            if (cur_s != 0xff) { sh_tpl_skind[slot][cur_s] = 0; sh_tpl_sstart[slot][cur_s] = (uint16_t)(pos + 1 - ps); sh_tpl_send[slot][cur_s] = 0xffff; }
+        }
+        if (!in_num && now_num) {                                             // a number opens
+            cur_n = n_ids < LGW_TPL_IDS ? n_ids++ : 0xffu;
+            if (cur_n != 0xff) { sh_tpl_skind[slot][cur_n] = 1; sh_tpl_sstart[slot][cur_n] = (uint16_t)(pos - ps); sh_tpl_send[slot][cur_n] = 0xffff; }
+            map[pos - ps] = (uint8_t)cur_n;                                    // the number's first character belongs to the span
+        }
         ++pos;
     }
     const uint32_t f = lm.finish();
-    if (!(f & PF_VALID_A) || (f & (TK_USAGE | TK_ERROR | TK_DETAIL | TK_CODE))) return;    // plain events only
+    if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL | TK_CODE))) return;
     if (pos + 2 < limit && env->at(pos + 2) == '\n') return;
     const uint32_t len = pos - ps;
-    for (uint32_t k = 0; k < LGW_TPL_MAX + 16; ++k) sh_tpl_bytes[k] = k < len ? (uint8_t)env->at(ps + k) : (uint8_t)0;
-    sh_tpl_len = len; sh_tpl_flags = f; sh_tpl_cls = cls;
+    for (uint32_t k = 0; k < n_ids; ++k) if (sh_tpl_send[slot][k] >= len) return;      // every span must be closed
+    uint8_t* text = sh_tpl_bytes + slot * LGW_TPL_STRIDE;
+    for (uint32_t k = 0; k < LGW_TPL_STRIDE; ++k) text[k] = k < len ? (uint8_t)env->at(ps + k) : (uint8_t)0;
+    sh_tpl_len[slot] = len; sh_tpl_flags[slot] = f; sh_tpl_cls[slot] = cls;
     __threadfence_block();
-    sh_tpl_valid = 1;
+    sh_tpl_valid[slot] = 1;
 }
 
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
@@ -258,7 +303,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
     const uint32_t n_bytes = a.n_bytes;
     if (tid < 64) reinterpret_cast<uint32_t*>(sh_cls)[tid] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[tid];
     else if (tid < 64 + LGW_LEAN_ROWS * 8) reinterpret_cast<uint32_t*>(sh_trans)[tid - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[tid - 64];
-    if (tid == 0) { sh_tpl_valid = 0; sh_tpl_len = 0; }
+    if (tid == 0) { sh_tpl_valid[0] = sh_tpl_valid[1] = 0; sh_tpl_len[0] = sh_tpl_len[1] = 0; sh_tpl_cand1 = 0xFFFFFFFFu; sh_tpl_tries1 = 0; }
 
     TileEnv env;
     env.tile_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tile));
@@ -275,6 +320,20 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
         env.t0 = t0;
         const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
         __syncthreads();                                       // the previous tile's readers are done
+        // second template: learnt from the first event of the previous tiles that missed slot 0; the
+        // whole block stages its bytes from global memory, one thread validates the staged copy
+        if (!sh_tpl_valid[1] && sh_tpl_cand1 != 0xFFFFFFFFu) {
+            const uint32_t cps = sh_tpl_cand1;
+            for (uint32_t k = tid; k < LGW_TPL_STRIDE; k += LGW_RELAY_THREADS) sh_stage[k] = cps + k < n_bytes ? __ldg(a.data + cps + k) : (uint8_t)0;
+            __syncthreads();
+            if (tid == 0) {
+                StageEnv senv{cps, env.cls_s, env.trans_s};
+                build_template(&senv, 1, cps, sh_tpl_cand1_limit);
+                sh_tpl_cand1 = 0xFFFFFFFFu;
+                if (!sh_tpl_valid[1]) ++sh_tpl_tries1;
+            }
+            __syncthreads();
+        }
 
         // (0) segment range of this tile's chunks
         if (tid >= 224 && tid < 226 && c_hi > c_lo) {
@@ -328,7 +387,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
         const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
 
         // (1b) no template yet: the lowest thread whose chunk starts with an event builds one
-        if (!sh_tpl_valid) {
+        if (!sh_tpl_valid[0]) {
             uint32_t cand_ps = 0, cand_limit = 0;
             if (c_lo + tid < c_hi) {
                 const uint32_t c = c_lo + tid;
@@ -343,11 +402,10 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
                 }
             }
             __syncthreads();
-            if (sh_tpl_cand == tid) build_template(&env, cand_ps, cand_limit);
+            if (sh_tpl_cand == tid) build_template(&env, 0, cand_ps, cand_limit);
             __syncthreads();
         }
-        const bool have_tpl = sh_tpl_valid != 0;
-        const uint32_t tpl_flags = sh_tpl_flags, tpl_cls = sh_tpl_cls;
+        const bool have_tpl0 = sh_tpl_valid[0] != 0, have_tpl1 = sh_tpl_valid[1] != 0;
 
         // (2) events of the chunks that START in this tile
         uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
@@ -371,8 +429,18 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
                 acc_seg = seg; ev_a = ev_b = 0;
             }
 
-            // chunk-level UTF-8: ASCII tiles need no check for chunks that end inside the tile
-            if ((tile_high || e > t0 + LGW_TILE_BYTES) && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
+            // chunk-level UTF-8: ASCII tiles need no check; the part of a chunk beyond the tile is
+            // scanned for bytes >= 0x80 with 16-byte loads first
+            bool need_utf8 = tile_high != 0;
+            if (!need_utf8 && e > t0 + LGW_TILE_BYTES) {
+                uint32_t hi_bits = 0;
+                for (uint32_t v = (t0 + LGW_TILE_BYTES) >> 4; (v << 4) < e; ++v) {
+                    if ((v << 4) + 16 <= n_bytes) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(a.data) + v); hi_bits |= x.x | x.y | x.z | x.w; }
+                    else hi_bits = 0x80;                      // ragged end: take the exact path
+                }
+                need_utf8 = (hi_bits & 0x80808080u) != 0;     // bytes after e in the last vector can only cause a spurious check
+            }
+            if (need_utf8 && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
 
             // where does the event that is open at the start of this chunk begin?
             uint32_t b = o;
@@ -390,9 +458,12 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
             while (ps < e) {
                 uint32_t cls = PC_NONE, f = 0, pos = 0;
                 bool ended = false;
-                if (have_tpl && match_template(env, ps, &pos)) {
+                uint32_t hit = 2;
+                if (have_tpl0 && match_template(env, 0, ps, &pos)) hit = 0;
+                else if (have_tpl1 && match_template(env, 1, ps, &pos)) hit = 1;
+                if (hit < 2) {
                     if (pos + 1 >= e) break;                         // the separator completes in a later chunk
-                    ended = true; cls = tpl_cls; f = tpl_flags;
+                    ended = true; cls = sh_tpl_cls[hit]; f = sh_tpl_flags[hit];
                 } else {
                     // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
                     const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
@@ -401,6 +472,8 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
                         if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
                         else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
                     }
+                    // nominate the event for the second template (any valid event is a sound template, wherever it came from)
+                    if (cls != PC_NONE && have_tpl0 && !have_tpl1 && sh_tpl_tries1 < 3) { atomicMin(&sh_tpl_cand1, ps); sh_tpl_cand1_limit = seg_end; }
                     LeanMachine lm;
                     lm.reset(cls == PC_DATA);
                     pos = ps + (cls == PC_DATA ? 6u : 0u);          // "data: " holds no LF

@@ -277,3 +277,82 @@ def test_gateway_seam_on_the_real_engine(engine):
             assert r["emitted"] == c["emitted"], c["name"]
         assert batcher.steps > 0
     asyncio.run(go())
+
+
+def _template_variant_streams(n_streams, seed):
+    """Streams of near-identical events: the bulk kernel's template shortcut must accept exactly the
+    variants that differ inside ONE string value by plain bytes, and fall back for everything else."""
+    import sse_cases as sc
+    rng = random.Random(seed)
+    base = {"id": "chatcmpl-9x", "object": "chat.completion.chunk", "created": 1726900000, "model": "gpt-x",
+            "choices": [{"index": 0, "delta": {"content": "hello"}, "finish_reason": None}]}
+    plain = ["a", "hello", "hello world", "", "x" * 40, "café 中", "}{][,:", "data: {"]
+    nasty = ['q"q', "b\\s", "line\nbreak", "tab\t", " ", "\x01", "a\\u0041", '\\"']
+    out = []
+    for s in range(n_streams):
+        evs = [sc.ev(base), sc.ev(base)]
+        for _ in range(rng.randrange(5, 40)):
+            d = json.loads(json.dumps(base))
+            k = rng.random()
+            if k < 0.55:
+                d["choices"][0]["delta"]["content"] = rng.choice(plain) + rng.choice(plain)
+            elif k < 0.70:
+                d["choices"][0]["delta"]["content"] = rng.choice(nasty) + rng.choice(plain)
+            elif k < 0.75:
+                d["id"] = "chatcmpl-" + rng.choice(plain)
+            elif k < 0.80:
+                d["created"] = rng.randrange(10**9)
+            elif k < 0.84:
+                d["choices"][0]["finish_reason"] = "stop"
+            elif k < 0.88:
+                d["usage"] = dict(sc.USAGE)
+            elif k < 0.91:
+                d["choices"][0]["delta"] = {"conten": "x"}
+            elif k < 0.94:
+                d = {"error": {"message": "late"}}
+            text = json.dumps(d, separators=(",", ":"), ensure_ascii=bool(rng.random() < 0.3))
+            m = rng.random()
+            if m < 0.06:                      # raw mutations of the text
+                i = rng.randrange(len(text))
+                text = text[:i] + rng.choice(['"', "\\", "}", "{", ",", " ", "\n", "\x00", "x"]) + text[i + 1:]
+            elif m < 0.09:
+                text = text.replace('"content"', '"cont\\u0065nt"')
+            elif m < 0.12:
+                text = text + rng.choice([" ", "\t", "\x0c", "x"])
+            evs.append(sc.ev(text))
+            if rng.random() < 0.03:
+                evs.append(rng.choice([b": ping\n\n", sc.DONE, b"\n", b'{"usage":{"prompt_tokens":1}}\n\n']))
+        blob = b"".join(evs)
+        m = rng.random()
+        if m < 0.6:
+            chunks = evs
+        elif m < 0.8:
+            step = rng.randrange(20, 400)
+            chunks = sc.rechunk(blob, list(range(step, len(blob), step)))
+        else:
+            chunks = sc.rechunk(blob, [rng.randrange(1, len(blob)) for _ in range(rng.randrange(1, 10))])
+        out.append([c for c in chunks if c])
+    return out
+
+
+@pytest.mark.parametrize("n_steps", [1, 2])
+def test_template_shortcut_is_exact(engine, n_steps):
+    from oracle.sse_oracle import run_stream
+    streams = _template_variant_streams(1200, seed=4242 + n_steps)
+    s_fast, r_fast, e_fast = _run_all(engine, streams, 0, n_steps, seed=9)
+    s_seq, r_seq, e_seq = _run_all(engine, streams, 1, n_steps, seed=9)
+    assert e_fast == e_seq and r_fast == r_seq
+    n_rows = 0
+    for i, (a, b) in enumerate(zip(s_fast, s_seq)):
+        assert bytes(a)[:64] == bytes(b)[:64], (i, [c[:80] for c in streams[i][:4]])
+        relay, tap = run_stream(streams[i])
+        assert e_fast[i] == relay.emitted, i
+        assert (a.phase == _abi.PHASE_FAILED) == relay.failed
+        if not relay.failed and not a.n_exotic:
+            got = [json.loads(r[2])[0] for r in r_fast if r[0] == i]
+            if a.flags & _abi.SF_EMITTED_ANY:
+                got.append(json.loads(canon_rows([_abi.usage_rec_to_dict(a.rec)]))[0])
+            assert canon_rows(got) == canon_rows(tap.rows), i
+            assert (not (a.flags & _abi.SF_A_USAGE_BOUND)) == relay.end_raises
+            n_rows += 1
+    assert n_rows > 900
