@@ -19,6 +19,8 @@
 
 #define LGW_RELAY_THREADS 256
 #define LGW_TILE_VECS (LGW_TILE_BYTES / 16)
+#define LGW_HALO_BYTES 512u          /* read-only look-ahead into the next tile: events that straddle the tile end */
+#define LGW_STAGE_BYTES (LGW_TILE_BYTES + LGW_HALO_BYTES)
 #define LGW_TPL_MAX 504u            /* longest event kept as a template */
 #define LGW_TPL_IDS 32u
 
@@ -28,7 +30,7 @@
 //   physical offset = d ^ X(d),  X(d) = ((d >> 3) & 0x30) | ((d >> 7) & 0x0c)
 __device__ __forceinline__ uint32_t swz(uint32_t d) { return d ^ (((d >> 3) & 0x30u) | ((d >> 7) & 0x0cu)); }
 
-__shared__ __align__(16) uint8_t sh_tile[LGW_TILE_BYTES];
+__shared__ __align__(16) uint8_t sh_tile[LGW_STAGE_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
@@ -63,7 +65,7 @@ struct TileEnv {
     // aligned 32-bit word containing byte `pos` (little endian); bytes past n_bytes read as 0
     __device__ __forceinline__ uint32_t word(uint32_t pos) const {
         const uint32_t p4 = pos & ~3u, d = p4 - t0;
-        if (d < LGW_TILE_BYTES) return lds_u32(tile_s + swz(d));
+        if (d < LGW_STAGE_BYTES) return lds_u32(tile_s + swz(d));
         return word_global(p4);
     }
     __device__ __noinline__ uint32_t word_global(uint32_t p4) const {
@@ -109,19 +111,27 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
     uint32_t ia = 0, ib = ps;
     bool fresh = false;                      // a span was just skipped: the next bytes must agree
     for (;;) {
-        while (ia < lenA) {                  // equal run
-            uint32_t x = env.wordu(ib) ^ env.tplu(tb, ia);
-            const uint32_t left = lenA - ia;
-            if (left < 4) x &= (1u << (8 * left)) - 1u;
-            if (x) {
-                const uint32_t k = (uint32_t)(__ffs(x) - 1) >> 3;
-                if (k == 0 && fresh) return false;
-                ia += k; ib += k;
-                break;
+        // equal run: both texts advance a word at a time, so their alignments stay fixed; keep the
+        // aligned words rolling (one load per side per step) and funnel-shift them into place
+        if (ia < lenA) {
+            const uint32_t shB = 8 * (ib & 3u), shA = 8 * (ia & 3u);
+            uint32_t pb = ib & ~3u, pa = ia & ~3u;
+            uint32_t loB = env.word(pb), loA = lds_u32(tb + pa);
+            for (;;) {
+                const uint32_t hiB = env.word(pb + 4), hiA = lds_u32(tb + pa + 4);
+                uint32_t x = (shB ? __funnelshift_r(loB, hiB, shB) : loB) ^ (shA ? __funnelshift_r(loA, hiA, shA) : loA);
+                const uint32_t left = lenA - ia;
+                if (left < 4) x &= (1u << (8 * left)) - 1u;
+                if (x) {
+                    const uint32_t k = (uint32_t)(__ffs(x) - 1) >> 3;
+                    if (k == 0 && fresh) return false;
+                    ia += k; ib += k;
+                    break;
+                }
+                fresh = false;
+                if (left <= 4) { ia += left; ib += left; break; }
+                ia += 4; ib += 4; pb += 4; pa += 4; loB = hiB; loA = hiA;
             }
-            fresh = false;
-            const uint32_t adv = left < 4 ? left : 4u;
-            ia += adv; ib += adv;
         }
         if (ia >= lenA) break;
         const uint32_t id = lds_u8(sb + ia);
@@ -381,6 +391,29 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
                 y.w = kx == 0 ? x[k].w : kx == 1 ? x[k].z : kx == 2 ? x[k].y : x[k].x;
                 const uint32_t slot16 = (r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4);
                 *reinterpret_cast<uint4*>(sh_tile + slot16) = y;
+            }
+            // halo: the first bytes of the next tile, staged only (their own tile copies them out)
+            if (tid < LGW_HALO_BYTES / 16) {
+                const uint32_t v = LGW_TILE_VECS + tid;
+                const uint32_t pos = t0 + v * 16;
+                uint4 h = make_uint4(0, 0, 0, 0);
+                if (pos + 16 <= n_bytes) h = __ldg(src + v);
+                else if (pos < n_bytes) {
+                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                    for (uint32_t b = pos; b < n_bytes; ++b) {
+                        const uint32_t c = a.data[b];
+                        const uint32_t sh = c << (8 * ((b - pos) & 3)), wi = (b - pos) >> 2;
+                        if (wi == 0) w0 |= sh; else if (wi == 1) w1 |= sh; else if (wi == 2) w2 |= sh; else w3 |= sh;
+                    }
+                    h = make_uint4(w0, w1, w2, w3);
+                }
+                const uint32_t r = v >> 2, kx = (r >> 3) & 3u;
+                uint4 y;
+                y.x = kx == 0 ? h.x : kx == 1 ? h.y : kx == 2 ? h.z : h.w;
+                y.y = kx == 0 ? h.y : kx == 1 ? h.x : kx == 2 ? h.w : h.z;
+                y.z = kx == 0 ? h.z : kx == 1 ? h.w : kx == 2 ? h.x : h.y;
+                y.w = kx == 0 ? h.w : kx == 1 ? h.z : kx == 2 ? h.y : h.x;
+                *reinterpret_cast<uint4*>(sh_tile + ((r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4))) = y;
             }
         }
         const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
