@@ -17,7 +17,12 @@
 // recogniser through the same states as A: same validity, same top-level keys -- no byte of it needs
 // to be re-validated beyond the comparison.  Anything else takes the byte-wise recogniser.
 
-#define LGW_RELAY_THREADS 256
+#ifndef LGW_RELAY_THREADS
+#define LGW_RELAY_THREADS 128
+#endif
+#ifndef LGW_RELAY_BLOCKS_PER_SM
+#define LGW_RELAY_BLOCKS_PER_SM 8
+#endif
 #define LGW_TILE_VECS (LGW_TILE_BYTES / 16)
 #define LGW_HALO_BYTES 512u          /* read-only look-ahead into the next tile: events that straddle the tile end */
 #define LGW_STAGE_BYTES (LGW_TILE_BYTES + LGW_HALO_BYTES)
@@ -308,11 +313,13 @@ __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
 
 // ---- k_relay ---------------------------------------------------------------------------------------
 // Persistent blocks: block b handles tiles [b*tiles_per_block, ...) so that its template carries over.
-__global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint32_t n_tiles, uint32_t tiles_per_block) {
+__global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_relay(StepArgs a, uint32_t n_tiles, uint32_t tiles_per_block) {
     const uint32_t tid = threadIdx.x;
     const uint32_t n_bytes = a.n_bytes;
-    if (tid < 64) reinterpret_cast<uint32_t*>(sh_cls)[tid] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[tid];
-    else if (tid < 64 + LGW_LEAN_ROWS * 8) reinterpret_cast<uint32_t*>(sh_trans)[tid - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[tid - 64];
+    for (uint32_t k = tid; k < 64 + LGW_LEAN_ROWS * 8; k += LGW_RELAY_THREADS) {
+        if (k < 64) reinterpret_cast<uint32_t*>(sh_cls)[k] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[k];
+        else reinterpret_cast<uint32_t*>(sh_trans)[k - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[k - 64];
+    }
     if (tid == 0) { sh_tpl_valid[0] = sh_tpl_valid[1] = 0; sh_tpl_len[0] = sh_tpl_len[1] = 0; sh_tpl_cand1 = 0xFFFFFFFFu; sh_tpl_tries1 = 0; }
 
     TileEnv env;
@@ -346,11 +353,11 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, 4) k_relay(StepArgs a, uint
         }
 
         // (0) segment range of this tile's chunks
-        if (tid >= 224 && tid < 226 && c_hi > c_lo) {
-            const uint32_t c = tid == 224 ? c_lo : c_hi - 1;
+        if (tid >= LGW_RELAY_THREADS - 32 && tid < LGW_RELAY_THREADS - 30 && c_hi > c_lo) {
+            const uint32_t c = tid == LGW_RELAY_THREADS - 32 ? c_lo : c_hi - 1;
             uint32_t lo = 0, hi = a.n_segs;
             while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
-            if (tid == 224) sh_seg_lo = lo; else sh_seg_hi = lo;
+            if (tid == LGW_RELAY_THREADS - 32) sh_seg_lo = lo; else sh_seg_hi = lo;
         }
         if (tid == 0) sh_tpl_cand = 0xFFFFFFFFu;
 
@@ -651,7 +658,7 @@ static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cuda
     k_prime<<<(n_prime + 127) / 128, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
     if (n_tiles) {
-        const uint32_t max_blocks = (uint32_t)sm_count * 4u;
+        const uint32_t max_blocks = (uint32_t)sm_count * LGW_RELAY_BLOCKS_PER_SM;
         const uint32_t tpb = (n_tiles + max_blocks - 1) / max_blocks;
         const uint32_t blocks = (n_tiles + tpb - 1) / tpb;
         k_relay<<<blocks, LGW_RELAY_THREADS, 0, stream>>>(a, n_tiles, tpb); ++*launched;

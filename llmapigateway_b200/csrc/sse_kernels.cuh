@@ -56,7 +56,9 @@ struct StepArgs {
     StepScratch s;
 };
 
-#define LGW_TILE_BYTES 16384u
+#ifndef LGW_TILE_BYTES
+#define LGW_TILE_BYTES 8192u
+#endif
 
 static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size_t max_chunks, size_t max_bytes) {
     cudaError_t r;
