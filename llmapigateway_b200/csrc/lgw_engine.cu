@@ -375,3 +375,7 @@ extern "C" int lgw_device_zero(lgw_engine* e, void* d, uint64_t bytes) {
     CK(e, cudaMemsetAsync(d, 0, bytes, e->stream));
     return LGW_OK;
 }
+
+#ifdef LGW_DEBUG_TIMING
+extern "C" int lgw_debug_read(unsigned long long* out) { return cudaMemcpyFromSymbol(out, lgw::g_dbg, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2; }
+#endif

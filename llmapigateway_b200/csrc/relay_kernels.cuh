@@ -39,6 +39,12 @@ __shared__ __align__(16) uint8_t sh_tile[LGW_STAGE_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
+#ifdef LGW_DEBUG_TIMING
+__device__ unsigned long long g_dbg[16];
+#define DBG_STAMP(i) do { if (blockIdx.x == 7 && threadIdx.x == 0 && tile == tile_first + 3) g_dbg[i] = clock64(); } while (0)
+#else
+#define DBG_STAMP(i) do {} while (0)
+#endif
 // the block's event templates (two slots): validated events kept as skeletons
 #define LGW_TPL_SLOTS 2u
 #define LGW_TPL_STRIDE (LGW_TPL_MAX + 16u)
@@ -118,25 +124,28 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
     for (;;) {
         // equal run: both texts advance a word at a time, so their alignments stay fixed; keep the
         // aligned words rolling (one load per side per step) and funnel-shift them into place
+        // (a funnel shift by 0 returns the low word)
         if (ia < lenA) {
             const uint32_t shB = 8 * (ib & 3u), shA = 8 * (ia & 3u);
-            uint32_t pb = ib & ~3u, pa = ia & ~3u;
-            uint32_t loB = env.word(pb), loA = lds_u32(tb + pa);
-            for (;;) {
-                const uint32_t hiB = env.word(pb + 4), hiA = lds_u32(tb + pa + 4);
-                uint32_t x = (shB ? __funnelshift_r(loB, hiB, shB) : loB) ^ (shA ? __funnelshift_r(loA, hiA, shA) : loA);
-                const uint32_t left = lenA - ia;
-                if (left < 4) x &= (1u << (8 * left)) - 1u;
-                if (x) {
-                    const uint32_t k = (uint32_t)(__ffs(x) - 1) >> 3;
-                    if (k == 0 && fresh) return false;
-                    ia += k; ib += k;
-                    break;
-                }
-                fresh = false;
-                if (left <= 4) { ia += left; ib += left; break; }
-                ia += 4; ib += 4; pb += 4; pa += 4; loB = hiB; loA = hiA;
+            uint32_t pb = ib & ~3u, pa = tb + (ia & ~3u);
+            uint32_t loB = env.word(pb), loA = lds_u32(pa);
+            uint32_t left = lenA - ia, x = 0;
+            while (left > 4) {
+                const uint32_t hiB = env.word(pb + 4), hiA = lds_u32(pa + 4);
+                x = __funnelshift_r(loB, hiB, shB) ^ __funnelshift_r(loA, hiA, shA);
+                if (x) break;
+                pb += 4; pa += 4; loB = hiB; loA = hiA; left -= 4;
             }
+            if (!x) {                                   // the last (possibly partial) word
+                const uint32_t hiB = env.word(pb + 4), hiA = lds_u32(pa + 4);
+                x = __funnelshift_r(loB, hiB, shB) ^ __funnelshift_r(loA, hiA, shA);
+                if (left < 4) x &= (1u << (8 * left)) - 1u;
+            }
+            uint32_t adv = (lenA - ia) - left;          // bytes matched in whole words
+            adv += x ? ((uint32_t)(__ffs(x) - 1) >> 3) : left;
+            if (adv == 0 && fresh) return false;
+            ia += adv; ib += adv;
+            fresh = false;
         }
         if (ia >= lenA) break;
         const uint32_t id = lds_u8(sb + ia);
@@ -152,6 +161,13 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
         } else {                             // number value: re-validate the event's own number
             uint32_t bs = ib - (ia - sh_tpl_sstart[slot][id]);
             uint32_t st = L_VALUE;
+            {   // common case first: a plain run of digits ("0" or [1-9][0-9]*)
+                uint32_t q = bs, c = env.at(q);
+                if (c - '1' < 9u) { do { c = env.at(++q); } while (c - '0' < 10u); }
+                else if (c == '0') c = env.at(++q);
+                else q = bs;
+                if (q != bs && c != '.' && c != 'e' && c != 'E') { ib = q; ia = sh_tpl_send[slot][id]; fresh = true; continue; }
+            }
             for (;;) {
                 const uint32_t cl = env.cls(env.at(bs));
                 if (cl < C_MINUS || cl > C_EXP) break;
@@ -336,7 +352,9 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         const uint32_t t0 = tile * LGW_TILE_BYTES;
         env.t0 = t0;
         const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
+        DBG_STAMP(0);
         __syncthreads();                                       // the previous tile's readers are done
+        DBG_STAMP(1);
         // second template: learnt from the first event of the previous tiles that missed slot 0; the
         // whole block stages its bytes from global memory, one thread validates the staged copy
         if (!sh_tpl_valid[1] && sh_tpl_cand1 != 0xFFFFFFFFu) {
@@ -423,7 +441,9 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                 *reinterpret_cast<uint4*>(sh_tile + ((r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4))) = y;
             }
         }
+        DBG_STAMP(2);
         const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
+        DBG_STAMP(3);
         const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
 
         // (1b) no template yet: the lowest thread whose chunk starts with an event builds one
@@ -447,6 +467,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         }
         const bool have_tpl0 = sh_tpl_valid[0] != 0, have_tpl1 = sh_tpl_valid[1] != 0;
 
+        DBG_STAMP(4);
         // (2) events of the chunks that START in this tile
         uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
         for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
@@ -569,6 +590,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
             if (a_usage) pl->a_usage = 1;
         }
 
+        DBG_STAMP(5);
         // (3) post the event counters: one atomic per warp when the whole warp worked on one segment
         {
             const uint32_t full = 0xFFFFFFFFu;
