@@ -26,6 +26,8 @@ struct lgw_engine {
     int device = 0;
     lgw_limits lim{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;       // copy streams of the pipelined host entry point
+    cudaEvent_t ev_in[16]{}, ev_k[16]{};
     DeviceTables t{};               // persistent per-slot state
     uint32_t* d_rowq_count = nullptr;
     RowEvent* d_rowq = nullptr;
@@ -74,6 +76,9 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     e->sm_count = prop.multiProcessorCount;
     if ((r = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", r);
     e->stream = e->own_stream;
+    if ((r = cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", r);
+    if ((r = cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", r);
+    for (int i = 0; i < 16; ++i) { if ((r = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", r); if ((r = cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", r); }
     for (auto& ev : e->ev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
     for (auto& ev : e->rev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
     const size_t S = e->lim.max_streams, C = e->lim.max_step_chunks, B = e->lim.max_step_bytes;
@@ -111,6 +116,9 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->rev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_rows); cudaFree(e->d_nrows);
+    for (int i = 0; i < 16; ++i) { if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]); }
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return LGW_OK;
@@ -175,18 +183,24 @@ extern "C" int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uin
 }
 
 // ---- the step ------------------------------------------------------------------------------------
+// One launch set over segments [s0, s1) of a step (the whole step when s0 = 0, s1 = n_segs).  All
+// offsets and chunk indices stay absolute, so slices of a pipelined step share the device arrays.
 static int step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, const uint32_t* d_chunk_off, uint32_t n_chunks,
                        const uint32_t* d_seg_chunk, const uint32_t* d_seg_slot, uint32_t n_segs,
-                       uint8_t* d_out, SegResult* d_seg_out) {
+                       uint8_t* d_out, SegResult* d_seg_out,
+                       uint32_t s0 = 0, uint32_t s1 = 0xFFFFFFFFu, uint32_t c0 = 0, uint32_t c1 = 0xFFFFFFFFu,
+                       uint32_t b0 = 0, uint64_t b1 = ~0ull, bool reset_rows = true) {
     if (n_segs > e->lim.max_streams || n_chunks > e->lim.max_step_chunks || n_bytes > e->lim.max_step_bytes) {
         e->err = "step exceeds the limits given to lgw_engine_create"; return LGW_ERR_CAPACITY;
     }
     if (n_bytes >= 0xFFFF0000ull) { e->err = "step larger than 4 GiB - 64 KiB"; return LGW_ERR_CAPACITY; }
+    if (s1 == 0xFFFFFFFFu) { s1 = n_segs; c1 = n_chunks; b1 = n_bytes; }
     StepArgs a{};
-    a.t = e->t; a.data = d_bytes; a.n_bytes = (uint32_t)n_bytes; a.chunk_off = d_chunk_off; a.n_chunks = n_chunks;
-    a.seg_chunk = d_seg_chunk; a.seg_slot = d_seg_slot; a.n_segs = n_segs; a.out = d_out; a.seg_out = d_seg_out;
+    a.t = e->t; a.data = d_bytes; a.n_bytes = (uint32_t)b1; a.chunk_off = d_chunk_off; a.n_chunks = n_chunks;
+    a.tile_base = b0 & ~(LGW_TILE_BYTES - 1u); a.chunk_lo = c0; a.chunk_hi = c1;
+    a.seg_chunk = d_seg_chunk + s0; a.seg_slot = d_seg_slot + s0; a.n_segs = s1 - s0; a.out = d_out; a.seg_out = d_seg_out + s0;
     a.rowq = e->d_rowq; a.rowq_count = e->d_rowq_count; a.rowq_cap = e->lim.rowq_cap; a.s = e->scratch;
-    CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
+    if (reset_rows) CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
     int launched = 0;
     cudaError_t r = launch_step(a, e->mode, e->sm_count, e->stream, e->ev, &launched);
     e->launches += (uint64_t)launched;
@@ -237,14 +251,42 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
     for (uint32_t s = 0; s < n_segs; ++s) if (seg_chunk[s] > seg_chunk[s + 1] || seg_slot[s] >= e->lim.max_streams) { e->err = "bad segment table"; return LGW_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaEventRecord(e->ev[4], e->stream));
-    if (n_bytes) CK(e, cudaMemcpyAsync(e->d_in, bytes, n_bytes, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_chunk_off, chunk_off, (size_t)(n_chunks + 1) * 4, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_seg_chunk, seg_chunk, (size_t)(n_segs + 1) * 4, cudaMemcpyHostToDevice, e->stream));
-    if (n_segs) CK(e, cudaMemcpyAsync(e->d_seg_slot, seg_slot, (size_t)n_segs * 4, cudaMemcpyHostToDevice, e->stream));
-    int rc = step_device(e, e->d_in, n_bytes, e->d_chunk_off, n_chunks, e->d_seg_chunk, e->d_seg_slot, n_segs, e->d_out, e->d_seg_out);
-    if (rc != LGW_OK) return rc;
-    if (n_bytes) CK(e, cudaMemcpyAsync(out_bytes, e->d_out, n_bytes, cudaMemcpyDeviceToHost, e->stream));
+    // Pipelined: the step is cut at segment boundaries into up to 8 slices; the upload of slice k+1,
+    // the kernels of slice k and the download of slice k-1 overlap (PCIe is full duplex).
+    uint32_t n_slices = n_bytes >= (8u << 20) && n_segs >= 16 ? 4u : 1u;
+    if (const char* sl = getenv("LGW_SLICES")) { int v = atoi(sl); if (v >= 1 && v <= 16) n_slices = (uint32_t)v; }
+    if (e->mode == 1 || n_segs < n_slices) n_slices = 1;
+    uint32_t cut[18]; cut[0] = 0;
+    for (uint32_t j = 1; j < n_slices; ++j) {           // segment index whose start byte is closest below j/n of the bytes
+        const uint64_t want = n_bytes * j / n_slices;
+        uint32_t lo = cut[j - 1], hi = n_segs;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint64_t)chunk_off[seg_chunk[mid]] < want) lo = mid + 1; else hi = mid; }
+        cut[j] = lo;
+    }
+    cut[n_slices] = n_segs;
+    CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
+    int rc = LGW_OK;
+    for (uint32_t j = 0; j < n_slices; ++j) {
+        const uint32_t s0 = cut[j], s1 = cut[j + 1];
+        if (s1 <= s0 && n_slices > 1) continue;
+        const uint32_t c0 = seg_chunk[s0], c1 = seg_chunk[s1];
+        const uint32_t b0 = chunk_off[c0]; const uint64_t b1 = chunk_off[c1];
+        cudaStream_t sin = n_slices > 1 ? e->s_in : e->stream, sout = n_slices > 1 ? e->s_out : e->stream;
+        if (b1 > b0) CK(e, cudaMemcpyAsync(e->d_in + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, sin));
+        CK(e, cudaMemcpyAsync(e->d_chunk_off + c0, chunk_off + c0, (size_t)(c1 - c0 + 1) * 4, cudaMemcpyHostToDevice, sin));
+        CK(e, cudaMemcpyAsync(e->d_seg_chunk + s0, seg_chunk + s0, (size_t)(s1 - s0 + 1) * 4, cudaMemcpyHostToDevice, sin));
+        if (s1 > s0) CK(e, cudaMemcpyAsync(e->d_seg_slot + s0, seg_slot + s0, (size_t)(s1 - s0) * 4, cudaMemcpyHostToDevice, sin));
+        if (n_slices > 1) { CK(e, cudaEventRecord(e->ev_in[j], sin)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[j], 0)); }
+        rc = step_device(e, e->d_in, n_bytes, e->d_chunk_off, n_chunks, e->d_seg_chunk, e->d_seg_slot, n_segs, e->d_out, e->d_seg_out,
+                         s0, s1, c0, c1, b0, b1, false);
+        if (rc != LGW_OK) return rc;
+        if (n_slices > 1) { CK(e, cudaEventRecord(e->ev_k[j], e->stream)); CK(e, cudaStreamWaitEvent(sout, e->ev_k[j], 0)); }
+        if (b1 > b0) CK(e, cudaMemcpyAsync(out_bytes + b0, e->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, sout));
+    }
+    // per-segment results: one copy at the end (a copy into pageable host memory blocks the host thread,
+    // which would serialise the pipeline if it were issued per slice)
     if (n_segs) CK(e, cudaMemcpyAsync(seg_out, e->d_seg_out, (size_t)n_segs * sizeof(SegResult), cudaMemcpyDeviceToHost, e->stream));
+    if (n_slices > 1) { CK(e, cudaStreamSynchronize(e->s_out)); CK(e, cudaStreamSynchronize(e->s_in)); }
     CK(e, cudaEventRecord(e->ev[5], e->stream));
     rc = lgw_fetch_rows(e, rows_out, rows_cap, n_rows);
     if (rc != LGW_OK) return rc;

@@ -300,8 +300,8 @@ __device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o
 __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n_tiles) {
-        const uint32_t target = i * LGW_TILE_BYTES;
-        uint32_t lo = 0, hi = a.n_chunks;                 // first c in [0, n_chunks] with chunk_off[c] >= target
+        const uint32_t target = a.tile_base + i * LGW_TILE_BYTES;
+        uint32_t lo = a.chunk_lo, hi = a.chunk_hi;        // first c in [chunk_lo, chunk_hi] with chunk_off[c] >= target
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.chunk_off + mid) < target) lo = mid + 1; else hi = mid; }
         a.s.tile_chunk[i] = lo;
     }
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
     const uint32_t tile_first = blockIdx.x * tiles_per_block;
     const uint32_t tile_last = min(n_tiles, tile_first + tiles_per_block);
     for (uint32_t tile = tile_first; tile < tile_last; ++tile) {
-        const uint32_t t0 = tile * LGW_TILE_BYTES;
+        const uint32_t t0 = a.tile_base + tile * LGW_TILE_BYTES;
         env.t0 = t0;
         const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
         DBG_STAMP(0);
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
 
 static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
     cudaError_t r;
-    const uint32_t n_tiles = (a.n_bytes + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
+    const uint32_t n_tiles = (a.n_bytes - a.tile_base + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
     const uint32_t n_prime = (a.n_segs > n_tiles + 1 ? a.n_segs : n_tiles + 1);
     k_prime<<<(n_prime + 127) / 128, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;

@@ -48,8 +48,10 @@ struct StepScratch {
 
 struct StepArgs {
     DeviceTables t;
-    const uint8_t* data; uint32_t n_bytes;
+    const uint8_t* data; uint32_t n_bytes;     // n_bytes = end of the valid bytes (a slice of a pipelined step ends earlier)
     const uint32_t* chunk_off; uint32_t n_chunks;
+    uint32_t tile_base;                        // byte offset of tile 0 (multiple of LGW_TILE_BYTES)
+    uint32_t chunk_lo, chunk_hi;               // chunks of this launch: [chunk_lo, chunk_hi)
     const uint32_t* seg_chunk; const uint32_t* seg_slot; uint32_t n_segs;
     uint8_t* out; SegResult* seg_out;
     RowEvent* rowq; uint32_t* rowq_count; uint32_t rowq_cap;
