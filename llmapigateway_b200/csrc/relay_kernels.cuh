@@ -58,6 +58,7 @@ __shared__ uint32_t sh_tpl_len[LGW_TPL_SLOTS], sh_tpl_flags[LGW_TPL_SLOTS], sh_t
 __shared__ uint32_t sh_tpl_cand;                  // slot 0: lowest thread with a candidate event in this tile
 __shared__ uint32_t sh_tpl_cand1, sh_tpl_cand1_limit;   // slot 1: position of the first event that missed slot 0
 __shared__ uint32_t sh_tpl_tries1;                        // failed attempts to build slot 1 (give up after a few)
+__shared__ uint32_t sh_tpl_miss, sh_tpl_replace1, sh_tpl_cstate[LGW_TPL_SLOTS];   // misses in the current tile; slot 1 was re-learnt; cache states
 // block-staged copy of a second-template candidate (its tile is gone; one thread walking global
 // memory byte by byte would stall the whole block)
 __shared__ __align__(16) uint8_t sh_stage[LGW_TPL_STRIDE + 16];
@@ -244,6 +245,19 @@ __device__ __noinline__ void build_template(const ENV* env, uint32_t slot, uint3
     sh_tpl_valid[slot] = 1;
 }
 
+// publish a freshly built local template to the engine-wide cache (first writer wins per slot;
+// `replace` lets a block that re-learnt a slot overwrite a stale entry)
+__device__ __noinline__ void publish_template(TemplateCache* tc, uint32_t slot, bool replace) {
+    const uint32_t expect = replace ? 2u : 0u;
+    if (atomicCAS(&tc->state[slot], expect, 1u) != expect) return;
+    tc->len[slot] = sh_tpl_len[slot]; tc->flags[slot] = sh_tpl_flags[slot]; tc->cls[slot] = sh_tpl_cls[slot];
+    for (uint32_t k = 0; k < LGW_TPL_IDS; ++k) { tc->sstart[slot][k] = sh_tpl_sstart[slot][k]; tc->send[slot][k] = sh_tpl_send[slot][k]; tc->skind[slot][k] = sh_tpl_skind[slot][k]; }
+    for (uint32_t k = 0; k < LGW_TPLC_TEXT; ++k) tc->text[slot][k] = sh_tpl_bytes[slot * LGW_TPL_STRIDE + k];
+    for (uint32_t k = 0; k < LGW_TPLC_MAP; ++k) tc->map[slot][k] = sh_tpl_strid[slot * LGW_TPL_MAPSTRIDE + k];
+    __threadfence();
+    atomicExch(&tc->state[slot], 2u);
+}
+
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
 __device__ __noinline__ bool chunk_utf8_ok(const TileEnv* rd, uint32_t o, uint32_t e) {
     uint32_t p = o;
@@ -337,6 +351,20 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         else reinterpret_cast<uint32_t*>(sh_trans)[k - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[k - 64];
     }
     if (tid == 0) { sh_tpl_valid[0] = sh_tpl_valid[1] = 0; sh_tpl_len[0] = sh_tpl_len[1] = 0; sh_tpl_cand1 = 0xFFFFFFFFu; sh_tpl_tries1 = 0; }
+    __syncthreads();
+    {   // start from the engine-wide template cache when it has entries
+        const TemplateCache* tc = a.s.tpl_cache;
+        if (tid < LGW_TPL_SLOTS) sh_tpl_cstate[tid] = *reinterpret_cast<const volatile uint32_t*>(&tc->state[tid]);
+        if (tid == 0) { sh_tpl_miss = 0; sh_tpl_replace1 = 0; }
+        __syncthreads();
+        for (uint32_t slot = 0; slot < LGW_TPL_SLOTS; ++slot) {
+            if (sh_tpl_cstate[slot] != 2u) continue;                                                // one decision for the whole block
+            for (uint32_t k = tid; k < LGW_TPLC_TEXT; k += LGW_RELAY_THREADS) sh_tpl_bytes[slot * LGW_TPL_STRIDE + k] = tc->text[slot][k];
+            for (uint32_t k = tid; k < LGW_TPLC_MAP; k += LGW_RELAY_THREADS) sh_tpl_strid[slot * LGW_TPL_MAPSTRIDE + k] = tc->map[slot][k];
+            if (tid < LGW_TPL_IDS) { sh_tpl_sstart[slot][tid] = tc->sstart[slot][tid]; sh_tpl_send[slot][tid] = tc->send[slot][tid]; sh_tpl_skind[slot][tid] = tc->skind[slot][tid]; }
+            if (tid == 0) { sh_tpl_len[slot] = tc->len[slot]; sh_tpl_flags[slot] = tc->flags[slot]; sh_tpl_cls[slot] = tc->cls[slot]; sh_tpl_valid[slot] = 1; }
+        }
+    }
 
     TileEnv env;
     env.tile_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tile));
@@ -355,6 +383,13 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         DBG_STAMP(0);
         __syncthreads();                                       // the previous tile's readers are done
         DBG_STAMP(1);
+        // slot 1 adapts: when most events of the previous tile matched neither template, forget it and
+        // re-learn it from an event that missed (the engine-wide cache entry is then replaced too)
+        if (tid == 0) {
+            if (sh_tpl_valid[1] && sh_tpl_miss > LGW_RELAY_THREADS / 2) { sh_tpl_valid[1] = 0; sh_tpl_tries1 = 0; sh_tpl_replace1 = 1; }
+            sh_tpl_miss = 0;
+        }
+        __syncthreads();
         // second template: learnt from the first event of the previous tiles that missed slot 0; the
         // whole block stages its bytes from global memory, one thread validates the staged copy
         if (!sh_tpl_valid[1] && sh_tpl_cand1 != 0xFFFFFFFFu) {
@@ -365,7 +400,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                 StageEnv senv{cps, env.cls_s, env.trans_s};
                 build_template(&senv, 1, cps, sh_tpl_cand1_limit);
                 sh_tpl_cand1 = 0xFFFFFFFFu;
-                if (!sh_tpl_valid[1]) ++sh_tpl_tries1;
+                if (!sh_tpl_valid[1]) ++sh_tpl_tries1; else publish_template(a.s.tpl_cache, 1, sh_tpl_replace1 != 0);
             }
             __syncthreads();
         }
@@ -462,7 +497,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                 }
             }
             __syncthreads();
-            if (sh_tpl_cand == tid) build_template(&env, 0, cand_ps, cand_limit);
+            if (sh_tpl_cand == tid) { build_template(&env, 0, cand_ps, cand_limit); if (sh_tpl_valid[0]) publish_template(a.s.tpl_cache, 0, false); }
             __syncthreads();
         }
         const bool have_tpl0 = sh_tpl_valid[0] != 0, have_tpl1 = sh_tpl_valid[1] != 0;
@@ -534,7 +569,10 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                         else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
                     }
                     // nominate the event for the second template (any valid event is a sound template, wherever it came from)
-                    if (cls != PC_NONE && have_tpl0 && !have_tpl1 && sh_tpl_tries1 < 3) { atomicMin(&sh_tpl_cand1, ps); sh_tpl_cand1_limit = seg_end; }
+                    if (cls != PC_NONE && have_tpl0) {
+                        if (!have_tpl1 && sh_tpl_tries1 < 3) { atomicMin(&sh_tpl_cand1, ps); sh_tpl_cand1_limit = seg_end; }
+                        else if (have_tpl1) atomicAdd(&sh_tpl_miss, 1u);
+                    }
                     LeanMachine lm;
                     lm.reset(cls == PC_DATA);
                     pos = ps + (cls == PC_DATA ? 6u : 0u);          // "data: " holds no LF

@@ -40,9 +40,23 @@ struct SegPlan {
 };
 static_assert(sizeof(SegPlan) == 64, "SegPlan");
 
+// Event templates that survive across launches (any validated event is a sound template wherever it
+// came from, so sharing them between blocks, steps and slices is safe).  state: 0 empty, 1 being
+// written, 2 ready.
+#define LGW_TPLC_TEXT 520u
+#define LGW_TPLC_MAP 512u
+struct TemplateCache {
+    uint32_t state[2], len[2], flags[2], cls[2];
+    uint16_t sstart[2][32], send[2][32];
+    uint8_t skind[2][32];
+    uint8_t text[2][LGW_TPLC_TEXT];
+    uint8_t map[2][LGW_TPLC_MAP];
+};
+
 struct StepScratch {
     SegPlan* plan;             // [max_streams]
     uint32_t* tile_chunk;      // [max tiles + 2] first chunk starting at or after each tile
+    TemplateCache* tpl_cache;  // persistent across steps
     uint32_t max_tiles;
 };
 
@@ -67,9 +81,11 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size
     if ((r = cudaMalloc((void**)&s.plan, max_streams * sizeof(SegPlan))) != cudaSuccess) return r;
     s.max_tiles = (uint32_t)((max_bytes + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES);
     if ((r = cudaMalloc((void**)&s.tile_chunk, ((size_t)s.max_tiles + 2) * 4)) != cudaSuccess) return r;
+    if ((r = cudaMalloc((void**)&s.tpl_cache, sizeof(TemplateCache))) != cudaSuccess) return r;
+    if ((r = cudaMemset(s.tpl_cache, 0, sizeof(TemplateCache))) != cudaSuccess) return r;
     return cudaSuccess;
 }
-static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); s.plan = nullptr; s.tile_chunk = nullptr; }
+static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); cudaFree(s.tpl_cache); s.plan = nullptr; s.tile_chunk = nullptr; s.tpl_cache = nullptr; }
 
 __device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot, StreamHdr* local_hdr) {
     StepIO io;
