@@ -43,6 +43,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # ---- CPU reference arm ------------------------------------------------------------------------
 def _cpu_worker(args):
     seed, n_streams, n_events = args
@@ -201,9 +210,17 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- value: device-resident ------------------------------------------------------------------
+    sampler = ClockSampler(local); sampler.start()
     for k in range(W):
         device_step(k); eng.sync()
-    sampler = ClockSampler(local); sampler.start()
+    # keep the GPU under the same load for ~0.4 s before the timed steps so that the clock sampler
+    # (20 ms period) sees clocks and throttle reasons under this very workload; not timed
+    t_load = time.perf_counter(); k_load = 0
+    while time.perf_counter() - t_load < 0.4:
+        device_step(k_load); k_load += 1
+        if k_load % 16 == 0:
+            eng.sync()
+    eng.sync()
     barrier()
     l0 = eng.launch_count()
     kern = {"prime": 0.0, "relay": 0.0, "commit": 0.0}
@@ -288,7 +305,7 @@ def main():
                 "json_gbs": e2e_value * EVENT_BYTES / 1e9},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": _traffic(), "peak_source": peak_src,
                      "kernel": "k_prime + k_relay + k_commit (summed; 128 B algorithmic per 64-B event)"},
         "wall_s_timed_loop": t_wall,
     }
