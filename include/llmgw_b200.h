@@ -218,6 +218,63 @@ int64_t lgw_rollup_bucket_of(int64_t ts_us, int period);
 /* device time of the last accum / emit kernels, milliseconds */
 int lgw_rollup_last_ms(lgw_engine* e, float ms[2]);
 
+/* ---- request-body rewrite: SURVEY 8 rows a1, a3, a4 --------------------------------------------------
+ * Replaces, for a batch of client requests, chat.py:31-45 (parse: lgw_bodies_scan) and, per upstream
+ * attempt, chat.py:112-119,:135-139,:150,:164-168 (deepcopy + key assignments) followed by the encoder
+ * of request_handler.py:23 (httpx `json=`) or :153 (json5.dumps): lgw_bodies_rewrite.
+ * The rule table (loader.py:150-154 dicts) is compiled on the host into "plans": one plan = the ordered
+ * key assignments of one attempt (rule x sub-provider x retry) in one render mode, with keys and values
+ * already rendered (llmapigateway_b200/rewrite.py does this; rule lookup/rotation a2 stays in Python). */
+enum lgw_render_mode {
+    LGW_RM_HTTPX028 = 0,   /* json.dumps(ensure_ascii=False, separators=(",",":"), allow_nan=False)  (installed httpx 0.28.1) */
+    LGW_RM_HTTPX027 = 1,   /* json.dumps(obj) stdlib defaults                                        (requirements.txt pin)   */
+    LGW_RM_JSON5 = 2       /* json5.dumps defaults (non-streaming branch); restated, unpinned                               */
+};
+enum lgw_body_status {
+    LGW_BODY_OK = 0,
+    LGW_BODY_PARSE_ERROR = 1,   /* chat.py:37-39: HTTP 400 "Error reading request body" (bad UTF-8/JSON, not an object, no "model") */
+    LGW_BODY_NO_MODEL = 2,      /* chat.py:44-45: HTTP 400 "Missing 'model'"                                                       */
+    LGW_BODY_OVERFLOW = 3,      /* out slot too small: out_len holds the size needed                                               */
+    LGW_BODY_EXOTIC = 4,        /* shape the engine does not model (duplicate keys, float with > 15 significant digits,
+                                   key > 128 B, > 24 keys in one object below... see DESIGN.md): caller takes its own path    */
+    LGW_BODY_ENCODE_ERROR = 5   /* the reference's encoder raises (NaN/Infinity under allow_nan=False, lone surrogate under
+                                   ensure_ascii=False): the attempt fails at request_handler.py:183                            */
+};
+typedef struct lgw_body_op {        /* one `payload[key] = value` */
+    uint32_t key_off, key_len;      /* key text (UTF-8) in the blob */
+    uint32_t rkey_off, rkey_len;    /* key as the mode renders it   */
+    uint32_t rval_off, rval_len;    /* value as the mode renders it */
+    uint32_t flags;                 /* bit0: only when the client's body lacks the key (chat.py:114) */
+    uint32_t _pad;
+} lgw_body_op;
+typedef struct lgw_body_plan { uint32_t op_begin, op_end, mode, _pad; } lgw_body_plan;
+typedef struct lgw_body_result { uint32_t status, out_len; } lgw_body_result;
+typedef struct lgw_body_scan {
+    uint32_t status;                /* LGW_BODY_OK / PARSE_ERROR / NO_MODEL */
+    uint32_t model_len;             /* bytes of the model string (may exceed model_cap: truncated) */
+    uint8_t model_kind, model_truthy, stream_kind, stream_truthy;   /* lgw_kind of body["model"], body.get("stream") */
+    uint32_t _pad;
+} lgw_body_scan;
+
+/* upload the compiled plan table (replaces the previous one; at most 32 ops per plan) */
+int lgw_rules_load(lgw_engine* e, const lgw_body_plan* plans, uint32_t n_plans,
+                   const lgw_body_op* ops, uint32_t n_ops, const uint8_t* blob, uint32_t blob_len);
+/* chat.py:31-45 for n bodies: host pointers; models_out = n slots of model_cap bytes */
+int lgw_bodies_scan(lgw_engine* e, const uint8_t* bodies, const uint64_t* body_off /* n+1 */, uint32_t n,
+                    uint32_t model_cap, lgw_body_scan* scans_out, uint8_t* models_out);
+/* one attempt's payload bytes for n bodies: body i is rewritten by plan plan_idx[i].  Outputs are packed
+ * back to back: body i occupies out[out_off[i] .. out_off[i+1]) (empty unless status OK).  out_cap is the
+ * size of `out`; slot_cap bounds one output (bodies needing more report LGW_BODY_OVERFLOW). */
+int lgw_bodies_rewrite(lgw_engine* e, const uint8_t* bodies, const uint64_t* body_off /* n+1 */, uint32_t n,
+                       const uint32_t* plan_idx, uint32_t slot_cap,
+                       uint8_t* out, uint64_t out_cap, uint64_t* out_off /* n+1 */, lgw_body_result* results);
+/* same with every pointer in device memory (bench `value`, callers that keep bodies resident) */
+int lgw_bodies_rewrite_device(lgw_engine* e, const uint8_t* d_bodies, const uint64_t* d_body_off, uint32_t n,
+                              uint64_t n_bytes, const uint32_t* d_plan_idx, uint32_t slot_cap,
+                              uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off, lgw_body_result* d_results);
+/* device time of the last rewrite's kernels (rewrite, offsets, pack), milliseconds */
+int lgw_bodies_last_ms(lgw_engine* e, float ms[3]);
+
 /* ---- device memory helpers for callers without their own CUDA allocator ----------------------------- */
 int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out);
 int lgw_device_free(lgw_engine* e, void* p);

@@ -16,6 +16,7 @@ EXPORTS = [
     "lgw_launch_count", "lgw_alloc_pinned", "lgw_free_pinned",
     "lgw_usage_rollup_accum", "lgw_usage_rollup_emit", "lgw_rollup_bucket_of", "lgw_rollup_last_ms",
     "lgw_device_alloc", "lgw_device_free", "lgw_device_upload", "lgw_device_download", "lgw_device_zero",
+    "lgw_rules_load", "lgw_bodies_scan", "lgw_bodies_rewrite", "lgw_bodies_rewrite_device", "lgw_bodies_last_ms",
 ]
 
 _lib = None
@@ -66,6 +67,13 @@ def load():
     lib.lgw_device_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     lib.lgw_device_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     lib.lgw_device_zero.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lgw_rules_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.lgw_bodies_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.lgw_bodies_rewrite.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lgw_bodies_rewrite_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32,
+                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lgw_bodies_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
     if hasattr(lib, "lgw_engine_set_mode"):
         lib.lgw_engine_set_mode.argtypes = [C.c_void_p, C.c_int]
     if lib.lgw_abi_version() != 1:

@@ -10,6 +10,7 @@
 #include "stream_machine.cuh"
 #include "sse_kernels.cuh"
 #include "rollup.cuh"
+#include "body_kernels.cuh"
 
 using namespace lgw;
 
@@ -44,6 +45,13 @@ struct lgw_engine {
     float ms[4]{0, 0, 0, 0};
     bool timed = false;
     uint64_t launches = 0;
+    // request-body rewrite (rows a1-a4): plan table + grow-only staging
+    BodyPlan* d_plans = nullptr; BodyOp* d_ops = nullptr; uint8_t* d_blob = nullptr; uint32_t n_plans = 0, n_ops = 0;
+    uint8_t *b_in = nullptr, *b_slots = nullptr, *b_out = nullptr, *b_models = nullptr;
+    uint64_t *b_off = nullptr, *b_out_off = nullptr; uint32_t* b_plan_idx = nullptr; BodyResult* b_results = nullptr; BodyScan* b_scans = nullptr;
+    uint64_t b_in_cap = 0, b_slots_cap = 0, b_out_cap = 0, b_n_cap = 0, b_models_cap = 0;
+    cudaEvent_t bev[4]{};
+    float bms[3]{0, 0, 0};
     int mode = 0;                   // 0: fast path + general fix-up, 1: general path only
     int sm_count = 148;
     std::string err;
@@ -81,6 +89,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     for (int i = 0; i < 16; ++i) { if ((r = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", r); if ((r = cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", r); }
     for (auto& ev : e->ev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
     for (auto& ev : e->rev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
+    for (auto& ev : e->bev) if ((r = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", r);
     const size_t S = e->lim.max_streams, C = e->lim.max_step_chunks, B = e->lim.max_step_bytes;
 #define ALLOC(ptr, bytes) if ((r = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return fail("cudaMalloc " #ptr, r)
     ALLOC(e->t.state, S * sizeof(StreamState));
@@ -116,6 +125,10 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->rev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_rows); cudaFree(e->d_nrows);
+    cudaFree(e->d_plans); cudaFree(e->d_ops); cudaFree(e->d_blob);
+    cudaFree(e->b_in); cudaFree(e->b_slots); cudaFree(e->b_out); cudaFree(e->b_models); cudaFree(e->b_off); cudaFree(e->b_out_off);
+    cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans);
+    for (auto& ev : e->bev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 16; ++i) { if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]); }
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -421,3 +434,138 @@ extern "C" int lgw_device_zero(lgw_engine* e, void* d, uint64_t bytes) {
 #ifdef LGW_DEBUG_TIMING
 extern "C" int lgw_debug_read(unsigned long long* out) { return cudaMemcpyFromSymbol(out, lgw::g_dbg, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2; }
 #endif
+
+
+// ---- request-body rewrite (rows a1, a3, a4) -------------------------------------------------------
+static_assert(sizeof(BodyOp) == sizeof(lgw_body_op), "lgw_body_op");
+static_assert(sizeof(BodyPlan) == sizeof(lgw_body_plan), "lgw_body_plan");
+static_assert(sizeof(BodyResult) == sizeof(lgw_body_result), "lgw_body_result");
+static_assert(sizeof(BodyScan) == sizeof(lgw_body_scan), "lgw_body_scan");
+
+template <class T>
+static cudaError_t grow(T*& p, uint64_t& cap, uint64_t need) {
+    if (need <= cap && p) return cudaSuccess;
+    if (p) { cudaError_t r = cudaFree(p); p = nullptr; cap = 0; if (r != cudaSuccess) return r; }
+    const uint64_t n = need + need / 4 + 64;
+    cudaError_t r = cudaMalloc((void**)&p, n * sizeof(T));
+    if (r == cudaSuccess) cap = n;
+    return r;
+}
+
+extern "C" int lgw_rules_load(lgw_engine* e, const lgw_body_plan* plans, uint32_t n_plans,
+                              const lgw_body_op* ops, uint32_t n_ops, const uint8_t* blob, uint32_t blob_len) {
+    if (!e || (n_plans && !plans) || (n_ops && !ops) || (blob_len && !blob)) return LGW_ERR_ARG;
+    for (uint32_t i = 0; i < n_plans; ++i) {
+        if (plans[i].op_begin > plans[i].op_end || plans[i].op_end > n_ops || plans[i].op_end - plans[i].op_begin > 32 || plans[i].mode > 2) {
+            e->err = "lgw_rules_load: malformed plan"; return LGW_ERR_ARG; }
+    }
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const lgw_body_op& o = ops[i];
+        if ((uint64_t)o.key_off + o.key_len > blob_len || (uint64_t)o.rkey_off + o.rkey_len > blob_len || (uint64_t)o.rval_off + o.rval_len > blob_len) {
+            e->err = "lgw_rules_load: op outside the blob"; return LGW_ERR_ARG; }
+    }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_plans); cudaFree(e->d_ops); cudaFree(e->d_blob); e->d_plans = nullptr; e->d_ops = nullptr; e->d_blob = nullptr;
+    CK(e, cudaMalloc((void**)&e->d_plans, (n_plans + 1) * sizeof(BodyPlan)));
+    CK(e, cudaMalloc((void**)&e->d_ops, (n_ops + 1) * sizeof(BodyOp)));
+    CK(e, cudaMalloc((void**)&e->d_blob, blob_len + 16));
+    if (n_plans) CK(e, cudaMemcpyAsync(e->d_plans, plans, n_plans * sizeof(BodyPlan), cudaMemcpyHostToDevice, e->stream));
+    if (n_ops) CK(e, cudaMemcpyAsync(e->d_ops, ops, n_ops * sizeof(BodyOp), cudaMemcpyHostToDevice, e->stream));
+    if (blob_len) CK(e, cudaMemcpyAsync(e->d_blob, blob, blob_len, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->n_plans = n_plans; e->n_ops = n_ops;
+    return LGW_OK;
+}
+
+static int bodies_stage_in(lgw_engine* e, const uint8_t* bodies, const uint64_t* body_off, uint32_t n) {
+    const uint64_t n_bytes = body_off[n];
+    for (uint32_t i = 0; i < n; ++i) if (body_off[i + 1] < body_off[i] || body_off[i + 1] - body_off[i] > 0xFFFFFFF0ull) { e->err = "body offsets not monotonic"; return LGW_ERR_ARG; }
+    CK(e, grow(e->b_in, e->b_in_cap, n_bytes + 64));
+    uint64_t ncap = e->b_n_cap;
+    if (n + 1 > e->b_n_cap || !e->b_off) {
+        uint64_t c1 = e->b_n_cap, c2 = e->b_n_cap, c3 = e->b_n_cap, c4 = e->b_n_cap, c5 = e->b_n_cap;
+        CK(e, grow(e->b_off, c1, n + 1)); CK(e, grow(e->b_out_off, c2, n + 1)); CK(e, grow(e->b_plan_idx, c3, n + 1));
+        CK(e, grow(e->b_results, c4, n + 1)); CK(e, grow(e->b_scans, c5, n + 1));
+        ncap = c1;
+    }
+    e->b_n_cap = ncap;
+    if (n_bytes) CK(e, cudaMemcpyAsync(e->b_in, bodies, n_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->b_off, body_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_bodies_scan(lgw_engine* e, const uint8_t* bodies, const uint64_t* body_off, uint32_t n,
+                               uint32_t model_cap, lgw_body_scan* scans_out, uint8_t* models_out) {
+    if (!e || !body_off || (!bodies && n && body_off[n]) || !scans_out || (model_cap && !models_out)) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    CK(e, cudaSetDevice(e->device));
+    int rc = bodies_stage_in(e, bodies, body_off, n);
+    if (rc != LGW_OK) return rc;
+    CK(e, grow(e->b_models, e->b_models_cap, (uint64_t)n * model_cap + 16));
+    k_body_scan<<<(n + LGW_BODY_WARPS - 1) / LGW_BODY_WARPS, 32 * LGW_BODY_WARPS, 0, e->stream>>>(e->b_in, e->b_off, n, model_cap, e->b_scans, e->b_models);
+    ++e->launches;
+    CK(e, cudaGetLastError());
+    CK(e, cudaMemcpyAsync(scans_out, e->b_scans, n * sizeof(BodyScan), cudaMemcpyDeviceToHost, e->stream));
+    if (model_cap) CK(e, cudaMemcpyAsync(models_out, e->b_models, (uint64_t)n * model_cap, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+static int bodies_launch(lgw_engine* e, const uint8_t* d_bodies, const uint64_t* d_body_off, uint32_t n, const uint32_t* d_plan_idx,
+                         uint32_t slot_cap, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off, BodyResult* d_results) {
+    if (!e->d_plans) { e->err = "lgw_bodies_rewrite before lgw_rules_load"; return LGW_ERR_ARG; }
+    CK(e, grow(e->b_slots, e->b_slots_cap, (uint64_t)n * slot_cap + 64));
+    CK(e, cudaEventRecord(e->bev[0], e->stream));
+    k_body_rewrite<<<(n + LGW_BODY_WARPS - 1) / LGW_BODY_WARPS, 32 * LGW_BODY_WARPS, 0, e->stream>>>(
+        d_bodies, d_body_off, n, d_plan_idx, e->d_plans, e->n_plans, e->d_ops, e->d_blob, e->b_slots, slot_cap, d_results);
+    CK(e, cudaEventRecord(e->bev[1], e->stream));
+    k_body_offsets<<<1, 1024, 0, e->stream>>>(d_results, n, out_cap, d_out_off);
+    CK(e, cudaEventRecord(e->bev[2], e->stream));
+    const uint32_t grid = n < (uint32_t)e->sm_count * 8u ? n : (uint32_t)e->sm_count * 8u;
+    k_body_pack<<<grid, 256, 0, e->stream>>>(e->b_slots, slot_cap, d_results, n, d_out_off, d_out, out_cap);
+    CK(e, cudaEventRecord(e->bev[3], e->stream));
+    e->launches += 3;
+    CK(e, cudaGetLastError());
+    return LGW_OK;
+}
+
+extern "C" int lgw_bodies_rewrite_device(lgw_engine* e, const uint8_t* d_bodies, const uint64_t* d_body_off, uint32_t n, uint64_t n_bytes,
+                                         const uint32_t* d_plan_idx, uint32_t slot_cap, uint8_t* d_out, uint64_t out_cap,
+                                         uint64_t* d_out_off, lgw_body_result* d_results) {
+    (void)n_bytes;
+    if (!e || !d_bodies || !d_body_off || !d_plan_idx || !d_out || !d_out_off || !d_results || slot_cap == 0) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    CK(e, cudaSetDevice(e->device));
+    return bodies_launch(e, d_bodies, d_body_off, n, d_plan_idx, slot_cap, d_out, out_cap, d_out_off, (BodyResult*)d_results);
+}
+
+extern "C" int lgw_bodies_rewrite(lgw_engine* e, const uint8_t* bodies, const uint64_t* body_off, uint32_t n,
+                                  const uint32_t* plan_idx, uint32_t slot_cap,
+                                  uint8_t* out, uint64_t out_cap, uint64_t* out_off, lgw_body_result* results) {
+    if (!e || !body_off || (!bodies && n && body_off[n]) || !plan_idx || (!out && out_cap) || !out_off || !results || slot_cap == 0) return LGW_ERR_ARG;
+    if (n == 0) { out_off[0] = 0; return LGW_OK; }
+    CK(e, cudaSetDevice(e->device));
+    int rc = bodies_stage_in(e, bodies, body_off, n);
+    if (rc != LGW_OK) return rc;
+    CK(e, cudaMemcpyAsync(e->b_plan_idx, plan_idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(e, grow(e->b_out, e->b_out_cap, out_cap + 64));
+    rc = bodies_launch(e, e->b_in, e->b_off, n, e->b_plan_idx, slot_cap, e->b_out, out_cap, e->b_out_off, e->b_results);
+    if (rc != LGW_OK) return rc;
+    // the packed size is only known on the device: offsets first, then exactly that many bytes
+    CK(e, cudaMemcpyAsync(out_off, e->b_out_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(results, e->b_results, n * sizeof(BodyResult), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    const uint64_t total = out_off[n] < out_cap ? out_off[n] : out_cap;
+    if (total) CK(e, cudaMemcpyAsync(out, e->b_out, total, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_bodies_last_ms(lgw_engine* e, float ms[3]) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    cudaEventSynchronize(e->bev[3]);
+    for (int i = 0; i < 3; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->bev[i], e->bev[i + 1]) == cudaSuccess) e->bms[i] = t; ms[i] = e->bms[i]; }
+    return LGW_OK;
+}

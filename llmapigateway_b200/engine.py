@@ -144,3 +144,57 @@ class Engine:
         n = C.c_uint64(0)
         self._ck(self._lib.lgw_launch_count(self._h, C.byref(n)), "launch_count")
         return n.value
+
+    # ---- request-body rewrite (rows a1-a4) -------------------------------------------------------
+    def load_rules(self, plans) -> None:
+        """Upload a compiled plan table (`rewrite.RulePlans`).  chat.py reads the rule dicts per request;
+        here they are compiled once per config load."""
+        from . import rewrite as rw
+        p, o, blob = plans.packed()
+        assert p.dtype == rw.PLAN_DTYPE and o.dtype == rw.OP_DTYPE
+        self._ck(self._lib.lgw_rules_load(self._h, _ptr(p) if len(p) else None, len(p), _ptr(o) if len(o) else None, len(o),
+                                          _ptr(blob), len(blob)), "rules_load")
+        self._plan_growth = plans.max_growth()
+
+    def scan_bodies(self, bodies, model_cap: int = 256):
+        """chat.py:31-45 for a batch: (SCAN_DTYPE array, list of model bytes)."""
+        from . import rewrite as rw
+        buf, off = rw.pack_bodies(bodies)
+        n = len(bodies)
+        scans = np.zeros(max(n, 1), dtype=rw.SCAN_DTYPE)
+        models = np.zeros(max(n, 1) * model_cap, dtype=np.uint8)
+        self._ck(self._lib.lgw_bodies_scan(self._h, _ptr(buf), _ptr(off), n, model_cap, _ptr(scans), _ptr(models)), "bodies_scan")
+        texts = [bytes(models[i * model_cap:i * model_cap + min(int(scans["model_len"][i]), model_cap)]) for i in range(n)]
+        return scans[:n], texts
+
+    def rewrite_packed(self, buf: np.ndarray, off: np.ndarray, plan_idx: np.ndarray, slot_cap: int, out: np.ndarray | None = None):
+        """One upstream attempt for n packed bodies -> (out bytes, out_off[n+1], RESULT_DTYPE[n])."""
+        from . import rewrite as rw
+        n = len(off) - 1
+        plan_idx = np.ascontiguousarray(plan_idx, dtype=np.uint32)
+        assert len(plan_idx) == n and off.dtype == np.uint64 and buf.dtype == np.uint8
+        if out is None:
+            growth = getattr(self, "_plan_growth", 0) + 64
+            out = np.empty(min(n * slot_cap, 6 * int(off[n]) + n * growth) + 64, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        res = np.zeros(max(n, 1), dtype=rw.RESULT_DTYPE)
+        self._ck(self._lib.lgw_bodies_rewrite(self._h, _ptr(buf), _ptr(off), n, _ptr(plan_idx), slot_cap,
+                                              _ptr(out), out.nbytes, _ptr(out_off), _ptr(res)), "bodies_rewrite")
+        return out, out_off, res[:n]
+
+    def rewrite_bodies(self, bodies, plan_idx, slot_cap: int | None = None):
+        """list[bytes] in -> list[(status, payload bytes)] (payload empty unless status == BODY_OK)."""
+        from . import rewrite as rw
+        buf, off = rw.pack_bodies(bodies)
+        if slot_cap is None:
+            longest = max((len(b) for b in bodies), default=0)
+            slot_cap = 6 * longest + getattr(self, "_plan_growth", 0) + 64      # worst case: every byte becomes \u00XX
+            slot_cap = (slot_cap + 15) & ~15
+        out, out_off, res = self.rewrite_packed(buf, off, np.asarray(plan_idx, dtype=np.uint32), slot_cap)
+        return [(int(res["status"][i]), bytes(out[int(out_off[i]):int(out_off[i + 1])]) if res["status"][i] == rw.BODY_OK else b"")
+                for i in range(len(bodies))]
+
+    def bodies_last_ms(self):
+        ms = (C.c_float * 3)()
+        self._ck(self._lib.lgw_bodies_last_ms(self._h, C.byref(ms)), "bodies_last_ms")
+        return dict(rewrite=ms[0], offsets=ms[1], pack=ms[2])

@@ -146,3 +146,47 @@ def pack_streams(streams: list[list[bytes]], slots: list[int] | None = None) -> 
     slots = list(range(len(streams))) if slots is None else slots
     return PackedBatch(data, np.array(offs, dtype=np.uint32), np.array(segc, dtype=np.uint32),
                        np.array(slots, dtype=np.uint32), 0, [])
+
+
+# ---- config 2: client request bodies (BASELINE.json configs[1]: 1024 non-streaming requests, 4 KiB JSON bodies) ----
+_WORDS = ("the of and to in is that for it as was with be by on not he this are or his from at which but have an had they you were "
+          "their one all we can her has there been if more when will would who so no out up said what its about than into them only "
+          "model token stream gateway provider fallback latency batch kernel memory request response usage prompt completion").split()
+_NON_ASCII = ["é", "ü", "中文", "日本語", "—", "“quoted”", "\U0001F600", "naïve", "Ω"]
+
+
+def chat_bodies(n: int = 1024, target_bytes: int = 4096, seed: int = 2, model: str = "gw/chain", non_ascii: float = 0.02,
+                stream: bool = False) -> list[bytes]:
+    """Synthetic OpenAI chat-completions request bodies of about `target_bytes` each, written the way
+    client SDKs write them (json.dumps defaults or compact separators, a few escapes, some UTF-8)."""
+    import json
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        msgs = [{"role": "system", "content": "You are a helpful assistant.\nAnswer briefly; cite \"sources\" when asked."}]
+        body = {"model": model, "messages": msgs, "temperature": float(rng.choice([0.0, 0.2, 0.7, 1.0, 1.5])),
+                "top_p": float(rng.choice([1.0, 0.9, 0.95])), "max_tokens": int(rng.choice([256, 512, 1024, 4096])), "stream": stream,
+                "user": "user-%06d" % int(rng.integers(0, 10 ** 6))}
+        if rng.random() < 0.3:
+            body["stop"] = ["\n\n", "###"]
+        if rng.random() < 0.2:
+            body["tools"] = [{"type": "function", "function": {"name": "lookup", "description": "Look something up",
+                                                                "parameters": {"type": "object", "properties": {"q": {"type": "string"}}, "required": ["q"]}}}]
+        if rng.random() < 0.15:
+            body["usage"] = {"include": True}
+        compact = rng.random() < 0.5
+        ascii_out = rng.random() < 0.5
+        turn = 0
+        while True:
+            words = []
+            for _ in range(int(rng.integers(20, 90))):
+                words.append(_NON_ASCII[int(rng.integers(0, len(_NON_ASCII)))] if rng.random() < non_ascii else _WORDS[int(rng.integers(0, len(_WORDS)))])
+                if rng.random() < 0.03:
+                    words.append("\n")
+            msgs.append({"role": "user" if turn % 2 == 0 else "assistant", "content": " ".join(words)})
+            turn += 1
+            text = json.dumps(body, ensure_ascii=ascii_out, separators=(",", ":") if compact else None)
+            if len(text.encode("utf-8")) >= target_bytes - 200:
+                break
+        out.append(text.encode("utf-8"))
+    return out

@@ -28,7 +28,7 @@ ES5_RESERVED = {
     "class", "const", "enum", "export", "extends", "import", "super", "null", "true", "false",
     "implements", "interface", "let", "package", "private", "protected", "public", "static", "yield",
 }
-_IDENT = re.compile(r"^[A-Za-z_$][A-Za-z0-9_$]*$")
+_IDENT = re.compile(r"[A-Za-z_$][A-Za-z0-9_$]*\Z")
 
 
 def parse_body(raw: bytes):

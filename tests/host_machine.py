@@ -80,3 +80,27 @@ def run_stream(chunks: list[bytes], steps: list[int] | None = None, http_status:
                           rows, C.c_uint32(rows_cap), C.byref(n_rows))
     return dict(segs=list(segs), state=st, detail=detail.raw[:st.detail_len],
                 rows=[rows[i] for i in range(n_rows.value)], step_chunk=step_chunk)
+
+
+def rewrite_body(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 << 16):
+    """body_machine.cuh rewrite_body() on the host build: (status, out_bytes, needed_len)."""
+    p = plans[plan_idx]
+    sub = np.ascontiguousarray(ops[p["op_begin"]:p["op_end"]])
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    n = C.c_uint32(0)
+    buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    lib().lgwt_rewrite_body.restype = C.c_uint32
+    st = lib().lgwt_rewrite_body(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.c_int(int(p["mode"])),
+                                 sub.ctypes.data_as(C.c_void_p), C.c_uint32(len(sub)), blob.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n))
+    return st, bytes(out[:min(n.value, cap)]), n.value
+
+
+def scan_body(raw: bytes, model_cap: int = 256):
+    from llmapigateway_b200.rewrite import SCAN_DTYPE
+    sc = np.zeros(1, dtype=SCAN_DTYPE)
+    model = np.zeros(model_cap, dtype=np.uint8)
+    buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    lib().lgwt_scan_body(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), sc.ctypes.data_as(C.c_void_p),
+                         model.ctypes.data_as(C.c_void_p), C.c_uint32(model_cap))
+    return sc[0], bytes(model[:min(int(sc[0]["model_len"]), model_cap)])

@@ -71,3 +71,23 @@ int lgwt_run_stream(const uint8_t* data, const uint32_t* chunk_off, const uint32
 }
 
 }  // extern "C"
+
+// ---- request-body rewrite (body_machine.cuh) ----------------------------------------------------
+#include "../../llmapigateway_b200/csrc/body_machine.cuh"
+static_assert(sizeof(BodyOp) == sizeof(lgw_body_op), "BodyOp");
+static_assert(sizeof(BodyScan) == sizeof(lgw_body_scan), "BodyScan");
+
+extern "C" {
+
+uint32_t lgwt_rewrite_body(const uint8_t* in, uint32_t n, int mode, const lgw_body_op* ops, uint32_t n_ops,
+                           const uint8_t* blob, uint8_t* out, uint32_t cap, uint32_t* out_len) {
+    BodyRewriter m;
+    return rewrite_body(m, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len);
+}
+
+void lgwt_scan_body(const uint8_t* in, uint32_t n, lgw_body_scan* sc, uint8_t* model_buf, uint32_t model_cap) {
+    BodyRewriter m;
+    scan_body(m, in, n, (BodyScan*)sc, model_buf, model_cap);
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""Request-body rewrite (rows a1-a4) on the CPU: the device machine (host build, test aid) against the
+oracle and the reference-generated goldens; the host-side plan compiler against the oracle's rule_ops."""
+import base64
+import json
+import random
+
+import numpy as np
+import pytest
+
+from llmapigateway_b200 import rewrite as rw
+from oracle import body_oracle as bo
+import body_cases as bc
+import host_machine as hm
+from golden_io import GOLDEN as GOLDEN_DIR
+
+MODE_NAMES = ["httpx028", "httpx027", "json5"]
+
+
+@pytest.fixture(scope="module")
+def plans028():
+    return rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+
+
+@pytest.fixture(scope="module")
+def plans027():
+    return rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx027")
+
+
+def test_golden_attempt_bytes(plans028):
+    """every attempt the reference's chat_completions made (payload bytes by the real httpx) == the machine's output"""
+    doc = json.loads((GOLDEN_DIR / "body_cases.json").read_text())
+    assert doc["rules"]["gw/chain"]["fallback_models"] == bc.RULES["gw/chain"]["fallback_models"][:4]
+    plans, ops, blob = plans028.packed()
+    n = 0
+    for case in doc["cases"]:
+        raw = base64.b64decode(case["body"])
+        model = json.loads(raw)["model"]
+        seq = bc.CHAIN_ATTEMPTS if model == "gw/chain" else [None]
+        assert len(seq) == len(case["attempts"])
+        for att, a in zip(seq, case["attempts"]):
+            want = base64.b64decode(a["httpx_bytes"])
+            pi = plans028.plan_index(model, *att) if att else plans028.plan_index(model)
+            st, out, need = hm.rewrite_body(raw, plans, ops, blob, pi)
+            assert st == rw.BODY_OK and out == want, (model, att, out, want)
+            n += 1
+    assert n == 25
+
+
+def test_plan_compiler_matches_oracle_rule_ops(plans028):
+    for ri, sub, retry in bc.CHAIN_ATTEMPTS + [(4, -1, False)]:
+        rule, prov, sp, rt = bc.attempt_for_oracle(ri, sub, retry)
+        assert rw.attempt_assignments(rule, prov, sp, rt) == bo.rule_ops(rule, prov, sp, rt)
+
+
+def _check(raw, plans_obj, packed, att, mode_name, stream):
+    plans, ops, blob = packed
+    ri, sub, retry = att
+    rule, prov, sp, rt = bc.attempt_for_oracle(ri, sub, retry)
+    pi = plans_obj.plan_index("gw/chain", ri, sub, retry, stream=stream)
+    assert MODE_NAMES[int(plans[pi]["mode"])] == mode_name
+    st, out, need = hm.rewrite_body(raw, plans, ops, blob, pi)
+    ost, body, _, _ = bo.parse_body(raw)
+    if ost == 1:
+        # the rewrite entry point reports malformed bodies; a missing "model" is lgw_bodies_scan's business
+        try:
+            json.loads(raw.decode("utf-8"))
+            is_obj = isinstance(json.loads(raw.decode("utf-8")), dict)
+        except Exception:
+            assert st == rw.BODY_PARSE_ERROR, raw
+            return "parse_error"
+        if not is_obj:
+            assert st in (rw.BODY_OK, rw.BODY_EXOTIC, rw.BODY_ENCODE_ERROR)     # non-object roots are filtered by the scan
+            return "non_object"
+        body = json.loads(raw.decode("utf-8"))
+    payload = bo.rewrite_payload(body, bo.rule_ops(rule, prov, sp, rt))
+    try:
+        want = bo.RENDERERS[mode_name](payload)
+    except (ValueError, UnicodeEncodeError):
+        assert st == rw.BODY_ENCODE_ERROR, (raw, st)
+        return "encode_error"
+    if st == rw.BODY_EXOTIC:
+        assert _may_be_exotic(payload, mode_name), (mode_name, raw)
+        return "exotic"
+    assert st == rw.BODY_OK, (raw, st)
+    assert out == want, (mode_name, raw, out, want)
+    return "ok"
+
+
+def _may_be_exotic(v, mode_name):
+    """shapes the engine is allowed to hand back: json5 keys whose identifier test reaches a
+    non-ASCII character, floats outside 1e-290..1e290"""
+    if isinstance(v, dict):
+        for k, x in v.items():
+            if mode_name == "json5":
+                for i, ch in enumerate(k):
+                    if ch.isascii() and (ch.isalpha() or ch in "_$" or (i > 0 and ch.isdigit())):
+                        continue
+                    if not ch.isascii():
+                        return True
+                    break
+            if _may_be_exotic(x, mode_name):
+                return True
+        return False
+    if isinstance(v, list):
+        return any(_may_be_exotic(x, mode_name) for x in v)
+    if isinstance(v, float):
+        return v != 0 and not (1e-289 < abs(v) < 1e289)
+    return False
+
+
+def test_fuzz_against_oracle(plans028, plans027):
+    rng = random.Random(20260921)
+    tally = {}
+    packed = {"httpx028": plans028.packed(), "httpx027": plans027.packed()}
+    atts = bc.CHAIN_ATTEMPTS + [(4, -1, False)]
+    for it in range(4000):
+        body = bc.rand_body(rng)
+        raw = bc.spell(rng, body).encode("utf-8")
+        att = atts[it % len(atts)]
+        for mode_name, obj, stream in (("httpx028", plans028, True), ("httpx027", plans027, True), ("json5", plans028, False)):
+            r = _check(raw, obj, packed["httpx027" if obj is plans027 else "httpx028"], att, mode_name, stream)
+            tally[r] = tally.get(r, 0) + 1
+    assert tally.get("ok", 0) > 9000, tally
+    assert tally.get("exotic", 0) < 2500, tally
+
+
+@pytest.mark.parametrize("text,status", [
+    (b'{"model":"gw/chain","a":1,"a":2}', rw.BODY_EXOTIC),                     # duplicate key (dict keeps first position, last value)
+    (b'{"model":"gw/chain","x":{"k":1,"k":1}}', rw.BODY_EXOTIC),
+    (b'{"model":"gw/chain","t":0.1234567890123456789}', rw.BODY_EXOTIC),       # repr() needs the correctly rounded 17-digit form
+    (b'{"model":"gw/chain","t":1e999}', rw.BODY_EXOTIC),
+    (b'{"model":"gw/chain","t":NaN}', rw.BODY_ENCODE_ERROR),
+    (b'{"model":"gw/chain","t":-Infinity}', rw.BODY_ENCODE_ERROR),
+    (b'{"model":"gw/chain","t":"\\ud800"}', rw.BODY_ENCODE_ERROR),
+    (b'{"model":"gw/chain","t":"\\ud800\\u0041"}', rw.BODY_ENCODE_ERROR),
+    (b'{"model":"gw/chain",}', rw.BODY_PARSE_ERROR),
+    (b'{"model":"gw/chain"} x', rw.BODY_PARSE_ERROR),
+    (b'{"model":"gw/chain","t":01}', rw.BODY_PARSE_ERROR),
+    (b'{"model":"gw/chain","t":"\xff"}', rw.BODY_PARSE_ERROR),
+    (b'{"model":"gw/chain","t":"a\nb"}', rw.BODY_PARSE_ERROR),
+    (b'', rw.BODY_PARSE_ERROR),
+    (b'{"model":"gw/chain","t":[1,2}', rw.BODY_PARSE_ERROR),
+    (b"{'model':'gw/chain'}", rw.BODY_PARSE_ERROR),                             # JSON5-only syntax: unpinned, reported as a parse error
+])
+def test_statuses(plans028, text, status):
+    plans, ops, blob = plans028.packed()
+    st, out, need = hm.rewrite_body(text, plans, ops, blob, plans028.plan_index("gw/chain", 0))
+    assert st == status
+
+
+def test_nan_and_lone_surrogates_in_ascii_modes(plans027, plans028):
+    raw = b'{"model":"gw/chain","t":[NaN,Infinity,-Infinity,"\\ud800","\\udc00\\ud83d\\ude00\\ud83d"]}'
+    for obj, stream, mode in ((plans027, True, "httpx027"), (plans028, False, "json5")):
+        assert _check(raw, obj, obj.packed(), (0, -1, False), mode, stream) == "ok"
+
+
+def test_overflow_reports_needed_length(plans028):
+    plans, ops, blob = plans028.packed()
+    raw = json.dumps({"model": "gw/chain", "messages": [{"role": "user", "content": "x" * 500}]}).encode()
+    pi = plans028.plan_index("gw/chain", 1)
+    st, out, need = hm.rewrite_body(raw, plans, ops, blob, pi, cap=1 << 12)
+    assert st == rw.BODY_OK and need == len(out)
+    st2, out2, need2 = hm.rewrite_body(raw, plans, ops, blob, pi, cap=100)
+    assert st2 == rw.BODY_OVERFLOW and need2 == need and out2 == out[:100]
+
+
+def test_scan_matches_parse_body():
+    rng = random.Random(7)
+    cases = [b'{"model":"m","stream":true}', b'{"stream":1}', b'[1]', b'"s"', b'3', b'{"model":""}', b'{"model":null,"stream":"yes"}',
+             b'{"model":0.0}', b'{"model":[],"stream":[0]}', b'{"model":{"a":1}}', b'{"model":"\\u00e9\\ud83d\\ude00 x","stream":0}', b'{"model":"m"',
+             b'\xff', b'{"model":"m","stream":false} ', b'  {"x":{"model":""},"model":"deep ok","stream":{}}', b'{"model":12,"stream":null}',
+             b'{"model":false}', b'{"model":"a","model2":"b"}', b'null', b'{}']
+    for _ in range(1500):
+        cases.append(bc.spell(rng, bc.rand_body(rng)).encode("utf-8"))
+    seen = set()
+    for raw in cases:
+        sc, model = hm.scan_body(raw)
+        ost, body, omodel, ostream = bo.parse_body(raw)
+        try:
+            dup = len(json.loads(raw, object_pairs_hook=lambda p: p if len({k for k, _ in p}) == len(p) else (_ for _ in ()).throw(KeyError()))) < 0
+        except KeyError:
+            continue                                            # duplicate keys: last-wins, not modelled by the scan
+        except Exception:
+            pass
+        assert int(sc["status"]) == ost, (raw, sc)
+        seen.add(ost)
+        if ost == 1:
+            continue
+        assert bool(sc["model_truthy"]) == bool(omodel)
+        assert bool(sc["stream_truthy"]) == bool(ostream), raw
+        if isinstance(omodel, str):
+            assert model == omodel.encode("utf-8", "surrogatepass")[:256]
+    assert seen == {0, 1, 2}

@@ -1,0 +1,153 @@
+"""GPU: request-body rewrite kernels (rows a1-a4) through the C ABI, bit-exact against the oracle and
+the reference-generated goldens."""
+import base64
+import json
+import random
+
+import numpy as np
+import pytest
+
+import body_cases as bc
+from golden_io import GOLDEN
+from llmapigateway_b200 import rewrite as rw
+from llmapigateway_b200.synth import chat_bodies
+from oracle import body_oracle as bo
+
+pytestmark = pytest.mark.gpu
+MODE_NAMES = ["httpx028", "httpx027", "json5"]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import llmapigateway_b200 as L
+    e = L.Engine(max_streams=64, max_step_chunks=1024, max_step_bytes=1 << 20)
+    yield e
+    e.close_engine()
+
+
+def _want(raw, att, mode_name):
+    """(status, bytes) the reference path produces for one attempt; status None = engine may call it exotic"""
+    ri, sub, retry = att
+    rule, prov, sp, rt = bc.attempt_for_oracle(ri, sub, retry)
+    try:
+        body = json.loads(raw.decode("utf-8"))
+    except Exception:
+        return rw.BODY_PARSE_ERROR, b""
+    if not isinstance(body, dict):
+        return None, b""
+    payload = bo.rewrite_payload(body, bo.rule_ops(rule, prov, sp, rt))
+    try:
+        return rw.BODY_OK, bo.RENDERERS[mode_name](payload)
+    except (ValueError, UnicodeEncodeError):
+        return rw.BODY_ENCODE_ERROR, b""
+
+
+def test_golden_attempt_bytes(engine):
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+    engine.load_rules(plans)
+    doc = json.loads((GOLDEN / "body_cases.json").read_text())
+    bodies, idx, want = [], [], []
+    for case in doc["cases"]:
+        raw = base64.b64decode(case["body"])
+        model = json.loads(raw)["model"]
+        seq = bc.CHAIN_ATTEMPTS if model == "gw/chain" else [None]
+        for att, a in zip(seq, case["attempts"]):
+            bodies.append(raw)
+            idx.append(plans.plan_index(model, *att) if att else plans.plan_index(model))
+            want.append(base64.b64decode(a["httpx_bytes"]))
+    got = engine.rewrite_bodies(bodies, idx)
+    assert len(got) == 25
+    for (st, out), w in zip(got, want):
+        assert st == rw.BODY_OK and out == w
+
+
+@pytest.mark.parametrize("stream_mode", ["httpx028", "httpx027"])
+def test_fuzz_batch_against_oracle(engine, stream_mode):
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode=stream_mode)
+    engine.load_rules(plans)
+    rng = random.Random(99 if stream_mode == "httpx028" else 100)
+    atts = bc.CHAIN_ATTEMPTS + [(4, -1, False)]
+    bodies, idx, meta = [], [], []
+    for it in range(3000):
+        raw = bc.spell(rng, bc.rand_body(rng)).encode("utf-8")
+        if it % 97 == 0:
+            raw = raw[:-1]                                 # truncated JSON
+        if it % 101 == 0:
+            raw = raw.replace(b"a", b"\xff", 1)            # invalid UTF-8
+        att = atts[it % len(atts)]
+        stream = it % 3 != 0
+        bodies.append(raw)
+        idx.append(plans.plan_index("gw/chain", *att, stream=stream))
+        meta.append((att, stream_mode if stream else "json5"))
+    got = engine.rewrite_bodies(bodies, idx)
+    tally = {}
+    for raw, (att, mode_name), (st, out) in zip(bodies, meta, got):
+        wst, w = _want(raw, att, mode_name)
+        if st == rw.BODY_EXOTIC or wst is None:
+            tally["exotic"] = tally.get("exotic", 0) + 1
+            continue
+        assert st == wst, (raw, st, wst)
+        assert out == w, (mode_name, raw)
+        tally[st] = tally.get(st, 0) + 1
+    assert tally[rw.BODY_OK] > 2000 and tally.get(rw.BODY_PARSE_ERROR, 0) > 20, tally
+
+
+def test_config2_bodies_bit_exact(engine):
+    """BASELINE.json configs[1]: 1024 bodies x 4 KiB, every body checked against the oracle in every mode"""
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+    engine.load_rules(plans)
+    bodies = chat_bodies(1024, 4096, seed=2)
+    for att, stream in (((1, -1, False), True), ((3, -1, True), True), ((4, -1, False), False), ((2, 1, False), False)):
+        idx = [plans.plan_index("gw/chain", *att, stream=stream)] * len(bodies)
+        got = engine.rewrite_bodies(bodies, idx)
+        mode_name = "httpx028" if stream else "json5"
+        for raw, (st, out) in zip(bodies, got):
+            wst, w = _want(raw, att, mode_name)
+            assert st == wst == rw.BODY_OK and out == w
+    # unknown model -> fallback-provider plan: re-rendered, nothing assigned
+    other = chat_bodies(64, 1024, seed=5, model="not-in-rules")
+    got = engine.rewrite_bodies(other, [plans.plan_index("not-in-rules")] * len(other))
+    for raw, (st, out) in zip(other, got):
+        assert st == rw.BODY_OK and out == bo.render_httpx028(json.loads(raw))
+
+
+def test_packed_offsets_and_overflow(engine):
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+    engine.load_rules(plans)
+    bodies = chat_bodies(37, 600, seed=8) + [b"{bad", b'{"model":"gw/chain","a":1,"a":2}']
+    buf, off = rw.pack_bodies(bodies)
+    idx = np.full(len(bodies), plans.plan_index("gw/chain", 1), dtype=np.uint32)
+    out, out_off, res = engine.rewrite_packed(buf, off, idx, slot_cap=2048)
+    assert list(res["status"][-2:]) == [rw.BODY_PARSE_ERROR, rw.BODY_EXOTIC]
+    assert out_off[0] == 0 and np.all(np.diff(out_off.astype(np.int64)) == np.where(res["status"] == 0, res["out_len"], 0))
+    for i, raw in enumerate(bodies[:37]):
+        assert bytes(out[int(out_off[i]):int(out_off[i + 1])]) == _want(raw, (1, -1, False), "httpx028")[1]
+    # a slot too small for some bodies: those report OVERFLOW with the size they need, the rest are unaffected
+    sizes = res["out_len"][:37]
+    cap = int(np.sort(sizes)[18])
+    out2, off2, res2 = engine.rewrite_packed(buf, off, idx, slot_cap=cap)
+    for i in range(37):
+        if sizes[i] > cap:
+            assert res2["status"][i] == rw.BODY_OVERFLOW and res2["out_len"][i] == sizes[i] and off2[i] == off2[i + 1]
+        else:
+            assert res2["status"][i] == rw.BODY_OK and bytes(out2[int(off2[i]):int(off2[i + 1])]) == bytes(out[int(out_off[i]):int(out_off[i + 1])])
+
+
+def test_scan_batch(engine):
+    rng = random.Random(5)
+    bodies = [b'{"model":"m","stream":true}', b'{"stream":1}', b'[1]', b'{"model":""}', b'{"model":"\\u00e9\\ud83d\\ude00 x","stream":0}', b'\xff', b'{}',
+              b'{"model":"m"', b'{"model":12,"stream":null}']
+    bodies += [bc.spell(rng, bc.rand_body(rng)).encode("utf-8") for _ in range(1000)]
+    bodies += chat_bodies(64, 4096, seed=3, stream=True)
+    scans, models = engine.scan_bodies(bodies)
+    seen = set()
+    for raw, sc, model in zip(bodies, scans, models):
+        ost, body, omodel, ostream = bo.parse_body(raw)
+        assert int(sc["status"]) == ost, raw
+        seen.add(ost)
+        if ost == 1:
+            continue
+        assert bool(sc["model_truthy"]) == bool(omodel) and bool(sc["stream_truthy"]) == bool(ostream)
+        if isinstance(omodel, str):
+            assert model == omodel.encode("utf-8", "surrogatepass")[:256]
+    assert seen == {0, 1, 2}
