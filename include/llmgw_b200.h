@@ -244,11 +244,17 @@ typedef struct lgw_body_op {        /* one `payload[key] = value` */
     uint32_t key_off, key_len;      /* key text (UTF-8) in the blob */
     uint32_t rkey_off, rkey_len;    /* key as the mode renders it   */
     uint32_t rval_off, rval_len;    /* value as the mode renders it */
-    uint32_t flags;                 /* bit0: only when the client's body lacks the key (chat.py:114) */
+    uint32_t flags;                 /* bit0: only when the client's body lacks the key (chat.py:114)
+                                       bit1: presence probe: nothing assigned/appended, only reported in lgw_body_result.matched */
     uint32_t _pad;
 } lgw_body_op;
+#define LGW_PLAN_RESPONSE 0x100u     /* or-ed into lgw_body_plan.mode: the document is an upstream RESPONSE (row a12) */
 typedef struct lgw_body_plan { uint32_t op_begin, op_end, mode, _pad; } lgw_body_plan;
-typedef struct lgw_body_result { uint32_t status, out_len; } lgw_body_result;
+typedef struct lgw_body_result {
+    uint32_t status, out_len;
+    uint32_t matched;               /* bit i: op i's key is present at the top level of the body */
+    uint32_t _pad;
+} lgw_body_result;
 typedef struct lgw_body_scan {
     uint32_t status;                /* LGW_BODY_OK / PARSE_ERROR / NO_MODEL */
     uint32_t model_len;             /* bytes of the model string (may exceed model_cap: truncated) */

@@ -12,11 +12,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "body_machine.cuh"
+#include "body_fast.cuh"
 
 namespace lgw {
 
 struct BodyPlan { uint32_t op_begin, op_end, mode, _pad; };
-struct BodyResult { uint32_t status, out_len; };
+struct BodyResult { uint32_t status, out_len, matched, _pad; };
 
 #define LGW_BODY_WARPS 4
 
@@ -28,28 +29,55 @@ __device__ __forceinline__ bool body_all_ascii(const uint8_t* in, uint32_t n) {
     return !__any_sync(0xffffffffu, (acc & 0x80u) != 0);
 }
 
-__global__ void __launch_bounds__(32 * LGW_BODY_WARPS)
-k_body_rewrite(const uint8_t* __restrict__ bodies, const uint64_t* __restrict__ body_off, uint32_t n,
-               const uint32_t* __restrict__ plan_idx, const BodyPlan* __restrict__ plans, uint32_t n_plans,
-               const BodyOp* __restrict__ ops, const uint8_t* __restrict__ blob,
-               uint8_t* __restrict__ slots, uint32_t slot_cap, BodyResult* __restrict__ results) {
-    const uint32_t b = blockIdx.x * LGW_BODY_WARPS + (threadIdx.x >> 5);
+// data-parallel path: one block per body; bodies it calls irregular are queued for the exact machine
+__global__ void __launch_bounds__(LGW_FAST_THREADS)
+k_body_fast(const uint8_t* __restrict__ bodies, const uint64_t* __restrict__ body_off, uint32_t n,
+            const uint32_t* __restrict__ plan_idx, const BodyPlan* __restrict__ plans, uint32_t n_plans,
+            const BodyOp* __restrict__ ops, const uint8_t* __restrict__ blob,
+            uint8_t* __restrict__ slots, uint32_t slot_cap, BodyResult* __restrict__ results,
+            uint32_t* __restrict__ redo_count, uint32_t* __restrict__ redo_list) {
+    __shared__ FastShared sh;
+    const uint32_t b = blockIdx.x;
     if (b >= n) return;
     const uint8_t* in = bodies + body_off[b];
     const uint32_t len = (uint32_t)(body_off[b + 1] - body_off[b]);
     const uint32_t pi = plan_idx[b];
-    BodyResult res{BS_PARSE_ERROR, 0};
-    if (pi < n_plans) {
-        const BodyPlan pl = plans[pi];
-        BodyRewriter m;
-        uint32_t out_len = 0;
-        m.reset((int)pl.mode, ops + pl.op_begin, pl.op_end - pl.op_begin, blob, slots + (size_t)b * slot_cap, slot_cap);
-        res.status = rewrite_body_checked(m, in, len, body_all_ascii(in, len), &out_len);
-        res.out_len = out_len;
-    } else {
-        res.status = BS_EXOTIC;
+    if (pi >= n_plans) { if (threadIdx.x == 0) results[b] = BodyResult{BS_EXOTIC, 0, 0, 0}; return; }
+    const BodyPlan pl = plans[pi];
+    uint32_t out_len = 0, matched = 0;
+    const uint32_t st = fast_rewrite(&sh, in, len, (int)pl.mode, ops + pl.op_begin, pl.op_end - pl.op_begin, blob,
+                                     slots + (size_t)b * slot_cap, slot_cap, &out_len, &matched);
+    if (threadIdx.x == 0) {
+        if (st == LGW_FAST_IRREGULAR) redo_list[atomicAdd(redo_count, 1u)] = b;
+        else results[b] = BodyResult{st, out_len, matched, 0};
     }
-    if ((threadIdx.x & 31u) == 0) results[b] = res;
+}
+
+// the exact sequential machine, one warp per queued body (every lane runs it redundantly; lane 0 writes)
+__global__ void __launch_bounds__(32 * LGW_BODY_WARPS)
+k_body_rewrite(const uint8_t* __restrict__ bodies, const uint64_t* __restrict__ body_off, uint32_t n,
+               const uint32_t* __restrict__ plan_idx, const BodyPlan* __restrict__ plans, uint32_t n_plans,
+               const BodyOp* __restrict__ ops, const uint8_t* __restrict__ blob,
+               uint8_t* __restrict__ slots, uint32_t slot_cap, BodyResult* __restrict__ results,
+               const uint32_t* __restrict__ redo_count, const uint32_t* __restrict__ redo_list) {
+    const uint32_t todo = redo_list ? *redo_count : n;
+    for (uint32_t w = blockIdx.x * LGW_BODY_WARPS + (threadIdx.x >> 5); w < todo; w += gridDim.x * LGW_BODY_WARPS) {
+        const uint32_t b = redo_list ? redo_list[w] : w;
+        const uint8_t* in = bodies + body_off[b];
+        const uint32_t len = (uint32_t)(body_off[b + 1] - body_off[b]);
+        const uint32_t pi = plan_idx[b];
+        BodyResult res{BS_EXOTIC, 0, 0, 0};
+        if (pi < n_plans) {
+            const BodyPlan pl = plans[pi];
+            BodyRewriter m;
+            uint32_t out_len = 0;
+            m.reset((int)pl.mode, ops + pl.op_begin, pl.op_end - pl.op_begin, blob, slots + (size_t)b * slot_cap, slot_cap);
+            res.status = rewrite_body_checked(m, in, len, body_all_ascii(in, len), &out_len);
+            res.out_len = out_len;
+            res.matched = m.matched;
+        }
+        if ((threadIdx.x & 31u) == 0) results[b] = res;
+    }
 }
 
 // exclusive scan over the OK lengths; one block, n is small (thousands) compared with the bodies

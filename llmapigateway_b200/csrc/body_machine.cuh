@@ -34,6 +34,8 @@ struct BodyOp {             // == lgw_body_op
     uint32_t rkey_off, rkey_len;    // rendered key token (quotes included when the mode quotes it)
     uint32_t rval_off, rval_len;    // rendered value
     uint32_t flags;                 // bit0: only if the key is absent from the client's body (chat.py:114)
+                                    // bit1: presence probe -- nothing is assigned or appended, the key only sets its bit in `matched`
+                                    //       (request_handler.py:167 `"error" in response_json`)
     uint32_t _pad;
 };
 
@@ -48,6 +50,52 @@ struct BodyScan {           // == lgw_body_scan: what chat.py:41-45 reads
     uint8_t model_kind, model_truthy, stream_kind, stream_truthy;
     uint32_t _pad;
 };
+
+// Number token with a fraction or exponent -> the text Python's repr(float(token)) gives, when the token has
+// <= 15 significant digits (then the shortest round-trip digits ARE the token's digits, David Gay's
+// guarantee for doubles) and its magnitude is inside 1e-290..1e290.  Returns the length (<= 24) or -1
+// ("exotic": the caller reports LGW_BODY_EXOTIC).  Format rule = CPython float_repr_style 'short', repr:
+// exponent form iff decpt <= -4 or decpt > 16, at least two exponent digits.
+LGW_HD int format_float(const char* t, uint32_t n, char* out) {
+    uint32_t i = 0; int o = 0;
+    if (n && t[0] == '-') { out[o++] = '-'; i = 1; }
+    char dig[20]; int nd = 0; int decpt = 0; bool seen_nz = false, extra_nz = false, in_frac = false; int exp10 = 0;
+    for (; i < n; ++i) {
+        const char c = t[i];
+        if (c == '.') { in_frac = true; continue; }
+        if (c == 'e' || c == 'E') {
+            ++i; bool eneg = false;
+            if (i < n && (t[i] == '+' || t[i] == '-')) { eneg = t[i] == '-'; ++i; }
+            int e = 0; for (; i < n; ++i) if (e < 100000) e = e * 10 + (t[i] - '0');
+            exp10 = eneg ? -e : e;
+            break;
+        }
+        if (c != '0' || seen_nz) {
+            seen_nz = true;
+            if (nd < 17) dig[nd++] = c; else if (c != '0') extra_nz = true;
+            if (!in_frac) ++decpt;
+        } else if (in_frac) --decpt;                 // zeros between the point and the first significant digit
+    }
+    while (nd > 0 && dig[nd - 1] == '0') --nd;
+    if (nd == 0) { out[o++] = '0'; out[o++] = '.'; out[o++] = '0'; return o; }
+    if (nd > 15 || extra_nz) return -1;
+    decpt += exp10;
+    if (decpt < -290 || decpt > 290) return -1;
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) { out[o++] = '0'; out[o++] = '.'; for (int k = 0; k < -decpt; ++k) out[o++] = '0'; for (int k = 0; k < nd; ++k) out[o++] = dig[k]; }
+        else if (decpt < nd) { for (int k = 0; k < decpt; ++k) out[o++] = dig[k]; out[o++] = '.'; for (int k = decpt; k < nd; ++k) out[o++] = dig[k]; }
+        else { for (int k = 0; k < nd; ++k) out[o++] = dig[k]; for (int k = nd; k < decpt; ++k) out[o++] = '0'; out[o++] = '.'; out[o++] = '0'; }
+    } else {
+        out[o++] = dig[0];
+        if (nd > 1) { out[o++] = '.'; for (int k = 1; k < nd; ++k) out[o++] = dig[k]; }
+        out[o++] = 'e';
+        int e = decpt - 1;
+        if (e < 0) { out[o++] = '-'; e = -e; } else out[o++] = '+';
+        if (e >= 100) { out[o++] = (char)('0' + e / 100); e %= 100; }
+        out[o++] = (char)('0' + e / 10); out[o++] = (char)('0' + e % 10);
+    }
+    return o;
+}
 
 struct BodyRewriter {
     // configuration
@@ -71,7 +119,7 @@ struct BodyRewriter {
     // scan outputs (scan_body only)
     uint8_t want_scan; uint8_t cur_top_key;  // 1 model, 2 stream
     BodyScan* scan; uint8_t* model_buf; uint32_t model_cap;
-    uint8_t str_nonempty, root_obj;
+    uint8_t str_nonempty, root_obj, response_mode;
 
     LGW_HD void fail(uint32_t s) { if (status == BS_OK) status = s; st = S_ERR; }
     LGW_HD void soft(uint32_t s) { if (status == BS_OK) status = s; }          // keep parsing, remember the verdict
@@ -222,7 +270,7 @@ struct BodyRewriter {
         }
         if (hit) {
             matched |= 1u << (hit - 1);
-            if (!(ops[hit - 1].flags & 1u)) {            // assigned: rendered key, value replaced in place
+            if (!(ops[hit - 1].flags & 3u)) {            // assigned: rendered key, value replaced in place
                 emit_blob(ops[hit - 1].rkey_off, ops[hit - 1].rkey_len);
                 pending_replace = (uint8_t)hit;
                 st = S_COLON;
@@ -258,49 +306,12 @@ struct BodyRewriter {
         st = S_COLON;
     }
 
-    // float text -> repr(float(text)) when the text has <= 15 significant digits (then the shortest
-    // round-trip digits ARE the text's digits); otherwise BS_EXOTIC
+    // float text -> repr(float(text)): see format_float()
     LGW_HD void emit_float() {
-        uint32_t i = 0; bool neg = false;
-        if (nbuf[0] == '-') { neg = true; i = 1; }
-        char dig[20]; int nd = 0; int decpt = 0; bool seen_nz = false; bool extra_nz = false; bool in_frac = false; int exp10 = 0;
-        for (; i < nlen; ++i) {
-            const char c = nbuf[i];
-            if (c == '.') { in_frac = true; continue; }
-            if (c == 'e' || c == 'E') {
-                ++i; bool eneg = false;
-                if (i < nlen && (nbuf[i] == '+' || nbuf[i] == '-')) { eneg = nbuf[i] == '-'; ++i; }
-                int e = 0; for (; i < nlen; ++i) if (e < 100000) e = e * 10 + (nbuf[i] - '0');
-                exp10 = eneg ? -e : e;
-                break;
-            }
-            if (c != '0' || seen_nz) {
-                seen_nz = true;
-                if (nd < 17) dig[nd++] = c; else if (c != '0') extra_nz = true;
-                if (!in_frac) ++decpt;
-            } else if (in_frac && !seen_nz) --decpt;       // leading zeros after the point
-            else if (!in_frac && !seen_nz) { /* leading zero of "0.xxx" */ }
-        }
-        // digits beyond the 17 kept that were integer digits still count for decpt (handled above)
-        while (nd > 0 && dig[nd - 1] == '0') --nd;
-        if (neg) emit('-');
-        if (nd == 0) { emit('0'); emit('.'); emit('0'); return; }
-        if (nd > 15 || extra_nz) { soft(BS_EXOTIC); return; }
-        decpt += exp10;
-        if (decpt < -290 || decpt > 290) { soft(BS_EXOTIC); return; }
-        if (decpt > -4 + 0 && decpt <= 16) {
-            if (decpt <= 0) { emit('0'); emit('.'); for (int k = 0; k < -decpt; ++k) emit('0'); for (int k = 0; k < nd; ++k) emit(dig[k]); }
-            else if (decpt < nd) { for (int k = 0; k < decpt; ++k) emit(dig[k]); emit('.'); for (int k = decpt; k < nd; ++k) emit(dig[k]); }
-            else { for (int k = 0; k < nd; ++k) emit(dig[k]); for (int k = nd; k < decpt; ++k) emit('0'); emit('.'); emit('0'); }
-        } else {
-            emit(dig[0]);
-            if (nd > 1) { emit('.'); for (int k = 1; k < nd; ++k) emit(dig[k]); }
-            emit('e');
-            int e = decpt - 1;
-            if (e < 0) { emit('-'); e = -e; } else emit('+');
-            if (e >= 100) { emit('0' + e / 100); e %= 100; emit('0' + e / 10); emit('0' + e % 10); }
-            else { emit('0' + e / 10); emit('0' + e % 10); }
-        }
+        char buf[32];
+        const int k = format_float(nbuf, nlen, buf);
+        if (k < 0) { if (nbuf[0] == '-') emit('-'); soft(BS_EXOTIC); return; }
+        for (int j = 0; j < k; ++j) emit((uint8_t)buf[j]);
     }
 
     LGW_HD void end_number() {
@@ -319,7 +330,7 @@ struct BodyRewriter {
     LGW_HD void open_container(bool is_obj) {
         if (depth >= LGW_BODY_MAXD) { soft(BS_EXOTIC); if (depth >= 63) { fail(BS_EXOTIC); return; } }
         value_begins();
-        if (depth == 0) root_obj = is_obj;
+        if (depth == 0) { root_obj = is_obj; if (!is_obj && response_mode) soft(BS_EXOTIC); }
         emit(is_obj ? '{' : '[');
         if (is_obj) stack |= (1ull << depth); else stack &= ~(1ull << depth);
         ++depth;
@@ -331,7 +342,7 @@ struct BodyRewriter {
         if (depth == 1 && is_obj) {                   // append the assigned keys the client did not send (chat.py dict order)
             bool any = top_members > 0;
             for (uint32_t i = 0; i < n_ops; ++i) {
-                if (matched & (1u << i)) continue;
+                if ((matched & (1u << i)) || (ops[i].flags & 2u)) continue;
                 if (any) emit_comma();
                 emit_blob(ops[i].rkey_off, ops[i].rkey_len); emit_colon(); emit_blob(ops[i].rval_off, ops[i].rval_len);
                 any = true;
@@ -482,7 +493,7 @@ struct BodyRewriter {
         mode = render_mode; ops = o; n_ops = n; blob = b; out = dst; cap = dst_cap; len = 0;
         st = S_VALUE; depth = 0; in_key = 0; lit_id = 0; lit_pos = 0; ucount = 0; neg_lit = 0; skipping = 0; skip_depth = 0; pending_replace = 0;
         status = BS_OK; stack = 0; ucode = 0; pending_high = 0; matched = 0; top_members = 0; klen = 0; k_has_surrogate = 0; nlen = 0; n_float = 0;
-        want_scan = 0; cur_top_key = 0; scan = nullptr; model_buf = nullptr; model_cap = 0; str_nonempty = 0; root_obj = 0;
+        want_scan = 0; cur_top_key = 0; scan = nullptr; model_buf = nullptr; model_cap = 0; str_nonempty = 0; root_obj = 0; response_mode = (uint8_t)((render_mode >> 8) & 1); mode = render_mode & 0xff;
     }
 };
 
@@ -543,6 +554,7 @@ LGW_HD_NOINLINE uint32_t rewrite_body_checked(BodyRewriter& m, const uint8_t* in
     }
     if (m.st == S_ERR) return m.status ? m.status : BS_PARSE_ERROR;
     if (m.st != S_DONE) return BS_PARSE_ERROR;
+    if (m.response_mode && !m.root_obj) return BS_EXOTIC;        // `"error" in <list|str|number>` is not modelled
     *out_len = m.len;
     if (m.status) return m.status;
     if (m.len > cap) return BS_OVERFLOW;

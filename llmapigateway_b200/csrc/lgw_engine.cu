@@ -49,7 +49,9 @@ struct lgw_engine {
     BodyPlan* d_plans = nullptr; BodyOp* d_ops = nullptr; uint8_t* d_blob = nullptr; uint32_t n_plans = 0, n_ops = 0;
     uint8_t *b_in = nullptr, *b_slots = nullptr, *b_out = nullptr, *b_models = nullptr;
     uint64_t *b_off = nullptr, *b_out_off = nullptr; uint32_t* b_plan_idx = nullptr; BodyResult* b_results = nullptr; BodyScan* b_scans = nullptr;
-    uint64_t b_in_cap = 0, b_slots_cap = 0, b_out_cap = 0, b_n_cap = 0, b_models_cap = 0;
+    uint64_t b_in_cap = 0, b_slots_cap = 0, b_out_cap = 0, b_n_cap = 0, b_models_cap = 0, b_redo_cap = 0;
+    uint32_t* b_redo = nullptr;
+    int body_mode = 0;              // 0: data-parallel path + exact machine for the rest, 1: exact machine only (tests)
     cudaEvent_t bev[4]{};
     float bms[3]{0, 0, 0};
     int mode = 0;                   // 0: fast path + general fix-up, 1: general path only
@@ -127,7 +129,7 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     cudaFree(e->d_rows); cudaFree(e->d_nrows);
     cudaFree(e->d_plans); cudaFree(e->d_ops); cudaFree(e->d_blob);
     cudaFree(e->b_in); cudaFree(e->b_slots); cudaFree(e->b_out); cudaFree(e->b_models); cudaFree(e->b_off); cudaFree(e->b_out_off);
-    cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans);
+    cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans); cudaFree(e->b_redo);
     for (auto& ev : e->bev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 16; ++i) { if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]); }
     if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -145,7 +147,7 @@ extern "C" int lgw_engine_set_stream(lgw_engine* e, void* s) {
 
 extern "C" int lgw_engine_set_mode(lgw_engine* e, int mode) {     // 0 fast+fix-up, 1 general only (tests)
     if (!e) return LGW_ERR_ARG;
-    e->mode = mode;
+    e->mode = mode; e->body_mode = mode;
     return LGW_OK;
 }
 
@@ -456,7 +458,7 @@ extern "C" int lgw_rules_load(lgw_engine* e, const lgw_body_plan* plans, uint32_
                               const lgw_body_op* ops, uint32_t n_ops, const uint8_t* blob, uint32_t blob_len) {
     if (!e || (n_plans && !plans) || (n_ops && !ops) || (blob_len && !blob)) return LGW_ERR_ARG;
     for (uint32_t i = 0; i < n_plans; ++i) {
-        if (plans[i].op_begin > plans[i].op_end || plans[i].op_end > n_ops || plans[i].op_end - plans[i].op_begin > 32 || plans[i].mode > 2) {
+        if (plans[i].op_begin > plans[i].op_end || plans[i].op_end > n_ops || plans[i].op_end - plans[i].op_begin > 32 || (plans[i].mode & 0xffu) > 2 || (plans[i].mode & ~0x1ffu)) {
             e->err = "lgw_rules_load: malformed plan"; return LGW_ERR_ARG; }
     }
     for (uint32_t i = 0; i < n_ops; ++i) {
@@ -516,9 +518,21 @@ static int bodies_launch(lgw_engine* e, const uint8_t* d_bodies, const uint64_t*
                          uint32_t slot_cap, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off, BodyResult* d_results) {
     if (!e->d_plans) { e->err = "lgw_bodies_rewrite before lgw_rules_load"; return LGW_ERR_ARG; }
     CK(e, grow(e->b_slots, e->b_slots_cap, (uint64_t)n * slot_cap + 64));
+    CK(e, grow(e->b_redo, e->b_redo_cap, (uint64_t)n + 4));
+    uint32_t* redo_count = e->b_redo + n;            // list first, counter behind it
+    const uint32_t seq_grid = (n + LGW_BODY_WARPS - 1) / LGW_BODY_WARPS < (uint32_t)e->sm_count * 4u ? (n + LGW_BODY_WARPS - 1) / LGW_BODY_WARPS : (uint32_t)e->sm_count * 4u;
     CK(e, cudaEventRecord(e->bev[0], e->stream));
-    k_body_rewrite<<<(n + LGW_BODY_WARPS - 1) / LGW_BODY_WARPS, 32 * LGW_BODY_WARPS, 0, e->stream>>>(
-        d_bodies, d_body_off, n, d_plan_idx, e->d_plans, e->n_plans, e->d_ops, e->d_blob, e->b_slots, slot_cap, d_results);
+    if (e->body_mode == 0) {
+        CK(e, cudaMemsetAsync(redo_count, 0, 4, e->stream));
+        k_body_fast<<<n, LGW_FAST_THREADS, 0, e->stream>>>(d_bodies, d_body_off, n, d_plan_idx, e->d_plans, e->n_plans, e->d_ops, e->d_blob,
+                                                             e->b_slots, slot_cap, d_results, redo_count, e->b_redo);
+        k_body_rewrite<<<seq_grid, 32 * LGW_BODY_WARPS, 0, e->stream>>>(d_bodies, d_body_off, n, d_plan_idx, e->d_plans, e->n_plans, e->d_ops, e->d_blob,
+                                                                        e->b_slots, slot_cap, d_results, redo_count, e->b_redo);
+        ++e->launches;
+    } else {
+        k_body_rewrite<<<seq_grid, 32 * LGW_BODY_WARPS, 0, e->stream>>>(d_bodies, d_body_off, n, d_plan_idx, e->d_plans, e->n_plans, e->d_ops, e->d_blob,
+                                                                        e->b_slots, slot_cap, d_results, nullptr, nullptr);
+    }
     CK(e, cudaEventRecord(e->bev[1], e->stream));
     k_body_offsets<<<1, 1024, 0, e->stream>>>(d_results, n, out_cap, d_out_off);
     CK(e, cudaEventRecord(e->bev[2], e->stream));

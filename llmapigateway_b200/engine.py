@@ -182,8 +182,9 @@ class Engine:
                                               _ptr(out), out.nbytes, _ptr(out_off), _ptr(res)), "bodies_rewrite")
         return out, out_off, res[:n]
 
-    def rewrite_bodies(self, bodies, plan_idx, slot_cap: int | None = None):
-        """list[bytes] in -> list[(status, payload bytes)] (payload empty unless status == BODY_OK)."""
+    def rewrite_bodies(self, bodies, plan_idx, slot_cap: int | None = None, with_matched: bool = False):
+        """list[bytes] in -> list[(status, payload bytes)] (payload empty unless status == BODY_OK);
+        with_matched adds the bit mask of plan keys present at the top level."""
         from . import rewrite as rw
         buf, off = rw.pack_bodies(bodies)
         if slot_cap is None:
@@ -191,8 +192,11 @@ class Engine:
             slot_cap = 6 * longest + getattr(self, "_plan_growth", 0) + 64      # worst case: every byte becomes \u00XX
             slot_cap = (slot_cap + 15) & ~15
         out, out_off, res = self.rewrite_packed(buf, off, np.asarray(plan_idx, dtype=np.uint32), slot_cap)
-        return [(int(res["status"][i]), bytes(out[int(out_off[i]):int(out_off[i + 1])]) if res["status"][i] == rw.BODY_OK else b"")
+        rows = [(int(res["status"][i]), bytes(out[int(out_off[i]):int(out_off[i + 1])]) if res["status"][i] == rw.BODY_OK else b"")
                 for i in range(len(bodies))]
+        if with_matched:
+            return [(st, b, int(res["matched"][i])) for i, (st, b) in enumerate(rows)]
+        return rows
 
     def bodies_last_ms(self):
         ms = (C.c_float * 3)()

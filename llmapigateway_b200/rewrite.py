@@ -24,10 +24,13 @@ STATUS_NAMES = ["ok", "parse_error", "no_model", "overflow", "exotic", "encode_e
 OP_DTYPE = np.dtype([("key_off", "<u4"), ("key_len", "<u4"), ("rkey_off", "<u4"), ("rkey_len", "<u4"),
                      ("rval_off", "<u4"), ("rval_len", "<u4"), ("flags", "<u4"), ("_pad", "<u4")])
 PLAN_DTYPE = np.dtype([("op_begin", "<u4"), ("op_end", "<u4"), ("mode", "<u4"), ("_pad", "<u4")])
-RESULT_DTYPE = np.dtype([("status", "<u4"), ("out_len", "<u4")])
+RESULT_DTYPE = np.dtype([("status", "<u4"), ("out_len", "<u4"), ("matched", "<u4"), ("_pad", "<u4")])
 SCAN_DTYPE = np.dtype([("status", "<u4"), ("model_len", "<u4"), ("model_kind", "u1"), ("model_truthy", "u1"),
                        ("stream_kind", "u1"), ("stream_truthy", "u1"), ("_pad", "<u4")])
 MAX_OPS_PER_PLAN = 32
+OP_IF_ABSENT, OP_PRESENCE = 1, 2
+PLAN_RESPONSE = 0x100          # or-ed into a plan's mode: the document is an upstream response (row a12)
+RESPONSE_PROBES = ("error", "detail")      # request_handler.py:167
 
 _ES5_WORDS = frozenset(
     "break case catch continue debugger default delete do else finally for function if in instanceof new return "
@@ -155,6 +158,14 @@ class RulePlans:
         for mode in modes:
             extra = [("usage", {"include": True}, True)] if self.fallback_provider == "openrouter" else []
             self._add((None, 0, -1, False, mode), extra, mode)
+        # row a12: an upstream non-streaming response is re-rendered the way Starlette's JSONResponse does
+        # (same encoder settings as httpx 0.28) and probed for the keys request_handler.py:167 looks for
+        begin = len(self._ops)
+        for k in RESPONSE_PROBES:
+            ko, kl = self._put(k.encode("utf-8"))
+            self._ops.append((ko, kl, 0, 0, 0, 0, OP_PRESENCE, 0))
+        self.index[("response",)] = len(self._plans)
+        self._plans.append((begin, len(self._ops), MODES["httpx028"] | PLAN_RESPONSE, 0))
 
     def _put(self, b: bytes):
         off = len(self._blob)
@@ -180,6 +191,9 @@ class RulePlans:
         if gw_model not in self.fallback_rules:
             return self.index[(None, 0, -1, False, mode)]
         return self.index[(gw_model, rule_idx, sub_idx, retry, mode)]
+
+    def response_plan(self) -> int:
+        return self.index[("response",)]
 
     def packed(self):
         plans = np.array(self._plans, dtype=PLAN_DTYPE) if self._plans else np.zeros(0, PLAN_DTYPE)

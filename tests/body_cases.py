@@ -65,13 +65,15 @@ def _str_text(rng, s: str) -> str:
     return "".join(out)
 
 
-def spell(rng: random.Random, v, float_texts=True) -> str:
-    """JSON text for v with random whitespace / escape spellings (json.loads(spell(v)) == v)"""
+def spell(rng: random.Random, v, float_texts=True, plain_keys=False) -> str:
+    """JSON text for v with random whitespace / escape spellings (json.loads(spell(v)) == v).
+    plain_keys: keys are written without optional escapes (the shape client SDKs produce)."""
     ws = lambda: rng.choice(["", "", "", " ", "\n", "\t ", "  \r\n"])
+    key = (lambda k: json.dumps(k, ensure_ascii=False)) if plain_keys else (lambda k: _str_text(rng, k))
     if isinstance(v, dict):
-        return "{" + ws() + ",".join(ws() + _str_text(rng, k) + ws() + ":" + ws() + spell(rng, x) + ws() for k, x in v.items()) + "}"
+        return "{" + ws() + ",".join(ws() + key(k) + ws() + ":" + ws() + spell(rng, x, float_texts, plain_keys) + ws() for k, x in v.items()) + "}"
     if isinstance(v, list):
-        return "[" + ws() + ",".join(ws() + spell(rng, x) + ws() for x in v) + "]"
+        return "[" + ws() + ",".join(ws() + spell(rng, x, float_texts, plain_keys) + ws() for x in v) + "]"
     if isinstance(v, str):
         return _str_text(rng, v)
     if isinstance(v, float) and float_texts and rng.random() < 0.3:

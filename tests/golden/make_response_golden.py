@@ -1,0 +1,58 @@
+"""Generate tests/golden/response_cases.json from the UNMODIFIED reference (dev container only):
+    python tests/golden/make_response_golden.py
+Each case: upstream status + body bytes -> what make_llm_request(is_streaming=False) + chat.py:146 +
+Starlette's JSONResponse produce."""
+import base64
+import json
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE)); sys.path.insert(0, str(HERE.parent.parent))
+import ref_driver  # noqa: E402
+
+OK_DOC = {"id": "chatcmpl-1", "object": "chat.completion", "created": 1700000000, "model": "m-1",
+          "choices": [{"index": 0, "message": {"role": "assistant", "content": "Hé \"there\"\n\t中 \U0001F600 \x7f /"}, "finish_reason": "stop", "logprobs": None}],
+          "usage": {"prompt_tokens": 12, "completion_tokens": 7, "total_tokens": 19, "cost": 1.50e-4, "completion_tokens_details": {"reasoning_tokens": 0}},
+          "system_fingerprint": None, "x": [1e16, 1e15, 0.1, -0.0, 2.5e-7, 100.0, 12345678901234567890, True]}
+
+CASES = [
+    (200, json.dumps(OK_DOC).encode()),
+    (200, json.dumps(OK_DOC, ensure_ascii=False, indent=2).encode()),
+    (200, json.dumps(OK_DOC, separators=(",", ":")).encode()),
+    (201, b'{"a":1}'),
+    (200, b'{ "cost" : 1.50e-4 , "k" : "\\u00e9\\ud83d\\ude00\\/" }'),
+    (200, b'{}'),
+    (200, b'{"error":{"message":"boom","code":429}}'),
+    (200, b'{"error":{"code":429},"detail":"fallback detail"}'),
+    (200, b'{"error":"a string"}'),
+    (200, b'{"detail":"Not found"}'),
+    (200, b'{"detail":null,"a":1}'),
+    (200, b'{"choices":[],"error":null}'),
+    (200, b'{"nested":{"error":1,"detail":2},"ok":true}'),
+    (400, b'{"error":{"message":"bad request"}}'),
+    (500, b'upstream exploded \xff'),
+    (404, b''),
+    (200, b'not json'),
+    (200, b''),
+    (200, b'{"a":1,}'),
+    (200, b'{"a":NaN}'),
+    (200, b'{"a":"\\ud800"}'),
+]
+
+
+def main():
+    out = []
+    for status, content in CASES:
+        r = ref_driver.run_nonstream(content, status)
+        out.append({"status": status, "content": base64.b64encode(content).decode(), "kind": r["kind"],
+                    "detail": r["detail"], "body": base64.b64encode(r["body"]).decode()})
+    import httpx
+    import starlette
+    doc = {"generator": "tests/golden/make_response_golden.py", "httpx": httpx.__version__, "starlette": starlette.__version__, "cases": out}
+    (HERE / "response_cases.json").write_text(json.dumps(doc, indent=0))
+    print("wrote", len(out), "cases:", [c["kind"] for c in out])
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,37 @@ def run_relay(chunks: list[bytes], http_status: int = 200, url: str = "http://up
     return asyncio.run(go())
 
 
+def run_nonstream(content: bytes, http_status: int = 200, url: str = "http://upstream.test/v1/chat/completions"):
+    """Real make_llm_request(..., is_streaming=False) (request_handler.py:152-176) over a MockTransport upstream,
+    then what chat.py:146 and FastAPI do with the result.  Returns dict(kind, detail, body)."""
+    import httpx
+    from starlette.responses import JSONResponse
+    rh, _ = load_reference()
+
+    def handler(request):
+        return httpx.Response(http_status, headers={"content-type": "application/json"}, content=content)
+
+    real_client = httpx.AsyncClient
+
+    def patched(**kw):
+        return real_client(transport=httpx.MockTransport(handler), **kw)
+
+    async def go():
+        rh.httpx.AsyncClient = patched
+        try:
+            return await rh.make_llm_request(url, {}, {"model": "m", "messages": []}, False)
+        finally:
+            rh.httpx.AsyncClient = real_client
+
+    resp, err = asyncio.run(go())
+    if resp and err is None:                                   # chat.py:146
+        try:
+            return dict(kind="ok", detail=None, body=bytes(JSONResponse(content=resp).body))
+        except ValueError:
+            return dict(kind="raise", detail=None, body=b"")
+    return dict(kind="fail", detail=err, body=b"")
+
+
 class _NoWaitQueue(queue.Queue):
     def get(self, block=True, timeout=None):  # chat_logging.py:94 waits 5 s; we know the stream is over
         return super().get(block=False)

@@ -92,8 +92,16 @@ def rewrite_body(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 << 16
     lib().lgwt_rewrite_body.restype = C.c_uint32
     st = lib().lgwt_rewrite_body(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.c_int(int(p["mode"])),
                                  sub.ctypes.data_as(C.c_void_p), C.c_uint32(len(sub)), blob.ctypes.data_as(C.c_void_p),
-                                 out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n))
+                                 out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n), C.byref(_last_matched))
     return st, bytes(out[:min(n.value, cap)]), n.value
+
+
+_last_matched = C.c_uint32(0)
+
+
+def last_matched() -> int:
+    """`matched` bits of the most recent rewrite_body / rewrite_body_fast call"""
+    return _last_matched.value
 
 
 def scan_body(raw: bytes, model_cap: int = 256):
@@ -104,3 +112,20 @@ def scan_body(raw: bytes, model_cap: int = 256):
     lib().lgwt_scan_body(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), sc.ctypes.data_as(C.c_void_p),
                          model.ctypes.data_as(C.c_void_p), C.c_uint32(model_cap))
     return sc[0], bytes(model[:min(int(sc[0]["model_len"]), model_cap)])
+
+
+FAST_IRREGULAR = 0xFFFFFFFF
+
+
+def rewrite_body_fast(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 << 16):
+    """body_fast.cuh fast_rewrite() with its phases run thread by thread: (status | FAST_IRREGULAR, out, needed)."""
+    p = plans[plan_idx]
+    sub = np.ascontiguousarray(ops[p["op_begin"]:p["op_end"]])
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    n = C.c_uint32(0)
+    buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    lib().lgwt_rewrite_body_fast.restype = C.c_uint32
+    st = lib().lgwt_rewrite_body_fast(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.c_int(int(p["mode"])),
+                                      sub.ctypes.data_as(C.c_void_p), C.c_uint32(len(sub)), blob.ctypes.data_as(C.c_void_p),
+                                      out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n), C.byref(_last_matched))
+    return st, bytes(out[:min(n.value, cap)]) if st == 0 else b"", n.value

@@ -80,9 +80,11 @@ static_assert(sizeof(BodyScan) == sizeof(lgw_body_scan), "BodyScan");
 extern "C" {
 
 uint32_t lgwt_rewrite_body(const uint8_t* in, uint32_t n, int mode, const lgw_body_op* ops, uint32_t n_ops,
-                           const uint8_t* blob, uint8_t* out, uint32_t cap, uint32_t* out_len) {
+                           const uint8_t* blob, uint8_t* out, uint32_t cap, uint32_t* out_len, uint32_t* matched_out) {
     BodyRewriter m;
-    return rewrite_body(m, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len);
+    const uint32_t st = rewrite_body(m, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len);
+    if (matched_out) *matched_out = m.matched;
+    return st;
 }
 
 void lgwt_scan_body(const uint8_t* in, uint32_t n, lgw_body_scan* sc, uint8_t* model_buf, uint32_t model_cap) {
@@ -91,3 +93,14 @@ void lgwt_scan_body(const uint8_t* in, uint32_t n, lgw_body_scan* sc, uint8_t* m
 }
 
 }  // extern "C"
+
+// ---- data-parallel body rewrite (body_fast.cuh), phases emulated thread by thread ---------------------
+#include "../../llmapigateway_b200/csrc/body_fast.cuh"
+extern "C" uint32_t lgwt_rewrite_body_fast(const uint8_t* in, uint32_t n, int mode, const lgw_body_op* ops, uint32_t n_ops,
+                                           const uint8_t* blob, uint8_t* out, uint32_t cap, uint32_t* out_len, uint32_t* matched_out) {
+    static FastShared sh;
+    uint32_t matched = 0;
+    const uint32_t st = fast_rewrite(&sh, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len, &matched);
+    if (matched_out) *matched_out = matched;
+    return st;
+}

@@ -191,3 +191,125 @@ def test_scan_matches_parse_body():
         if isinstance(omodel, str):
             assert model == omodel.encode("utf-8", "surrogatepass")[:256]
     assert seen == {0, 1, 2}
+
+
+# ---- the data-parallel path (body_fast.cuh) against the sequential machine ----------------------------
+def _fast_vs_sequential(corpus, objs, atts, tally):
+    for it, raw in enumerate(corpus):
+        att = atts[it % len(atts)]
+        for obj, stream in objs:
+            plans, ops, blob = obj.packed()
+            pi = obj.plan_index("gw/chain", *att, stream=stream)
+            fst, fout, fneed = hm.rewrite_body_fast(raw, plans, ops, blob, pi)
+            if fst == hm.FAST_IRREGULAR:
+                tally["irregular"] = tally.get("irregular", 0) + 1
+                continue
+            st, out, need = hm.rewrite_body(raw, plans, ops, blob, pi)
+            assert (fst, fout, fneed) == (st, out, need), (raw, att, stream)
+            tally["fast"] = tally.get("fast", 0) + 1
+
+
+def test_fast_path_equals_sequential_machine(plans028, plans027):
+    """contract of body_fast.cuh: whenever it does not say "irregular", status, length and bytes are the
+    sequential machine's (which the tests above pin to the oracle)"""
+    from llmapigateway_b200.synth import chat_bodies
+    rng = random.Random(4242)
+    atts = bc.CHAIN_ATTEMPTS + [(4, -1, False)]
+    objs = ((plans028, True), (plans027, True), (plans028, False))
+    tally = {}
+    plain = [bc.spell(rng, bc.rand_body(rng), plain_keys=True).encode("utf-8") for _ in range(2500)]
+    _fast_vs_sequential(plain, objs, atts, tally)
+    assert tally["fast"] > 4000, tally                      # the fast path really is exercised (json5 + non-ASCII keys fall back)
+    escaped = [bc.spell(rng, bc.rand_body(rng)).encode("utf-8") for _ in range(800)]
+    _fast_vs_sequential(escaped, objs, atts, tally)
+    chat = chat_bodies(48, 4096, seed=2) + chat_bodies(48, 300, seed=3, non_ascii=0.3) + chat_bodies(16, 6000, seed=4) + chat_bodies(4, 9000, seed=5)
+    t2 = {}
+    _fast_vs_sequential(chat, objs, atts, t2)
+    assert t2["fast"] >= 3 * (48 + 48 + 16) - 10 and t2.get("irregular", 0) >= 12, t2      # > 6 KiB bodies take the sequential machine
+    # small output slots: same OVERFLOW verdict and needed length
+    plans, ops, blob = plans028.packed()
+    for raw in chat[:20]:
+        pi = plans028.plan_index("gw/chain", 1)
+        assert hm.rewrite_body_fast(raw, plans, ops, blob, pi, cap=1000)[::2] == hm.rewrite_body(raw, plans, ops, blob, pi, cap=1000)[::2]
+
+
+def test_fast_path_never_accepts_what_the_machine_rejects(plans028, plans027):
+    rng = random.Random(77)
+    bad = [b'{"model":"gw/chain","a":1,"a":2}', b'{"model":"gw/chain","x":{"k":1,"k":1}}', b'{"model":"gw/chain","t":0.1234567890123456789}',
+           b'{"model":"gw/chain","t":NaN}', b'{"model":"gw/chain","t":"\\ud800"}', b'{"model":"gw/chain",}', b'{"model":"gw/chain"} x',
+           b'{"model":"gw/chain","t":01}', b'{"model":"gw/chain","t":"\xff"}', b'{"model":"gw/chain","t":"a\nb"}', b'', b'{"model":"gw/chain","t":[1,2}',
+           b'{"a":1}}', b'{"a":1}{', b'[{"a":1}]', b'{"a":tru}', b'{"a":-}', b'{"a":1.}', b'{"a":.5}', b'{"a":1e}', b'{"a" 1}', b'{"a"::1}', b'{1:2}',
+           b'{"a":"\\x"}', b'{"a":"\\u12G4"}', b'{"a":"x}', b'{"a":1,,"b":2}', b'{"a":[,1]}', b'{"a":[1 2]}', b'{"a":"b" "c":1}', b'{"a":1}\\', b'\\{"a":1}',
+           b'{"a":\\"b"}', b'{"a":"\xc3"}', b'{"a":"\x80"}', b'{"a":"\xed\xa0\x80"}', b'{"a":"\xf4\x90\x80\x80"}', b'{"a":"\xc0\xaf"}', b'{"a":1}\xc3\xa9']
+    # mutations of valid bodies: drop / flip / duplicate one byte
+    for _ in range(1500):
+        raw = bytearray(bc.spell(rng, bc.rand_body(rng), plain_keys=True).encode("utf-8"))
+        k = rng.randrange(len(raw))
+        op = rng.randrange(3)
+        if op == 0:
+            del raw[k]
+        elif op == 1:
+            raw[k] = rng.choice(b'{}[]",:\\ 0a\x80\xe2')
+        else:
+            raw.insert(k, raw[k])
+        bad.append(bytes(raw))
+    tally = {}
+    _fast_vs_sequential(bad, ((plans028, True), (plans027, True), (plans028, False)), [(1, -1, False), (3, -1, True)], tally)
+    assert tally.get("irregular", 0) > 500
+
+
+# ---- row a12: non-streaming responses ---------------------------------------------------------------
+@pytest.mark.parametrize("fast", [False, True])
+def test_response_goldens(plans028, fast):
+    """status + body bytes of an upstream response -> what the unmodified make_llm_request + chat.py:146 +
+    Starlette made of it (tests/golden/response_cases.json); the host build stands in for the GPU"""
+    from fake_body_engine import HostBodyEngine
+    from llmapigateway_b200.responses import ExoticResponse, normalise_responses
+    from oracle import response_oracle as ro
+    doc = json.loads((GOLDEN_DIR / "response_cases.json").read_text())
+    eng = HostBodyEngine(plans028, fast=fast)
+    url = "http://upstream.test/v1/chat/completions"
+    kinds = set()
+    for c in doc["cases"]:
+        content = base64.b64decode(c["content"])
+        okind, oval = ro.normalise(c["status"], content, url)
+        assert okind == c["kind"] and (okind != "ok" or oval == base64.b64decode(c["body"]))        # the oracle is pinned
+        try:
+            body, detail = normalise_responses(eng, plans028, [content], [c["status"]], url)[0]
+        except ExoticResponse:
+            assert c["kind"] == "raise"
+            kinds.add("raise")
+            continue
+        kinds.add(c["kind"])
+        if c["kind"] == "ok":
+            assert detail is None and body == base64.b64decode(c["body"])
+        else:
+            assert c["kind"] == "fail" and body is None
+            if not (c["detail"] or "").startswith("Unexpected error during request") or "has no attribute" in c["detail"]:
+                assert detail == c["detail"]
+    assert kinds == {"ok", "fail", "raise"}
+
+
+def test_response_fuzz_against_oracle(plans028):
+    from fake_body_engine import HostBodyEngine
+    from llmapigateway_b200.responses import normalise_responses
+    from oracle import response_oracle as ro
+    rng = random.Random(2718)
+    eng = HostBodyEngine(plans028, fast=True)
+    n_ok = 0
+    for it in range(1500):
+        doc = bc.rand_body(rng)
+        if it % 7 == 0:
+            doc[rng.choice(["error", "detail"])] = rng.choice([{"message": "m"}, "text", None, {"code": 1}, 5])
+        raw = bc.spell(rng, doc, plain_keys=(it % 2 == 0)).encode("utf-8")
+        status = rng.choice([200, 200, 200, 201, 404, 500])
+        kind, val = ro.normalise(status, raw, "u")
+        body, detail = normalise_responses(eng, plans028, [raw], [status], "u", strict=False)[0]
+        if body == "exotic":
+            continue
+        if kind == "ok":
+            assert (body, detail) == (val, None)
+            n_ok += 1
+        else:
+            assert kind == "fail" and body is None and detail == val, (raw, detail, val)
+    assert n_ok > 500

@@ -151,3 +151,68 @@ def test_scan_batch(engine):
         if isinstance(omodel, str):
             assert model == omodel.encode("utf-8", "surrogatepass")[:256]
     assert seen == {0, 1, 2}
+
+
+def test_data_parallel_path_equals_exact_machine(engine):
+    """mode 0 (block-per-body fast path + exact machine for what it calls irregular) == mode 1 (exact machine only)"""
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx027")
+    engine.load_rules(plans)
+    rng = random.Random(31337)
+    corpus = [bc.spell(rng, bc.rand_body(rng), plain_keys=True).encode("utf-8") for _ in range(1500)]
+    corpus += [bc.spell(rng, bc.rand_body(rng)).encode("utf-8") for _ in range(300)]
+    corpus += chat_bodies(128, 4096, seed=12) + chat_bodies(64, 300, seed=13, non_ascii=0.3) + chat_bodies(8, 9000, seed=14)
+    for _ in range(600):                                            # damaged bodies
+        raw = bytearray(bc.spell(rng, bc.rand_body(rng), plain_keys=True).encode("utf-8"))
+        k = rng.randrange(len(raw))
+        raw[k] = rng.choice(b'{}[]",:\\ 0a\x80\xe2')
+        corpus.append(bytes(raw))
+    atts = bc.CHAIN_ATTEMPTS + [(4, -1, False)]
+    idx = [plans.plan_index("gw/chain", *atts[i % len(atts)], stream=(i % 2 == 0)) for i in range(len(corpus))]
+    try:
+        engine.set_mode(1)
+        exact = engine.rewrite_bodies(corpus, idx)
+        engine.set_mode(0)
+        fast = engine.rewrite_bodies(corpus, idx)
+    finally:
+        engine.set_mode(0)
+    assert fast == exact
+    assert sum(1 for st, _ in fast if st == rw.BODY_OK) > 1500
+
+
+def test_responses_normalise(engine):
+    """row a12 through the engine: goldens from the unmodified reference + fuzz against the oracle"""
+    from llmapigateway_b200.responses import normalise_responses
+    from oracle import response_oracle as ro
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+    engine.load_rules(plans)
+    doc = json.loads((GOLDEN / "response_cases.json").read_text())
+    url = "http://upstream.test/v1/chat/completions"
+    contents = [base64.b64decode(c["content"]) for c in doc["cases"]]
+    got = normalise_responses(engine, plans, contents, [c["status"] for c in doc["cases"]], url, strict=False)
+    for c, (body, detail) in zip(doc["cases"], got):
+        if c["kind"] == "ok":
+            assert (body, detail) == (base64.b64decode(c["body"]), None)
+        elif c["kind"] == "raise":
+            assert body == "exotic"
+        else:
+            assert body is None
+    rng = random.Random(161)
+    raws, sts = [], []
+    for it in range(2000):
+        d = bc.rand_body(rng)
+        if it % 7 == 0:
+            d[rng.choice(["error", "detail"])] = rng.choice([{"message": "m"}, "text", None, {"code": 1}, 5])
+        raws.append(bc.spell(rng, d, plain_keys=(it % 2 == 0)).encode("utf-8"))
+        sts.append(rng.choice([200, 200, 200, 201, 404, 500]))
+    got = normalise_responses(engine, plans, raws, sts, "u", strict=False)
+    n_ok = 0
+    for raw, st, (body, detail) in zip(raws, sts, got):
+        if body == "exotic":
+            continue
+        kind, val = ro.normalise(st, raw, "u")
+        if kind == "ok":
+            assert (body, detail) == (val, None)
+            n_ok += 1
+        else:
+            assert body is None and detail == val
+    assert n_ok > 600
