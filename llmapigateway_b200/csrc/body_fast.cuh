@@ -37,7 +37,7 @@ enum FastTok : uint8_t { TK_OBJ_OPEN = 0, TK_OBJ_CLOSE = 1, TK_ARR_OPEN = 2, TK_
 enum FastFlag : uint8_t { TF_KEY = 1, TF_UNQUOTED = 2, TF_SKIP = 4, TF_REPLACE = 8, TF_FLOAT = 16, TF_NEGZERO = 32, TF_TOPKEY = 64 };
 
 struct alignas(16) FastShared {
-    uint8_t text[LGW_FAST_MAXB + 32];
+    uint8_t text[LGW_FAST_MAXB + 96];
     uint16_t tok_pos[LGW_FAST_MAXT], tok_end[LGW_FAST_MAXT], tok_br[LGW_FAST_MAXT];
     uint8_t tok_type[LGW_FAST_MAXT], tok_flags[LGW_FAST_MAXT], tok_depth[LGW_FAST_MAXT], tok_ctx[LGW_FAST_MAXT], tok_aux[LGW_FAST_MAXT];
     uint16_t br_tok[LGW_FAST_MAXBR], br_open_after[LGW_FAST_MAXBR];

@@ -117,15 +117,16 @@ def scan_body(raw: bytes, model_cap: int = 256):
 FAST_IRREGULAR = 0xFFFFFFFF
 
 
-def rewrite_body_fast(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 << 16):
+def rewrite_body_fast(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 << 16, fn: str = "lgwt_rewrite_body_fast"):
     """body_fast.cuh fast_rewrite() with its phases run thread by thread: (status | FAST_IRREGULAR, out, needed)."""
     p = plans[plan_idx]
     sub = np.ascontiguousarray(ops[p["op_begin"]:p["op_end"]])
     out = np.zeros(max(cap, 1), dtype=np.uint8)
     n = C.c_uint32(0)
     buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
-    lib().lgwt_rewrite_body_fast.restype = C.c_uint32
-    st = lib().lgwt_rewrite_body_fast(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.c_int(int(p["mode"])),
+    f = getattr(lib(), fn)
+    f.restype = C.c_uint32
+    st = f(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.c_int(int(p["mode"])),
                                       sub.ctypes.data_as(C.c_void_p), C.c_uint32(len(sub)), blob.ctypes.data_as(C.c_void_p),
                                       out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n), C.byref(_last_matched))
     return st, bytes(out[:min(n.value, cap)]) if st == 0 else b"", n.value

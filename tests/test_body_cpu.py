@@ -194,13 +194,17 @@ def test_scan_matches_parse_body():
 
 
 # ---- the data-parallel path (body_fast.cuh) against the sequential machine ----------------------------
-def _fast_vs_sequential(corpus, objs, atts, tally):
+FAST_IMPL = {"chunks": hm.rewrite_body_fast}
+
+
+def _fast_vs_sequential(corpus, objs, atts, tally, impl="chunks"):
+    fast_fn = FAST_IMPL[impl]
     for it, raw in enumerate(corpus):
         att = atts[it % len(atts)]
         for obj, stream in objs:
             plans, ops, blob = obj.packed()
             pi = obj.plan_index("gw/chain", *att, stream=stream)
-            fst, fout, fneed = hm.rewrite_body_fast(raw, plans, ops, blob, pi)
+            fst, fout, fneed = fast_fn(raw, plans, ops, blob, pi)
             if fst == hm.FAST_IRREGULAR:
                 tally["irregular"] = tally.get("irregular", 0) + 1
                 continue
@@ -209,7 +213,8 @@ def _fast_vs_sequential(corpus, objs, atts, tally):
             tally["fast"] = tally.get("fast", 0) + 1
 
 
-def test_fast_path_equals_sequential_machine(plans028, plans027):
+@pytest.mark.parametrize("impl", ["chunks"])
+def test_fast_path_equals_sequential_machine(plans028, plans027, impl):
     """contract of body_fast.cuh: whenever it does not say "irregular", status, length and bytes are the
     sequential machine's (which the tests above pin to the oracle)"""
     from llmapigateway_b200.synth import chat_bodies
@@ -218,22 +223,23 @@ def test_fast_path_equals_sequential_machine(plans028, plans027):
     objs = ((plans028, True), (plans027, True), (plans028, False))
     tally = {}
     plain = [bc.spell(rng, bc.rand_body(rng), plain_keys=True).encode("utf-8") for _ in range(2500)]
-    _fast_vs_sequential(plain, objs, atts, tally)
+    _fast_vs_sequential(plain, objs, atts, tally, impl)
     assert tally["fast"] > 4000, tally                      # the fast path really is exercised (json5 + non-ASCII keys fall back)
     escaped = [bc.spell(rng, bc.rand_body(rng)).encode("utf-8") for _ in range(800)]
-    _fast_vs_sequential(escaped, objs, atts, tally)
+    _fast_vs_sequential(escaped, objs, atts, tally, impl)
     chat = chat_bodies(48, 4096, seed=2) + chat_bodies(48, 300, seed=3, non_ascii=0.3) + chat_bodies(16, 6000, seed=4) + chat_bodies(4, 9000, seed=5)
     t2 = {}
-    _fast_vs_sequential(chat, objs, atts, t2)
+    _fast_vs_sequential(chat, objs, atts, t2, impl)
     assert t2["fast"] >= 3 * (48 + 48 + 16) - 10 and t2.get("irregular", 0) >= 12, t2      # > 6 KiB bodies take the sequential machine
     # small output slots: same OVERFLOW verdict and needed length
     plans, ops, blob = plans028.packed()
     for raw in chat[:20]:
         pi = plans028.plan_index("gw/chain", 1)
-        assert hm.rewrite_body_fast(raw, plans, ops, blob, pi, cap=1000)[::2] == hm.rewrite_body(raw, plans, ops, blob, pi, cap=1000)[::2]
+        assert FAST_IMPL[impl](raw, plans, ops, blob, pi, cap=1000)[::2] == hm.rewrite_body(raw, plans, ops, blob, pi, cap=1000)[::2]
 
 
-def test_fast_path_never_accepts_what_the_machine_rejects(plans028, plans027):
+@pytest.mark.parametrize("impl", ["chunks"])
+def test_fast_path_never_accepts_what_the_machine_rejects(plans028, plans027, impl):
     rng = random.Random(77)
     bad = [b'{"model":"gw/chain","a":1,"a":2}', b'{"model":"gw/chain","x":{"k":1,"k":1}}', b'{"model":"gw/chain","t":0.1234567890123456789}',
            b'{"model":"gw/chain","t":NaN}', b'{"model":"gw/chain","t":"\\ud800"}', b'{"model":"gw/chain",}', b'{"model":"gw/chain"} x',
@@ -254,7 +260,7 @@ def test_fast_path_never_accepts_what_the_machine_rejects(plans028, plans027):
             raw.insert(k, raw[k])
         bad.append(bytes(raw))
     tally = {}
-    _fast_vs_sequential(bad, ((plans028, True), (plans027, True), (plans028, False)), [(1, -1, False), (3, -1, True)], tally)
+    _fast_vs_sequential(bad, ((plans028, True), (plans027, True), (plans028, False)), [(1, -1, False), (3, -1, True)], tally, impl)
     assert tally.get("irregular", 0) > 500
 
 
