@@ -29,13 +29,14 @@
 #define LGW_TPL_MAX 504u            /* longest event kept as a template */
 #define LGW_TPL_IDS 32u
 
-// 16 KB tile in shared memory, swizzled so that 32 lanes reading the same byte position of 32
-// consecutive 64-byte rows (the 64-byte-event pattern) hit 32 different banks, while a 16-byte
-// vector store stays one STS.128 (the four words are permuted inside their own vector):
-//   physical offset = d ^ X(d),  X(d) = ((d >> 3) & 0x30) | ((d >> 7) & 0x0c)
-__device__ __forceinline__ uint32_t swz(uint32_t d) { return d ^ (((d >> 3) & 0x30u) | ((d >> 7) & 0x0cu)); }
+// Tile in shared memory, one pad word after every 64-byte row: 32 lanes reading the same byte position of 32
+// consecutive 64-byte rows (the 64-byte-event pattern) then hit 32 different banks, and the address of a byte
+// is two instructions away from its offset:  physical offset = d + 4 * (d / 64).
+__device__ __forceinline__ uint32_t phys(uint32_t d) { return d + ((d >> 6) << 2); }
+#define LGW_TILE_PHYS_BYTES (LGW_STAGE_BYTES + LGW_STAGE_BYTES / 16 + 16)
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
-__shared__ __align__(16) uint8_t sh_tile[LGW_STAGE_BYTES];
+__shared__ __align__(16) uint8_t sh_tile[LGW_TILE_PHYS_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
@@ -77,7 +78,7 @@ struct TileEnv {
     // aligned 32-bit word containing byte `pos` (little endian); bytes past n_bytes read as 0
     __device__ __forceinline__ uint32_t word(uint32_t pos) const {
         const uint32_t p4 = pos & ~3u, d = p4 - t0;
-        if (d < LGW_STAGE_BYTES) return lds_u32(tile_s + swz(d));
+        if (d < LGW_STAGE_BYTES) return lds_u32(tile_s + phys(d));
         return word_global(p4);
     }
     __device__ __noinline__ uint32_t word_global(uint32_t p4) const {
@@ -442,15 +443,8 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                     x[k] = make_uint4(w0, w1, w2, w3);
                 }
                 high |= x[k].x | x[k].y | x[k].z | x[k].w;
-                const uint32_t r = v >> 2;                          // 64-byte row
-                const uint32_t kx = (r >> 3) & 3u;                  // word permutation inside the vector
-                uint4 y;
-                y.x = kx == 0 ? x[k].x : kx == 1 ? x[k].y : kx == 2 ? x[k].z : x[k].w;
-                y.y = kx == 0 ? x[k].y : kx == 1 ? x[k].x : kx == 2 ? x[k].w : x[k].z;
-                y.z = kx == 0 ? x[k].z : kx == 1 ? x[k].w : kx == 2 ? x[k].x : x[k].y;
-                y.w = kx == 0 ? x[k].w : kx == 1 ? x[k].z : kx == 2 ? x[k].y : x[k].x;
-                const uint32_t slot16 = (r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4);
-                *reinterpret_cast<uint4*>(sh_tile + slot16) = y;
+                const uint32_t pa = env.tile_s + phys(v << 4);      // a 16-byte vector never straddles a 64-byte row
+                sts_u32(pa, x[k].x); sts_u32(pa + 4, x[k].y); sts_u32(pa + 8, x[k].z); sts_u32(pa + 12, x[k].w);
             }
             // halo: the first bytes of the next tile, staged only (their own tile copies them out)
             if (tid < LGW_HALO_BYTES / 16) {
@@ -467,13 +461,8 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                     }
                     h = make_uint4(w0, w1, w2, w3);
                 }
-                const uint32_t r = v >> 2, kx = (r >> 3) & 3u;
-                uint4 y;
-                y.x = kx == 0 ? h.x : kx == 1 ? h.y : kx == 2 ? h.z : h.w;
-                y.y = kx == 0 ? h.y : kx == 1 ? h.x : kx == 2 ? h.w : h.z;
-                y.z = kx == 0 ? h.z : kx == 1 ? h.w : kx == 2 ? h.x : h.y;
-                y.w = kx == 0 ? h.w : kx == 1 ? h.z : kx == 2 ? h.y : h.x;
-                *reinterpret_cast<uint4*>(sh_tile + ((r << 6) | (((v & 3u) ^ ((r >> 1) & 3u)) << 4))) = y;
+                const uint32_t pa = env.tile_s + phys(v << 4);
+                sts_u32(pa, h.x); sts_u32(pa + 4, h.y); sts_u32(pa + 8, h.z); sts_u32(pa + 12, h.w);
             }
         }
         DBG_STAMP(2);
