@@ -78,6 +78,23 @@ class StreamBatcher:
                 self.usage_sink.insert_usage(usage)
         return st, usage
 
+    # -- request bodies / non-streaming responses (rows a1-a4, a12): same worker thread, same engine ---------
+    def load_rules(self, plans) -> None:
+        """Compiled plan table (rewrite.RulePlans); call at config load / hot reload, before serving."""
+        self._worker.submit(self.eng.load_rules, plans).result()
+        self.plans = plans
+
+    async def rewrite_bodies(self, bodies, plan_idx):
+        return await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.rewrite_bodies, list(bodies), list(plan_idx))
+
+    async def scan_bodies(self, bodies):
+        return await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.scan_bodies, list(bodies))
+
+    async def normalise_responses(self, contents, http_status, target_url: str):
+        from .responses import normalise_responses
+        return await asyncio.get_running_loop().run_in_executor(
+            self._worker, lambda: normalise_responses(self.eng, self.plans, list(contents), list(http_status), target_url))
+
     async def detail(self, slot: int) -> str:
         raw = await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.detail, slot)
         return raw.decode("utf-8", errors="replace")
@@ -131,16 +148,31 @@ class StreamBatcher:
 
 async def make_llm_request(target_url: str, headers: dict, payload: dict, is_streaming: bool, *, batcher: StreamBatcher,
                            client_factory=None):
-    """Drop-in for request_handler.py:8 on the streaming branch.  Returns (StreamingResponse, None) on
-    success and (None, error_detail) on failure; never raises (request_handler.py:178-187)."""
+    """Drop-in for request_handler.py:8.  Returns (response, None) on success and (None, error_detail) on
+    failure; never raises (request_handler.py:178-187).  `payload` is the attempt's body: the bytes
+    `StreamBatcher.rewrite_bodies` produced (rows a3/a4) -- a dict is still accepted on the streaming branch
+    and encoded by httpx as in the reference.  Non-streaming success is a ready `Response` whose body is
+    byte-identical to what FastAPI renders from the reference's returned dict (row a12)."""
     import httpx
-    from fastapi.responses import StreamingResponse
-    if not is_streaming:
-        raise NotImplementedError("non-streaming requests stay on the reference's own path in this round (rows a4/a12)")
+    from fastapi.responses import Response, StreamingResponse
     client = (client_factory or (lambda **kw: httpx.AsyncClient(**kw)))(timeout=httpx.Timeout(300.0, connect=60.0))
     slot = None
+    body_kw = {"content": bytes(payload)} if isinstance(payload, (bytes, bytearray, memoryview)) else {"json": payload}
+    if not is_streaming:                                                  # request_handler.py:152-176
+        try:
+            if "json" in body_kw:
+                raise TypeError("non-streaming payloads must be the bytes produced by rewrite_bodies (no CPU serialiser in this package)")
+            response = await client.post(target_url, headers=headers, timeout=None, **body_kw)
+            body, detail = (await batcher.normalise_responses([response.content], [response.status_code], target_url))[0]
+            if body is None:
+                return None, detail
+            return Response(content=body, status_code=200, media_type="application/json"), None
+        except httpx.RequestError as e:                                   # request_handler.py:178-182
+            return None, f"RequestError connecting to {target_url}: {str(e)}"
+        except Exception as e:                                            # request_handler.py:183-187
+            return None, f"Unexpected error during request to {target_url}: {str(e)}"
     try:
-        ctx = client.stream("POST", target_url, headers=headers, json=payload, timeout=None)
+        ctx = client.stream("POST", target_url, headers=headers, timeout=None, **body_kw)
         response = await ctx.__aenter__()
         if response.status_code >= 400:                                   # request_handler.py:25-30
             body = await response.aread()

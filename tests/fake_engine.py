@@ -60,3 +60,12 @@ class FakeEngine:
         for s in slots:
             self.hist.pop(int(s), None)
         return out
+
+
+    # ---- request bodies / responses: host build of the body machine (fake_body_engine.HostBodyEngine) ----
+    def load_rules(self, plans):
+        from fake_body_engine import HostBodyEngine
+        self._body = HostBodyEngine(plans, fast=True)
+
+    def rewrite_bodies(self, bodies, plan_idx, slot_cap=None, with_matched=False):
+        return self._body.rewrite_bodies(bodies, plan_idx, slot_cap, with_matched)

@@ -102,3 +102,42 @@ def test_two_rank_gloo_sharded_path():
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK" in outs[0], outs[0]
+
+
+def test_non_streaming_seam_matches_reference_goldens():
+    """make_llm_request(..., is_streaming=False): engine-rewritten body bytes go upstream as they are; the upstream
+    response comes back as the reference would have rendered it (tests/golden/response_cases.json)"""
+    import base64
+    import body_cases as bc
+    from golden_io import GOLDEN
+    from llmapigateway_b200 import rewrite as rw
+    doc = json.loads((GOLDEN / "response_cases.json").read_text())
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb")
+    url = "http://upstream.test/v1/chat/completions"
+
+    async def go():
+        batcher = StreamBatcher(FakeEngine(max_streams=8), window_s=0.0005)
+        batcher.load_rules(plans)
+        raw = json.dumps({"model": "gw/chain", "messages": [{"role": "user", "content": "hi"}]}).encode()
+        (st, payload), = await batcher.rewrite_bodies([raw], [plans.plan_index("gw/chain", 1, stream=False)])
+        assert st == rw.BODY_OK and payload.startswith(b'{model: "m-or"')            # json5.dumps form (request_handler.py:153)
+        seen = []
+        for c in doc["cases"]:
+            content = base64.b64decode(c["content"])
+
+            def handler(request, content=content, status=c["status"]):
+                seen.append(request.content)
+                return httpx.Response(status, headers={"content-type": "application/json"}, content=content)
+
+            resp, err = await make_llm_request(url, {"Content-Type": "application/json"}, payload, False, batcher=batcher,
+                                               client_factory=lambda **kw: httpx.AsyncClient(transport=httpx.MockTransport(handler), **kw))
+            if c["kind"] == "ok":
+                assert err is None and bytes(resp.body) == base64.b64decode(c["body"])
+            elif c["kind"] == "fail":
+                assert resp is None
+                if c["detail"] is None or not c["detail"].startswith("Unexpected error during request") or "has no attribute" in c["detail"]:
+                    assert err == c["detail"]
+            else:                                               # the reference's renderer raises -> our seam reports the attempt as failed
+                assert resp is None and err.startswith("Unexpected error during request")
+        assert seen and all(s == payload for s in seen)          # the bytes on the wire are the engine's bytes
+    asyncio.run(go())
