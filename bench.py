@@ -319,9 +319,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         # the other built rows of SURVEY 8 on their own configurations (C2 bodies, C5 rollup at 2M records), same box, same run
         try:
-            import importlib.util
-            spec = importlib.util.spec_from_file_location("bench_rows", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_rows.py"))
-            br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))   # (spawned CPU workers import it by name)
+            import bench_rows as br
             eng2 = L.Engine(max_streams=64, max_step_chunks=1024, max_step_bytes=1 << 20, device=local)
             line["other_rows"] = br.bench_bodies(eng2, 1024, reps=10) + br.bench_rollup(eng2, 2_000_000)
             eng2.close_engine()
