@@ -60,6 +60,7 @@ class UsageTable:
         self._lib = _native.load()
         self._host = {c: np.zeros(0, dtype=d) for c, d in zip(self.COLS, self.DTYPES)}
         self._models: list[str | None] = []      # per record, until encoded
+        self._providers: list[str | None] = []   # per record (listing only; the rollup does not group by provider)
         self._dev = None                          # (n, {col: device ptr}, names)
         self._pending_rows: list[tuple] = []
 
@@ -69,7 +70,7 @@ class UsageTable:
         ts = to_us(timestamp or datetime.now())
         g = tokens_usage.get
         self._pending_rows.append((ts, g("model"), int(g("prompt_tokens", 0)), int(g("completion_tokens", 0)), int(g("total_tokens", 0)),
-                                   int(g("reasoning_tokens", 0)), int(g("cached_tokens", 0)), float(g("cost", 0.0))))
+                                   int(g("reasoning_tokens", 0)), int(g("cached_tokens", 0)), float(g("cost", 0.0)), g("provider")))
         self._dev = None
 
     def load_columns(self, ts_us, models, prompt, completion, total, reasoning, cached, cost):
@@ -79,6 +80,7 @@ class UsageTable:
                       "total_tokens": np.ascontiguousarray(total, np.int32), "reasoning_tokens": np.ascontiguousarray(reasoning, np.int32),
                       "cached_tokens": np.ascontiguousarray(cached, np.int32), "cost": np.ascontiguousarray(cost, np.float64)}
         self._models = list(models)
+        self._providers = [None] * len(self._models)
         self._pending_rows = []
         self._dev = None
 
@@ -92,6 +94,7 @@ class UsageTable:
                 self._host[name] = np.concatenate([h[name], np.array(cols[2 + k], np.int32)])
             self._host["cost"] = np.concatenate([h["cost"], np.array(cols[7], np.float64)])
             self._models = list(old_models) + list(cols[1])
+            self._providers = list(self._providers) + list(cols[8])
             self._pending_rows = []
         names = sorted({m for m in self._models if m is not None}, key=lambda s: s.encode("utf-8"))
         rank = {m: i + 1 for i, m in enumerate(names)}
@@ -180,6 +183,31 @@ class UsageTable:
                         "prompt_tokens": int(r["prompt_tokens"]), "completion_tokens": int(r["completion_tokens"]),
                         "total_tokens": int(r["total_tokens"]), "reasoning_tokens": int(r["reasoning_tokens"]),
                         "cached_tokens": int(r["cached_tokens"]), "cost": float(r["cost"]), "count": int(r["count"])})
+        return out
+
+    # -- record listing: /v1/api/usage-records (stats.py:69-87) ---------------------------------------------
+    def get_total_records_count(self) -> int:
+        """tokens_usage_db.py:200-220"""
+        return len(self)
+
+    def get_latest_usage_records(self, limit: int = 25, offset: int = 0) -> list[dict]:
+        """tokens_usage_db.py:69-117: newest first (`ORDER BY timestamp DESC LIMIT ? OFFSET ?`), same keys.  Host
+        side: a page of 25 rows out of the host copy of the columns is not GPU work.  Records with equal
+        timestamps come in insertion order (SQLite leaves their order unspecified)."""
+        self._materialise()
+        h = self._host
+        n = int(h["ts_us"].size)
+        if limit < 0:
+            limit = n                                           # SQLite: a negative LIMIT means no limit
+        order = np.argsort(-h["ts_us"], kind="stable")[max(offset, 0):max(offset, 0) + limit]
+        out = []
+        for i in order:
+            i = int(i)
+            out.append({"id": i + 1, "timestamp": (_EPOCH + timedelta(microseconds=int(h["ts_us"][i]))).isoformat(),
+                        "prompt_tokens": int(h["prompt_tokens"][i]), "completion_tokens": int(h["completion_tokens"][i]),
+                        "total_tokens": int(h["total_tokens"][i]), "reasoning_tokens": int(h["reasoning_tokens"][i]),
+                        "cached_tokens": int(h["cached_tokens"][i]), "cost": float(h["cost"][i]),
+                        "model": self._models[i], "provider": self._providers[i]})
         return out
 
     def last_ms(self):

@@ -40,3 +40,27 @@ def test_bucket_arithmetic_matches_sqlite_strftime():
             want = conn.execute(f"SELECT strftime('{fmt}', ?)", (text,)).fetchone()[0]
             b = lib.lgw_rollup_bucket_of(to_us(dt), PERIODS[period])
             assert period_label(period, b) == want, (text, period)
+
+
+def test_record_listing_matches_the_reference_sql():
+    """/v1/api/usage-records (stats.py:69-87): UsageTable.get_latest_usage_records / get_total_records_count against the
+    reference's statement (tokens_usage_db.py:85-103, :211) on the same rows"""
+    from datetime import datetime, timedelta
+    from llmapigateway_b200.usage import UsageTable
+    t = UsageTable(engine=None)
+    base = datetime(2026, 9, 20, 12, 0, 0)
+    rows = []
+    for i in range(200):
+        ts = base + timedelta(seconds=(i * 7919) % 5000, microseconds=(i * 104729) % 1000000 if i % 11 else 0)
+        u = {"prompt_tokens": i, "completion_tokens": 2 * i, "total_tokens": 3 * i, "reasoning_tokens": i % 5, "cached_tokens": i % 3,
+             "cost": i * 1e-6, "model": None if i % 17 == 0 else "m-%d" % (i % 4), "provider": "P%d" % (i % 3)}
+        t.insert_usage(u, timestamp=ts)
+        rows.append((ts.isoformat(), u["prompt_tokens"], u["completion_tokens"], u["total_tokens"], u["reasoning_tokens"], u["cached_tokens"], u["cost"], u["model"], u["provider"]))
+    conn = ro.make_db(rows)
+    assert t.get_total_records_count() == conn.execute("SELECT COUNT(*) FROM tokens_usage").fetchone()[0] == 200
+    for limit, offset in ((25, 0), (25, 25), (7, 190), (50, 180), (0, 0), (300, 0)):
+        cur = conn.execute("SELECT id, timestamp, prompt_tokens, completion_tokens, total_tokens, reasoning_tokens, cached_tokens, cost, model, provider"
+                           " FROM tokens_usage ORDER BY timestamp DESC LIMIT ? OFFSET ?", (limit, offset))
+        cols = [d[0] for d in cur.description]
+        want = [dict(zip(cols, r)) for r in cur.fetchall()]
+        assert t.get_latest_usage_records(limit=limit, offset=offset) == want
