@@ -583,3 +583,18 @@ extern "C" int lgw_bodies_last_ms(lgw_engine* e, float ms[3]) {
     for (int i = 0; i < 3; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->bev[i], e->bev[i + 1]) == cudaSuccess) e->bms[i] = t; ms[i] = e->bms[i]; }
     return LGW_OK;
 }
+
+// diagnostics (not part of the public header, like lgw_engine_set_mode): the engine-wide event-template cache
+// out[0..7] = state[2], len[2], flags[2], cls[2]; text = first `cap` bytes of each slot's template
+extern "C" int lgw_debug_template_cache(lgw_engine* e, uint32_t out[8], uint8_t* text0, uint8_t* text1, uint32_t cap) {
+    if (!e || !out) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    TemplateCache h;
+    CK(e, cudaMemcpy(&h, e->scratch.tpl_cache, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2; ++i) { out[i] = h.state[i]; out[2 + i] = h.len[i]; out[4 + i] = h.flags[i]; out[6 + i] = h.cls[i]; }
+    if (cap > LGW_TPLC_TEXT) cap = LGW_TPLC_TEXT;
+    if (text0) memcpy(text0, h.text[0], cap);
+    if (text1) memcpy(text1, h.text[1], cap);
+    return LGW_OK;
+}

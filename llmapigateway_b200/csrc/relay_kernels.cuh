@@ -18,10 +18,10 @@
 // to be re-validated beyond the comparison.  Anything else takes the byte-wise recogniser.
 
 #ifndef LGW_RELAY_THREADS
-#define LGW_RELAY_THREADS 128
+#define LGW_RELAY_THREADS 64
 #endif
 #ifndef LGW_RELAY_BLOCKS_PER_SM
-#define LGW_RELAY_BLOCKS_PER_SM 8
+#define LGW_RELAY_BLOCKS_PER_SM 16
 #endif
 #define LGW_TILE_VECS (LGW_TILE_BYTES / 16)
 #define LGW_HALO_BYTES 512u          /* read-only look-ahead into the next tile: events that straddle the tile end */
@@ -57,7 +57,8 @@ __shared__ uint16_t sh_tpl_send[LGW_TPL_SLOTS][LGW_TPL_IDS];                    
 __shared__ uint8_t sh_tpl_skind[LGW_TPL_SLOTS][LGW_TPL_IDS];                       // 0 string value, 1 number value
 __shared__ uint32_t sh_tpl_len[LGW_TPL_SLOTS], sh_tpl_flags[LGW_TPL_SLOTS], sh_tpl_cls[LGW_TPL_SLOTS], sh_tpl_valid[LGW_TPL_SLOTS];
 __shared__ uint32_t sh_tpl_cand;                  // slot 0: lowest thread with a candidate event in this tile
-__shared__ uint32_t sh_tpl_cand1, sh_tpl_cand1_limit;   // slot 1: position of the first event that missed slot 0
+__shared__ unsigned long long sh_tpl_cand1;             // slot 1: (position << 32 | segment end) of the first event that missed slot 0 (one word: the pair must belong together)
+__shared__ uint32_t sh_tpl0_canon;                          // this block's slot 0 IS the engine-wide cache's slot 0
 __shared__ uint32_t sh_tpl_tries1;                        // failed attempts to build slot 1 (give up after a few)
 __shared__ uint32_t sh_tpl_miss, sh_tpl_replace1, sh_tpl_cstate[LGW_TPL_SLOTS];   // misses in the current tile; slot 1 was re-learnt; cache states
 // block-staged copy of a second-template candidate (its tile is gone; one thread walking global
@@ -248,15 +249,22 @@ __device__ __noinline__ void build_template(const ENV* env, uint32_t slot, uint3
 
 // publish a freshly built local template to the engine-wide cache (first writer wins per slot;
 // `replace` lets a block that re-learnt a slot overwrite a stale entry)
-__device__ __noinline__ void publish_template(TemplateCache* tc, uint32_t slot, bool replace) {
+// Slot 1 is only meaningful next to the slot 0 it was learnt against ("first event that missed slot 0"): a block
+// whose own slot 0 is not the cache's (it lost the publication race in a cold step) must not define the cache's
+// slot 1 -- it could publish the very skeleton that is already in slot 0 and leave the real second shape (the
+// usage event) without a template in every later step.
+__device__ __noinline__ bool publish_template(TemplateCache* tc, uint32_t slot, bool replace) {
     const uint32_t expect = replace ? 2u : 0u;
-    if (atomicCAS(&tc->state[slot], expect, 1u) != expect) return;
+    if (slot == 1 && !sh_tpl0_canon) return false;
+    if (atomicCAS(&tc->state[slot], expect, 1u) != expect) return false;
     tc->len[slot] = sh_tpl_len[slot]; tc->flags[slot] = sh_tpl_flags[slot]; tc->cls[slot] = sh_tpl_cls[slot];
     for (uint32_t k = 0; k < LGW_TPL_IDS; ++k) { tc->sstart[slot][k] = sh_tpl_sstart[slot][k]; tc->send[slot][k] = sh_tpl_send[slot][k]; tc->skind[slot][k] = sh_tpl_skind[slot][k]; }
     for (uint32_t k = 0; k < LGW_TPLC_TEXT; ++k) tc->text[slot][k] = sh_tpl_bytes[slot * LGW_TPL_STRIDE + k];
     for (uint32_t k = 0; k < LGW_TPLC_MAP; ++k) tc->map[slot][k] = sh_tpl_strid[slot * LGW_TPL_MAPSTRIDE + k];
     __threadfence();
     atomicExch(&tc->state[slot], 2u);
+    if (slot == 0) sh_tpl0_canon = 1;
+    return true;
 }
 
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         if (k < 64) reinterpret_cast<uint32_t*>(sh_cls)[k] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[k];
         else reinterpret_cast<uint32_t*>(sh_trans)[k - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[k - 64];
     }
-    if (tid == 0) { sh_tpl_valid[0] = sh_tpl_valid[1] = 0; sh_tpl_len[0] = sh_tpl_len[1] = 0; sh_tpl_cand1 = 0xFFFFFFFFu; sh_tpl_tries1 = 0; }
+    if (tid == 0) { sh_tpl_valid[0] = sh_tpl_valid[1] = 0; sh_tpl_len[0] = sh_tpl_len[1] = 0; sh_tpl_cand1 = ~0ull; sh_tpl_tries1 = 0; sh_tpl0_canon = 0; }
     __syncthreads();
     {   // start from the engine-wide template cache when it has entries
         const TemplateCache* tc = a.s.tpl_cache;
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
             for (uint32_t k = tid; k < LGW_TPLC_TEXT; k += LGW_RELAY_THREADS) sh_tpl_bytes[slot * LGW_TPL_STRIDE + k] = tc->text[slot][k];
             for (uint32_t k = tid; k < LGW_TPLC_MAP; k += LGW_RELAY_THREADS) sh_tpl_strid[slot * LGW_TPL_MAPSTRIDE + k] = tc->map[slot][k];
             if (tid < LGW_TPL_IDS) { sh_tpl_sstart[slot][tid] = tc->sstart[slot][tid]; sh_tpl_send[slot][tid] = tc->send[slot][tid]; sh_tpl_skind[slot][tid] = tc->skind[slot][tid]; }
-            if (tid == 0) { sh_tpl_len[slot] = tc->len[slot]; sh_tpl_flags[slot] = tc->flags[slot]; sh_tpl_cls[slot] = tc->cls[slot]; sh_tpl_valid[slot] = 1; }
+            if (tid == 0) { sh_tpl_len[slot] = tc->len[slot]; sh_tpl_flags[slot] = tc->flags[slot]; sh_tpl_cls[slot] = tc->cls[slot]; sh_tpl_valid[slot] = 1; if (slot == 0) sh_tpl0_canon = 1; }
         }
     }
 
@@ -393,14 +401,14 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         __syncthreads();
         // second template: learnt from the first event of the previous tiles that missed slot 0; the
         // whole block stages its bytes from global memory, one thread validates the staged copy
-        if (!sh_tpl_valid[1] && sh_tpl_cand1 != 0xFFFFFFFFu) {
-            const uint32_t cps = sh_tpl_cand1;
+        if (!sh_tpl_valid[1] && sh_tpl_cand1 != ~0ull) {
+            const uint32_t cps = (uint32_t)(sh_tpl_cand1 >> 32), climit = (uint32_t)sh_tpl_cand1;
             for (uint32_t k = tid; k < LGW_TPL_STRIDE; k += LGW_RELAY_THREADS) sh_stage[k] = cps + k < n_bytes ? __ldg(a.data + cps + k) : (uint8_t)0;
             __syncthreads();
             if (tid == 0) {
                 StageEnv senv{cps, env.cls_s, env.trans_s};
-                build_template(&senv, 1, cps, sh_tpl_cand1_limit);
-                sh_tpl_cand1 = 0xFFFFFFFFu;
+                build_template(&senv, 1, cps, climit);
+                sh_tpl_cand1 = ~0ull;
                 if (!sh_tpl_valid[1]) ++sh_tpl_tries1; else publish_template(a.s.tpl_cache, 1, sh_tpl_replace1 != 0);
             }
             __syncthreads();
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                     }
                     // nominate the event for the second template (any valid event is a sound template, wherever it came from)
                     if (cls != PC_NONE && have_tpl0) {
-                        if (!have_tpl1 && sh_tpl_tries1 < 3) { atomicMin(&sh_tpl_cand1, ps); sh_tpl_cand1_limit = seg_end; }
+                        if (!have_tpl1 && sh_tpl_tries1 < 3) atomicMin(&sh_tpl_cand1, ((unsigned long long)ps << 32) | seg_end);
                         else if (have_tpl1) atomicAdd(&sh_tpl_miss, 1u);
                     }
                     LeanMachine lm;

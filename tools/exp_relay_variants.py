@@ -14,4 +14,9 @@ for name,kw in [("full",{}),("no_usage_done",dict(with_usage=False,with_done=Fal
         eng.open(b.seg_slot)
         eng.step_device(d["data"].data_ptr(),int(b.data.size),d["chunk_off"].data_ptr(),b.n_chunks,d["seg_chunk"].data_ptr(),d["seg_slot"].data_ptr(),S,out.data_ptr(),segs.data_ptr())
         eng.sync(); ms.append(eng.last_step_ms())
-    print(name, {k:round(v,4) for k,v in ms[-1].items()}, "equal", bool(torch.equal(out,d["data"])))
+    print(name, {k:round(v,4) for k,v in ms[-1].items()}, "equal", bool(torch.equal(out,d["data"])), "relay per iteration", [round(m["relay"],3) for m in ms])
+    import ctypes as C
+    st=(C.c_uint32*8)(); t0=C.create_string_buffer(64); t1=C.create_string_buffer(64)
+    if hasattr(eng._lib,"lgw_debug_template_cache"):
+        eng._lib.lgw_debug_template_cache(C.c_void_p(eng._h.value if hasattr(eng._h,"value") else eng._h), st, t0, t1, 64)
+        print("   template cache: state", list(st)[:2], "len", list(st)[2:4], "slot0", t0.raw[:40], "slot1", t1.raw[:40])
