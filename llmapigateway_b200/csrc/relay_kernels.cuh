@@ -69,6 +69,7 @@ __shared__ __align__(16) uint8_t sh_stage[LGW_TPL_STRIDE + 16];
 // rebuilds the CTA's shared-window base -- S2UR SR_CgaCtaId + ULEA -- in front of every access)
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
 // byte source + tables of the bulk kernel: the staged tile, global memory outside it
@@ -389,6 +390,9 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         const uint32_t t0 = a.tile_base + tile * LGW_TILE_BYTES;
         env.t0 = t0;
         const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
+        // the walk of a chunk starts with dependent global loads (its offsets, its segment's plan): pull those lines
+        // into L1 now, while the tile is being staged
+        for (uint32_t c = c_lo + tid; c <= c_hi; c += LGW_RELAY_THREADS) prefetch_l1(a.chunk_off + c);
         DBG_STAMP(0);
         __syncthreads();                                       // the previous tile's readers are done
         DBG_STAMP(1);
@@ -477,6 +481,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         const int tile_high = __syncthreads_or((high & 0x80808080u) != 0);
         DBG_STAMP(3);
         const uint32_t seg_lo = sh_seg_lo, seg_hi = sh_seg_hi;
+        if (tid <= seg_hi - seg_lo && tid < 8) prefetch_l1(a.s.plan + seg_lo + tid);
 
         // (1b) no template yet: the lowest thread whose chunk starts with an event builds one
         if (!sh_tpl_valid[0]) {
