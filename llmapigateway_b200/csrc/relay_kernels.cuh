@@ -386,6 +386,13 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
 
     const uint32_t tile_first = blockIdx.x * tiles_per_block;
     const uint32_t tile_last = min(n_tiles, tile_first + tiles_per_block);
+    uint32_t seg_hint = 0;                     // lower bound of the segment index of this thread's next search
+    if (tid >= LGW_RELAY_THREADS - 32 && tid < LGW_RELAY_THREADS - 30 && tile_first < tile_last) {      // first tile: one binary search
+        const uint32_t c = a.s.tile_chunk[tile_first];
+        uint32_t lo = 0, hi = a.n_segs;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+        seg_hint = lo;
+    }
     for (uint32_t tile = tile_first; tile < tile_last; ++tile) {
         const uint32_t t0 = a.tile_base + tile * LGW_TILE_BYTES;
         env.t0 = t0;
@@ -419,10 +426,16 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         }
 
         // (0) segment range of this tile's chunks
+        //     (a block walks consecutive tiles, so both ends are at or just after the previous tile's last segment:
+        //     a few forward steps instead of a binary search of dependent loads over all segments)
         if (tid >= LGW_RELAY_THREADS - 32 && tid < LGW_RELAY_THREADS - 30 && c_hi > c_lo) {
             const uint32_t c = tid == LGW_RELAY_THREADS - 32 ? c_lo : c_hi - 1;
-            uint32_t lo = 0, hi = a.n_segs;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+            uint32_t lo = seg_hint, hi = a.n_segs;
+            for (uint32_t k = 0; k < 4 && lo < hi && __ldg(a.seg_chunk + lo + 1) <= c; ++k) ++lo;
+            if (lo < hi && __ldg(a.seg_chunk + lo + 1) <= c) {
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+            }
+            seg_hint = lo;                      // (the thread looking for the first chunk's segment lags the other by one tile: still a lower bound)
             if (tid == LGW_RELAY_THREADS - 32) sh_seg_lo = lo; else sh_seg_hi = lo;
         }
         if (tid == 0) sh_tpl_cand = 0xFFFFFFFFu;
