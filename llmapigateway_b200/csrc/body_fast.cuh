@@ -26,7 +26,9 @@
 
 namespace lgw {
 
-#define LGW_FAST_THREADS 128
+#ifndef LGW_FAST_THREADS
+#define LGW_FAST_THREADS 384
+#endif
 #define LGW_FAST_MAXB 6144
 #define LGW_FAST_MAXT 1536
 #define LGW_FAST_MAXBR 512
