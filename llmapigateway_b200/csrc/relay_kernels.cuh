@@ -323,11 +323,19 @@ __device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o
 //               their first non-empty chunk; the bulk kernel verifies, k_commit applies or falls back.
 __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n_tiles) {
-        const uint32_t target = a.tile_base + i * LGW_TILE_BYTES;
-        uint32_t lo = a.chunk_lo, hi = a.chunk_hi;        // first c in [chunk_lo, chunk_hi] with chunk_off[c] >= target
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.chunk_off + mid) < target) lo = mid + 1; else hi = mid; }
-        a.s.tile_chunk[i] = lo;
+    // tile table: tile_chunk[t] = first c in [chunk_lo, chunk_hi] with chunk_off[c] >= start of tile t.  One thread per
+    // chunk writes the tiles whose start falls in (chunk_off[c-1], chunk_off[c]] -- one coalesced pass over the offsets
+    // instead of a binary search of ~20 dependent loads per tile.
+    if (i <= a.chunk_hi - a.chunk_lo) {
+        const uint32_t c = a.chunk_lo + i;
+        const uint32_t off = __ldg(a.chunk_off + c);
+        uint32_t t_first = 0;
+        if (i > 0) { const uint32_t prev = __ldg(a.chunk_off + c - 1); t_first = prev < a.tile_base ? 0u : (prev - a.tile_base) / LGW_TILE_BYTES + 1u; }
+        uint32_t t_last = off < a.tile_base ? 0u : (off - a.tile_base) / LGW_TILE_BYTES;      // off >= tile_base always holds for c >= chunk_lo
+        if (off < a.tile_base) t_first = 1;                                                  // (defensive: nothing to write)
+        if (c == a.chunk_hi) t_last = n_tiles;                                               // tiles past the last offset
+        if (t_last > n_tiles) t_last = n_tiles;
+        for (uint32_t t = t_first; t <= t_last; ++t) a.s.tile_chunk[t] = c;
     }
     if (i >= a.n_segs) return;
     const uint32_t seg = i, c0 = a.seg_chunk[seg], c1 = a.seg_chunk[seg + 1];
@@ -729,7 +737,8 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
 static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
     cudaError_t r;
     const uint32_t n_tiles = (a.n_bytes - a.tile_base + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
-    const uint32_t n_prime = (a.n_segs > n_tiles + 1 ? a.n_segs : n_tiles + 1);
+    const uint32_t n_off = a.chunk_hi - a.chunk_lo + 1;
+    const uint32_t n_prime = (a.n_segs > n_off ? a.n_segs : n_off);
     k_prime<<<(n_prime + 127) / 128, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
     if (n_tiles) {
