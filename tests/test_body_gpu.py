@@ -216,3 +216,23 @@ def test_responses_normalise(engine):
         else:
             assert body is None and detail == val
     assert n_ok > 600
+
+
+def test_packed_output_smaller_than_needed(engine):
+    """the caller's packed buffer is too small: bodies that still fit are intact, the rest report OVERFLOW"""
+    plans = rw.RulePlans(bc.RULES, fallback_provider="fb", stream_mode="httpx028")
+    engine.load_rules(plans)
+    bodies = chat_bodies(40, 600, seed=21)
+    buf, off = rw.pack_bodies(bodies)
+    idx = np.full(len(bodies), plans.plan_index("gw/chain", 1), dtype=np.uint32)
+    full, full_off, res = engine.rewrite_packed(buf, off, idx, slot_cap=2048)
+    assert np.all(res["status"] == rw.BODY_OK)
+    cut = int(full_off[25]) + 10                                  # room for 25 bodies and a bit
+    small = np.zeros(cut, dtype=np.uint8)
+    out2, off2, res2 = engine.rewrite_packed(buf, off, idx, slot_cap=2048, out=small)
+    assert np.array_equal(off2, full_off)                          # offsets still say where everything would go
+    for i in range(len(bodies)):
+        if int(full_off[i + 1]) <= cut:
+            assert res2["status"][i] == rw.BODY_OK and bytes(out2[int(off2[i]):int(off2[i + 1])]) == bytes(full[int(full_off[i]):int(full_off[i + 1])])
+        else:
+            assert res2["status"][i] == rw.BODY_OVERFLOW
