@@ -143,7 +143,18 @@ def run_reference_arm(args):
             "json_gbs": value * EVENT_BYTES / 1e9,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -157,6 +168,12 @@ def main():
     ap.add_argument("--mode", type=int, default=0, help="0 bulk kernel (default), 1 exact sequential path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one line, the JSON result: everything else that writes to fd 1 during the run (NCCL's
+    # version banner, library chatter of child processes) is sent to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -174,7 +191,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries exactly one line: the JSON result
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     S, E = args.streams, args.events
@@ -327,7 +343,7 @@ def main():
             eng2.close_engine()
         except Exception as ex:                                    # never lose the headline line to a side measurement
             line["other_rows"] = {"error": repr(ex)}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

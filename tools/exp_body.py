@@ -17,6 +17,9 @@ size = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 e = L.Engine(max_streams=64, max_step_chunks=1024, max_step_bytes=1 << 20)
 plans = rw.RulePlans(bc.RULES, fallback_provider="fb")
 e.load_rules(plans)
+import os
+if os.environ.get("LGW_BODY_MODE") == "1":
+    e.set_mode(1)      # exact machine only
 base = chat_bodies(min(n, 1024), size, seed=2)
 bodies = [base[i % len(base)] for i in range(n)]
 buf, off = rw.pack_bodies(bodies)
