@@ -252,8 +252,10 @@ typedef struct lgw_body_op {        /* one `payload[key] = value` */
 typedef struct lgw_body_plan { uint32_t op_begin, op_end, mode, _pad; } lgw_body_plan;
 typedef struct lgw_body_result {
     uint32_t status, out_len;
-    uint32_t matched;               /* bit i: op i's key is present at the top level of the body */
-    uint32_t _pad;
+    uint32_t matched;               /* bit i: op i's key is present at the top level of the body (response plans on a root
+                                       that is not an object: Python's `in` -- an element of the list equals the key, the key is a
+                                       substring of the string) */
+    uint32_t root_kind;             /* lgw_kind of the document's root value */
 } lgw_body_result;
 typedef struct lgw_body_scan {
     uint32_t status;                /* LGW_BODY_OK / PARSE_ERROR / NO_MODEL */

@@ -17,7 +17,7 @@
 namespace lgw {
 
 struct BodyPlan { uint32_t op_begin, op_end, mode, _pad; };
-struct BodyResult { uint32_t status, out_len, matched, _pad; };
+struct BodyResult { uint32_t status, out_len, matched, root_kind; };
 
 #define LGW_BODY_WARPS 4
 
@@ -49,7 +49,7 @@ k_body_fast(const uint8_t* __restrict__ bodies, const uint64_t* __restrict__ bod
                                      slots + (size_t)b * slot_cap, slot_cap, &out_len, &matched);
     if (threadIdx.x == 0) {
         if (st == LGW_FAST_IRREGULAR) redo_list[atomicAdd(redo_count, 1u)] = b;
-        else results[b] = BodyResult{st, out_len, matched, 0};
+        else results[b] = BodyResult{st, out_len, matched, KD_OBJ};       // the data-parallel path only accepts object roots
     }
 }
 
@@ -75,6 +75,7 @@ k_body_rewrite(const uint8_t* __restrict__ bodies, const uint64_t* __restrict__ 
             res.status = rewrite_body_checked(m, in, len, body_all_ascii(in, len), &out_len);
             res.out_len = out_len;
             res.matched = m.matched;
+            res.root_kind = m.root_kind;
         }
         if ((threadIdx.x & 31u) == 0) results[b] = res;
     }

@@ -119,7 +119,7 @@ struct BodyRewriter {
     // scan outputs (scan_body only)
     uint8_t want_scan; uint8_t cur_top_key;  // 1 model, 2 stream
     BodyScan* scan; uint8_t* model_buf; uint32_t model_cap;
-    uint8_t str_nonempty, root_obj, response_mode;
+    uint8_t str_nonempty, root_obj, response_mode, root_kind, probe_str;     // probe_str: this value string takes part in the `in` test of request_handler.py:167
 
     LGW_HD void fail(uint32_t s) { if (status == BS_OK) status = s; st = S_ERR; }
     LGW_HD void soft(uint32_t s) { if (status == BS_OK) status = s; }          // keep parsing, remember the verdict
@@ -189,6 +189,13 @@ struct BodyRewriter {
             for (uint32_t i = 0; i < n; ++i) { if (scan->model_len < model_cap) model_buf[scan->model_len] = tmp[i]; ++scan->model_len; }
             if (lone) soft(BS_EXOTIC);
         }
+        if (probe_str) {
+            if (lone) { probe_byte(0xED); probe_byte(0xA0 | ((cp >> 6) & 31)); probe_byte(0x80 | (cp & 63)); }     // never equal to a probe's UTF-8
+            else if (cp < 0x80) probe_byte(cp);
+            else if (cp < 0x800) { probe_byte(0xC0 | (cp >> 6)); probe_byte(0x80 | (cp & 63)); }
+            else if (cp < 0x10000) { probe_byte(0xE0 | (cp >> 12)); probe_byte(0x80 | ((cp >> 6) & 63)); probe_byte(0x80 | (cp & 63)); }
+            else { probe_byte(0xF0 | (cp >> 18)); probe_byte(0x80 | ((cp >> 12) & 63)); probe_byte(0x80 | ((cp >> 6) & 63)); probe_byte(0x80 | (cp & 63)); }
+        }
         emit_char(cp, lone);
     }
     LGW_HD void flush_high() { if (pending_high) { const uint32_t h = pending_high; pending_high = 0; str_cp(h, true); } }
@@ -218,7 +225,37 @@ struct BodyRewriter {
             else { scan->stream_kind = kind; scan->stream_truthy = truthy; }
             cur_top_key = 0;
         }
+        if (depth == 0) root_kind = kind;
         st = depth == 0 ? S_DONE : S_AFTER;
+    }
+
+    // request_handler.py:167 on a root that is not a dict: `"error" in <list>` asks whether an ELEMENT equals the
+    // string, `"error" in <str>` whether it occurs as a substring.  The probed string's text is collected in kbuf
+    // (elements) or kept as a sliding window of its last bytes (root string).
+    LGW_HD void probe_byte(uint32_t b) {
+        if (probe_str == 1) { key_byte(b); return; }                 // element of a root list: whole text (bounded; probes are short)
+        // root string: does the text so far END with a probe?
+        if (klen < 16) kbuf[klen++] = (uint8_t)b;
+        else { for (uint32_t i = 0; i < 15; ++i) kbuf[i] = kbuf[i + 1]; kbuf[15] = (uint8_t)b; }
+        for (uint32_t k = 0; k < n_ops; ++k) {
+            const BodyOp& op = ops[k];
+            if (!(op.flags & 2u) || op.key_len > klen || op.key_len == 0) continue;
+            uint32_t j = 0;
+            while (j < op.key_len && blob[op.key_off + j] == kbuf[klen - op.key_len + j]) ++j;
+            if (j == op.key_len) matched |= 1u << k;
+        }
+    }
+    LGW_HD void probe_end() {                                        // end of a list element: equal to a probe?
+        if (probe_str == 1 && klen <= LGW_BODY_KEYCAP) {
+            for (uint32_t k = 0; k < n_ops; ++k) {
+                const BodyOp& op = ops[k];
+                if (!(op.flags & 2u) || op.key_len != klen) continue;
+                uint32_t j = 0;
+                while (j < klen && blob[op.key_off + j] == kbuf[j]) ++j;
+                if (j == klen) matched |= 1u << k;
+            }
+        }
+        probe_str = 0;
     }
 
     LGW_HD uint32_t key_hash() const {
@@ -330,7 +367,7 @@ struct BodyRewriter {
     LGW_HD void open_container(bool is_obj) {
         if (depth >= LGW_BODY_MAXD) { soft(BS_EXOTIC); if (depth >= 63) { fail(BS_EXOTIC); return; } }
         value_begins();
-        if (depth == 0) { root_obj = is_obj; if (!is_obj && response_mode) soft(BS_EXOTIC); }
+        if (depth == 0) root_obj = is_obj;
         emit(is_obj ? '{' : '[');
         if (is_obj) stack |= (1ull << depth); else stack &= ~(1ull << depth);
         ++depth;
@@ -354,7 +391,11 @@ struct BodyRewriter {
     }
 
     LGW_HD void begin_value(uint32_t c) {
-        if (c == '"') { value_begins(); emit('"'); in_key = 0; st = S_STR; pending_high = 0; str_nonempty = 0; }
+        if (c == '"') {
+            value_begins(); emit('"'); in_key = 0; st = S_STR; pending_high = 0; str_nonempty = 0;
+            probe_str = 0;
+            if (response_mode && (depth == 0 || (depth == 1 && !root_obj))) { probe_str = depth == 0 ? 2 : 1; klen = 0; }
+        }
         else if (c == '{') open_container(true);
         else if (c == '[') open_container(false);
         else if (c == '-') { value_begins(); nlen = 0; n_float = 0; num_char(c); st = S_NUM_MINUS; }
@@ -377,6 +418,7 @@ struct BodyRewriter {
                 if (c == '"') {
                     flush_high();
                     if (in_key) { end_key(); return; }
+                    if (probe_str) probe_end();
                     emit('"'); value_ends(KD_STR, str_nonempty != 0); return;
                 }
                 if (c == '\\') { st = S_STR_ESC; return; }
@@ -493,7 +535,7 @@ struct BodyRewriter {
         mode = render_mode; ops = o; n_ops = n; blob = b; out = dst; cap = dst_cap; len = 0;
         st = S_VALUE; depth = 0; in_key = 0; lit_id = 0; lit_pos = 0; ucount = 0; neg_lit = 0; skipping = 0; skip_depth = 0; pending_replace = 0;
         status = BS_OK; stack = 0; ucode = 0; pending_high = 0; matched = 0; top_members = 0; klen = 0; k_has_surrogate = 0; nlen = 0; n_float = 0;
-        want_scan = 0; cur_top_key = 0; scan = nullptr; model_buf = nullptr; model_cap = 0; str_nonempty = 0; root_obj = 0; response_mode = (uint8_t)((render_mode >> 8) & 1); mode = render_mode & 0xff;
+        want_scan = 0; cur_top_key = 0; scan = nullptr; model_buf = nullptr; model_cap = 0; str_nonempty = 0; root_obj = 0; root_kind = KD_ABSENT; probe_str = 0; response_mode = (uint8_t)((render_mode >> 8) & 1); mode = render_mode & 0xff;
     }
 };
 
@@ -540,7 +582,7 @@ LGW_HD_NOINLINE uint32_t rewrite_body_checked(BodyRewriter& m, const uint8_t* in
     if (!known_ascii && !body_utf8_valid(in, n)) return BS_PARSE_ERROR;
     uint32_t i = 0;
     while (i < n && m.st != S_ERR) {
-        if (m.st == S_STR && !m.in_key && !m.pending_high) {
+        if (m.st == S_STR && !m.in_key && !m.pending_high && !m.probe_str) {
             // bulk path for string content: a run of characters that every mode renders verbatim
             const uint32_t r = plain_run(in, i, n, mode);
             if (r) {
@@ -552,9 +594,9 @@ LGW_HD_NOINLINE uint32_t rewrite_body_checked(BodyRewriter& m, const uint8_t* in
         }
         m.feed(in[i]); ++i;
     }
+    if (m.st != S_ERR) m.feed(' ');                   // a number at the very end of the document (root scalar) ends here
     if (m.st == S_ERR) return m.status ? m.status : BS_PARSE_ERROR;
     if (m.st != S_DONE) return BS_PARSE_ERROR;
-    if (m.response_mode && !m.root_obj) return BS_EXOTIC;        // `"error" in <list|str|number>` is not modelled
     *out_len = m.len;
     if (m.status) return m.status;
     if (m.len > cap) return BS_OVERFLOW;

@@ -184,7 +184,7 @@ class Engine:
 
     def rewrite_bodies(self, bodies, plan_idx, slot_cap: int | None = None, with_matched: bool = False):
         """list[bytes] in -> list[(status, payload bytes)] (payload empty unless status == BODY_OK);
-        with_matched adds the bit mask of plan keys present at the top level."""
+        with_matched adds the bit mask of plan keys present at the top level and the kind of the root value."""
         from . import rewrite as rw
         buf, off = rw.pack_bodies(bodies)
         if slot_cap is None:
@@ -195,7 +195,7 @@ class Engine:
         rows = [(int(res["status"][i]), bytes(out[int(out_off[i]):int(out_off[i + 1])]) if res["status"][i] == rw.BODY_OK else b"")
                 for i in range(len(bodies))]
         if with_matched:
-            return [(st, b, int(res["matched"][i])) for i, (st, b) in enumerate(rows)]
+            return [(st, b, int(res["matched"][i]), int(res["root_kind"][i])) for i, (st, b) in enumerate(rows)]
         return rows
 
     def bodies_last_ms(self):

@@ -20,7 +20,7 @@ from . import rewrite as rw
 
 
 class ExoticResponse(ValueError):
-    """The engine does not model this document (duplicate keys, non-object root, float with more than 15
+    """The engine does not model this document (duplicate keys, float with more than 15
     significant digits, NaN...).  The caller keeps the reference's own code path for it."""
 
 
@@ -28,7 +28,9 @@ def _error_detail(content: bytes, target_url: str):
     # request_handler.py:168 -- only reached for the rare failing response, so it runs on the host
     try:
         doc = json.loads(content)
-        return doc.get("error", {}).get("message") or doc.get("detail")
+        if "error" in doc or "detail" in doc:                # (raises for roots that do not support `in`)
+            return doc.get("error", {}).get("message") or doc.get("detail")
+        return None
     except Exception as e:                                   # request_handler.py:183-187
         return f"Unexpected error during request to {target_url}: {str(e)}"
 
@@ -43,12 +45,14 @@ def normalise_responses(engine, plans: rw.RulePlans, contents, http_status, targ
             out[i] = (None, contents[i].decode("utf-8", "replace"))
     if todo:
         got = engine.rewrite_bodies([contents[i] for i in todo], np.full(len(todo), plans.response_plan(), dtype=np.uint32), with_matched=True)
-        for i, (st, body, matched) in zip(todo, got):
+        for i, (st, body, matched, root_kind) in zip(todo, got):
             if st == rw.BODY_PARSE_ERROR:                    # request_handler.py:172-176 / :183-187 (detail text depends on json5)
                 out[i] = (None, f"Invalid JSON response from {target_url}")
-            elif st == rw.BODY_OK and matched:               # request_handler.py:167-170
+            elif st == rw.BODY_OK and (matched or root_kind not in (rw.KIND_OBJ, rw.KIND_ARR, rw.KIND_STR)):
+                # request_handler.py:167-170: the probe hit (dict key, list element, substring of a string); on a number /
+                # null / bool root `"error" in x` itself raises -> :183-187.  Rare: the text is recomputed on the host.
                 out[i] = (None, _error_detail(contents[i], target_url))
-            elif st == rw.BODY_OK and body == b"{}":         # chat.py:146: an empty dict is falsy -> failed attempt
+            elif st == rw.BODY_OK and body in (b"{}", b"[]", b'""'):       # chat.py:146: falsy response_data -> failed attempt
                 out[i] = (None, None)
             elif st == rw.BODY_OK:
                 out[i] = (body, None)

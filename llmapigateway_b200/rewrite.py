@@ -24,7 +24,8 @@ STATUS_NAMES = ["ok", "parse_error", "no_model", "overflow", "exotic", "encode_e
 OP_DTYPE = np.dtype([("key_off", "<u4"), ("key_len", "<u4"), ("rkey_off", "<u4"), ("rkey_len", "<u4"),
                      ("rval_off", "<u4"), ("rval_len", "<u4"), ("flags", "<u4"), ("_pad", "<u4")])
 PLAN_DTYPE = np.dtype([("op_begin", "<u4"), ("op_end", "<u4"), ("mode", "<u4"), ("_pad", "<u4")])
-RESULT_DTYPE = np.dtype([("status", "<u4"), ("out_len", "<u4"), ("matched", "<u4"), ("_pad", "<u4")])
+RESULT_DTYPE = np.dtype([("status", "<u4"), ("out_len", "<u4"), ("matched", "<u4"), ("root_kind", "<u4")])
+KIND_STR, KIND_OBJ, KIND_ARR = 6, 8, 9       # lgw_kind values of container / string roots (include/llmgw_b200.h)
 SCAN_DTYPE = np.dtype([("status", "<u4"), ("model_len", "<u4"), ("model_kind", "u1"), ("model_truthy", "u1"),
                        ("stream_kind", "u1"), ("stream_truthy", "u1"), ("_pad", "<u4")])
 MAX_OPS_PER_PLAN = 32

@@ -18,5 +18,5 @@ class HostBodyEngine:
             if st == hm.FAST_IRREGULAR:
                 st, out, need = hm.rewrite_body(raw, plans, ops, blob, int(pi))
             out = out if st == 0 else b""
-            rows.append((st, out, hm.last_matched()) if with_matched else (st, out))
+            rows.append((st, out, hm.last_matched(), hm.last_root_kind()) if with_matched else (st, out))
         return rows

@@ -60,6 +60,22 @@ BODIES = [
     {"model": "unknown-model", "messages": [{"role": "user", "content": "fallback provider path"}], "stream": True},
     {"model": "gw/chain", "allow_fallbacks": True, "messages": "<already a string>", "reasoning_effort": "low", "temperature": 1.5e3,
      "x": [1e16, 1e15, 123456.789, 0.0001, 0.00001, 1e22, 2.5, 100.0, 1.0, 0.1, 123456789012345.0, 1e-7, 6.02e23]},
+    # a realistic tool-calling conversation (nested schemas, escapes, empty containers, nulls)
+    {"model": "gw/chain", "stream": True, "stream_options": {"include_usage": True}, "max_completion_tokens": 2048, "parallel_tool_calls": False,
+     "response_format": {"type": "json_schema", "json_schema": {"name": "answer", "strict": True, "schema": {"type": "object", "properties": {
+         "city": {"type": "string", "description": "City name, e.g. \"Zürich\""}, "temp_c": {"type": "number", "minimum": -90.5, "maximum": 60},
+         "tags": {"type": "array", "items": {"type": "string"}, "default": []}}, "required": ["city", "temp_c"], "additionalProperties": False}}},
+     "tools": [{"type": "function", "function": {"name": "get_weather", "description": "Look up the weather.\nReturns °C.", "parameters": {
+         "type": "object", "properties": {"q": {"type": "string"}, "days": {"type": "integer", "enum": [1, 3, 7]}, "units": {"type": ["string", "null"]}}, "required": ["q"]}}}],
+     "tool_choice": {"type": "function", "function": {"name": "get_weather"}},
+     "messages": [{"role": "system", "content": [{"type": "text", "text": "Be terse."}]},
+                  {"role": "user", "content": "What's the weather in Zürich?\tUse the tool. Path: C:\\tmp\\x   end"},
+                  {"role": "assistant", "content": None, "tool_calls": [{"id": "call_1", "type": "function", "function": {"name": "get_weather", "arguments": "{\"q\": \"Z\u00fcrich\", \"days\": 1}"}}]},
+                  {"role": "tool", "tool_call_id": "call_1", "content": "{\"temp_c\": 21.5, \"tags\": []}"}],
+     "metadata": {}, "logprobs": False, "top_logprobs": None, "seed": 1234567890123, "user": "u-🧪"},
+    # the client already sends the keys the rules assign (in place replacement keeps their positions)
+    {"provider": {"order": ["X"], "allow_fallbacks": True}, "usage": {"include": True}, "top_p": 0.5, "stop": None, "model": "gw/chain",
+     "reasoning_effort": {"nested": [1, {"a": None}]}, "temperature": 0, "messages": [{"role": "user", "content": "q"}], "allow_fallbacks": None},
 ]
 
 

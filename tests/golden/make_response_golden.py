@@ -38,6 +38,17 @@ CASES = [
     (200, b'{"a":1,}'),
     (200, b'{"a":NaN}'),
     (200, b'{"a":"\\ud800"}'),
+    (200, b'{"detail":""}'),
+    (200, b'{"detail":0,"error":{}}'),
+    (200, b'{"error":{"message":""},"detail":"second choice"}'),
+    (200, b'{"error":[1,2]}'),
+    (202, b' {"id" :"r1", "choices":[{"message":{"role":"assistant","content":null,"tool_calls":[{"id":"c","type":"function","function":{"name":"f","arguments":"{\\"a\\": 1}"}}]},"finish_reason":"tool_calls"}],"usage":{"prompt_tokens":5,"completion_tokens":0,"total_tokens":5,"prompt_tokens_details":{"cached_tokens":0}}} '),
+    (200, b'[{"error":1}]'),
+    (200, b'["error"]'),
+    (200, b'"an error string"'),
+    (200, b'12'),
+    (200, b'null'),
+    (200, b'{"big":123456789012345678901234567890,"neg":-0,"f":-0.0,"e":1E+2,"tiny":5e-324}'),
 ]
 
 

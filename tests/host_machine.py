@@ -104,6 +104,11 @@ def last_matched() -> int:
     return _last_matched.value
 
 
+def last_root_kind() -> int:
+    lib().lgwt_last_root_kind.restype = C.c_uint32
+    return lib().lgwt_last_root_kind()
+
+
 def scan_body(raw: bytes, model_cap: int = 256):
     from llmapigateway_b200.rewrite import SCAN_DTYPE
     sc = np.zeros(1, dtype=SCAN_DTYPE)

@@ -79,11 +79,15 @@ static_assert(sizeof(BodyScan) == sizeof(lgw_body_scan), "BodyScan");
 
 extern "C" {
 
+static uint32_t g_last_root_kind = 0;
+uint32_t lgwt_last_root_kind(void) { return g_last_root_kind; }
+
 uint32_t lgwt_rewrite_body(const uint8_t* in, uint32_t n, int mode, const lgw_body_op* ops, uint32_t n_ops,
                            const uint8_t* blob, uint8_t* out, uint32_t cap, uint32_t* out_len, uint32_t* matched_out) {
     BodyRewriter m;
     const uint32_t st = rewrite_body(m, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len);
     if (matched_out) *matched_out = m.matched;
+    g_last_root_kind = m.root_kind;
     return st;
 }
 
@@ -102,5 +106,6 @@ extern "C" uint32_t lgwt_rewrite_body_fast(const uint8_t* in, uint32_t n, int mo
     uint32_t matched = 0;
     const uint32_t st = fast_rewrite(&sh, in, n, mode, (const BodyOp*)ops, n_ops, blob, out, cap, out_len, &matched);
     if (matched_out) *matched_out = matched;
+    g_last_root_kind = KD_OBJ;
     return st;
 }

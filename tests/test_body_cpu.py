@@ -43,7 +43,7 @@ def test_golden_attempt_bytes(plans028):
             st, out, need = hm.rewrite_body(raw, plans, ops, blob, pi)
             assert st == rw.BODY_OK and out == want, (model, att, out, want)
             n += 1
-    assert n == 25
+    assert n == 37
 
 
 def test_plan_compiler_matches_oracle_rule_ops(plans028):
@@ -283,7 +283,12 @@ def test_response_goldens(plans028, fast):
         try:
             body, detail = normalise_responses(eng, plans028, [content], [c["status"]], url)[0]
         except ExoticResponse:
-            assert c["kind"] == "raise"
+            # documented hand-backs: the reference's renderer raises; a float outside 1e-290..1e290
+            try:
+                root = json.loads(content)
+            except Exception:
+                root = None
+            assert c["kind"] == "raise" or _may_be_exotic(root, "httpx028"), content
             kinds.add("raise")
             continue
         kinds.add(c["kind"])
@@ -319,3 +324,29 @@ def test_response_fuzz_against_oracle(plans028):
         else:
             assert kind == "fail" and body is None and detail == val, (raw, detail, val)
     assert n_ok > 500
+    # roots that are not objects: `"error" in x` is list membership / substring / TypeError (request_handler.py:167)
+    n_ok = 0
+    for it in range(600):
+        t = it % 6
+        if t == 0:
+            doc = [rng.choice(["error", "detail", "errors", "x", 1, None, {"error": 1}, ["detail"], "d\u00e9tail"]) for _ in range(rng.randint(0, 5))]
+        elif t == 1:
+            doc = rng.choice(["", "an error occurred", "no problem", "detaildetail", "deta il", "err or", "xerrorx", "\u00e9rror", "detai", "e"]) * rng.randint(1, 2)
+        elif t == 2:
+            doc = rng.choice([0, 12, -1.5, None, True, False])
+        elif t == 3:
+            doc = [[bc.rand_value(rng) for _ in range(3)], "error " if it % 4 else "error"]
+        else:
+            doc = [bc.rand_value(rng) for _ in range(rng.randint(0, 4))]
+        raw = bc.spell(rng, doc).encode("utf-8")
+        kind, val = ro.normalise(200, raw, "u")
+        body, detail = normalise_responses(eng, plans028, [raw], [200], "u", strict=False)[0]
+        if body == "exotic":
+            assert _may_be_exotic(doc, "httpx028") or kind == "raise", raw
+            continue
+        if kind == "ok":
+            assert (body, detail) == (val, None), raw
+            n_ok += 1
+        else:
+            assert kind == "fail" and body is None and detail == val, (raw, detail, val)
+    assert n_ok > 100
