@@ -106,7 +106,49 @@ async def run_one(body):
     return raw, status, attempts
 
 
+# chat.py:31-45: the 400 conditions, and how `stream` is read (is_streaming of the first attempt)
+PARSE_CASES = [
+    b'{"model":"gw/chain","stream":true,"messages":[]}', b'{"model":"gw/chain","stream":1,"messages":[]}', b'{"model":"gw/chain","stream":"yes"}',
+    b'{"model":"gw/chain","stream":0}', b'{"model":"gw/chain","stream":null}', b'{"model":"gw/chain","stream":[]}', b'{"model":"gw/chain","stream":[0]}',
+    b'{"model":"gw/chain"}', b'  {"stream":false,"model":"gw/chain"}  ', b'{"model":"gw\\u002fchain","stream":{}}',
+    b'{"messages":[]}', b'{"model":"","messages":[]}', b'{"model":null}', b'{"model":0}', b'{"model":[]}', b'{"model":{}}', b'{"model":false}',
+    b'{"model":["gw/chain"]}', b'{"model":7}', b'{"model":1.5}',
+    b'[{"model":"gw/chain"}]', b'"gw/chain"', b'42', b'null', b'true', b'{}', b'', b'{"model":"gw/chain"', b'{"model":"gw/chain",}', b'\xff\xfe',
+    b'{"model":"gw/chain"} trailing', b'{"x":{"model":"inner"}}', b'{"model":"a","model":""}', b'{"model":"","model":"gw/chain"}',
+]
+
+
+async def run_parse(raw):
+    attempts = []
+
+    async def fake_make_llm_request(target_url, headers, payload, is_streaming):
+        attempts.append(bool(is_streaming))
+        return None, "forced failure"
+
+    chat.make_llm_request = fake_make_llm_request
+    chat.settings.fallback_provider = "fb"
+    state = types.SimpleNamespace(config_loader=types.SimpleNamespace(providers_config=PROVIDERS, fallback_rules=RULES))
+
+    class _Req:
+        app = types.SimpleNamespace(state=state)
+        headers = {"Authorization": "Bearer k"}
+
+        async def body(self):
+            return raw
+
+    try:
+        await chat.chat_completions(_Req())
+        return 200, None, attempts
+    except Exception as e:
+        return getattr(e, "status_code", 500), str(getattr(e, "detail", "")), attempts
+
+
 def main():
+    parse = []
+    for raw in PARSE_CASES:
+        status, detail, attempts = asyncio.run(run_parse(raw))
+        parse.append({"body": base64.b64encode(raw).decode(), "http_status": status, "detail_head": (detail or "")[:26],
+                      "is_streaming": attempts[0] if attempts else None})
     cases = []
     for body in BODIES:
         raw, status, attempts = asyncio.run(run_one(body))
@@ -116,10 +158,11 @@ def main():
             a["payload_items"] = json.dumps(list(a["payload"].items()), ensure_ascii=True)   # key order preserved
             del a["payload"]
         cases.append({"body": base64.b64encode(raw).decode(), "status": status, "attempts": attempts})
-    doc = {"generator": "tests/golden/make_body_golden.py", "httpx": httpx.__version__, "rules": RULES, "cases": cases}
+    doc = {"generator": "tests/golden/make_body_golden.py", "httpx": httpx.__version__, "rules": RULES, "cases": cases, "parse": parse}
     out = HERE / "body_cases.json"
     out.write_text(json.dumps(doc))
     print("wrote", out, [len(c["attempts"]) for c in cases], [c["status"] for c in cases])
+    print("parse:", [(p["http_status"], p["detail_head"][:14], p["is_streaming"]) for p in parse])
 
 
 if __name__ == "__main__":

@@ -350,3 +350,21 @@ def test_response_fuzz_against_oracle(plans028):
         else:
             assert kind == "fail" and body is None and detail == val, (raw, detail, val)
     assert n_ok > 100
+
+
+def test_scan_matches_reference_parse_goldens():
+    """chat.py:31-45 driven for real (tests/golden/make_body_golden.py `parse`): which bodies are answered 400 and with which
+    message, and what `stream` means for the first attempt"""
+    doc = json.loads((GOLDEN_DIR / "body_cases.json").read_text())
+    seen = set()
+    for p in doc["parse"]:
+        raw = base64.b64decode(p["body"])
+        sc, model = hm.scan_body(raw)
+        ost = bo.parse_body(raw)[0]
+        want = 1 if p["detail_head"].startswith("Error reading") else 2 if p["detail_head"].startswith("Missing 'model") else 0
+        assert ost == want, raw                                   # the oracle is pinned
+        assert int(sc["status"]) == want, (raw, sc)
+        seen.add(want)
+        if want == 0 and p["is_streaming"] is not None:
+            assert bool(sc["stream_truthy"]) == p["is_streaming"], raw
+    assert seen == {0, 1, 2}

@@ -238,3 +238,15 @@ def test_packed_output_smaller_than_needed(engine):
             assert res2["status"][i] == rw.BODY_OK and bytes(out2[int(off2[i]):int(off2[i + 1])]) == bytes(full[int(full_off[i]):int(full_off[i + 1])])
         else:
             assert res2["status"][i] == rw.BODY_OVERFLOW
+
+
+def test_scan_reference_parse_goldens(engine):
+    """chat.py:31-45 goldens (made by driving the unmodified endpoint) through lgw_bodies_scan"""
+    doc = json.loads((GOLDEN / "body_cases.json").read_text())
+    raws = [base64.b64decode(p["body"]) for p in doc["parse"]]
+    scans, models = engine.scan_bodies(raws)
+    for p, raw, sc in zip(doc["parse"], raws, scans):
+        want = 1 if p["detail_head"].startswith("Error reading") else 2 if p["detail_head"].startswith("Missing 'model") else 0
+        assert int(sc["status"]) == want, raw
+        if want == 0 and p["is_streaming"] is not None:
+            assert bool(sc["stream_truthy"]) == p["is_streaming"], raw
