@@ -114,8 +114,21 @@ __device__ __forceinline__ uint32_t first_special(uint32_t w) {
     return m ? (uint32_t)(__ffs(m) - 1) >> 3 : 4u;      // the lowest flagged byte is exact (borrows only travel upward)
 }
 
+// length of the valid escape sequence whose backslash sits at `ib` (2, or 6 for \\uXXXX), 0 when the recogniser would
+// reject it (lean_json.cuh L_STR_ESC / L_STR_U)
+__device__ __noinline__ uint32_t escape_length(const TileEnv& env, uint32_t ib) {
+    const uint32_t w = env.wordu(ib + 1);
+    const uint32_t c = w & 0xffu;
+    if (c == 'u') {
+        const uint32_t h = (w >> 8) | (env.at(ib + 5) << 24);     // the four hex digits
+        for (uint32_t j = 0; j < 4; ++j) { const uint32_t x = (h >> (8 * j)) & 0xffu; if (!(x - '0' < 10u || (x | 0x20u) - 'a' < 6u)) return 0; }
+        return 6;
+    }
+    return (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') ? 2u : 0u;
+}
+
 // Does the event starting at ps follow template `slot`?  The event may differ from the template in
-// any number of VALUE spans: inside a string value it may hold any plain bytes (no quote, backslash
+// any number of VALUE spans: inside a string value it may hold any plain bytes and valid escapes (no quote, bare backslash
 // or control byte) up to its closing quote; a number value may be any valid JSON number (checked
 // with the number rows of the recogniser's table).  Everything else must be byte-identical, so the
 // recogniser would walk the same states: same validity, same top-level keys.
@@ -154,14 +167,19 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
         if (ia >= lenA) break;
         const uint32_t id = lds_u8(sb + ia);
         if (id == 0xffu) return false;       // the texts part at a literal position
-        if (sh_tpl_skind[slot][id] == 0) {   // string value: plain bytes up to the closing quote
+        if (sh_tpl_skind[slot][id] == 0) {   // string value: plain bytes and valid escapes up to the closing quote
             for (;;) {
-                const uint32_t k = first_special(env.wordu(ib));
+                const uint32_t w4 = env.wordu(ib);
+                const uint32_t k = first_special(w4);
                 ib += k;
-                if (k < 4) break;
-                if (ib - ps > 8192u) return false;
+                if (k == 4) { if (ib - ps > 8192u) return false; continue; }
+                const uint32_t sp = (w4 >> (8 * k)) & 0xffu;            // the special byte itself: no second load
+                if (sp == '"') break;                                   // the closing quote
+                if (sp != '\\') return false;                           // a control byte
+                const uint32_t adv = escape_length(env, ib);            // (out of line: keeps the scan loop tight)
+                if (adv == 0) return false;
+                ib += adv;
             }
-            if (env.at(ib) != '"') return false;
         } else {                             // number value: re-validate the event's own number
             uint32_t bs = ib - (ia - sh_tpl_sstart[slot][id]);
             uint32_t st = L_VALUE;

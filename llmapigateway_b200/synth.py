@@ -190,3 +190,36 @@ def chat_bodies(n: int = 1024, target_bytes: int = 4096, seed: int = 2, model: s
                 break
         out.append(text.encode("utf-8"))
     return out
+
+
+# ---- a realistic OpenAI-style stream (not BASELINE's 64-byte deltas): id / created / model on every chunk, a role chunk,
+#      content pieces of varying length with the usual escapes, a finish chunk, the usage chunk, [DONE] -------------------
+_PIECES = [" the", " of", " and", " model", ".", ",", "\\n", "\\n\\n", ' \\"quoted\\"', " stream", " token", " B200", " gateway", " caf\\u00e9",
+           " 中文", " x", " 42", " -", " a/b", " long-ish-piece-of-text", " ok", "!", " \\\\path", " \U0001F600"]
+
+
+def openai_stream(rng, n_deltas: int, truth: UsageTruth, chunk_id: str, events_per_chunk=(1, 1)) -> list[bytes]:
+    """One upstream response as network chunks (each chunk = 1..k whole events here; use `recut` for arbitrary cuts)."""
+    head = '{"id":"%s","object":"chat.completion.chunk","created":%d,"model":"%s",' % (chunk_id, 1700000000 + int(rng.integers(0, 10**7)), truth.model)
+    ev = ['data: ' + head + '"choices":[{"index":0,"delta":{"role":"assistant","content":""},"logprobs":null,"finish_reason":null}]}\n\n']
+    for _ in range(n_deltas):
+        piece = _PIECES[int(rng.integers(0, len(_PIECES)))]
+        ev.append('data: ' + head + '"choices":[{"index":0,"delta":{"content":"%s"},"logprobs":null,"finish_reason":null}]}\n\n' % piece)
+    ev.append('data: ' + head + '"choices":[{"index":0,"delta":{},"logprobs":null,"finish_reason":"stop"}]}\n\n')
+    ev.append(usage_event(truth).decode())
+    ev.append(DONE_EVENT.decode())
+    chunks, i = [], 0
+    while i < len(ev):
+        k = int(rng.integers(events_per_chunk[0], events_per_chunk[1] + 1))
+        chunks.append("".join(ev[i:i + k]).encode("utf-8"))
+        i += k
+    return chunks
+
+
+def openai_batch(n_streams: int = 1024, n_deltas: int = 256, seed: int = 9, events_per_chunk=(1, 1)) -> PackedBatch:
+    rng = np.random.default_rng([seed, n_streams, n_deltas])
+    truths = _usage_truths(n_streams, seed)
+    streams = [openai_stream(rng, n_deltas, truths[s], "chatcmpl-%08x" % int(rng.integers(0, 2**32)), events_per_chunk) for s in range(n_streams)]
+    b = pack_streams(streams)
+    b.truths = truths
+    return b

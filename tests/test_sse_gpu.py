@@ -356,3 +356,30 @@ def test_template_shortcut_is_exact(engine, n_steps):
             assert (not (a.flags & _abi.SF_A_USAGE_BOUND)) == relay.end_raises
             n_rows += 1
     assert n_rows > 900
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("events_per_chunk", [(1, 1), (1, 4)])
+def test_openai_shaped_streams_vs_oracle(engine, mode, events_per_chunk):
+    """Realistic OpenAI chunks (id / created / model on every event, role and finish chunks, content pieces of varying length
+    with escapes and raw UTF-8, usage chunk, [DONE]): multi-span templates, bytes / usage rows / counters against the oracle"""
+    from llmapigateway_b200.synth import openai_batch
+    from oracle.sse_oracle import run_stream
+    engine.set_mode(mode)
+    try:
+        b = openai_batch(n_streams=48, n_deltas=40, seed=17, events_per_chunk=events_per_chunk)
+        engine.open(b.seg_slot)
+        res = engine.step(b.data, b.chunk_off, b.seg_chunk, b.seg_slot)
+        states = engine.close(b.seg_slot)
+        assert np.array_equal(res.out, b.data)
+        assert (res.segs["emit_chunk_begin"] == b.seg_chunk[:-1]).all()
+        for s in range(48):
+            relay, tap = run_stream(b.stream_chunks(s))
+            assert not relay.failed
+            st = states[s]
+            assert st.phase == _abi.PHASE_COMMITTED
+            assert canon_rows([_abi.usage_rec_to_dict(st.rec)]) == canon_rows(tap.rows)
+            assert tap.rows[-1] == b.truths[s].expected_row()
+            assert st.n_chunks_emitted == len(relay.emitted) and st.bytes_emitted == sum(map(len, relay.emitted))
+    finally:
+        engine.set_mode(0)
