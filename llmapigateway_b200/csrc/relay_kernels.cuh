@@ -596,8 +596,11 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                 uint32_t cls = PC_NONE, f = 0, pos = 0;
                 bool ended = false;
                 uint32_t hit = 2;
-                if (have_tpl0 && match_template(env, 0, ps, &pos)) hit = 0;
-                else if (have_tpl1 && match_template(env, 1, ps, &pos)) hit = 1;
+#pragma unroll 1
+                for (uint32_t sl = 0; sl < LGW_TPL_SLOTS && hit == 2u; ++sl) {   // (one copy of the matcher in the loop: fewer registers, faster)
+                    if (!(sl ? have_tpl1 : have_tpl0)) continue;
+                    if (match_template(env, sl, ps, &pos)) hit = sl;
+                }
                 if (hit < 2) {
                     if (pos + 1 >= e) break;                         // the separator completes in a later chunk
                     ended = true; cls = sh_tpl_cls[hit]; f = sh_tpl_flags[hit];
