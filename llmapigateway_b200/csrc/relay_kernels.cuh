@@ -208,6 +208,134 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
     return true;
 }
 
+// ---- window matcher ------------------------------------------------------------------------------------
+// The same judgement as match_template for an event that lies inside the staged window [t0, t0 + LGW_STAGE_BYTES):
+// positions are offsets into the window, every load is a plain shared-memory load (no "is it staged?" test and no
+// out-of-line global fallback in front of each word).  Returns 1 match, 0 no match, 2 "left the window" (the caller then
+// asks match_template, which reads anywhere).
+#ifndef LGW_WINDOW_MATCH
+#define LGW_WINDOW_MATCH 1
+#endif
+// first byte of w that is not an ASCII digit: index 0..3, or 4 when all four are digits
+__device__ __forceinline__ uint32_t first_nondigit(uint32_t w) {
+    const uint32_t t = w ^ 0x30303030u;                                         // digits become 0x00..0x09
+    const uint32_t m = (((t & 0x7f7f7f7fu) + 0x76767676u) | t) & 0x80808080u;   // byte flagged <=> t >= 0x0a (no carries between bytes)
+    return m ? (uint32_t)(__ffs(m) - 1) >> 3 : 4u;
+}
+__device__ __forceinline__ uint32_t match_window(const TileEnv& env, uint32_t slot, uint32_t ps, uint32_t* end) {
+    const uint32_t lenA = sh_tpl_len[slot];
+    const uint32_t tb = env.tpl_s + slot * LGW_TPL_STRIDE, sb = env.strid_s + slot * LGW_TPL_MAPSTRIDE;
+    const uint32_t ts = env.tile_s;
+#define LGW_WW(d4) lds_u32(ts + phys(d4))
+    uint32_t ia = 0, db = ps - env.t0;                 // db: offset of the event's current byte in the window
+    if (db >= LGW_STAGE_BYTES - 16u) return 2;
+    bool fresh = false;
+    for (;;) {
+        if (ia < lenA) {
+            uint32_t left = lenA - ia, x = 0;
+            if (db + left + 12u > LGW_STAGE_BYTES) return 2;
+            const uint32_t shB = 8 * (db & 3u), shA = 8 * (ia & 3u);
+            uint32_t qb = db & ~3u, pa = tb + (ia & ~3u);
+            uint32_t loB = LGW_WW(qb), loA = lds_u32(pa);
+            const uint32_t left0 = left;
+            while (left > 4) {
+                const uint32_t hiB = LGW_WW(qb + 4), hiA = lds_u32(pa + 4);
+                x = __funnelshift_r(loB, hiB, shB) ^ __funnelshift_r(loA, hiA, shA);
+                if (x) break;
+                qb += 4; pa += 4; loB = hiB; loA = hiA; left -= 4;
+            }
+            if (!x) {
+                const uint32_t hiB = LGW_WW(qb + 4), hiA = lds_u32(pa + 4);
+                x = __funnelshift_r(loB, hiB, shB) ^ __funnelshift_r(loA, hiA, shA);
+                if (left < 4) x &= (1u << (8 * left)) - 1u;
+            }
+            uint32_t adv = left0 - left;
+            adv += x ? ((uint32_t)(__ffs(x) - 1) >> 3) : left;
+            if (adv == 0 && fresh) return 0;
+            ia += adv; db += adv;
+            fresh = false;
+        }
+        if (ia >= lenA) break;
+        const uint32_t id = lds_u8(sb + ia);
+        if (id == 0xffu) return 0;
+        if (sh_tpl_skind[slot][id] == 0) {   // string value
+            for (;;) {
+                uint32_t q = db & ~3u;
+                const uint32_t sh = 8 * (db & 3u);
+                if (q + 12u > LGW_STAGE_BYTES) return 2;
+                uint32_t lo = LGW_WW(q), hi = LGW_WW(q + 4), w4, k;
+                for (;;) {
+                    w4 = __funnelshift_r(lo, hi, sh);
+                    k = first_special(w4);
+                    if (k != 4) break;
+                    q += 4;
+                    if (q + 12u > LGW_STAGE_BYTES) return 2;
+                    lo = hi; hi = LGW_WW(q + 4);
+                }
+                db = q + (sh >> 3) + k;
+                const uint32_t sp = (w4 >> (8 * k)) & 0xffu;
+                if (sp == '"') break;
+                if (sp != '\\') return 0;
+                const uint32_t adv = escape_length(env, env.t0 + db);
+                if (adv == 0) return 0;
+                db += adv;
+            }
+        } else {                             // number value: re-validate the event's own number
+            const uint32_t bs = db - (ia - sh_tpl_sstart[slot][id]);
+            uint32_t q = bs & ~3u;
+            const uint32_t sh = 8 * (bs & 3u);
+            if (q + 12u > LGW_STAGE_BYTES) return 2;
+            uint32_t lo = LGW_WW(q), hi = LGW_WW(q + 4);
+            uint32_t w4 = __funnelshift_r(lo, hi, sh);
+            const uint32_t c0 = w4 & 0xffu;
+            uint32_t pe = bs;                                     // first byte after the number
+            bool plain = false;                                   // common case: "0" or [1-9][0-9]*, four digits per step
+            if (c0 == '0') { pe = bs + 1; plain = true; }
+            else if (c0 - '1' < 9u) {
+                for (;;) {
+                    const uint32_t k = first_nondigit(w4);
+                    pe += k;
+                    if (k != 4) break;
+                    q += 4;
+                    if (q + 12u > LGW_STAGE_BYTES) return 2;
+                    lo = hi; hi = LGW_WW(q + 4);
+                    w4 = __funnelshift_r(lo, hi, sh);
+                }
+                plain = true;
+            }
+            if (plain) {
+                const uint32_t c = (LGW_WW(pe & ~3u) >> (8 * (pe & 3u))) & 0xffu;
+                if (c == '.' || c == 'e' || c == 'E') plain = false;
+            }
+            if (!plain) {                                         // sign, fraction, exponent: the recogniser's number rows
+                uint32_t st = L_VALUE;
+                pe = bs;
+                for (;;) {
+                    if (pe + 12u > LGW_STAGE_BYTES) return 2;
+                    const uint32_t cl = env.cls((LGW_WW(pe & ~3u) >> (8 * (pe & 3u))) & 0xffu);
+                    if (cl < C_MINUS || cl > C_EXP) break;
+                    st = env.trans(st * 32 + cl) & 31u;
+                    if (st == L_ERR) return 0;
+                    ++pe;
+                }
+                if (!(st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP)) return 0;
+            }
+            db = pe;
+        }
+        ia = sh_tpl_send[slot][id];
+        fresh = true;
+    }
+    {   // LF LF must follow
+        const uint32_t q = db & ~3u;
+        if (q + 12u > LGW_STAGE_BYTES) return 2;
+        if ((__funnelshift_r(LGW_WW(q), LGW_WW(q + 4), 8 * (db & 3u)) & 0xffffu) != 0x0a0au) return 0;
+    }
+#undef LGW_WW
+    *end = env.t0 + db;
+    return 1;
+}
+__device__ __noinline__ bool match_template_far(const TileEnv& env, uint32_t slot, uint32_t ps, uint32_t* end) { return match_template(env, slot, ps, end); }
+
 // reader over the block-staged copy [base, base + LGW_TPL_STRIDE)
 struct StageEnv {
     uint32_t base, cls_s, trans_s;
@@ -463,6 +591,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
             }
             seg_hint = lo;                      // (the thread looking for the first chunk's segment lags the other by one tile: still a lower bound)
             if (tid == LGW_RELAY_THREADS - 32) sh_seg_lo = lo; else sh_seg_hi = lo;
+            prefetch_l1(a.s.plan + (lo < a.n_segs ? lo : 0u));      // the walk starts from these plans: have them in L1 by the time the tile is staged
         }
         if (tid == 0) sh_tpl_cand = 0xFFFFFFFFu;
 
@@ -599,7 +728,13 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
 #pragma unroll 1
                 for (uint32_t sl = 0; sl < LGW_TPL_SLOTS && hit == 2u; ++sl) {   // (one copy of the matcher in the loop: fewer registers, faster)
                     if (!(sl ? have_tpl1 : have_tpl0)) continue;
+#if LGW_WINDOW_MATCH
+                    uint32_t r = match_window(env, sl, ps, &pos);
+                    if (r == 2u) r = match_template_far(env, sl, ps, &pos) ? 1u : 0u;
+                    if (r) hit = sl;
+#else
                     if (match_template(env, sl, ps, &pos)) hit = sl;
+#endif
                 }
                 if (hit < 2) {
                     if (pos + 1 >= e) break;                         // the separator completes in a later chunk
