@@ -40,6 +40,8 @@ __shared__ __align__(16) uint8_t sh_tile[LGW_TILE_PHYS_BYTES];
 __shared__ __align__(4) uint8_t sh_cls[256];
 __shared__ __align__(4) uint8_t sh_trans[LGW_LEAN_ROWS * 32];
 __shared__ uint32_t sh_seg_lo, sh_seg_hi;
+#define LGW_TC_STAGED 16u
+__shared__ uint32_t sh_tile_chunk[LGW_TC_STAGED];
 #ifdef LGW_DEBUG_TIMING
 __device__ unsigned long long g_dbg[16];
 #define DBG_STAMP(i) do { if (blockIdx.x == 7 && threadIdx.x == 0 && tile == tile_first + 3) g_dbg[i] = clock64(); } while (0)
@@ -69,6 +71,14 @@ __shared__ __align__(16) uint8_t sh_stage[LGW_TPL_STRIDE + 16];
 // rebuilds the CTA's shared-window base -- S2UR SR_CgaCtaId + ULEA -- in front of every access)
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// 16-byte read-only load that does not allocate in L1: the tile is staged in shared memory anyway, and with 225 KB of
+// shared memory per SM the L1 that is left is a few KB -- it should keep the chunk offsets and segment plans that were
+// prefetched for the walk, not the bytes streaming through
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
@@ -107,6 +117,33 @@ struct TileEnv {
     }
 };
 
+// the same reader over global memory only (k_relay_long: chunks that were left out of the tile walk)
+struct GlobalEnv {
+    uint32_t cls_s, trans_s, tpl_s, strid_s;
+    const uint8_t* __restrict__ g;
+    uint32_t n_bytes;
+    __device__ __forceinline__ uint32_t word(uint32_t pos) const {
+        const uint32_t p4 = pos & ~3u;
+        if (p4 + 4 <= n_bytes) return __ldg(reinterpret_cast<const uint32_t*>(g + p4));
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < 4 && p4 + k < n_bytes; ++k) w |= (uint32_t)__ldg(g + p4 + k) << (8 * k);
+        return w;
+    }
+    __device__ __forceinline__ uint32_t wordu(uint32_t pos) const {
+        const uint32_t lo = word(pos);
+        if ((pos & 3u) == 0) return lo;
+        return __funnelshift_r(lo, word(pos + 4), 8 * (pos & 3u));
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (word(pos) >> (8 * (pos & 3u))) & 0xffu; }
+    __device__ __forceinline__ uint32_t cls(uint32_t c) const { return lds_u8(cls_s + c); }
+    __device__ __forceinline__ uint32_t trans(uint32_t i) const { return lds_u8(trans_s + i); }
+    __device__ __forceinline__ uint32_t tplu(uint32_t tb, uint32_t k) const {
+        const uint32_t lo = lds_u32(tb + (k & ~3u));
+        if ((k & 3u) == 0) return lo;
+        return __funnelshift_r(lo, lds_u32(tb + (k & ~3u) + 4), 8 * (k & 3u));
+    }
+};
+
 // first byte of w (little endian) that is '"', '\\' or < 0x20: index 0..3, or 4 when none
 __device__ __forceinline__ uint32_t first_special(uint32_t w) {
     const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5c5c5c5cu, c = w & 0xe0e0e0e0u;
@@ -116,7 +153,8 @@ __device__ __forceinline__ uint32_t first_special(uint32_t w) {
 
 // length of the valid escape sequence whose backslash sits at `ib` (2, or 6 for \\uXXXX), 0 when the recogniser would
 // reject it (lean_json.cuh L_STR_ESC / L_STR_U)
-__device__ __noinline__ uint32_t escape_length(const TileEnv& env, uint32_t ib) {
+template <class ENV>
+__device__ __noinline__ uint32_t escape_length(const ENV& env, uint32_t ib) {
     const uint32_t w = env.wordu(ib + 1);
     const uint32_t c = w & 0xffu;
     if (c == 'u') {
@@ -133,7 +171,8 @@ __device__ __noinline__ uint32_t escape_length(const TileEnv& env, uint32_t ib) 
 // with the number rows of the recogniser's table).  Everything else must be byte-identical, so the
 // recogniser would walk the same states: same validity, same top-level keys.
 // On success *end = position of the first LF of the event's LF LF separator (verified to be there).
-__device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot, uint32_t ps, uint32_t* end) {
+template <class ENV>
+__device__ __forceinline__ bool match_template(const ENV& env, uint32_t slot, uint32_t ps, uint32_t* end) {
     const uint32_t lenA = sh_tpl_len[slot];
     const uint32_t tb = env.tpl_s + slot * LGW_TPL_STRIDE, sb = env.strid_s + slot * LGW_TPL_MAPSTRIDE;
     uint32_t ia = 0, ib = ps;
@@ -216,6 +255,16 @@ __device__ __forceinline__ bool match_template(const TileEnv& env, uint32_t slot
 #ifndef LGW_WINDOW_MATCH
 #define LGW_WINDOW_MATCH 1
 #endif
+#ifndef LGW_EQ_UNROLL
+#define LGW_EQ_UNROLL 1
+#endif
+// Experimental (off): chunks much longer than their neighbours (the 300-byte usage chunk among 64-byte deltas) are queued by
+// k_relay and walked by k_relay_long, one warp per chunk, instead of by one lane whose warp and block wait for it.
+// Measured on B200: k_relay 146 -> 120 us, but k_relay_long costs 32 us (thread per chunk: 43 us), so the
+// step is slower for now.  Parity is the same either way (tests/test_sse_gpu.py passes with -DLGW_DEFER_LONG=1).
+#ifndef LGW_DEFER_LONG
+#define LGW_DEFER_LONG 0
+#endif
 // first byte of w that is not an ASCII digit: index 0..3, or 4 when all four are digits
 __device__ __forceinline__ uint32_t first_nondigit(uint32_t w) {
     const uint32_t t = w ^ 0x30303030u;                                         // digits become 0x00..0x09
@@ -238,7 +287,21 @@ __device__ __forceinline__ uint32_t match_window(const TileEnv& env, uint32_t sl
             uint32_t qb = db & ~3u, pa = tb + (ia & ~3u);
             uint32_t loB = LGW_WW(qb), loA = lds_u32(pa);
             const uint32_t left0 = left;
+#if LGW_EQ_UNROLL
+            while (left > 8) {                          // two words per round: four independent loads, one branch
+                const uint32_t m1B = LGW_WW(qb + 4), m2B = LGW_WW(qb + 8), m1A = lds_u32(pa + 4), m2A = lds_u32(pa + 8);
+                const uint32_t x1 = __funnelshift_r(loB, m1B, shB) ^ __funnelshift_r(loA, m1A, shA);
+                const uint32_t x2 = __funnelshift_r(m1B, m2B, shB) ^ __funnelshift_r(m1A, m2A, shA);
+                if (x1 | x2) {
+                    if (x1) x = x1; else { x = x2; qb += 4; pa += 4; left -= 4; loB = m1B; loA = m1A; }
+                    break;
+                }
+                qb += 8; pa += 8; left -= 8; loB = m2B; loA = m2A;
+            }
+            while (!x && left > 4) {
+#else
             while (left > 4) {
+#endif
                 const uint32_t hiB = LGW_WW(qb + 4), hiA = lds_u32(pa + 4);
                 x = __funnelshift_r(loB, hiB, shB) ^ __funnelshift_r(loA, hiA, shA);
                 if (x) break;
@@ -415,7 +478,8 @@ __device__ __noinline__ bool publish_template(TemplateCache* tc, uint32_t slot, 
 }
 
 // rare path: chunk-level UTF-8 validation (request_handler.py:111 decodes each chunk on its own)
-__device__ __noinline__ bool chunk_utf8_ok(const TileEnv* rd, uint32_t o, uint32_t e) {
+template <class ENV>
+__device__ __noinline__ bool chunk_utf8_ok(const ENV* rd, uint32_t o, uint32_t e) {
     uint32_t p = o;
     while (p < e) {
         const uint32_t ch = rd->at(p);
@@ -441,7 +505,8 @@ __device__ __noinline__ bool chunk_utf8_ok(const TileEnv* rd, uint32_t o, uint32
 
 // rare path: where does the event that is open at byte o begin?  (o is not right after a separator)
 // returns false when the stream must go to the sequential path
-__device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o, uint32_t relay_begin, uint32_t seg_end, uint32_t carry_cap, uint32_t* out_b) {
+template <class ENV>
+__device__ __noinline__ bool find_open_event_start(const ENV* rd, uint32_t o, uint32_t relay_begin, uint32_t seg_end, uint32_t carry_cap, uint32_t* out_b) {
     uint32_t k = o;
     bool found = false;
     const uint32_t limit = (o - relay_begin > carry_cap + 2) ? o - carry_cap - 2 : relay_begin;
@@ -463,6 +528,242 @@ __device__ __noinline__ bool find_open_event_start(const TileEnv* rd, uint32_t o
     return true;
 }
 
+#if LGW_DEFER_LONG
+// ---- warp matcher (k_relay_long) -------------------------------------------------------------------------
+// The judgement of match_template made by a whole warp for ONE event: every lane holds the same arguments, lane l
+// compares the l-th word of the current 128 bytes, a ballot finds the first difference / the first special byte of a
+// string value.  Number values are short and are re-validated by every lane alike.
+template <class ENV>
+__device__ __forceinline__ bool match_template_warp(const ENV& env, uint32_t slot, uint32_t ps, uint32_t* end) {
+    const uint32_t full = 0xFFFFFFFFu, lane = threadIdx.x & 31u;
+    const uint32_t lenA = sh_tpl_len[slot];
+    const uint32_t tb = env.tpl_s + slot * LGW_TPL_STRIDE, sb = env.strid_s + slot * LGW_TPL_MAPSTRIDE;
+    uint32_t ia = 0, ib = ps;
+    bool fresh = false;
+    for (;;) {
+        if (ia < lenA) {
+            uint32_t run = 0;
+            for (;;) {                                   // equal run, 128 bytes per round
+                const uint32_t left = lenA - ia, k = 4 * lane;
+                uint32_t x = 0;
+                if (k < left) {
+                    x = env.tplu(tb, ia + k) ^ env.wordu(ib + k);
+                    if (left - k < 4) x &= (1u << (8 * (left - k))) - 1u;
+                }
+                const uint32_t m = __ballot_sync(full, x != 0);
+                if (m == 0) {
+                    const uint32_t adv = left < 128u ? left : 128u;
+                    ia += adv; ib += adv; run += adv;
+                    if (ia >= lenA) break;
+                    continue;
+                }
+                const uint32_t j = (uint32_t)__ffs(m) - 1u;
+                const uint32_t xj = __shfl_sync(full, x, j);
+                const uint32_t adv = 4 * j + ((uint32_t)(__ffs(xj) - 1) >> 3);
+                ia += adv; ib += adv; run += adv;
+                break;
+            }
+            if (run == 0 && fresh) return false;
+            fresh = false;
+        }
+        if (ia >= lenA) break;
+        const uint32_t id = lds_u8(sb + ia);
+        if (id == 0xffu) return false;
+        if (sh_tpl_skind[slot][id] == 0) {   // string value: plain bytes and valid escapes up to the closing quote
+            for (;;) {
+                const uint32_t w4 = env.wordu(ib + 4 * lane);
+                const uint32_t k = first_special(w4);
+                const uint32_t m = __ballot_sync(full, k != 4u);
+                if (m == 0) { ib += 128u; if (ib - ps > 8192u) return false; continue; }
+                const uint32_t j = (uint32_t)__ffs(m) - 1u;
+                const uint32_t kj = __shfl_sync(full, k, j), wj = __shfl_sync(full, w4, j);
+                ib += 4 * j + kj;
+                const uint32_t sp = (wj >> (8 * kj)) & 0xffu;
+                if (sp == '"') break;
+                if (sp != '\\') return false;
+                const uint32_t adv = escape_length(env, ib);
+                if (adv == 0) return false;
+                ib += adv;
+            }
+        } else {                             // number value: re-validate the event's own number
+            uint32_t bs = ib - (ia - sh_tpl_sstart[slot][id]);
+            uint32_t st = L_VALUE;
+            {   // common case first: a plain run of digits ("0" or [1-9][0-9]*)
+                uint32_t q = bs, c = env.at(q);
+                if (c - '1' < 9u) { do { c = env.at(++q); } while (c - '0' < 10u); }
+                else if (c == '0') c = env.at(++q);
+                else q = bs;
+                if (q != bs && c != '.' && c != 'e' && c != 'E') { ib = q; ia = sh_tpl_send[slot][id]; fresh = true; continue; }
+            }
+            for (;;) {
+                const uint32_t cl = env.cls(env.at(bs));
+                if (cl < C_MINUS || cl > C_EXP) break;
+                st = env.trans(st * 32 + cl) & 31u;
+                if (st == L_ERR || bs - ps > 8192u) return false;
+                ++bs;
+            }
+            if (!(st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP)) return false;
+            ib = bs;
+        }
+        ia = sh_tpl_send[slot][id];
+        fresh = true;
+    }
+    if ((env.wordu(ib) & 0xffffu) != 0x0a0au) return false;     // LF LF must follow
+    *end = ib;
+    return true;
+}
+
+#endif  // LGW_DEFER_LONG
+
+// ---- one chunk: the events that complete in it ---------------------------------------------------------
+// BULK: called by k_relay for a chunk that starts in the staged tile (ENV = TileEnv).  Otherwise: k_relay_long, reading
+// global memory (ENV = GlobalEnv).  Findings are posted with atomics, so which kernel walked a chunk does not matter.
+template <class ENV, bool BULK>
+__device__ __forceinline__ void walk_chunk(const StepArgs& a, const ENV& env, const uint32_t c, const uint32_t seg_lo, const uint32_t seg_hi,
+                                           const int tile_high, const uint32_t utf8_from, const bool have_tpl0, const bool have_tpl1,
+                                           uint32_t& acc_seg, uint32_t& ev_a, uint32_t& ev_b, const uint32_t defer_min, const bool lead) {
+    const uint32_t n_bytes = a.n_bytes;      // (!BULK: a whole warp walks the chunk, every lane alike; `lead` posts the sums)
+    uint32_t seg = seg_lo;
+    if (seg_lo != seg_hi) {                                // segment of chunk c: last seg with seg_chunk[seg] <= c
+        uint32_t lo = seg_lo, hi = seg_hi;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
+        seg = lo;
+    }
+    SegPlan* pl = a.s.plan + seg;
+    const uint32_t seg_end = pl->seg_end, kept_chunk = pl->kept_chunk;
+    const bool is_kept = c == kept_chunk;
+    // text visible to both loops starts after the kept chunk; the kept chunk itself is tap-only
+    const uint32_t relay_begin = (kept_chunk != 0xFFFFFFFFu && !is_kept) ? pl->kept_end : pl->relay_begin;
+    const uint32_t o = __ldg(a.chunk_off + c), e = __ldg(a.chunk_off + c + 1);
+    if (o < relay_begin || pl->irregular) return;
+    if (e == o) { pl->irregular = 1; return; }
+    if (BULK && e - o > defer_min) {                       // a chunk much longer than its neighbours: one lane would walk it while its warp and,
+        const uint32_t qi = atomicAdd(a.s.long_count, 1u);   // at the next barrier, its block wait -> k_relay_long takes it, thread per long chunk
+        if (qi < a.s.long_cap) { a.s.long_q[2 * qi] = c; a.s.long_q[2 * qi + 1] = seg; return; }
+    }
+    if (seg != acc_seg) {
+        if (acc_seg != 0xFFFFFFFFu) { if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a); if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b); }
+        acc_seg = seg; ev_a = ev_b = 0;
+    }
+
+    // chunk-level UTF-8: ASCII tiles need no check; the part of a chunk beyond the tile is
+    // scanned for bytes >= 0x80 with 16-byte loads first
+    bool need_utf8 = tile_high != 0;
+    const uint32_t scan_from = BULK ? utf8_from : (o & ~15u);     // (bytes of a neighbouring chunk in the first or last vector can only cause a spurious check)
+    if (!need_utf8 && e > scan_from) {
+        uint32_t hi_bits = 0;
+        for (uint32_t v = scan_from >> 4; (v << 4) < e; ++v) {
+            if ((v << 4) + 16 <= n_bytes) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(a.data) + v); hi_bits |= x.x | x.y | x.z | x.w; }
+            else hi_bits = 0x80;                      // ragged end: take the exact path
+        }
+        need_utf8 = (hi_bits & 0x80808080u) != 0;     // bytes after e in the last vector can only cause a spurious check
+    }
+    if (need_utf8 && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; return; }
+
+    // where does the event that is open at the start of this chunk begin?
+    uint32_t b = o;
+    if (o != relay_begin) {
+        const bool sep_before = o >= relay_begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au;
+        if (sep_before) {
+            if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; return; }   // LF run >= 3
+        } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; return; }
+    }
+
+    // walk the events that complete inside this chunk (second LF of the separator in [o, e))
+    bool irregular = false, primed = false;
+    uint32_t us_b = 0, a_usage = 0; unsigned long long last_usage = 0;
+    uint32_t ps = b;
+    while (ps < e) {
+        uint32_t cls = PC_NONE, f = 0, pos = 0;
+        bool ended = false;
+        uint32_t hit = 2;
+#pragma unroll 1
+        for (uint32_t sl = 0; sl < LGW_TPL_SLOTS && hit == 2u; ++sl) {   // (one copy of the matcher in the loop: fewer registers, faster)
+            if (!(sl ? have_tpl1 : have_tpl0)) continue;
+#if LGW_WINDOW_MATCH
+            if constexpr (BULK) {
+                uint32_t r = match_window(env, sl, ps, &pos);
+                if (r == 2u) r = match_template_far(env, sl, ps, &pos) ? 1u : 0u;
+                if (r) hit = sl;
+            } else
+#endif
+#if LGW_DEFER_LONG
+            if (match_template_warp(env, sl, ps, &pos)) hit = sl;
+#else
+            if (match_template(env, sl, ps, &pos)) hit = sl;
+#endif
+        }
+        if (hit < 2) {
+            if (pos + 1 >= e) break;                         // the separator completes in a later chunk
+            ended = true; cls = sh_tpl_cls[hit]; f = sh_tpl_flags[hit];
+        } else {
+            // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
+            const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
+            if ((w0 & 0xffu) == '{') cls = PC_BRACE;
+            else if ((w0 & 0xffu) == 'd') {
+                if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
+                else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
+            }
+            // nominate the event for the second template (any valid event is a sound template, wherever it came from)
+            if (BULK && cls != PC_NONE && have_tpl0) {
+                if (!have_tpl1 && sh_tpl_tries1 < 3) atomicMin(&sh_tpl_cand1, ((unsigned long long)ps << 32) | seg_end);
+                else if (have_tpl1) atomicAdd(&sh_tpl_miss, 1u);
+            }
+            LeanMachine lm;
+            lm.reset(cls == PC_DATA);
+            pos = ps + (cls == PC_DATA ? 6u : 0u);          // "data: " holds no LF
+            while (pos < e && !ended) {                      // word-wise byte loop
+                uint32_t w = env.word(pos) >> (8 * (pos & 3u));
+                uint32_t nb = 4 - (pos & 3u);
+                if (nb > e - pos) nb = e - pos;
+#pragma unroll 1
+                for (; nb; --nb, w >>= 8, ++pos) {
+                    const uint32_t ch = w & 0xffu;
+                    // hot path: a plain byte inside a string changes nothing
+                    if (lm.st == L_STR && ch >= 0x20u && ch != '"' && ch != '\\') continue;
+                    if (ch == '\n') {
+                        if (pos + 1 >= e) { pos = e; break; }     // a separator starting on the last byte completes later
+                        if (env.at(pos + 1) == '\n') { ended = true; break; }
+                    }
+                    if (cls != PC_NONE) lm.step(ch, pos, env);
+                }
+            }
+            if (!ended) break;                               // the open event completes in a later chunk
+            f = lm.finish();
+        }
+        // ---- one complete event [ps, pos) ----
+        if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
+        if (cls != PC_NONE) {
+            if (cls == PC_DATA) {
+                if (is_kept) {                               // priming loop on the kept chunk, request_handler.py:82-91
+                    if (!primed) {
+                        if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) { irregular = true; break; }   // attempt fails: exact path
+                        primed = true;
+                    }
+                } else {                                     // handler loop, request_handler.py:122-134
+                    ++ev_a;
+                    if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
+                }
+            }
+            if (f & PF_VALID_B) {                            // tap loop, chat_logging.py:123-141
+                ++ev_b;
+                // events with "error" (extra DB row) go to the sequential path; a "usage" event is
+                // a candidate whose values k_commit stashes for extraction on demand
+                if (f & TK_ERROR) { irregular = true; break; }
+                if (f & TK_USAGE) { ++us_b; last_usage = ((unsigned long long)(ps + 1) << 32) | (pos - ps); }
+            }
+        }
+        ps = pos + 2;
+    }
+    if (is_kept && !irregular) {
+        // the speculation holds when a real event was accepted and the chunk ends on a separator
+        if (primed && ps == e) pl->prime_ok = 1; else irregular = true;
+    }
+    if (irregular) { pl->irregular = 1; return; }
+    if (us_b && lead) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage, last_usage); }
+    if (a_usage) pl->a_usage = 1;
+}
+
 // ---- k_prime ---------------------------------------------------------------------------------------
 // thread i: (a) tile table entry i = first chunk that starts at or after byte i*TILE;
 //           (b) segment i: the plan the bulk kernel works to.  Fresh streams are SPECULATED to commit on
@@ -471,12 +772,15 @@ __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // tile table: tile_chunk[t] = first c in [chunk_lo, chunk_hi] with chunk_off[c] >= start of tile t.  One thread per
     // chunk writes the tiles whose start falls in (chunk_off[c-1], chunk_off[c]] -- one coalesced pass over the offsets
-    // instead of a binary search of ~20 dependent loads per tile.
-    if (i <= a.chunk_hi - a.chunk_lo) {
-        const uint32_t c = a.chunk_lo + i;
+    // instead of a binary search of ~20 dependent loads per tile.  Grid-stride: a block per 128 chunks would be 16 k
+    // blocks of a few instructions each, and the block scheduler then sets the pace (15 us for 2 M chunks).
+    if (i == 0) *a.s.long_count = 0;                       // queue of the chunks k_relay leaves to k_relay_long
+    const uint32_t n_off = a.chunk_hi - a.chunk_lo + 1;
+    for (uint32_t j = i; j < n_off; j += gridDim.x * blockDim.x) {
+        const uint32_t c = a.chunk_lo + j;
         const uint32_t off = __ldg(a.chunk_off + c);
         uint32_t t_first = 0;
-        if (i > 0) { const uint32_t prev = __ldg(a.chunk_off + c - 1); t_first = prev < a.tile_base ? 0u : (prev - a.tile_base) / LGW_TILE_BYTES + 1u; }
+        if (j > 0) { const uint32_t prev = __ldg(a.chunk_off + c - 1); t_first = prev < a.tile_base ? 0u : (prev - a.tile_base) / LGW_TILE_BYTES + 1u; }
         uint32_t t_last = off < a.tile_base ? 0u : (off - a.tile_base) / LGW_TILE_BYTES;      // off >= tile_base always holds for c >= chunk_lo
         if (off < a.tile_base) t_first = 1;                                                  // (defensive: nothing to write)
         if (c == a.chunk_hi) t_last = n_tiles;                                               // tiles past the last offset
@@ -505,11 +809,8 @@ __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     a.s.plan[seg] = p;
 }
 
-// ---- k_relay ---------------------------------------------------------------------------------------
-// Persistent blocks: block b handles tiles [b*tiles_per_block, ...) so that its template carries over.
-__global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_relay(StepArgs a, uint32_t n_tiles, uint32_t tiles_per_block) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n_bytes = a.n_bytes;
+// tables of the recogniser and the engine-wide event templates into shared memory (k_relay, k_relay_long)
+__device__ __forceinline__ void relay_prologue(const StepArgs& a, const uint32_t tid) {
     for (uint32_t k = tid; k < 64 + LGW_LEAN_ROWS * 8; k += LGW_RELAY_THREADS) {
         if (k < 64) reinterpret_cast<uint32_t*>(sh_cls)[k] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.cls)[k];
         else reinterpret_cast<uint32_t*>(sh_trans)[k - 64] = reinterpret_cast<const uint32_t*>(g_lean_tables_dev.trans)[k - 64];
@@ -529,6 +830,18 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
             if (tid == 0) { sh_tpl_len[slot] = tc->len[slot]; sh_tpl_flags[slot] = tc->flags[slot]; sh_tpl_cls[slot] = tc->cls[slot]; sh_tpl_valid[slot] = 1; if (slot == 0) sh_tpl0_canon = 1; }
         }
     }
+}
+
+// ---- k_relay ---------------------------------------------------------------------------------------
+// Persistent blocks: block b handles tiles [b*tiles_per_block, ...) so that its template carries over.
+__global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_relay(StepArgs a, uint32_t n_tiles, uint32_t tiles_per_block) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_bytes = a.n_bytes;
+    // this block's slice of the tile table (tiles_per_block + 1 entries) once, instead of two L2 round trips at the top of every tile
+    const uint32_t tile_first = blockIdx.x * tiles_per_block;
+    const uint32_t tile_last = min(n_tiles, tile_first + tiles_per_block);
+    if (tid < LGW_TC_STAGED && tile_first + tid <= tile_last) sh_tile_chunk[tid] = a.s.tile_chunk[tile_first + tid];
+    relay_prologue(a, tid);
 
     TileEnv env;
     env.tile_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tile));
@@ -538,8 +851,6 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
     env.strid_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tpl_strid));
     env.g = a.data; env.n_bytes = n_bytes;
 
-    const uint32_t tile_first = blockIdx.x * tiles_per_block;
-    const uint32_t tile_last = min(n_tiles, tile_first + tiles_per_block);
     uint32_t seg_hint = 0;                     // lower bound of the segment index of this thread's next search
     if (tid >= LGW_RELAY_THREADS - 32 && tid < LGW_RELAY_THREADS - 30 && tile_first < tile_last) {      // first tile: one binary search
         const uint32_t c = a.s.tile_chunk[tile_first];
@@ -550,7 +861,9 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
     for (uint32_t tile = tile_first; tile < tile_last; ++tile) {
         const uint32_t t0 = a.tile_base + tile * LGW_TILE_BYTES;
         env.t0 = t0;
-        const uint32_t c_lo = a.s.tile_chunk[tile], c_hi = a.s.tile_chunk[tile + 1];
+        const uint32_t ti = tile - tile_first;
+        const uint32_t c_lo = ti < LGW_TC_STAGED ? sh_tile_chunk[ti] : a.s.tile_chunk[tile];
+        const uint32_t c_hi = ti + 1 < LGW_TC_STAGED ? sh_tile_chunk[ti + 1] : a.s.tile_chunk[tile + 1];
         // the walk of a chunk starts with dependent global loads (its offsets, its segment's plan): pull those lines
         // into L1 now, while the tile is being staged
         for (uint32_t c = c_lo + tid; c <= c_hi; c += LGW_RELAY_THREADS) prefetch_l1(a.chunk_off + c);
@@ -605,7 +918,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
 #pragma unroll
             for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
                 const uint32_t v = k * LGW_RELAY_THREADS + tid;
-                x[k] = (t0 + v * 16 + 16 <= n_bytes) ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
+                x[k] = (t0 + v * 16 + 16 <= n_bytes) ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
@@ -631,7 +944,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                 const uint32_t v = LGW_TILE_VECS + tid;
                 const uint32_t pos = t0 + v * 16;
                 uint4 h = make_uint4(0, 0, 0, 0);
-                if (pos + 16 <= n_bytes) h = __ldg(src + v);
+                if (pos + 16 <= n_bytes) h = ldg_stream(src + v);
                 else if (pos < n_bytes) {
                     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
                     for (uint32_t b = pos; b < n_bytes; ++b) {
@@ -641,6 +954,7 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
                     }
                     h = make_uint4(w0, w1, w2, w3);
                 }
+                high |= h.x | h.y | h.z | h.w;                    // (the halo counts: chunks that end inside it need no further scan)
                 const uint32_t pa = env.tile_s + phys(v << 4);
                 sts_u32(pa, h.x); sts_u32(pa + 4, h.y); sts_u32(pa + 8, h.z); sts_u32(pa + 12, h.w);
             }
@@ -675,137 +989,13 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         DBG_STAMP(4);
         // (2) events of the chunks that START in this tile
         uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;       // per-thread counters of the current segment
-        for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS) {
-            uint32_t seg = seg_lo;
-            if (seg_lo != seg_hi) {                                // segment of chunk c: last seg with seg_chunk[seg] <= c
-                uint32_t lo = seg_lo, hi = seg_hi;
-                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.seg_chunk + mid + 1) <= c) lo = mid + 1; else hi = mid; }
-                seg = lo;
-            }
-            SegPlan* pl = a.s.plan + seg;
-            const uint32_t seg_end = pl->seg_end, kept_chunk = pl->kept_chunk;
-            const bool is_kept = c == kept_chunk;
-            // text visible to both loops starts after the kept chunk; the kept chunk itself is tap-only
-            const uint32_t relay_begin = (kept_chunk != 0xFFFFFFFFu && !is_kept) ? pl->kept_end : pl->relay_begin;
-            const uint32_t o = __ldg(a.chunk_off + c), e = __ldg(a.chunk_off + c + 1);
-            if (o < relay_begin || pl->irregular) continue;
-            if (e == o) { pl->irregular = 1; continue; }
-            if (seg != acc_seg) {
-                if (acc_seg != 0xFFFFFFFFu) { if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a); if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b); }
-                acc_seg = seg; ev_a = ev_b = 0;
-            }
-
-            // chunk-level UTF-8: ASCII tiles need no check; the part of a chunk beyond the tile is
-            // scanned for bytes >= 0x80 with 16-byte loads first
-            bool need_utf8 = tile_high != 0;
-            if (!need_utf8 && e > t0 + LGW_TILE_BYTES) {
-                uint32_t hi_bits = 0;
-                for (uint32_t v = (t0 + LGW_TILE_BYTES) >> 4; (v << 4) < e; ++v) {
-                    if ((v << 4) + 16 <= n_bytes) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(a.data) + v); hi_bits |= x.x | x.y | x.z | x.w; }
-                    else hi_bits = 0x80;                      // ragged end: take the exact path
-                }
-                need_utf8 = (hi_bits & 0x80808080u) != 0;     // bytes after e in the last vector can only cause a spurious check
-            }
-            if (need_utf8 && !chunk_utf8_ok(&env, o, e)) { pl->irregular = 1; continue; }
-
-            // where does the event that is open at the start of this chunk begin?
-            uint32_t b = o;
-            if (o != relay_begin) {
-                const bool sep_before = o >= relay_begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au;
-                if (sep_before) {
-                    if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; continue; }   // LF run >= 3
-                } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; continue; }
-            }
-
-            // walk the events that complete inside this chunk (second LF of the separator in [o, e))
-            bool irregular = false, primed = false;
-            uint32_t us_b = 0, a_usage = 0; unsigned long long last_usage = 0;
-            uint32_t ps = b;
-            while (ps < e) {
-                uint32_t cls = PC_NONE, f = 0, pos = 0;
-                bool ended = false;
-                uint32_t hit = 2;
-#pragma unroll 1
-                for (uint32_t sl = 0; sl < LGW_TPL_SLOTS && hit == 2u; ++sl) {   // (one copy of the matcher in the loop: fewer registers, faster)
-                    if (!(sl ? have_tpl1 : have_tpl0)) continue;
-#if LGW_WINDOW_MATCH
-                    uint32_t r = match_window(env, sl, ps, &pos);
-                    if (r == 2u) r = match_template_far(env, sl, ps, &pos) ? 1u : 0u;
-                    if (r) hit = sl;
-#else
-                    if (match_template(env, sl, ps, &pos)) hit = sl;
+        // chunks longer than 128 B and than twice this tile's average chunk are left to k_relay_long
+        uint32_t defer_min = 0xFFFFFFFFu;
+#if LGW_DEFER_LONG
+        if (c_hi > c_lo && a.n_bytes < 0xFFFF0000u) { defer_min = 2u * (LGW_TILE_BYTES / (c_hi - c_lo)); if (defer_min < 128u) defer_min = 128u; }
 #endif
-                }
-                if (hit < 2) {
-                    if (pos + 1 >= e) break;                         // the separator completes in a later chunk
-                    ended = true; cls = sh_tpl_cls[hit]; f = sh_tpl_flags[hit];
-                } else {
-                    // classify the event prefix: "data: {" (handler + tap), "{" (tap only), anything else is skipped
-                    const uint32_t w0 = env.word(ps) >> (8 * (ps & 3u));
-                    if ((w0 & 0xffu) == '{') cls = PC_BRACE;
-                    else if ((w0 & 0xffu) == 'd') {
-                        if ((ps & 3u) == 0) cls = (w0 == 0x61746164u && (env.word(ps + 4) & 0xFFFFFFu) == 0x7b203au) ? PC_DATA : PC_NONE;
-                        else cls = (env.at(ps + 1) == 'a' && env.at(ps + 2) == 't' && env.at(ps + 3) == 'a' && env.at(ps + 4) == ':' && env.at(ps + 5) == ' ' && env.at(ps + 6) == '{') ? PC_DATA : PC_NONE;
-                    }
-                    // nominate the event for the second template (any valid event is a sound template, wherever it came from)
-                    if (cls != PC_NONE && have_tpl0) {
-                        if (!have_tpl1 && sh_tpl_tries1 < 3) atomicMin(&sh_tpl_cand1, ((unsigned long long)ps << 32) | seg_end);
-                        else if (have_tpl1) atomicAdd(&sh_tpl_miss, 1u);
-                    }
-                    LeanMachine lm;
-                    lm.reset(cls == PC_DATA);
-                    pos = ps + (cls == PC_DATA ? 6u : 0u);          // "data: " holds no LF
-                    while (pos < e && !ended) {                      // word-wise byte loop
-                        uint32_t w = env.word(pos) >> (8 * (pos & 3u));
-                        uint32_t nb = 4 - (pos & 3u);
-                        if (nb > e - pos) nb = e - pos;
-#pragma unroll 1
-                        for (; nb; --nb, w >>= 8, ++pos) {
-                            const uint32_t ch = w & 0xffu;
-                            // hot path: a plain byte inside a string changes nothing
-                            if (lm.st == L_STR && ch >= 0x20u && ch != '"' && ch != '\\') continue;
-                            if (ch == '\n') {
-                                if (pos + 1 >= e) { pos = e; break; }     // a separator starting on the last byte completes later
-                                if (env.at(pos + 1) == '\n') { ended = true; break; }
-                            }
-                            if (cls != PC_NONE) lm.step(ch, pos, env);
-                        }
-                    }
-                    if (!ended) break;                               // the open event completes in a later chunk
-                    f = lm.finish();
-                }
-                // ---- one complete event [ps, pos) ----
-                if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
-                if (cls != PC_NONE) {
-                    if (cls == PC_DATA) {
-                        if (is_kept) {                               // priming loop on the kept chunk, request_handler.py:82-91
-                            if (!primed) {
-                                if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) { irregular = true; break; }   // attempt fails: exact path
-                                primed = true;
-                            }
-                        } else {                                     // handler loop, request_handler.py:122-134
-                            ++ev_a;
-                            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) a_usage = 1;
-                        }
-                    }
-                    if (f & PF_VALID_B) {                            // tap loop, chat_logging.py:123-141
-                        ++ev_b;
-                        // events with "error" (extra DB row) go to the sequential path; a "usage" event is
-                        // a candidate whose values k_commit stashes for extraction on demand
-                        if (f & TK_ERROR) { irregular = true; break; }
-                        if (f & TK_USAGE) { ++us_b; last_usage = ((unsigned long long)(ps + 1) << 32) | (pos - ps); }
-                    }
-                }
-                ps = pos + 2;
-            }
-            if (is_kept && !irregular) {
-                // the speculation holds when a real event was accepted and the chunk ends on a separator
-                if (primed && ps == e) pl->prime_ok = 1; else irregular = true;
-            }
-            if (irregular) { pl->irregular = 1; continue; }
-            if (us_b) { atomicAdd(&pl->n_usage_b, us_b); atomicMax(&pl->last_usage, last_usage); }
-            if (a_usage) pl->a_usage = 1;
-        }
+        for (uint32_t c = c_lo + tid; c < c_hi; c += LGW_RELAY_THREADS)
+            walk_chunk<TileEnv, true>(a, env, c, seg_lo, seg_hi, tile_high, t0 + LGW_STAGE_BYTES, have_tpl0, have_tpl1, acc_seg, ev_a, ev_b, defer_min, true);
 
         DBG_STAMP(5);
         // (3) post the event counters: one atomic per warp when the whole warp worked on one segment
@@ -825,6 +1015,57 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         }
     }
 }
+
+#if LGW_DEFER_LONG
+// ---- k_relay_long ----------------------------------------------------------------------------------
+// One WARP per chunk that k_relay left out (much longer than its neighbours: in a warp of 64-byte deltas the one lane
+// with a 300-byte usage event holds 31 lanes and, at the tile barrier, its whole block).  Here every lane has a long
+// chunk.  Same walk, same templates (from the engine-wide cache), bytes read from global memory.
+__global__ void __launch_bounds__(LGW_RELAY_THREADS) k_relay_long(StepArgs a) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t n = *a.s.long_count;
+    if (n > a.s.long_cap) n = a.s.long_cap;
+    const uint32_t wpb = LGW_RELAY_THREADS / 32u, warp = tid >> 5, lane = tid & 31u;      // one WARP per long chunk
+    if (blockIdx.x * wpb >= n) return;                        // (uniform per block)
+    relay_prologue(a, tid);
+    __syncthreads();
+    GlobalEnv env;
+    env.cls_s = opaque((uint32_t)__cvta_generic_to_shared(sh_cls));
+    env.trans_s = opaque((uint32_t)__cvta_generic_to_shared(sh_trans));
+    env.tpl_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tpl_bytes));
+    env.strid_s = opaque((uint32_t)__cvta_generic_to_shared(sh_tpl_strid));
+    env.g = a.data; env.n_bytes = a.n_bytes;
+    // The long chunks are not walked by k_relay any more, so it never meets (and never learns) their skeleton: the second
+    // template is learnt here, from the first event of this block's first chunk when it does not follow slot 0.
+    if (sh_tpl_valid[0] && !sh_tpl_valid[1]) {                  // (uniform per block)
+        if (tid == 0) {
+            const uint32_t i0 = blockIdx.x * wpb;
+            const uint32_t c = a.s.long_q[2 * i0], seg = a.s.long_q[2 * i0 + 1];
+            const SegPlan* pl = a.s.plan + seg;
+            const uint32_t o = __ldg(a.chunk_off + c);
+            const uint32_t begin = (pl->kept_chunk != 0xFFFFFFFFu && c > pl->kept_chunk) ? pl->kept_end : pl->relay_begin;
+            uint32_t pos_unused;
+            if (!pl->irregular && o >= begin && o + 8 < pl->seg_end && (o == begin || (o >= begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au))
+                && !match_template(env, 0, o, &pos_unused)) {
+                build_template(&env, 1, o, pl->seg_end);
+                if (sh_tpl_valid[1]) publish_template(a.s.tpl_cache, 1, false);
+            }
+        }
+        __syncthreads();
+    }
+    const bool have_tpl0 = sh_tpl_valid[0] != 0, have_tpl1 = sh_tpl_valid[1] != 0;
+    for (uint32_t i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+        const uint32_t c = a.s.long_q[2 * i], lo = a.s.long_q[2 * i + 1];      // (chunk, its segment)
+        uint32_t acc_seg = 0xFFFFFFFFu, ev_a = 0, ev_b = 0;
+        walk_chunk<GlobalEnv, false>(a, env, c, lo, lo, 0, 0u, have_tpl0, have_tpl1, acc_seg, ev_a, ev_b, 0xFFFFFFFFu, lane == 0);
+        if (lane == 0 && acc_seg != 0xFFFFFFFFu) {
+            if (ev_a) atomicAdd(&a.s.plan[acc_seg].n_events_a, ev_a);
+            if (ev_b) atomicAdd(&a.s.plan[acc_seg].n_events_b, ev_b);
+        }
+    }
+}
+
+#endif  // LGW_DEFER_LONG
 
 // ---- k_commit --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
@@ -865,7 +1106,16 @@ __global__ void __launch_bounds__(64) k_commit(StepArgs a) {
                 const uint32_t off = ups & 15u, nv = (off + ulen + 15u) >> 4;
                 const uint4* src = reinterpret_cast<const uint4*>(d + (ups - off));
                 uint4* dst = reinterpret_cast<uint4*>(io.pending);
-                if (((size_t)(ups - off) + ((size_t)nv << 4)) <= a.n_bytes) { for (uint32_t k = 0; k < nv; ++k) dst[k] = __ldg(src + k); }
+                if (((size_t)(ups - off) + ((size_t)nv << 4)) <= a.n_bytes) {
+                    // eight loads in flight per round (dst may alias src for the compiler: a plain loop is one DRAM round trip per vector)
+                    for (uint32_t k0 = 0; k0 < nv; k0 += 8) {
+                        uint4 r[8];
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) if (k0 + j < nv) r[j] = __ldg(src + k0 + j);
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) if (k0 + j < nv) dst[k0 + j] = r[j];
+                    }
+                }
                 else { for (uint32_t k = 0; k < ulen; ++k) io.pending[off + k] = __ldg(d + ups + k); }
                 st.pending_len = ulen | (off << 16); st.flags |= SF_PENDING; ++st.n_usage_b;
             }
@@ -894,14 +1144,19 @@ static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cuda
     cudaError_t r;
     const uint32_t n_tiles = (a.n_bytes - a.tile_base + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
     const uint32_t n_off = a.chunk_hi - a.chunk_lo + 1;
-    const uint32_t n_prime = (a.n_segs > n_off ? a.n_segs : n_off);
-    k_prime<<<(n_prime + 127) / 128, 128, 0, stream>>>(a, n_tiles); ++*launched;
+    uint32_t prime_blocks = (n_off + 127) / 128;                        // chunks: grid-stride over at most 8 blocks per SM
+    if (prime_blocks > (uint32_t)sm_count * 8u) prime_blocks = (uint32_t)sm_count * 8u;
+    if (prime_blocks < (a.n_segs + 127) / 128) prime_blocks = (a.n_segs + 127) / 128;   // segments: one thread each
+    k_prime<<<prime_blocks, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
     if (n_tiles) {
         const uint32_t max_blocks = (uint32_t)sm_count * LGW_RELAY_BLOCKS_PER_SM;
         const uint32_t tpb = (n_tiles + max_blocks - 1) / max_blocks;
         const uint32_t blocks = (n_tiles + tpb - 1) / tpb;
         k_relay<<<blocks, LGW_RELAY_THREADS, 0, stream>>>(a, n_tiles, tpb); ++*launched;
+#if LGW_DEFER_LONG
+        k_relay_long<<<(uint32_t)sm_count * 16u, LGW_RELAY_THREADS, 0, stream>>>(a); ++*launched;
+#endif
     }
     if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
     if (a.n_segs) { k_commit<<<(a.n_segs + 63) / 64, 64, 0, stream>>>(a); ++*launched; }

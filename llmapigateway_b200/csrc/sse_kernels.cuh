@@ -58,6 +58,9 @@ struct StepScratch {
     uint32_t* tile_chunk;      // [max tiles + 2] first chunk starting at or after each tile
     TemplateCache* tpl_cache;  // persistent across steps
     uint32_t max_tiles;
+    uint32_t* long_q;          // [long_cap][2] (chunk, segment) pairs left out of the tile walk (k_relay -> k_relay_long)
+    uint32_t* long_count;      // entries wanted (may exceed long_cap: the excess was walked in place)
+    uint32_t long_cap;
 };
 
 struct StepArgs {
@@ -83,9 +86,13 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size
     if ((r = cudaMalloc((void**)&s.tile_chunk, ((size_t)s.max_tiles + 2) * 4)) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.tpl_cache, sizeof(TemplateCache))) != cudaSuccess) return r;
     if ((r = cudaMemset(s.tpl_cache, 0, sizeof(TemplateCache))) != cudaSuccess) return r;
+    s.long_cap = (uint32_t)(max_chunks < (1u << 20) ? (max_chunks ? max_chunks : 1) : (1u << 20));
+    if ((r = cudaMalloc((void**)&s.long_q, ((size_t)s.long_cap * 2 + 1) * 4)) != cudaSuccess) return r;
+    s.long_count = s.long_q + (size_t)s.long_cap * 2;
+    if ((r = cudaMemset(s.long_count, 0, 4)) != cudaSuccess) return r;
     return cudaSuccess;
 }
-static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); cudaFree(s.tpl_cache); s.plan = nullptr; s.tile_chunk = nullptr; s.tpl_cache = nullptr; }
+static inline void scratch_free(StepScratch& s) { cudaFree(s.plan); cudaFree(s.tile_chunk); cudaFree(s.tpl_cache); cudaFree(s.long_q); s.long_q = nullptr; s.long_count = nullptr; s.plan = nullptr; s.tile_chunk = nullptr; s.tpl_cache = nullptr; }
 
 __device__ __forceinline__ StepIO make_io(const StepArgs& a, uint32_t slot, StreamHdr* local_hdr) {
     StepIO io;
