@@ -388,10 +388,11 @@ __device__ __forceinline__ uint32_t match_window(const TileEnv& env, uint32_t sl
         ia = sh_tpl_send[slot][id];
         fresh = true;
     }
-    {   // LF LF must follow
+    {   // LF LF must follow -- and no third LF (a run of three is the sequential path's business; the caller need not look again)
         const uint32_t q = db & ~3u;
         if (q + 12u > LGW_STAGE_BYTES) return 2;
-        if ((__funnelshift_r(LGW_WW(q), LGW_WW(q + 4), 8 * (db & 3u)) & 0xffffu) != 0x0a0au) return 0;
+        const uint32_t w = __funnelshift_r(LGW_WW(q), LGW_WW(q + 4), 8 * (db & 3u));
+        if ((w & 0xffffu) != 0x0a0au || ((w >> 16) & 0xffu) == '\n') return 0;
     }
 #undef LGW_WW
     *end = env.t0 + db;
@@ -662,7 +663,12 @@ __device__ __forceinline__ void walk_chunk(const StepArgs& a, const ENV& env, co
 
     // where does the event that is open at the start of this chunk begin?
     uint32_t b = o;
-    if (o != relay_begin) {
+    if (o >= relay_begin + 3) {                               // common case: one read of the bytes o-3 .. o
+        const uint32_t w = env.wordu(o - 3);
+        if ((w & 0x00ffff00u) == 0x000a0a00u) {               // a separator ends right before the chunk
+            if ((w & 0xffu) == '\n' || (w >> 24) == '\n') { pl->irregular = 1; return; }   // LF run >= 3
+        } else if (!find_open_event_start(&env, o, relay_begin, seg_end, a.t.carry_cap, &b)) { pl->irregular = 1; return; }
+    } else if (o != relay_begin) {
         const bool sep_before = o >= relay_begin + 2 && (env.wordu(o - 2) & 0xffffu) == 0x0a0au;
         if (sep_before) {
             if ((o >= relay_begin + 3 && env.at(o - 3) == '\n') || env.at(o) == '\n') { pl->irregular = 1; return; }   // LF run >= 3
@@ -677,6 +683,7 @@ __device__ __forceinline__ void walk_chunk(const StepArgs& a, const ENV& env, co
         uint32_t cls = PC_NONE, f = 0, pos = 0;
         bool ended = false;
         uint32_t hit = 2;
+        bool lf3_clear = false;                                  // the window matcher saw that no third LF follows
 #pragma unroll 1
         for (uint32_t sl = 0; sl < LGW_TPL_SLOTS && hit == 2u; ++sl) {   // (one copy of the matcher in the loop: fewer registers, faster)
             if (!(sl ? have_tpl1 : have_tpl0)) continue;
@@ -684,6 +691,7 @@ __device__ __forceinline__ void walk_chunk(const StepArgs& a, const ENV& env, co
             if constexpr (BULK) {
                 uint32_t r = match_window(env, sl, ps, &pos);
                 if (r == 2u) r = match_template_far(env, sl, ps, &pos) ? 1u : 0u;
+                else if (r) lf3_clear = true;
                 if (r) hit = sl;
             } else
 #endif
@@ -732,7 +740,7 @@ __device__ __forceinline__ void walk_chunk(const StepArgs& a, const ENV& env, co
             f = lm.finish();
         }
         // ---- one complete event [ps, pos) ----
-        if (pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
+        if (!lf3_clear && pos + 2 < seg_end && env.at(pos + 2) == '\n') { irregular = true; break; }   // LF run >= 3
         if (cls != PC_NONE) {
             if (cls == PC_DATA) {
                 if (is_kept) {                               // priming loop on the kept chunk, request_handler.py:82-91
@@ -772,20 +780,28 @@ __global__ void __launch_bounds__(128) k_prime(StepArgs a, uint32_t n_tiles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // tile table: tile_chunk[t] = first c in [chunk_lo, chunk_hi] with chunk_off[c] >= start of tile t.  One thread per
     // chunk writes the tiles whose start falls in (chunk_off[c-1], chunk_off[c]] -- one coalesced pass over the offsets
-    // instead of a binary search of ~20 dependent loads per tile.  Grid-stride: a block per 128 chunks would be 16 k
-    // blocks of a few instructions each, and the block scheduler then sets the pace (15 us for 2 M chunks).
+    // instead of a binary search of ~20 dependent loads per tile.
     if (i == 0) *a.s.long_count = 0;                       // queue of the chunks k_relay leaves to k_relay_long
     const uint32_t n_off = a.chunk_hi - a.chunk_lo + 1;
-    for (uint32_t j = i; j < n_off; j += gridDim.x * blockDim.x) {
-        const uint32_t c = a.chunk_lo + j;
-        const uint32_t off = __ldg(a.chunk_off + c);
-        uint32_t t_first = 0;
-        if (j > 0) { const uint32_t prev = __ldg(a.chunk_off + c - 1); t_first = prev < a.tile_base ? 0u : (prev - a.tile_base) / LGW_TILE_BYTES + 1u; }
-        uint32_t t_last = off < a.tile_base ? 0u : (off - a.tile_base) / LGW_TILE_BYTES;      // off >= tile_base always holds for c >= chunk_lo
-        if (off < a.tile_base) t_first = 1;                                                  // (defensive: nothing to write)
-        if (c == a.chunk_hi) t_last = n_tiles;                                               // tiles past the last offset
-        if (t_last > n_tiles) t_last = n_tiles;
-        for (uint32_t t = t_first; t <= t_last; ++t) a.s.tile_chunk[t] = c;
+    const uint32_t j0 = i * 4u;                              // four consecutive chunks per thread, their five offsets loaded up front
+    if (j0 < n_off) {
+        uint32_t offs[5];                                    // offs[k] = offset of chunk chunk_lo + j0 + k - 1
+#pragma unroll
+        for (uint32_t k = 0; k < 5; ++k) { const uint32_t j = j0 + k; offs[k] = (j >= 1u && j - 1u < n_off) ? __ldg(a.chunk_off + a.chunk_lo + j - 1u) : 0u; }
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t j = j0 + k;
+            if (j < n_off) {
+                const uint32_t c = a.chunk_lo + j, off = offs[k + 1];
+                uint32_t t_first = 0;
+                if (j > 0) { const uint32_t prev = offs[k]; t_first = prev < a.tile_base ? 0u : (prev - a.tile_base) / LGW_TILE_BYTES + 1u; }
+                uint32_t t_last = off < a.tile_base ? 0u : (off - a.tile_base) / LGW_TILE_BYTES;      // off >= tile_base always holds for c >= chunk_lo
+                if (off < a.tile_base) t_first = 1;                                                  // (defensive: nothing to write)
+                if (c == a.chunk_hi) t_last = n_tiles;                                               // tiles past the last offset
+                if (t_last > n_tiles) t_last = n_tiles;
+                for (uint32_t t = t_first; t <= t_last; ++t) a.s.tile_chunk[t] = c;
+            }
+        }
     }
     if (i >= a.n_segs) return;
     const uint32_t seg = i, c0 = a.seg_chunk[seg], c1 = a.seg_chunk[seg + 1];
@@ -911,7 +927,28 @@ __global__ void __launch_bounds__(LGW_RELAY_THREADS, LGW_RELAY_BLOCKS_PER_SM) k_
         // (1) re-emit: position-preserving 16-byte copy of the tile, staged (swizzled) into shared memory
         //     on the way; note whether the tile has any byte >= 0x80 (UTF-8 checks are skipped otherwise)
         uint32_t high = 0;
-        {
+        if (t0 + LGW_STAGE_BYTES <= n_bytes) {              // every tile but the last: no bounds tests
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
+            uint4 x[LGW_TILE_VECS / LGW_RELAY_THREADS];
+#pragma unroll
+            for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) x[k] = ldg_stream(src + k * LGW_RELAY_THREADS + tid);
+#pragma unroll
+            for (uint32_t k = 0; k < LGW_TILE_VECS / LGW_RELAY_THREADS; ++k) {
+                const uint32_t v = k * LGW_RELAY_THREADS + tid;
+                dst[v] = x[k];
+                high |= x[k].x | x[k].y | x[k].z | x[k].w;
+                const uint32_t pa = env.tile_s + phys(v << 4);
+                sts_u32(pa, x[k].x); sts_u32(pa + 4, x[k].y); sts_u32(pa + 8, x[k].z); sts_u32(pa + 12, x[k].w);
+            }
+            if (tid < LGW_HALO_BYTES / 16) {
+                const uint32_t v = LGW_TILE_VECS + tid;
+                const uint4 h = ldg_stream(src + v);
+                high |= h.x | h.y | h.z | h.w;
+                const uint32_t pa = env.tile_s + phys(v << 4);
+                sts_u32(pa, h.x); sts_u32(pa + 4, h.y); sts_u32(pa + 8, h.z); sts_u32(pa + 12, h.w);
+            }
+        } else {
             const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.data + t0);
             uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.out + t0);
             uint4 x[LGW_TILE_VECS / LGW_RELAY_THREADS];
@@ -1144,8 +1181,7 @@ static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cuda
     cudaError_t r;
     const uint32_t n_tiles = (a.n_bytes - a.tile_base + LGW_TILE_BYTES - 1) / LGW_TILE_BYTES;
     const uint32_t n_off = a.chunk_hi - a.chunk_lo + 1;
-    uint32_t prime_blocks = (n_off + 127) / 128;                        // chunks: grid-stride over at most 8 blocks per SM
-    if (prime_blocks > (uint32_t)sm_count * 8u) prime_blocks = (uint32_t)sm_count * 8u;
+    uint32_t prime_blocks = (n_off + 511) / 512;                        // chunks: four per thread
     if (prime_blocks < (a.n_segs + 127) / 128) prime_blocks = (a.n_segs + 127) / 128;   // segments: one thread each
     k_prime<<<prime_blocks, 128, 0, stream>>>(a, n_tiles); ++*launched;
     if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
