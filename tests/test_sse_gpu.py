@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path through the C ABI against the golden fixtures (outputs of the
 unmodified reference) and against the oracle on seeded synthetic streams.  Byte-exact."""
 import json
+import re
 import random
 
 import numpy as np
@@ -279,6 +280,10 @@ def test_gateway_seam_on_the_real_engine(engine):
     asyncio.run(go())
 
 
+NUMBER_SPELLINGS = ["0", "-0", "01", "00", "7", "1.5", "1.", ".5", "-", "-12", "+1", "1e5", "1E+5", "1e", "1e+", "1.5e-3", "1.e3", "1e5.3",
+                    "0x10", "1_0", "9" * 25, "12345678", "123456789012", "0.001234", "-0.0", "1-2", "1 2", "NaN", "-Infinity", "Infinity", "1e005"]
+
+
 def _template_variant_streams(n_streams, seed):
     """Streams of near-identical events: the bulk kernel's template shortcut must accept exactly the
     variants that differ inside ONE string value by plain bytes, and fall back for everything else."""
@@ -319,6 +324,8 @@ def _template_variant_streams(n_streams, seed):
                 text = text.replace('"content"', '"cont\\u0065nt"')
             elif m < 0.12:
                 text = text + rng.choice([" ", "\t", "\x0c", "x"])
+            elif m < 0.22 and '"created":' in text:      # number values: valid and invalid spellings (number spans of the templates)
+                text = re.sub(r'"created":\d+', '"created":' + rng.choice(NUMBER_SPELLINGS), text)
             evs.append(sc.ev(text))
             if rng.random() < 0.03:
                 evs.append(rng.choice([b": ping\n\n", sc.DONE, b"\n", b'{"usage":{"prompt_tokens":1}}\n\n']))
