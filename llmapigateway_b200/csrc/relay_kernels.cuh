@@ -9,13 +9,14 @@
 // findings with atomics.  Everything else is flagged irregular and redone by k_commit with the exact
 // sequential machine, so the result never depends on which path ran (tests run both and the oracle).
 //
-// Event templates.  SSE deltas of a stream are the same JSON skeleton over and over with one string
-// value changing.  Each persistent block keeps ONE validated event as a template (bytes + for every
-// byte position whether the recogniser is inside a string VALUE there).  An event B that equals the
-// template A up to a position inside a value string, continues with plain string bytes up to a
-// closing quote, and from there equals A's text after that string's closing quote, drives the
-// recogniser through the same states as A: same validity, same top-level keys -- no byte of it needs
-// to be re-validated beyond the comparison.  Anything else takes the byte-wise recogniser.
+// Event templates.  SSE deltas of a stream are the same JSON skeleton over and over with a few values
+// changing.  Each persistent block keeps TWO validated events as templates (bytes + for every byte position
+// the id of the string or number VALUE span it lies in), shared engine-wide through TemplateCache.  An event
+// that is byte-identical to a template outside value spans, holds plain string bytes / valid escapes up to the
+// closing quote inside string spans and a valid JSON number inside number spans drives the recogniser through
+// the same states as the template: same validity, same top-level keys -- no byte of it needs to be
+// re-validated beyond the comparison (match_window for events inside the staged window, match_template
+// anywhere).  Anything else takes the byte-wise recogniser.
 
 #ifndef LGW_RELAY_THREADS
 #define LGW_RELAY_THREADS 64

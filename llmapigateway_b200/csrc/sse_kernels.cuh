@@ -1,13 +1,14 @@
 // Kernels of the SSE step (sm_100a).  See DESIGN.md for the data layout and the roofline of each.
 //
-//   k_prime    one thread per segment: streams still PRIMING walk their chunks with the exact
-//              sequential machine until they commit or fail (a handful of chunks per stream);
-//              writes the per-segment plan the bulk kernel reads.
-//   k_relay    bulk kernel: every block copies one byte tile in -> out with 16-byte vector
-//              accesses (the re-emit) and parses the events of the chunks that start in it.
+//   k_prime    tile table (first chunk of every 8 KiB byte tile, one coalesced pass over the chunk offsets)
+//              and, one thread per segment, the plan the bulk kernel works to; a fresh stream is
+//              speculated to commit on its first non-empty chunk.
+//   k_relay    bulk kernel: persistent blocks copy byte tiles in -> out with 16-byte vector accesses
+//              (the re-emit), staging them in shared memory, and walk the events of the chunks that
+//              start in the tile (event templates, window matcher, lean recogniser).
 //   k_commit   one thread per segment: folds the bulk kernel's findings into the persistent
-//              stream state; streams the bulk kernel flagged irregular are redone sequentially
-//              with the exact machine.
+//              stream state; streams the bulk kernel flagged irregular (or whose speculation failed)
+//              are redone sequentially with the exact machine.
 //   k_general  (mode 1 / fix-up) the exact sequential machine over whole segments.
 #pragma once
 #include <cuda_runtime.h>
