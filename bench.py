@@ -240,7 +240,7 @@ def main():
     eng.sync()
     barrier()
     l0 = eng.launch_count()
-    kern = {"prime": 0.0, "relay": 0.0, "commit": 0.0}
+    kern = {"prime": 0.0, "relay": 0.0, "commit": 0.0, "usage_extract": 0.0}
     step_ms = []
     # Between timed steps (not timed): 256 MiB written on the same stream.  It evicts L2 (126 MB) and keeps the GPU busy
     # while the host enqueues the step's launches, so the timed region is the device's work, not the host's launch latency
@@ -329,7 +329,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(), "peak_source": peak_src,
-                     "kernel": "k_prime + k_relay (+ k_relay_long) + k_commit (summed; 128 B algorithmic per 64-B event)"},
+                     "kernel": "k_prime2 + k_relay2 + k_commit2 + k_usage_extract (summed; 128 B algorithmic per 64-B event; usage extraction on the clock)"},
         "wall_s_timed_loop": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:

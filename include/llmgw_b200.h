@@ -176,8 +176,11 @@ int lgw_fetch_rows(lgw_engine* e, lgw_row_event* rows_out, uint32_t rows_cap, ui
 int lgw_sync(lgw_engine* e);
 
 /* device time of the kernels of the last step (CUDA events on the launching stream), milliseconds:
- * [0] prime  [1] relay (bulk parse + re-emit)  [2] commit  [3] whole step incl. copies (host entry only) */
+ * [0] prime  [1] relay (bulk parse + re-emit + usage fields of template-following events)  [2] commit + usage extract
+ * [3] whole step incl. copies (host entry only) */
 int lgw_last_step_ms(lgw_engine* e, float ms[4]);
+/* the four kernels one by one: [0] prime  [1] relay  [2] commit  [3] usage extract (stashed usage events) */
+int lgw_last_step_kernel_ms(lgw_engine* e, float ms[4]);
 /* number of kernels launched by this engine since creation */
 int lgw_launch_count(lgw_engine* e, uint64_t* out);
 

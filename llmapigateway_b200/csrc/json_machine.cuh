@@ -116,6 +116,19 @@ struct ChoiceSide {     // what the tap needs to know about choice["delta"] / ch
     uint8_t present, kind, has_content, content_kind, content_truthy;
 };
 
+// Optional position tracker (template-driven usage extraction, relay2.cuh): where the values of the eight usage
+// fields start and end in the text, how often each tracked key occurs, and the extent of the "choices" value.
+enum UsageField : uint8_t { UF_PROMPT = 0, UF_COMPLETION, UF_TOTAL, UF_COST, UF_REASONING, UF_CACHED, UF_MODEL, UF_PROVIDER, UF_N };
+struct ValueTrack {
+    uint32_t pos;                  // position of the byte being fed (set by the caller before feed())
+    uint32_t vstart;               // where the value being read began
+    uint32_t fstart[UF_N], fend[UF_N];   // value extent per field: [fstart, fend) (numbers: fend = terminator; strings: fend = closing quote + 1)
+    uint32_t dup;                  // some tracked key occurred more than once
+    uint32_t seen;                 // bit per tracked slot
+    uint32_t choices_lo, choices_hi;
+    LGW_HD void reset() { pos = 0; vstart = 0; dup = 0; seen = 0; choices_lo = choices_hi = 0xFFFFFFFFu; for (int i = 0; i < UF_N; ++i) { fstart[i] = fend[i] = 0xFFFFFFFFu; } }
+};
+
 template <bool EXTRACT>
 struct JsonMachine {
     // syntax
@@ -142,13 +155,16 @@ struct JsonMachine {
     // capture target
     UsageRaw* rec;
     char* cap; uint8_t* cap_len; uint8_t* cap_flags;
+    ValueTrack* trk;           // optional (nullptr: no tracking)
+
+    LGW_HD void track_field(int f, bool is_str) { if (EXTRACT && trk) { trk->fstart[f] = trk->vstart; trk->fend[f] = trk->pos + (is_str ? 1u : 0u); } }
 
     LGW_HD void reset(UsageRaw* r, bool strip) {
         st = S_VALUE; depth = 0; ctx = X_TOP; slot = SL_NONE; other_ret = X_TOP; other_depth = 0;
         in_key = 0; lit_id = 0; lit_pos = 0; ucount = 0; strip_mode = strip ? 1 : 0; cont_empty = 0;
         stack = 0; flags = 0; k0 = k1 = k2 = k3 = 0; klen = 0; key_bad = 0; ucode = 0; pending_high = 0;
         num.reset(); slen = 0; cd = ChoiceSide{0, 0, 0, 0, 0}; cm = cd; ch_stop = 0; ret_slots = 0;
-        rec = r; cap = nullptr; cap_len = nullptr; cap_flags = nullptr;
+        rec = r; cap = nullptr; cap_len = nullptr; cap_flags = nullptr; trk = nullptr;
         if (EXTRACT && r) clear_usage(*r);
     }
 
@@ -184,9 +200,10 @@ struct JsonMachine {
         case X_TOP:
             if (EXTRACT && rec) {
                 if (s == SL_USAGE) rec->usage_kind = kind;
-                else if (s == SL_MODEL) { rec->model_kind = kind; rec->model_val.kind = kind; rec->model_val.bits = bits; }
-                else if (s == SL_PROVIDER) { rec->provider_kind = kind; rec->provider_val.kind = kind; rec->provider_val.bits = bits; }
+                else if (s == SL_MODEL) { rec->model_kind = kind; rec->model_val.kind = kind; rec->model_val.bits = bits; track_field(UF_MODEL, kind == KD_STR); }
+                else if (s == SL_PROVIDER) { rec->provider_kind = kind; rec->provider_val.kind = kind; rec->provider_val.bits = bits; track_field(UF_PROVIDER, kind == KD_STR); }
             }
+            if (EXTRACT && trk && s == SL_CHOICES) trk->choices_hi = trk->pos;
             if (s == SL_CHOICES) {
                 // chat_logging.py:125 `for choice in chunk_json["choices"]`
                 if (kind == KD_OBJ) { if (!cont_empty) flags |= PF_EXOTIC; }        // iterates keys
@@ -197,19 +214,19 @@ struct JsonMachine {
         case X_USAGE:
             if (EXTRACT && rec) {
                 Val v; v.kind = kind; v.bits = bits;
-                if (s == SL_PROMPT) rec->prompt = v;
-                else if (s == SL_COMPLETION) rec->completion = v;
-                else if (s == SL_TOTAL) rec->total = v;
-                else if (s == SL_COST) rec->cost = v;
+                if (s == SL_PROMPT) { rec->prompt = v; track_field(UF_PROMPT, kind == KD_STR); }
+                else if (s == SL_COMPLETION) { rec->completion = v; track_field(UF_COMPLETION, kind == KD_STR); }
+                else if (s == SL_TOTAL) { rec->total = v; track_field(UF_TOTAL, kind == KD_STR); }
+                else if (s == SL_COST) { rec->cost = v; track_field(UF_COST, kind == KD_STR); }
                 else if (s == SL_CTD) rec->ctd_kind = kind;
                 else if (s == SL_PTD) rec->ptd_kind = kind;
             }
             break;
         case X_CTD:
-            if (EXTRACT && rec && s == SL_REASONING) { rec->reasoning.kind = kind; rec->reasoning.bits = bits; }
+            if (EXTRACT && rec && s == SL_REASONING) { rec->reasoning.kind = kind; rec->reasoning.bits = bits; track_field(UF_REASONING, kind == KD_STR); }
             break;
         case X_PTD:
-            if (EXTRACT && rec && s == SL_CACHED) { rec->cached.kind = kind; rec->cached.bits = bits; }
+            if (EXTRACT && rec && s == SL_CACHED) { rec->cached.kind = kind; rec->cached.bits = bits; track_field(UF_CACHED, kind == KD_STR); }
             break;
         case X_CHOICES:
             // a scalar / string / nested array element of the choices list (objects are
@@ -335,6 +352,14 @@ struct JsonMachine {
             default: break;
             }
         }
+        if (EXTRACT && trk && s != SL_NONE) {
+            // one bit per (context, key): the same key name in two different contexts is not a duplicate, but the
+            // second "usage" object of a document re-enters X_USAGE -- its keys then count as repeats (conservative)
+            const uint32_t bit = 1u << s;
+            if (trk->seen & bit) trk->dup = 1;
+            trk->seen |= bit;
+            if (s == SL_CHOICES) trk->choices_lo = trk->pos;
+        }
         slot = s;
         st = S_COLON;
     }
@@ -395,6 +420,7 @@ struct JsonMachine {
     }
 
     LGW_HD void begin_value(uint32_t c) {
+        if (EXTRACT && trk) trk->vstart = trk->pos;
         if (c == '"') { begin_string(false); }
         else if (c == '{') open_container(true);
         else if (c == '[') open_container(false);

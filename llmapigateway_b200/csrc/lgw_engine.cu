@@ -38,11 +38,11 @@ struct lgw_engine {
     uint32_t *d_chunk_off = nullptr, *d_seg_chunk = nullptr, *d_seg_slot = nullptr;
     SegResult* d_seg_out = nullptr;
     uint32_t* d_slots = nullptr; int32_t* d_status = nullptr; StreamState* d_state_stage = nullptr;
-    cudaEvent_t ev[6]{};
+    cudaEvent_t ev[7]{};            // [0..4] bracket prime / relay / commit / usage extract; [5],[6] the host-buffer step
     cudaEvent_t rev[4]{};
     float rms[2]{0, 0};
     RollupRow* d_rows = nullptr; uint64_t d_rows_cap = 0; unsigned long long* d_nrows = nullptr;
-    float ms[4]{0, 0, 0, 0};
+    float ms[5]{0, 0, 0, 0, 0};     // prime, relay, commit, usage extract, whole host-buffer step
     bool timed = false;
     uint64_t launches = 0;
     // request-body rewrite (rows a1-a4): plan table + grow-only staging
@@ -106,7 +106,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     ALLOC(e->d_chunk_off, (C + 1) * 4); ALLOC(e->d_seg_chunk, (S + 1) * 4); ALLOC(e->d_seg_slot, S * 4);
     ALLOC(e->d_seg_out, S * sizeof(SegResult));
     ALLOC(e->d_slots, S * 4); ALLOC(e->d_status, S * 4); ALLOC(e->d_state_stage, S * sizeof(StreamState));
-    if ((r = scratch_alloc(e->scratch, S, C, B)) != cudaSuccess) return fail("scratch_alloc", r);
+    if ((r = scratch_alloc(e->scratch, S, e->sm_count)) != cudaSuccess) return fail("scratch_alloc", r);
 #undef ALLOC
     if ((r = cudaMemset(e->t.state, 0, S * sizeof(StreamState))) != cudaSuccess) return fail("cudaMemset", r);
     if ((r = cudaMemset(e->d_rowq_count, 0, 16)) != cudaSuccess) return fail("cudaMemset", r);
@@ -212,7 +212,7 @@ static int step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, 
     if (s1 == 0xFFFFFFFFu) { s1 = n_segs; c1 = n_chunks; b1 = n_bytes; }
     StepArgs a{};
     a.t = e->t; a.data = d_bytes; a.n_bytes = (uint32_t)b1; a.chunk_off = d_chunk_off; a.n_chunks = n_chunks;
-    a.tile_base = b0 & ~(LGW_TILE_BYTES - 1u); a.chunk_lo = c0; a.chunk_hi = c1;
+    a.tile_base = b0; a.chunk_lo = c0; a.chunk_hi = c1;
     a.seg_chunk = d_seg_chunk + s0; a.seg_slot = d_seg_slot + s0; a.n_segs = s1 - s0; a.out = d_out; a.seg_out = d_seg_out + s0;
     a.rowq = e->d_rowq; a.rowq_count = e->d_rowq_count; a.rowq_cap = e->lim.rowq_cap; a.s = e->scratch;
     if (reset_rows) CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
@@ -265,7 +265,7 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
     if (n_segs && (seg_chunk[0] != 0 || seg_chunk[n_segs] != n_chunks)) { e->err = "seg_chunk must cover all chunks"; return LGW_ERR_ARG; }
     for (uint32_t s = 0; s < n_segs; ++s) if (seg_chunk[s] > seg_chunk[s + 1] || seg_slot[s] >= e->lim.max_streams) { e->err = "bad segment table"; return LGW_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
-    CK(e, cudaEventRecord(e->ev[4], e->stream));
+    CK(e, cudaEventRecord(e->ev[5], e->stream));
     // Pipelined: the step is cut at segment boundaries into up to 8 slices; the upload of slice k+1,
     // the kernels of slice k and the download of slice k-1 overlap (PCIe is full duplex).
     uint32_t n_slices = n_bytes >= (8u << 20) && n_segs >= 16 ? 4u : 1u;
@@ -302,20 +302,32 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
     // which would serialise the pipeline if it were issued per slice)
     if (n_segs) CK(e, cudaMemcpyAsync(seg_out, e->d_seg_out, (size_t)n_segs * sizeof(SegResult), cudaMemcpyDeviceToHost, e->stream));
     if (n_slices > 1) { CK(e, cudaStreamSynchronize(e->s_out)); CK(e, cudaStreamSynchronize(e->s_in)); }
-    CK(e, cudaEventRecord(e->ev[5], e->stream));
+    CK(e, cudaEventRecord(e->ev[6], e->stream));
     rc = lgw_fetch_rows(e, rows_out, rows_cap, n_rows);
     if (rc != LGW_OK) return rc;
-    float t = 0; if (cudaEventElapsedTime(&t, e->ev[4], e->ev[5]) == cudaSuccess) e->ms[3] = t;
+    float t = 0; if (cudaEventElapsedTime(&t, e->ev[5], e->ev[6]) == cudaSuccess) e->ms[4] = t;
     return LGW_OK;
 }
 
-extern "C" int lgw_last_step_ms(lgw_engine* e, float ms[4]) {
-    if (!e || !ms) return LGW_ERR_ARG;
+static int read_step_ms(lgw_engine* e) {
     if (e->timed) {
         CK(e, cudaSetDevice(e->device));
-        CK(e, cudaEventSynchronize(e->ev[3]));
-        for (int i = 0; i < 3; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->ms[i] = t; }
+        CK(e, cudaEventSynchronize(e->ev[4]));
+        for (int i = 0; i < 4; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->ms[i] = t; }
     }
+    return LGW_OK;
+}
+extern "C" int lgw_last_step_ms(lgw_engine* e, float ms[4]) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    const int rc = read_step_ms(e);
+    if (rc != LGW_OK) return rc;
+    ms[0] = e->ms[0]; ms[1] = e->ms[1]; ms[2] = e->ms[2] + e->ms[3]; ms[3] = e->ms[4];
+    return LGW_OK;
+}
+extern "C" int lgw_last_step_kernel_ms(lgw_engine* e, float ms[4]) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    const int rc = read_step_ms(e);
+    if (rc != LGW_OK) return rc;
     for (int i = 0; i < 4; ++i) ms[i] = e->ms[i];
     return LGW_OK;
 }
@@ -584,17 +596,27 @@ extern "C" int lgw_bodies_last_ms(lgw_engine* e, float ms[3]) {
     return LGW_OK;
 }
 
-// diagnostics (not part of the public header, like lgw_engine_set_mode): the engine-wide event-template cache
-// out[0..7] = state[2], len[2], flags[2], cls[2]; text = first `cap` bytes of each slot's template
-extern "C" int lgw_debug_template_cache(lgw_engine* e, uint32_t out[8], uint8_t* text0, uint8_t* text1, uint32_t cap) {
+// diagnostics (not part of the public header): how the segments of all steps so far were settled
+// out[0] redone sequentially, [1] folded from the bulk kernel, [2] usage records read from template spans, [3] usage events stashed
+extern "C" int lgw_debug_counters(lgw_engine* e, uint32_t out[4]) {
     if (!e || !out) return LGW_ERR_ARG;
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
-    TemplateCache h;
-    CK(e, cudaMemcpy(&h, e->scratch.tpl_cache, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 2; ++i) { out[i] = h.state[i]; out[2 + i] = h.len[i]; out[4 + i] = h.flags[i]; out[6 + i] = h.cls[i]; }
-    if (cap > LGW_TPLC_TEXT) cap = LGW_TPLC_TEXT;
-    if (text0) memcpy(text0, h.text[0], cap);
-    if (text1) memcpy(text1, h.text[1], cap);
+    CK(e, cudaMemcpy(out, e->scratch.counters, 16, cudaMemcpyDeviceToHost));
+    return LGW_OK;
+}
+
+// diagnostics (not part of the public header, like lgw_engine_set_mode): the engine-wide event-template cache
+// out[0..15] = state[4], len[4], flags[4], hits[4]; text = first `cap` bytes of each slot's template (4 x cap bytes)
+extern "C" int lgw_debug_template_cache(lgw_engine* e, uint32_t out[16], uint8_t* text, uint32_t cap) {
+    if (!e || !out) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    std::vector<uint8_t> buf(sizeof(TemplateCache2));
+    CK(e, cudaMemcpy(buf.data(), e->scratch.tpl_cache2, sizeof(TemplateCache2), cudaMemcpyDeviceToHost));
+    const TemplateCache2* h = reinterpret_cast<const TemplateCache2*>(buf.data());
+    for (int i = 0; i < 4; ++i) { out[i] = h->state[i]; out[4 + i] = h->tpl[i].m.len; out[8 + i] = h->tpl[i].m.flags | (h->tpl[i].m.usage_ok << 31); out[12 + i] = h->hits[i]; }
+    if (cap > R2_TEXT) cap = R2_TEXT;
+    if (text) for (int i = 0; i < 4; ++i) memcpy(text + (size_t)i * cap, h->tpl[i].text, cap);
     return LGW_OK;
 }

@@ -1,0 +1,1157 @@
+// Bulk path of the SSE step, round 2:  k_prime2 -> k_relay2 -> k_commit2 -> k_usage_extract.
+// (included from sse_kernels.cuh, inside namespace lgw)
+//
+// What changed against round 1 (relay_kernels.cuh, thread-per-chunk walk of a staged tile):
+//   * The re-emit is done by the TMA engine: every warp owns a contiguous byte range and runs its own ring of
+//     4 KiB shared-memory buffers -- cp.async.bulk global -> shared (mbarrier complete_tx), cp.async.bulk shared ->
+//     global straight from the same buffer.  No byte of the copy passes through a register.
+//   * The parse is warp-cooperative and driven by bytes, not by chunks: 16 bytes per lane, 512 bytes per pass.  SSE
+//     deltas of a stream are the same JSON skeleton over and over, so the event text is compared against a PERIODIC
+//     image of a validated event template (text ++ LF LF ++ text ...): one unaligned 16-byte load of the image per lane
+//     (16 pre-shifted copies of the default template in shared memory make it an aligned LDS.128), one XOR/AND per word
+//     against the literal mask, a SWAR test of the bytes that lie in string-value spans (control, quote, backslash)
+//     and one ballot.  A pass that matches proves the boundaries and the validity of every event it covers
+//     (the LF LF separators are literal bytes of the image).  A mismatch is classified by its template offset: inside
+//     a string or number VALUE span the value's own end is found (ballot scan for the closing quote, number automaton)
+//     and the comparison is re-anchored behind it; anywhere else the event is tried against the other template slots
+//     and finally walked by the byte-wise recogniser (lean_json.cuh).  Same judgement as round 1's matcher: an event
+//     that equals a template outside value spans, holds plain bytes / valid escapes inside string spans and a valid JSON
+//     number in number spans drives the recogniser through the same states as the template.
+//   * Usage extraction is on the clock: an event that follows a usage-bearing template has its eight fields read
+//     straight from the value spans the match located (number text -> decimal.cuh, strings decoded like the full
+//     machine does) into a per-segment candidate record that k_commit2 installs.  Usage events without such a template
+//     are stashed as before and settled by k_usage_extract at the end of the same step.
+//
+// Regular streams -- committed (or committing on their first chunk), carries empty and equal at the start of the bulk
+// region, every chunk valid UTF-8 and non-empty, no run of three or more LFs, no event the tap turns into an extra row
+// ("error"), at most one usage event per step, no event longer than the carry capacity -- are exactly the streams for
+// which the reference's chunk-by-chunk split (request_handler.py:111-115, chat_logging.py:108-112) equals a split of
+// the CONCATENATED text on every LF LF pair.  Everything else is flagged irregular and redone by k_commit2 with the
+// exact sequential machine, so the result never depends on which path ran (tests run both and the oracle).
+//
+// The file also compiles with g++ against tests/support/simt_emu.h (fibers as lanes) so that the CPU test-suite can run
+// these very kernels; that build is a test aid, the product has no CPU path.
+#pragma once
+
+#if defined(__CUDACC__)
+#define R2_DEV __device__ __forceinline__
+#define R2_MEM __device__ __forceinline__
+#define R2_DEV_NOINLINE __device__ __noinline__
+#define R2_GLOBAL __global__
+#define R2_TID (threadIdx.x)
+#define R2_BID (blockIdx.x)
+#define R2_NBLK (gridDim.x)
+#define R2_NTHR (blockDim.x)
+#define R2_HOST_EMU 0
+#else
+#define R2_DEV static inline
+#define R2_MEM inline
+#define R2_DEV_NOINLINE static
+#define R2_GLOBAL static
+#define R2_TID (simt::tid())
+#define R2_BID (simt::bid())
+#define R2_NBLK (simt::nblocks())
+#define R2_NTHR (simt::nthreads())
+#define R2_HOST_EMU 1
+#endif
+
+#define R2_WARPS 16u
+#define R2_THREADS (R2_WARPS * 32u)
+#define R2_TILE 4096u
+#define R2_NBUF 3u
+#define R2_SLOTS 4u
+#define R2_TPL_MAX 504u                 /* longest event kept as a template (text without its LF LF) */
+#define R2_TPL_MIN 16u
+#define R2_TEXT 544u                    /* periodic image: period <= 506, + 16 + 15 bytes of run-over, rounded to 16 */
+#define R2_SPANS 32u
+#define R2_FULL 0xFFFFFFFFu
+#define R2_NONE 0xFFFFFFFFu
+#define R2_MAX_STR 8192u                /* longest string value the matcher follows (as in round 1) */
+
+struct TplMeta {
+    uint32_t len, P, recip, flags, cls, n_spans, usage_ok, full_flags;
+    uint16_t sstart[R2_SPANS], send[R2_SPANS];     // value span: first content byte / first number char .. closing quote / terminator
+    uint8_t skind[R2_SPANS];                       // 0 string value, 1 number value
+    uint8_t field_span[8];                         // usage field (UsageField) -> span id, 0xff: the template's own value
+};
+struct Tpl2 {
+    TplMeta m;
+    uint8_t text[R2_TEXT];       // periodic image: text ++ LF LF ++ text ...
+    uint8_t lit[R2_TEXT];        // 0xff: byte must equal the image; 0x00: content of a string value span
+    uint8_t span_id[R2_TPL_MAX + 8];   // per text position: id of the value span it belongs to (sstart..send inclusive), 0xff none
+};
+// Event templates survive across launches (any validated event is a sound template wherever it came from).
+// state: 0 empty, 1 being written, 2 ready.
+struct TemplateCache2 {
+    uint32_t state[R2_SLOTS];
+    uint32_t hits[R2_SLOTS];         // events matched per slot (decayed in k_prime2)
+    uint32_t general;                // events that matched no slot
+    uint32_t lock;                   // publication lock
+    uint32_t _pad[2];
+    Tpl2 tpl[R2_SLOTS];
+    UsageRaw raw[R2_SLOTS];          // the template event's own UsageRaw (usage_ok slots)
+};
+
+// ---- shared memory of k_relay2 -------------------------------------------------------------------------------------
+struct R2Shared {
+    alignas(16) uint8_t fast_text[16 * R2_TEXT];     // default slot: copy c holds image[c ..], so image[t .. t+16) is an aligned vector of copy t & 15
+    alignas(16) uint8_t fast_lit[16 * R2_TEXT];
+    alignas(16) Tpl2 tpl[R2_SLOTS];
+    alignas(8) unsigned long long mbar[R2_WARPS * R2_NBUF];
+    uint32_t slot_state[R2_SLOTS];                   // 0 empty, 1 being built, 2 ready
+    uint32_t hits[R2_SLOTS];
+    uint32_t general;
+    uint32_t dflt, fast_ready;
+    uint32_t learn_lock;                             // one warp of the block learns a template at a time
+    alignas(4) uint8_t cls[256];
+    alignas(4) uint8_t trans[LGW_LEAN_ROWS * 32];
+};
+#define R2_RING_BYTES (R2_WARPS * R2_NBUF * R2_TILE)
+#define R2_SMEM_BYTES (R2_RING_BYTES + sizeof(R2Shared) + 128)
+
+// ---- platform layer: shared-window addresses, TMA, mbarrier ----------------------------------------------------------
+#if !R2_HOST_EMU
+typedef uint32_t SPtr;                         // 32-bit shared-window address
+R2_DEV SPtr sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+R2_DEV uint4 sld128(SPtr a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+R2_DEV uint32_t sld32(SPtr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+R2_DEV uint32_t sld8(SPtr a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+R2_DEV void sst8(SPtr a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+R2_DEV uint4 gld128(const uint8_t* p) { uint4 v; asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+R2_DEV void mbar_init(SPtr a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(n)); }
+R2_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+R2_DEV void mbar_expect(SPtr a, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory"); }
+R2_DEV void mbar_wait(SPtr a, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(a), "r"(parity) : "memory");
+}
+R2_DEV void tma_load(SPtr dst, const void* src, uint32_t bytes, SPtr mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+R2_DEV void tma_store(void* dst, SPtr src, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;\ncp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+R2_DEV void tma_store_commit_empty() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+R2_DEV void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+R2_DEV void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+R2_DEV uint8_t* smem_base() { extern __shared__ __align__(128) uint8_t r2_smem[]; return r2_smem; }
+#else
+typedef uint8_t* SPtr;
+R2_DEV SPtr sptr(const void* p) { return (uint8_t*)p; }
+R2_DEV uint4 sld128(SPtr a) { uint4 v; memcpy(&v, a, 16); return v; }
+R2_DEV uint32_t sld32(SPtr a) { uint32_t v; memcpy(&v, a, 4); return v; }
+R2_DEV uint32_t sld8(SPtr a) { return *a; }
+R2_DEV void sst8(SPtr a, uint32_t v) { *a = (uint8_t)v; }
+R2_DEV uint4 gld128(const uint8_t* p) { uint4 v; memcpy(&v, p, 16); return v; }
+R2_DEV void mbar_init(SPtr a, uint32_t) { memset(a, 0, 8); }
+R2_DEV void mbar_fence_init() {}
+R2_DEV void mbar_expect(SPtr, uint32_t) {}
+R2_DEV void mbar_wait(SPtr, uint32_t) {}
+R2_DEV void tma_load(SPtr dst, const void* src, uint32_t bytes, SPtr) { memcpy(dst, src, bytes); }
+R2_DEV void tma_store(void* dst, SPtr src, uint32_t bytes) { memcpy(dst, src, bytes); }
+R2_DEV void tma_store_commit_empty() {}
+R2_DEV void tma_wait_read1() {}
+R2_DEV void tma_wait_all() {}
+R2_DEV uint8_t* smem_base() { return simt::g_dyn_smem; }
+#endif
+R2_DEV uint32_t r2_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+R2_DEV uint32_t r2_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// bit 7 of every byte: set <=> the byte is plain string content (>= 0x20, not '"', not '\\'; bytes >= 0x80 are plain) or lies
+// outside a string span (m byte = 0xff)
+R2_DEV uint32_t span_ok(uint32_t w, uint32_t m) {
+    const uint32_t w7 = w & 0x7f7f7f7fu;
+    const uint32_t a = w7 + 0x60606060u;
+    const uint32_t b = (w7 ^ 0x22222222u) + 0x7f7f7f7fu;
+    const uint32_t c = (w7 ^ 0x5c5c5c5cu) + 0x7f7f7f7fu;
+    return (a & b & c) | w | m;
+}
+// bit 7 of every byte: set <=> byte != 0
+R2_DEV uint32_t nonzero_bytes(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
+// bits 7/15/23/31 -> bits 0..3
+R2_DEV uint32_t movemask4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+// 16-bit mask of the bytes of a vector equal to LF
+R2_DEV uint32_t lf_mask16(const uint4& d) {
+    const uint32_t a = ~nonzero_bytes(d.x ^ 0x0a0a0a0au) & 0x80808080u, b = ~nonzero_bytes(d.y ^ 0x0a0a0a0au) & 0x80808080u;
+    const uint32_t c = ~nonzero_bytes(d.z ^ 0x0a0a0a0au) & 0x80808080u, e = ~nonzero_bytes(d.w ^ 0x0a0a0a0au) & 0x80808080u;
+    return movemask4(a) | (movemask4(b) << 4) | (movemask4(c) << 8) | (movemask4(e) << 12);
+}
+
+// ---- per-warp context --------------------------------------------------------------------------------------------------
+struct R2Ctx {
+    const StepArgs* a;
+    R2Shared* sh;
+    uint32_t lane;
+    // pipeline
+    SPtr ring; SPtr bars;
+    uint32_t base;               // byte offset of this warp's tile 0 (16-byte aligned)
+    uint32_t n_tiles;            // tiles of the range
+    uint32_t k;                  // resident tile (R2_NONE before the first)
+    uint32_t tile_lo, tile_hi;   // bytes of the resident tile [tile_lo, tile_hi): tile_hi is clamped to n_bytes
+    SPtr buf;                    // its buffer
+    uint32_t n_bytes;            // end of the valid bytes
+    // segment
+    uint32_t seg, tb, te, kept_end;    // text of the current segment [tb, te); kept_end: end of the speculatively kept chunk (0: none)
+    uint32_t in_kept, primed;
+    uint32_t ev_a, ev_b, a_usage;
+    uint32_t high;               // some byte >= 0x80 was seen in the current segment's text
+    uint32_t walk_lo;            // first text position this warp walked in the current segment
+    // matcher
+    uint32_t slot, t, pos, s_open, tried;
+    uint32_t dflt, fast;         // default (periodic) slot of the block; its pre-shifted copies are ready
+    uint32_t ready, free_slots;  // bit per slot: template usable / slot empty (refreshed by refresh_slots, the same in every lane)
+    uint32_t last_ra;            // position of the last number re-anchor (a mismatch right there is final)
+    uint32_t hits_d;             // events matched by the default slot
+    UsageRaw* block_raw;         // [R2_SLOTS] the block's template events' own UsageRaw (global scratch)
+    UsageRaw* warp_raw;          // this warp's assembly buffer (global scratch)
+    // usage extraction while following a usage_ok template: this lane's field
+    uint32_t f_delta, f_len;
+};
+
+R2_DEV uint8_t ring_byte(const R2Ctx& c, uint32_t p) {
+    const uint32_t d = p - c.tile_lo;
+    if (p >= c.tile_lo && d < c.tile_hi - c.tile_lo) return (uint8_t)sld8(c.buf + d);
+    return p < c.n_bytes ? __ldg(c.a->data + p) : (uint8_t)0;
+}
+// byte source for the single-lane walks (recogniser, template builder): the resident tile, global memory outside it
+struct R2Bytes {
+    const R2Ctx* c;
+    R2_MEM uint32_t at(uint32_t p) const { return ring_byte(*c, p); }
+    R2_MEM uint32_t cls(uint32_t ch) const { return c->sh->cls[ch]; }
+    R2_MEM uint32_t trans(uint32_t i) const { return c->sh->trans[i]; }
+};
+// 16 bytes at the 16-byte aligned position p: resident tile, else global memory; bytes at or after n_bytes read as 0
+R2_DEV uint4 ld16(const R2Ctx& c, uint32_t p) {
+    if (p >= c.tile_lo && p + 16 <= c.tile_hi) return sld128(c.buf + (p - c.tile_lo));
+    if (p + 16 <= c.n_bytes) return gld128(c.a->data + p);
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < 16 && p + i < c.n_bytes; ++i) w[i >> 2] |= (uint32_t)ring_byte(c, p + i) << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- pipeline ----------------------------------------------------------------------------------------------------------
+R2_DEV uint32_t tile_bytes(const R2Ctx& c, uint32_t k) {              // valid bytes of tile k
+    const uint32_t lo = c.base + k * R2_TILE;
+    return c.n_bytes - lo < R2_TILE ? c.n_bytes - lo : R2_TILE;
+}
+R2_DEV void pipe_issue_load(const R2Ctx& c, uint32_t k) {            // lane 0
+    const uint32_t b = k % R2_NBUF, n16 = tile_bytes(c, k) & ~15u;
+    if (n16) { mbar_expect(c.bars + 8 * b, n16); tma_load(c.ring + b * R2_TILE, c.a->data + c.base + k * R2_TILE, n16, c.bars + 8 * b); }
+}
+R2_DEV void pipe_start(R2Ctx& c) {
+    c.k = R2_NONE; c.tile_lo = c.tile_hi = c.base; c.buf = c.ring;
+    if (c.lane == 0) for (uint32_t k = 0; k < R2_NBUF - 1 && k < c.n_tiles; ++k) pipe_issue_load(c, k);
+}
+// make tile k resident (k = previous + 1): wait for its bytes, hand it to the store engine, refill the buffer that just became free
+R2_DEV void pipe_advance(R2Ctx& c) {
+    const uint32_t k = c.k == R2_NONE ? 0u : c.k + 1u;
+    __syncwarp();                                   // every lane is done with the buffers of the earlier tiles
+    const uint32_t b = k % R2_NBUF, nb = tile_bytes(c, k), n16 = nb & ~15u;
+    c.k = k; c.tile_lo = c.base + k * R2_TILE; c.tile_hi = c.tile_lo + nb; c.buf = c.ring + b * R2_TILE;
+    if (n16) mbar_wait(c.bars + 8 * b, (k / R2_NBUF) & 1u);
+    if (nb != n16) {                                // ragged end of the buffer: the last bytes move by hand
+        const uint32_t i = n16 + c.lane;
+        if (c.lane < 16) {
+            const uint32_t v = i < nb ? (uint32_t)__ldg(c.a->data + c.tile_lo + i) : 0u;
+            sst8(c.buf + i, v);
+            if (i < nb) c.a->out[c.tile_lo + i] = (uint8_t)v;
+        }
+        __syncwarp();
+    }
+    if (c.lane == 0) {
+        if (n16) tma_store(c.a->out + c.tile_lo, c.buf, n16); else tma_store_commit_empty();
+        tma_wait_read1();                           // the store of tile k-1 has read its buffer
+        const uint32_t kn = k + R2_NBUF - 1;
+        if (kn < c.n_tiles) pipe_issue_load(c, kn);
+    }
+}
+
+// ---- templates ---------------------------------------------------------------------------------------------------------
+// image[t .. t+16) of slot `slot` and its literal mask
+R2_DEV void tpl_vec(const R2Ctx& c, uint32_t slot, uint32_t t, uint4& tx, uint4& mk) {
+    if (slot == c.dflt && c.fast) {
+        const uint32_t ad = (t & 15u) * R2_TEXT + (t & ~15u);
+        tx = sld128(sptr(c.sh->fast_text) + ad); mk = sld128(sptr(c.sh->fast_lit) + ad);
+        return;
+    }
+    const SPtr tp = sptr(c.sh->tpl[slot].text) + (t & ~3u), lp = sptr(c.sh->tpl[slot].lit) + (t & ~3u);
+    const uint32_t sh = 8 * (t & 3u);
+    const uint32_t a0 = sld32(tp), a1 = sld32(tp + 4), a2 = sld32(tp + 8), a3 = sld32(tp + 12), a4 = sld32(tp + 16);
+    const uint32_t b0 = sld32(lp), b1 = sld32(lp + 4), b2 = sld32(lp + 8), b3 = sld32(lp + 12), b4 = sld32(lp + 16);
+    tx = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh));
+    mk = make_uint4(__funnelshift_r(b0, b1, sh), __funnelshift_r(b1, b2, sh), __funnelshift_r(b2, b3, sh), __funnelshift_r(b3, b4, sh));
+}
+
+// the 16 pre-shifted copies of slot `slot` (whole warp)
+R2_DEV void build_fast_tables(R2Shared* sh, uint32_t slot, uint32_t lane, uint32_t step) {
+    const Tpl2& tp = sh->tpl[slot];
+    const uint32_t P = tp.m.P;
+    for (uint32_t i = lane; i < 16 * R2_TEXT; i += step) {
+        const uint32_t cpy = i / R2_TEXT, j = i - cpy * R2_TEXT;
+        uint32_t x = j + cpy; while (x >= P) x -= P;
+        sh->fast_text[i] = tp.text[x]; sh->fast_lit[i] = tp.lit[x];
+    }
+}
+
+// One lane validates the event [ps, LF LF) and, when it qualifies, fills `tp` with it.  limit = end of the segment's text.
+template <class RD>
+R2_DEV_NOINLINE bool build_template2(const RD& rd, Tpl2* tp, UsageRaw* raw_out, uint32_t ps, uint32_t limit) {
+    uint32_t cls = PC_NONE;
+    const uint32_t c0 = rd.at(ps);
+    if (c0 == '{') cls = PC_BRACE;
+    else if (c0 == 'd' && rd.at(ps + 1) == 'a' && rd.at(ps + 2) == 't' && rd.at(ps + 3) == 'a' && rd.at(ps + 4) == ':' && rd.at(ps + 5) == ' ' && rd.at(ps + 6) == '{') cls = PC_DATA;
+    if (cls == PC_NONE) return false;
+    TplMeta& m = tp->m;
+    LeanMachine lm;
+    lm.reset(cls == PC_DATA);
+    const uint32_t skip = cls == PC_DATA ? 6u : 0u;
+    for (uint32_t k = 0; k < R2_TPL_MAX + 8; ++k) tp->span_id[k] = 0xff;
+    for (uint32_t k = 0; k < R2_TEXT; ++k) tp->lit[k] = 0xff;
+    uint32_t pos = ps + skip, n_ids = 0, cur_s = 0xff, cur_n = 0xff;
+    for (;;) {
+        if (pos + 1 >= limit || pos - ps >= R2_TPL_MAX) return false;
+        const uint32_t c = rd.at(pos);
+        if (c == '\n' && rd.at(pos + 1) == '\n') break;
+        const uint32_t prev = lm.st;
+        const bool in_str = (prev == L_STR || prev == L_STR_ESC || prev == L_STR_U) && !lm.in_key;
+        const bool in_num = prev >= L_NUM_MINUS && prev <= L_NUM_EXP;
+        const uint32_t x = pos - ps;
+        if (in_str && cur_s != 0xff) {
+            tp->span_id[x] = (uint8_t)cur_s;
+            if (prev == L_STR && c == '"') m.send[cur_s] = (uint16_t)x;         // the closing quote: literal
+            else tp->lit[x] = 0x00;                                              // content
+        }
+        lm.step(c, pos, rd);
+        const bool now_num = lm.st >= L_NUM_MINUS && lm.st <= L_NUM_EXP;
+        if (in_num && cur_n != 0xff) {
+            tp->span_id[x] = (uint8_t)cur_n;                                    // number characters and the terminator
+            if (!now_num) { m.send[cur_n] = (uint16_t)x; cur_n = 0xff; }
+        }
+        if (prev < LGW_LEAN_ROWS && lm.st == L_STR && !lm.in_key) {              // a string VALUE opens
+            cur_s = n_ids < R2_SPANS ? n_ids++ : 0xffu;
+            if (cur_s != 0xff) { m.skind[cur_s] = 0; m.sstart[cur_s] = (uint16_t)(x + 1); m.send[cur_s] = 0xffff; }
+        }
+        if (!in_num && now_num) {                                               // a number opens
+            cur_n = n_ids < R2_SPANS ? n_ids++ : 0xffu;
+            if (cur_n != 0xff) { m.skind[cur_n] = 1; m.sstart[cur_n] = (uint16_t)x; m.send[cur_n] = 0xffff; tp->span_id[x] = (uint8_t)cur_n; }
+        }
+        if (lm.st == L_ERR) return false;
+        ++pos;
+    }
+    const uint32_t f = lm.finish();
+    if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL | TK_CODE))) return false;
+    if (pos + 2 < limit && rd.at(pos + 2) == '\n') return false;
+    const uint32_t len = pos - ps;
+    if (len < R2_TPL_MIN) return false;
+    for (uint32_t k = 0; k < n_ids; ++k) if (m.send[k] >= len) return false;        // every span must be closed inside the event
+    const uint32_t P = len + 2;
+    for (uint32_t k = 0; k < R2_TEXT; ++k) {
+        uint32_t x = k; while (x >= P) x -= P;
+        tp->text[k] = x < len ? (uint8_t)rd.at(ps + x) : (uint8_t)'\n';
+        if (k >= len) tp->lit[k] = x < len ? tp->lit[x] : (uint8_t)0xff;
+    }
+    m.len = len; m.P = P; m.recip = (uint32_t)((0x100000000ull + P - 1) / P); m.flags = f; m.cls = cls; m.n_spans = n_ids;
+    m.usage_ok = 0; m.full_flags = 0;
+    for (uint32_t k = 0; k < 8; ++k) m.field_span[k] = 0xff;
+    if (f & TK_USAGE) {
+        // the full machine over the template, tracking where the eight usage fields sit: events that follow the template
+        // can then have their fields read straight from the matched value spans
+        JsonMachine<true> jm; ValueTrack trk; trk.reset();
+        jm.reset(raw_out, cls == PC_DATA); jm.trk = &trk;
+        for (uint32_t i = skip; i < len; ++i) { trk.pos = i; jm.feed(rd.at(ps + i)); if (jm.failed()) break; }
+        const uint32_t ff = jm.finish();
+        m.full_flags = ff;
+        bool ok = !jm.failed() && (ff & PF_VALID_B) && !(ff & PF_EXOTIC) && !((ff & TK_CHOICES) && (ff & PF_TYPE_ERROR)) && !trk.dup && n_ids <= R2_SPANS;
+        if (ok && (ff & TK_CHOICES)) for (uint32_t k = 0; k < n_ids; ++k) if (m.send[k] >= trk.choices_lo && m.sstart[k] <= trk.choices_hi) ok = false;
+        for (uint32_t fi = 0; ok && fi < UF_N; ++fi) {
+            if (trk.fstart[fi] == 0xFFFFFFFFu) continue;                          // field absent: the template's (absent) value stands
+            uint32_t j = 0xff;
+            for (uint32_t k = 0; k < n_ids; ++k) {
+                if (m.skind[k] == 1 && m.sstart[k] == trk.fstart[fi] && m.send[k] == trk.fend[fi]) j = k;
+                if (m.skind[k] == 0 && (uint32_t)m.sstart[k] == trk.fstart[fi] + 1 && (uint32_t)m.send[k] + 1 == trk.fend[fi]) j = k;
+            }
+            if (j != 0xff && (m.skind[j] == 1) != (fi < UF_MODEL)) ok = false;      // a string where a number goes (or the reverse): not modelled here
+            m.field_span[fi] = (uint8_t)j;
+            // a field whose value is not a span (null, true, a container ...) is part of the literal text: same value in every match
+            if (j == 0xff) for (uint32_t k = 0; k < n_ids; ++k) if (m.sstart[k] < trk.fend[fi] && m.send[k] >= trk.fstart[fi]) ok = false;   // spans inside a container value
+        }
+        m.usage_ok = ok ? 1u : 0u;
+    }
+    return true;
+}
+
+// ---- field extraction from matched value spans (usage_ok templates) ---------------------------------------------------------
+// number text [p, p+n) (already validated by the number automaton) -> value exactly as json_machine.cuh reads it
+template <class RD>
+R2_DEV_NOINLINE Val parse_number_span(const RD& rd, uint32_t p, uint32_t n) {
+    DecAcc num; num.reset();
+    uint32_t i = 0;
+    if (i < n && rd.at(p) == '-') { num.neg = 1; ++i; }
+    for (; i < n; ++i) { const uint32_t c = rd.at(p + i); if (c - '0' >= 10u) break; num.digit(c - '0', false); }
+    if (i < n && rd.at(p + i) == '.') { ++i; for (; i < n; ++i) { const uint32_t c = rd.at(p + i); if (c - '0' >= 10u) break; num.is_float = 1; num.digit(c - '0', true); } }
+    if (i < n && (rd.at(p + i) | 0x20u) == 'e') {
+        num.is_float = 1; ++i;
+        if (i < n && rd.at(p + i) == '+') ++i; else if (i < n && rd.at(p + i) == '-') { num.exp_neg = 1; ++i; }
+        for (; i < n; ++i) num.exp_digit(rd.at(p + i) - '0');
+    }
+    uint8_t kind; int64_t bits; bool truthy;
+    num.finish(kind, bits, truthy);
+    Val v; v.kind = kind; v.bits = bits;
+    return v;
+}
+// string content [p, p+n) (validated: plain bytes and valid escapes) -> the capture json_machine.cuh makes of it
+template <class RD>
+R2_DEV_NOINLINE void decode_string_span(const RD& rd, uint32_t p, uint32_t n, char* dst, uint8_t& dlen, uint8_t& dflags) {
+    uint32_t len = 0, flags = 0, pending_high = 0;
+    auto put = [&](uint32_t b) { if (len < LGW_STR_CAP) dst[len++] = (char)b; else flags |= 1; };
+    auto put_cp = [&](uint32_t cp) {
+        if (cp < 0x80) put(cp);
+        else if (cp < 0x800) { put(0xC0 | (cp >> 6)); put(0x80 | (cp & 63)); }
+        else if (cp < 0x10000) { put(0xE0 | (cp >> 12)); put(0x80 | ((cp >> 6) & 63)); put(0x80 | (cp & 63)); }
+        else { put(0xF0 | (cp >> 18)); put(0x80 | ((cp >> 12) & 63)); put(0x80 | ((cp >> 6) & 63)); put(0x80 | (cp & 63)); }
+    };
+    auto flush_high = [&]() { if (pending_high) { flags |= 2; pending_high = 0; } };
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t c = rd.at(p + i);
+        if (c != '\\') { flush_high(); put(c); continue; }
+        const uint32_t e = rd.at(p + ++i);
+        if (e != 'u') { c = e == 'b' ? 8u : e == 'f' ? 12u : e == 'n' ? 10u : e == 'r' ? 13u : e == 't' ? 9u : e; flush_high(); put(c); continue; }
+        uint32_t cp = 0;
+        for (int d = 0; d < 4; ++d) { const uint32_t h = rd.at(p + ++i); cp = (cp << 4) | (h - '0' < 10u ? h - '0' : (h | 0x20u) - 'a' + 10u); }
+        if (cp < 0x80) { flush_high(); put(cp); }
+        else if (cp >= 0xD800 && cp <= 0xDBFF) { flush_high(); pending_high = cp; }
+        else if (cp >= 0xDC00 && cp <= 0xDFFF) { if (pending_high) { put_cp(0x10000 + ((pending_high - 0xD800) << 10) + (cp - 0xDC00)); pending_high = 0; } else flags |= 2; }
+        else { flush_high(); put_cp(cp); }
+    }
+    flush_high();
+    dlen = (uint8_t)len; dflags = (uint8_t)flags;
+}
+
+// ---- helpers of the walk ---------------------------------------------------------------------------------------------------
+R2_DEV void flush_counts(R2Ctx& c) {
+    if (c.lane == 0 && c.seg != R2_NONE) {
+        SegPlan* pl = c.a->s.plan + c.seg;
+        if (c.ev_a) atomicAdd(&pl->n_events_a, c.ev_a);
+        if (c.ev_b) atomicAdd(&pl->n_events_b, c.ev_b);
+        if (c.a_usage) pl->a_usage = 1;
+    }
+    c.ev_a = c.ev_b = c.a_usage = 0;
+}
+R2_DEV void mark_irregular(R2Ctx& c) { if (c.lane == 0 && c.seg != R2_NONE) c.a->s.plan[c.seg].irregular = 1; }
+
+// one complete event [ps, e) of class cls with recogniser flags f (e = position of its LF LF).  Returns false when the
+// stream has to go to the sequential path.
+R2_DEV bool account_event(R2Ctx& c, uint32_t cls, uint32_t f, uint32_t n, uint32_t ps, uint32_t e) {
+    if (cls == PC_NONE) return true;
+    if (cls == PC_DATA) {
+        if (c.in_kept) {                                      // priming loop on the kept chunk, request_handler.py:82-91
+            if (!c.primed) { if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) return false; c.primed = 1; }
+        } else {                                              // handler loop, request_handler.py:122-134
+            c.ev_a += n;
+            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) c.a_usage = 1;
+        }
+    }
+    if (f & PF_VALID_B) {                                     // tap loop, chat_logging.py:123-141
+        c.ev_b += n;
+        if (f & TK_ERROR) return false;                       // extra DB row: sequential path
+        if (f & TK_USAGE) {
+            if (c.lane == 0) {
+                SegPlan* pl = c.a->s.plan + c.seg;
+                atomicAdd(&pl->n_usage_b, n);
+                atomicMax(&pl->last_usage, ((unsigned long long)(ps + 1) << 32) | (e - ps));
+            }
+        }
+    }
+    return true;
+}
+
+// chunk-level UTF-8 (request_handler.py:111 decodes every chunk on its own): the chunks of segment `seg` that overlap [lo, hi)
+R2_DEV_NOINLINE bool chunks_utf8_ok(const R2Ctx& c, uint32_t seg, uint32_t lo, uint32_t hi) {
+    const StepArgs& a = *c.a;
+    uint32_t c0 = __ldg(a.seg_chunk + seg), c1 = __ldg(a.seg_chunk + seg + 1);
+    {   // first chunk that ends after lo
+        uint32_t l = c0, h = c1;
+        while (l < h) { const uint32_t mid = (l + h) >> 1; if (__ldg(a.chunk_off + mid + 1) <= lo) l = mid + 1; else h = mid; }
+        c0 = l;
+    }
+    bool ok = true;
+    for (uint32_t ch = c0 + c.lane; ch < c1; ch += 32) {
+        const uint32_t o = __ldg(a.chunk_off + ch), e = __ldg(a.chunk_off + ch + 1);
+        if (o >= hi) break;
+        if (e > a.n_bytes) { ok = false; break; }
+        if (!utf8_valid(a.data + o, e - o)) ok = false;
+    }
+    return __all_sync(R2_FULL, ok);
+}
+
+// first LF LF pair at or after `from` whose second LF lies before `end`: position of its first LF, R2_NONE when there is none
+R2_DEV uint32_t find_lflf(R2Ctx& c, uint32_t from, uint32_t end, uint32_t& high) {
+    uint32_t wb = from & ~15u;
+    for (;;) {
+        if (wb >= end) return R2_NONE;
+        const uint32_t lp = wb + 16 * c.lane;
+        const uint4 d = lp < end ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
+        high |= d.x | d.y | d.z | d.w;
+        const uint32_t lf = lf_mask16(d);
+        const uint32_t nxt = __shfl_down_sync(R2_FULL, lf, 1);
+        uint32_t pair = lf & ((lf >> 1) | ((c.lane < 31 ? nxt & 1u : 0u) << 15));      // bit i: LF at i and at i+1
+        if (lp < from) pair &= from - lp >= 16 ? 0u : (0xFFFFu << (from - lp));
+        if (lp + 17 > end) pair &= end <= lp + 1 ? 0u : (0xFFFFu >> (lp + 17 - end));   // the second LF must lie before end
+        const uint32_t any = __ballot_sync(R2_FULL, pair != 0);
+        if (any) {
+            const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+            const uint32_t pr = __shfl_sync(R2_FULL, pair, (int)fl);
+            return wb + 16 * fl + ((uint32_t)__ffs(pr) - 1u);
+        }
+        wb += 31 * 16;                                                                   // the last lane is looked at again (pairs across windows)
+    }
+}
+
+// first byte at or after `from` (before `end`) that is not plain string content: its position, R2_NONE when there is none
+R2_DEV uint32_t find_special(R2Ctx& c, uint32_t from, uint32_t end, uint32_t& high) {
+    uint32_t wb = from & ~15u;
+    for (;;) {
+        if (wb >= end) return R2_NONE;
+        const uint32_t lp = wb + 16 * c.lane;
+        const uint4 d = lp < end ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
+        high |= d.x | d.y | d.z | d.w;
+        uint32_t sp = movemask4(~span_ok(d.x, 0) & 0x80808080u) | (movemask4(~span_ok(d.y, 0) & 0x80808080u) << 4) |
+                      (movemask4(~span_ok(d.z, 0) & 0x80808080u) << 8) | (movemask4(~span_ok(d.w, 0) & 0x80808080u) << 12);
+        if (lp >= end) sp = 0;
+        if (lp < from) sp &= from - lp >= 16 ? 0u : (0xFFFFu << (from - lp));
+        if (lp + 16 > end) sp &= 0xFFFFu >> (lp + 16 - end);
+        const uint32_t any = __ballot_sync(R2_FULL, sp != 0);
+        if (any) {
+            const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+            const uint32_t s = __shfl_sync(R2_FULL, sp, (int)fl);
+            return wb + 16 * fl + ((uint32_t)__ffs(s) - 1u);
+        }
+        wb += 512;
+    }
+}
+
+// the recogniser over one event starting at ps (single lane does the walk): finds its LF LF (e) or runs into `end`.
+// out: cls, flags; returns e, or R2_NONE when the event is still open at `end`.
+R2_DEV_NOINLINE uint32_t lean_event(R2Ctx& c, uint32_t ps, uint32_t end, uint32_t& cls_out, uint32_t& f_out, uint32_t& high) {
+    uint32_t e = R2_NONE, cls = PC_NONE, f = 0, hi = 0;
+    if (c.lane == 0) {
+        R2Bytes rd{&c};
+        const uint32_t c0 = ps < end ? rd.at(ps) : 0u;
+        if (c0 == '{') cls = PC_BRACE;
+        else if (c0 == 'd' && ps + 7 <= end && rd.at(ps + 1) == 'a' && rd.at(ps + 2) == 't' && rd.at(ps + 3) == 'a' && rd.at(ps + 4) == ':' && rd.at(ps + 5) == ' ' && rd.at(ps + 6) == '{') cls = PC_DATA;
+        LeanMachine lm; lm.reset(cls == PC_DATA);
+        uint32_t pos = ps;
+        const uint32_t body = ps + (cls == PC_DATA ? 6u : 0u);
+        for (; pos < end; ++pos) {
+            const uint32_t ch = rd.at(pos);
+            hi |= ch;
+            if (ch == '\n' && pos + 1 < end && rd.at(pos + 1) == '\n') { e = pos; break; }
+            if (cls != PC_NONE && pos >= body) lm.step(ch, pos, rd);
+        }
+        if (e != R2_NONE && cls != PC_NONE) f = lm.finish();
+    }
+    e = __shfl_sync(R2_FULL, e, 0); cls_out = __shfl_sync(R2_FULL, cls, 0); f_out = __shfl_sync(R2_FULL, f, 0);
+    high |= __shfl_sync(R2_FULL, hi, 0);
+    return e;
+}
+
+// Slot states as one lane sees them, handed to all (other warps of the block publish templates while this one runs; every
+// lane of a warp must act on the same view).
+R2_DEV void refresh_slots(R2Ctx& c) {
+    uint32_t r = 0, f = 0, fast = 0;
+    if (c.lane == 0) {
+        for (uint32_t k = 0; k < R2_SLOTS; ++k) { const uint32_t st = *(volatile uint32_t*)&c.sh->slot_state[k]; if (st == 2u) r |= 1u << k; else if (st == 0u) f |= 1u << k; }
+        fast = *(volatile uint32_t*)&c.sh->fast_ready;
+    }
+    c.ready = __shfl_sync(R2_FULL, r, 0); c.free_slots = __shfl_sync(R2_FULL, f, 0); c.fast = __shfl_sync(R2_FULL, fast, 0);
+}
+// ---- template learning ---------------------------------------------------------------------------------------------------------
+R2_DEV bool tpl_same(const Tpl2& x, const Tpl2& y) {
+    if (x.m.len != y.m.len || x.m.cls != y.m.cls) return false;
+    for (uint32_t k = 0; k < x.m.len; ++k) if (x.lit[k] != y.lit[k] || (x.lit[k] && x.text[k] != y.text[k])) return false;
+    return true;
+}
+// The event [ps, LF LF) was walked by the recogniser and is valid: install it in a free slot of this block and, when the
+// engine-wide cache has room and does not hold the same skeleton yet, publish it there.  One warp of a block learns at a
+// time, and not when another warp has just made a template ready that this event was not tried against (it may be the very
+// same skeleton: in a cold step every warp meets the first delta at the same moment).
+R2_DEV_NOINLINE void learn_template(R2Ctx& c, uint32_t ps, uint32_t end) {
+    R2Shared* sh = c.sh;
+    uint32_t got = 0;
+    if (c.lane == 0) got = atomicCAS(&sh->learn_lock, 0u, 1u) == 0u ? 1u : 0u;
+    got = __shfl_sync(R2_FULL, got, 0);
+    if (!got) return;
+    const uint32_t ready_before = c.ready;
+    refresh_slots(c);
+    uint32_t slot = R2_NONE;
+    if (c.ready == ready_before && c.free_slots) {
+        if (c.lane == 0) {
+            slot = (uint32_t)__ffs(c.free_slots) - 1u;
+            atomicExch(&sh->slot_state[slot], 1u);
+            R2Bytes rd{&c};
+            TemplateCache2* tc = c.a->s.tpl_cache2;
+            UsageRaw* raw = c.block_raw + slot;
+            if (build_template2(rd, &sh->tpl[slot], raw, ps, end)) {
+                if (atomicCAS(&tc->lock, 0u, 1u) == 0u) {                        // (busy: the template stays local to this block for this launch)
+                    bool dup = false; uint32_t dst = R2_NONE;
+                    for (uint32_t k = 0; k < R2_SLOTS; ++k) {
+                        const uint32_t st = *(volatile uint32_t*)&tc->state[k];
+                        if (st == 2u) { if (tpl_same(tc->tpl[k], sh->tpl[slot])) dup = true; }
+                        else if (st == 0u && dst == R2_NONE) dst = k;
+                    }
+                    if (!dup && dst != R2_NONE) {
+                        tc->tpl[dst] = sh->tpl[slot]; tc->raw[dst] = *raw; tc->hits[dst] = 0;
+                        __threadfence();
+                        atomicExch(&tc->state[dst], 2u);
+                    }
+                    __threadfence();
+                    atomicExch(&tc->lock, 0u);
+                }
+            } else { atomicExch(&sh->slot_state[slot], 0u); slot = R2_NONE; }
+        }
+        slot = __shfl_sync(R2_FULL, slot, 0);
+    }
+    if (slot != R2_NONE) {
+        uint32_t need_fast = 0;
+        if (c.lane == 0) need_fast = (slot == sh->dflt && !*(volatile uint32_t*)&sh->fast_ready) ? 1u : 0u;
+        need_fast = __shfl_sync(R2_FULL, need_fast, 0);
+        if (need_fast) {                                                        // a cold block: its first template becomes the default
+            build_fast_tables(sh, slot, c.lane, 32);
+            __threadfence_block();
+            __syncwarp();
+            if (c.lane == 0) *(volatile uint32_t*)&sh->fast_ready = 1u;
+        }
+        __threadfence_block();
+        if (c.lane == 0) atomicExch(&sh->slot_state[slot], 2u);
+    }
+    __syncwarp();
+    if (c.lane == 0) { __threadfence_block(); atomicExch(&sh->learn_lock, 0u); }
+    __syncwarp();
+}
+
+// ---- the walk of one warp over its byte range ------------------------------------------------------------------------------------
+// this lane's usage field: span length and accumulated shift start from the template's own
+R2_DEV void reset_fields(R2Ctx& c, uint32_t slot) {
+    c.f_delta = 0; c.f_len = 0; c.last_ra = R2_NONE;
+    if (slot < R2_SLOTS && c.lane < 8u && (c.ready & (1u << slot))) {
+        const TplMeta& m = c.sh->tpl[slot].m;
+        const uint32_t fj = m.field_span[c.lane];
+        if (fj != 0xffu) c.f_len = (uint32_t)m.send[fj] - (uint32_t)m.sstart[fj];
+    }
+}
+R2_DEV uint32_t next_slot(const R2Ctx& c) {
+    const uint32_t m = c.ready & ~c.tried & ((1u << R2_SLOTS) - 1u);
+    return m ? (uint32_t)__ffs(m) - 1u : R2_SLOTS;
+}
+
+// Enter segment `seg`; `from` = the warp's range start when the segment's bytes begin before it, else the segment's first
+// byte.  Sets the text range and the first event start this warp owns in it; false: the warp owns nothing here.
+R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_hi) {
+    const SegPlan* pl = c.a->s.plan + seg;
+    c.seg = seg; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0; c.in_kept = 0; c.primed = 0;
+    const uint32_t tb = pl->relay_begin, te = pl->seg_end;
+    c.tb = tb; c.te = te;
+    const uint32_t kept = pl->kept_chunk != 0xFFFFFFFFu ? pl->kept_end : 0u;
+    c.kept_end = kept;
+    c.pos = te; c.walk_lo = te;
+    c.slot = c.dflt; c.t = 0; c.tried = 0;
+    if (pl->irregular || tb >= te) return false;
+    if (from <= tb) {
+        if (tb >= range_hi) return false;
+        if (kept) { if (kept > range_hi) { mark_irregular(c); return false; } c.in_kept = 1u; }   // the kept chunk is walked by ONE warp
+        c.pos = c.s_open = c.walk_lo = tb;
+        reset_fields(c, c.slot);
+        return true;
+    }
+    // the range starts inside the segment's text: the event that is open there belongs to the previous warp; ours start
+    // behind the first separator that ends at or after `from`
+    if (from >= te) return false;
+    if (kept && from < kept) return false;                                       // (the warp that owns tb flagged the stream)
+    c.walk_lo = from;
+    const uint32_t p = find_lflf(c, from - tb >= 2u ? from - 2u : tb, te, c.high);
+    if (p == R2_NONE) return false;
+    const uint32_t s = p + 2u;
+    if (s >= range_hi && s != te) return false;                                  // its first event starts in a later range
+    if ((p > tb && ring_byte(c, p - 1) == '\n') || (s < te && ring_byte(c, s) == '\n')) { mark_irregular(c); return false; }   // LF run >= 3
+    if (s >= te) return false;                                                   // the text ends on this separator (the previous warp posts the tail)
+    c.pos = c.s_open = s;
+    reset_fields(c, c.slot);
+    return true;
+}
+
+// first segment whose end lies after `pos` (plans are in byte order)
+R2_DEV uint32_t find_segment(const StepArgs& a, uint32_t pos) {
+    uint32_t lo = 0, hi = a.n_segs;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.s.plan[mid].seg_end <= pos) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// leave the current segment (its text is done as far as this warp is concerned)
+R2_DEV void leave_segment(R2Ctx& c, uint32_t range_hi) {
+    if (c.seg == R2_NONE) return;
+    if (__any_sync(R2_FULL, (c.high & 0x80808080u) != 0)) {
+        if (!chunks_utf8_ok(c, c.seg, c.walk_lo, r2_min(c.te, r2_max(c.pos, range_hi)))) mark_irregular(c);
+    }
+    flush_counts(c);
+    c.seg = R2_NONE;
+}
+
+// usage fields of the event [ps, e) straight from the value spans the match located (usage_ok templates)
+R2_DEV_NOINLINE void extract_usage(R2Ctx& c, const TplMeta& m, uint32_t slot, uint32_t ps) {
+    R2Bytes rd{&c};
+    UsageRaw* raw = c.warp_raw;
+    Val v; v.kind = KD_ABSENT; v.bits = 0;
+    const uint32_t fj = c.lane < 8u ? m.field_span[c.lane] : 0xffu;
+    if (c.lane == 0) *raw = c.block_raw[slot];
+    __syncwarp();
+    if (fj != 0xffu) {
+        const uint32_t fs = ps + m.sstart[fj] + c.f_delta;
+        if (c.lane < UF_MODEL) v = parse_number_span(rd, fs, c.f_len);
+        else if (c.lane == UF_MODEL) decode_string_span(rd, fs, c.f_len, raw->model, raw->model_len, raw->model_flags);
+        else decode_string_span(rd, fs, c.f_len, raw->provider, raw->provider_len, raw->provider_flags);
+    }
+    __syncwarp();
+    for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
+        const unsigned long long vb = __shfl_sync(R2_FULL, (unsigned long long)v.bits, (int)fi);
+        const uint32_t vk = __shfl_sync(R2_FULL, (uint32_t)v.kind, (int)fi);
+        if (c.lane == 0 && m.field_span[fi] != 0xffu) {
+            Val x; x.bits = (int64_t)vb; x.kind = (uint8_t)vk;
+            if (fi == UF_PROMPT) raw->prompt = x; else if (fi == UF_COMPLETION) raw->completion = x; else if (fi == UF_TOTAL) raw->total = x;
+            else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
+        }
+    }
+    if (c.lane == 0) {
+        normalise_usage(*raw, m.full_flags, c.a->s.usage_cand[c.seg]);
+        __threadfence();
+        c.a->s.plan[c.seg].cand_ps = ps + 1u;
+    }
+    __syncwarp();
+}
+
+// Walk the current segment from c.pos.  Returns true when the warp is done (the open event starts in the next warp's
+// range); false when the segment's text is finished for this warp (go on with the next segment).
+R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
+    R2Shared* sh = c.sh;
+    const StepArgs& a = *c.a;
+    const uint32_t lane = c.lane;
+    TemplateCache2* tc = a.s.tpl_cache2;
+    for (;;) {
+        const uint32_t sub_end = c.in_kept ? c.kept_end : c.te;                // the text the current phase may read
+        if (c.pos >= sub_end) {
+            // ---- end of the kept chunk / of the segment's text ----
+            if (c.in_kept) {                                                   // the speculation holds when a real event was accepted
+                if (c.s_open != c.kept_end || !c.primed) { mark_irregular(c); leave_segment(c, range_hi); return false; }   //   and the chunk ends on a separator
+                if (lane == 0) a.s.plan[c.seg].prime_ok = 1;
+                c.in_kept = 0;
+                continue;
+            }
+            if (lane == 0) a.s.plan[c.seg].tail_start = c.s_open;              // the open event is the new carry
+            leave_segment(c, range_hi);
+            return false;
+        }
+        if (c.s_open >= range_hi && c.pos == c.s_open) { leave_segment(c, range_hi); return true; }   // the open event starts in the next warp's range
+        while (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) pipe_advance(c);      // (slow paths may have run ahead of the resident tile)
+
+        if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
+            c.tried |= 1u << c.slot; c.slot = next_slot(c); reset_fields(c, c.slot);
+            continue;
+        }
+        if (c.slot < R2_SLOTS) {
+            const TplMeta& m = sh->tpl[c.slot].m;
+            const uint32_t P = m.P;
+            const bool single = c.slot != c.dflt || (m.flags & TK_USAGE) != 0;
+            // ---- compare pass: up to 512 bytes from pos against the periodic image ----
+            const uint32_t wbase = c.pos & ~15u;
+            uint32_t lim = r2_min(sub_end, wbase + 512u);
+            if (c.pos >= c.tile_lo && c.pos < c.tile_hi) lim = r2_min(lim, c.tile_hi);          // windows do not straddle the resident tile's end
+            if (single) lim = r2_min(lim, c.pos + (P - c.t));                                   // one event, then back to the default slot
+            else if (wbase + 512u > range_hi) {                                                  // stop at the first event boundary in the next range
+                const uint32_t nb = c.pos + (P - c.t);
+                uint32_t b = nb;
+                if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
+                lim = r2_min(lim, b);
+            }
+            const uint32_t lp = wbase + 16u * lane;
+            const uint32_t u = c.t + P + 16u * lane - (c.pos & 15u);
+            const uint32_t tl = u - __umulhi(u, m.recip) * P;
+            uint4 tx, mk;
+            tpl_vec(c, c.slot, tl, tx, mk);
+            const bool active = lp < lim;
+            const uint4 d = active ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
+            c.high |= d.x | d.y | d.z | d.w;
+            const uint32_t r0 = (d.x ^ tx.x) & mk.x, r1 = (d.y ^ tx.y) & mk.y, r2 = (d.z ^ tx.z) & mk.z, r3 = (d.w ^ tx.w) & mk.w;
+            const uint32_t s0 = ~span_ok(d.x, mk.x) & 0x80808080u, s1 = ~span_ok(d.y, mk.y) & 0x80808080u;
+            const uint32_t s2 = ~span_ok(d.z, mk.z) & 0x80808080u, s3 = ~span_ok(d.w, mk.w) & 0x80808080u;
+            uint32_t bad = (r0 | r1 | r2 | r3 | s0 | s1 | s2 | s3) != 0 ? 1u : 0u;
+            uint32_t bm = 0xFFFFu;                                                              // bytes of this lane that count
+            if (lp < c.pos || lp + 16u > lim) {
+                if (lp < c.pos) bm &= c.pos - lp >= 16u ? 0u : (0xFFFFu << (c.pos - lp));
+                if (lp + 16u > lim) bm &= lp >= lim ? 0u : (0xFFFFu >> (lp + 16u - lim));
+                if (bad) {
+                    const uint32_t bb = movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12);
+                    bad = (bb & bm) != 0 ? 1u : 0u;
+                }
+            }
+            const uint32_t any = __ballot_sync(R2_FULL, active && bad);
+            uint32_t mpos = lim;
+            if (any) {
+                const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+                uint32_t bb = 0;
+                if (lane == fl) bb = (movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12)) & bm;
+                bb = __shfl_sync(R2_FULL, bb, (int)fl);
+                mpos = wbase + 16u * fl + ((uint32_t)__ffs(bb) - 1u);
+            }
+            // ---- events completed by the pass ----
+            const uint32_t u2 = c.t + (mpos - c.pos);
+            const uint32_t nwr = __umulhi(u2, m.recip);                                           // separators passed
+            const uint32_t t2 = u2 - nwr * P;
+            if (nwr) {
+                const uint32_t last_start = mpos - t2;                                           // start of the event that is open now
+                const uint32_t ev_e = last_start - 2u;                                           // LF LF of the last completed event
+                const uint32_t ps = c.s_open;                                                    // (a usage event is matched alone: its start)
+                if (c.slot == c.dflt) c.hits_d += nwr; else if (lane == 0) atomicAdd(&tc->hits[c.slot], nwr);
+                if (!account_event(c, m.cls, m.flags, nwr, ps, ev_e)) { mark_irregular(c); leave_segment(c, range_hi); return false; }
+                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && ev_e - ps <= LGW_PENDING_CAP) extract_usage(c, m, c.slot, ps);
+                c.s_open = last_start; c.tried = 0;
+                if (single) { c.slot = c.dflt; c.t = 0; c.pos = mpos; reset_fields(c, c.slot); continue; }
+            }
+            c.pos = mpos; c.t = t2;
+            if (!any) continue;                                                                  // the pass ran to its limit
+            // ---- a mismatch at mpos, template offset t2: inside a value span? ----
+            const uint32_t id = (t2 < m.len && mpos != c.last_ra) ? sh->tpl[c.slot].span_id[t2] : 0xffu;
+            bool ok = false;
+            if (id != 0xffu) {
+                const uint32_t sstart = m.sstart[id], send = m.send[id];
+                const uint32_t ev_end = r2_min(sub_end, c.s_open + a.t.carry_cap + 2u);
+                uint32_t ev_len = 0;
+                if (m.skind[id] == 0) {                                                          // string value: plain bytes and valid escapes up to the closing quote
+                    uint32_t q = mpos;
+                    for (;;) {
+                        const uint32_t x = find_special(c, q, ev_end, c.high);
+                        if (x == R2_NONE || x - mpos > R2_MAX_STR) break;
+                        R2Bytes rd{&c};
+                        const uint32_t ch = rd.at(x);
+                        if (ch == '"') { q = x; ok = true; break; }
+                        if (ch != '\\') break;                                                   // a control byte
+                        const uint32_t e1 = rd.at(x + 1);
+                        uint32_t el = 0;
+                        if (e1 == 'u') { el = 6; for (uint32_t j = 2; j < 6; ++j) { const uint32_t h = rd.at(x + j); if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
+                        else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
+                        if (el == 0 || x + el > ev_end) break;
+                        q = x + el;
+                    }
+                    if (ok) { ev_len = q - (mpos - (t2 - sstart)); c.pos = q; c.t = send; }      // (the closing quote itself is compared by the next pass)
+                } else {                                                                          // number value: the event's own number must be valid
+                    const uint32_t bs = mpos - (t2 - sstart);
+                    uint32_t x2 = 0, good = 0;
+                    if (lane == 0) {
+                        R2Bytes rd{&c};
+                        uint32_t st = L_VALUE, p = bs;
+                        for (;;) {
+                            if (p >= ev_end) break;
+                            const uint32_t cl = rd.cls(rd.at(p));
+                            if (cl < C_MINUS || cl > C_EXP) break;
+                            st = rd.trans(st * 32 + cl) & 31u;
+                            if (st == L_ERR) break;
+                            ++p;
+                        }
+                        good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
+                        x2 = p;
+                    }
+                    x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
+                    if (good && x2 >= mpos) { ev_len = x2 - bs; c.pos = x2; c.t = send; c.last_ra = x2; ok = true; }
+                }
+                if (ok && lane < 8u) {                                                           // this lane's usage field follows the shift
+                    const uint32_t fj = m.field_span[lane];
+                    if (fj != 0xffu) { if (fj == id) c.f_len = ev_len; else if ((uint32_t)m.sstart[fj] >= send) c.f_delta += ev_len - (send - sstart); }
+                }
+            }
+            if (ok) continue;
+            // the event does not follow this slot: rewind to its start and try the next one
+            c.tried |= 1u << c.slot;
+            c.pos = c.s_open; c.t = 0;
+            c.slot = next_slot(c);
+            reset_fields(c, c.slot);
+            continue;
+        }
+        // ---- no template fits: the byte-wise recogniser walks the event ----
+        {
+            refresh_slots(c);
+            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; reset_fields(c, c.slot); continue; }   // another warp has just published one
+            const uint32_t ps = c.s_open;
+            const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
+            if (ps > c.tb && ring_byte(c, ps) == '\n') { mark_irregular(c); leave_segment(c, range_hi); return false; }   // LF run >= 3
+            uint32_t cls = PC_NONE, f = 0;
+            const uint32_t e = lean_event(c, ps, ev_end, cls, f, c.high);
+            if (e == R2_NONE) {
+                if (ev_end < sub_end) { mark_irregular(c); leave_segment(c, range_hi); return false; }   // longer than the carry capacity
+                c.pos = sub_end;                                                                // open at the end of the text: the carry
+                continue;
+            }
+            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { mark_irregular(c); leave_segment(c, range_hi); return false; }
+            if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
+            if (!account_event(c, cls, f, 1, ps, e)) { mark_irregular(c); leave_segment(c, range_hi); return false; }
+            if (cls != PC_NONE && (f & PF_VALID_A) && !(f & (TK_ERROR | TK_DETAIL | TK_CODE)) && e - ps >= R2_TPL_MIN && e - ps <= R2_TPL_MAX && c.free_slots) {
+                learn_template(c, ps, sub_end);
+                refresh_slots(c);
+            }
+            c.pos = c.s_open = e + 2; c.t = 0; c.tried = 0;
+            c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
+            reset_fields(c, c.slot);
+        }
+    }
+}
+
+R2_GLOBAL void
+#if !R2_HOST_EMU
+__launch_bounds__(R2_THREADS, 1)
+#endif
+k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t base0) {
+    uint8_t* smem = smem_base();
+    R2Shared* sh = reinterpret_cast<R2Shared*>(smem + R2_RING_BYTES);
+    const uint32_t tid = R2_TID, warp = tid >> 5, lane = tid & 31u;
+    TemplateCache2* tc = a.s.tpl_cache2;
+    UsageRaw* block_raw = a.s.raw_scratch + (size_t)R2_BID * (R2_WARPS + R2_SLOTS) + R2_WARPS;
+
+    // ---- block prologue: recogniser tables, templates from the engine-wide cache, default slot, barriers ----
+    for (uint32_t k = tid; k < 64 + LGW_LEAN_ROWS * 8; k += R2_THREADS) {
+        if (k < 64) reinterpret_cast<uint32_t*>(sh->cls)[k] = reinterpret_cast<const uint32_t*>(lean_tables().cls)[k];
+        else reinterpret_cast<uint32_t*>(sh->trans)[k - 64] = reinterpret_cast<const uint32_t*>(lean_tables().trans)[k - 64];
+    }
+    if (tid < R2_SLOTS) sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u;
+    if (tid == 0) { sh->fast_ready = 0; sh->learn_lock = 0; }
+    if (lane == 0) for (uint32_t b = 0; b < R2_NBUF; ++b) mbar_init(sptr(&sh->mbar[warp * R2_NBUF + b]), 1);
+    mbar_fence_init();
+    __syncthreads();
+    for (uint32_t s = 0; s < R2_SLOTS; ++s) {
+        if (sh->slot_state[s] != 2u) continue;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&tc->tpl[s]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh->tpl[s]);
+        for (uint32_t k = tid; k < sizeof(Tpl2) / 4; k += R2_THREADS) dst[k] = src[k];
+        const uint32_t* rs = reinterpret_cast<const uint32_t*>(&tc->raw[s]);
+        uint32_t* rd = reinterpret_cast<uint32_t*>(&block_raw[s]);
+        for (uint32_t k = tid; k < sizeof(UsageRaw) / 4; k += R2_THREADS) rd[k] = rs[k];
+    }
+    if (tid == 0) {
+        uint32_t d = 0, best = 0; bool have = false;
+        for (uint32_t s = 0; s < R2_SLOTS; ++s) if (sh->slot_state[s] == 2u) { const uint32_t h = tc->hits[s]; if (!have || h > best) { d = s; best = h; have = true; } }
+        sh->dflt = d;
+    }
+    __syncthreads();
+    if (sh->slot_state[sh->dflt] == 2u) {
+        build_fast_tables(sh, sh->dflt, tid, R2_THREADS);
+        __syncthreads();
+        if (tid == 0) sh->fast_ready = 1;
+    }
+    __syncthreads();
+
+    // ---- this warp's byte range ----
+    const uint32_t gw = R2_BID * R2_WARPS + warp;
+    const uint32_t t_first = gw * tiles_per_warp;
+    R2Ctx c;
+    c.a = &a; c.sh = sh; c.lane = lane;
+    c.ring = sptr(smem) + warp * R2_NBUF * R2_TILE; c.bars = sptr(&sh->mbar[warp * R2_NBUF]);
+    c.n_bytes = a.n_bytes;
+    c.base = base0 + t_first * R2_TILE;
+    c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
+    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0;
+    refresh_slots(c);
+    c.block_raw = block_raw; c.warp_raw = a.s.raw_scratch + (size_t)R2_BID * (R2_WARPS + R2_SLOTS) + warp;
+    c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
+    c.slot = c.dflt; c.t = 0; c.tried = 0; c.pos = c.s_open = 0; c.f_delta = 0; c.f_len = 0;
+    c.in_kept = c.primed = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;
+    if (c.n_tiles == 0) return;
+    const uint32_t range_lo = r2_max(c.base, a.tile_base);          // (tile_base = first byte of this launch; a slice starts inside tile 0)
+    const uint32_t range_hi = r2_min(c.base + c.n_tiles * R2_TILE, a.n_bytes);
+    pipe_start(c);
+    pipe_advance(c);
+
+    for (uint32_t seg = find_segment(a, range_lo); seg < a.n_segs; ++seg) {
+        const uint32_t seg_first = seg ? a.s.plan[seg - 1].seg_end : a.tile_base;
+        if (seg_first >= range_hi) break;
+        if (!enter_segment(c, seg, r2_max(range_lo, seg_first), range_hi)) { leave_segment(c, range_hi); continue; }
+        if (walk_segment(c, range_hi)) break;
+    }
+    // ---- the rest of the range is copy only ----
+    while (c.k + 1 < c.n_tiles) pipe_advance(c);
+    __syncwarp();
+    if (lane == 0) {
+        tma_wait_all();
+        if (c.hits_d) atomicAdd(&tc->hits[c.dflt], c.hits_d);
+    }
+}
+
+// ---- k_prime2 ------------------------------------------------------------------------------------------------------------------
+// thread i: the plan of segment i the bulk kernel works to.  Fresh streams are SPECULATED to commit on their first
+// non-empty chunk; the bulk kernel verifies, k_commit2 applies or falls back.  Thread 0 also looks after the template cache.
+R2_GLOBAL void k_prime2(StepArgs a) {
+    const uint32_t i = R2_BID * R2_NTHR + R2_TID;
+    if (i == 0) {
+        *a.s.pend_count = 0;
+        TemplateCache2* tc = a.s.tpl_cache2;
+        uint32_t total = 0, full = 1, lo = 0;
+        for (uint32_t s = 0; s < R2_SLOTS; ++s) { total += tc->hits[s]; if (tc->state[s] != 2u) full = 0; if (tc->hits[s] < tc->hits[lo]) lo = s; }
+        // most events of the last steps matched no template although every slot is taken: forget the least useful one
+        // -- or one slot has not matched anything for many steps while events go unmatched
+        if (full && tc->general && (tc->hits[lo] == 0 || (tc->general > 64u && tc->general > total / 2u))) { tc->state[lo] = 0; tc->hits[lo] = 0; }
+        for (uint32_t s = 0; s < R2_SLOTS; ++s) tc->hits[s] >>= 1;
+        tc->general >>= 1;
+    }
+    if (i >= a.n_segs) return;
+    const uint32_t seg = i, c0 = a.seg_chunk[seg], c1 = a.seg_chunk[seg + 1];
+    const uint32_t slot = a.seg_slot[seg];
+    const StreamHdr st = a.t.state[slot].h;
+    SegPlan p;
+    p.seg_end = a.chunk_off[c1]; p.relay_begin = p.seg_end; p.irregular = 0; p.last_usage = 0; p.a_usage = 0;
+    p.n_events_a = p.n_events_b = p.n_usage_b = 0; p.tail_start = 0xFFFFFFFFu; p.cand_ps = 0;
+    p.kept_chunk = 0xFFFFFFFFu; p.kept_end = 0; p.prime_ok = 0;
+    p.resume_chunk = c0; p.emit_chunk_begin = (st.phase == PH_COMMITTED) ? c0 : c1;
+    if (st.phase == PH_COMMITTED && c0 < c1) {
+        if ((st.flags & SF_SYNCED) && st.carry_a_len == 0) p.relay_begin = a.chunk_off[c0];
+        else p.irregular = 1;
+    } else if (st.phase == PH_PRIMING && c0 < c1) {
+        uint32_t c = c0;
+        while (c < c1 && a.chunk_off[c + 1] == a.chunk_off[c]) ++c;          // empty chunks are never yielded (:60-63)
+        if (c < c1 && st.carry_a_len == 0) {
+            p.kept_chunk = c; p.kept_end = a.chunk_off[c + 1]; p.relay_begin = a.chunk_off[c]; p.emit_chunk_begin = c;
+        } else if (c < c1) p.irregular = 1;                                    // an event is open from an earlier step
+    }
+    a.s.plan[seg] = p;
+}
+
+// ---- k_commit2 (one warp per segment) ----------------------------------------------------------------------------------------------
+R2_GLOBAL void k_commit2(StepArgs a) {
+    const uint32_t seg = (R2_BID * R2_NTHR + R2_TID) >> 5, lane = R2_TID & 31u;
+    if (seg >= a.n_segs) return;
+    const uint32_t c1 = a.seg_chunk[seg + 1];
+    const uint32_t slot = a.seg_slot[seg];
+    StreamHdr st = a.t.state[slot].h;                     // (every lane holds a copy; lane 0's is the one written back)
+    const StepIO io = make_io(a, slot, &st);
+    const SegPlan p = a.s.plan[seg];
+    uint32_t emit_begin = p.emit_chunk_begin;
+    const bool speculated = p.kept_chunk != 0xFFFFFFFFu;
+    if ((st.phase == PH_COMMITTED || st.phase == PH_PRIMING) && p.resume_chunk < c1) {
+        const uint8_t* __restrict__ d = a.data;
+        // an empty chunk is never yielded (request_handler.py:60-63): the concatenation argument does not cover it
+        bool empty = false;
+        for (uint32_t c = p.resume_chunk + lane; c < c1; c += 32) if (__ldg(a.chunk_off + c + 1) == __ldg(a.chunk_off + c)) empty = true;
+        bool sequential = p.irregular || p.n_usage_b > 1 || __any_sync(R2_FULL, empty);   // several usage candidates: let the exact path count them
+        if (st.phase == PH_PRIMING && !(speculated && p.prime_ok)) sequential = true;
+        const uint32_t ups = (uint32_t)(p.last_usage >> 32) - 1u, ulen = (uint32_t)p.last_usage;   // the winning usage event
+        if (!sequential && p.last_usage && ulen > LGW_PENDING_CAP) sequential = true;
+        if (!sequential && p.tail_start == 0xFFFFFFFFu) sequential = true;                        // (nobody reached the end of the text)
+        if (lane == 0) atomicAdd(a.s.counters + (sequential ? 0 : 1), 1u);
+        if (sequential) {
+            if (lane == 0) {
+                emit_begin = (st.phase == PH_COMMITTED) ? p.resume_chunk : c1;
+                run_chunks(io, a.data, a.chunk_off, p.resume_chunk, c1, emit_begin, false);
+            }
+        } else {
+            uint32_t first = p.resume_chunk;
+            if (speculated) {                       // apply the verified commit (request_handler.py:89-90, chat_logging.py:200)
+                st.phase = PH_COMMITTED; st.verdict = VD_OK;
+                st.flags |= SF_EMITTED_ANY | SF_SYNCED;
+                st.carry_a_len = st.carry_b_len = 0;
+                ++st.n_events_a;                    // the priming parse of the first real event
+                first = p.kept_chunk;
+            }
+            const uint32_t nch = c1 - first, nby = p.seg_end - p.relay_begin;
+            st.n_chunks_in += nch; st.n_chunks_emitted += nch; st.bytes_in += nby; st.bytes_emitted += nby;
+            st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b;
+            if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
+            if (p.last_usage) {                     // the last usage-bearing event wins (chat_logging.py:134-135)
+                if (lane == 0 && (st.flags & SF_PENDING)) resolve_pending(io);     // an older stash must be settled first
+                if (p.cand_ps == ups + 1u) {
+                    // its fields were read from the matched template spans: install the candidate record
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.s.usage_cand + seg);
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(io.rec);
+                    for (uint32_t k = lane; k < sizeof(UsageRec) / 4; k += 32) dst[k] = src[k];
+                    st.flags |= SF_REC_VALID; ++st.n_usage_b;
+                    if (a.s.usage_cand[seg].exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+                    if (lane == 0) atomicAdd(a.s.counters + 2, 1u);
+                } else {
+                    // stash its text as whole 16-byte vectors; k_usage_extract reads the values out at the end of the step
+                    const uint32_t off = ups & 15u, nv = (off + ulen + 15u) >> 4;
+                    if (((size_t)(ups - off) + ((size_t)nv << 4)) <= a.n_bytes) {
+                        const uint4* src = reinterpret_cast<const uint4*>(d + (ups - off));
+                        uint4* dst = reinterpret_cast<uint4*>(io.pending);
+                        for (uint32_t k = lane; k < nv; k += 32) dst[k] = __ldg(src + k);
+                    } else { for (uint32_t k = lane; k < ulen; k += 32) io.pending[off + k] = __ldg(d + ups + k); }
+                    st.pending_len = ulen | (off << 16); st.flags |= SF_PENDING; ++st.n_usage_b;
+                    if (lane == 0) { const uint32_t q = atomicAdd(a.s.pend_count, 1u); if (q < a.t.max_streams) a.s.pend_list[q] = slot; atomicAdd(a.s.counters + 3, 1u); }
+                }
+            }
+            // new carry = text after the last separator (both loops: SF_SYNCED)
+            const uint32_t tail = p.tail_start, n = p.seg_end - tail;
+            if (n > a.t.carry_cap) { st.carry_a_len = 0; st.flags |= SF_CARRY_OVERFLOW; }
+            else { for (uint32_t k = lane; k < n; k += 32) io.carry_a[k] = d[tail + k]; st.carry_a_len = n; }
+        }
+        __syncwarp();
+        if (lane == 0) a.t.state[slot].h = st;
+    }
+    if (lane == 0) {
+        SegResult res;
+        fill_seg_result(st, emit_begin, c1, res);
+        a.seg_out[seg] = res;
+    }
+}
+
+// ---- k_usage_extract (one warp per stashed usage event) -----------------------------------------------------------------------------
+// Usage events that followed no usage template were stashed by k_commit2; their values are read out here, at the end of
+// the same step (chat_logging.py:134-135 -> get_token_usage :233-272), so that reading a stream's state is a plain copy.
+#define R2_XWARPS 4u
+R2_GLOBAL void k_usage_extract(StepArgs a) {
+#if !R2_HOST_EMU
+    __shared__ __align__(16) uint8_t stage[R2_XWARPS][LGW_PENDING_STRIDE];
+#else
+    static uint8_t stage[R2_XWARPS][LGW_PENDING_STRIDE];
+#endif
+    uint32_t n = *a.s.pend_count;
+    if (n > a.t.max_streams) n = a.t.max_streams;
+    const uint32_t warp = R2_TID >> 5, lane = R2_TID & 31u;
+    for (uint32_t i = R2_BID * R2_XWARPS + warp; i < n; i += R2_NBLK * R2_XWARPS) {
+        const uint32_t slot = a.s.pend_list[i];
+        StreamState* s = a.t.state + slot;
+        StreamHdr st = s->h;
+        if (st.flags & SF_PENDING) {
+            const uint8_t* src = a.t.pending + (size_t)slot * LGW_PENDING_STRIDE;
+            for (uint32_t k = lane; k < LGW_PENDING_STRIDE / 16; k += 32) reinterpret_cast<uint4*>(stage[warp])[k] = reinterpret_cast<const uint4*>(src)[k];
+            __syncwarp();
+            if (lane == 0) {
+                StepIO io;
+                io.st = &st; io.rec = &s->rec; io.pending = stage[warp];
+                io.carry_a = io.carry_b = io.detail = nullptr; io.carry_cap = io.detail_cap = 0;
+                io.rowq = nullptr; io.rowq_count = nullptr; io.rowq_cap = 0; io.slot = slot;
+                resolve_pending(io);
+                s->h = st;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+#if !R2_HOST_EMU
+static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
+    cudaError_t r;
+    const uint32_t base0 = a.tile_base & ~15u;
+    const uint32_t n_tiles = a.n_bytes > base0 ? (a.n_bytes - base0 + R2_TILE - 1) / R2_TILE : 0u;
+    if (a.n_segs) { k_prime2<<<(a.n_segs + 127) / 128, 128, 0, stream>>>(a); ++*launched; }
+    if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
+    if (n_tiles) {
+        const uint32_t max_warps = (uint32_t)sm_count * R2_WARPS;
+        const uint32_t tpw = (n_tiles + max_warps - 1) / max_warps;
+        const uint32_t warps = (n_tiles + tpw - 1) / tpw;
+        const uint32_t blocks = (warps + R2_WARPS - 1) / R2_WARPS;
+        k_relay2<<<blocks, R2_THREADS, R2_SMEM_BYTES, stream>>>(a, n_tiles, tpw, base0); ++*launched;
+    }
+    if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
+    if (a.n_segs) { k_commit2<<<(a.n_segs + 7) / 8, 256, 0, stream>>>(a); ++*launched; }
+    if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
+    if (a.n_segs) {
+        uint32_t xb = (a.n_segs + R2_XWARPS - 1) / R2_XWARPS; if (xb > (uint32_t)sm_count * 4u) xb = (uint32_t)sm_count * 4u;
+        k_usage_extract<<<xb, R2_XWARPS * 32, 0, stream>>>(a); ++*launched;
+    }
+    if ((r = cudaEventRecord(ev[4], stream)) != cudaSuccess) return r;
+    return cudaGetLastError();
+}
+#endif
+

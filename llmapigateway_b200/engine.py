@@ -136,9 +136,16 @@ class Engine:
         self._ck(self._lib.lgw_sync(self._h), "sync")
 
     def last_step_ms(self):
-        ms = (C.c_float * 4)()
+        """Device time of the four kernels of the last step (CUDA events on the launching stream) and of the whole host-buffer call."""
+        ms, k = (C.c_float * 4)(), (C.c_float * 4)()
         self._ck(self._lib.lgw_last_step_ms(self._h, C.byref(ms)), "last_step_ms")
-        return dict(prime=ms[0], relay=ms[1], commit=ms[2], host_step=ms[3])
+        self._ck(self._lib.lgw_last_step_kernel_ms(self._h, C.byref(k)), "last_step_kernel_ms")
+        return dict(prime=k[0], relay=k[1], commit=k[2], usage_extract=k[3], host_step=ms[3])
+
+    def debug_counters(self):
+        out = (C.c_uint32 * 4)()
+        self._ck(self._lib.lgw_debug_counters(self._h, out), "debug_counters")
+        return dict(sequential=out[0], bulk=out[1], from_template=out[2], stashed=out[3])
 
     def launch_count(self) -> int:
         n = C.c_uint64(0)
