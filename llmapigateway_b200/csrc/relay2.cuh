@@ -207,25 +207,43 @@ struct R2Ctx {
     uint32_t f_delta, f_len;
 };
 
+// Where bytes are read from: the resident tile in shared memory, global memory outside it.  A small value type: the
+// out-of-line slow paths take a COPY, so that the warp context itself never has its address taken and stays in registers.
+struct R2Io {
+    const uint8_t* data; const R2Shared* sh;
+    uint32_t n_bytes, tile_lo, tile_hi; SPtr buf;
+};
+R2_DEV R2Io io_of(const R2Ctx& c) { R2Io io; io.data = c.a->data; io.sh = c.sh; io.n_bytes = c.n_bytes; io.tile_lo = c.tile_lo; io.tile_hi = c.tile_hi; io.buf = c.buf; return io; }
+R2_DEV uint8_t io_byte(const R2Io& io, uint32_t p) {
+    if (p >= io.tile_lo && p < io.tile_hi) return (uint8_t)sld8(io.buf + (p - io.tile_lo));
+    return p < io.n_bytes ? __ldg(io.data + p) : (uint8_t)0;
+}
 R2_DEV uint8_t ring_byte(const R2Ctx& c, uint32_t p) {
-    const uint32_t d = p - c.tile_lo;
-    if (p >= c.tile_lo && d < c.tile_hi - c.tile_lo) return (uint8_t)sld8(c.buf + d);
+    if (p >= c.tile_lo && p < c.tile_hi) return (uint8_t)sld8(c.buf + (p - c.tile_lo));
     return p < c.n_bytes ? __ldg(c.a->data + p) : (uint8_t)0;
 }
-// byte source for the single-lane walks (recogniser, template builder): the resident tile, global memory outside it
+// byte source for the single-lane walks (recogniser, template builder, field readers)
 struct R2Bytes {
-    const R2Ctx* c;
-    R2_MEM uint32_t at(uint32_t p) const { return ring_byte(*c, p); }
-    R2_MEM uint32_t cls(uint32_t ch) const { return c->sh->cls[ch]; }
-    R2_MEM uint32_t trans(uint32_t i) const { return c->sh->trans[i]; }
+    R2Io io;
+    R2_MEM uint32_t at(uint32_t p) const { return io_byte(io, p); }
+    R2_MEM uint32_t cls(uint32_t ch) const { return io.sh->cls[ch]; }
+    R2_MEM uint32_t trans(uint32_t i) const { return io.sh->trans[i]; }
+};
+// plain global-memory reader (field extraction: a handful of bytes per lane, L1/L2 hits)
+struct R2Glob {
+    const uint8_t* data; uint32_t n_bytes;
+    R2_MEM uint32_t at(uint32_t p) const { return p < n_bytes ? (uint32_t)__ldg(data + p) : 0u; }
 };
 // 16 bytes at the 16-byte aligned position p: resident tile, else global memory; bytes at or after n_bytes read as 0
 R2_DEV uint4 ld16(const R2Ctx& c, uint32_t p) {
     if (p >= c.tile_lo && p + 16 <= c.tile_hi) return sld128(c.buf + (p - c.tile_lo));
     if (p + 16 <= c.n_bytes) return gld128(c.a->data + p);
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (uint32_t i = 0; i < 16 && p + i < c.n_bytes; ++i) w[i >> 2] |= (uint32_t)ring_byte(c, p + i) << (8 * (i & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    for (uint32_t i = 0; i < 16 && p + i < c.n_bytes; ++i) {
+        const uint32_t v = (uint32_t)ring_byte(c, p + i) << (8 * (i & 3));
+        if (i < 4) w0 |= v; else if (i < 8) w1 |= v; else if (i < 12) w2 |= v; else w3 |= v;
+    }
+    return make_uint4(w0, w1, w2, w3);
 }
 
 // ---- pipeline ----------------------------------------------------------------------------------------------------------
@@ -242,27 +260,37 @@ R2_DEV void pipe_start(R2Ctx& c) {
     if (c.lane == 0) for (uint32_t k = 0; k < R2_NBUF - 1 && k < c.n_tiles; ++k) pipe_issue_load(c, k);
 }
 // make tile k resident (k = previous + 1): wait for its bytes, hand it to the store engine, refill the buffer that just became free
-R2_DEV void pipe_advance(R2Ctx& c) {
-    const uint32_t k = c.k == R2_NONE ? 0u : c.k + 1u;
+struct PipeState { uint32_t k, tile_lo, tile_hi; SPtr buf; };
+R2_DEV_NOINLINE PipeState pipe_advance_impl(const StepArgs* ap, SPtr ring, SPtr bars, uint32_t base, uint32_t n_tiles, uint32_t n_bytes, uint32_t k_prev, uint32_t lane) {
+    const uint32_t k = k_prev == R2_NONE ? 0u : k_prev + 1u;
     __syncwarp();                                   // every lane is done with the buffers of the earlier tiles
-    const uint32_t b = k % R2_NBUF, nb = tile_bytes(c, k), n16 = nb & ~15u;
-    c.k = k; c.tile_lo = c.base + k * R2_TILE; c.tile_hi = c.tile_lo + nb; c.buf = c.ring + b * R2_TILE;
-    if (n16) mbar_wait(c.bars + 8 * b, (k / R2_NBUF) & 1u);
+    const uint32_t lo = base + k * R2_TILE;
+    const uint32_t b = k % R2_NBUF, nb = n_bytes - lo < R2_TILE ? n_bytes - lo : R2_TILE, n16 = nb & ~15u;
+    PipeState ps; ps.k = k; ps.tile_lo = lo; ps.tile_hi = lo + nb; ps.buf = ring + b * R2_TILE;
+    if (n16) mbar_wait(bars + 8 * b, (k / R2_NBUF) & 1u);
     if (nb != n16) {                                // ragged end of the buffer: the last bytes move by hand
-        const uint32_t i = n16 + c.lane;
-        if (c.lane < 16) {
-            const uint32_t v = i < nb ? (uint32_t)__ldg(c.a->data + c.tile_lo + i) : 0u;
-            sst8(c.buf + i, v);
-            if (i < nb) c.a->out[c.tile_lo + i] = (uint8_t)v;
+        const uint32_t i = n16 + lane;
+        if (lane < 16) {
+            const uint32_t v = i < nb ? (uint32_t)__ldg(ap->data + lo + i) : 0u;
+            sst8(ps.buf + i, v);
+            if (i < nb) ap->out[lo + i] = (uint8_t)v;
         }
         __syncwarp();
     }
-    if (c.lane == 0) {
-        if (n16) tma_store(c.a->out + c.tile_lo, c.buf, n16); else tma_store_commit_empty();
+    if (lane == 0) {
+        if (n16) tma_store(ap->out + lo, ps.buf, n16); else tma_store_commit_empty();
         tma_wait_read1();                           // the store of tile k-1 has read its buffer
         const uint32_t kn = k + R2_NBUF - 1;
-        if (kn < c.n_tiles) pipe_issue_load(c, kn);
+        if (kn < n_tiles) {
+            const uint32_t bn = kn % R2_NBUF, lon = base + kn * R2_TILE, nn = (n_bytes - lon < R2_TILE ? n_bytes - lon : R2_TILE) & ~15u;
+            if (nn) { mbar_expect(bars + 8 * bn, nn); tma_load(ring + bn * R2_TILE, ap->data + lon, nn, bars + 8 * bn); }
+        }
     }
+    return ps;
+}
+R2_DEV void pipe_advance(R2Ctx& c) {
+    const PipeState ps = pipe_advance_impl(c.a, c.ring, c.bars, c.base, c.n_tiles, c.n_bytes, c.k, c.lane);
+    c.k = ps.k; c.tile_lo = ps.tile_lo; c.tile_hi = ps.tile_hi; c.buf = ps.buf;
 }
 
 // ---- templates ---------------------------------------------------------------------------------------------------------
@@ -465,8 +493,8 @@ R2_DEV bool account_event(R2Ctx& c, uint32_t cls, uint32_t f, uint32_t n, uint32
 }
 
 // chunk-level UTF-8 (request_handler.py:111 decodes every chunk on its own): the chunks of segment `seg` that overlap [lo, hi)
-R2_DEV_NOINLINE bool chunks_utf8_ok(const R2Ctx& c, uint32_t seg, uint32_t lo, uint32_t hi) {
-    const StepArgs& a = *c.a;
+R2_DEV_NOINLINE bool chunks_utf8_ok(const StepArgs* ap, uint32_t lane, uint32_t seg, uint32_t lo, uint32_t hi) {
+    const StepArgs& a = *ap;
     uint32_t c0 = __ldg(a.seg_chunk + seg), c1 = __ldg(a.seg_chunk + seg + 1);
     {   // first chunk that ends after lo
         uint32_t l = c0, h = c1;
@@ -474,7 +502,7 @@ R2_DEV_NOINLINE bool chunks_utf8_ok(const R2Ctx& c, uint32_t seg, uint32_t lo, u
         c0 = l;
     }
     bool ok = true;
-    for (uint32_t ch = c0 + c.lane; ch < c1; ch += 32) {
+    for (uint32_t ch = c0 + lane; ch < c1; ch += 32) {
         const uint32_t o = __ldg(a.chunk_off + ch), e = __ldg(a.chunk_off + ch + 1);
         if (o >= hi) break;
         if (e > a.n_bytes) { ok = false; break; }
@@ -531,10 +559,11 @@ R2_DEV uint32_t find_special(R2Ctx& c, uint32_t from, uint32_t end, uint32_t& hi
 
 // the recogniser over one event starting at ps (single lane does the walk): finds its LF LF (e) or runs into `end`.
 // out: cls, flags; returns e, or R2_NONE when the event is still open at `end`.
-R2_DEV_NOINLINE uint32_t lean_event(R2Ctx& c, uint32_t ps, uint32_t end, uint32_t& cls_out, uint32_t& f_out, uint32_t& high) {
+struct LeanOut { uint32_t e, cls, f, high; };
+R2_DEV_NOINLINE LeanOut lean_event(R2Io io, uint32_t lane, uint32_t ps, uint32_t end) {
     uint32_t e = R2_NONE, cls = PC_NONE, f = 0, hi = 0;
-    if (c.lane == 0) {
-        R2Bytes rd{&c};
+    if (lane == 0) {
+        R2Bytes rd{io};
         const uint32_t c0 = ps < end ? rd.at(ps) : 0u;
         if (c0 == '{') cls = PC_BRACE;
         else if (c0 == 'd' && ps + 7 <= end && rd.at(ps + 1) == 'a' && rd.at(ps + 2) == 't' && rd.at(ps + 3) == 'a' && rd.at(ps + 4) == ':' && rd.at(ps + 5) == ' ' && rd.at(ps + 6) == '{') cls = PC_DATA;
@@ -549,9 +578,9 @@ R2_DEV_NOINLINE uint32_t lean_event(R2Ctx& c, uint32_t ps, uint32_t end, uint32_
         }
         if (e != R2_NONE && cls != PC_NONE) f = lm.finish();
     }
-    e = __shfl_sync(R2_FULL, e, 0); cls_out = __shfl_sync(R2_FULL, cls, 0); f_out = __shfl_sync(R2_FULL, f, 0);
-    high |= __shfl_sync(R2_FULL, hi, 0);
-    return e;
+    LeanOut o;
+    o.e = __shfl_sync(R2_FULL, e, 0); o.cls = __shfl_sync(R2_FULL, cls, 0); o.f = __shfl_sync(R2_FULL, f, 0); o.high = __shfl_sync(R2_FULL, hi, 0);
+    return o;
 }
 
 // Slot states as one lane sees them, handed to all (other warps of the block publish templates while this one runs; every
@@ -574,22 +603,22 @@ R2_DEV bool tpl_same(const Tpl2& x, const Tpl2& y) {
 // engine-wide cache has room and does not hold the same skeleton yet, publish it there.  One warp of a block learns at a
 // time, and not when another warp has just made a template ready that this event was not tried against (it may be the very
 // same skeleton: in a cold step every warp meets the first delta at the same moment).
-R2_DEV_NOINLINE void learn_template(R2Ctx& c, uint32_t ps, uint32_t end) {
-    R2Shared* sh = c.sh;
+R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, UsageRaw* block_raw, uint32_t lane, uint32_t ready_before, uint32_t ps, uint32_t end) {
     uint32_t got = 0;
-    if (c.lane == 0) got = atomicCAS(&sh->learn_lock, 0u, 1u) == 0u ? 1u : 0u;
+    if (lane == 0) got = atomicCAS(&sh->learn_lock, 0u, 1u) == 0u ? 1u : 0u;
     got = __shfl_sync(R2_FULL, got, 0);
     if (!got) return;
-    const uint32_t ready_before = c.ready;
-    refresh_slots(c);
+    uint32_t ready = 0, free_slots = 0;
+    if (lane == 0) for (uint32_t k = 0; k < R2_SLOTS; ++k) { const uint32_t st = *(volatile uint32_t*)&sh->slot_state[k]; if (st == 2u) ready |= 1u << k; else if (st == 0u) free_slots |= 1u << k; }
+    ready = __shfl_sync(R2_FULL, ready, 0); free_slots = __shfl_sync(R2_FULL, free_slots, 0);
     uint32_t slot = R2_NONE;
-    if (c.ready == ready_before && c.free_slots) {
-        if (c.lane == 0) {
-            slot = (uint32_t)__ffs(c.free_slots) - 1u;
+    if (ready == ready_before && free_slots) {
+        if (lane == 0) {
+            slot = (uint32_t)__ffs(free_slots) - 1u;
             atomicExch(&sh->slot_state[slot], 1u);
-            R2Bytes rd{&c};
-            TemplateCache2* tc = c.a->s.tpl_cache2;
-            UsageRaw* raw = c.block_raw + slot;
+            R2Bytes rd{io};
+            TemplateCache2* tc = ap->s.tpl_cache2;
+            UsageRaw* raw = block_raw + slot;
             if (build_template2(rd, &sh->tpl[slot], raw, ps, end)) {
                 if (atomicCAS(&tc->lock, 0u, 1u) == 0u) {                        // (busy: the template stays local to this block for this launch)
                     bool dup = false; uint32_t dst = R2_NONE;
@@ -612,23 +641,22 @@ R2_DEV_NOINLINE void learn_template(R2Ctx& c, uint32_t ps, uint32_t end) {
     }
     if (slot != R2_NONE) {
         uint32_t need_fast = 0;
-        if (c.lane == 0) need_fast = (slot == sh->dflt && !*(volatile uint32_t*)&sh->fast_ready) ? 1u : 0u;
+        if (lane == 0) need_fast = (slot == sh->dflt && !*(volatile uint32_t*)&sh->fast_ready) ? 1u : 0u;
         need_fast = __shfl_sync(R2_FULL, need_fast, 0);
         if (need_fast) {                                                        // a cold block: its first template becomes the default
-            build_fast_tables(sh, slot, c.lane, 32);
+            build_fast_tables(sh, slot, lane, 32);
             __threadfence_block();
             __syncwarp();
-            if (c.lane == 0) *(volatile uint32_t*)&sh->fast_ready = 1u;
+            if (lane == 0) *(volatile uint32_t*)&sh->fast_ready = 1u;
         }
         __threadfence_block();
-        if (c.lane == 0) atomicExch(&sh->slot_state[slot], 2u);
+        if (lane == 0) atomicExch(&sh->slot_state[slot], 2u);
     }
     __syncwarp();
-    if (c.lane == 0) { __threadfence_block(); atomicExch(&sh->learn_lock, 0u); }
+    if (lane == 0) { __threadfence_block(); atomicExch(&sh->learn_lock, 0u); }
     __syncwarp();
 }
 
-// ---- the walk of one warp over its byte range ------------------------------------------------------------------------------------
 // this lane's usage field: span length and accumulated shift start from the template's own
 R2_DEV void reset_fields(R2Ctx& c, uint32_t slot) {
     c.f_delta = 0; c.f_len = 0; c.last_ra = R2_NONE;
@@ -657,7 +685,7 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     if (pl->irregular || tb >= te) return false;
     if (from <= tb) {
         if (tb >= range_hi) return false;
-        if (kept) { if (kept > range_hi) { mark_irregular(c); return false; } c.in_kept = 1u; }   // the kept chunk is walked by ONE warp
+        if (kept) c.in_kept = 1u;                            // the kept chunk is walked by ONE warp, the one that owns its first byte (beyond its range if need be)
         c.pos = c.s_open = c.walk_lo = tb;
         reset_fields(c, c.slot);
         return true;
@@ -665,8 +693,13 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     // the range starts inside the segment's text: the event that is open there belongs to the previous warp; ours start
     // behind the first separator that ends at or after `from`
     if (from >= te) return false;
-    if (kept && from < kept) return false;                                       // (the warp that owns tb flagged the stream)
     c.walk_lo = from;
+    if (kept && from < kept) {                                                   // the range starts inside the kept chunk: the warp before walks that to its end;
+        if (kept >= range_hi || kept >= te) return false;                        //   the speculation holds only if the chunk ends on a separator, so ours begin right there
+        c.pos = c.s_open = kept;
+        reset_fields(c, c.slot);
+        return true;
+    }
     const uint32_t p = find_lflf(c, from - tb >= 2u ? from - 2u : tb, te, c.high);
     if (p == R2_NONE) return false;
     const uint32_t s = p + 2u;
@@ -689,46 +722,47 @@ R2_DEV uint32_t find_segment(const StepArgs& a, uint32_t pos) {
 R2_DEV void leave_segment(R2Ctx& c, uint32_t range_hi) {
     if (c.seg == R2_NONE) return;
     if (__any_sync(R2_FULL, (c.high & 0x80808080u) != 0)) {
-        if (!chunks_utf8_ok(c, c.seg, c.walk_lo, r2_min(c.te, r2_max(c.pos, range_hi)))) mark_irregular(c);
+        if (!chunks_utf8_ok(c.a, c.lane, c.seg, c.walk_lo, r2_min(c.te, r2_max(c.pos, range_hi)))) mark_irregular(c);
     }
     flush_counts(c);
     c.seg = R2_NONE;
 }
 
 // usage fields of the event [ps, e) straight from the value spans the match located (usage_ok templates)
-R2_DEV_NOINLINE void extract_usage(R2Ctx& c, const TplMeta& m, uint32_t slot, uint32_t ps) {
-    R2Bytes rd{&c};
-    UsageRaw* raw = c.warp_raw;
+R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, uint32_t lane, uint32_t seg, uint32_t ps, uint32_t f_delta, uint32_t f_len) {
+    const TplMeta& m = *mp;
+    R2Glob rd{io.data, io.n_bytes};
     Val v; v.kind = KD_ABSENT; v.bits = 0;
-    const uint32_t fj = c.lane < 8u ? m.field_span[c.lane] : 0xffu;
-    if (c.lane == 0) *raw = c.block_raw[slot];
+    const uint32_t fj = lane < 8u ? m.field_span[lane] : 0xffu;
+    for (uint32_t k = lane; k < sizeof(UsageRaw) / 4; k += 32) reinterpret_cast<uint32_t*>(raw)[k] = reinterpret_cast<const uint32_t*>(tpl_raw)[k];
     __syncwarp();
     if (fj != 0xffu) {
-        const uint32_t fs = ps + m.sstart[fj] + c.f_delta;
-        if (c.lane < UF_MODEL) v = parse_number_span(rd, fs, c.f_len);
-        else if (c.lane == UF_MODEL) decode_string_span(rd, fs, c.f_len, raw->model, raw->model_len, raw->model_flags);
-        else decode_string_span(rd, fs, c.f_len, raw->provider, raw->provider_len, raw->provider_flags);
+        const uint32_t fs = ps + m.sstart[fj] + f_delta;
+        if (lane < UF_MODEL) v = parse_number_span(rd, fs, f_len);
+        else if (lane == UF_MODEL) decode_string_span(rd, fs, f_len, raw->model, raw->model_len, raw->model_flags);
+        else decode_string_span(rd, fs, f_len, raw->provider, raw->provider_len, raw->provider_flags);
     }
     __syncwarp();
     for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
         const unsigned long long vb = __shfl_sync(R2_FULL, (unsigned long long)v.bits, (int)fi);
         const uint32_t vk = __shfl_sync(R2_FULL, (uint32_t)v.kind, (int)fi);
-        if (c.lane == 0 && m.field_span[fi] != 0xffu) {
+        if (lane == 0 && m.field_span[fi] != 0xffu) {
             Val x; x.bits = (int64_t)vb; x.kind = (uint8_t)vk;
             if (fi == UF_PROMPT) raw->prompt = x; else if (fi == UF_COMPLETION) raw->completion = x; else if (fi == UF_TOTAL) raw->total = x;
             else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
         }
     }
-    if (c.lane == 0) {
-        normalise_usage(*raw, m.full_flags, c.a->s.usage_cand[c.seg]);
+    if (lane == 0) {
+        normalise_usage(*raw, m.full_flags, ap->s.usage_cand[seg]);
         __threadfence();
-        c.a->s.plan[c.seg].cand_ps = ps + 1u;
+        ap->s.plan[seg].cand_ps = ps + 1u;
     }
     __syncwarp();
 }
 
 // Walk the current segment from c.pos.  Returns true when the warp is done (the open event starts in the next warp's
-// range); false when the segment's text is finished for this warp (go on with the next segment).
+// range); false when the segment's text is finished for this warp (go on with the next segment).  The caller leaves the
+// segment (counters, chunk-level UTF-8) either way.
 R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
     R2Shared* sh = c.sh;
     const StepArgs& a = *c.a;
@@ -739,17 +773,59 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
         if (c.pos >= sub_end) {
             // ---- end of the kept chunk / of the segment's text ----
             if (c.in_kept) {                                                   // the speculation holds when a real event was accepted
-                if (c.s_open != c.kept_end || !c.primed) { mark_irregular(c); leave_segment(c, range_hi); return false; }   //   and the chunk ends on a separator
+                if (c.s_open != c.kept_end || !c.primed) { mark_irregular(c); return false; }   //   and the chunk ends on a separator
                 if (lane == 0) a.s.plan[c.seg].prime_ok = 1;
                 c.in_kept = 0;
                 continue;
             }
             if (lane == 0) a.s.plan[c.seg].tail_start = c.s_open;              // the open event is the new carry
-            leave_segment(c, range_hi);
             return false;
         }
-        if (c.s_open >= range_hi && c.pos == c.s_open) { leave_segment(c, range_hi); return true; }   // the open event starts in the next warp's range
+        if (c.s_open >= range_hi && c.pos == c.s_open && !c.in_kept) return true;   // the open event starts in the next warp's range
         while (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) pipe_advance(c);      // (slow paths may have run ahead of the resident tile)
+
+        // ---- fast loop: whole 16-byte aligned windows of the resident tile against the default slot's periodic image ----
+        // (no boundary lanes, no limits other than the tile's end; anything else -- a mismatch, the end of the text or of the
+        //  range, a usage-bearing default -- leaves the loop and is handled by the general pass below, from the same position)
+        if (c.slot == c.dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
+            const TplMeta& dm = sh->tpl[c.dflt].m;
+            const uint32_t P = dm.P, recip = dm.recip, dflags = dm.flags;
+            if (!(dflags & TK_USAGE)) {
+                const uint32_t stop = r2_min(sub_end, range_hi);          // whole windows must end at or before this
+                const SPtr ft = sptr(sh->fast_text), fl = sptr(sh->fast_lit);
+                uint32_t nfast = 0, pos = c.pos, t = c.t, s_open = c.s_open, high = 0;
+                for (;;) {
+                    const uint32_t lim = r2_min(pos + 512u, c.tile_hi);
+                    if (lim > stop || (lim & 15u)) break;
+                    const uint32_t lp = pos + 16u * lane;
+                    const uint32_t u = t + 16u * lane;
+                    const uint32_t tl = u - __umulhi(u, recip) * P;
+                    const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
+                    uint32_t bad = 0;
+                    if (lp < lim) {
+                        const uint4 d = sld128(c.buf + (lp - c.tile_lo));
+                        const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad);
+                        high |= d.x | d.y | d.z | d.w;
+                        const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
+                        const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
+                        bad = lit | (~ok & 0x80808080u);
+                    }
+                    if (__ballot_sync(R2_FULL, bad != 0)) break;           // the general pass finds out where and why
+                    const uint32_t u2 = t + (lim - pos);
+                    const uint32_t nwr = __umulhi(u2, recip);
+                    t = u2 - nwr * P; pos = lim; nfast += nwr;
+                    if (nwr) s_open = pos - t;
+                    if (pos >= c.tile_hi) { if (c.k + 1 < c.n_tiles) pipe_advance(c); else break; }
+                }
+                c.high |= high;
+                if (nfast) {
+                    c.hits_d += nfast; c.tried = 0; c.s_open = s_open;
+                    if (dm.cls == PC_DATA) c.ev_a += nfast;
+                    if (dflags & PF_VALID_B) c.ev_b += nfast;
+                }
+                if (pos != c.pos) { c.pos = pos; c.t = t; continue; }
+            }
+        }
 
         if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
             c.tried |= 1u << c.slot; c.slot = next_slot(c); reset_fields(c, c.slot);
@@ -764,7 +840,7 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             uint32_t lim = r2_min(sub_end, wbase + 512u);
             if (c.pos >= c.tile_lo && c.pos < c.tile_hi) lim = r2_min(lim, c.tile_hi);          // windows do not straddle the resident tile's end
             if (single) lim = r2_min(lim, c.pos + (P - c.t));                                   // one event, then back to the default slot
-            else if (wbase + 512u > range_hi) {                                                  // stop at the first event boundary in the next range
+            else if (wbase + 512u > range_hi && !c.in_kept) {                                    // stop at the first event boundary in the next range
                 const uint32_t nb = c.pos + (P - c.t);
                 uint32_t b = nb;
                 if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
@@ -809,8 +885,9 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
                 const uint32_t ev_e = last_start - 2u;                                           // LF LF of the last completed event
                 const uint32_t ps = c.s_open;                                                    // (a usage event is matched alone: its start)
                 if (c.slot == c.dflt) c.hits_d += nwr; else if (lane == 0) atomicAdd(&tc->hits[c.slot], nwr);
-                if (!account_event(c, m.cls, m.flags, nwr, ps, ev_e)) { mark_irregular(c); leave_segment(c, range_hi); return false; }
-                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && ev_e - ps <= LGW_PENDING_CAP) extract_usage(c, m, c.slot, ps);
+                if (!account_event(c, m.cls, m.flags, nwr, ps, ev_e)) { mark_irregular(c); return false; }
+                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && ev_e - ps <= LGW_PENDING_CAP)
+                    extract_usage(c.a, io_of(c), &m, c.block_raw + c.slot, c.warp_raw, lane, c.seg, ps, c.f_delta, c.f_len);
                 c.s_open = last_start; c.tried = 0;
                 if (single) { c.slot = c.dflt; c.t = 0; c.pos = mpos; reset_fields(c, c.slot); continue; }
             }
@@ -828,7 +905,7 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
                     for (;;) {
                         const uint32_t x = find_special(c, q, ev_end, c.high);
                         if (x == R2_NONE || x - mpos > R2_MAX_STR) break;
-                        R2Bytes rd{&c};
+                        R2Bytes rd{io_of(c)};
                         const uint32_t ch = rd.at(x);
                         if (ch == '"') { q = x; ok = true; break; }
                         if (ch != '\\') break;                                                   // a control byte
@@ -844,7 +921,7 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
                     const uint32_t bs = mpos - (t2 - sstart);
                     uint32_t x2 = 0, good = 0;
                     if (lane == 0) {
-                        R2Bytes rd{&c};
+                        R2Bytes rd{io_of(c)};
                         uint32_t st = L_VALUE, p = bs;
                         for (;;) {
                             if (p >= ev_end) break;
@@ -879,19 +956,20 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; reset_fields(c, c.slot); continue; }   // another warp has just published one
             const uint32_t ps = c.s_open;
             const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
-            if (ps > c.tb && ring_byte(c, ps) == '\n') { mark_irregular(c); leave_segment(c, range_hi); return false; }   // LF run >= 3
-            uint32_t cls = PC_NONE, f = 0;
-            const uint32_t e = lean_event(c, ps, ev_end, cls, f, c.high);
+            if (ps > c.tb && ring_byte(c, ps) == '\n') { mark_irregular(c); return false; }   // LF run >= 3
+            const LeanOut lo = lean_event(io_of(c), lane, ps, ev_end);
+            const uint32_t cls = lo.cls, f = lo.f, e = lo.e;
+            c.high |= lo.high;
             if (e == R2_NONE) {
-                if (ev_end < sub_end) { mark_irregular(c); leave_segment(c, range_hi); return false; }   // longer than the carry capacity
+                if (ev_end < sub_end) { mark_irregular(c); return false; }   // longer than the carry capacity
                 c.pos = sub_end;                                                                // open at the end of the text: the carry
                 continue;
             }
-            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { mark_irregular(c); leave_segment(c, range_hi); return false; }
+            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { mark_irregular(c); return false; }
             if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
-            if (!account_event(c, cls, f, 1, ps, e)) { mark_irregular(c); leave_segment(c, range_hi); return false; }
+            if (!account_event(c, cls, f, 1, ps, e)) { mark_irregular(c); return false; }
             if (cls != PC_NONE && (f & PF_VALID_A) && !(f & (TK_ERROR | TK_DETAIL | TK_CODE)) && e - ps >= R2_TPL_MIN && e - ps <= R2_TPL_MAX && c.free_slots) {
-                learn_template(c, ps, sub_end);
+                learn_template(c.a, sh, io_of(c), c.block_raw, lane, c.ready, ps, sub_end);
                 refresh_slots(c);
             }
             c.pos = c.s_open = e + 2; c.t = 0; c.tried = 0;
@@ -968,8 +1046,9 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     for (uint32_t seg = find_segment(a, range_lo); seg < a.n_segs; ++seg) {
         const uint32_t seg_first = seg ? a.s.plan[seg - 1].seg_end : a.tile_base;
         if (seg_first >= range_hi) break;
-        if (!enter_segment(c, seg, r2_max(range_lo, seg_first), range_hi)) { leave_segment(c, range_hi); continue; }
-        if (walk_segment(c, range_hi)) break;
+        const bool done = enter_segment(c, seg, r2_max(range_lo, seg_first), range_hi) && walk_segment(c, range_hi);
+        leave_segment(c, range_hi);
+        if (done) break;
     }
     // ---- the rest of the range is copy only ----
     while (c.k + 1 < c.n_tiles) pipe_advance(c);
