@@ -106,7 +106,7 @@ extern "C" int lgw_engine_create(int device, const lgw_limits* limits, lgw_engin
     ALLOC(e->d_chunk_off, (C + 1) * 4); ALLOC(e->d_seg_chunk, (S + 1) * 4); ALLOC(e->d_seg_slot, S * 4);
     ALLOC(e->d_seg_out, S * sizeof(SegResult));
     ALLOC(e->d_slots, S * 4); ALLOC(e->d_status, S * 4); ALLOC(e->d_state_stage, S * sizeof(StreamState));
-    if ((r = scratch_alloc(e->scratch, S, e->sm_count)) != cudaSuccess) return fail("scratch_alloc", r);
+    if ((r = scratch_alloc(e->scratch, S, B, e->sm_count)) != cudaSuccess) return fail("scratch_alloc", r);
 #undef ALLOC
     if ((r = cudaMemset(e->t.state, 0, S * sizeof(StreamState))) != cudaSuccess) return fail("cudaMemset", r);
     if ((r = cudaMemset(e->d_rowq_count, 0, 16)) != cudaSuccess) return fail("cudaMemset", r);

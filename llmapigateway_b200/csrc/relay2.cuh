@@ -1,4 +1,4 @@
-// Bulk path of the SSE step, round 2:  k_prime2 -> k_relay2 -> k_commit2 -> k_usage_extract.
+// Bulk path of the SSE step, round 2:  k_prime2 -> k_relay2 -> k_commit2.
 // (included from sse_kernels.cuh, inside namespace lgw)
 //
 // What changed against round 1 (relay_kernels.cuh, thread-per-chunk walk of a staged tile):
@@ -20,7 +20,8 @@
 //   * Usage extraction is on the clock: an event that follows a usage-bearing template has its eight fields read
 //     straight from the value spans the match located (number text -> decimal.cuh, strings decoded like the full
 //     machine does) into a per-segment candidate record that k_commit2 installs.  Usage events without such a template
-//     are stashed as before and settled by k_usage_extract at the end of the same step.
+//     are staged in shared memory by k_commit2 and read with the full machine right there: reading a stream's state is a
+//     plain copy, nothing is deferred.
 //
 // Regular streams -- committed (or committing on their first chunk), carries empty and equal at the start of the bulk
 // region, every chunk valid UTF-8 and non-empty, no run of three or more LFs, no event the tap turns into an extra row
@@ -201,10 +202,9 @@ struct R2Ctx {
     uint32_t ready, free_slots;  // bit per slot: template usable / slot empty (refreshed by refresh_slots, the same in every lane)
     uint32_t last_ra;            // position of the last number re-anchor (a mismatch right there is final)
     uint32_t hits_d;             // events matched by the default slot
+    uint32_t status;             // general_step: 1 = the stream goes to the sequential path
     UsageRaw* block_raw;         // [R2_SLOTS] the block's template events' own UsageRaw (global scratch)
     UsageRaw* warp_raw;          // this warp's assembly buffer (global scratch)
-    // usage extraction while following a usage_ok template: this lane's field
-    uint32_t f_delta, f_len;
 };
 
 // Where bytes are read from: the resident tile in shared memory, global memory outside it.  A small value type: the
@@ -312,11 +312,13 @@ R2_DEV void tpl_vec(const R2Ctx& c, uint32_t slot, uint32_t t, uint4& tx, uint4&
 // the 16 pre-shifted copies of slot `slot` (whole warp)
 R2_DEV void build_fast_tables(R2Shared* sh, uint32_t slot, uint32_t lane, uint32_t step) {
     const Tpl2& tp = sh->tpl[slot];
-    const uint32_t P = tp.m.P;
-    for (uint32_t i = lane; i < 16 * R2_TEXT; i += step) {
-        const uint32_t cpy = i / R2_TEXT, j = i - cpy * R2_TEXT;
-        uint32_t x = j + cpy; while (x >= P) x -= P;
-        sh->fast_text[i] = tp.text[x]; sh->fast_lit[i] = tp.lit[x];
+    const uint32_t P = tp.m.P, recip = tp.m.recip;
+    for (uint32_t i4 = lane; i4 < 16 * R2_TEXT / 4; i4 += step) {                 // four bytes per trip (R2_TEXT is a multiple of 4)
+        const uint32_t i = i4 * 4u, cpy = i / R2_TEXT, j = i - cpy * R2_TEXT;
+        uint32_t x = j + cpy; x -= __umulhi(x, recip) * P;
+        uint32_t wt = 0, wl = 0;
+        for (uint32_t b = 0; b < 4; ++b) { wt |= (uint32_t)tp.text[x] << (8 * b); wl |= (uint32_t)tp.lit[x] << (8 * b); if (++x == P) x = 0; }
+        reinterpret_cast<uint32_t*>(sh->fast_text)[i4] = wt; reinterpret_cast<uint32_t*>(sh->fast_lit)[i4] = wl;
     }
 }
 
@@ -657,15 +659,6 @@ R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, U
     __syncwarp();
 }
 
-// this lane's usage field: span length and accumulated shift start from the template's own
-R2_DEV void reset_fields(R2Ctx& c, uint32_t slot) {
-    c.f_delta = 0; c.f_len = 0; c.last_ra = R2_NONE;
-    if (slot < R2_SLOTS && c.lane < 8u && (c.ready & (1u << slot))) {
-        const TplMeta& m = c.sh->tpl[slot].m;
-        const uint32_t fj = m.field_span[c.lane];
-        if (fj != 0xffu) c.f_len = (uint32_t)m.send[fj] - (uint32_t)m.sstart[fj];
-    }
-}
 R2_DEV uint32_t next_slot(const R2Ctx& c) {
     const uint32_t m = c.ready & ~c.tried & ((1u << R2_SLOTS) - 1u);
     return m ? (uint32_t)__ffs(m) - 1u : R2_SLOTS;
@@ -687,7 +680,7 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
         if (tb >= range_hi) return false;
         if (kept) c.in_kept = 1u;                            // the kept chunk is walked by ONE warp, the one that owns its first byte (beyond its range if need be)
         c.pos = c.s_open = c.walk_lo = tb;
-        reset_fields(c, c.slot);
+        c.last_ra = R2_NONE;
         return true;
     }
     // the range starts inside the segment's text: the event that is open there belongs to the previous warp; ours start
@@ -697,7 +690,7 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     if (kept && from < kept) {                                                   // the range starts inside the kept chunk: the warp before walks that to its end;
         if (kept >= range_hi || kept >= te) return false;                        //   the speculation holds only if the chunk ends on a separator, so ours begin right there
         c.pos = c.s_open = kept;
-        reset_fields(c, c.slot);
+        c.last_ra = R2_NONE;
         return true;
     }
     const uint32_t p = find_lflf(c, from - tb >= 2u ? from - 2u : tb, te, c.high);
@@ -707,16 +700,10 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     if ((p > tb && ring_byte(c, p - 1) == '\n') || (s < te && ring_byte(c, s) == '\n')) { mark_irregular(c); return false; }   // LF run >= 3
     if (s >= te) return false;                                                   // the text ends on this separator (the previous warp posts the tail)
     c.pos = c.s_open = s;
-    reset_fields(c, c.slot);
+    c.last_ra = R2_NONE;
     return true;
 }
 
-// first segment whose end lies after `pos` (plans are in byte order)
-R2_DEV uint32_t find_segment(const StepArgs& a, uint32_t pos) {
-    uint32_t lo = 0, hi = a.n_segs;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.s.plan[mid].seg_end <= pos) lo = mid + 1; else hi = mid; }
-    return lo;
-}
 
 // leave the current segment (its text is done as far as this warp is concerned)
 R2_DEV void leave_segment(R2Ctx& c, uint32_t range_hi) {
@@ -728,19 +715,98 @@ R2_DEV void leave_segment(R2Ctx& c, uint32_t range_hi) {
     c.seg = R2_NONE;
 }
 
-// usage fields of the event [ps, e) straight from the value spans the match located (usage_ok templates)
-R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, uint32_t lane, uint32_t seg, uint32_t ps, uint32_t f_delta, uint32_t f_len) {
+// ---- one event against one (non-periodic) slot: hop from value span to value span ------------------------------------------------
+// The judgement of the compare pass for a single event, made span by span instead of window by window: the literal text
+// between two value spans is compared byte for byte (a lane per byte), a number span ends at the first byte that no JSON
+// number holds and must be a valid number (a plain run of digits is judged from the ballot, anything else by the
+// recogniser's number rows), a string span holds plain bytes and valid escapes up to its closing quote.  Usage events and
+// the odd chunks of a stream (role, finish) take this path: ~30 warp-instructions per span instead of a pass per span.
+// ok: the event follows the slot; e = position of its LF LF.  Lanes 0..7 also learn where their usage field sits.
+struct SingleOut { uint32_t ok, e, high, f_start, f_len, f_esc; };
+R2_DEV_NOINLINE SingleOut match_single(R2Io io, const Tpl2* tp, uint32_t lane, uint32_t ps, uint32_t ev_end) {
+    const TplMeta& m = tp->m;
+    SingleOut o; o.ok = 0; o.e = 0; o.high = 0; o.f_start = 0; o.f_len = 0; o.f_esc = 0;
+    const uint32_t my_span = lane < 8u ? (uint32_t)m.field_span[lane] : 0xffu;
+    const uint32_t n_spans = m.n_spans, len = m.len;
+    uint32_t pos = ps, ta = 0, high = 0;
+    for (uint32_t j = 0; j <= n_spans; ++j) {
+        const uint32_t tb = j < n_spans ? (uint32_t)m.sstart[j] : len + 2u;          // literal text [ta, tb) of the image (the last piece ends with LF LF)
+        bool same = true;
+        for (uint32_t off = lane; off < tb - ta; off += 32) {
+            const uint32_t c = pos + off < ev_end ? (uint32_t)io_byte(io, pos + off) : 0x100u;
+            if (c != (uint32_t)tp->text[ta + off]) same = false;
+            high |= c;
+        }
+        if (!__all_sync(R2_FULL, same)) return o;
+        pos += tb - ta;
+        if (j == n_spans) break;
+        uint32_t span_len = 0, esc = 0;
+        if (m.skind[j] == 1) {                                                         // number value
+            const uint32_t c = pos + lane < ev_end ? (uint32_t)io_byte(io, pos + lane) : 0u;
+            const uint32_t cl = io.sh->cls[c & 0xffu];
+            const uint32_t isnum = __ballot_sync(R2_FULL, cl >= C_MINUS && cl <= C_EXP);
+            const uint32_t isdig = __ballot_sync(R2_FULL, cl == C_ZERO || cl == C_DIGIT);
+            const uint32_t run = (uint32_t)__ffs(~isnum) - 1u;                            // (32 number characters in a row: not followed here)
+            if (run == 0u || run >= 32u) return o;
+            const uint32_t runmask = (1u << run) - 1u;
+            const uint32_t first = __shfl_sync(R2_FULL, c, 0);
+            if ((isdig & runmask) != runmask || (run > 1u && first == '0')) {           // sign, fraction, exponent, leading zero: the recogniser's number rows
+                uint32_t good = 0;
+                if (lane == 0) {
+                    uint32_t st = L_VALUE;
+                    for (uint32_t k = 0; k < run && st != L_ERR; ++k) st = io.sh->trans[st * 32 + io.sh->cls[io_byte(io, pos + k)]] & 31u;
+                    good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
+                }
+                if (!__shfl_sync(R2_FULL, good, 0)) return o;
+            }
+            span_len = run;
+        } else {                                                                       // string value
+            uint32_t q = pos;
+            for (;;) {
+                const uint32_t c = q + lane < ev_end ? (uint32_t)io_byte(io, q + lane) : 0u;   // (past the end: reads as a control byte, the scan stops)
+                high |= c;
+                const uint32_t sp = __ballot_sync(R2_FULL, c < 0x20u || c == '"' || c == '\\');
+                if (!sp) { q += 32; if (q - pos > R2_MAX_STR) return o; continue; }
+                const uint32_t k = (uint32_t)__ffs(sp) - 1u, x = q + k;
+                const uint32_t ch = __shfl_sync(R2_FULL, c, (int)k);
+                if (ch == '"') { q = x; break; }
+                if (ch != '\\') return o;                                            // a control byte (or the end of the readable text)
+                const uint32_t e1 = x + 1 < ev_end ? (uint32_t)io_byte(io, x + 1) : 0u;
+                uint32_t el = 0;
+                if (e1 == 'u') { el = 6; for (uint32_t h4 = 2; h4 < 6; ++h4) { const uint32_t h = x + h4 < ev_end ? (uint32_t)io_byte(io, x + h4) : 0u; if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
+                else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
+                if (el == 0) return o;
+                esc = 1; q = x + el;
+                if (q - pos > R2_MAX_STR) return o;
+            }
+            span_len = q - pos;
+        }
+        if (my_span == j) { o.f_start = pos; o.f_len = span_len; o.f_esc = esc; }
+        pos += span_len; ta = m.send[j];
+    }
+    o.ok = 1; o.e = pos - 2u; o.high = high;
+    return o;
+}
+
+// usage fields of the event at ps straight from the value spans the match located (usage_ok templates): numbers through
+// decimal.cuh, strings copied (decoded like the full machine does when they hold escapes), get_token_usage's arithmetic
+// (normalise_usage) on the assembled record -> the segment's candidate record, which k_commit2 installs.
+R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, uint32_t lane, uint32_t seg, uint32_t ps,
+                                   uint32_t f_start, uint32_t f_len, uint32_t f_esc) {
     const TplMeta& m = *mp;
     R2Glob rd{io.data, io.n_bytes};
     Val v; v.kind = KD_ABSENT; v.bits = 0;
     const uint32_t fj = lane < 8u ? m.field_span[lane] : 0xffu;
     for (uint32_t k = lane; k < sizeof(UsageRaw) / 4; k += 32) reinterpret_cast<uint32_t*>(raw)[k] = reinterpret_cast<const uint32_t*>(tpl_raw)[k];
     __syncwarp();
+    const uint32_t slow_str = __ballot_sync(R2_FULL, fj != 0xffu && lane >= UF_MODEL && f_esc != 0u);
     if (fj != 0xffu) {
-        const uint32_t fs = ps + m.sstart[fj] + f_delta;
-        if (lane < UF_MODEL) v = parse_number_span(rd, fs, f_len);
-        else if (lane == UF_MODEL) decode_string_span(rd, fs, f_len, raw->model, raw->model_len, raw->model_flags);
-        else decode_string_span(rd, fs, f_len, raw->provider, raw->provider_len, raw->provider_flags);
+        if (lane < UF_MODEL) v = parse_number_span(rd, f_start, f_len);
+        else if (f_esc) {                                                              // escapes: decode like json_machine.cuh does
+            if (lane == UF_MODEL) decode_string_span(rd, f_start, f_len, raw->model, raw->model_len, raw->model_flags);
+            else decode_string_span(rd, f_start, f_len, raw->provider, raw->provider_len, raw->provider_flags);
+        } else if (lane == UF_MODEL) { raw->model_len = 0; raw->model_flags = 0; }
+        else { raw->provider_len = 0; raw->provider_flags = 0; }
     }
     __syncwarp();
     for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
@@ -752,12 +818,201 @@ R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* m
             else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
         }
     }
+    UsageRec* cand = ap->s.usage_cand + seg;
+    uint32_t has = 0;                                                                  // bit 0: the record carries "model" as a string, bit 1: "provider"
     if (lane == 0) {
-        normalise_usage(*raw, m.full_flags, ap->s.usage_cand[seg]);
+        normalise_usage(*raw, m.full_flags, *cand);
+        has = (cand->model_val.kind == KD_STR ? 1u : 0u) | (cand->provider_val.kind == KD_STR ? 2u : 0u);
+    }
+    has = __shfl_sync(R2_FULL, has, 0);
+    // plain strings (no escapes): the span's bytes ARE the decoded text -- copy them into the record, a lane per byte
+    for (uint32_t which = 0; which < 2; ++which) {
+        const uint32_t fl = UF_MODEL + which;
+        const uint32_t span = m.field_span[fl];
+        const uint32_t st = __shfl_sync(R2_FULL, f_start, (int)fl), ln = __shfl_sync(R2_FULL, f_len, (int)fl);
+        if (span == 0xffu || (slow_str & (1u << fl)) || !(has & (1u << which))) continue;
+        const uint32_t n = ln < LGW_STR_CAP ? ln : (uint32_t)LGW_STR_CAP;
+        char* dst = which == 0 ? cand->model : cand->provider;
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = (char)rd.at(st + k);
+        if (lane == 0) {
+            if (which == 0) cand->model_len = (uint8_t)n; else cand->provider_len = (uint8_t)n;
+            if (ln > LGW_STR_CAP) { cand->str_flags |= which == 0 ? 1u : 4u; cand->exotic = 1; }      // truncated: reported, like the full machine's capture
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
         __threadfence();
         ap->s.plan[seg].cand_ps = ps + 1u;
     }
     __syncwarp();
+}
+
+// One step of the walk that the fast loop cannot take: an event against a non-default slot, a compare pass with boundary
+// lanes / limits / a mismatch to classify, or the byte-wise recogniser.  Out of line, the context goes in and comes back by
+// value: the fast loop in walk_segment then keeps its few live values in registers.
+R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32_t range_hi) {
+    R2Shared* sh = c.sh;
+    const StepArgs& a = *c.a;
+    const uint32_t lane = c.lane;
+    TemplateCache2* tc = a.s.tpl_cache2;
+    {
+        if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
+            c.tried |= 1u << c.slot; c.slot = next_slot(c);
+            return c;
+        }
+        if (c.slot < R2_SLOTS && (c.slot != c.dflt || (sh->tpl[c.slot].m.flags & TK_USAGE))) {
+            // ---- one event against a slot that is not the periodic default: span by span ----
+            const TplMeta& m = sh->tpl[c.slot].m;
+            const uint32_t ps = c.s_open;
+            const SingleOut so = match_single(io_of(c), &sh->tpl[c.slot], lane, ps, r2_min(sub_end, ps + a.t.carry_cap + 2u));
+            if (so.ok) {
+                c.high |= so.high;
+                if (c.slot == c.dflt) c.hits_d += 1u; else if (lane == 0) atomicAdd(&tc->hits[c.slot], 1u);
+                if (!account_event(c, m.cls, m.flags, 1, ps, so.e)) { c.status = 1u; return c; }
+                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP)
+                    extract_usage(c.a, io_of(c), &m, c.block_raw + c.slot, c.warp_raw, lane, c.seg, ps, so.f_start, so.f_len, so.f_esc);
+                c.pos = c.s_open = so.e + 2u; c.t = 0; c.tried = 0; c.last_ra = R2_NONE;
+                c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
+            } else {                                                       // the event does not follow this slot: the next one
+                c.tried |= 1u << c.slot;
+                c.slot = next_slot(c);
+            }
+            return c;
+        }
+        if (c.slot < R2_SLOTS) {
+            const TplMeta& m = sh->tpl[c.slot].m;
+            const uint32_t P = m.P;
+            // ---- compare pass: up to 512 bytes from pos against the periodic image ----
+            const uint32_t wbase = c.pos & ~15u;
+            uint32_t lim = r2_min(sub_end, wbase + 512u);
+            if (c.pos >= c.tile_lo && c.pos < c.tile_hi) lim = r2_min(lim, c.tile_hi);          // windows do not straddle the resident tile's end
+            if (wbase + 512u > range_hi && !c.in_kept) {                                    // stop at the first event boundary in the next range
+                const uint32_t nb = c.pos + (P - c.t);
+                uint32_t b = nb;
+                if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
+                lim = r2_min(lim, b);
+            }
+            const uint32_t lp = wbase + 16u * lane;
+            const uint32_t u = c.t + P + 16u * lane - (c.pos & 15u);
+            const uint32_t tl = u - __umulhi(u, m.recip) * P;
+            uint4 tx, mk;
+            tpl_vec(c, c.slot, tl, tx, mk);
+            const bool active = lp < lim;
+            const uint4 d = active ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
+            c.high |= d.x | d.y | d.z | d.w;
+            const uint32_t r0 = (d.x ^ tx.x) & mk.x, r1 = (d.y ^ tx.y) & mk.y, r2 = (d.z ^ tx.z) & mk.z, r3 = (d.w ^ tx.w) & mk.w;
+            const uint32_t s0 = ~span_ok(d.x, mk.x) & 0x80808080u, s1 = ~span_ok(d.y, mk.y) & 0x80808080u;
+            const uint32_t s2 = ~span_ok(d.z, mk.z) & 0x80808080u, s3 = ~span_ok(d.w, mk.w) & 0x80808080u;
+            uint32_t bad = (r0 | r1 | r2 | r3 | s0 | s1 | s2 | s3) != 0 ? 1u : 0u;
+            uint32_t bm = 0xFFFFu;                                                              // bytes of this lane that count
+            if (lp < c.pos || lp + 16u > lim) {
+                if (lp < c.pos) bm &= c.pos - lp >= 16u ? 0u : (0xFFFFu << (c.pos - lp));
+                if (lp + 16u > lim) bm &= lp >= lim ? 0u : (0xFFFFu >> (lp + 16u - lim));
+                if (bad) {
+                    const uint32_t bb = movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12);
+                    bad = (bb & bm) != 0 ? 1u : 0u;
+                }
+            }
+            const uint32_t any = __ballot_sync(R2_FULL, active && bad);
+            uint32_t mpos = lim;
+            if (any) {
+                const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+                uint32_t bb = 0;
+                if (lane == fl) bb = (movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12)) & bm;
+                bb = __shfl_sync(R2_FULL, bb, (int)fl);
+                mpos = wbase + 16u * fl + ((uint32_t)__ffs(bb) - 1u);
+            }
+            // ---- events completed by the pass ----
+            const uint32_t u2 = c.t + (mpos - c.pos);
+            const uint32_t nwr = __umulhi(u2, m.recip);                                           // separators passed
+            const uint32_t t2 = u2 - nwr * P;
+            if (nwr) {
+                const uint32_t last_start = mpos - t2;                                           // start of the event that is open now
+                c.hits_d += nwr;
+                if (!account_event(c, m.cls, m.flags, nwr, c.s_open, last_start - 2u)) { c.status = 1u; return c; }
+                c.s_open = last_start; c.tried = 0;
+            }
+            c.pos = mpos; c.t = t2;
+            if (!any) return c;                                                                  // the pass ran to its limit
+            // ---- a mismatch at mpos, template offset t2: inside a value span? ----
+            const uint32_t id = (t2 < m.len && mpos != c.last_ra) ? sh->tpl[c.slot].span_id[t2] : 0xffu;
+            bool ok = false;
+            if (id != 0xffu) {
+                const uint32_t sstart = m.sstart[id], send = m.send[id];
+                const uint32_t ev_end = r2_min(sub_end, c.s_open + a.t.carry_cap + 2u);
+                if (m.skind[id] == 0) {                                                          // string value: plain bytes and valid escapes up to the closing quote
+                    uint32_t q = mpos;
+                    for (;;) {
+                        const uint32_t x = find_special(c, q, ev_end, c.high);
+                        if (x == R2_NONE || x - mpos > R2_MAX_STR) break;
+                        R2Bytes rd{io_of(c)};
+                        const uint32_t ch = rd.at(x);
+                        if (ch == '"') { q = x; ok = true; break; }
+                        if (ch != '\\') break;                                                   // a control byte
+                        const uint32_t e1 = rd.at(x + 1);
+                        uint32_t el = 0;
+                        if (e1 == 'u') { el = 6; for (uint32_t j = 2; j < 6; ++j) { const uint32_t h = rd.at(x + j); if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
+                        else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
+                        if (el == 0 || x + el > ev_end) break;
+                        q = x + el;
+                    }
+                    if (ok) { c.pos = q; c.t = send; }                                          // (the closing quote itself is compared by the next pass)
+                } else {                                                                          // number value: the event's own number must be valid
+                    const uint32_t bs = mpos - (t2 - sstart);
+                    uint32_t x2 = 0, good = 0;
+                    if (lane == 0) {
+                        R2Bytes rd{io_of(c)};
+                        uint32_t st = L_VALUE, p = bs;
+                        for (;;) {
+                            if (p >= ev_end) break;
+                            const uint32_t cl = rd.cls(rd.at(p));
+                            if (cl < C_MINUS || cl > C_EXP) break;
+                            st = rd.trans(st * 32 + cl) & 31u;
+                            if (st == L_ERR) break;
+                            ++p;
+                        }
+                        good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
+                        x2 = p;
+                    }
+                    x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
+                    if (good && x2 >= mpos) { c.pos = x2; c.t = send; c.last_ra = x2; ok = true; }
+                }
+            }
+            if (ok) return c;
+            // the event does not follow this slot: rewind to its start and try the next one
+            c.tried |= 1u << c.slot;
+            c.pos = c.s_open; c.t = 0; c.last_ra = R2_NONE;
+            c.slot = next_slot(c);
+            return c;
+        }
+        // ---- no template fits: the byte-wise recogniser walks the event ----
+        {
+            refresh_slots(c);
+            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; return c; }   // another warp has just published one
+            const uint32_t ps = c.s_open;
+            const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
+            if (ps > c.tb && ring_byte(c, ps) == '\n') { c.status = 1u; return c; }   // LF run >= 3
+            const LeanOut lo = lean_event(io_of(c), lane, ps, ev_end);
+            const uint32_t cls = lo.cls, f = lo.f, e = lo.e;
+            c.high |= lo.high;
+            if (e == R2_NONE) {
+                if (ev_end < sub_end) { c.status = 1u; return c; }   // longer than the carry capacity
+                c.pos = sub_end;                                                                // open at the end of the text: the carry
+                return c;
+            }
+            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { c.status = 1u; return c; }
+            if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
+            if (!account_event(c, cls, f, 1, ps, e)) { c.status = 1u; return c; }
+            if (cls != PC_NONE && (f & PF_VALID_A) && !(f & (TK_ERROR | TK_DETAIL | TK_CODE)) && e - ps >= R2_TPL_MIN && e - ps <= R2_TPL_MAX && c.free_slots) {
+                learn_template(c.a, sh, io_of(c), c.block_raw, lane, c.ready, ps, sub_end);
+                refresh_slots(c);
+            }
+            c.pos = c.s_open = e + 2; c.t = 0; c.tried = 0;
+            c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
+            c.last_ra = R2_NONE;
+        }
+    }
+    return c;
 }
 
 // Walk the current segment from c.pos.  Returns true when the warp is done (the open event starts in the next warp's
@@ -827,155 +1082,8 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             }
         }
 
-        if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
-            c.tried |= 1u << c.slot; c.slot = next_slot(c); reset_fields(c, c.slot);
-            continue;
-        }
-        if (c.slot < R2_SLOTS) {
-            const TplMeta& m = sh->tpl[c.slot].m;
-            const uint32_t P = m.P;
-            const bool single = c.slot != c.dflt || (m.flags & TK_USAGE) != 0;
-            // ---- compare pass: up to 512 bytes from pos against the periodic image ----
-            const uint32_t wbase = c.pos & ~15u;
-            uint32_t lim = r2_min(sub_end, wbase + 512u);
-            if (c.pos >= c.tile_lo && c.pos < c.tile_hi) lim = r2_min(lim, c.tile_hi);          // windows do not straddle the resident tile's end
-            if (single) lim = r2_min(lim, c.pos + (P - c.t));                                   // one event, then back to the default slot
-            else if (wbase + 512u > range_hi && !c.in_kept) {                                    // stop at the first event boundary in the next range
-                const uint32_t nb = c.pos + (P - c.t);
-                uint32_t b = nb;
-                if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
-                lim = r2_min(lim, b);
-            }
-            const uint32_t lp = wbase + 16u * lane;
-            const uint32_t u = c.t + P + 16u * lane - (c.pos & 15u);
-            const uint32_t tl = u - __umulhi(u, m.recip) * P;
-            uint4 tx, mk;
-            tpl_vec(c, c.slot, tl, tx, mk);
-            const bool active = lp < lim;
-            const uint4 d = active ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
-            c.high |= d.x | d.y | d.z | d.w;
-            const uint32_t r0 = (d.x ^ tx.x) & mk.x, r1 = (d.y ^ tx.y) & mk.y, r2 = (d.z ^ tx.z) & mk.z, r3 = (d.w ^ tx.w) & mk.w;
-            const uint32_t s0 = ~span_ok(d.x, mk.x) & 0x80808080u, s1 = ~span_ok(d.y, mk.y) & 0x80808080u;
-            const uint32_t s2 = ~span_ok(d.z, mk.z) & 0x80808080u, s3 = ~span_ok(d.w, mk.w) & 0x80808080u;
-            uint32_t bad = (r0 | r1 | r2 | r3 | s0 | s1 | s2 | s3) != 0 ? 1u : 0u;
-            uint32_t bm = 0xFFFFu;                                                              // bytes of this lane that count
-            if (lp < c.pos || lp + 16u > lim) {
-                if (lp < c.pos) bm &= c.pos - lp >= 16u ? 0u : (0xFFFFu << (c.pos - lp));
-                if (lp + 16u > lim) bm &= lp >= lim ? 0u : (0xFFFFu >> (lp + 16u - lim));
-                if (bad) {
-                    const uint32_t bb = movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12);
-                    bad = (bb & bm) != 0 ? 1u : 0u;
-                }
-            }
-            const uint32_t any = __ballot_sync(R2_FULL, active && bad);
-            uint32_t mpos = lim;
-            if (any) {
-                const uint32_t fl = (uint32_t)__ffs(any) - 1u;
-                uint32_t bb = 0;
-                if (lane == fl) bb = (movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12)) & bm;
-                bb = __shfl_sync(R2_FULL, bb, (int)fl);
-                mpos = wbase + 16u * fl + ((uint32_t)__ffs(bb) - 1u);
-            }
-            // ---- events completed by the pass ----
-            const uint32_t u2 = c.t + (mpos - c.pos);
-            const uint32_t nwr = __umulhi(u2, m.recip);                                           // separators passed
-            const uint32_t t2 = u2 - nwr * P;
-            if (nwr) {
-                const uint32_t last_start = mpos - t2;                                           // start of the event that is open now
-                const uint32_t ev_e = last_start - 2u;                                           // LF LF of the last completed event
-                const uint32_t ps = c.s_open;                                                    // (a usage event is matched alone: its start)
-                if (c.slot == c.dflt) c.hits_d += nwr; else if (lane == 0) atomicAdd(&tc->hits[c.slot], nwr);
-                if (!account_event(c, m.cls, m.flags, nwr, ps, ev_e)) { mark_irregular(c); return false; }
-                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && ev_e - ps <= LGW_PENDING_CAP)
-                    extract_usage(c.a, io_of(c), &m, c.block_raw + c.slot, c.warp_raw, lane, c.seg, ps, c.f_delta, c.f_len);
-                c.s_open = last_start; c.tried = 0;
-                if (single) { c.slot = c.dflt; c.t = 0; c.pos = mpos; reset_fields(c, c.slot); continue; }
-            }
-            c.pos = mpos; c.t = t2;
-            if (!any) continue;                                                                  // the pass ran to its limit
-            // ---- a mismatch at mpos, template offset t2: inside a value span? ----
-            const uint32_t id = (t2 < m.len && mpos != c.last_ra) ? sh->tpl[c.slot].span_id[t2] : 0xffu;
-            bool ok = false;
-            if (id != 0xffu) {
-                const uint32_t sstart = m.sstart[id], send = m.send[id];
-                const uint32_t ev_end = r2_min(sub_end, c.s_open + a.t.carry_cap + 2u);
-                uint32_t ev_len = 0;
-                if (m.skind[id] == 0) {                                                          // string value: plain bytes and valid escapes up to the closing quote
-                    uint32_t q = mpos;
-                    for (;;) {
-                        const uint32_t x = find_special(c, q, ev_end, c.high);
-                        if (x == R2_NONE || x - mpos > R2_MAX_STR) break;
-                        R2Bytes rd{io_of(c)};
-                        const uint32_t ch = rd.at(x);
-                        if (ch == '"') { q = x; ok = true; break; }
-                        if (ch != '\\') break;                                                   // a control byte
-                        const uint32_t e1 = rd.at(x + 1);
-                        uint32_t el = 0;
-                        if (e1 == 'u') { el = 6; for (uint32_t j = 2; j < 6; ++j) { const uint32_t h = rd.at(x + j); if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
-                        else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
-                        if (el == 0 || x + el > ev_end) break;
-                        q = x + el;
-                    }
-                    if (ok) { ev_len = q - (mpos - (t2 - sstart)); c.pos = q; c.t = send; }      // (the closing quote itself is compared by the next pass)
-                } else {                                                                          // number value: the event's own number must be valid
-                    const uint32_t bs = mpos - (t2 - sstart);
-                    uint32_t x2 = 0, good = 0;
-                    if (lane == 0) {
-                        R2Bytes rd{io_of(c)};
-                        uint32_t st = L_VALUE, p = bs;
-                        for (;;) {
-                            if (p >= ev_end) break;
-                            const uint32_t cl = rd.cls(rd.at(p));
-                            if (cl < C_MINUS || cl > C_EXP) break;
-                            st = rd.trans(st * 32 + cl) & 31u;
-                            if (st == L_ERR) break;
-                            ++p;
-                        }
-                        good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
-                        x2 = p;
-                    }
-                    x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
-                    if (good && x2 >= mpos) { ev_len = x2 - bs; c.pos = x2; c.t = send; c.last_ra = x2; ok = true; }
-                }
-                if (ok && lane < 8u) {                                                           // this lane's usage field follows the shift
-                    const uint32_t fj = m.field_span[lane];
-                    if (fj != 0xffu) { if (fj == id) c.f_len = ev_len; else if ((uint32_t)m.sstart[fj] >= send) c.f_delta += ev_len - (send - sstart); }
-                }
-            }
-            if (ok) continue;
-            // the event does not follow this slot: rewind to its start and try the next one
-            c.tried |= 1u << c.slot;
-            c.pos = c.s_open; c.t = 0;
-            c.slot = next_slot(c);
-            reset_fields(c, c.slot);
-            continue;
-        }
-        // ---- no template fits: the byte-wise recogniser walks the event ----
-        {
-            refresh_slots(c);
-            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; reset_fields(c, c.slot); continue; }   // another warp has just published one
-            const uint32_t ps = c.s_open;
-            const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
-            if (ps > c.tb && ring_byte(c, ps) == '\n') { mark_irregular(c); return false; }   // LF run >= 3
-            const LeanOut lo = lean_event(io_of(c), lane, ps, ev_end);
-            const uint32_t cls = lo.cls, f = lo.f, e = lo.e;
-            c.high |= lo.high;
-            if (e == R2_NONE) {
-                if (ev_end < sub_end) { mark_irregular(c); return false; }   // longer than the carry capacity
-                c.pos = sub_end;                                                                // open at the end of the text: the carry
-                continue;
-            }
-            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { mark_irregular(c); return false; }
-            if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
-            if (!account_event(c, cls, f, 1, ps, e)) { mark_irregular(c); return false; }
-            if (cls != PC_NONE && (f & PF_VALID_A) && !(f & (TK_ERROR | TK_DETAIL | TK_CODE)) && e - ps >= R2_TPL_MIN && e - ps <= R2_TPL_MAX && c.free_slots) {
-                learn_template(c.a, sh, io_of(c), c.block_raw, lane, c.ready, ps, sub_end);
-                refresh_slots(c);
-            }
-            c.pos = c.s_open = e + 2; c.t = 0; c.tried = 0;
-            c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
-            reset_fields(c, c.slot);
-        }
+        c = general_step(c, sub_end, range_hi);
+        if (c.status) { c.status = 0; mark_irregular(c); return false; }
     }
 }
 
@@ -1031,11 +1139,11 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     c.n_bytes = a.n_bytes;
     c.base = base0 + t_first * R2_TILE;
     c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
-    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0;
+    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0; c.status = 0;
     refresh_slots(c);
     c.block_raw = block_raw; c.warp_raw = a.s.raw_scratch + (size_t)R2_BID * (R2_WARPS + R2_SLOTS) + warp;
     c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
-    c.slot = c.dflt; c.t = 0; c.tried = 0; c.pos = c.s_open = 0; c.f_delta = 0; c.f_len = 0;
+    c.slot = c.dflt; c.t = 0; c.tried = 0; c.pos = c.s_open = 0;
     c.in_kept = c.primed = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;
     if (c.n_tiles == 0) return;
     const uint32_t range_lo = r2_max(c.base, a.tile_base);          // (tile_base = first byte of this launch; a slice starts inside tile 0)
@@ -1043,7 +1151,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     pipe_start(c);
     pipe_advance(c);
 
-    for (uint32_t seg = find_segment(a, range_lo); seg < a.n_segs; ++seg) {
+    for (uint32_t seg = a.s.tile_seg[t_first]; seg < a.n_segs; ++seg) {            // (the segment that holds the range's first byte: k_prime2's table)
         const uint32_t seg_first = seg ? a.s.plan[seg - 1].seg_end : a.tile_base;
         if (seg_first >= range_hi) break;
         const bool done = enter_segment(c, seg, r2_max(range_lo, seg_first), range_hi) && walk_segment(c, range_hi);
@@ -1065,7 +1173,6 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
 R2_GLOBAL void k_prime2(StepArgs a) {
     const uint32_t i = R2_BID * R2_NTHR + R2_TID;
     if (i == 0) {
-        *a.s.pend_count = 0;
         TemplateCache2* tc = a.s.tpl_cache2;
         uint32_t total = 0, full = 1, lo = 0;
         for (uint32_t s = 0; s < R2_SLOTS; ++s) { total += tc->hits[s]; if (tc->state[s] != 2u) full = 0; if (tc->hits[s] < tc->hits[lo]) lo = s; }
@@ -1095,17 +1202,56 @@ R2_GLOBAL void k_prime2(StepArgs a) {
         } else if (c < c1) p.irregular = 1;                                    // an event is open from an earlier step
     }
     a.s.plan[seg] = p;
+    // the byte tiles whose first byte lies in this segment: where the bulk kernel's warps start looking
+    const uint32_t base0 = a.tile_base & ~15u;
+    const uint32_t b0 = a.chunk_off[c0], b1 = p.seg_end;
+    if (b1 > b0) {
+        uint32_t t_lo = seg == 0 ? 0u : (b0 - base0 + R2_TILE - 1) / R2_TILE;        // (tile 0 starts at the launch's first byte)
+        const uint32_t t_hi = (b1 - 1 - base0) / R2_TILE;
+        for (uint32_t t = t_lo; t <= t_hi; ++t) a.s.tile_seg[t] = seg;
+    }
 }
 
 // ---- k_commit2 (one warp per segment) ----------------------------------------------------------------------------------------------
-R2_GLOBAL void k_commit2(StepArgs a) {
-    const uint32_t seg = (R2_BID * R2_NTHR + R2_TID) >> 5, lane = R2_TID & 31u;
+#define R2_CWARPS 8u
+// the exact sequential machine over a stream's chunks (streams the bulk kernel could not vouch for), out of line
+R2_DEV_NOINLINE uint32_t commit_sequential(StepIO io, const uint8_t* data, const uint32_t* chunk_off, uint32_t c_from, uint32_t c_to, uint32_t emit_begin) {
+    run_chunks(io, data, chunk_off, c_from, c_to, emit_begin, false);
+    return emit_begin;
+}
+// a usage event that followed no usage template: the full machine over its staged text (chat_logging.py:123-135 ->
+// get_token_usage :233-272), exactly what the sequential path does for the event
+R2_DEV_NOINLINE void commit_usage_event(StepIO io, const uint8_t* text, uint32_t n) {
+    StreamHdr& st = *io.st;
+    Rope r{nullptr, 0, text, n};
+    const uint8_t cls = classify_part(r, 0, n);
+    UsageRaw raw;
+    const uint32_t f = parse_part<true>(r, 0, n, cls, &raw);
+    if (f & PF_EXOTIC) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; return; }
+    if ((f & TK_CHOICES) && (f & PF_TYPE_ERROR)) return;
+    normalise_usage(raw, f, *io.rec);
+    st.flags |= SF_REC_VALID; ++st.n_usage_b;
+    if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+}
+R2_DEV_NOINLINE void commit_settle_pending(StepIO io) { resolve_pending(io); }
+
+R2_GLOBAL void
+#if !R2_HOST_EMU
+__launch_bounds__(R2_CWARPS * 32, 6)      // (the full machine behind commit_usage_event / commit_sequential spills instead of costing every warp 142 registers)
+#endif
+k_commit2(StepArgs a) {
+#if !R2_HOST_EMU
+    __shared__ __align__(16) uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
+#else
+    static uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
+#endif
+    const uint32_t seg = (R2_BID * R2_NTHR + R2_TID) >> 5, lane = R2_TID & 31u, warp = (R2_TID >> 5) % R2_CWARPS;
     if (seg >= a.n_segs) return;
-    const uint32_t c1 = a.seg_chunk[seg + 1];
-    const uint32_t slot = a.seg_slot[seg];
+    const uint32_t c1 = __ldg(a.seg_chunk + seg + 1);
+    const uint32_t slot = __ldg(a.seg_slot + seg);
+    const SegPlan p = a.s.plan[seg];
     StreamHdr st = a.t.state[slot].h;                     // (every lane holds a copy; lane 0's is the one written back)
     const StepIO io = make_io(a, slot, &st);
-    const SegPlan p = a.s.plan[seg];
     uint32_t emit_begin = p.emit_chunk_begin;
     const bool speculated = p.kept_chunk != 0xFFFFFFFFu;
     if ((st.phase == PH_COMMITTED || st.phase == PH_PRIMING) && p.resume_chunk < c1) {
@@ -1120,10 +1266,7 @@ R2_GLOBAL void k_commit2(StepArgs a) {
         if (!sequential && p.tail_start == 0xFFFFFFFFu) sequential = true;                        // (nobody reached the end of the text)
         if (lane == 0) atomicAdd(a.s.counters + (sequential ? 0 : 1), 1u);
         if (sequential) {
-            if (lane == 0) {
-                emit_begin = (st.phase == PH_COMMITTED) ? p.resume_chunk : c1;
-                run_chunks(io, a.data, a.chunk_off, p.resume_chunk, c1, emit_begin, false);
-            }
+            if (lane == 0) emit_begin = commit_sequential(io, a.data, a.chunk_off, p.resume_chunk, c1, (st.phase == PH_COMMITTED) ? p.resume_chunk : c1);
         } else {
             uint32_t first = p.resume_chunk;
             if (speculated) {                       // apply the verified commit (request_handler.py:89-90, chat_logging.py:200)
@@ -1138,7 +1281,7 @@ R2_GLOBAL void k_commit2(StepArgs a) {
             st.n_events_a += p.n_events_a; st.n_events_b += p.n_events_b;
             if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
             if (p.last_usage) {                     // the last usage-bearing event wins (chat_logging.py:134-135)
-                if (lane == 0 && (st.flags & SF_PENDING)) resolve_pending(io);     // an older stash must be settled first
+                if (lane == 0 && (st.flags & SF_PENDING)) commit_settle_pending(io);   // (a stash left by an older engine version of this stream)
                 if (p.cand_ps == ups + 1u) {
                     // its fields were read from the matched template spans: install the candidate record
                     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.s.usage_cand + seg);
@@ -1148,15 +1291,10 @@ R2_GLOBAL void k_commit2(StepArgs a) {
                     if (a.s.usage_cand[seg].exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
                     if (lane == 0) atomicAdd(a.s.counters + 2, 1u);
                 } else {
-                    // stash its text as whole 16-byte vectors; k_usage_extract reads the values out at the end of the step
-                    const uint32_t off = ups & 15u, nv = (off + ulen + 15u) >> 4;
-                    if (((size_t)(ups - off) + ((size_t)nv << 4)) <= a.n_bytes) {
-                        const uint4* src = reinterpret_cast<const uint4*>(d + (ups - off));
-                        uint4* dst = reinterpret_cast<uint4*>(io.pending);
-                        for (uint32_t k = lane; k < nv; k += 32) dst[k] = __ldg(src + k);
-                    } else { for (uint32_t k = lane; k < ulen; k += 32) io.pending[off + k] = __ldg(d + ups + k); }
-                    st.pending_len = ulen | (off << 16); st.flags |= SF_PENDING; ++st.n_usage_b;
-                    if (lane == 0) { const uint32_t q = atomicAdd(a.s.pend_count, 1u); if (q < a.t.max_streams) a.s.pend_list[q] = slot; atomicAdd(a.s.counters + 3, 1u); }
+                    // no usage template: stage its text in shared memory and read the values out with the full machine now
+                    for (uint32_t k = lane; k < ulen; k += 32) stage[warp][k] = __ldg(d + ups + k);
+                    __syncwarp();
+                    if (lane == 0) { commit_usage_event(io, stage[warp], ulen); atomicAdd(a.s.counters + 3, 1u); }
                 }
             }
             // new carry = text after the last separator (both loops: SF_SYNCED)
@@ -1171,40 +1309,6 @@ R2_GLOBAL void k_commit2(StepArgs a) {
         SegResult res;
         fill_seg_result(st, emit_begin, c1, res);
         a.seg_out[seg] = res;
-    }
-}
-
-// ---- k_usage_extract (one warp per stashed usage event) -----------------------------------------------------------------------------
-// Usage events that followed no usage template were stashed by k_commit2; their values are read out here, at the end of
-// the same step (chat_logging.py:134-135 -> get_token_usage :233-272), so that reading a stream's state is a plain copy.
-#define R2_XWARPS 4u
-R2_GLOBAL void k_usage_extract(StepArgs a) {
-#if !R2_HOST_EMU
-    __shared__ __align__(16) uint8_t stage[R2_XWARPS][LGW_PENDING_STRIDE];
-#else
-    static uint8_t stage[R2_XWARPS][LGW_PENDING_STRIDE];
-#endif
-    uint32_t n = *a.s.pend_count;
-    if (n > a.t.max_streams) n = a.t.max_streams;
-    const uint32_t warp = R2_TID >> 5, lane = R2_TID & 31u;
-    for (uint32_t i = R2_BID * R2_XWARPS + warp; i < n; i += R2_NBLK * R2_XWARPS) {
-        const uint32_t slot = a.s.pend_list[i];
-        StreamState* s = a.t.state + slot;
-        StreamHdr st = s->h;
-        if (st.flags & SF_PENDING) {
-            const uint8_t* src = a.t.pending + (size_t)slot * LGW_PENDING_STRIDE;
-            for (uint32_t k = lane; k < LGW_PENDING_STRIDE / 16; k += 32) reinterpret_cast<uint4*>(stage[warp])[k] = reinterpret_cast<const uint4*>(src)[k];
-            __syncwarp();
-            if (lane == 0) {
-                StepIO io;
-                io.st = &st; io.rec = &s->rec; io.pending = stage[warp];
-                io.carry_a = io.carry_b = io.detail = nullptr; io.carry_cap = io.detail_cap = 0;
-                io.rowq = nullptr; io.rowq_count = nullptr; io.rowq_cap = 0; io.slot = slot;
-                resolve_pending(io);
-                s->h = st;
-            }
-        }
-        __syncwarp();
     }
 }
 
@@ -1223,12 +1327,8 @@ static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cuda
         k_relay2<<<blocks, R2_THREADS, R2_SMEM_BYTES, stream>>>(a, n_tiles, tpw, base0); ++*launched;
     }
     if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
-    if (a.n_segs) { k_commit2<<<(a.n_segs + 7) / 8, 256, 0, stream>>>(a); ++*launched; }
+    if (a.n_segs) { k_commit2<<<(a.n_segs + R2_CWARPS - 1) / R2_CWARPS, R2_CWARPS * 32, 0, stream>>>(a); ++*launched; }
     if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
-    if (a.n_segs) {
-        uint32_t xb = (a.n_segs + R2_XWARPS - 1) / R2_XWARPS; if (xb > (uint32_t)sm_count * 4u) xb = (uint32_t)sm_count * 4u;
-        k_usage_extract<<<xb, R2_XWARPS * 32, 0, stream>>>(a); ++*launched;
-    }
     if ((r = cudaEventRecord(ev[4], stream)) != cudaSuccess) return r;
     return cudaGetLastError();
 }

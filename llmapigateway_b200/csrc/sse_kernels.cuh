@@ -9,7 +9,6 @@
 //   k_commit2  one warp per segment: folds the bulk kernel's findings into the persistent stream state; streams
 //              the bulk kernel flagged irregular (or whose speculation failed) are redone sequentially with the
 //              exact machine.
-//   k_usage_extract  settles the usage events that had to be stashed (no usage template) at the end of the step.
 //   k_general  (mode 1 / fix-up) the exact sequential machine over whole segments.
 #pragma once
 #include <cuda_runtime.h>
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(256) k_copy(const uint8_t* __restrict__ in, ui
 
 #include "relay2.cuh"
 
-static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, int sm_count) {
+static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size_t max_bytes, int sm_count) {
     cudaError_t r;
     if ((r = cudaMalloc((void**)&s.plan, max_streams * sizeof(SegPlan))) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.tpl_cache2, sizeof(TemplateCache2))) != cudaSuccess) return r;
@@ -77,20 +76,19 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, int 
     s.raw_blocks = (uint32_t)sm_count;
     if ((r = cudaMalloc((void**)&s.raw_scratch, (size_t)s.raw_blocks * (R2_WARPS + R2_SLOTS) * sizeof(UsageRaw))) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.usage_cand, max_streams * sizeof(UsageRec))) != cudaSuccess) return r;
-    if ((r = cudaMalloc((void**)&s.pend_list, (max_streams + 1) * 4)) != cudaSuccess) return r;
-    s.pend_count = s.pend_list + max_streams;
-    if ((r = cudaMemset(s.pend_count, 0, 4)) != cudaSuccess) return r;
+    if ((r = cudaMalloc((void**)&s.tile_seg, (max_bytes / R2_TILE + 4) * 4)) != cudaSuccess) return r;
+    if ((r = cudaMemset(s.tile_seg, 0, (max_bytes / R2_TILE + 4) * 4)) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.counters, 64)) != cudaSuccess) return r;
     if ((r = cudaMemset(s.counters, 0, 64)) != cudaSuccess) return r;
     if ((r = cudaFuncSetAttribute(k_relay2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM_BYTES)) != cudaSuccess) return r;
     return cudaSuccess;
 }
 static inline void scratch_free(StepScratch& s) {
-    cudaFree(s.plan); cudaFree(s.tpl_cache2); cudaFree(s.raw_scratch); cudaFree(s.usage_cand); cudaFree(s.pend_list); cudaFree(s.counters); s.counters = nullptr;
-    s.plan = nullptr; s.tpl_cache2 = nullptr; s.raw_scratch = nullptr; s.usage_cand = nullptr; s.pend_list = nullptr; s.pend_count = nullptr;
+    cudaFree(s.plan); cudaFree(s.tpl_cache2); cudaFree(s.raw_scratch); cudaFree(s.usage_cand); cudaFree(s.counters); s.counters = nullptr; cudaFree(s.tile_seg); s.tile_seg = nullptr;
+    s.plan = nullptr; s.tpl_cache2 = nullptr; s.raw_scratch = nullptr; s.usage_cand = nullptr;
 }
 
-// Launch one step on `stream`.  ev[0..4] bracket prime / relay / commit / usage extract.
+// Launch one step on `stream`.  ev[0..3] bracket prime / relay / commit (ev[4] = ev[3]: usage extraction is inside relay and commit).
 static inline cudaError_t launch_step(const StepArgs& a, int mode, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
     *launched = 0;
     cudaError_t r;

@@ -1,4 +1,4 @@
-// TEST AID ONLY: the bulk kernels of csrc/relay2.cuh (k_prime2, k_relay2, k_commit2, k_usage_extract) compiled for the
+// TEST AID ONLY: the bulk kernels of csrc/relay2.cuh (k_prime2, k_relay2, k_commit2) compiled for the
 // host over a small SIMT emulator (simt_emu.h: fibers as lanes, rendezvous collectives, instant TMA), so that the CPU
 // test-suite can run the very kernel code against the sequential machine, the goldens and the oracle without a GPU.
 // Never linked into the product library; the product has no CPU path.
@@ -25,8 +25,8 @@ struct HostEngine {
     std::vector<uint8_t> cache;          // TemplateCache2
     std::vector<UsageRaw> raw;
     std::vector<UsageRec> cand;
-    std::vector<uint32_t> pend;
     uint32_t counters[16] = {0};
+    std::vector<uint32_t> tile_seg;
     std::vector<RowEvent> rowq; uint32_t rowq_count;
     int mode;
 };
@@ -43,7 +43,6 @@ void* lgwt_bulk_new(uint32_t max_streams, uint32_t carry_cap, uint32_t detail_ca
     e->cache.assign(sizeof(TemplateCache2), 0);
     e->raw.assign((size_t)e->n_blocks * (R2_WARPS + R2_SLOTS), UsageRaw{});
     e->cand.assign(max_streams, UsageRec{});
-    e->pend.assign(max_streams + 1, 0);
     e->rowq.assign(rowq_cap + 1, RowEvent{}); e->rowq_count = 0;
     e->mode = 0;
     return e;
@@ -66,7 +65,8 @@ static StepArgs make_args(HostEngine* e, const uint8_t* data, uint32_t n_bytes, 
     a.seg_chunk = seg_chunk; a.seg_slot = seg_slot; a.n_segs = n_segs; a.out = out; a.seg_out = (SegResult*)seg_out;
     a.rowq = e->rowq.data(); a.rowq_count = &e->rowq_count; a.rowq_cap = e->rowq_cap;
     a.s.plan = e->plan.data(); a.s.tpl_cache2 = (TemplateCache2*)e->cache.data(); a.s.raw_scratch = e->raw.data(); a.s.usage_cand = e->cand.data();
-    a.s.pend_list = e->pend.data(); a.s.pend_count = e->pend.data() + e->max_streams; a.s.raw_blocks = e->n_blocks; a.s.counters = e->counters;
+    a.s.raw_blocks = e->n_blocks; a.s.counters = e->counters;
+    e->tile_seg.assign(n_bytes / R2_TILE + 4, 0); a.s.tile_seg = e->tile_seg.data();
     return a;
 }
 
@@ -99,8 +99,7 @@ int lgwt_bulk_step(void* h, const uint8_t* data, uint32_t n_bytes, const uint32_
             const uint32_t blocks = (warps + R2_WARPS - 1) / R2_WARPS;
             simt::launch(blocks, R2_THREADS, [&] { k_relay2(a, n_tiles, tpw, 0u); });
         }
-        if (n_segs) simt::launch((n_segs + 7) / 8, 256, [&] { k_commit2(a); });
-        if (n_segs) simt::launch(1, R2_XWARPS * 32, [&] { k_usage_extract(a); });
+        if (n_segs) simt::launch((n_segs + R2_CWARPS - 1) / R2_CWARPS, R2_CWARPS * 32, [&] { k_commit2(a); });
     }
     uint32_t cnt = e->rowq_count < e->rowq_cap ? e->rowq_count : e->rowq_cap;
     if (cnt > rows_cap) cnt = rows_cap;

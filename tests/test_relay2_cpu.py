@@ -1,4 +1,4 @@
-"""The bulk kernels of csrc/relay2.cuh (k_prime2 -> k_relay2 -> k_commit2 -> k_usage_extract) on the CPU box: the kernel
+"""The bulk kernels of csrc/relay2.cuh (k_prime2 -> k_relay2 -> k_commit2) on the CPU box: the kernel
 source is compiled with g++ over a SIMT emulator (tests/support/simt_emu.h, host_relay2.cpp) and driven through the
 same test bodies as the GPU parity tests (tests/test_sse_gpu.py): goldens of the unmodified reference, the oracle, and
 the exact sequential machine.  Test aid only -- the product has no CPU path."""
