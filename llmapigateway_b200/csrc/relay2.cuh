@@ -98,6 +98,8 @@ struct R2Shared {
     alignas(16) uint8_t fast_text[16 * R2_TEXT];     // default slot: copy c holds image[c ..], so image[t .. t+16) is an aligned vector of copy t & 15
     alignas(16) uint8_t fast_lit[16 * R2_TEXT];
     alignas(16) Tpl2 tpl[R2_SLOTS];
+    alignas(8) UsageRaw raw_tpl[R2_SLOTS];           // the template events' own UsageRaw (usage_ok slots)
+    alignas(8) UsageRaw raw_warp[R2_WARPS];          // per warp: the record being assembled from a matched usage event
     alignas(8) unsigned long long mbar[R2_WARPS * R2_NBUF];
     uint32_t slot_state[R2_SLOTS];                   // 0 empty, 1 being built, 2 ready
     uint32_t hits[R2_SLOTS];
@@ -203,8 +205,8 @@ struct R2Ctx {
     uint32_t last_ra;            // position of the last number re-anchor (a mismatch right there is final)
     uint32_t hits_d;             // events matched by the default slot
     uint32_t status;             // general_step: 1 = the stream goes to the sequential path
-    UsageRaw* block_raw;         // [R2_SLOTS] the block's template events' own UsageRaw (global scratch)
-    UsageRaw* warp_raw;          // this warp's assembly buffer (global scratch)
+    UsageRaw* block_raw;         // [R2_SLOTS] the block's template events' own UsageRaw (shared memory)
+    UsageRaw* warp_raw;          // this warp's assembly buffer (shared memory)
 };
 
 // Where bytes are read from: the resident tile in shared memory, global memory outside it.  A small value type: the
@@ -840,25 +842,37 @@ R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* m
         }
     }
     __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        ap->s.plan[seg].cand_ps = ps + 1u;
-    }
+    if (lane == 0) ap->s.plan[seg].cand_ps = ps + 1u;            // (k_commit2 runs after this kernel: no fence needed)
     __syncwarp();
 }
 
 // One step of the walk that the fast loop cannot take: an event against a non-default slot, a compare pass with boundary
 // lanes / limits / a mismatch to classify, or the byte-wise recogniser.  Out of line, the context goes in and comes back by
 // value: the fast loop in walk_segment then keeps its few live values in registers.
-R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32_t range_hi) {
+R2_DEV bool fast_ready(const R2Ctx& c, uint32_t sub_end, uint32_t range_hi) {
+    if (!(c.slot == c.dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi)) return false;
+    if (c.sh->tpl[c.dflt].m.flags & TK_USAGE) return false;
+    const uint32_t lim = r2_min(c.pos + 512u, c.tile_hi);
+    return lim <= r2_min(sub_end, range_hi) && (lim & 15u) == 0u;
+}
+R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t range_hi) {
     R2Shared* sh = c.sh;
     const StepArgs& a = *c.a;
     const uint32_t lane = c.lane;
     TemplateCache2* tc = a.s.tpl_cache2;
-    {
+    bool first = true;
+    for (;;) {
+        // back to the walk when it has something to do: the text or the range ends here, the pipeline must move on, or the
+        // fast loop can take over again (not before one step was made: the fast loop has just given up at this very position)
+        const uint32_t sub_end = c.in_kept ? c.kept_end : c.te;
+        if (c.pos >= sub_end) return c;
+        if (c.s_open >= range_hi && c.pos == c.s_open && !c.in_kept) return c;
+        if (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) return c;
+        if (!first && fast_ready(c, sub_end, range_hi)) return c;
+        first = false;
         if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
             c.tried |= 1u << c.slot; c.slot = next_slot(c);
-            return c;
+            continue;
         }
         if (c.slot < R2_SLOTS && (c.slot != c.dflt || (sh->tpl[c.slot].m.flags & TK_USAGE))) {
             // ---- one event against a slot that is not the periodic default: span by span ----
@@ -877,7 +891,7 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32
                 c.tried |= 1u << c.slot;
                 c.slot = next_slot(c);
             }
-            return c;
+            continue;
         }
         if (c.slot < R2_SLOTS) {
             const TplMeta& m = sh->tpl[c.slot].m;
@@ -933,7 +947,7 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32
                 c.s_open = last_start; c.tried = 0;
             }
             c.pos = mpos; c.t = t2;
-            if (!any) return c;                                                                  // the pass ran to its limit
+            if (!any) continue;                                                                  // the pass ran to its limit
             // ---- a mismatch at mpos, template offset t2: inside a value span? ----
             const uint32_t id = (t2 < m.len && mpos != c.last_ra) ? sh->tpl[c.slot].span_id[t2] : 0xffu;
             bool ok = false;
@@ -978,17 +992,17 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32
                     if (good && x2 >= mpos) { c.pos = x2; c.t = send; c.last_ra = x2; ok = true; }
                 }
             }
-            if (ok) return c;
+            if (ok) continue;
             // the event does not follow this slot: rewind to its start and try the next one
             c.tried |= 1u << c.slot;
             c.pos = c.s_open; c.t = 0; c.last_ra = R2_NONE;
             c.slot = next_slot(c);
-            return c;
+            continue;
         }
         // ---- no template fits: the byte-wise recogniser walks the event ----
         {
             refresh_slots(c);
-            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; return c; }   // another warp has just published one
+            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; continue; }   // another warp has just published one
             const uint32_t ps = c.s_open;
             const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
             if (ps > c.tb && ring_byte(c, ps) == '\n') { c.status = 1u; return c; }   // LF run >= 3
@@ -998,7 +1012,7 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32
             if (e == R2_NONE) {
                 if (ev_end < sub_end) { c.status = 1u; return c; }   // longer than the carry capacity
                 c.pos = sub_end;                                                                // open at the end of the text: the carry
-                return c;
+                continue;
             }
             if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { c.status = 1u; return c; }
             if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
@@ -1012,7 +1026,6 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t sub_end, const uint32
             c.last_ra = R2_NONE;
         }
     }
-    return c;
 }
 
 // Walk the current segment from c.pos.  Returns true when the warp is done (the open event starts in the next warp's
@@ -1082,7 +1095,7 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             }
         }
 
-        c = general_step(c, sub_end, range_hi);
+        c = general_step(c, range_hi);
         if (c.status) { c.status = 0; mark_irregular(c); return false; }
     }
 }
@@ -1096,7 +1109,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     R2Shared* sh = reinterpret_cast<R2Shared*>(smem + R2_RING_BYTES);
     const uint32_t tid = R2_TID, warp = tid >> 5, lane = tid & 31u;
     TemplateCache2* tc = a.s.tpl_cache2;
-    UsageRaw* block_raw = a.s.raw_scratch + (size_t)R2_BID * (R2_WARPS + R2_SLOTS) + R2_WARPS;
+    UsageRaw* block_raw = sh->raw_tpl;
 
     // ---- block prologue: recogniser tables, templates from the engine-wide cache, default slot, barriers ----
     for (uint32_t k = tid; k < 64 + LGW_LEAN_ROWS * 8; k += R2_THREADS) {
@@ -1141,7 +1154,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
     c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0; c.status = 0;
     refresh_slots(c);
-    c.block_raw = block_raw; c.warp_raw = a.s.raw_scratch + (size_t)R2_BID * (R2_WARPS + R2_SLOTS) + warp;
+    c.block_raw = block_raw; c.warp_raw = &sh->raw_warp[warp];
     c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
     c.slot = c.dflt; c.t = 0; c.tried = 0; c.pos = c.s_open = 0;
     c.in_kept = c.primed = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;

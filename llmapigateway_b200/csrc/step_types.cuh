@@ -36,9 +36,7 @@ struct TemplateCache2;     // relay2.cuh
 struct StepScratch {
     SegPlan* plan;             // [max_streams]
     TemplateCache2* tpl_cache2;  // event templates, persistent across steps
-    UsageRaw* raw_scratch;     // [raw_blocks][R2_WARPS + R2_SLOTS] per-warp assembly buffers and per-block template records
     UsageRec* usage_cand;      // [max_streams] usage record read from a template-following usage event of this step
-    uint32_t raw_blocks;
     uint32_t* tile_seg;        // [max tiles + 1] segment that holds the first byte of each 4 KiB tile of the launch
     uint32_t* counters;        // diagnostics since engine creation: [0] segments redone sequentially, [1] segments folded from the bulk
                                //   kernel's findings, [2] usage records read from template spans, [3] usage events stashed
