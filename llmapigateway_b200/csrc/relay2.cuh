@@ -58,7 +58,7 @@
 
 #define R2_WARPS 16u
 #define R2_THREADS (R2_WARPS * 32u)
-#define R2_TILE 4096u
+#define R2_TILE 3072u
 #define R2_NBUF 3u
 #define R2_SLOTS 4u
 #define R2_TPL_MAX 504u                 /* longest event kept as a template (text without its LF LF) */
@@ -106,6 +106,8 @@ struct R2Shared {
     uint32_t general;
     uint32_t dflt, fast_ready;
     uint32_t learn_lock;                             // one warp of the block learns a template at a time
+    StepArgs args;                                   // the kernel's arguments (read through a pointer by the out-of-line paths: taking the
+                                                     //   address of the parameter itself would move it to local memory)
     alignas(4) uint8_t cls[256];
     alignas(4) uint8_t trans[LGW_LEAN_ROWS * 32];
 };
@@ -199,14 +201,11 @@ struct R2Ctx {
     uint32_t high;               // some byte >= 0x80 was seen in the current segment's text
     uint32_t walk_lo;            // first text position this warp walked in the current segment
     // matcher
-    uint32_t slot, t, pos, s_open, tried;
+    uint32_t t, pos, s_open;
     uint32_t dflt, fast;         // default (periodic) slot of the block; its pre-shifted copies are ready
     uint32_t ready, free_slots;  // bit per slot: template usable / slot empty (refreshed by refresh_slots, the same in every lane)
     uint32_t last_ra;            // position of the last number re-anchor (a mismatch right there is final)
     uint32_t hits_d;             // events matched by the default slot
-    uint32_t status;             // general_step: 1 = the stream goes to the sequential path
-    UsageRaw* block_raw;         // [R2_SLOTS] the block's template events' own UsageRaw (shared memory)
-    UsageRaw* warp_raw;          // this warp's assembly buffer (shared memory)
 };
 
 // Where bytes are read from: the resident tile in shared memory, global memory outside it.  A small value type: the
@@ -296,21 +295,6 @@ R2_DEV void pipe_advance(R2Ctx& c) {
 }
 
 // ---- templates ---------------------------------------------------------------------------------------------------------
-// image[t .. t+16) of slot `slot` and its literal mask
-R2_DEV void tpl_vec(const R2Ctx& c, uint32_t slot, uint32_t t, uint4& tx, uint4& mk) {
-    if (slot == c.dflt && c.fast) {
-        const uint32_t ad = (t & 15u) * R2_TEXT + (t & ~15u);
-        tx = sld128(sptr(c.sh->fast_text) + ad); mk = sld128(sptr(c.sh->fast_lit) + ad);
-        return;
-    }
-    const SPtr tp = sptr(c.sh->tpl[slot].text) + (t & ~3u), lp = sptr(c.sh->tpl[slot].lit) + (t & ~3u);
-    const uint32_t sh = 8 * (t & 3u);
-    const uint32_t a0 = sld32(tp), a1 = sld32(tp + 4), a2 = sld32(tp + 8), a3 = sld32(tp + 12), a4 = sld32(tp + 16);
-    const uint32_t b0 = sld32(lp), b1 = sld32(lp + 4), b2 = sld32(lp + 8), b3 = sld32(lp + 12), b4 = sld32(lp + 16);
-    tx = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh));
-    mk = make_uint4(__funnelshift_r(b0, b1, sh), __funnelshift_r(b1, b2, sh), __funnelshift_r(b2, b3, sh), __funnelshift_r(b3, b4, sh));
-}
-
 // the 16 pre-shifted copies of slot `slot` (whole warp)
 R2_DEV void build_fast_tables(R2Shared* sh, uint32_t slot, uint32_t lane, uint32_t step) {
     const Tpl2& tp = sh->tpl[slot];
@@ -470,32 +454,6 @@ R2_DEV void flush_counts(R2Ctx& c) {
 }
 R2_DEV void mark_irregular(R2Ctx& c) { if (c.lane == 0 && c.seg != R2_NONE) c.a->s.plan[c.seg].irregular = 1; }
 
-// one complete event [ps, e) of class cls with recogniser flags f (e = position of its LF LF).  Returns false when the
-// stream has to go to the sequential path.
-R2_DEV bool account_event(R2Ctx& c, uint32_t cls, uint32_t f, uint32_t n, uint32_t ps, uint32_t e) {
-    if (cls == PC_NONE) return true;
-    if (cls == PC_DATA) {
-        if (c.in_kept) {                                      // priming loop on the kept chunk, request_handler.py:82-91
-            if (!c.primed) { if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) return false; c.primed = 1; }
-        } else {                                              // handler loop, request_handler.py:122-134
-            c.ev_a += n;
-            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) c.a_usage = 1;
-        }
-    }
-    if (f & PF_VALID_B) {                                     // tap loop, chat_logging.py:123-141
-        c.ev_b += n;
-        if (f & TK_ERROR) return false;                       // extra DB row: sequential path
-        if (f & TK_USAGE) {
-            if (c.lane == 0) {
-                SegPlan* pl = c.a->s.plan + c.seg;
-                atomicAdd(&pl->n_usage_b, n);
-                atomicMax(&pl->last_usage, ((unsigned long long)(ps + 1) << 32) | (e - ps));
-            }
-        }
-    }
-    return true;
-}
-
 // chunk-level UTF-8 (request_handler.py:111 decodes every chunk on its own): the chunks of segment `seg` that overlap [lo, hi)
 R2_DEV_NOINLINE bool chunks_utf8_ok(const StepArgs* ap, uint32_t lane, uint32_t seg, uint32_t lo, uint32_t hi) {
     const StepArgs& a = *ap;
@@ -535,29 +493,6 @@ R2_DEV uint32_t find_lflf(R2Ctx& c, uint32_t from, uint32_t end, uint32_t& high)
             return wb + 16 * fl + ((uint32_t)__ffs(pr) - 1u);
         }
         wb += 31 * 16;                                                                   // the last lane is looked at again (pairs across windows)
-    }
-}
-
-// first byte at or after `from` (before `end`) that is not plain string content: its position, R2_NONE when there is none
-R2_DEV uint32_t find_special(R2Ctx& c, uint32_t from, uint32_t end, uint32_t& high) {
-    uint32_t wb = from & ~15u;
-    for (;;) {
-        if (wb >= end) return R2_NONE;
-        const uint32_t lp = wb + 16 * c.lane;
-        const uint4 d = lp < end ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
-        high |= d.x | d.y | d.z | d.w;
-        uint32_t sp = movemask4(~span_ok(d.x, 0) & 0x80808080u) | (movemask4(~span_ok(d.y, 0) & 0x80808080u) << 4) |
-                      (movemask4(~span_ok(d.z, 0) & 0x80808080u) << 8) | (movemask4(~span_ok(d.w, 0) & 0x80808080u) << 12);
-        if (lp >= end) sp = 0;
-        if (lp < from) sp &= from - lp >= 16 ? 0u : (0xFFFFu << (from - lp));
-        if (lp + 16 > end) sp &= 0xFFFFu >> (lp + 16 - end);
-        const uint32_t any = __ballot_sync(R2_FULL, sp != 0);
-        if (any) {
-            const uint32_t fl = (uint32_t)__ffs(any) - 1u;
-            const uint32_t s = __shfl_sync(R2_FULL, sp, (int)fl);
-            return wb + 16 * fl + ((uint32_t)__ffs(s) - 1u);
-        }
-        wb += 512;
     }
 }
 
@@ -661,11 +596,6 @@ R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, U
     __syncwarp();
 }
 
-R2_DEV uint32_t next_slot(const R2Ctx& c) {
-    const uint32_t m = c.ready & ~c.tried & ((1u << R2_SLOTS) - 1u);
-    return m ? (uint32_t)__ffs(m) - 1u : R2_SLOTS;
-}
-
 // Enter segment `seg`; `from` = the warp's range start when the segment's bytes begin before it, else the segment's first
 // byte.  Sets the text range and the first event start this warp owns in it; false: the warp owns nothing here.
 R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_hi) {
@@ -676,7 +606,7 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     const uint32_t kept = pl->kept_chunk != 0xFFFFFFFFu ? pl->kept_end : 0u;
     c.kept_end = kept;
     c.pos = te; c.walk_lo = te;
-    c.slot = c.dflt; c.t = 0; c.tried = 0;
+    c.t = 0;
     if (pl->irregular || tb >= te) return false;
     if (from <= tb) {
         if (tb >= range_hi) return false;
@@ -846,186 +776,190 @@ R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* m
     __syncwarp();
 }
 
-// One step of the walk that the fast loop cannot take: an event against a non-default slot, a compare pass with boundary
-// lanes / limits / a mismatch to classify, or the byte-wise recogniser.  Out of line, the context goes in and comes back by
-// value: the fast loop in walk_segment then keeps its few live values in registers.
-R2_DEV bool fast_ready(const R2Ctx& c, uint32_t sub_end, uint32_t range_hi) {
-    if (!(c.slot == c.dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi)) return false;
-    if (c.sh->tpl[c.dflt].m.flags & TK_USAGE) return false;
-    const uint32_t lim = r2_min(c.pos + 512u, c.tile_hi);
-    return lim <= r2_min(sub_end, range_hi) && (lim & 15u) == 0u;
-}
-R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t range_hi) {
-    R2Shared* sh = c.sh;
-    const StepArgs& a = *c.a;
-    const uint32_t lane = c.lane;
-    TemplateCache2* tc = a.s.tpl_cache2;
-    bool first = true;
-    for (;;) {
-        // back to the walk when it has something to do: the text or the range ends here, the pipeline must move on, or the
-        // fast loop can take over again (not before one step was made: the fast loop has just given up at this very position)
-        const uint32_t sub_end = c.in_kept ? c.kept_end : c.te;
-        if (c.pos >= sub_end) return c;
-        if (c.s_open >= range_hi && c.pos == c.s_open && !c.in_kept) return c;
-        if (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) return c;
-        if (!first && fast_ready(c, sub_end, range_hi)) return c;
-        first = false;
-        if (c.slot < R2_SLOTS && !(c.ready & (1u << c.slot))) {                              // empty (or being built): next
-            c.tried |= 1u << c.slot; c.slot = next_slot(c);
-            continue;
-        }
-        if (c.slot < R2_SLOTS && (c.slot != c.dflt || (sh->tpl[c.slot].m.flags & TK_USAGE))) {
-            // ---- one event against a slot that is not the periodic default: span by span ----
-            const TplMeta& m = sh->tpl[c.slot].m;
-            const uint32_t ps = c.s_open;
-            const SingleOut so = match_single(io_of(c), &sh->tpl[c.slot], lane, ps, r2_min(sub_end, ps + a.t.carry_cap + 2u));
-            if (so.ok) {
-                c.high |= so.high;
-                if (c.slot == c.dflt) c.hits_d += 1u; else if (lane == 0) atomicAdd(&tc->hits[c.slot], 1u);
-                if (!account_event(c, m.cls, m.flags, 1, ps, so.e)) { c.status = 1u; return c; }
-                if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP)
-                    extract_usage(c.a, io_of(c), &m, c.block_raw + c.slot, c.warp_raw, lane, c.seg, ps, so.f_start, so.f_len, so.f_esc);
-                c.pos = c.s_open = so.e + 2u; c.t = 0; c.tried = 0; c.last_ra = R2_NONE;
-                c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
-            } else {                                                       // the event does not follow this slot: the next one
-                c.tried |= 1u << c.slot;
-                c.slot = next_slot(c);
-            }
-            continue;
-        }
-        if (c.slot < R2_SLOTS) {
-            const TplMeta& m = sh->tpl[c.slot].m;
-            const uint32_t P = m.P;
-            // ---- compare pass: up to 512 bytes from pos against the periodic image ----
-            const uint32_t wbase = c.pos & ~15u;
-            uint32_t lim = r2_min(sub_end, wbase + 512u);
-            if (c.pos >= c.tile_lo && c.pos < c.tile_hi) lim = r2_min(lim, c.tile_hi);          // windows do not straddle the resident tile's end
-            if (wbase + 512u > range_hi && !c.in_kept) {                                    // stop at the first event boundary in the next range
-                const uint32_t nb = c.pos + (P - c.t);
-                uint32_t b = nb;
-                if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
-                lim = r2_min(lim, b);
-            }
-            const uint32_t lp = wbase + 16u * lane;
-            const uint32_t u = c.t + P + 16u * lane - (c.pos & 15u);
-            const uint32_t tl = u - __umulhi(u, m.recip) * P;
-            uint4 tx, mk;
-            tpl_vec(c, c.slot, tl, tx, mk);
-            const bool active = lp < lim;
-            const uint4 d = active ? ld16(c, lp) : make_uint4(0, 0, 0, 0);
-            c.high |= d.x | d.y | d.z | d.w;
-            const uint32_t r0 = (d.x ^ tx.x) & mk.x, r1 = (d.y ^ tx.y) & mk.y, r2 = (d.z ^ tx.z) & mk.z, r3 = (d.w ^ tx.w) & mk.w;
-            const uint32_t s0 = ~span_ok(d.x, mk.x) & 0x80808080u, s1 = ~span_ok(d.y, mk.y) & 0x80808080u;
-            const uint32_t s2 = ~span_ok(d.z, mk.z) & 0x80808080u, s3 = ~span_ok(d.w, mk.w) & 0x80808080u;
-            uint32_t bad = (r0 | r1 | r2 | r3 | s0 | s1 | s2 | s3) != 0 ? 1u : 0u;
-            uint32_t bm = 0xFFFFu;                                                              // bytes of this lane that count
-            if (lp < c.pos || lp + 16u > lim) {
-                if (lp < c.pos) bm &= c.pos - lp >= 16u ? 0u : (0xFFFFu << (c.pos - lp));
-                if (lp + 16u > lim) bm &= lp >= lim ? 0u : (0xFFFFu >> (lp + 16u - lim));
-                if (bad) {
-                    const uint32_t bb = movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12);
-                    bad = (bb & bm) != 0 ? 1u : 0u;
-                }
-            }
-            const uint32_t any = __ballot_sync(R2_FULL, active && bad);
-            uint32_t mpos = lim;
-            if (any) {
-                const uint32_t fl = (uint32_t)__ffs(any) - 1u;
-                uint32_t bb = 0;
-                if (lane == fl) bb = (movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12)) & bm;
-                bb = __shfl_sync(R2_FULL, bb, (int)fl);
-                mpos = wbase + 16u * fl + ((uint32_t)__ffs(bb) - 1u);
-            }
-            // ---- events completed by the pass ----
-            const uint32_t u2 = c.t + (mpos - c.pos);
-            const uint32_t nwr = __umulhi(u2, m.recip);                                           // separators passed
-            const uint32_t t2 = u2 - nwr * P;
-            if (nwr) {
-                const uint32_t last_start = mpos - t2;                                           // start of the event that is open now
-                c.hits_d += nwr;
-                if (!account_event(c, m.cls, m.flags, nwr, c.s_open, last_start - 2u)) { c.status = 1u; return c; }
-                c.s_open = last_start; c.tried = 0;
-            }
-            c.pos = mpos; c.t = t2;
-            if (!any) continue;                                                                  // the pass ran to its limit
-            // ---- a mismatch at mpos, template offset t2: inside a value span? ----
-            const uint32_t id = (t2 < m.len && mpos != c.last_ra) ? sh->tpl[c.slot].span_id[t2] : 0xffu;
-            bool ok = false;
-            if (id != 0xffu) {
-                const uint32_t sstart = m.sstart[id], send = m.send[id];
-                const uint32_t ev_end = r2_min(sub_end, c.s_open + a.t.carry_cap + 2u);
-                if (m.skind[id] == 0) {                                                          // string value: plain bytes and valid escapes up to the closing quote
-                    uint32_t q = mpos;
-                    for (;;) {
-                        const uint32_t x = find_special(c, q, ev_end, c.high);
-                        if (x == R2_NONE || x - mpos > R2_MAX_STR) break;
-                        R2Bytes rd{io_of(c)};
-                        const uint32_t ch = rd.at(x);
-                        if (ch == '"') { q = x; ok = true; break; }
-                        if (ch != '\\') break;                                                   // a control byte
-                        const uint32_t e1 = rd.at(x + 1);
-                        uint32_t el = 0;
-                        if (e1 == 'u') { el = 6; for (uint32_t j = 2; j < 6; ++j) { const uint32_t h = rd.at(x + j); if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
-                        else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
-                        if (el == 0 || x + el > ev_end) break;
-                        q = x + el;
-                    }
-                    if (ok) { c.pos = q; c.t = send; }                                          // (the closing quote itself is compared by the next pass)
-                } else {                                                                          // number value: the event's own number must be valid
-                    const uint32_t bs = mpos - (t2 - sstart);
-                    uint32_t x2 = 0, good = 0;
-                    if (lane == 0) {
-                        R2Bytes rd{io_of(c)};
-                        uint32_t st = L_VALUE, p = bs;
-                        for (;;) {
-                            if (p >= ev_end) break;
-                            const uint32_t cl = rd.cls(rd.at(p));
-                            if (cl < C_MINUS || cl > C_EXP) break;
-                            st = rd.trans(st * 32 + cl) & 31u;
-                            if (st == L_ERR) break;
-                            ++p;
-                        }
-                        good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
-                        x2 = p;
-                    }
-                    x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
-                    if (good && x2 >= mpos) { c.pos = x2; c.t = send; c.last_ra = x2; ok = true; }
-                }
-            }
-            if (ok) continue;
-            // the event does not follow this slot: rewind to its start and try the next one
-            c.tried |= 1u << c.slot;
-            c.pos = c.s_open; c.t = 0; c.last_ra = R2_NONE;
-            c.slot = next_slot(c);
-            continue;
-        }
-        // ---- no template fits: the byte-wise recogniser walks the event ----
-        {
-            refresh_slots(c);
-            if (next_slot(c) < R2_SLOTS) { c.slot = next_slot(c); c.pos = c.s_open; c.t = 0; continue; }   // another warp has just published one
-            const uint32_t ps = c.s_open;
-            const uint32_t ev_end = r2_min(sub_end, ps + a.t.carry_cap + 2u);
-            if (ps > c.tb && ring_byte(c, ps) == '\n') { c.status = 1u; return c; }   // LF run >= 3
-            const LeanOut lo = lean_event(io_of(c), lane, ps, ev_end);
-            const uint32_t cls = lo.cls, f = lo.f, e = lo.e;
-            c.high |= lo.high;
-            if (e == R2_NONE) {
-                if (ev_end < sub_end) { c.status = 1u; return c; }   // longer than the carry capacity
-                c.pos = sub_end;                                                                // open at the end of the text: the carry
-                continue;
-            }
-            if (e + 2 < sub_end && ring_byte(c, e + 2) == '\n') { c.status = 1u; return c; }
-            if (cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
-            if (!account_event(c, cls, f, 1, ps, e)) { c.status = 1u; return c; }
-            if (cls != PC_NONE && (f & PF_VALID_A) && !(f & (TK_ERROR | TK_DETAIL | TK_CODE)) && e - ps >= R2_TPL_MIN && e - ps <= R2_TPL_MAX && c.free_slots) {
-                learn_template(c.a, sh, io_of(c), c.block_raw, lane, c.ready, ps, sub_end);
-                refresh_slots(c);
-            }
-            c.pos = c.s_open = e + 2; c.t = 0; c.tried = 0;
-            c.slot = (c.ready & (1u << c.dflt)) ? c.dflt : next_slot(c);
-            c.last_ra = R2_NONE;
+// ---- the two out-of-line steps of the walk ---------------------------------------------------------------------------------------
+// Both take a handful of scalars and return a handful: the walk's own values stay in registers across the calls (passing the
+// whole context by value cost ~90 local-memory words per call, and with 180 KB of shared memory there is next to no L1 left
+// to hide that behind).
+
+// what one completed event (or n events of a template) adds to the segment's counters
+struct Acct { uint32_t ok, ev_a, ev_b, a_usage, primed; };
+R2_DEV Acct account(const StepArgs* ap, uint32_t lane, uint32_t seg, uint32_t in_kept, uint32_t primed, uint32_t cls, uint32_t f, uint32_t n, uint32_t ps, uint32_t e) {
+    Acct r; r.ok = 1; r.ev_a = 0; r.ev_b = 0; r.a_usage = 0; r.primed = primed;
+    if (cls == PC_NONE) return r;
+    if (cls == PC_DATA) {
+        if (in_kept) {                                        // priming loop on the kept chunk, request_handler.py:82-91
+            if (!primed) { if (!(f & PF_VALID_A) || (f & (TK_ERROR | TK_DETAIL))) { r.ok = 0; return r; } r.primed = 1; }
+        } else {                                              // handler loop, request_handler.py:122-134
+            r.ev_a = n;
+            if ((f & PF_VALID_A) && !(f & TK_CODE) && (f & TK_USAGE)) r.a_usage = 1;
         }
     }
+    if (f & PF_VALID_B) {                                     // tap loop, chat_logging.py:123-141
+        r.ev_b = n;
+        if (f & TK_ERROR) { r.ok = 0; return r; }             // extra DB row: sequential path
+        if ((f & TK_USAGE) && lane == 0) {
+            SegPlan* pl = ap->s.plan + seg;
+            atomicAdd(&pl->n_usage_b, n);
+            atomicMax(&pl->last_usage, ((unsigned long long)(ps + 1) << 32) | (e - ps));
+        }
+    }
+    return r;
+}
+
+// One compare pass of up to 512 bytes from pos against the default slot's periodic image, boundary lanes and limits
+// included, and -- on a mismatch inside a value span -- the re-anchoring behind the value's own end.
+//   kind 0: fine (ran to its limit, or re-anchored): go on from (pos, t)
+//   kind 1: the event that starts at s_open does not follow the default slot
+struct PassOut { uint32_t pos, t, s_open, nwr, kind, last_ra, high; };
+R2_DEV_NOINLINE PassOut pass_step(R2Io io, uint32_t lane, uint32_t slot, uint32_t fast, uint32_t pos0, uint32_t t0, uint32_t s_open0, uint32_t last_ra,
+                                  uint32_t sub_end, uint32_t range_hi, uint32_t in_kept, uint32_t carry_cap) {
+    const R2Shared* sh = io.sh;
+    const TplMeta& m = sh->tpl[slot].m;
+    const uint32_t P = m.P;
+    PassOut o; o.pos = pos0; o.t = t0; o.s_open = s_open0; o.nwr = 0; o.kind = 0; o.last_ra = last_ra; o.high = 0;
+    const uint32_t wbase = pos0 & ~15u;
+    uint32_t lim = r2_min(sub_end, wbase + 512u);
+    if (pos0 >= io.tile_lo && pos0 < io.tile_hi) lim = r2_min(lim, io.tile_hi);             // windows do not straddle the resident tile's end
+    if (wbase + 512u > range_hi && !in_kept) {                                               // stop at the first event boundary in the next range
+        const uint32_t nb = pos0 + (P - t0);
+        uint32_t b = nb;
+        if (b < range_hi) b = nb + __umulhi(range_hi - nb + P - 1u, m.recip) * P;
+        lim = r2_min(lim, b);
+    }
+    const uint32_t lp = wbase + 16u * lane;
+    const uint32_t u = t0 + P + 16u * lane - (pos0 & 15u);
+    const uint32_t tl = u - __umulhi(u, m.recip) * P;
+    uint4 tx, mk;
+    if (fast) {
+        const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
+        tx = sld128(sptr(sh->fast_text) + ad); mk = sld128(sptr(sh->fast_lit) + ad);
+    } else {
+        const SPtr tp = sptr(sh->tpl[slot].text) + (tl & ~3u), lpm = sptr(sh->tpl[slot].lit) + (tl & ~3u);
+        const uint32_t shf = 8 * (tl & 3u);
+        const uint32_t a0 = sld32(tp), a1 = sld32(tp + 4), a2 = sld32(tp + 8), a3 = sld32(tp + 12), a4 = sld32(tp + 16);
+        const uint32_t b0 = sld32(lpm), b1 = sld32(lpm + 4), b2 = sld32(lpm + 8), b3 = sld32(lpm + 12), b4 = sld32(lpm + 16);
+        tx = make_uint4(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(a2, a3, shf), __funnelshift_r(a3, a4, shf));
+        mk = make_uint4(__funnelshift_r(b0, b1, shf), __funnelshift_r(b1, b2, shf), __funnelshift_r(b2, b3, shf), __funnelshift_r(b3, b4, shf));
+    }
+    const bool active = lp < lim;
+    uint4 d = make_uint4(0, 0, 0, 0);
+    if (active) {
+        if (lp >= io.tile_lo && lp + 16 <= io.tile_hi) d = sld128(io.buf + (lp - io.tile_lo));
+        else if (lp + 16 <= io.n_bytes) d = gld128(io.data + lp);
+        else { uint32_t w[4] = {0, 0, 0, 0}; for (uint32_t i = 0; i < 16; ++i) w[i >> 2] |= (uint32_t)io_byte(io, lp + i) << (8 * (i & 3)); d = make_uint4(w[0], w[1], w[2], w[3]); }
+    }
+    o.high = d.x | d.y | d.z | d.w;
+    const uint32_t r0 = (d.x ^ tx.x) & mk.x, r1 = (d.y ^ tx.y) & mk.y, r2 = (d.z ^ tx.z) & mk.z, r3 = (d.w ^ tx.w) & mk.w;
+    const uint32_t s0 = ~span_ok(d.x, mk.x) & 0x80808080u, s1 = ~span_ok(d.y, mk.y) & 0x80808080u;
+    const uint32_t s2 = ~span_ok(d.z, mk.z) & 0x80808080u, s3 = ~span_ok(d.w, mk.w) & 0x80808080u;
+    uint32_t bm = 0xFFFFu;                                                                  // bytes of this lane that count
+    if (lp < pos0) bm &= pos0 - lp >= 16u ? 0u : (0xFFFFu << (pos0 - lp));
+    if (lp + 16u > lim) bm &= lp >= lim ? 0u : (0xFFFFu >> (lp + 16u - lim));
+    const uint32_t bb = (movemask4(nonzero_bytes(r0) | s0) | (movemask4(nonzero_bytes(r1) | s1) << 4) | (movemask4(nonzero_bytes(r2) | s2) << 8) | (movemask4(nonzero_bytes(r3) | s3) << 12)) & bm;
+    const uint32_t any = __ballot_sync(R2_FULL, active && bb != 0);
+    uint32_t mpos = lim;
+    if (any) {
+        const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+        const uint32_t b1 = __shfl_sync(R2_FULL, bb, (int)fl);
+        mpos = wbase + 16u * fl + ((uint32_t)__ffs(b1) - 1u);
+    }
+    // ---- events completed by the pass ----
+    const uint32_t u2 = t0 + (mpos - pos0);
+    const uint32_t nwr = __umulhi(u2, m.recip);                                               // separators passed
+    const uint32_t t2 = u2 - nwr * P;
+    o.nwr = nwr; o.pos = mpos; o.t = t2;
+    if (nwr) o.s_open = mpos - t2;                                                          // start of the event that is open now
+    if (!any) return o;                                                                     // the pass ran to its limit
+    // ---- a mismatch at mpos, template offset t2: inside a value span? ----
+    const uint32_t id = (t2 < m.len && mpos != last_ra) ? sh->tpl[slot].span_id[t2] : 0xffu;
+    if (id != 0xffu) {
+        const uint32_t sstart = m.sstart[id], send = m.send[id];
+        const uint32_t ev_end = r2_min(sub_end, o.s_open + carry_cap + 2u);
+        if (m.skind[id] == 0) {                                                              // string value: plain bytes and valid escapes up to the closing quote
+            uint32_t q = mpos;
+            for (;;) {
+                // first byte at or after q that is not plain string content, a lane per byte
+                const uint32_t c = q + lane < ev_end ? (uint32_t)io_byte(io, q + lane) : 0u;   // (past the end: reads as a control byte, the scan stops)
+                o.high |= c;
+                const uint32_t sp = __ballot_sync(R2_FULL, c < 0x20u || c == '"' || c == '\\');
+                if (!sp) { q += 32; if (q - mpos > R2_MAX_STR) break; continue; }
+                const uint32_t k = (uint32_t)__ffs(sp) - 1u, x = q + k;
+                const uint32_t ch = __shfl_sync(R2_FULL, c, (int)k);
+                if (ch == '"') { o.pos = x; o.t = send; return o; }                           // (the closing quote itself is compared by the next pass)
+                if (ch != '\\') break;                                                       // a control byte (or the end of the readable text)
+                const uint32_t e1 = x + 1 < ev_end ? (uint32_t)io_byte(io, x + 1) : 0u;
+                uint32_t el = 0;
+                if (e1 == 'u') { el = 6; for (uint32_t h4 = 2; h4 < 6; ++h4) { const uint32_t h = x + h4 < ev_end ? (uint32_t)io_byte(io, x + h4) : 0u; if (!(h - '0' < 10u || (h | 0x20u) - 'a' < 6u)) el = 0; } }
+                else if (e1 == '"' || e1 == '\\' || e1 == '/' || e1 == 'b' || e1 == 'f' || e1 == 'n' || e1 == 'r' || e1 == 't') el = 2;
+                if (el == 0) break;
+                q = x + el;
+                if (q - mpos > R2_MAX_STR) break;
+            }
+        } else {                                                                              // number value: the event's own number must be valid
+            const uint32_t bs = mpos - (t2 - sstart);
+            uint32_t x2 = 0, good = 0;
+            if (lane == 0) {
+                uint32_t st = L_VALUE, p = bs;
+                for (;;) {
+                    if (p >= ev_end) break;
+                    const uint32_t cl = sh->cls[io_byte(io, p)];
+                    if (cl < C_MINUS || cl > C_EXP) break;
+                    st = sh->trans[st * 32 + cl] & 31u;
+                    if (st == L_ERR) break;
+                    ++p;
+                }
+                good = (st == L_NUM_ZERO || st == L_NUM_INT || st == L_NUM_FRAC || st == L_NUM_EXP) ? 1u : 0u;
+                x2 = p;
+            }
+            x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
+            if (good && x2 >= mpos) { o.pos = x2; o.t = send; o.last_ra = x2; return o; }
+        }
+    }
+    // the event does not follow this slot: back to its start
+    o.kind = 1; o.pos = o.s_open; o.t = 0; o.last_ra = R2_NONE;
+    return o;
+}
+
+// One event that does not follow the default slot: the other slots span by span (usage events read their fields on the
+// way), else the byte-wise recogniser (which may leave a new template behind).
+//   e: position of the event's LF LF; R2_NONE: still open at the end of the text
+//   status 1: the stream goes to the sequential path
+struct OddOut { uint32_t e, status, ev_a, ev_b, a_usage, primed, high; };
+R2_DEV_NOINLINE OddOut odd_event(const StepArgs* ap, R2Shared* sh, R2Io io, uint32_t lane, uint32_t seg, uint32_t tb, uint32_t ps, uint32_t sub_end,
+                                 uint32_t in_kept, uint32_t primed, uint32_t skip_slot) {
+    OddOut o; o.e = R2_NONE; o.status = 0; o.ev_a = o.ev_b = o.a_usage = 0; o.primed = primed; o.high = 0;
+    TemplateCache2* tc = ap->s.tpl_cache2;
+    const uint32_t ev_end = r2_min(sub_end, ps + ap->t.carry_cap + 2u);
+    uint32_t ready = 0, free_slots = 0;
+    if (lane == 0) for (uint32_t k = 0; k < R2_SLOTS; ++k) { const uint32_t st = *(volatile uint32_t*)&sh->slot_state[k]; if (st == 2u) ready |= 1u << k; else if (st == 0u) free_slots |= 1u << k; }
+    ready = __shfl_sync(R2_FULL, ready, 0); free_slots = __shfl_sync(R2_FULL, free_slots, 0);
+    for (uint32_t slot = 0; slot < R2_SLOTS; ++slot) {
+        if (!(ready & (1u << slot)) || slot == skip_slot) continue;
+        const TplMeta& m = sh->tpl[slot].m;
+        const SingleOut so = match_single(io, &sh->tpl[slot], lane, ps, ev_end);
+        if (!so.ok) continue;
+        o.high |= so.high;
+        if (lane == 0) atomicAdd(&tc->hits[slot], 1u);
+        const Acct ac = account(ap, lane, seg, in_kept, primed, m.cls, m.flags, 1, ps, so.e);
+        if (!ac.ok) { o.status = 1; return o; }
+        if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP)
+            extract_usage(ap, io, &m, sh->raw_tpl + slot, &sh->raw_warp[R2_TID >> 5], lane, seg, ps, so.f_start, so.f_len, so.f_esc);
+        o.e = so.e; o.ev_a = ac.ev_a; o.ev_b = ac.ev_b; o.a_usage = ac.a_usage; o.primed = ac.primed;
+        return o;
+    }
+    // ---- no template fits: the byte-wise recogniser walks the event ----
+    if (ps > tb && io_byte(io, ps) == '\n') { o.status = 1; return o; }                       // LF run >= 3
+    const LeanOut lo = lean_event(io, lane, ps, ev_end);
+    o.high |= lo.high;
+    if (lo.e == R2_NONE) { if (ev_end < sub_end) o.status = 1; return o; }                    // longer than the carry capacity / open at the end of the text
+    if (lo.e + 2 < sub_end && io_byte(io, lo.e + 2) == '\n') { o.status = 1; return o; }
+    if (lo.cls != PC_NONE && lane == 0) atomicAdd(&tc->general, 1u);
+    const Acct ac = account(ap, lane, seg, in_kept, primed, lo.cls, lo.f, 1, ps, lo.e);
+    if (!ac.ok) { o.status = 1; return o; }
+    if (lo.cls != PC_NONE && (lo.f & PF_VALID_A) && !(lo.f & (TK_ERROR | TK_DETAIL | TK_CODE)) && lo.e - ps >= R2_TPL_MIN && lo.e - ps <= R2_TPL_MAX && free_slots)
+        learn_template(ap, sh, io, sh->raw_tpl, lane, ready, ps, sub_end);
+    o.e = lo.e; o.ev_a = ac.ev_a; o.ev_b = ac.ev_b; o.a_usage = ac.a_usage; o.primed = ac.primed;
+    return o;
 }
 
 // Walk the current segment from c.pos.  Returns true when the warp is done (the open event starts in the next warp's
@@ -1033,70 +967,87 @@ R2_DEV_NOINLINE R2Ctx general_step(R2Ctx c, const uint32_t range_hi) {
 // segment (counters, chunk-level UTF-8) either way.
 R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
     R2Shared* sh = c.sh;
-    const StepArgs& a = *c.a;
     const uint32_t lane = c.lane;
-    TemplateCache2* tc = a.s.tpl_cache2;
     for (;;) {
         const uint32_t sub_end = c.in_kept ? c.kept_end : c.te;                // the text the current phase may read
         if (c.pos >= sub_end) {
             // ---- end of the kept chunk / of the segment's text ----
             if (c.in_kept) {                                                   // the speculation holds when a real event was accepted
                 if (c.s_open != c.kept_end || !c.primed) { mark_irregular(c); return false; }   //   and the chunk ends on a separator
-                if (lane == 0) a.s.plan[c.seg].prime_ok = 1;
+                if (lane == 0) c.a->s.plan[c.seg].prime_ok = 1;
                 c.in_kept = 0;
                 continue;
             }
-            if (lane == 0) a.s.plan[c.seg].tail_start = c.s_open;              // the open event is the new carry
+            if (lane == 0) c.a->s.plan[c.seg].tail_start = c.s_open;           // the open event is the new carry
             return false;
         }
         if (c.s_open >= range_hi && c.pos == c.s_open && !c.in_kept) return true;   // the open event starts in the next warp's range
         while (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) pipe_advance(c);      // (slow paths may have run ahead of the resident tile)
 
+        const bool have_dflt = (c.ready & (1u << c.dflt)) != 0u && !(sh->tpl[c.dflt].m.flags & TK_USAGE);
         // ---- fast loop: whole 16-byte aligned windows of the resident tile against the default slot's periodic image ----
         // (no boundary lanes, no limits other than the tile's end; anything else -- a mismatch, the end of the text or of the
-        //  range, a usage-bearing default -- leaves the loop and is handled by the general pass below, from the same position)
-        if (c.slot == c.dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
+        //  range -- leaves the loop and is handled by the pass below, from the same position)
+        if (have_dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
             const TplMeta& dm = sh->tpl[c.dflt].m;
-            const uint32_t P = dm.P, recip = dm.recip, dflags = dm.flags;
-            if (!(dflags & TK_USAGE)) {
-                const uint32_t stop = r2_min(sub_end, range_hi);          // whole windows must end at or before this
-                const SPtr ft = sptr(sh->fast_text), fl = sptr(sh->fast_lit);
-                uint32_t nfast = 0, pos = c.pos, t = c.t, s_open = c.s_open, high = 0;
-                for (;;) {
-                    const uint32_t lim = r2_min(pos + 512u, c.tile_hi);
-                    if (lim > stop || (lim & 15u)) break;
-                    const uint32_t lp = pos + 16u * lane;
-                    const uint32_t u = t + 16u * lane;
-                    const uint32_t tl = u - __umulhi(u, recip) * P;
-                    const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
-                    uint32_t bad = 0;
-                    if (lp < lim) {
-                        const uint4 d = sld128(c.buf + (lp - c.tile_lo));
-                        const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad);
-                        high |= d.x | d.y | d.z | d.w;
-                        const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
-                        const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
-                        bad = lit | (~ok & 0x80808080u);
-                    }
-                    if (__ballot_sync(R2_FULL, bad != 0)) break;           // the general pass finds out where and why
-                    const uint32_t u2 = t + (lim - pos);
-                    const uint32_t nwr = __umulhi(u2, recip);
-                    t = u2 - nwr * P; pos = lim; nfast += nwr;
-                    if (nwr) s_open = pos - t;
-                    if (pos >= c.tile_hi) { if (c.k + 1 < c.n_tiles) pipe_advance(c); else break; }
+            const uint32_t P = dm.P, recip = dm.recip;
+            const uint32_t stop = r2_min(sub_end, range_hi);              // whole windows must end at or before this
+            const SPtr ft = sptr(sh->fast_text), fl = sptr(sh->fast_lit);
+            uint32_t nfast = 0, pos = c.pos, t = c.t, s_open = c.s_open, high = 0;
+            for (;;) {
+                const uint32_t lim = r2_min(pos + 512u, c.tile_hi);
+                if (lim > stop || (lim & 15u)) break;
+                const uint32_t lp = pos + 16u * lane;
+                const uint32_t u = t + 16u * lane;
+                const uint32_t tl = u - __umulhi(u, recip) * P;
+                const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
+                uint32_t bad = 0;
+                if (lp < lim) {
+                    const uint4 d = sld128(c.buf + (lp - c.tile_lo));
+                    const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad);
+                    high |= d.x | d.y | d.z | d.w;
+                    const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
+                    const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
+                    bad = lit | (~ok & 0x80808080u);
                 }
-                c.high |= high;
-                if (nfast) {
-                    c.hits_d += nfast; c.tried = 0; c.s_open = s_open;
-                    if (dm.cls == PC_DATA) c.ev_a += nfast;
-                    if (dflags & PF_VALID_B) c.ev_b += nfast;
-                }
-                if (pos != c.pos) { c.pos = pos; c.t = t; continue; }
+                if (__ballot_sync(R2_FULL, bad != 0)) break;               // the pass below finds out where and why
+                const uint32_t u2 = t + (lim - pos);
+                const uint32_t nwr = __umulhi(u2, recip);
+                t = u2 - nwr * P; pos = lim; nfast += nwr;
+                if (nwr) s_open = pos - t;
+                if (pos >= c.tile_hi) break;                                // (the walk moves the pipeline on: no call inside this loop)
             }
+            c.high |= high;
+            if (nfast) {
+                c.hits_d += nfast; c.s_open = s_open;
+                if (dm.cls == PC_DATA) c.ev_a += nfast;
+                if (dm.flags & PF_VALID_B) c.ev_b += nfast;
+            }
+            if (pos != c.pos) { c.pos = pos; c.t = t; continue; }
         }
-
-        c = general_step(c, range_hi);
-        if (c.status) { c.status = 0; mark_irregular(c); return false; }
+        // ---- one pass with its boundary lanes, limits and re-anchoring (out of line) ----
+        if (have_dflt) {
+            const PassOut po = pass_step(io_of(c), lane, c.dflt, c.fast, c.pos, c.t, c.s_open, c.last_ra, sub_end, range_hi, c.in_kept, c.a->t.carry_cap);
+            c.high |= po.high;
+            if (po.nwr) {
+                const TplMeta& dm = sh->tpl[c.dflt].m;
+                c.hits_d += po.nwr;
+                if (dm.cls == PC_DATA) { if (c.in_kept) c.primed = 1; else c.ev_a += po.nwr; }      // (a template is a valid event without error/detail)
+                if (dm.flags & PF_VALID_B) c.ev_b += po.nwr;
+            }
+            c.pos = po.pos; c.t = po.t; c.s_open = po.s_open; c.last_ra = po.last_ra;
+            if (po.kind == 0) continue;
+        }
+        // ---- the event at s_open does not follow the default slot ----
+        {
+            const OddOut oo = odd_event(c.a, sh, io_of(c), lane, c.seg, c.tb, c.s_open, sub_end, c.in_kept, c.primed, have_dflt ? c.dflt : R2_NONE);
+            c.high |= oo.high;
+            if (oo.status) { mark_irregular(c); return false; }
+            refresh_slots(c);
+            if (oo.e == R2_NONE) { c.pos = sub_end; continue; }             // open at the end of the text: the carry
+            c.ev_a += oo.ev_a; c.ev_b += oo.ev_b; c.a_usage |= oo.a_usage; c.primed = oo.primed;
+            c.pos = c.s_open = oo.e + 2u; c.t = 0; c.last_ra = R2_NONE;
+        }
     }
 }
 
@@ -1117,7 +1068,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
         else reinterpret_cast<uint32_t*>(sh->trans)[k - 64] = reinterpret_cast<const uint32_t*>(lean_tables().trans)[k - 64];
     }
     if (tid < R2_SLOTS) sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u;
-    if (tid == 0) { sh->fast_ready = 0; sh->learn_lock = 0; }
+    if (tid == 0) { sh->fast_ready = 0; sh->learn_lock = 0; sh->args = a; }
     if (lane == 0) for (uint32_t b = 0; b < R2_NBUF; ++b) mbar_init(sptr(&sh->mbar[warp * R2_NBUF + b]), 1);
     mbar_fence_init();
     __syncthreads();
@@ -1147,16 +1098,15 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     const uint32_t gw = R2_BID * R2_WARPS + warp;
     const uint32_t t_first = gw * tiles_per_warp;
     R2Ctx c;
-    c.a = &a; c.sh = sh; c.lane = lane;
+    c.a = &sh->args; c.sh = sh; c.lane = lane;
     c.ring = sptr(smem) + warp * R2_NBUF * R2_TILE; c.bars = sptr(&sh->mbar[warp * R2_NBUF]);
     c.n_bytes = a.n_bytes;
     c.base = base0 + t_first * R2_TILE;
     c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
-    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0; c.status = 0;
+    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0;
     refresh_slots(c);
-    c.block_raw = block_raw; c.warp_raw = &sh->raw_warp[warp];
     c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
-    c.slot = c.dflt; c.t = 0; c.tried = 0; c.pos = c.s_open = 0;
+    c.t = 0; c.pos = c.s_open = 0;
     c.in_kept = c.primed = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;
     if (c.n_tiles == 0) return;
     const uint32_t range_lo = r2_max(c.base, a.tile_base);          // (tile_base = first byte of this launch; a slice starts inside tile 0)
