@@ -194,11 +194,20 @@ LGW_HD_NOINLINE bool exact_convert(uint64_t man, int exp10, uint64_t& out_bits) 
     return true;
 }
 
+#define LGW_P10_LIST {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22}
+#if defined(__CUDACC__)
+__device__ __constant__ double g_p10_dev[23] = LGW_P10_LIST;      // (a local array would be rebuilt on the stack by every call)
+#endif
+static const double g_p10_host[23] = LGW_P10_LIST;
+
 LGW_HD bool dec_to_double(uint64_t man, int exp10, uint64_t& bits) {
     // Clinger: both operands exact doubles
     if (man < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
-        const double p10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                              1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+#if defined(__CUDA_ARCH__)
+        const double* p10 = g_p10_dev;
+#else
+        const double* p10 = g_p10_host;
+#endif
         double d = (double)man;
         d = exp10 < 0 ? d / p10[-exp10] : d * p10[exp10];
         bits = dbl2bits(d);

@@ -262,7 +262,7 @@ R2_DEV void pipe_start(R2Ctx& c) {
 }
 // make tile k resident (k = previous + 1): wait for its bytes, hand it to the store engine, refill the buffer that just became free
 struct PipeState { uint32_t k, tile_lo, tile_hi; SPtr buf; };
-R2_DEV_NOINLINE PipeState pipe_advance_impl(const StepArgs* ap, SPtr ring, SPtr bars, uint32_t base, uint32_t n_tiles, uint32_t n_bytes, uint32_t k_prev, uint32_t lane) {
+R2_DEV PipeState pipe_advance_impl(const StepArgs* ap, SPtr ring, SPtr bars, uint32_t base, uint32_t n_tiles, uint32_t n_bytes, uint32_t k_prev, uint32_t lane) {
     const uint32_t k = k_prev == R2_NONE ? 0u : k_prev + 1u;
     __syncwarp();                                   // every lane is done with the buffers of the earlier tiles
     const uint32_t lo = base + k * R2_TILE;
@@ -806,6 +806,68 @@ R2_DEV Acct account(const StepArgs* ap, uint32_t lane, uint32_t seg, uint32_t in
     return r;
 }
 
+// The hot loop of the kernel.  Whole 16-byte aligned windows of the resident tile against the default slot's periodic image,
+// two windows per trip while two fit (two independent chains of loads and byte tests in flight), moving the TMA pipeline on
+// from tile to tile.  No boundary lanes, no limits other than `stop` (end of the text / of the range); a mismatch, or a window
+// that does not fit before `stop`, ends the run -- the caller's pass finds out where and why, from the same position.  Out of
+// line with scalar arguments so that nothing but the loop's own values lives in registers here (no spill code in the loop).
+struct FastOut { uint32_t k, tile_lo, tile_hi; SPtr buf; uint32_t pos, t, s_open, nfast, high; };
+R2_DEV_NOINLINE FastOut fast_run(const StepArgs* ap, const R2Shared* sh, SPtr ring, SPtr bars, uint32_t base, uint32_t n_tiles, uint32_t n_bytes,
+                                 uint32_t k, uint32_t tile_lo, uint32_t tile_hi, SPtr buf, uint32_t pos, uint32_t t, uint32_t s_open,
+                                 const uint32_t stop, const uint32_t P, const uint32_t recip, const uint32_t lane) {
+    const SPtr ft = sptr(sh->fast_text), fl = sptr(sh->fast_lit);
+    uint32_t nfast = 0, high = 0;
+    for (;;) {
+        if (pos >= tile_hi) {
+            if (k + 1 >= n_tiles) break;
+            const PipeState ps = pipe_advance_impl(ap, ring, bars, base, n_tiles, n_bytes, k, lane);
+            k = ps.k; tile_lo = ps.tile_lo; tile_hi = ps.tile_hi; buf = ps.buf;
+        }
+        const uint32_t u = t + 16u * lane;
+        const uint32_t tl = u - __umulhi(u, recip) * P;
+        const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
+        const SPtr dp = buf + (pos + 16u * lane - tile_lo);
+        if (pos + 1024u <= tile_hi && pos + 1024u <= stop) {
+            const uint32_t ub = u + 512u;
+            const uint32_t tlb = ub - __umulhi(ub, recip) * P;
+            const uint32_t adb = (tlb & 15u) * R2_TEXT + (tlb & ~15u);
+            const uint4 d = sld128(dp), e = sld128(dp + 512u);
+            const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad), txb = sld128(ft + adb), mkb = sld128(fl + adb);
+            high |= d.x | d.y | d.z | d.w | e.x | e.y | e.z | e.w;
+            const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
+            const uint32_t litb = ((e.x ^ txb.x) & mkb.x) | ((e.y ^ txb.y) & mkb.y) | ((e.z ^ txb.z) & mkb.z) | ((e.w ^ txb.w) & mkb.w);
+            const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
+            const uint32_t okb = span_ok(e.x, mkb.x) & span_ok(e.y, mkb.y) & span_ok(e.z, mkb.z) & span_ok(e.w, mkb.w);
+            if (!__ballot_sync(R2_FULL, (lit | litb | (~(ok & okb) & 0x80808080u)) != 0)) {
+                const uint32_t u2 = t + 1024u;
+                const uint32_t nwr = __umulhi(u2, recip);
+                t = u2 - nwr * P; pos += 1024u; nfast += nwr;
+                if (nwr) s_open = pos - t;
+                continue;
+            }
+        }
+        // one window (the last of a tile, or the first of a pair that did not match)
+        const uint32_t lim = r2_min(pos + 512u, tile_hi);
+        if (lim > stop || (lim & 15u)) break;
+        uint32_t bad = 0;
+        if (pos + 16u * lane < lim) {
+            const uint4 d = sld128(dp);
+            const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad);
+            high |= d.x | d.y | d.z | d.w;
+            const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
+            const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
+            bad = lit | (~ok & 0x80808080u);
+        }
+        if (__ballot_sync(R2_FULL, bad != 0)) break;
+        const uint32_t u2 = t + (lim - pos);
+        const uint32_t nwr = __umulhi(u2, recip);
+        t = u2 - nwr * P; pos = lim; nfast += nwr;
+        if (nwr) s_open = pos - t;
+    }
+    FastOut o; o.k = k; o.tile_lo = tile_lo; o.tile_hi = tile_hi; o.buf = buf; o.pos = pos; o.t = t; o.s_open = s_open; o.nfast = nfast; o.high = high;
+    return o;
+}
+
 // One compare pass of up to 512 bytes from pos against the default slot's periodic image, boundary lanes and limits
 // included, and -- on a mismatch inside a value span -- the re-anchoring behind the value's own end.
 //   kind 0: fine (ran to its limit, or re-anchored): go on from (pos, t)
@@ -985,45 +1047,19 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
         while (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) pipe_advance(c);      // (slow paths may have run ahead of the resident tile)
 
         const bool have_dflt = (c.ready & (1u << c.dflt)) != 0u && !(sh->tpl[c.dflt].m.flags & TK_USAGE);
-        // ---- fast loop: whole 16-byte aligned windows of the resident tile against the default slot's periodic image ----
-        // (no boundary lanes, no limits other than the tile's end; anything else -- a mismatch, the end of the text or of the
-        //  range -- leaves the loop and is handled by the pass below, from the same position)
+        // ---- fast run: whole 16-byte aligned windows against the default slot's periodic image, tile after tile (out of line) ----
         if (have_dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
             const TplMeta& dm = sh->tpl[c.dflt].m;
-            const uint32_t P = dm.P, recip = dm.recip;
-            const uint32_t stop = r2_min(sub_end, range_hi);              // whole windows must end at or before this
-            const SPtr ft = sptr(sh->fast_text), fl = sptr(sh->fast_lit);
-            uint32_t nfast = 0, pos = c.pos, t = c.t, s_open = c.s_open, high = 0;
-            for (;;) {
-                const uint32_t lim = r2_min(pos + 512u, c.tile_hi);
-                if (lim > stop || (lim & 15u)) break;
-                const uint32_t lp = pos + 16u * lane;
-                const uint32_t u = t + 16u * lane;
-                const uint32_t tl = u - __umulhi(u, recip) * P;
-                const uint32_t ad = (tl & 15u) * R2_TEXT + (tl & ~15u);
-                uint32_t bad = 0;
-                if (lp < lim) {
-                    const uint4 d = sld128(c.buf + (lp - c.tile_lo));
-                    const uint4 tx = sld128(ft + ad), mk = sld128(fl + ad);
-                    high |= d.x | d.y | d.z | d.w;
-                    const uint32_t lit = ((d.x ^ tx.x) & mk.x) | ((d.y ^ tx.y) & mk.y) | ((d.z ^ tx.z) & mk.z) | ((d.w ^ tx.w) & mk.w);
-                    const uint32_t ok = span_ok(d.x, mk.x) & span_ok(d.y, mk.y) & span_ok(d.z, mk.z) & span_ok(d.w, mk.w);
-                    bad = lit | (~ok & 0x80808080u);
-                }
-                if (__ballot_sync(R2_FULL, bad != 0)) break;               // the pass below finds out where and why
-                const uint32_t u2 = t + (lim - pos);
-                const uint32_t nwr = __umulhi(u2, recip);
-                t = u2 - nwr * P; pos = lim; nfast += nwr;
-                if (nwr) s_open = pos - t;
-                if (pos >= c.tile_hi) break;                                // (the walk moves the pipeline on: no call inside this loop)
+            const FastOut fo = fast_run(c.a, sh, c.ring, c.bars, c.base, c.n_tiles, c.n_bytes, c.k, c.tile_lo, c.tile_hi, c.buf,
+                                        c.pos, c.t, c.s_open, r2_min(sub_end, range_hi), dm.P, dm.recip, lane);
+            c.k = fo.k; c.tile_lo = fo.tile_lo; c.tile_hi = fo.tile_hi; c.buf = fo.buf;
+            c.high |= fo.high;
+            if (fo.nfast) {
+                c.hits_d += fo.nfast; c.s_open = fo.s_open;
+                if (dm.cls == PC_DATA) c.ev_a += fo.nfast;
+                if (dm.flags & PF_VALID_B) c.ev_b += fo.nfast;
             }
-            c.high |= high;
-            if (nfast) {
-                c.hits_d += nfast; c.s_open = s_open;
-                if (dm.cls == PC_DATA) c.ev_a += nfast;
-                if (dm.flags & PF_VALID_B) c.ev_b += nfast;
-            }
-            if (pos != c.pos) { c.pos = pos; c.t = t; continue; }
+            if (fo.pos != c.pos) { c.pos = fo.pos; c.t = fo.t; continue; }
         }
         // ---- one pass with its boundary lanes, limits and re-anchoring (out of line) ----
         if (have_dflt) {
