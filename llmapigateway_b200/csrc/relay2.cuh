@@ -99,9 +99,9 @@ struct R2Shared {
     alignas(16) uint8_t fast_lit[16 * R2_TEXT];
     alignas(16) Tpl2 tpl[R2_SLOTS];
     alignas(8) UsageRaw raw_tpl[R2_SLOTS];           // the template events' own UsageRaw (usage_ok slots)
-    alignas(8) UsageRaw raw_warp[R2_WARPS];          // per warp: the record being assembled from a matched usage event
     alignas(8) unsigned long long mbar[R2_WARPS * R2_NBUF];
     uint32_t slot_state[R2_SLOTS];                   // 0 empty, 1 being built, 2 ready
+    uint32_t slot_gidx[R2_SLOTS];                    // the same template's slot in the engine-wide cache (R2_NONE: local to this block)
     uint32_t hits[R2_SLOTS];
     uint32_t general;
     uint32_t dflt, fast_ready;
@@ -196,7 +196,7 @@ struct R2Ctx {
     uint32_t n_bytes;            // end of the valid bytes
     // segment
     uint32_t seg, tb, te, kept_end;    // text of the current segment [tb, te); kept_end: end of the speculatively kept chunk (0: none)
-    uint32_t in_kept, primed;
+    uint32_t in_kept, primed, kept_tried;   // in_kept: 0 no kept chunk (any more), 1 walking it on its own, 2 walking it optimistically
     uint32_t ev_a, ev_b, a_usage;
     uint32_t high;               // some byte >= 0x80 was seen in the current segment's text
     uint32_t walk_lo;            // first text position this warp walked in the current segment
@@ -559,6 +559,7 @@ R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, U
             TemplateCache2* tc = ap->s.tpl_cache2;
             UsageRaw* raw = block_raw + slot;
             if (build_template2(rd, &sh->tpl[slot], raw, ps, end)) {
+                sh->slot_gidx[slot] = R2_NONE;
                 if (atomicCAS(&tc->lock, 0u, 1u) == 0u) {                        // (busy: the template stays local to this block for this launch)
                     bool dup = false; uint32_t dst = R2_NONE;
                     for (uint32_t k = 0; k < R2_SLOTS; ++k) {
@@ -566,10 +567,12 @@ R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, U
                         if (st == 2u) { if (tpl_same(tc->tpl[k], sh->tpl[slot])) dup = true; }
                         else if (st == 0u && dst == R2_NONE) dst = k;
                     }
+                    sh->slot_gidx[slot] = R2_NONE;
                     if (!dup && dst != R2_NONE) {
                         tc->tpl[dst] = sh->tpl[slot]; tc->raw[dst] = *raw; tc->hits[dst] = 0;
                         __threadfence();
                         atomicExch(&tc->state[dst], 2u);
+                        sh->slot_gidx[slot] = dst;
                     }
                     __threadfence();
                     atomicExch(&tc->lock, 0u);
@@ -600,7 +603,7 @@ R2_DEV_NOINLINE void learn_template(const StepArgs* ap, R2Shared* sh, R2Io io, U
 // byte.  Sets the text range and the first event start this warp owns in it; false: the warp owns nothing here.
 R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_hi) {
     const SegPlan* pl = c.a->s.plan + seg;
-    c.seg = seg; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0; c.in_kept = 0; c.primed = 0;
+    c.seg = seg; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0; c.in_kept = 0; c.primed = 0; c.kept_tried = 0;
     const uint32_t tb = pl->relay_begin, te = pl->seg_end;
     c.tb = tb; c.te = te;
     const uint32_t kept = pl->kept_chunk != 0xFFFFFFFFu ? pl->kept_end : 0u;
@@ -720,62 +723,6 @@ R2_DEV_NOINLINE SingleOut match_single(R2Io io, const Tpl2* tp, uint32_t lane, u
     return o;
 }
 
-// usage fields of the event at ps straight from the value spans the match located (usage_ok templates): numbers through
-// decimal.cuh, strings copied (decoded like the full machine does when they hold escapes), get_token_usage's arithmetic
-// (normalise_usage) on the assembled record -> the segment's candidate record, which k_commit2 installs.
-R2_DEV_NOINLINE void extract_usage(const StepArgs* ap, R2Io io, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, uint32_t lane, uint32_t seg, uint32_t ps,
-                                   uint32_t f_start, uint32_t f_len, uint32_t f_esc) {
-    const TplMeta& m = *mp;
-    R2Glob rd{io.data, io.n_bytes};
-    Val v; v.kind = KD_ABSENT; v.bits = 0;
-    const uint32_t fj = lane < 8u ? m.field_span[lane] : 0xffu;
-    for (uint32_t k = lane; k < sizeof(UsageRaw) / 4; k += 32) reinterpret_cast<uint32_t*>(raw)[k] = reinterpret_cast<const uint32_t*>(tpl_raw)[k];
-    __syncwarp();
-    const uint32_t slow_str = __ballot_sync(R2_FULL, fj != 0xffu && lane >= UF_MODEL && f_esc != 0u);
-    if (fj != 0xffu) {
-        if (lane < UF_MODEL) v = parse_number_span(rd, f_start, f_len);
-        else if (f_esc) {                                                              // escapes: decode like json_machine.cuh does
-            if (lane == UF_MODEL) decode_string_span(rd, f_start, f_len, raw->model, raw->model_len, raw->model_flags);
-            else decode_string_span(rd, f_start, f_len, raw->provider, raw->provider_len, raw->provider_flags);
-        } else if (lane == UF_MODEL) { raw->model_len = 0; raw->model_flags = 0; }
-        else { raw->provider_len = 0; raw->provider_flags = 0; }
-    }
-    __syncwarp();
-    for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
-        const unsigned long long vb = __shfl_sync(R2_FULL, (unsigned long long)v.bits, (int)fi);
-        const uint32_t vk = __shfl_sync(R2_FULL, (uint32_t)v.kind, (int)fi);
-        if (lane == 0 && m.field_span[fi] != 0xffu) {
-            Val x; x.bits = (int64_t)vb; x.kind = (uint8_t)vk;
-            if (fi == UF_PROMPT) raw->prompt = x; else if (fi == UF_COMPLETION) raw->completion = x; else if (fi == UF_TOTAL) raw->total = x;
-            else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
-        }
-    }
-    UsageRec* cand = ap->s.usage_cand + seg;
-    uint32_t has = 0;                                                                  // bit 0: the record carries "model" as a string, bit 1: "provider"
-    if (lane == 0) {
-        normalise_usage(*raw, m.full_flags, *cand);
-        has = (cand->model_val.kind == KD_STR ? 1u : 0u) | (cand->provider_val.kind == KD_STR ? 2u : 0u);
-    }
-    has = __shfl_sync(R2_FULL, has, 0);
-    // plain strings (no escapes): the span's bytes ARE the decoded text -- copy them into the record, a lane per byte
-    for (uint32_t which = 0; which < 2; ++which) {
-        const uint32_t fl = UF_MODEL + which;
-        const uint32_t span = m.field_span[fl];
-        const uint32_t st = __shfl_sync(R2_FULL, f_start, (int)fl), ln = __shfl_sync(R2_FULL, f_len, (int)fl);
-        if (span == 0xffu || (slow_str & (1u << fl)) || !(has & (1u << which))) continue;
-        const uint32_t n = ln < LGW_STR_CAP ? ln : (uint32_t)LGW_STR_CAP;
-        char* dst = which == 0 ? cand->model : cand->provider;
-        for (uint32_t k = lane; k < n; k += 32) dst[k] = (char)rd.at(st + k);
-        if (lane == 0) {
-            if (which == 0) cand->model_len = (uint8_t)n; else cand->provider_len = (uint8_t)n;
-            if (ln > LGW_STR_CAP) { cand->str_flags |= which == 0 ? 1u : 4u; cand->exotic = 1; }      // truncated: reported, like the full machine's capture
-        }
-    }
-    __syncwarp();
-    if (lane == 0) ap->s.plan[seg].cand_ps = ps + 1u;            // (k_commit2 runs after this kernel: no fence needed)
-    __syncwarp();
-}
-
 // ---- the two out-of-line steps of the walk ---------------------------------------------------------------------------------------
 // Both take a handful of scalars and return a handful: the walk's own values stay in registers across the calls (passing the
 // whole context by value cost ~90 local-memory words per call, and with 180 KB of shared memory there is next to no L1 left
@@ -872,13 +819,13 @@ R2_DEV_NOINLINE FastOut fast_run(const StepArgs* ap, const R2Shared* sh, SPtr ri
 // included, and -- on a mismatch inside a value span -- the re-anchoring behind the value's own end.
 //   kind 0: fine (ran to its limit, or re-anchored): go on from (pos, t)
 //   kind 1: the event that starts at s_open does not follow the default slot
-struct PassOut { uint32_t pos, t, s_open, nwr, kind, last_ra, high; };
+struct PassOut { uint32_t pos, t, s_open, nwr, kind, last_ra, high, reanchored; };
 R2_DEV_NOINLINE PassOut pass_step(R2Io io, uint32_t lane, uint32_t slot, uint32_t fast, uint32_t pos0, uint32_t t0, uint32_t s_open0, uint32_t last_ra,
                                   uint32_t sub_end, uint32_t range_hi, uint32_t in_kept, uint32_t carry_cap) {
     const R2Shared* sh = io.sh;
     const TplMeta& m = sh->tpl[slot].m;
     const uint32_t P = m.P;
-    PassOut o; o.pos = pos0; o.t = t0; o.s_open = s_open0; o.nwr = 0; o.kind = 0; o.last_ra = last_ra; o.high = 0;
+    PassOut o; o.pos = pos0; o.t = t0; o.s_open = s_open0; o.nwr = 0; o.kind = 0; o.last_ra = last_ra; o.high = 0; o.reanchored = 0;
     const uint32_t wbase = pos0 & ~15u;
     uint32_t lim = r2_min(sub_end, wbase + 512u);
     if (pos0 >= io.tile_lo && pos0 < io.tile_hi) lim = r2_min(lim, io.tile_hi);             // windows do not straddle the resident tile's end
@@ -947,7 +894,7 @@ R2_DEV_NOINLINE PassOut pass_step(R2Io io, uint32_t lane, uint32_t slot, uint32_
                 if (!sp) { q += 32; if (q - mpos > R2_MAX_STR) break; continue; }
                 const uint32_t k = (uint32_t)__ffs(sp) - 1u, x = q + k;
                 const uint32_t ch = __shfl_sync(R2_FULL, c, (int)k);
-                if (ch == '"') { o.pos = x; o.t = send; return o; }                           // (the closing quote itself is compared by the next pass)
+                if (ch == '"') { o.pos = x; o.t = send; o.reanchored = 1; return o; }        // (the closing quote itself is compared by the next pass)
                 if (ch != '\\') break;                                                       // a control byte (or the end of the readable text)
                 const uint32_t e1 = x + 1 < ev_end ? (uint32_t)io_byte(io, x + 1) : 0u;
                 uint32_t el = 0;
@@ -974,12 +921,19 @@ R2_DEV_NOINLINE PassOut pass_step(R2Io io, uint32_t lane, uint32_t slot, uint32_
                 x2 = p;
             }
             x2 = __shfl_sync(R2_FULL, x2, 0); good = __shfl_sync(R2_FULL, good, 0);
-            if (good && x2 >= mpos) { o.pos = x2; o.t = send; o.last_ra = x2; return o; }
+            if (good && x2 >= mpos) { o.pos = x2; o.t = send; o.last_ra = x2; o.reanchored = 1; return o; }
         }
     }
     // the event does not follow this slot: back to its start
     o.kind = 1; o.pos = o.s_open; o.t = 0; o.last_ra = R2_NONE;
     return o;
+}
+
+// the first eight bytes of the event at ps against the first eight of a template (literal positions only): true = they part
+R2_DEV bool head_differs(const R2Io& io, const Tpl2* tp, uint32_t lane, uint32_t ps, uint32_t ev_end) {
+    bool diff = false;
+    if (lane < 8u && tp->lit[lane]) diff = ps + lane >= ev_end || (uint32_t)io_byte(io, ps + lane) != (uint32_t)tp->text[lane];
+    return __any_sync(R2_FULL, diff) != 0;
 }
 
 // One event that does not follow the default slot: the other slots span by span (usage events read their fields on the
@@ -997,15 +951,20 @@ R2_DEV_NOINLINE OddOut odd_event(const StepArgs* ap, R2Shared* sh, R2Io io, uint
     ready = __shfl_sync(R2_FULL, ready, 0); free_slots = __shfl_sync(R2_FULL, free_slots, 0);
     for (uint32_t slot = 0; slot < R2_SLOTS; ++slot) {
         if (!(ready & (1u << slot)) || slot == skip_slot) continue;
+        if (head_differs(io, &sh->tpl[slot], lane, ps, ev_end)) continue;            // (most wrong slots part within the first bytes)
         const TplMeta& m = sh->tpl[slot].m;
         const SingleOut so = match_single(io, &sh->tpl[slot], lane, ps, ev_end);
         if (!so.ok) continue;
         o.high |= so.high;
-        if (lane == 0) atomicAdd(&tc->hits[slot], 1u);
+        if (lane == 0 && sh->slot_gidx[slot] != R2_NONE) atomicAdd(&tc->hits[sh->slot_gidx[slot]], 1u);
         const Acct ac = account(ap, lane, seg, in_kept, primed, m.cls, m.flags, 1, ps, so.e);
         if (!ac.ok) { o.status = 1; return o; }
-        if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP)
-            extract_usage(ap, io, &m, sh->raw_tpl + slot, &sh->raw_warp[R2_TID >> 5], lane, seg, ps, so.f_start, so.f_len, so.f_esc);
+        if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP && sh->slot_gidx[slot] != R2_NONE) {
+            // where its eight usage fields sit: k_commit2 reads the values out (one warp per segment there, nothing serial here)
+            uint2* uf = ap->s.usage_fields + (size_t)seg * 9u;
+            if (lane < 8u) uf[lane] = make_uint2(so.f_start, so.f_len | (so.f_esc << 31));
+            if (lane == 0) { uf[8] = make_uint2(sh->slot_gidx[slot], 0u); ap->s.plan[seg].cand_ps = ps + 1u; }
+        }
         o.e = so.e; o.ev_a = ac.ev_a; o.ev_b = ac.ev_b; o.a_usage = ac.a_usage; o.primed = ac.primed;
         return o;
     }
@@ -1031,9 +990,21 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
     R2Shared* sh = c.sh;
     const uint32_t lane = c.lane;
     for (;;) {
-        const uint32_t sub_end = c.in_kept ? c.kept_end : c.te;                // the text the current phase may read
+        // The kept chunk of a freshly speculated stream (in_kept 1) is walked on its own: its events are the priming loop's and the
+        // tap's, not the handler's, and it must end on a separator.  When the chunk is a whole number of default-slot periods
+        // long it is first walked OPTIMISTICALLY (in_kept 2) as part of the periodic run: if nothing but rigid default events
+        // happened up to its end, that end is a separator and the events before it were valid real events -- accounts are
+        // corrected and the chunk is done; any surprise before its end rewinds to the segment's start and walks it the careful way.
+        if (c.in_kept == 2u && c.s_open >= c.kept_end) {
+            const TplMeta& dm = sh->tpl[c.dflt].m;
+            c.ev_a -= __umulhi(c.kept_end - c.tb, dm.recip);                   // the kept chunk's events are not the handler's
+            if (lane == 0) c.a->s.plan[c.seg].prime_ok = 1;
+            c.in_kept = 0;
+        }
+        const uint32_t sub_end = c.in_kept == 1u ? c.kept_end : c.te;          // the text the current phase may read
         if (c.pos >= sub_end) {
             // ---- end of the kept chunk / of the segment's text ----
+            if (c.in_kept == 2u) { c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE; continue; }
             if (c.in_kept) {                                                   // the speculation holds when a real event was accepted
                 if (c.s_open != c.kept_end || !c.primed) { mark_irregular(c); return false; }   //   and the chunk ends on a separator
                 if (lane == 0) c.a->s.plan[c.seg].prime_ok = 1;
@@ -1047,8 +1018,13 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
         while (c.pos >= c.tile_hi && c.k + 1 < c.n_tiles) pipe_advance(c);      // (slow paths may have run ahead of the resident tile)
 
         const bool have_dflt = (c.ready & (1u << c.dflt)) != 0u && !(sh->tpl[c.dflt].m.flags & TK_USAGE);
+        if (c.in_kept == 1u && c.pos == c.tb && have_dflt && c.kept_end > c.tb && c.kept_end < c.te) {
+            const TplMeta& dm = sh->tpl[c.dflt].m;
+            const uint32_t n = c.kept_end - c.tb, q = __umulhi(n, dm.recip);
+            if (dm.cls == PC_DATA && q * dm.P == n && !c.kept_tried) { c.in_kept = 2u; c.kept_tried = 1u; }
+        }
         // ---- fast run: whole 16-byte aligned windows against the default slot's periodic image, tile after tile (out of line) ----
-        if (have_dflt && c.fast && !c.in_kept && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
+        if (have_dflt && c.fast && c.in_kept != 1u && (c.pos & 15u) == 0u && c.pos >= c.tile_lo && c.pos < c.tile_hi) {
             const TplMeta& dm = sh->tpl[c.dflt].m;
             const FastOut fo = fast_run(c.a, sh, c.ring, c.bars, c.base, c.n_tiles, c.n_bytes, c.k, c.tile_lo, c.tile_hi, c.buf,
                                         c.pos, c.t, c.s_open, r2_min(sub_end, range_hi), dm.P, dm.recip, lane);
@@ -1062,21 +1038,30 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             if (fo.pos != c.pos) { c.pos = fo.pos; c.t = fo.t; continue; }
         }
         // ---- one pass with its boundary lanes, limits and re-anchoring (out of line) ----
-        if (have_dflt) {
-            const PassOut po = pass_step(io_of(c), lane, c.dflt, c.fast, c.pos, c.t, c.s_open, c.last_ra, sub_end, range_hi, c.in_kept, c.a->t.carry_cap);
+        bool try_pass = have_dflt;
+        if (try_pass && c.t == 0u && c.pos == c.s_open && head_differs(io_of(c), &sh->tpl[c.dflt], lane, c.pos, sub_end)) try_pass = false;   // not a default event: no pass
+        if (try_pass) {
+            const PassOut po = pass_step(io_of(c), lane, c.dflt, c.fast, c.pos, c.t, c.s_open, c.last_ra, sub_end, range_hi, c.in_kept == 1u ? 1u : 0u, c.a->t.carry_cap);
             c.high |= po.high;
             if (po.nwr) {
                 const TplMeta& dm = sh->tpl[c.dflt].m;
                 c.hits_d += po.nwr;
-                if (dm.cls == PC_DATA) { if (c.in_kept) c.primed = 1; else c.ev_a += po.nwr; }      // (a template is a valid event without error/detail)
+                if (dm.cls == PC_DATA) { if (c.in_kept == 1u) c.primed = 1; else c.ev_a += po.nwr; }      // (a template is a valid event without error/detail)
                 if (dm.flags & PF_VALID_B) c.ev_b += po.nwr;
             }
             c.pos = po.pos; c.t = po.t; c.s_open = po.s_open; c.last_ra = po.last_ra;
+            if (c.in_kept == 2u && (po.kind || po.reanchored) && c.s_open < c.kept_end) {      // a surprise inside the kept chunk: walk it the careful way
+                c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE;
+                continue;
+            }
             if (po.kind == 0) continue;
+        } else if (c.in_kept == 2u && c.s_open < c.kept_end) {
+            c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE;
+            continue;
         }
         // ---- the event at s_open does not follow the default slot ----
         {
-            const OddOut oo = odd_event(c.a, sh, io_of(c), lane, c.seg, c.tb, c.s_open, sub_end, c.in_kept, c.primed, have_dflt ? c.dflt : R2_NONE);
+            const OddOut oo = odd_event(c.a, sh, io_of(c), lane, c.seg, c.tb, c.s_open, sub_end, c.in_kept == 1u ? 1u : 0u, c.primed, have_dflt ? c.dflt : R2_NONE);
             c.high |= oo.high;
             if (oo.status) { mark_irregular(c); return false; }
             refresh_slots(c);
@@ -1103,11 +1088,21 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
         if (k < 64) reinterpret_cast<uint32_t*>(sh->cls)[k] = reinterpret_cast<const uint32_t*>(lean_tables().cls)[k];
         else reinterpret_cast<uint32_t*>(sh->trans)[k - 64] = reinterpret_cast<const uint32_t*>(lean_tables().trans)[k - 64];
     }
-    if (tid < R2_SLOTS) sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u;
+    if (tid < R2_SLOTS) { sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u; sh->slot_gidx[tid] = tid; }
     if (tid == 0) { sh->fast_ready = 0; sh->learn_lock = 0; sh->args = a; }
     if (lane == 0) for (uint32_t b = 0; b < R2_NBUF; ++b) mbar_init(sptr(&sh->mbar[warp * R2_NBUF + b]), 1);
     mbar_fence_init();
     __syncthreads();
+    // this warp's byte range; its first tiles are requested now, they travel while the block sets up its tables
+    const uint32_t gw = R2_BID * R2_WARPS + warp;
+    const uint32_t t_first = gw * tiles_per_warp;
+    R2Ctx c;
+    c.a = &sh->args; c.sh = sh; c.lane = lane;
+    c.ring = sptr(smem) + warp * R2_NBUF * R2_TILE; c.bars = sptr(&sh->mbar[warp * R2_NBUF]);
+    c.n_bytes = a.n_bytes;
+    c.base = base0 + t_first * R2_TILE;
+    c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
+    pipe_start(c);
     for (uint32_t s = 0; s < R2_SLOTS; ++s) {
         if (sh->slot_state[s] != 2u) continue;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tc->tpl[s]);
@@ -1130,24 +1125,14 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     }
     __syncthreads();
 
-    // ---- this warp's byte range ----
-    const uint32_t gw = R2_BID * R2_WARPS + warp;
-    const uint32_t t_first = gw * tiles_per_warp;
-    R2Ctx c;
-    c.a = &sh->args; c.sh = sh; c.lane = lane;
-    c.ring = sptr(smem) + warp * R2_NBUF * R2_TILE; c.bars = sptr(&sh->mbar[warp * R2_NBUF]);
-    c.n_bytes = a.n_bytes;
-    c.base = base0 + t_first * R2_TILE;
-    c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
     c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0;
     refresh_slots(c);
     c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
     c.t = 0; c.pos = c.s_open = 0;
-    c.in_kept = c.primed = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;
+    c.in_kept = c.primed = c.kept_tried = 0; c.tb = c.te = c.kept_end = 0; c.walk_lo = 0;
     if (c.n_tiles == 0) return;
     const uint32_t range_lo = r2_max(c.base, a.tile_base);          // (tile_base = first byte of this launch; a slice starts inside tile 0)
     const uint32_t range_hi = r2_min(c.base + c.n_tiles * R2_TILE, a.n_bytes);
-    pipe_start(c);
     pipe_advance(c);
 
     for (uint32_t seg = a.s.tile_seg[t_first]; seg < a.n_segs; ++seg) {            // (the segment that holds the range's first byte: k_prime2's table)
@@ -1162,7 +1147,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     __syncwarp();
     if (lane == 0) {
         tma_wait_all();
-        if (c.hits_d) atomicAdd(&tc->hits[c.dflt], c.hits_d);
+        if (c.hits_d && sh->slot_gidx[c.dflt] != R2_NONE) atomicAdd(&tc->hits[sh->slot_gidx[c.dflt]], c.hits_d);
     }
 }
 
@@ -1232,6 +1217,59 @@ R2_DEV_NOINLINE void commit_usage_event(StepIO io, const uint8_t* text, uint32_t
     st.flags |= SF_REC_VALID; ++st.n_usage_b;
     if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
 }
+// usage fields of a template-following usage event straight from the value spans the bulk kernel's match located (usage_ok
+// templates): numbers through decimal.cuh, strings copied (decoded like the full machine does when they hold escapes),
+// get_token_usage's arithmetic (normalise_usage) on the assembled record, which lands in the stream's tap record.
+R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* data, uint32_t n_bytes, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, UsageRec* cand, uint32_t lane,
+                                         uint32_t f_start, uint32_t f_len, uint32_t f_esc) {
+    const TplMeta& m = *mp;
+    R2Glob rd{data, n_bytes};
+    Val v; v.kind = KD_ABSENT; v.bits = 0;
+    const uint32_t fj = lane < 8u ? m.field_span[lane] : 0xffu;
+    for (uint32_t k = lane; k < sizeof(UsageRaw) / 4; k += 32) reinterpret_cast<uint32_t*>(raw)[k] = reinterpret_cast<const uint32_t*>(tpl_raw)[k];
+    __syncwarp();
+    const uint32_t slow_str = __ballot_sync(R2_FULL, fj != 0xffu && lane >= UF_MODEL && f_esc != 0u);
+    if (fj != 0xffu) {
+        if (lane < UF_MODEL) v = parse_number_span(rd, f_start, f_len);
+        else if (f_esc) {                                                              // escapes: decode like json_machine.cuh does
+            if (lane == UF_MODEL) decode_string_span(rd, f_start, f_len, raw->model, raw->model_len, raw->model_flags);
+            else decode_string_span(rd, f_start, f_len, raw->provider, raw->provider_len, raw->provider_flags);
+        } else if (lane == UF_MODEL) { raw->model_len = 0; raw->model_flags = 0; }
+        else { raw->provider_len = 0; raw->provider_flags = 0; }
+    }
+    __syncwarp();
+    for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
+        const unsigned long long vb = __shfl_sync(R2_FULL, (unsigned long long)v.bits, (int)fi);
+        const uint32_t vk = __shfl_sync(R2_FULL, (uint32_t)v.kind, (int)fi);
+        if (lane == 0 && m.field_span[fi] != 0xffu) {
+            Val x; x.bits = (int64_t)vb; x.kind = (uint8_t)vk;
+            if (fi == UF_PROMPT) raw->prompt = x; else if (fi == UF_COMPLETION) raw->completion = x; else if (fi == UF_TOTAL) raw->total = x;
+            else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
+        }
+    }
+    uint32_t has = 0;                                                                  // bit 0: the record carries "model" as a string, bit 1: "provider"
+    if (lane == 0) {
+        normalise_usage(*raw, m.full_flags, *cand);
+        has = (cand->model_val.kind == KD_STR ? 1u : 0u) | (cand->provider_val.kind == KD_STR ? 2u : 0u);
+    }
+    has = __shfl_sync(R2_FULL, has, 0);
+    // plain strings (no escapes): the span's bytes ARE the decoded text -- copy them into the record, a lane per byte
+    for (uint32_t which = 0; which < 2; ++which) {
+        const uint32_t fl = UF_MODEL + which;
+        const uint32_t span = m.field_span[fl];
+        const uint32_t st = __shfl_sync(R2_FULL, f_start, (int)fl), ln = __shfl_sync(R2_FULL, f_len, (int)fl);
+        if (span == 0xffu || (slow_str & (1u << fl)) || !(has & (1u << which))) continue;
+        const uint32_t n = ln < LGW_STR_CAP ? ln : (uint32_t)LGW_STR_CAP;
+        char* dst = which == 0 ? cand->model : cand->provider;
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = (char)rd.at(st + k);
+        if (lane == 0) {
+            if (which == 0) cand->model_len = (uint8_t)n; else cand->provider_len = (uint8_t)n;
+            if (ln > LGW_STR_CAP) { cand->str_flags |= which == 0 ? 1u : 4u; cand->exotic = 1; }      // truncated: reported, like the full machine's capture
+        }
+    }
+    __syncwarp();
+}
+
 R2_DEV_NOINLINE void commit_settle_pending(StepIO io) { resolve_pending(io); }
 
 R2_GLOBAL void
@@ -1282,12 +1320,15 @@ k_commit2(StepArgs a) {
             if (p.last_usage) {                     // the last usage-bearing event wins (chat_logging.py:134-135)
                 if (lane == 0 && (st.flags & SF_PENDING)) commit_settle_pending(io);   // (a stash left by an older engine version of this stream)
                 if (p.cand_ps == ups + 1u) {
-                    // its fields were read from the matched template spans: install the candidate record
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.s.usage_cand + seg);
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(io.rec);
-                    for (uint32_t k = lane; k < sizeof(UsageRec) / 4; k += 32) dst[k] = src[k];
+                    // the bulk kernel matched it against a usage template and noted where the eight fields sit: read them out
+                    const uint2* uf = a.s.usage_fields + (size_t)seg * 9u;
+                    const uint32_t g = uf[8].x;
+                    const TemplateCache2* tc = a.s.tpl_cache2;
+                    const uint2 fld = lane < 8u ? uf[lane] : make_uint2(0u, 0u);
+                    commit_usage_fields(d, a.n_bytes, &tc->tpl[g].m, &tc->raw[g], reinterpret_cast<UsageRaw*>(stage[warp]), io.rec, lane, fld.x, fld.y & 0x7FFFFFFFu, fld.y >> 31);
+                    __syncwarp();
                     st.flags |= SF_REC_VALID; ++st.n_usage_b;
-                    if (a.s.usage_cand[seg].exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
+                    if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
                     if (lane == 0) atomicAdd(a.s.counters + 2, 1u);
                 } else {
                     // no usage template: stage its text in shared memory and read the values out with the full machine now

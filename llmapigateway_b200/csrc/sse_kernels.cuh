@@ -74,7 +74,7 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size
     if ((r = cudaMalloc((void**)&s.tpl_cache2, sizeof(TemplateCache2))) != cudaSuccess) return r;
     if ((r = cudaMemset(s.tpl_cache2, 0, sizeof(TemplateCache2))) != cudaSuccess) return r;
     (void)sm_count;
-    if ((r = cudaMalloc((void**)&s.usage_cand, max_streams * sizeof(UsageRec))) != cudaSuccess) return r;
+    if ((r = cudaMalloc((void**)&s.usage_fields, max_streams * 9 * sizeof(uint2))) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.tile_seg, (max_bytes / R2_TILE + 4) * 4)) != cudaSuccess) return r;
     if ((r = cudaMemset(s.tile_seg, 0, (max_bytes / R2_TILE + 4) * 4)) != cudaSuccess) return r;
     if ((r = cudaMalloc((void**)&s.counters, 64)) != cudaSuccess) return r;
@@ -83,8 +83,8 @@ static inline cudaError_t scratch_alloc(StepScratch& s, size_t max_streams, size
     return cudaSuccess;
 }
 static inline void scratch_free(StepScratch& s) {
-    cudaFree(s.plan); cudaFree(s.tpl_cache2); cudaFree(s.usage_cand); cudaFree(s.counters); s.counters = nullptr; cudaFree(s.tile_seg); s.tile_seg = nullptr;
-    s.plan = nullptr; s.tpl_cache2 = nullptr; s.usage_cand = nullptr;
+    cudaFree(s.plan); cudaFree(s.tpl_cache2); cudaFree(s.usage_fields); cudaFree(s.counters); s.counters = nullptr; cudaFree(s.tile_seg); s.tile_seg = nullptr;
+    s.plan = nullptr; s.tpl_cache2 = nullptr; s.usage_fields = nullptr;
 }
 
 // Launch one step on `stream`.  ev[0..3] bracket prime / relay / commit (ev[4] = ev[3]: usage extraction is inside relay and commit).

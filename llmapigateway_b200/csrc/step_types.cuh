@@ -27,7 +27,7 @@ struct SegPlan {
     uint32_t kept_end;         // byte offset of the end of the kept chunk = where the handler's text starts
     uint32_t prime_ok;         // set by the warp that walks the kept chunk when the speculation holds
     uint32_t tail_start;       // where the event that is open at the end of the text begins (= new carry); 0xFFFFFFFF: not reached
-    uint32_t cand_ps;          // 1 + start of the usage event whose fields sit in usage_cand[seg] (0: none)
+    uint32_t cand_ps;          // 1 + start of the usage event whose field spans sit in usage_fields[9 * seg ..] (0: none)
 };
 static_assert(sizeof(SegPlan) == 64, "SegPlan");
 
@@ -36,7 +36,8 @@ struct TemplateCache2;     // relay2.cuh
 struct StepScratch {
     SegPlan* plan;             // [max_streams]
     TemplateCache2* tpl_cache2;  // event templates, persistent across steps
-    UsageRec* usage_cand;      // [max_streams] usage record read from a template-following usage event of this step
+    uint2* usage_fields;       // [max_streams][9] a template-following usage event of this step: (start, length | escapes << 31) of its eight
+                               //   usage fields as the match located them, [8].x = the template's slot in the engine-wide cache
     uint32_t* tile_seg;        // [max tiles + 1] segment that holds the first byte of each 4 KiB tile of the launch
     uint32_t* counters;        // diagnostics since engine creation: [0] segments redone sequentially, [1] segments folded from the bulk
                                //   kernel's findings, [2] usage records read from template spans, [3] usage events stashed

@@ -23,7 +23,7 @@ struct HostEngine {
     std::vector<uint8_t> carry_a, carry_b, detail, pending;
     std::vector<SegPlan> plan;
     std::vector<uint8_t> cache;          // TemplateCache2
-    std::vector<UsageRec> cand;
+    std::vector<uint2> fields;
     uint32_t counters[16] = {0};
     std::vector<uint32_t> tile_seg;
     std::vector<RowEvent> rowq; uint32_t rowq_count;
@@ -40,7 +40,7 @@ void* lgwt_bulk_new(uint32_t max_streams, uint32_t carry_cap, uint32_t detail_ca
     e->detail.assign((size_t)max_streams * detail_cap, 0); e->pending.assign((size_t)max_streams * LGW_PENDING_STRIDE, 0);
     e->plan.assign(max_streams, SegPlan{});
     e->cache.assign(sizeof(TemplateCache2), 0);
-    e->cand.assign(max_streams, UsageRec{});
+    e->fields.assign((size_t)max_streams * 9, uint2{0, 0});
     e->rowq.assign(rowq_cap + 1, RowEvent{}); e->rowq_count = 0;
     e->mode = 0;
     return e;
@@ -62,7 +62,7 @@ static StepArgs make_args(HostEngine* e, const uint8_t* data, uint32_t n_bytes, 
     a.data = data; a.n_bytes = n_bytes; a.chunk_off = chunk_off; a.n_chunks = n_chunks; a.tile_base = 0; a.chunk_lo = 0; a.chunk_hi = n_chunks;
     a.seg_chunk = seg_chunk; a.seg_slot = seg_slot; a.n_segs = n_segs; a.out = out; a.seg_out = (SegResult*)seg_out;
     a.rowq = e->rowq.data(); a.rowq_count = &e->rowq_count; a.rowq_cap = e->rowq_cap;
-    a.s.plan = e->plan.data(); a.s.tpl_cache2 = (TemplateCache2*)e->cache.data(); a.s.usage_cand = e->cand.data();
+    a.s.plan = e->plan.data(); a.s.tpl_cache2 = (TemplateCache2*)e->cache.data(); a.s.usage_fields = e->fields.data();
     a.s.counters = e->counters;
     e->tile_seg.assign(n_bytes / R2_TILE + 4, 0); a.s.tile_seg = e->tile_seg.data();
     return a;
