@@ -176,11 +176,15 @@ int lgw_fetch_rows(lgw_engine* e, lgw_row_event* rows_out, uint32_t rows_cap, ui
 int lgw_sync(lgw_engine* e);
 
 /* device time of the kernels of the last step (CUDA events on the launching stream), milliseconds:
- * [0] prime  [1] relay (bulk parse + re-emit + usage fields of template-following events)  [2] commit + usage extract
- * [3] whole step incl. copies (host entry only) */
+ * [0] prime  [1] relay (bulk parse + re-emit)  [2] commit (incl. usage extraction)  [3] whole step incl. copies (host entry only);
+ * see lgw_last_step_kernel_ms for what [0..2] hold when the kernels overlap */
 int lgw_last_step_ms(lgw_engine* e, float ms[4]);
-/* the four kernels one by one: [0] prime  [1] relay  [2] commit  [3] usage extract (stashed usage events) */
+/* the kernels one by one: [0] prime  [1] relay  [2] commit  [3] 0 (usage extraction happens inside relay and commit).
+ * By default the kernels of a step are chained with programmatic dependent launches (each one's prologue overlaps the one
+ * before): then only their total is meaningful and comes back in [1].  lgw_engine_set_kernel_timing(e, 1) puts CUDA events
+ * between them instead (back-to-back launches) for a per-kernel breakdown. */
 int lgw_last_step_kernel_ms(lgw_engine* e, float ms[4]);
+int lgw_engine_set_kernel_timing(lgw_engine* e, int on);
 /* number of kernels launched by this engine since creation */
 int lgw_launch_count(lgw_engine* e, uint64_t* out);
 

@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "_native" / "libllmgw_b200.so"
 EXPORTS = [
     "lgw_abi_version", "lgw_engine_create", "lgw_engine_destroy", "lgw_last_error", "lgw_engine_set_stream",
     "lgw_streams_open", "lgw_streams_state", "lgw_stream_detail", "lgw_streams_close",
-    "lgw_sse_step", "lgw_sse_step_device", "lgw_fetch_rows", "lgw_sync", "lgw_last_step_ms", "lgw_last_step_kernel_ms",
+    "lgw_sse_step", "lgw_sse_step_device", "lgw_fetch_rows", "lgw_sync", "lgw_last_step_ms", "lgw_last_step_kernel_ms", "lgw_engine_set_kernel_timing",
     "lgw_launch_count", "lgw_alloc_pinned", "lgw_free_pinned",
     "lgw_usage_rollup_accum", "lgw_usage_rollup_emit", "lgw_rollup_bucket_of", "lgw_rollup_last_ms",
     "lgw_device_alloc", "lgw_device_free", "lgw_device_upload", "lgw_device_download", "lgw_device_zero",
@@ -54,6 +54,7 @@ def load():
     lib.lgw_sync.argtypes = [C.c_void_p]
     lib.lgw_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
     lib.lgw_last_step_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
+    lib.lgw_engine_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.lgw_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.lgw_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lgw_free_pinned.argtypes = [C.c_void_p, C.c_void_p]

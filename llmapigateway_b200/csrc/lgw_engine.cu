@@ -54,6 +54,8 @@ struct lgw_engine {
     int body_mode = 0;              // 0: data-parallel path + exact machine for the rest, 1: exact machine only (tests)
     cudaEvent_t bev[4]{};
     float bms[3]{0, 0, 0};
+    bool per_kernel_timing = false; // true: events between the step's kernels (lgw_last_step_kernel_ms); false: programmatic dependent launches
+    bool kernel_times_valid = false;
     int mode = 0;                   // 0: fast path + general fix-up, 1: general path only
     int sm_count = 148;
     std::string err;
@@ -145,6 +147,12 @@ extern "C" int lgw_engine_set_stream(lgw_engine* e, void* s) {
     return LGW_OK;
 }
 
+extern "C" int lgw_engine_set_kernel_timing(lgw_engine* e, int on) {   // 1: CUDA events between the kernels of a step (they then run back to back, not overlapped)
+    if (!e) return LGW_ERR_ARG;
+    e->per_kernel_timing = on != 0;
+    return LGW_OK;
+}
+
 extern "C" int lgw_engine_set_mode(lgw_engine* e, int mode) {     // 0 fast+fix-up, 1 general only (tests)
     if (!e) return LGW_ERR_ARG;
     e->mode = mode; e->body_mode = mode;
@@ -217,7 +225,9 @@ static int step_device(lgw_engine* e, const uint8_t* d_bytes, uint64_t n_bytes, 
     a.rowq = e->d_rowq; a.rowq_count = e->d_rowq_count; a.rowq_cap = e->lim.rowq_cap; a.s = e->scratch;
     if (reset_rows) CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
     int launched = 0;
-    cudaError_t r = launch_step(a, e->mode, e->sm_count, e->stream, e->ev, &launched);
+    const bool pk = e->per_kernel_timing || e->mode == 1;
+    cudaError_t r = launch_step(a, e->mode, e->sm_count, e->stream, e->ev, &launched, pk);
+    e->kernel_times_valid = pk;
     e->launches += (uint64_t)launched;
     if (r != cudaSuccess) { e->err = std::string("step launch: ") + cudaGetErrorString(r); return LGW_ERR_CUDA; }
     e->timed = true;
@@ -313,7 +323,12 @@ static int read_step_ms(lgw_engine* e) {
     if (e->timed) {
         CK(e, cudaSetDevice(e->device));
         CK(e, cudaEventSynchronize(e->ev[4]));
-        for (int i = 0; i < 4; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->ms[i] = t; }
+        if (e->kernel_times_valid) {
+            for (int i = 0; i < 4; ++i) { float t = 0; if (cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->ms[i] = t; }
+        } else {                            // kernels overlap (programmatic dependent launch): only their total is meaningful
+            float t = 0; e->ms[0] = e->ms[2] = e->ms[3] = 0;
+            if (cudaEventElapsedTime(&t, e->ev[0], e->ev[4]) == cudaSuccess) e->ms[1] = t;
+        }
     }
     return LGW_OK;
 }

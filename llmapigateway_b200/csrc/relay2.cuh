@@ -139,6 +139,10 @@ R2_DEV void tma_store_commit_empty() { asm volatile("cp.async.bulk.commit_group;
 R2_DEV void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 R2_DEV void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 R2_DEV uint8_t* smem_base() { extern __shared__ __align__(128) uint8_t r2_smem[]; return r2_smem; }
+// programmatic dependent launch: the next kernel of the step may start its prologue while this one still runs; it waits here
+// before it touches anything this one writes
+R2_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+R2_DEV void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #else
 typedef uint8_t* SPtr;
 R2_DEV SPtr sptr(const void* p) { return (uint8_t*)p; }
@@ -157,6 +161,8 @@ R2_DEV void tma_store_commit_empty() {}
 R2_DEV void tma_wait_read1() {}
 R2_DEV void tma_wait_all() {}
 R2_DEV uint8_t* smem_base() { return simt::g_dyn_smem; }
+R2_DEV void griddep_wait() {}
+R2_DEV void griddep_launch() {}
 #endif
 R2_DEV uint32_t r2_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 R2_DEV uint32_t r2_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
@@ -1083,12 +1089,12 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     TemplateCache2* tc = a.s.tpl_cache2;
     UsageRaw* block_raw = sh->raw_tpl;
 
-    // ---- block prologue: recogniser tables, templates from the engine-wide cache, default slot, barriers ----
+    // ---- block prologue: recogniser tables, barriers, the first tiles (all independent of k_prime2, which may still run) ----
+    griddep_launch();
     for (uint32_t k = tid; k < 64 + LGW_LEAN_ROWS * 8; k += R2_THREADS) {
         if (k < 64) reinterpret_cast<uint32_t*>(sh->cls)[k] = reinterpret_cast<const uint32_t*>(lean_tables().cls)[k];
         else reinterpret_cast<uint32_t*>(sh->trans)[k - 64] = reinterpret_cast<const uint32_t*>(lean_tables().trans)[k - 64];
     }
-    if (tid < R2_SLOTS) { sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u; sh->slot_gidx[tid] = tid; }
     if (tid == 0) { sh->fast_ready = 0; sh->learn_lock = 0; sh->args = a; }
     if (lane == 0) for (uint32_t b = 0; b < R2_NBUF; ++b) mbar_init(sptr(&sh->mbar[warp * R2_NBUF + b]), 1);
     mbar_fence_init();
@@ -1103,6 +1109,10 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     c.base = base0 + t_first * R2_TILE;
     c.n_tiles = t_first >= n_tiles_total ? 0u : r2_min(tiles_per_warp, n_tiles_total - t_first);
     pipe_start(c);
+    // ---- from here on: what k_prime2 wrote (plans, tile table, template cache upkeep) ----
+    griddep_wait();
+    if (tid < R2_SLOTS) { sh->slot_state[tid] = (*(volatile uint32_t*)&tc->state[tid] == 2u) ? 2u : 0u; sh->slot_gidx[tid] = tid; }
+    __syncthreads();
     for (uint32_t s = 0; s < R2_SLOTS; ++s) {
         if (sh->slot_state[s] != 2u) continue;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tc->tpl[s]);
@@ -1155,6 +1165,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
 // thread i: the plan of segment i the bulk kernel works to.  Fresh streams are SPECULATED to commit on their first
 // non-empty chunk; the bulk kernel verifies, k_commit2 applies or falls back.  Thread 0 also looks after the template cache.
 R2_GLOBAL void k_prime2(StepArgs a) {
+    griddep_launch();
     const uint32_t i = R2_BID * R2_NTHR + R2_TID;
     if (i == 0) {
         TemplateCache2* tc = a.s.tpl_cache2;
@@ -1286,6 +1297,7 @@ k_commit2(StepArgs a) {
     if (seg >= a.n_segs) return;
     const uint32_t c1 = __ldg(a.seg_chunk + seg + 1);
     const uint32_t slot = __ldg(a.seg_slot + seg);
+    griddep_wait();                                       // (the bulk kernel's findings from here on)
     const SegPlan p = a.s.plan[seg];
     StreamHdr st = a.t.state[slot].h;                     // (every lane holds a copy; lane 0's is the one written back)
     const StepIO io = make_io(a, slot, &st);
@@ -1295,7 +1307,13 @@ k_commit2(StepArgs a) {
         const uint8_t* __restrict__ d = a.data;
         // an empty chunk is never yielded (request_handler.py:60-63): the concatenation argument does not cover it
         bool empty = false;
-        for (uint32_t c = p.resume_chunk + lane; c < c1; c += 32) if (__ldg(a.chunk_off + c + 1) == __ldg(a.chunk_off + c)) empty = true;
+        for (uint32_t c = p.resume_chunk + lane; c < c1; c += 32 * 8) {          // eight independent trips in flight (a plain loop is one DRAM round trip per trip)
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) { const uint32_t cc = c + 32 * j; lo[j] = cc < c1 ? __ldg(a.chunk_off + cc) : 0u; hi[j] = cc < c1 ? __ldg(a.chunk_off + cc + 1) : 1u; }
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) if (lo[j] == hi[j]) empty = true;
+        }
         bool sequential = p.irregular || p.n_usage_b > 1 || __any_sync(R2_FULL, empty);   // several usage candidates: let the exact path count them
         if (st.phase == PH_PRIMING && !(speculated && p.prime_ok)) sequential = true;
         const uint32_t ups = (uint32_t)(p.last_usage >> 32) - 1u, ulen = (uint32_t)p.last_usage;   // the winning usage event
@@ -1353,22 +1371,38 @@ k_commit2(StepArgs a) {
 }
 
 #if !R2_HOST_EMU
-static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
+// The three kernels of a step.  per_kernel = true: CUDA events between them (ev[1..3]) for the per-kernel times; false: the
+// bulk kernel and the commit kernel are launched with programmatic stream serialisation, so that each one's prologue (and
+// its launch latency) overlaps the kernel before it -- they wait (griddepcontrol.wait) before reading what that kernel wrote.
+static inline cudaError_t launch_step_fast(const StepArgs& a, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched, bool per_kernel) {
     cudaError_t r;
     const uint32_t base0 = a.tile_base & ~15u;
     const uint32_t n_tiles = a.n_bytes > base0 ? (a.n_bytes - base0 + R2_TILE - 1) / R2_TILE : 0u;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     if (a.n_segs) { k_prime2<<<(a.n_segs + 127) / 128, 128, 0, stream>>>(a); ++*launched; }
-    if ((r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
+    if (per_kernel && (r = cudaEventRecord(ev[1], stream)) != cudaSuccess) return r;
     if (n_tiles) {
         const uint32_t max_warps = (uint32_t)sm_count * R2_WARPS;
         const uint32_t tpw = (n_tiles + max_warps - 1) / max_warps;
         const uint32_t warps = (n_tiles + tpw - 1) / tpw;
         const uint32_t blocks = (warps + R2_WARPS - 1) / R2_WARPS;
-        k_relay2<<<blocks, R2_THREADS, R2_SMEM_BYTES, stream>>>(a, n_tiles, tpw, base0); ++*launched;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = R2_SMEM_BYTES; cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = per_kernel ? 0 : 1;
+        if ((r = cudaLaunchKernelEx(&cfg, k_relay2, a, n_tiles, tpw, base0)) != cudaSuccess) return r;
+        ++*launched;
     }
-    if ((r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
-    if (a.n_segs) { k_commit2<<<(a.n_segs + R2_CWARPS - 1) / R2_CWARPS, R2_CWARPS * 32, 0, stream>>>(a); ++*launched; }
-    if ((r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
+    if (per_kernel && (r = cudaEventRecord(ev[2], stream)) != cudaSuccess) return r;
+    if (a.n_segs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((a.n_segs + R2_CWARPS - 1) / R2_CWARPS); cfg.blockDim = dim3(R2_CWARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = per_kernel ? 0 : 1;
+        if ((r = cudaLaunchKernelEx(&cfg, k_commit2, a)) != cudaSuccess) return r;
+        ++*launched;
+    }
+    if (per_kernel && (r = cudaEventRecord(ev[3], stream)) != cudaSuccess) return r;
     if ((r = cudaEventRecord(ev[4], stream)) != cudaSuccess) return r;
     return cudaGetLastError();
 }

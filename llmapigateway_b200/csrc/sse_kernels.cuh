@@ -88,7 +88,7 @@ static inline void scratch_free(StepScratch& s) {
 }
 
 // Launch one step on `stream`.  ev[0..3] bracket prime / relay / commit (ev[4] = ev[3]: usage extraction is inside relay and commit).
-static inline cudaError_t launch_step(const StepArgs& a, int mode, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched) {
+static inline cudaError_t launch_step(const StepArgs& a, int mode, int sm_count, cudaStream_t stream, cudaEvent_t* ev, int* launched, bool per_kernel) {
     *launched = 0;
     cudaError_t r;
     if ((r = cudaEventRecord(ev[0], stream)) != cudaSuccess) return r;
@@ -101,7 +101,7 @@ static inline cudaError_t launch_step(const StepArgs& a, int mode, int sm_count,
         if ((r = cudaEventRecord(ev[4], stream)) != cudaSuccess) return r;
         return cudaGetLastError();
     }
-    return launch_step_fast(a, sm_count, stream, ev, launched);
+    return launch_step_fast(a, sm_count, stream, ev, launched, per_kernel);
 }
 
 }  // namespace lgw

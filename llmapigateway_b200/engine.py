@@ -140,7 +140,12 @@ class Engine:
         ms, k = (C.c_float * 4)(), (C.c_float * 4)()
         self._ck(self._lib.lgw_last_step_ms(self._h, C.byref(ms)), "last_step_ms")
         self._ck(self._lib.lgw_last_step_kernel_ms(self._h, C.byref(k)), "last_step_kernel_ms")
-        return dict(prime=k[0], relay=k[1], commit=k[2], usage_extract=k[3], host_step=ms[3])
+        return dict(prime=k[0], relay=k[1], commit=k[2], host_step=ms[3])
+
+    def set_kernel_timing(self, on: bool):
+        """True: CUDA events between the kernels of a step (per-kernel times, back-to-back launches); False (default): the kernels
+        are chained with programmatic dependent launches and only their total is timed."""
+        self._ck(self._lib.lgw_engine_set_kernel_timing(self._h, 1 if on else 0), "set_kernel_timing")
 
     def debug_counters(self):
         out = (C.c_uint32 * 4)()
