@@ -968,8 +968,8 @@ R2_DEV_NOINLINE OddOut odd_event(const StepArgs* ap, R2Shared* sh, R2Io io, uint
         if ((m.flags & TK_USAGE) && (m.flags & PF_VALID_B) && m.usage_ok && so.e - ps <= LGW_PENDING_CAP && sh->slot_gidx[slot] != R2_NONE) {
             // where its eight usage fields sit: k_commit2 reads the values out (one warp per segment there, nothing serial here)
             uint2* uf = ap->s.usage_fields + (size_t)seg * 9u;
-            if (lane < 8u) uf[lane] = make_uint2(so.f_start, so.f_len | (so.f_esc << 31));
-            if (lane == 0) { uf[8] = make_uint2(sh->slot_gidx[slot], 0u); ap->s.plan[seg].cand_ps = ps + 1u; }
+            if (lane < 8u) uf[lane] = m.field_span[lane] != 0xffu ? make_uint2(so.f_start, so.f_len | (so.f_esc << 31)) : make_uint2(0u, 0xFFFFFFFFu);
+            if (lane == 0) { uf[8] = make_uint2(sh->slot_gidx[slot], m.full_flags); ap->s.plan[seg].cand_ps = ps + 1u; }
         }
         o.e = so.e; o.ev_a = ac.ev_a; o.ev_b = ac.ev_b; o.a_usage = ac.a_usage; o.primed = ac.primed;
         return o;
@@ -1231,16 +1231,22 @@ R2_DEV_NOINLINE void commit_usage_event(StepIO io, const uint8_t* text, uint32_t
 // usage fields of a template-following usage event straight from the value spans the bulk kernel's match located (usage_ok
 // templates): numbers through decimal.cuh, strings copied (decoded like the full machine does when they hold escapes),
 // get_token_usage's arithmetic (normalise_usage) on the assembled record, which lands in the stream's tap record.
-R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* data, uint32_t n_bytes, const TplMeta* mp, const UsageRaw* tpl_raw, UsageRaw* raw, UsageRec* cand, uint32_t lane,
-                                         uint32_t f_start, uint32_t f_len, uint32_t f_esc) {
-    const TplMeta& m = *mp;
-    R2Glob rd{data, n_bytes};
+// `text` holds the event's bytes (staged in shared memory), text[0] = the byte at position `ups` of the step's buffer.
+struct TextReader {
+    const uint8_t* text; uint32_t base, n;
+    R2_MEM uint32_t at(uint32_t p) const { return p - base < n ? (uint32_t)text[p - base] : 0u; }
+};
+R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* text, uint32_t ups, uint32_t ulen, uint32_t full_flags, const UsageRaw* tpl_raw, UsageRaw* raw, UsageRec* cand, uint32_t lane,
+                                         uint32_t f_start, uint32_t f_word) {
+    TextReader rd{text, ups, ulen};
+    const bool has_span = lane < 8u && f_word != 0xFFFFFFFFu;
+    const uint32_t f_len = f_word & 0x7FFFFFFFu, f_esc = has_span ? f_word >> 31 : 0u;
+    const uint32_t span_mask = __ballot_sync(R2_FULL, has_span);
     Val v; v.kind = KD_ABSENT; v.bits = 0;
-    const uint32_t fj = lane < 8u ? m.field_span[lane] : 0xffu;
     for (uint32_t k = lane; k < sizeof(UsageRaw) / 4; k += 32) reinterpret_cast<uint32_t*>(raw)[k] = reinterpret_cast<const uint32_t*>(tpl_raw)[k];
     __syncwarp();
-    const uint32_t slow_str = __ballot_sync(R2_FULL, fj != 0xffu && lane >= UF_MODEL && f_esc != 0u);
-    if (fj != 0xffu) {
+    const uint32_t slow_str = __ballot_sync(R2_FULL, has_span && lane >= UF_MODEL && f_esc != 0u);
+    if (has_span) {
         if (lane < UF_MODEL) v = parse_number_span(rd, f_start, f_len);
         else if (f_esc) {                                                              // escapes: decode like json_machine.cuh does
             if (lane == UF_MODEL) decode_string_span(rd, f_start, f_len, raw->model, raw->model_len, raw->model_flags);
@@ -1252,7 +1258,7 @@ R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* data, uint32_t n_bytes, 
     for (uint32_t fi = 0; fi < UF_MODEL; ++fi) {
         const unsigned long long vb = __shfl_sync(R2_FULL, (unsigned long long)v.bits, (int)fi);
         const uint32_t vk = __shfl_sync(R2_FULL, (uint32_t)v.kind, (int)fi);
-        if (lane == 0 && m.field_span[fi] != 0xffu) {
+        if (lane == 0 && (span_mask & (1u << fi))) {
             Val x; x.bits = (int64_t)vb; x.kind = (uint8_t)vk;
             if (fi == UF_PROMPT) raw->prompt = x; else if (fi == UF_COMPLETION) raw->completion = x; else if (fi == UF_TOTAL) raw->total = x;
             else if (fi == UF_COST) raw->cost = x; else if (fi == UF_REASONING) raw->reasoning = x; else raw->cached = x;
@@ -1260,16 +1266,15 @@ R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* data, uint32_t n_bytes, 
     }
     uint32_t has = 0;                                                                  // bit 0: the record carries "model" as a string, bit 1: "provider"
     if (lane == 0) {
-        normalise_usage(*raw, m.full_flags, *cand);
+        normalise_usage(*raw, full_flags, *cand);
         has = (cand->model_val.kind == KD_STR ? 1u : 0u) | (cand->provider_val.kind == KD_STR ? 2u : 0u);
     }
     has = __shfl_sync(R2_FULL, has, 0);
     // plain strings (no escapes): the span's bytes ARE the decoded text -- copy them into the record, a lane per byte
     for (uint32_t which = 0; which < 2; ++which) {
         const uint32_t fl = UF_MODEL + which;
-        const uint32_t span = m.field_span[fl];
         const uint32_t st = __shfl_sync(R2_FULL, f_start, (int)fl), ln = __shfl_sync(R2_FULL, f_len, (int)fl);
-        if (span == 0xffu || (slow_str & (1u << fl)) || !(has & (1u << which))) continue;
+        if (!(span_mask & (1u << fl)) || (slow_str & (1u << fl)) || !(has & (1u << which))) continue;
         const uint32_t n = ln < LGW_STR_CAP ? ln : (uint32_t)LGW_STR_CAP;
         char* dst = which == 0 ? cand->model : cand->provider;
         for (uint32_t k = lane; k < n; k += 32) dst[k] = (char)rd.at(st + k);
@@ -1289,9 +1294,11 @@ __launch_bounds__(R2_CWARPS * 32, 6)      // (the full machine behind commit_usa
 #endif
 k_commit2(StepArgs a) {
 #if !R2_HOST_EMU
-    __shared__ __align__(16) uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
+    __shared__ __align__(16) uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];           // the winning usage event's text
+    __shared__ __align__(16) UsageRaw stage_raw[R2_CWARPS];                           // the record being assembled from it
 #else
     static uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
+    static UsageRaw stage_raw[R2_CWARPS];
 #endif
     const uint32_t seg = (R2_BID * R2_NTHR + R2_TID) >> 5, lane = R2_TID & 31u, warp = (R2_TID >> 5) % R2_CWARPS;
     if (seg >= a.n_segs) return;
@@ -1305,6 +1312,14 @@ k_commit2(StepArgs a) {
     const bool speculated = p.kept_chunk != 0xFFFFFFFFu;
     if ((st.phase == PH_COMMITTED || st.phase == PH_PRIMING) && p.resume_chunk < c1) {
         const uint8_t* __restrict__ d = a.data;
+        // the winning usage event: its text (and, when the bulk kernel matched it against a usage template, where its fields sit)
+        // is requested now, together with the chunk offsets below -- one round trip for all of it
+        const uint32_t ups = (uint32_t)(p.last_usage >> 32) - 1u, ulen = (uint32_t)p.last_usage;
+        const bool staged = p.last_usage && ulen <= LGW_PENDING_CAP && (uint64_t)ups + ulen <= a.n_bytes;
+        const bool has_cand = staged && p.cand_ps == ups + 1u;
+        uint2 fld = make_uint2(0u, 0xFFFFFFFFu), gf = make_uint2(0u, 0u);
+        if (has_cand) { const uint2* uf = a.s.usage_fields + (size_t)seg * 9u; if (lane < 8u) fld = uf[lane]; gf = uf[8]; }
+        if (staged) for (uint32_t k = lane; k < ulen; k += 32) stage[warp][k] = __ldg(d + ups + k);
         // an empty chunk is never yielded (request_handler.py:60-63): the concatenation argument does not cover it
         bool empty = false;
         for (uint32_t c = p.resume_chunk + lane; c < c1; c += 32 * 8) {          // eight independent trips in flight (a plain loop is one DRAM round trip per trip)
@@ -1316,8 +1331,7 @@ k_commit2(StepArgs a) {
         }
         bool sequential = p.irregular || p.n_usage_b > 1 || __any_sync(R2_FULL, empty);   // several usage candidates: let the exact path count them
         if (st.phase == PH_PRIMING && !(speculated && p.prime_ok)) sequential = true;
-        const uint32_t ups = (uint32_t)(p.last_usage >> 32) - 1u, ulen = (uint32_t)p.last_usage;   // the winning usage event
-        if (!sequential && p.last_usage && ulen > LGW_PENDING_CAP) sequential = true;
+        if (!sequential && p.last_usage && !staged) sequential = true;
         if (!sequential && p.tail_start == 0xFFFFFFFFu) sequential = true;                        // (nobody reached the end of the text)
         if (lane == 0) atomicAdd(a.s.counters + (sequential ? 0 : 1), 1u);
         if (sequential) {
@@ -1337,21 +1351,16 @@ k_commit2(StepArgs a) {
             if (p.a_usage) st.flags |= SF_A_USAGE_BOUND;
             if (p.last_usage) {                     // the last usage-bearing event wins (chat_logging.py:134-135)
                 if (lane == 0 && (st.flags & SF_PENDING)) commit_settle_pending(io);   // (a stash left by an older engine version of this stream)
-                if (p.cand_ps == ups + 1u) {
+                __syncwarp();
+                if (has_cand) {
                     // the bulk kernel matched it against a usage template and noted where the eight fields sit: read them out
-                    const uint2* uf = a.s.usage_fields + (size_t)seg * 9u;
-                    const uint32_t g = uf[8].x;
-                    const TemplateCache2* tc = a.s.tpl_cache2;
-                    const uint2 fld = lane < 8u ? uf[lane] : make_uint2(0u, 0u);
-                    commit_usage_fields(d, a.n_bytes, &tc->tpl[g].m, &tc->raw[g], reinterpret_cast<UsageRaw*>(stage[warp]), io.rec, lane, fld.x, fld.y & 0x7FFFFFFFu, fld.y >> 31);
+                    commit_usage_fields(stage[warp], ups, ulen, gf.y, &a.s.tpl_cache2->raw[gf.x], &stage_raw[warp], io.rec, lane, fld.x, fld.y);
                     __syncwarp();
                     st.flags |= SF_REC_VALID; ++st.n_usage_b;
                     if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
                     if (lane == 0) atomicAdd(a.s.counters + 2, 1u);
                 } else {
-                    // no usage template: stage its text in shared memory and read the values out with the full machine now
-                    for (uint32_t k = lane; k < ulen; k += 32) stage[warp][k] = __ldg(d + ups + k);
-                    __syncwarp();
+                    // no usage template: read the values out of the staged text with the full machine now
                     if (lane == 0) { commit_usage_event(io, stage[warp], ulen); atomicAdd(a.s.counters + 3, 1u); }
                 }
             }
