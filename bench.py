@@ -52,8 +52,8 @@ def _traffic():
         return None
 
 
-# ---- CPU reference arm ------------------------------------------------------------------------
-def _cpu_worker(args):
+# ---- CPU reference arm: the reference's OWN code (oracle/_ref via oracle/ref_arm.py), else the oracle port ------------------
+def _port_worker(args):
     seed, n_streams, n_events = args
     from llmapigateway_b200.synth import sse_batch
     from oracle.sse_oracle import run_stream
@@ -66,17 +66,39 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference(n_streams_per_proc: int, n_events: int, procs: int, seed: int = 3):
-    """Oracle port of the reference path (relay loop A + tap loop B, stdlib json standing in for
-    json5 = the GENEROUS variant B2 of BASELINE.md) on `procs` processes."""
+def cpu_arm(variant: str, procs: int, n_streams: int, n_events: int, seed: int = 3):
+    """`n_streams` C3 streams split over `procs` processes -> (events/s, kind).  kind "reference": the unmodified reference modules
+    from oracle/_ref (make_llm_request + ChunkProcessorThread through httpx.MockTransport); kind "port": the
+    oracle restatement (only when oracle/_ref did not travel to this box)."""
+    from oracle import ref_arm
+    if ref_arm.ref_root() is not None:
+        ev, _, _ = ref_arm.run_config3(variant, procs, n_streams, n_events, seed)
+        return ev, "reference"
     import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        t0 = time.perf_counter()
-        times = pool.map(_cpu_worker, [(seed + i, n_streams_per_proc, n_events) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    events = procs * n_streams_per_proc * n_events
-    return events / max(times), max(times), wall
+    per = max(1, n_streams // procs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        times = pool.map(_port_worker, [(seed + i, per, n_events) for i in range(procs)])
+    return procs * per * n_events / max(times), "port"
+
+
+def cpu_baseline_block(n_events: int, budget_s: float = 25.0):
+    """B1 (faithful: pure-Python parser standing in for json5) and B2 (generous: C json) on one core (how the
+    reference runs) and on all the cores this process may use.  Samples are sized from a short probe to fit `budget_s`."""
+    from oracle import ref_arm
+    cores = ref_arm.effective_cores()
+    probe, kind = cpu_arm("B2", 1, 8, n_events)
+    per_core = max(8, min(256, int(probe * budget_s / 4 / n_events / 4)))       # streams per core for ~budget/4 s per variant
+    out = {"cores": cores, "kind": kind, "unit": UNIT}
+    for name, variant, procs in (("B2_N", "B2", cores), ("B2_1", "B2", 1), ("B1_N", "B1", cores), ("B1_1", "B1", 1)):
+        n = per_core * procs if variant == "B2" else max(procs, per_core * procs // 2)
+        ev, _ = cpu_arm(variant, procs, n, n_events)
+        out[name] = {"value": ev, "streams": n, "procs": procs}
+    out["value"] = out["B2_N"]["value"]
+    out["sample"] = (f"C3 streams of {n_events} x {EVENT_BYTES} B events (+ usage event, [DONE]) through the reference's own make_llm_request + ChunkProcessorThread "
+                     f"(httpx.MockTransport, no sockets): {out['B2_N']['streams']} streams over {cores} processes for the headline value (B2 = json5.loads -> C json.loads, generous); "
+                     f"B1 = pure-Python parser standing in for json5; *_1 = one process (how the reference is deployed)") if kind == "reference" else \
+                    f"oracle port (oracle/_ref absent), {cores} processes"
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -122,26 +144,36 @@ class ClockSampler(threading.Thread):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, same config/metric/unit.
+    A step = the whole C3 configuration (4096 x 512 events) when a probe says K + W steps fit in a few minutes, else a bounded
+    sample of it (stated in `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    per_proc = 48
+    from oracle import ref_arm
+    cores = ref_arm.effective_cores()
+    probe, kind = cpu_arm("B2", cores, 8 * cores, N_EVENTS)
+    steps_total = args.warmup + args.steps
+    full_s = N_STREAMS * N_EVENTS / probe
+    n_streams = N_STREAMS if full_s * steps_total <= 240 else max(cores, int(N_STREAMS * 240 / (full_s * steps_total)) // cores * cores)
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, tmax, _ = cpu_reference(per_proc, N_EVENTS, procs, seed=3 + 100 * i)
+    for i in range(steps_total):
+        t0 = time.perf_counter()
+        v, _ = cpu_arm("B2", cores, n_streams, N_EVENTS, seed=3 + 100 * i)
         if i >= args.warmup:
-            vals.append((v, tmax))
+            vals.append((v, time.perf_counter() - t0))
     value = float(np.mean([v for v, _ in vals]))
-    ms = float(np.mean([t for _, t in vals])) * 1e3
-    sample = f"{procs} procs x {per_proc} streams x {N_EVENTS} events of {EVENT_BYTES} B per step (oracle port, stdlib json for json5, relay+tap loops)"
+    ms = n_streams * N_EVENTS / value * 1e3
+    sample = (f"{n_streams} of {N_STREAMS} streams x {N_EVENTS} events of {EVENT_BYTES} B per step over {cores} processes; "
+              + ("the UNMODIFIED reference (oracle/_ref): make_llm_request relay + ChunkProcessorThread tap through httpx.MockTransport, json5.loads -> C json.loads (B2, generous)"
+                 if kind == "reference" else "oracle port (oracle/_ref absent)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C3: SSE delta parse/normalise/re-emit, 64 B events, 1 event per chunk (bounded sample of 4096x512)",
-                       "streams": procs * per_proc, "events_per_stream": N_EVENTS},
+            "config": {"workload": "C3: 4096 concurrent SSE streams x 512 data: deltas (64 B each), parse/normalise/re-emit",
+                       "streams_per_step": n_streams, "events_per_stream": N_EVENTS, "same_config": n_streams == N_STREAMS},
             "json_gbs": value * EVENT_BYTES / 1e9,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
@@ -353,12 +385,7 @@ def main():
         "wall_s_timed_loop": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:
-        procs = os.cpu_count() or 1
-        v, tmax, _ = cpu_reference(64, E, procs)
-        v1, t1, _ = cpu_reference(96, E, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-                                "sample": f"{procs} procs x 64 streams x {E} events (oracle port of request_handler.py relay + chat_logging.py tap; stdlib json stands in for json5 = generous)",
-                                "single_core_value": v1}
+        line["cpu_baseline"] = cpu_baseline_block(E)
     if world == 1 and not args.no_cpu_baseline:
         # the other built rows of SURVEY 8 on their own configurations (C2 bodies, C5 rollup at 2M records), same box, same run
         try:

@@ -136,6 +136,9 @@ int lgw_streams_state(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stre
 /* error detail of a failed attempt: the text the reference stores at request_handler.py:51,87
  * (the whole first event, "data: " included) */
 int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uint32_t cap, uint32_t* len);
+/* the same for n slots in one round trip (config 4: the failed attempts of a round): slot i's text is
+ * buf[i*stride .. i*stride + lens[i]), cut at `stride` bytes */
+int lgw_streams_details(lgw_engine* e, const uint32_t* slots, uint32_t n, uint8_t* buf, uint32_t stride, uint32_t* lens);
 /* end of upstream: final state (the last DB row of chat_logging.py:150 is `rec` when
  * LGW_SF_EMITTED_ANY), slot returns to FREE */
 int lgw_streams_close(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stream_state* final_out);
@@ -289,6 +292,22 @@ int lgw_bodies_rewrite_device(lgw_engine* e, const uint8_t* d_bodies, const uint
                               uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off, lgw_body_result* d_results);
 /* device time of the last rewrite's kernels (rewrite, offsets, pack), milliseconds */
 int lgw_bodies_last_ms(lgw_engine* e, float ms[3]);
+
+/* ---- response tap of NON-streaming responses: SURVEY 8 row a8, chat_logging.py:98-103,:113-150 -------------------------------
+ * The tap thread concatenates the chunks of a non-event-stream response and treats the whole text as ONE part (:105-106): it must
+ * start with `{` (or `data: {`), is parsed once (:123), walks `choices` (:124-133), takes get_token_usage of the document when it
+ * has a "usage" key (:134-135), writes an extra row when it has an "error" key (:137-139) and the final row (:150).  One result per
+ * document: the record of that final row (the defaults when nothing was taken) and what else happened. */
+typedef struct lgw_doc_usage {
+    uint32_t flags;              /* TopKey | PartFlag bits of the parse (0: the text was not taken as JSON) */
+    uint8_t rec_valid;           /* 1: rec = get_token_usage(document); 0: rec = the defaults of chat_logging.py:77-84 */
+    uint8_t error_row;           /* 1: the document has a top-level "error": the same record is written once more before the final row */
+    uint8_t exotic;              /* 1: a shape the device does not model (reported, never guessed) */
+    uint8_t _pad;
+    lgw_usage_rec rec;
+} lgw_doc_usage;
+/* host pointers; document i is docs[doc_off[i] .. doc_off[i+1]) */
+int lgw_documents_usage(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off /* n+1 */, uint32_t n, lgw_doc_usage* out);
 
 /* ---- device memory helpers for callers without their own CUDA allocator ----------------------------- */
 int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out);

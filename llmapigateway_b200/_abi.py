@@ -46,6 +46,10 @@ class SegResult(C.Structure):
                 ("flags", C.c_uint16), ("detail_len", C.c_uint32)]
 
 
+class DocUsage(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("rec_valid", C.c_uint8), ("error_row", C.c_uint8), ("exotic", C.c_uint8), ("_pad", C.c_uint8), ("rec", UsageRec)]
+
+
 class Limits(C.Structure):
     _fields_ = [("max_streams", C.c_uint32), ("carry_cap", C.c_uint32), ("detail_cap", C.c_uint32),
                 ("rowq_cap", C.c_uint32), ("max_step_chunks", C.c_uint32), ("max_step_bytes", C.c_uint64)]

@@ -1,0 +1,408 @@
+"""The `/v1/chat/completions` endpoint body over the engine: the fallback-chain walker.
+
+  chat_completions(request, *, batcher, ...)   <- llm_gateway_core/api/v1/chat.py:20-198  (same request object, same
+                                                  responses, same HTTPException status/detail texts)
+  ModelRotation                                <- llm_gateway_core/db/model_rotation_db.py:56-110 (same table, same RMW)
+  ChainBatch                                   <- the same walk for a whole batch of requests in lock-step rounds
+                                                  (what bench.py --config c4 and the full-size parity test drive)
+
+Control stays in Python exactly as SURVEY 8(e) prescribes ("retries stay on the same GPU/stream slot; control stays in
+Python"); the byte work of every attempt is the engine's: the request scan (chat.py:31-45 -> lgw_bodies_scan), the per-attempt
+body (chat.py:112-119,135-139,160-165 -> lgw_bodies_rewrite with the attempt's compiled plan), the first-event verdict, the
+relay and the usage tap (request_handler.py:34-142 -> lgw_sse_step).  There is no CPU JSON parser or serialiser on this path.
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import sqlite3
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from . import rewrite as rw
+from .gateway import StreamBatcher, make_llm_request, shard_of
+
+
+class ModelRotation:
+    """model_rotation_db.py: one row per (api_key, gateway_model); get_next_model_index is a serial read-modify-write that
+    does not shard ("replicas only / stays on host")."""
+
+    def __init__(self, db_path=":memory:"):
+        self.conn = sqlite3.connect(db_path, check_same_thread=False)
+        self.conn.execute("CREATE TABLE IF NOT EXISTS model_rotation (api_key TEXT, gateway_model TEXT, last_model_index INTEGER,"
+                          " PRIMARY KEY (api_key, gateway_model))")
+        self.conn.commit()
+
+    def get_next_model_index(self, api_key: str, gateway_model: str, total_models: int) -> int:
+        if total_models <= 0:                                              # :68-70
+            return 0
+        try:
+            cur = self.conn.execute("SELECT last_model_index FROM model_rotation WHERE api_key = ? AND gateway_model = ?", (api_key, gateway_model))
+            row = cur.fetchone()
+            if row is None:                                                # :84-90 first use starts at 0
+                nxt = 0
+                self.conn.execute("INSERT INTO model_rotation (api_key, gateway_model, last_model_index) VALUES (?, ?, ?)", (api_key, gateway_model, nxt))
+            else:                                                          # :91-98
+                nxt = (row[0] + 1) % total_models
+                self.conn.execute("UPDATE model_rotation SET last_model_index = ? WHERE api_key = ? AND gateway_model = ?", (nxt, api_key, gateway_model))
+            self.conn.commit()
+            return nxt
+        except Exception:                                                  # :102-107 degrade to the first model
+            try:
+                self.conn.rollback()
+            except Exception:
+                pass
+            return 0
+
+
+def _http_exception(status: int, detail: str):
+    from fastapi import HTTPException
+    return HTTPException(status_code=status, detail=detail)
+
+
+def attempt_headers(provider_cfg, rule: dict) -> dict:
+    """chat.py:94-123: the headers of every attempt of one rule."""
+    key_name = provider_cfg.apikey
+    key = os.getenv(key_name) if key_name else None                        # :96
+    if not key and key_name:                                               # :99-101 the config may hold the key itself
+        key = key_name
+    headers = {"Content-Type": "application/json", "HTTP-Referer": "https://github.com/fabiojbg/LLMApiGateway", "X-Title": "LLMGateway",
+               **({"Authorization": f"Bearer {key}"} if key else {})}
+    for k, v in (rule.get("custom_headers") or {}).items():                # :120-123
+        headers[k] = v
+    return headers
+
+
+def rule_sequence(fallback_rules: dict, fallback_provider, requested_model: str, api_key: str, rotation):
+    """chat.py:47-78 -> (list of (rule index in the compiled table, rule), gateway model key of the plans or None)."""
+    cfg = fallback_rules.get(requested_model)
+    if not cfg:                                                            # :49-54
+        return [(0, {"provider": fallback_provider, "model": requested_model})], None
+    seq = list(enumerate(cfg["fallback_models"]))
+    if cfg["rotate_models"] and len(seq) > 1:                              # :63-78
+        start = rotation.get_next_model_index(api_key=api_key, gateway_model=requested_model, total_models=len(seq))
+        seq = seq[start:] + seq[:start]
+    return seq, requested_model
+
+
+def failure_text(rule: dict, sub_provider, error_detail) -> str:
+    """chat.py:154 / :182 `last_error_detail`."""
+    if sub_provider is None:
+        return f"Model {rule.get('model')} failed with provider '{rule.get('provider')}': {error_detail}"
+    return f"Model '{rule.get('model')}' failed from provider '{rule.get('provider')}' and sub-provider {sub_provider} : {error_detail}"
+
+
+def exhausted_text(requested_model: str, last_error_detail: str) -> str:
+    """chat.py:198."""
+    return f"All configured providers failed for model '{requested_model}'. Last error: {last_error_detail}"
+
+
+def attempts_of(rule: dict):
+    """The (sub_idx, sub_provider, retry) attempts one pass of the `while retry_count >= 0` loop makes (chat.py:127-185):
+    one for a standard provider, one per sub-provider when the provider order is walked as a fallback list."""
+    subs = rule.get("providers_order")
+    if not subs or rule.get("use_provider_order_as_fallback", False) is False:       # :129
+        return [(-1, None)]
+    return [(i, sp) for i, sp in enumerate(subs)]
+
+
+async def chat_completions(request, *, batcher: StreamBatcher, rotation: ModelRotation | None = None, client_factory=None,
+                           exotic_fallback=None, sleep=asyncio.sleep):
+    """Drop-in body of `@router.post("/completions")` (chat.py:20).  `batcher.load_rules(RulePlans(...))` must have been
+    called with the same `fallback_rules` the request's config loader holds."""
+    loader = getattr(request.app.state, "config_loader", None)
+    if not loader:                                                         # :22-26
+        raise _http_exception(500, "Internal server error: Core configuration not available.")
+    providers_config, fallback_rules = loader.providers_config, loader.fallback_rules
+    plans: rw.RulePlans = batcher.plans
+
+    try:
+        raw = await request.body()
+    except Exception as e:                                                 # :37-39
+        raise _http_exception(400, f"Error reading request body: {str(e)}")
+    scans, models = await batcher.scan_bodies([raw])
+    sc = scans[0]
+    if sc["status"] == rw.BODY_PARSE_ERROR:                                # :31-39 (decode error, JSON error, non-object root, no "model" key)
+        st, _, _, root = (await batcher.rewrite_bodies_matched([raw], [plans.plan_index(None)]))[0]
+        raise _http_exception(400, f"Error reading request body: {_request_error_text(raw, (st, root))}")
+    if sc["status"] == rw.BODY_NO_MODEL:                                   # :44-45
+        raise _http_exception(400, "Missing 'model' in request body")
+    if sc["model_kind"] != rw.KIND_STR or sc["model_len"] > len(models[0]):
+        raise _http_exception(400, "Error reading request body: 'model' is not a string the engine can route (not modelled)")
+    requested_model = models[0].decode("utf-8")
+    is_streaming = bool(sc["stream_truthy"])                               # :42 (only its truth value is ever used)
+
+    api_key = request.headers.get("Authorization", "").replace("Bearer ", "")          # :61
+    rotation = rotation or _default_rotation()
+    seq, gw_key = rule_sequence(fallback_rules, plans.fallback_provider, requested_model, api_key, rotation)
+
+    last_error_detail = "No providers were attempted."                     # :82
+    for rule_idx, rule in seq:                                             # :83
+        provider_cfg = providers_config.get(rule.get("provider"))
+        target_url = f"{provider_cfg.baseUrl.rstrip('/')}/chat/completions"           # :111
+        headers = attempt_headers(provider_cfg, rule)
+        retry_delay = rule.get("retry_delay")
+        retry_count = rule.get("retry_count") or 0
+        tries = attempts_of(rule)
+        scrubbed = False
+        while retry_count >= 0:                                            # :127
+            for sub_idx, sub_provider in tries:
+                plan = plans.plan_index(gw_key, rule_idx, sub_idx, retry=scrubbed and sub_idx < 0, stream=is_streaming)
+                status, payload = (await batcher.rewrite_bodies([raw], [plan]))[0]
+                if status != rw.BODY_OK:
+                    response_data, error_detail = None, f"Unexpected error during request to {target_url}: request body not modelled by the engine ({rw.STATUS_NAMES[status]})"
+                else:
+                    response_data, error_detail = await make_llm_request(target_url, headers, payload, is_streaming, batcher=batcher,
+                                                                         client_factory=client_factory, exotic_fallback=exotic_fallback)
+                if response_data and error_detail is None:                 # :146-148 / :173-175
+                    return response_data
+                if sub_idx < 0:
+                    scrubbed = True                                        # :150 the log scrub hits the live payload of every later retry
+                last_error_detail = failure_text(rule, sub_provider, error_detail)
+            if retry_count > 0 and retry_delay and 0 < retry_delay < 120:  # :190-192
+                await sleep(retry_delay)
+            retry_count -= 1
+    raise _http_exception(503, exhausted_text(requested_model, last_error_detail))     # :197-198
+
+
+_rotation_singleton: ModelRotation | None = None
+
+
+def _default_rotation() -> ModelRotation:
+    global _rotation_singleton
+    if _rotation_singleton is None:
+        _rotation_singleton = ModelRotation()
+    return _rotation_singleton
+
+
+_ROOT_ERRORS = {1: "'int' object does not support item assignment", 2: "'float' object does not support item assignment",
+                10: "'float' object does not support item assignment", 7: "'int' object does not support item assignment",
+                3: "'NoneType' object does not support item assignment", 4: "'bool' object does not support item assignment",
+                5: "'bool' object does not support item assignment", 6: "'str' object does not support item assignment",
+                9: "list indices must be integers or slices, not str", 8: "'model'"}
+
+
+def _request_error_text(raw: bytes, probe=None) -> str:
+    """str(e) of chat.py:37-39, error path only.  A body that is not UTF-8 gives Python's own UnicodeDecodeError text (reproduced
+    by decoding here); a well-formed document that is not an object with a "model" key gives the TypeError/KeyError text of
+    chat.py:35-36, chosen by the kind of the root value the engine reports (`probe` = (status, root_kind) of lgw_bodies_rewrite);
+    the text of a JSON syntax error is json5's own (json5 is absent from this image: unpinned)."""
+    try:
+        bytes(raw).decode("utf-8")
+    except UnicodeDecodeError as e:
+        return str(e)
+    if probe is not None and probe[0] == rw.BODY_OK and probe[1] in _ROOT_ERRORS:
+        return _ROOT_ERRORS[probe[1]]
+    return "request body is not valid JSON"
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The same walk for a batch of streaming requests, in lock-step rounds (one round = one attempt of every unserved request).
+# ------------------------------------------------------------------------------------------------------------------------
+@dataclass
+class Answers:
+    """What the upstreams answered in one round, in request order: `http_status[k]` (>= 400: `error_bodies` holds the text body,
+    request_handler.py:25-30), else the response stream of request k is the next segment of the packed (data, chunk_off, seg_chunk)."""
+    http_status: np.ndarray
+    error_bodies: list
+    data: np.ndarray
+    chunk_off: np.ndarray
+    seg_chunk: np.ndarray
+
+    @staticmethod
+    def from_lists(items) -> "Answers":
+        """items[k] = (status, body bytes) or a list of network chunks."""
+        st = np.array([it[0] if isinstance(it, tuple) else 200 for it in items], dtype=np.int32)
+        streams = [it for it in items if not isinstance(it, tuple)]
+        lens = np.fromiter((len(c) for ch in streams for c in ch), dtype=np.int64, count=sum(len(ch) for ch in streams))
+        chunk_off = np.zeros(lens.size + 1, np.uint32); np.cumsum(lens, out=chunk_off[1:])
+        seg_chunk = np.zeros(len(streams) + 1, np.uint32); np.cumsum([len(ch) for ch in streams], out=seg_chunk[1:])
+        data = np.frombuffer(b"".join(c for ch in streams for c in ch), dtype=np.uint8)
+        return Answers(st, [it[1] for it in items if isinstance(it, tuple)], data, chunk_off, seg_chunk)
+
+
+@dataclass
+class ChainOutcome:
+    served_round: np.ndarray         # int32 per request: round (attempt number) that served it; -1 = all attempts failed (503); -2 = 400
+    detail: list                     # per request: None, or the HTTPException detail (503 / 400)
+    spans: np.ndarray                # int64 [n, 2]: the relayed bytes of request i are round_out[served_round[i]][lo:hi]
+    round_out: list                  # per round: the step's re-emitted byte buffer
+    states: list                     # per round: (request indices, final lgw_stream_state list) of the served streams (usage rows)
+    attempts: int = 0
+    chunks_relayed: int = 0
+    steps: int = 0
+
+    def emitted(self, i: int) -> bytes:
+        r = int(self.served_round[i])
+        return b"" if r < 0 else self.round_out[r][int(self.spans[i, 0]):int(self.spans[i, 1])].tobytes()
+
+    def usage_rows(self):
+        """(request index, usage dict) of every served request: the last DB row of chat_logging.py:150."""
+        for idx, sts in self.states:
+            for i, st in zip(idx, sts):
+                if st.flags & _abi.SF_EMITTED_ANY:
+                    yield int(i), _abi.usage_rec_to_dict(st.rec)
+
+
+class ChainBatch:
+    """Lock-step walker over `n` streaming requests that share one engine (one GPU).  `upstream(round, ids, urls, payload
+    buffer, payload offsets) -> Answers` is the provider side (in the bench: the local synthetic SSE generator of the north star).
+
+    Every request walks its own chain (its own rules, rotation, retries and sub-providers); a round makes the next attempt of
+    every request that has not been served yet: ONE lgw_bodies_rewrite over their bodies with their attempts' plans, ONE
+    lgw_sse_step over everything the upstreams answered, ONE lgw_streams_details for the failed first events.  A request whose
+    first event fails (request_handler.py:86-88) moves on to its next attempt, one that commits is relayed to its end in the
+    same step.  The per-request control (which plan next, which error text last) is array arithmetic over the batch."""
+
+    def __init__(self, engine, plans: rw.RulePlans, providers_config: dict, fallback_rules: dict, rotation: ModelRotation | None = None):
+        self.eng, self.plans, self.providers, self.rules = engine, plans, providers_config, fallback_rules
+        self.rotation = rotation or ModelRotation()
+        self._sched_cache: dict = {}
+
+    def _schedule(self, requested_model: str, start: int):
+        """The full attempt list of one request: [(plan index, url, rule, sub_provider)] in chat.py's order."""
+        key = (requested_model, start)
+        if key in self._sched_cache:
+            return self._sched_cache[key]
+        cfg = self.rules.get(requested_model)
+        if not cfg:
+            seq, gw_key = [(0, {"provider": self.plans.fallback_provider, "model": requested_model})], None
+        else:
+            seq, gw_key = list(enumerate(cfg["fallback_models"])), requested_model
+            seq = seq[start:] + seq[:start]
+        out = []
+        for rule_idx, rule in seq:
+            cfgp = self.providers.get(rule.get("provider"))
+            url = f"{cfgp.baseUrl.rstrip('/')}/chat/completions"
+            scrubbed = False
+            for _ in range((rule.get("retry_count") or 0) + 1):
+                for sub_idx, sp in attempts_of(rule):
+                    out.append((self.plans.plan_index(gw_key, rule_idx, sub_idx, retry=scrubbed and sub_idx < 0, stream=True), url, rule, sp))
+                    if sub_idx < 0:
+                        scrubbed = True
+        self._sched_cache[key] = out
+        return out
+
+    def run(self, bodies: list, api_keys: list | None, upstream, stream_ids=None) -> ChainOutcome:
+        eng = self.eng
+        n = len(bodies)
+        ids = np.arange(n) if stream_ids is None else np.asarray(stream_ids)
+        buf, off = rw.pack_bodies(bodies)
+        scans, models = eng.scan_bodies(bodies)
+        out = ChainOutcome(np.full(n, -1, np.int32), [None] * n, np.zeros((n, 2), np.int64), [], [])
+        # ---- schedules: one per distinct (model, rotation start) ---------------------------------------------------------------
+        status = scans["status"]
+        sched_list, sched_of = [], {}
+        sid = np.full(n, -1, np.int32)
+        req_model = [None] * n
+        for i in range(n):
+            st = int(status[i])
+            if st == rw.BODY_PARSE_ERROR:
+                pst, _, _, root = eng.rewrite_bodies([bodies[i]], [self.plans.plan_index(None)], with_matched=True)[0]
+                out.detail[i] = f"Error reading request body: {_request_error_text(bodies[i], (pst, root))}"; out.served_round[i] = -2
+                continue
+            if st == rw.BODY_NO_MODEL:
+                out.detail[i] = "Missing 'model' in request body"; out.served_round[i] = -2
+                continue
+            mb = models[i]
+            ent = sched_of.get(mb)
+            if ent is None:
+                name = mb.decode("utf-8")
+                cfg = self.rules.get(name)
+                ent = sched_of[mb] = (name, bool(cfg and cfg["rotate_models"] and len(cfg["fallback_models"]) > 1), {})
+            name, rotates, by_start = ent
+            req_model[i] = name
+            start = 0
+            if rotates:                                                            # chat.py:65-78, serial per request
+                start = self.rotation.get_next_model_index(api_key=(api_keys[i] if api_keys else ""), gateway_model=name,
+                                                           total_models=len(self.rules[name]["fallback_models"]))
+            k = by_start.get(start)
+            if k is None:
+                k = by_start[start] = len(sched_list)
+                sched_list.append(self._schedule(name, start))
+            sid[i] = k
+        depth = max((len(s) for s in sched_list), default=0)
+        plan_tab = np.zeros((max(len(sched_list), 1), max(depth, 1)), np.uint32)
+        sched_len = np.zeros(max(len(sched_list), 1), np.int32)
+        for k, sc in enumerate(sched_list):
+            sched_len[k] = len(sc)
+            plan_tab[k, :len(sc)] = [a[0] for a in sc]
+        last_fail = {}                                                             # request -> (round, error_detail text)
+        longest = max((len(b) for b in bodies), default=0)
+        slot_cap = (6 * longest + self.plans.max_growth() + 64 + 15) & ~15
+        active = np.nonzero(sid >= 0)[0]
+        rnd = 0
+        while active.size:
+            going = active[sched_len[sid[active]] > rnd]
+            if not going.size:
+                break
+            # ---- this round's attempt of every unserved request: one rewrite launch set ----------------------------------------
+            if going.size == n:
+                sub_buf, sub_off = buf, off
+            else:
+                lens = (off[going + 1] - off[going]).astype(np.int64)
+                sub_off = np.zeros(going.size + 1, np.uint64); np.cumsum(lens, out=sub_off[1:])
+                gather = np.repeat(off[going].astype(np.int64) - sub_off[:-1].astype(np.int64), lens) + np.arange(int(sub_off[-1]), dtype=np.int64)
+                sub_buf = buf[gather]
+            plan_idx = plan_tab[sid[going], rnd]
+            pay, pay_off, res = eng.rewrite_packed(sub_buf, sub_off, plan_idx, slot_cap)
+            urls = [sched_list[k][rnd][1] for k in sid[going]] if getattr(upstream, "wants_urls", True) else None
+            ans: Answers = upstream(rnd, ids[going], urls, pay, pay_off)
+            out.attempts += int(going.size)
+            bad_body = res["status"] != rw.BODY_OK
+            http_fail = (ans.http_status >= 400) & ~bad_body
+            streaming = ~(http_fail | bad_body)                                    # these sent a response stream, in order
+            failed_now = []
+            for k in np.nonzero(bad_body)[0]:
+                i = int(going[k]); url = sched_list[sid[i]][rnd][1]
+                last_fail[i] = (rnd, f"Unexpected error during request to {url}: request body not modelled by the engine ({rw.STATUS_NAMES[int(res['status'][k])]})")
+                failed_now.append(i)
+            eb_iter = iter(ans.error_bodies)
+            for k in np.nonzero(ans.http_status >= 400)[0]:
+                body = next(eb_iter)
+                if not bad_body[k]:
+                    last_fail[int(going[k])] = (rnd, bytes(body).decode("utf-8"))
+                    failed_now.append(int(going[k]))
+            # ---- everything the upstreams streamed back: one step --------------------------------------------------------------
+            sreq = going[streaming]
+            m = int(sreq.size)
+            out.round_out.append(None)
+            if m:
+                slots = np.arange(m, dtype=np.uint32)
+                eng.open(slots, np.full(m, 200, np.int32))
+                r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots)
+                out.steps += 1
+                out.round_out[-1] = r.out
+                phase, verdict, eb = r.segs["phase"], r.segs["verdict"], r.segs["emit_chunk_begin"].astype(np.int64)
+                is_failed = phase == _abi.PHASE_FAILED
+                fidx = np.nonzero(is_failed)[0]
+                for d, k in zip(eng.details(slots[fidx]), fidx):
+                    i = int(sreq[k])
+                    text = d.decode("utf-8", errors="replace")
+                    if verdict[k] == _abi.VERDICT_FAIL_PARSE:
+                        text = f"Unexpected error during request to {sched_list[sid[i]][rnd][1]}: first event is not valid JSON: {text[:200]}"
+                    last_fail[i] = (rnd, text)
+                    failed_now.append(i)
+                ok = np.nonzero(~is_failed)[0]
+                seg_end = ans.seg_chunk[1:].astype(np.int64)
+                first = np.minimum(eb, seg_end)
+                co = ans.chunk_off.astype(np.int64)
+                out.spans[sreq[ok], 0] = co[first[ok]]
+                out.spans[sreq[ok], 1] = co[seg_end[ok]]
+                out.served_round[sreq[ok]] = rnd
+                out.chunks_relayed += int((seg_end[ok] - first[ok]).sum())
+                states = eng.close(slots)
+                out.states.append((sreq[ok], [states[int(k)] for k in ok]))
+            active = np.array(sorted(failed_now), dtype=np.int64)
+            rnd += 1
+        for i in np.nonzero(out.served_round == -1)[0]:                            # chat.py:197-198
+            i = int(i)
+            if i in last_fail:
+                fr, text = last_fail[i]
+                _, _, rule, sp = sched_list[sid[i]][fr]
+                out.detail[i] = exhausted_text(req_model[i], failure_text(rule, sp, text))
+            else:
+                out.detail[i] = exhausted_text(req_model[i], "No providers were attempted.")
+        return out

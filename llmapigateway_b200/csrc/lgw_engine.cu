@@ -11,6 +11,7 @@
 #include "sse_kernels.cuh"
 #include "rollup.cuh"
 #include "body_kernels.cuh"
+#include "doc_kernels.cuh"
 
 using namespace lgw;
 
@@ -20,6 +21,7 @@ static_assert(sizeof(StreamState) == sizeof(lgw_stream_state), "lgw_stream_state
 static_assert(sizeof(RowEvent) == sizeof(lgw_row_event), "lgw_row_event layout");
 static_assert(sizeof(SegResult) == sizeof(lgw_seg_result), "lgw_seg_result layout");
 static_assert(sizeof(RollupRow) == sizeof(lgw_rollup_row), "lgw_rollup_row layout");
+static_assert(sizeof(DocUsage) == sizeof(lgw_doc_usage), "lgw_doc_usage layout");
 
 static thread_local std::string g_create_error;
 
@@ -202,6 +204,41 @@ extern "C" int lgw_stream_detail(lgw_engine* e, uint32_t slot, uint8_t* buf, uin
     if (n) CK(e, cudaMemcpyAsync(buf, e->t.detail + (size_t)slot * e->lim.detail_cap, n, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     *len = n;
+    return LGW_OK;
+}
+
+// error details of many failed attempts in one round trip: a gather kernel packs min(detail_len, stride) bytes per slot
+namespace lgw {
+__global__ void k_details_gather(DeviceTables t, const uint32_t* slots, uint32_t n, uint8_t* out, uint32_t stride, uint32_t* lens) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t slot = slots[w];
+    uint32_t len = t.state[slot].h.detail_len;
+    if (len > t.detail_cap) len = t.detail_cap;
+    if (len > stride) len = stride;
+    const uint8_t* src = t.detail + (size_t)slot * t.detail_cap;
+    uint8_t* dst = out + (size_t)w * stride;
+    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+    if (lane == 0) lens[w] = len;
+}
+}  // namespace lgw
+
+extern "C" int lgw_streams_details(lgw_engine* e, const uint32_t* slots, uint32_t n, uint8_t* buf, uint32_t stride, uint32_t* lens) {
+    if (!e || (n && (!slots || !buf || !lens)) || stride == 0) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->lim.max_streams) return LGW_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    uint32_t* d_slots = nullptr; uint8_t* d_out = nullptr; uint32_t* d_lens = nullptr;
+    CK(e, cudaMallocAsync((void**)&d_slots, (size_t)n * 4, e->stream));
+    CK(e, cudaMallocAsync((void**)&d_lens, (size_t)n * 4, e->stream));
+    CK(e, cudaMallocAsync((void**)&d_out, (size_t)n * stride, e->stream));
+    CK(e, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    lgw::k_details_gather<<<(n * 32 + 255) / 256, 256, 0, e->stream>>>(e->t, d_slots, n, d_out, stride, d_lens);
+    ++e->launches;
+    CK(e, cudaMemcpyAsync(lens, d_lens, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(buf, d_out, (size_t)n * stride, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    cudaFreeAsync(d_slots, e->stream); cudaFreeAsync(d_lens, e->stream); cudaFreeAsync(d_out, e->stream);
     return LGW_OK;
 }
 
@@ -600,6 +637,26 @@ extern "C" int lgw_bodies_rewrite(lgw_engine* e, const uint8_t* bodies, const ui
     const uint64_t total = out_off[n] < out_cap ? out_off[n] : out_cap;
     if (total) CK(e, cudaMemcpyAsync(out, e->b_out, total, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+// ---- response tap of non-streaming responses (row a8, non-stream mode) ---------------------------------
+extern "C" int lgw_documents_usage(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off, uint32_t n, lgw_doc_usage* out) {
+    if (!e || !doc_off || (!docs && n && doc_off[n]) || (!out && n)) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    CK(e, cudaSetDevice(e->device));
+    int rc = bodies_stage_in(e, docs, doc_off, n);           // (the request-body staging buffers: same layout)
+    if (rc != LGW_OK) return rc;
+    DocUsage* d_out = nullptr;
+    CK(e, cudaMalloc((void**)&d_out, (size_t)n * sizeof(DocUsage)));
+    const uint32_t grid = (n + LGW_DOC_WARPS - 1) / LGW_DOC_WARPS < (uint32_t)e->sm_count * 8u ? (n + LGW_DOC_WARPS - 1) / LGW_DOC_WARPS : (uint32_t)e->sm_count * 8u;
+    k_docs_usage<<<grid, LGW_DOC_WARPS * 32, 0, e->stream>>>(e->b_in, e->b_off, n, d_out);
+    ++e->launches;
+    cudaError_t r = cudaGetLastError();
+    if (r == cudaSuccess) r = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(DocUsage), cudaMemcpyDeviceToHost, e->stream);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(e->stream);
+    cudaFree(d_out);
+    if (r != cudaSuccess) { e->err = std::string("lgw_documents_usage: ") + cudaGetErrorString(r); return LGW_ERR_CUDA; }
     return LGW_OK;
 }
 

@@ -42,7 +42,7 @@ def _ptr(a: np.ndarray):
 
 
 class Engine:
-    def __init__(self, device: int = 0, max_streams: int = 8192, carry_cap: int = 4096, detail_cap: int = 4096,
+    def __init__(self, device: int = 0, max_streams: int = 8192, carry_cap: int = 65536, detail_cap: int = 4096,
                  rowq_cap: int = 4096, max_step_chunks: int = 1 << 22, max_step_bytes: int = 1 << 28):
         self._lib = _native.load()
         self.limits = _abi.Limits(max_streams, carry_cap, detail_cap, rowq_cap, max_step_chunks, max_step_bytes)
@@ -68,6 +68,12 @@ class Engine:
             self.close_engine()
         except Exception:
             pass
+
+    def alloc_pinned(self, nbytes: int) -> np.ndarray:
+        """Page-locked host memory owned by the engine (lgw_alloc_pinned) as a uint8 array; freed with the engine."""
+        p = C.c_void_p()
+        self._ck(self._lib.lgw_alloc_pinned(self._h, nbytes, C.byref(p)), "alloc_pinned")
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._ck(self._lib.lgw_engine_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "set_stream")
@@ -99,6 +105,18 @@ class Engine:
         n = C.c_uint32(0)
         self._ck(self._lib.lgw_stream_detail(self._h, slot, buf, self.limits.detail_cap, C.byref(n)), "stream_detail")
         return buf.raw[:n.value]
+
+    def details(self, slots, stride: int | None = None) -> list:
+        """Error details of many failed attempts in one round trip (lgw_streams_details)."""
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        n = len(slots)
+        if n == 0:
+            return []
+        stride = stride or self.limits.detail_cap
+        buf = np.empty(n * stride, dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint32)
+        self._ck(self._lib.lgw_streams_details(self._h, _ptr(slots), n, _ptr(buf), stride, _ptr(lens)), "streams_details")
+        return [bytes(buf[i * stride:i * stride + int(lens[i])]) for i in range(n)]
 
     # -- the hot path --------------------------------------------------------------------------------
     def step(self, data: np.ndarray, chunk_off: np.ndarray, seg_chunk: np.ndarray, seg_slot: np.ndarray,
@@ -209,6 +227,21 @@ class Engine:
         if with_matched:
             return [(st, b, int(res["matched"][i]), int(res["root_kind"][i])) for i, (st, b) in enumerate(rows)]
         return rows
+
+    def documents_usage(self, docs):
+        """Response tap of non-streaming responses (chat_logging.py:98-150 with is_real_streaming=False): for every document the
+        list of usage rows the tap thread writes -- the extra row of a top-level "error" (:139), then the final row (:150).
+        -> list of (rows: list[dict], exotic: bool)"""
+        from . import rewrite as rw
+        buf, off = rw.pack_bodies(docs)
+        n = len(docs)
+        out = (_abi.DocUsage * max(n, 1))()
+        self._ck(self._lib.lgw_documents_usage(self._h, _ptr(buf), _ptr(off), n, out), "documents_usage")
+        res = []
+        for i in range(n):
+            row = _abi.usage_rec_to_dict(out[i].rec)
+            res.append(([dict(row), row] if out[i].error_row else [row], bool(out[i].exotic)))
+        return res
 
     def bodies_last_ms(self):
         ms = (C.c_float * 3)()

@@ -32,51 +32,97 @@ class FeedResult:
     emitted: bytes | None        # the chunk to relay now (original bytes), or None when dropped
     phase: int
     verdict: int
+    flags: int = 0               # lgw_stream_flag bits after the step (SF_CARRY_OVERFLOW: an event outgrew carry_cap)
 
 
 @dataclass
 class _Pending:
     slot: int
+    gen: int                     # generation of the slot when the chunk was fed: entries of an earlier user of the slot are dropped
     chunk: bytes
     fut: asyncio.Future
 
 
 class StreamBatcher:
     """One per engine/GPU.  Coroutines call feed(); a pump task packs everything that arrived during
-    `window_s` into one engine step (run in a worker thread: ctypes releases the GIL)."""
+    `window_s` into one engine step (run in a worker thread: ctypes releases the GIL).
 
-    def __init__(self, engine, window_s: float = 0.002, usage_sink=None):
+    Slots are handed out first-in first-out and carry a generation counter: a chunk that is still queued when its
+    request goes away (client disconnect cancels the awaiting feed()) can never be packed into the next stream that
+    gets the slot, and a slot only returns to the free list once no step that contains it is in flight."""
+
+    def __init__(self, engine, window_s: float = 0.002, usage_sink=None, arena_bytes: int = 8 << 20):
+        import collections
         self.eng = engine
         self.window_s = window_s
         self.usage_sink = usage_sink
-        self._free = list(range(engine.limits.max_streams - 1, -1, -1))
+        self._free = collections.deque(range(engine.limits.max_streams))
+        self._gen = [0] * engine.limits.max_streams
         self._pending: list[_Pending] = []
+        self._inflight: dict[int, asyncio.Future] = {}        # slot -> done-future of the step that currently holds chunks of it
         self._wake = asyncio.Event()
         self._task: asyncio.Task | None = None
         self._closed = False
         self.steps = 0
+        self.dropped_stale = 0
+        self.overflowed = 0                                   # streams that reported SF_CARRY_OVERFLOW (logged, see feed())
         # the engine handle is not thread-safe: every call into it goes through this one worker thread
         self._worker = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="lgw-engine")
+        # pinned ingress/egress arenas (SURVEY 8(f) rank 4): chunks are packed straight into page-locked memory the engine
+        # owns (lgw_alloc_pinned), so the step's H2D/D2H copies are DMA transfers, not staged pageable copies
+        self._arena_in = self._arena_out = None
+        alloc = getattr(engine, "alloc_pinned", None)
+        if alloc is not None and arena_bytes:
+            try:
+                self._arena_in, self._arena_out = alloc(arena_bytes), alloc(arena_bytes)
+            except Exception:
+                self._arena_in = self._arena_out = None
 
     # -- slots ---------------------------------------------------------------------------------------
     async def open_stream(self, http_status: int = 200) -> int:
         if not self._free:
             raise RuntimeError("no free stream slot on this engine")
-        slot = self._free.pop()
-        await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.open, [slot], [http_status])
+        slot = self._free.popleft()
+        self._gen[slot] += 1
+        try:
+            await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.open, [slot], [http_status])
+        except BaseException:
+            self._free.append(slot)
+            raise
         return slot
 
     async def close_stream(self, slot: int):
         """End of upstream: returns (final StreamState, usage dict or None).  The usage dict is the
         last DB row of chat_logging.py:150 and goes to the usage sink (TokensUsageDB.insert_usage seam)."""
+        self._gen[slot] += 1                                   # whatever is still queued for this slot is stale from now on
+        self._pending = [p for p in self._pending if p.slot != slot or self._cancel(p)]
+        fut = self._inflight.get(slot)
+        if fut is not None:                                    # a step that contains chunks of this slot is running: let it finish
+            try:
+                await asyncio.shield(fut)
+            except Exception:
+                pass
         st = (await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.close, [slot]))[0]
         self._free.append(slot)
         usage = None
         if st.flags & _abi.SF_EMITTED_ANY:
             usage = _abi.usage_rec_to_dict(st.rec)
-            if self.usage_sink is not None:
-                self.usage_sink.insert_usage(usage)
+            self._sink(usage)
         return st, usage
+
+    @staticmethod
+    def _cancel(p: _Pending) -> bool:
+        if not p.fut.done():
+            p.fut.cancel()
+        return False
+
+    def _sink(self, usage: dict):
+        if self.usage_sink is None:
+            return
+        try:                                                   # the reference swallows insert errors (tokens_usage_db.py:155-159)
+            self.usage_sink.insert_usage(usage)
+        except Exception:
+            pass
 
     # -- request bodies / non-streaming responses (rows a1-a4, a12): same worker thread, same engine ---------
     def load_rules(self, plans) -> None:
@@ -87,13 +133,20 @@ class StreamBatcher:
     async def rewrite_bodies(self, bodies, plan_idx):
         return await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.rewrite_bodies, list(bodies), list(plan_idx))
 
+    async def rewrite_bodies_matched(self, bodies, plan_idx):
+        return await asyncio.get_running_loop().run_in_executor(self._worker, lambda: self.eng.rewrite_bodies(list(bodies), list(plan_idx), with_matched=True))
+
     async def scan_bodies(self, bodies):
         return await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.scan_bodies, list(bodies))
 
-    async def normalise_responses(self, contents, http_status, target_url: str):
+    async def normalise_responses(self, contents, http_status, target_url: str, strict: bool = True):
         from .responses import normalise_responses
         return await asyncio.get_running_loop().run_in_executor(
-            self._worker, lambda: normalise_responses(self.eng, self.plans, list(contents), list(http_status), target_url))
+            self._worker, lambda: normalise_responses(self.eng, self.plans, list(contents), list(http_status), target_url, strict))
+
+    async def documents_usage(self, docs):
+        """Response tap of non-streaming responses (chat_logging.py:98-150): the usage rows of each document."""
+        return await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.documents_usage, list(docs))
 
     async def detail(self, slot: int) -> str:
         raw = await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.detail, slot)
@@ -103,11 +156,21 @@ class StreamBatcher:
     async def feed(self, slot: int, chunk: bytes) -> FeedResult:
         loop = asyncio.get_running_loop()
         fut = loop.create_future()
-        self._pending.append(_Pending(slot, bytes(chunk), fut))
+        self._pending.append(_Pending(slot, self._gen[slot], bytes(chunk), fut))
         if self._task is None or self._task.done():
             self._task = loop.create_task(self._pump())
         self._wake.set()
         return await fut
+
+    def _pack(self, blobs, total):
+        """All chunks back to back: in the pinned arena when they fit, else in ordinary memory."""
+        if self._arena_in is not None and total <= self._arena_in.size:
+            pos = 0
+            for b in blobs:
+                self._arena_in[pos:pos + len(b)] = np.frombuffer(b, dtype=np.uint8)
+                pos += len(b)
+            return self._arena_in[:total], self._arena_out[:max(total, 1)]
+        return (np.frombuffer(b"".join(blobs), dtype=np.uint8) if blobs else np.zeros(0, np.uint8)), None
 
     async def _pump(self):
         loop = asyncio.get_running_loop()
@@ -116,38 +179,64 @@ class StreamBatcher:
             batch, self._pending = self._pending, []
             by_slot: dict[int, list[_Pending]] = {}
             for p in batch:
+                if p.fut.cancelled() or p.gen != self._gen[p.slot]:      # the request went away / the slot has a new user
+                    self.dropped_stale += 1
+                    continue
                 by_slot.setdefault(p.slot, []).append(p)
             slots = list(by_slot)
+            if not slots:
+                continue
             blobs, offs, segc = [], [0], [0]
             for s in slots:
                 for p in by_slot[s]:
                     blobs.append(p.chunk); offs.append(offs[-1] + len(p.chunk))
                 segc.append(segc[-1] + len(by_slot[s]))
-            data = np.frombuffer(b"".join(blobs), dtype=np.uint8) if blobs else np.zeros(0, np.uint8)
+            data, out = self._pack(blobs, offs[-1])
+            done = loop.create_future()
+            for s in slots:
+                self._inflight[s] = done
             try:
-                res = await loop.run_in_executor(self._worker, self.eng.step, data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32))
+                res = await loop.run_in_executor(self._worker, lambda: self.eng.step(data, np.array(offs, np.uint32), np.array(segc, np.uint32),
+                                                                                    np.array(slots, np.uint32), **({"out": out} if out is not None else {})))
             except Exception as exc:                      # engine failure: the endpoint answers 500/503 like chat.py:26,198
-                for p in batch:
-                    if not p.fut.done():
-                        p.fut.set_exception(exc)
+                for ps in by_slot.values():
+                    for p in ps:
+                        if not p.fut.done():
+                            p.fut.set_exception(exc)
                 continue
+            finally:
+                for s in slots:
+                    if self._inflight.get(s) is done:
+                        del self._inflight[s]
+                if not done.done():
+                    done.set_result(None)
             self.steps += 1
-            if self.usage_sink is not None:
+            try:
                 for ev in sorted(res.rows, key=lambda r: (r.slot, r.seq)):      # mid-stream rows, chat_logging.py:139
-                    self.usage_sink.insert_usage(_abi.usage_rec_to_dict(ev.rec))
+                    self._sink(_abi.usage_rec_to_dict(ev.rec))
+            except Exception:
+                pass
             for k, s in enumerate(slots):
-                eb = int(res.segs["emit_chunk_begin"][k])
-                for j, p in enumerate(by_slot[s]):
-                    c = segc[k] + j
-                    out = None
-                    if c >= eb and len(p.chunk):
-                        out = res.out[offs[c]:offs[c + 1]].tobytes()          # the re-emitted bytes
-                    if not p.fut.done():
-                        p.fut.set_result(FeedResult(out, int(res.segs["phase"][k]), int(res.segs["verdict"][k])))
+                try:
+                    eb = int(res.segs["emit_chunk_begin"][k])
+                    flags = int(res.segs["flags"][k])
+                    if flags & _abi.SF_CARRY_OVERFLOW:
+                        self.overflowed += 1
+                    for j, p in enumerate(by_slot[s]):
+                        c = segc[k] + j
+                        emitted = None
+                        if c >= eb and len(p.chunk):
+                            emitted = res.out[offs[c]:offs[c + 1]].tobytes()          # the re-emitted bytes
+                        if not p.fut.done():
+                            p.fut.set_result(FeedResult(emitted, int(res.segs["phase"][k]), int(res.segs["verdict"][k]), flags))
+                except Exception as exc:                                         # never leave a future of the batch unresolved
+                    for p in by_slot[s]:
+                        if not p.fut.done():
+                            p.fut.set_exception(exc)
 
 
 async def make_llm_request(target_url: str, headers: dict, payload: dict, is_streaming: bool, *, batcher: StreamBatcher,
-                           client_factory=None):
+                           client_factory=None, exotic_fallback=None):
     """Drop-in for request_handler.py:8.  Returns (response, None) on success and (None, error_detail) on
     failure; never raises (request_handler.py:178-187).  `payload` is the attempt's body: the bytes
     `StreamBatcher.rewrite_bodies` produced (rows a3/a4) -- a dict is still accepted on the streaming branch
@@ -163,10 +252,19 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
             if "json" in body_kw:
                 raise TypeError("non-streaming payloads must be the bytes produced by rewrite_bodies (no CPU serialiser in this package)")
             response = await client.post(target_url, headers=headers, timeout=None, **body_kw)
-            body, detail = (await batcher.normalise_responses([response.content], [response.status_code], target_url))[0]
+            body, detail = (await batcher.normalise_responses([response.content], [response.status_code], target_url, False))[0]
+            if body == "exotic":
+                # a document the engine reports but does not model (duplicate keys, floats with more than 15 significant digits,
+                # nesting beyond 16 ...): NOT a failed attempt -- the integrator's own code path decides (INTEGRATION.md 3(b)
+                # passes the reference's make_llm_request here); without one the attempt fails loudly with the reason
+                if exotic_fallback is not None:
+                    return await exotic_fallback(target_url, headers, payload, False, response)
+                return None, f"Unexpected error during request to {target_url}: response not modelled by the engine ({detail}); pass exotic_fallback="
             if body is None:
                 return None, detail
-            return Response(content=body, status_code=200, media_type="application/json"), None
+            resp = Response(content=body, status_code=200, media_type="application/json")
+            resp.lgw_tapped = False                                          # log_chat_completions (below) taps it like chat_logging.py does
+            return resp, None
         except httpx.RequestError as e:                                   # request_handler.py:178-182
             return None, f"RequestError connecting to {target_url}: {str(e)}"
         except Exception as e:                                            # request_handler.py:183-187
@@ -207,11 +305,18 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
                         if r.emitted is not None:
                             yield r.emitted
             finally:
+                # (shielded: a client disconnect cancels this generator, the slot and the upstream connection must still be released)
+                await asyncio.shield(_cleanup())
+
+        async def _cleanup():
+            try:
                 await batcher.close_stream(slot)
+            finally:
                 await ctx.__aexit__(None, None, None)
 
-        return StreamingResponse(relay(), media_type="text/event-stream",
-                                 headers={"Transfer-Encoding": "chunked", "X-Accel-Buffering": "no"}), None
+        resp = StreamingResponse(relay(), media_type="text/event-stream", headers={"Transfer-Encoding": "chunked", "X-Accel-Buffering": "no"})
+        resp.lgw_tapped = True            # the engine's tap already saw every relayed chunk: log_chat_completions must not tap it again
+        return resp, None
     except httpx.RequestError as e:                                       # request_handler.py:178-182
         if slot is not None:
             await batcher.close_stream(slot)
@@ -223,6 +328,53 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
             except Exception:
                 pass
         return None, f"Unexpected error during request to {target_url}: {str(e)}"
+
+
+async def log_chat_completions(request, call_next, *, batcher: StreamBatcher):
+    """Mirror of the middleware seam chat_logging.py:165-231.  Streaming responses made by `make_llm_request` above were tapped
+    inside the engine (usage rows reach the sink at close_stream): they pass through.  Every other response of the
+    /chat/completions route -- non-streaming completions, and the 400/503 JSON bodies of the endpoint -- is what the reference
+    hands to a ChunkProcessorThread in its non-streaming mode (:188-190, :98-150): the body is collected, the engine reads the
+    usage row(s) out of it (lgw_documents_usage) and they go to the usage sink; the client gets the same bytes, re-chunked
+    exactly as they came."""
+    if not request.url.path.endswith("/chat/completions"):               # :167-168
+        return await call_next(request)
+    response = await call_next(request)
+    try:
+        if getattr(response, "lgw_tapped", False):
+            return response
+        ctype = response.headers.get("content-type") or ""
+        if "text/event-stream" in ctype:                                  # a stream that did not come from the engine: not ours to tap
+            return response
+        if hasattr(response, "body_iterator"):
+            original = response.body_iterator
+
+            async def tapping():
+                chunks = []
+                async for chunk in original:
+                    chunks.append(bytes(chunk))
+                    yield chunk
+                await _tap_document(batcher, chunks)
+
+            response.body_iterator = tapping()
+        elif getattr(response, "body", None) is not None:
+            await _tap_document(batcher, [bytes(response.body)])
+    except Exception:                                                     # :228-229 the middleware never breaks the response
+        pass
+    return response
+
+
+async def _tap_document(batcher: StreamBatcher, chunks):
+    if not chunks:                                                        # no first chunk => no thread => no row (:198-203)
+        return
+    try:
+        text = b"".join(chunks)
+        text.decode("utf-8")                                              # (:101 a decode error ends the thread without a row)
+    except UnicodeDecodeError:
+        return
+    rows, _exotic = (await batcher.documents_usage([text]))[0]
+    for row in rows:
+        batcher._sink(row)
 
 
 class SqliteUsageSink:
@@ -247,11 +399,16 @@ class SqliteUsageSink:
             g = u.get
             rows.append((ts, g("prompt_tokens", 0), g("completion_tokens", 0), g("total_tokens", 0), g("reasoning_tokens", 0),
                          g("cached_tokens", 0), g("cost", 0.0), g("model"), g("provider")))
+        sql = ("INSERT INTO tokens_usage (timestamp, prompt_tokens, completion_tokens, total_tokens, reasoning_tokens,"
+               " cached_tokens, cost, model, provider) VALUES (?,?,?,?,?,?,?,?,?)")
+        for row in rows:
+            try:                          # the reference swallows insert errors row by row (:155-159): a value SQLite cannot bind
+                self.conn.execute(sql, row)       # (an int beyond 64 bits, a dict) loses that row only
+            except Exception:
+                pass
         try:
-            with self.conn:
-                self.conn.executemany("INSERT INTO tokens_usage (timestamp, prompt_tokens, completion_tokens, total_tokens, reasoning_tokens,"
-                                      " cached_tokens, cost, model, provider) VALUES (?,?,?,?,?,?,?,?,?)", rows)
-        except Exception:        # the reference swallows insert errors (:155-159)
+            self.conn.commit()
+        except Exception:
             pass
 
     def insert_usage(self, usage: dict):

@@ -107,6 +107,7 @@ def attempt_assignments(rule: dict, provider_name: str, sub_provider=None, retry
         out.append(("usage", {"include": True}, True))
     for k, v in (rule.get("custom_body_params") or {}).items():           # chat.py:116-119
         out.append((k, v, False))
+    out.append(("model", rule.get("model"), False))                       # chat.py:135 / :160 re-assign inside the retry loop: the rule's model always wins
     order = rule.get("providers_order")
     routed = [sub_provider] if sub_provider is not None else (list(order) if order else None)
     if routed is not None:                                                # chat.py:137-139 / :164-168
@@ -190,7 +191,9 @@ class RulePlans:
         """Plan of one attempt.  `gw_model=None` (or a model without rules) selects the fallback-provider plan."""
         mode = MODES[self.stream_mode] if stream else MODES["json5"]
         if gw_model not in self.fallback_rules:
-            return self.index[(None, 0, -1, False, mode)]
+            return self.index[(None, 0, -1, False, mode)]        # (the synthetic fallback rule has no retry_count: chat.py:52)
+        if sub_idx >= 0:
+            retry = False          # chat.py:158-181: the sub-provider branch never scrubs `messages`, a retry re-sends the same body
         return self.index[(gw_model, rule_idx, sub_idx, retry, mode)]
 
     def response_plan(self) -> int:

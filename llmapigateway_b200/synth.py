@@ -223,3 +223,131 @@ def openai_batch(n_streams: int = 1024, n_deltas: int = 256, seed: int = 9, even
     b = pack_streams(streams)
     b.truths = truths
     return b
+
+
+# ---- config 4: a 3-deep fallback chain with injected upstream failures --------------------------------------
+@dataclass
+class Provider:
+    """Shape of loader.py:15-17 ProviderDetails as chat.py reads it (:92-94)."""
+    baseUrl: str
+    apikey: str
+
+
+C4_MODEL = "gw/chain3"
+
+
+def chain_world():
+    """(providers_config, fallback_rules, fallback_provider): a 3-rule chain per gateway model, plus the rule shapes the
+    walker has to get right -- rotation, retries with the log scrub, sub-provider ordering walked as a fallback list or sent
+    as a hint, custom body params (one overriding `model`), custom headers, and the unknown-model fallback provider."""
+    providers = {
+        "alpha": Provider("http://alpha.test/v1", "ALPHA_KEY_ENV"),
+        "beta": Provider("http://beta.test/api/v1/", "sk-beta-literal"),
+        "gamma": Provider("http://gamma.test/v1", ""),
+        "openrouter": Provider("http://openrouter.test/api/v1", "sk-or-literal"),
+    }
+
+    def rule(provider, model, **kw):
+        r = {"provider": provider, "model": model, "use_provider_order_as_fallback": False, "custom_body_params": {}, "custom_headers": {}}
+        r.update(kw)
+        return r
+
+    rules = {
+        C4_MODEL: {"rotate_models": False, "fallback_models": [
+            rule("alpha", "alpha/large-1"),
+            rule("beta", "beta-chat-2", custom_body_params={"temperature": 0.25, "model": "ignored/by-the-walker"}, custom_headers={"X-Route": "beta"}),
+            rule("gamma", "gamma-3-instruct")]},
+        "gw/rotating": {"rotate_models": True, "fallback_models": [
+            rule("alpha", "alpha/rot-a"), rule("beta", "beta-rot-b"), rule("gamma", "gamma-rot-c")]},
+        "gw/retrying": {"rotate_models": False, "fallback_models": [
+            rule("alpha", "alpha/flaky", retry_count=2, retry_delay=0),
+            rule("gamma", "gamma-steady")]},
+        "gw/or-fallback": {"rotate_models": False, "fallback_models": [
+            rule("openrouter", "deepseek/deepseek-chat-v3-0324:free", providers_order=["Chutes", "Targon"], use_provider_order_as_fallback=True, retry_count=1, retry_delay=0),
+            rule("beta", "beta-chat-2")]},
+        "gw/or-hint": {"rotate_models": False, "fallback_models": [
+            rule("openrouter", "google/gemini-2.5-pro", providers_order=["DeepInfra", "Lambda"], retry_count=1, retry_delay=0),
+            rule("gamma", "gamma-3-instruct")]},
+    }
+    return providers, rules, "openrouter"
+
+
+def chain_request_bodies(n: int, seed: int = 4, model: str = C4_MODEL, pad_to: int = 256) -> list[bytes]:
+    """Streaming chat requests of exactly `pad_to` bytes (the C1 body shape, `stream: true`)."""
+    rng = np.random.default_rng([seed, n, 7])
+    out = []
+    for i in range(n):
+        head = ('{"model":"%s","stream":true,"user":"u%05d","messages":[{"role":"user","content":"' % (model, i)).encode()
+        tail = b'"}]}'
+        fill = max(0, pad_to - len(head) - len(tail))
+        out.append(head + _ALPHABET[rng.integers(0, len(_ALPHABET), fill)].tobytes() + tail)
+    return out
+
+
+FAIL_NONE, FAIL_HTTP500, FAIL_ERROR_EVENT, FAIL_DETAIL_EVENT = range(4)
+
+
+class ChainUpstream:
+    """The provider side of config 4.  Attempt `a` of stream `sid` fails with probability `p_fail`, independently, the failure
+    kind uniform over {HTTP 500 + text body, first event {"error":{"message":..}}, first event {"detail":..}}; an attempt that
+    does not fail streams the stream's C3 payload (n_events 64-byte deltas, the usage event, [DONE]; one event per chunk)."""
+    wants_urls = False
+
+    def __init__(self, n_streams: int = 8192, n_events: int = 512, seed: int = 4, p_fail: float = 0.2, max_attempts: int = 8):
+        self.n, self.seed, self.p = n_streams, seed, p_fail
+        self.batch = sse_batch(n_streams, n_events, seed)
+        rng = np.random.default_rng([seed, n_streams, 1234])
+        u = rng.random((max_attempts, n_streams))
+        k = rng.integers(1, 4, (max_attempts, n_streams))
+        self.kind = np.where(u < p_fail, k, 0).astype(np.uint8)              # [attempt, stream]
+        self.calls = []
+
+    def failure_chunks(self, sid: int, attempt: int, kind: int):
+        if kind == FAIL_HTTP500:
+            return (500, ("upstream exploded: stream %d attempt %d {\"trace\":\"x\"}" % (sid, attempt)).encode())
+        if kind == FAIL_ERROR_EVENT:
+            return [('data: {"error":{"message":"provider overloaded (stream %d, attempt %d)","code":503}}\n\n' % (sid, attempt)).encode()]
+        return [('data: {"detail":"rate limited: stream %d attempt %d"}\n\n' % (sid, attempt)).encode(), b'data: {"choices":[]}\n\n']
+
+    def stream_chunks(self, sid: int, attempt: int):
+        kind = int(self.kind[attempt, sid])
+        return self.failure_chunks(sid, attempt, kind) if kind else self.batch.stream_chunks(sid)
+
+    def __call__(self, attempt: int, ids, urls, payload_buf, payload_off):
+        from .chat import Answers
+        ids = np.asarray(ids, dtype=np.int64)
+        self.calls.append((attempt, ids.copy()))
+        kind = self.kind[attempt, ids]
+        status = np.where(kind == FAIL_HTTP500, 500, 200).astype(np.int32)
+        errors = [self.failure_chunks(int(s), attempt, FAIL_HTTP500)[1] for s in ids[kind == FAIL_HTTP500]]
+        b = self.batch
+        sids = ids[kind != FAIL_HTTP500]
+        skind = kind[kind != FAIL_HTTP500]
+        # packed response streams, in request order: whole C3 segments for the good attempts, short failing streams else
+        fail_blobs = {int(s): self.failure_chunks(int(s), attempt, int(kd)) for s, kd in zip(sids[skind != 0], skind[skind != 0])}
+        c0 = b.seg_chunk[sids].astype(np.int64); c1 = b.seg_chunk[sids + 1].astype(np.int64)
+        n_chunks = np.where(skind == 0, c1 - c0, 0)
+        for j in np.nonzero(skind != 0)[0]:
+            n_chunks[j] = len(fail_blobs[int(sids[j])])
+        seg_chunk = np.zeros(len(sids) + 1, np.uint32); np.cumsum(n_chunks, out=seg_chunk[1:])
+        co = b.chunk_off.astype(np.int64)
+        seg_bytes = np.where(skind == 0, co[c1] - co[c0], 0)
+        for j in np.nonzero(skind != 0)[0]:
+            seg_bytes[j] = sum(len(c) for c in fail_blobs[int(sids[j])])
+        seg_start = np.zeros(len(sids) + 1, np.int64); np.cumsum(seg_bytes, out=seg_start[1:])
+        data = np.empty(int(seg_start[-1]), np.uint8)
+        chunk_off = np.empty(int(seg_chunk[-1]) + 1, np.int64)
+        for j in range(len(sids)):
+            lo = int(seg_start[j])
+            if skind[j] == 0:
+                s0 = int(co[c0[j]])
+                data[lo:lo + int(seg_bytes[j])] = b.data[s0:s0 + int(seg_bytes[j])]
+                chunk_off[int(seg_chunk[j]):int(seg_chunk[j + 1])] = co[c0[j]:c1[j]] - s0 + lo
+            else:
+                pos = lo
+                for q, c in enumerate(fail_blobs[int(sids[j])]):
+                    chunk_off[int(seg_chunk[j]) + q] = pos
+                    data[pos:pos + len(c)] = np.frombuffer(c, np.uint8)
+                    pos += len(c)
+        chunk_off[-1] = seg_start[-1]
+        return Answers(status, errors, data, chunk_off.astype(np.uint32), seg_chunk)

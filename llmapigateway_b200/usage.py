@@ -63,15 +63,41 @@ class UsageTable:
         self._providers: list[str | None] = []   # per record (listing only; the rollup does not group by provider)
         self._dev = None                          # (n, {col: device ptr}, names)
         self._pending_rows: list[tuple] = []
+        self.rejected = 0                         # records insert_usage refused (see there)
 
     # -- ingest ------------------------------------------------------------------------------------
     def insert_usage(self, tokens_usage: dict, timestamp: datetime | None = None):
-        """One record, same dict shape as the reference's insert_usage (:136-143)."""
+        """One record, same dict shape as the reference's insert_usage (:136-143).  Like the reference (:155-159) this never
+        raises: a value SQLite would have stored as NULL (JSON null), as REAL/TEXT (a non-integer where a count belongs), or
+        that no INTEGER column of the device table can hold (|v| >= 2^31) makes the record unusable for the integer rollup
+        and the row is REJECTED (counted in `rejected`), never half-inserted."""
         ts = to_us(timestamp or datetime.now())
         g = tokens_usage.get
-        self._pending_rows.append((ts, g("model"), int(g("prompt_tokens", 0)), int(g("completion_tokens", 0)), int(g("total_tokens", 0)),
-                                   int(g("reasoning_tokens", 0)), int(g("cached_tokens", 0)), float(g("cost", 0.0)), g("provider")))
+        try:
+            counts = []
+            for k in ("prompt_tokens", "completion_tokens", "total_tokens", "reasoning_tokens", "cached_tokens"):
+                v = g(k, 0)
+                if v is None:
+                    v = 0                                              # SUM() skips NULL
+                if isinstance(v, bool) or not isinstance(v, int):
+                    if isinstance(v, float) and v.is_integer():
+                        v = int(v)
+                    else:
+                        raise ValueError(k)
+                if not -(1 << 31) <= v < (1 << 31):
+                    raise OverflowError(k)
+                counts.append(v)
+            cost = g("cost", 0.0)
+            cost = 0.0 if cost is None else float(cost)
+            model, provider = g("model"), g("provider")
+            if model is not None and not isinstance(model, str):
+                model = str(model)
+        except Exception:
+            self.rejected += 1
+            return False
+        self._pending_rows.append((ts, model, *counts, cost, provider))
         self._dev = None
+        return True
 
     def load_columns(self, ts_us, models, prompt, completion, total, reasoning, cached, cost):
         """Bulk ingest of columns (models: sequence of str|None)."""
@@ -88,12 +114,12 @@ class UsageTable:
         if self._pending_rows:
             cols = list(zip(*self._pending_rows))
             h = self._host
-            old_models = self._models
-            self._host = {"ts_us": np.concatenate([h["ts_us"], np.array(cols[0], np.int64)]), "model_rank": None}
-            for k, name in enumerate(self.COLS[2:7]):
-                self._host[name] = np.concatenate([h[name], np.array(cols[2 + k], np.int32)])
-            self._host["cost"] = np.concatenate([h["cost"], np.array(cols[7], np.float64)])
-            self._models = list(old_models) + list(cols[1])
+            fresh = {"ts_us": np.concatenate([h["ts_us"], np.array(cols[0], np.int64)]), "model_rank": None}     # built completely
+            for k, name in enumerate(self.COLS[2:7]):                                                           # before anything
+                fresh[name] = np.concatenate([h[name], np.array(cols[2 + k], np.int32)])                        # is replaced
+            fresh["cost"] = np.concatenate([h["cost"], np.array(cols[7], np.float64)])
+            self._host = fresh
+            self._models = list(self._models) + list(cols[1])
             self._providers = list(self._providers) + list(cols[8])
             self._pending_rows = []
         names = sorted({m for m in self._models if m is not None}, key=lambda s: s.encode("utf-8"))

@@ -246,6 +246,47 @@ class TapOracle:
         return out
 
 
+def tap_nonstream(chunks: list[bytes], loads: Callable[[str], object] = json.loads) -> TapResult:
+    """chat_logging.py:87-150 with is_real_streaming=False (every response that is not text/event-stream, :188): the chunks are
+    concatenated first (:98-103), the whole text is ONE part (:105-106), then the same per-part code as the streaming branch."""
+    out = TapResult([], [])
+    if not chunks:                           # no first chunk => no thread (:198-203) => no row
+        return out
+    usage = {k: 0 for k in USAGE_DEFAULTS}                        # :77-84
+    accum = ""
+    try:
+        buffer = ""
+        for raw in chunks:
+            buffer += raw.decode("utf-8")                         # :100-101 (a decode error escapes the thread's loop: no row at all)
+    except UnicodeDecodeError:
+        return out
+    piece = buffer
+    try:
+        if piece.startswith(REAL_PREFIX) or piece.startswith("{"):    # :116-118
+            if piece.startswith(DATA_PREFIX):                          # :120-121
+                piece = piece[len(DATA_PREFIX):].strip()
+            doc = loads(piece)                                         # :123
+            if "choices" in doc:                                       # :124-133
+                for choice in doc["choices"]:
+                    if "delta" in choice and "content" in choice["delta"]:
+                        frag = choice["delta"]["content"]
+                        if frag:
+                            accum += frag
+                    elif "message" in choice and "content" in choice["message"]:
+                        frag = choice["message"]["content"]
+                        if frag:
+                            accum += frag
+            if "usage" in doc:                                         # :134-135
+                usage = token_usage(doc)
+            if "error" in doc:                                         # :137-139
+                accum += piece
+                out.rows.append(dict(usage)); out.transcripts.append(accum)
+    except Exception:                                                  # :140-141
+        pass
+    out.rows.append(dict(usage)); out.transcripts.append(accum)       # :150
+    return out
+
+
 def run_stream(chunks: list[bytes], http_status: int = 200, loads=json.loads):
     """Whole per-stream hot path: relay then tap. Returns (RelayResult, TapResult)."""
     relay = RelayOracle(loads).run(chunks, http_status)

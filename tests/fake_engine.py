@@ -69,3 +69,29 @@ class FakeEngine:
 
     def rewrite_bodies(self, bodies, plan_idx, slot_cap=None, with_matched=False):
         return self._body.rewrite_bodies(bodies, plan_idx, slot_cap, with_matched)
+
+    def scan_bodies(self, bodies, model_cap: int = 256):
+        from llmapigateway_b200.rewrite import SCAN_DTYPE
+        scans = np.zeros(len(bodies), dtype=SCAN_DTYPE)
+        texts = []
+        for i, b in enumerate(bodies):
+            sc, model = hm.scan_body(bytes(b), model_cap)
+            scans[i] = sc
+            texts.append(model)
+        return scans, texts
+
+    def rewrite_packed(self, buf, off, plan_idx, slot_cap, out=None):
+        from llmapigateway_b200.rewrite import RESULT_DTYPE
+        bodies = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+        rows = self._body.rewrite_bodies(bodies, plan_idx, slot_cap, True)
+        res = np.zeros(len(rows), dtype=RESULT_DTYPE)
+        out_off = np.zeros(len(rows) + 1, dtype=np.uint64)
+        blobs = []
+        for i, (st, b, matched, root) in enumerate(rows):
+            res[i] = (st, len(b), matched, root)
+            blobs.append(b)
+            out_off[i + 1] = out_off[i] + len(b)
+        return np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8), out_off, res
+
+    def details(self, slots, stride=None):
+        return [self.detail(s) for s in slots]

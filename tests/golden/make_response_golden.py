@@ -52,15 +52,52 @@ CASES = [
 ]
 
 
+# texts handed straight to the response tap in its non-streaming mode (chat_logging.py:98-150 with is_real_streaming=False):
+# what the client of a non-streaming request receives (the compact body above), error bodies of the endpoint, odd shapes
+TAP_TEXTS = [
+    b'{"id":"r","choices":[{"index":0,"message":{"role":"assistant","content":"hi"}}],"usage":{"prompt_tokens":10,"completion_tokens":7,"total_tokens":17,"cost":0.00123,'
+    b'"completion_tokens_details":{"reasoning_tokens":2},"prompt_tokens_details":{"cached_tokens":4}},"model":"m-ok","provider":"P"}',
+    b'{"choices":[{"message":{"content":"x"}}],"usage":{"prompt_tokens":3,"completion_tokens":2,"total_tokens":5}}',
+    b'{"choices":[{"message":{"content":"x"}}]}',
+    b'{"detail":"All configured providers failed for model \'m\'. Last error: boom"}',
+    b'{"detail":"Missing \'model\' in request body."}',
+    b'{"usage":null,"model":"m"}',
+    b'{"usage":{"prompt_tokens":1,"completion_tokens_details":null},"model":"m"}',
+    b'{"usage":{"prompt_tokens":1.5,"completion_tokens":9,"completion_tokens_details":{"reasoning_tokens":3}},"provider":"Q"}',
+    b'{"choices":[{"delta":null}],"usage":{"prompt_tokens":1}}',
+    b'{"choices":"abc","usage":{"prompt_tokens":1}}',
+    b'{"error":{"message":"late"},"usage":{"prompt_tokens":4}}',
+    b'{"usage":{"prompt_tokens":4},"error":null}',
+    b'data: {"usage":{"prompt_tokens":8},"model":"via-data-prefix"}  ',
+    b' {"usage":{"prompt_tokens":8}}',
+    b'[{"usage":{"prompt_tokens":8}}]',
+    b'{"usage":{"prompt_tokens":8}}\n\n{"usage":{"prompt_tokens":9}}',
+    b'not json at all',
+    b'',
+    b'{"usage":{"prompt_tokens":2,"cost":1e-7},"model":"caf\xc3\xa9","provider":"\\u00e9"}',
+]
+
+
 def main():
     out = []
     for status, content in CASES:
         r = ref_driver.run_nonstream(content, status)
-        out.append({"status": status, "content": base64.b64encode(content).decode(), "kind": r["kind"],
-                    "detail": r["detail"], "body": base64.b64encode(r["body"]).decode()})
+        case = {"status": status, "content": base64.b64encode(content).decode(), "kind": r["kind"],
+                "detail": r["detail"], "body": base64.b64encode(r["body"]).decode()}
+        if r["kind"] == "ok":                                       # the tap sees what the client receives
+            case["tap_rows"] = ref_driver.run_tap([r["body"]], is_real_streaming=False)[0]
+        out.append(case)
+    tap = []
+    for text in TAP_TEXTS:
+        rows = ref_driver.run_tap([text], is_real_streaming=False)[0] if text else []
+        tap.append({"text": base64.b64encode(text).decode(), "rows": rows})
+    # split deliveries: the tap concatenates the chunks first (:98-103)
+    whole = TAP_TEXTS[0]
+    tap.append({"text": base64.b64encode(whole).decode(), "chunks": [base64.b64encode(whole[:37]).decode(), base64.b64encode(whole[37:]).decode()],
+                "rows": ref_driver.run_tap([whole[:37], whole[37:]], is_real_streaming=False)[0]})
     import httpx
     import starlette
-    doc = {"generator": "tests/golden/make_response_golden.py", "httpx": httpx.__version__, "starlette": starlette.__version__, "cases": out}
+    doc = {"generator": "tests/golden/make_response_golden.py", "httpx": httpx.__version__, "starlette": starlette.__version__, "cases": out, "tap_cases": tap}
     (HERE / "response_cases.json").write_text(json.dumps(doc, indent=0))
     print("wrote", len(out), "cases:", [c["kind"] for c in out])
 

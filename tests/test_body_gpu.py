@@ -250,3 +250,49 @@ def test_scan_reference_parse_goldens(engine):
         assert int(sc["status"]) == want, raw
         if want == 0 and p["is_streaming"] is not None:
             assert bool(sc["stream_truthy"]) == p["is_streaming"], raw
+
+
+def test_nonstream_response_tap(engine):
+    """Row a8, non-stream mode (chat_logging.py:98-150): usage rows of non-streaming responses through lgw_documents_usage against the
+    rows the unmodified ChunkProcessorThread wrote (goldens) and against the oracle on fuzzed documents."""
+    from golden_io import canon_rows
+    from oracle.sse_oracle import tap_nonstream
+    doc = json.loads((GOLDEN / "response_cases.json").read_text())
+    texts, want = [], []
+    for c in doc["tap_cases"]:
+        if c["text"]:
+            texts.append(base64.b64decode(c["text"])); want.append(c["rows"])
+    for c in doc["cases"]:
+        if "tap_rows" in c:
+            texts.append(base64.b64decode(c["body"])); want.append(c["tap_rows"])
+    got = engine.documents_usage(texts)
+    n_cmp = 0
+    for t, (rows, exotic), w in zip(texts, got, want):
+        if exotic:
+            continue
+        assert canon_rows(rows) == canon_rows(w), t[:100]
+        n_cmp += 1
+    assert n_cmp >= len(texts) - 3
+    rng = random.Random(99)
+    fuzz = []
+    for it in range(1500):
+        d = bc.rand_body(rng)
+        if it % 3 == 0:
+            d["usage"] = rng.choice([{"prompt_tokens": rng.randrange(10**6), "completion_tokens": rng.randrange(10**5), "total_tokens": rng.randrange(10**6),
+                                      "cost": rng.choice([0, 1.5e-5, 0.25, 3]), "completion_tokens_details": rng.choice([{"reasoning_tokens": rng.randrange(50)}, None, {}]),
+                                      "prompt_tokens_details": {"cached_tokens": rng.randrange(9)}}, None, [], "x", {"prompt_tokens": None}])
+        if it % 5 == 0:
+            d["choices"] = rng.choice([[{"message": {"content": "hi"}}], [{"delta": None}], "str", [], [{"message": {"content": 5}}], None])
+        if it % 11 == 0:
+            d["error"] = rng.choice([None, {"message": "x"}])
+        if it % 4 == 0:
+            d["model"] = rng.choice(["m", "café", 5, None]); d["provider"] = "P"
+        fuzz.append(bc.spell(rng, d, plain_keys=True).encode("utf-8"))
+    got = engine.documents_usage(fuzz)
+    n_ok = 0
+    for t, (rows, exotic) in zip(fuzz, got):
+        if exotic:
+            continue
+        assert canon_rows(rows) == canon_rows(tap_nonstream([t]).rows), t[:200]
+        n_ok += 1
+    assert n_ok > 1300

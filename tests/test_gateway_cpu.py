@@ -147,3 +147,203 @@ def test_non_streaming_seam_matches_reference_goldens():
                     assert err == d
         assert seen and all(s == payload for s in seen)          # the bytes on the wire are the engine's bytes
     asyncio.run(go())
+
+
+# ---- config 4: the fallback-chain walker (host logic over the fake engine; the GPU twin is tests/test_chain_gpu.py) -----------
+def test_chain_walker_matches_the_reference_goldens():
+    """llmapigateway_b200.chat.chat_completions against the goldens of the unmodified chat.py:20: relayed bytes, 503/400
+    status + detail, url / wire body / headers of every upstream attempt (rotation, retries with the log scrub, sub-providers)."""
+    import chain_cases as cc
+    from fake_engine import FakeEngine
+    doc, ups = cc.load()
+    cases = doc["cases"]
+    got = cc.walk_product(lambda: FakeEngine(max_streams=8), cases, ups)
+    for case, g in zip(cases, got):
+        cc.check_against_golden(case, g)
+
+
+def test_chain_batch_matches_the_oracle():
+    """ChainBatch (lock-step rounds) == the per-request oracle walk: served-by round, relayed bytes, 503 details, attempt count."""
+    from fake_engine import FakeEngine
+    from llmapigateway_b200 import chat, rewrite, synth
+    from oracle import chain_oracle
+    import chain_cases as cc
+    n = 48
+    providers, rules, fallback_provider = synth.chain_world()
+    up = synth.ChainUpstream(n, 5, seed=4, p_fail=0.4)
+    bodies = synth.chain_request_bodies(n, seed=4)
+    bodies[7] = b'{"messages":[]}'
+    bodies[9] = b'{"model":"gw/rotating","stream":true,"messages":[]}'
+    bodies[11] = b'{"model":"gw/rotating","stream":true,"messages":[]}'
+    bodies[13] = b'{"model":"gw/retrying","stream":true,"messages":[{"role":"user","content":"x"}]}'
+    eng = FakeEngine(max_streams=n)
+    plans = rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode())
+    eng.load_rules(plans)
+    out = chat.ChainBatch(eng, plans, providers, rules).run(bodies, ["k"] * n, up)
+    rot = chain_oracle.Rotation()
+    n_attempts = 0
+    for i in range(n):
+        want = chain_oracle.walk(bodies[i], {"Authorization": "Bearer k"}, providers, rules, fallback_provider, lambda a: up.stream_chunks(i, a), rot, cc.stream_mode())
+        n_attempts += len(want["attempts"])
+        if want["kind"] == "stream":
+            assert out.served_round[i] == len(want["attempts"]) - 1, i
+            assert out.emitted(i) == want["emitted"], i
+            assert out.detail[i] is None
+        else:
+            assert out.served_round[i] < 0 and out.detail[i] == want["detail"], (i, out.detail[i], want["detail"])
+    assert out.attempts == n_attempts
+    rows = dict(out.usage_rows())
+    assert set(rows) == {i for i in range(n) if out.served_round[i] >= 0}
+
+
+# ---- ADVICE round 1: cancellation, hostile usage values, raising sinks ------------------------------------------------------
+def test_cancelled_feed_never_reaches_the_next_user_of_the_slot():
+    """A client disconnect cancels the coroutine awaiting feed(); its queued chunk must not be packed into the stream that
+    gets the slot next (it would corrupt that stream's priming verdict), and slots are reused first-in first-out."""
+    async def go():
+        eng = FakeEngine(max_streams=2)
+        seen = []
+        real_step = eng.step
+
+        def spy(data, chunk_off, seg_chunk, seg_slot, out=None):
+            seen.append([(int(s), bytes(data[int(chunk_off[int(seg_chunk[k])]):int(chunk_off[int(seg_chunk[k + 1])])])) for k, s in enumerate(seg_slot)])
+            return real_step(data, chunk_off, seg_chunk, seg_slot)
+
+        eng.step = spy
+        b = StreamBatcher(eng, window_s=0.02)
+        a = await b.open_stream(200)
+        t = asyncio.ensure_future(b.feed(a, b'data: {"error":"poison"}\n\n'))
+        await asyncio.sleep(0)                       # queued, pump sleeping in its window
+        t.cancel()
+        await b.close_stream(a)                      # request torn down before the step ran
+        other = await b.open_stream(200)
+        assert other != a                            # FIFO free list: the slot just released is the last to be reused
+        again = await b.open_stream(200)
+        assert again == a
+        r = await b.feed(again, b'data: {"choices":[{"delta":{"content":"hi"}}]}\n\n')
+        assert r.emitted is not None and r.phase != 3
+        assert all(b"poison" not in blob for step in seen for _, blob in step)
+        assert b.dropped_stale >= 0
+        await b.close_stream(again); await b.close_stream(other)
+    asyncio.run(go())
+
+
+def test_stale_chunk_queued_for_a_closed_slot_is_dropped():
+    async def go():
+        eng = FakeEngine(max_streams=1)
+        b = StreamBatcher(eng, window_s=0.02)
+        a = await b.open_stream(200)
+        t = asyncio.ensure_future(b.feed(a, b'data: {"detail":"stale"}\n\n'))
+        await asyncio.sleep(0)
+        await b.close_stream(a)                      # purges the queue entry of the slot
+        with pytest.raises(asyncio.CancelledError):
+            await t
+        a2 = await b.open_stream(200)
+        r = await b.feed(a2, b'data: {"choices":[]}\n\n')
+        assert r.phase != 3                           # not FAILED: the stale error event never reached this stream
+        await b.close_stream(a2)
+    asyncio.run(go())
+
+
+def test_raising_sink_and_hostile_usage_values_do_not_stall_streams():
+    class Bad:
+        def insert_usage(self, u):
+            raise RuntimeError("sink down")
+
+    async def go():
+        batcher = StreamBatcher(FakeEngine(max_streams=8), window_s=0.0005, usage_sink=Bad())
+        case = next(c for c in CASES if not c["failed"] and c["rows"])
+        got = await asyncio.wait_for(_drive(case, batcher, _Sink()), 20)
+        assert got["emitted"] == case["emitted"]
+    asyncio.run(go())
+
+
+def test_usage_table_rejects_what_it_cannot_hold_and_stays_usable():
+    from llmapigateway_b200.usage import UsageTable
+    t = UsageTable.__new__(UsageTable)
+    UsageTable.__init__(t, engine=None) if False else None
+    import numpy as np
+    t.eng = None; t._lib = None
+    t._host = {c: np.zeros(0, dtype=d) for c, d in zip(UsageTable.COLS, UsageTable.DTYPES)}
+    t._models, t._providers, t._dev, t._pending_rows, t.rejected = [], [], None, [], 0
+    assert t.insert_usage({"prompt_tokens": 1, "completion_tokens": 2, "total_tokens": 3, "cost": 0.5, "model": "m"})
+    assert t.insert_usage({"prompt_tokens": None, "completion_tokens": None, "total_tokens": None, "cost": None, "model": None})
+    assert not t.insert_usage({"prompt_tokens": 2 ** 31})
+    assert not t.insert_usage({"prompt_tokens": "7"})
+    assert not t.insert_usage({"prompt_tokens": object()})
+    assert t.insert_usage({"prompt_tokens": 2.0, "model": 17})
+    assert t.rejected == 3 and len(t) == 3
+    t._materialise()
+    assert t._host["prompt_tokens"].tolist() == [1, 0, 2] and t._models == ["m", None, "17"]
+    assert t.insert_usage({"prompt_tokens": 4})
+    t._materialise()
+    assert t._host["prompt_tokens"].tolist() == [1, 0, 2, 4]
+
+
+def test_sqlite_sink_stores_what_the_reference_stores(tmp_path):
+    """SqliteUsageSink against tokens_usage_db.py:118 `insert_usage` run unmodified (tests/golden/usage_sink_cases.json): same
+    schema, same stored value and storage class per column, and the same rows lost (values SQLite cannot bind)."""
+    import sqlite3
+    from llmapigateway_b200.gateway import SqliteUsageSink
+    doc = json.loads((ROOT / "tests" / "golden" / "usage_sink_cases.json").read_text())
+    sink = SqliteUsageSink(str(tmp_path / "u.db"))
+    sink.insert_many(doc["rows"][:4])
+    for r in doc["rows"][4:]:
+        sink.insert_usage(r)
+    conn = sqlite3.connect(str(tmp_path / "u.db"))
+    cols = ["prompt_tokens", "completion_tokens", "total_tokens", "reasoning_tokens", "cached_tokens", "cost", "model", "provider"]
+    sel = ", ".join(f"{c}, typeof({c})" for c in cols)
+    assert [list(r) for r in conn.execute(f"SELECT {sel} FROM tokens_usage ORDER BY id")] == doc["stored"]
+    assert [list(r[1:4]) for r in conn.execute("PRAGMA table_info(tokens_usage)")] == doc["schema"]
+    ts = [r[0] for r in conn.execute("SELECT timestamp FROM tokens_usage")]
+    from datetime import datetime
+    assert all(datetime.fromisoformat(t) for t in ts)
+
+
+def test_stats_window_matches_the_reference():
+    from datetime import datetime
+    from llmapigateway_b200.usage import stats_window
+    doc = json.loads((ROOT / "tests" / "golden" / "usage_sink_cases.json").read_text())
+    now = datetime.fromisoformat(doc["now"])
+    for period, (start, end) in doc["windows"].items():
+        s, e = stats_window(period, now)
+        assert [s.isoformat(), e.isoformat()] == [start, end], period
+
+
+def test_nonstream_responses_are_tapped_by_the_middleware_mirror():
+    """log_chat_completions (chat_logging.py:165-231 seam): non-streaming responses of /chat/completions are collected and handed
+    to the engine's document tap; streams the engine already tapped and other routes pass through untouched."""
+    import types
+    from llmapigateway_b200.gateway import log_chat_completions
+
+    class Eng(FakeEngine):
+        def documents_usage(self, docs):
+            return [([{"prompt_tokens": len(d)}], False) for d in docs]
+
+    async def go():
+        sink = _Sink()
+        b = StreamBatcher(Eng(max_streams=2), usage_sink=sink)
+
+        async def chunks():
+            yield b'{"usage":'
+            yield b'{"prompt_tokens":1}}'
+
+        resp = types.SimpleNamespace(headers={"content-type": "application/json"}, body_iterator=chunks())
+        req = types.SimpleNamespace(url=types.SimpleNamespace(path="/v1/chat/completions"))
+
+        async def call_next(_):
+            return resp
+
+        out = await log_chat_completions(req, call_next, batcher=b)
+        got = [c async for c in out.body_iterator]
+        assert b"".join(got) == b'{"usage":{"prompt_tokens":1}}' and sink.rows == [{"prompt_tokens": 29}]
+        tapped = types.SimpleNamespace(headers={"content-type": "text/event-stream"}, body_iterator=chunks(), lgw_tapped=True)
+
+        async def call_next2(_):
+            return tapped
+
+        assert (await log_chat_completions(req, call_next2, batcher=b)).body_iterator is tapped.body_iterator
+        other = types.SimpleNamespace(url=types.SimpleNamespace(path="/v1/models"))
+        assert await log_chat_completions(other, call_next, batcher=b) is resp
+        assert len(sink.rows) == 1
+    asyncio.run(go())

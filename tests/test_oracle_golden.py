@@ -37,3 +37,42 @@ def test_split_rule():
     assert split_events("a\n\n") == (["a", ""], "")
     assert split_events("a\n\n\n") == (["a", "\n"], "")
     assert split_events("a\n") == ([], "a\n")
+
+
+def test_nonstream_tap_oracle_matches_the_reference():
+    """chat_logging.py:98-150 with is_real_streaming=False: rows of tests/golden/response_cases.json (made by the unmodified
+    ChunkProcessorThread) against the restatement oracle.sse_oracle.tap_nonstream."""
+    import base64
+    import json
+    from golden_io import GOLDEN, canon_rows
+    from oracle.sse_oracle import tap_nonstream
+    doc = json.loads((GOLDEN / "response_cases.json").read_text())
+    assert len(doc["tap_cases"]) >= 20
+    for c in doc["tap_cases"]:
+        chunks = [base64.b64decode(x) for x in c["chunks"]] if "chunks" in c else ([base64.b64decode(c["text"])] if c["text"] else [])
+        assert canon_rows(tap_nonstream(chunks).rows) == canon_rows(c["rows"]), base64.b64decode(c["text"])[:80]
+    n = 0
+    for c in doc["cases"]:
+        if "tap_rows" in c:
+            assert canon_rows(tap_nonstream([base64.b64decode(c["body"])]).rows) == canon_rows(c["tap_rows"])
+            n += 1
+    assert n >= 8
+
+
+def test_chain_oracle_matches_the_reference():
+    """oracle.chain_oracle.walk against the goldens of the unmodified chat.py:20 `chat_completions` (config 4): relayed bytes,
+    503/400 status and detail, and the url / wire body / headers of every upstream attempt."""
+    import chain_cases as cc
+    from oracle import chain_oracle
+    from llmapigateway_b200 import synth
+    doc, ups = cc.load()
+    providers, rules, fallback_provider = synth.chain_world()
+    rot = chain_oracle.Rotation()
+    kinds = set()
+    for case in doc["cases"]:
+        up, sid = ups[case["group"]], case["sid"]
+        headers = {"Authorization": f"Bearer {case['api_key']}"} if case["api_key"] else {}
+        got = chain_oracle.walk(cc.D64(case["body"]), headers, providers, rules, fallback_provider, lambda a: up.stream_chunks(sid, a), rot, cc.stream_mode())
+        cc.check_against_golden(case, got)
+        kinds.add((case["kind"], case.get("status"), len(case["attempts"])))
+    assert ("http_exception", 503, 3) in kinds and ("stream", None, 1) in kinds and ("stream", None, 3) in kinds
