@@ -178,7 +178,273 @@ def run_reference_arm(args):
     _emit(line)
 
 
+def run_reference_side(args):
+    """`--impl reference --config c4|c5`: the reference's own code for that configuration on this box's host cores (oracle/_ref),
+    on a bounded sample sized for a few minutes."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import ref_arm
+    cores = ref_arm.effective_cores()
+    if args.config == "c4":
+        n_total = 8192
+        ids = list(range(0, n_total, max(1, n_total // (16 * cores))))[:16 * cores]
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, slowest, served = ref_arm.run_config4("B2", cores, ids, n_total, N_EVENTS)
+            if i >= args.warmup:
+                vals.append(v)
+        value = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": len(ids) * N_EVENTS / value * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "C4: 3-deep fallback rule chain, 20% injected upstream failure, 8192 concurrent streams", "streams_per_step": len(ids), "same_config": False},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                                 "sample": f"{len(ids)} of 8192 streams per step over {cores} processes: the UNMODIFIED chat.py:20 chat_completions (oracle/_ref) + make_llm_request + ChunkProcessorThread tap, MockTransport upstream, json5.loads -> C json.loads"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    else:
+        n = min(args.records, 1_000_000)
+        r = ref_arm.run_config5(n)
+        q = [r[k] for k in ("hour_window_s", "hour_all_s", "day_window_s", "day_all_s")]
+        value = n * len(q) / sum(q)
+        line = {"impl": "reference", "metric": "usage_rollup_records_per_sec", "value": value, "unit": "records/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                "ms_per_step": sum(q) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": "C5: usage-stats rollup", "records": n, "same_config": n == args.records, "queries": r},
+                "cpu_baseline": {"value": value, "unit": "records/s", "cores": 1, "kind": "reference",
+                                 "sample": f"{n} rows in a SQLite file, the UNMODIFIED TokensUsageDB.get_aggregated_usage (tokens_usage_db.py:222) for hour/day, endpoint window and whole table; load time {r['load_s']:.1f} s not counted"},
+                "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    _emit(line)
+
+
 _RESULT_FD = None
+
+
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    return world, rank, local, dev, barrier, max_over_ranks, sum_over_ranks
+
+
+def run_c4(args):
+    """BASELINE configs[3]: 8 192 concurrent streaming requests, a 3-rule fallback chain each, every upstream attempt failing
+    independently with p = 0.2.  Streams go to GPUs by shard_of(stream_id, N) (strong scaling: the total is
+    fixed); no collective on the data path.  One step = the whole walk of this rank's requests through ChainBatch: request scan,
+    per-round body rewrite with the attempt's plan, one SSE step per round over what the upstreams streamed, error details of
+    the failed first events, usage rows of the served streams -- HOST buffers in, host buffers out (this config has no
+    device-resident form: the walk is host-driven by design)."""
+    import torch.distributed as dist
+    import llmapigateway_b200 as L
+    from llmapigateway_b200 import chat, rewrite, synth
+    from llmapigateway_b200.gateway import shard_of
+    world, rank, local, dev, barrier, max_over_ranks, sum_over_ranks = _dist_setup()
+    S, E = (8192 if args.streams == N_STREAMS else args.streams), args.events
+    W, K = max(args.warmup, 3), args.steps
+    providers, rules, fallback_provider = synth.chain_world()
+    os.environ.setdefault("ALPHA_KEY_ENV", "sk-alpha-from-env")
+    up = synth.ChainUpstream(S, E, seed=4, p_fail=0.2)
+    mine = np.array([i for i in range(S) if shard_of(i, world) == rank])
+    all_bodies = synth.chain_request_bodies(S, seed=4)
+    bodies = [all_bodies[i] for i in mine]
+    n = len(mine)
+    eng = L.Engine(device=local, max_streams=max(n, 1), max_step_chunks=n * (E + 2) + 64, max_step_bytes=n * (E * EVENT_BYTES + 512) + 4096)
+    import httpx
+    mode = "httpx028" if tuple(int(x) for x in httpx.__version__.split(".")[:2]) >= (0, 28) else "httpx027"
+    plans = rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=mode)
+    eng.load_rules(plans)
+    up.prepare(mine, 3, alloc=eng.alloc_pinned)
+    walker = chat.ChainBatch(eng, plans, providers, rules)
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(W):
+        out = walker.run(bodies, None, up, stream_ids=mine)
+    barrier()
+    l0 = eng.launch_count()
+    times = []
+    for _ in range(K):
+        barrier()
+        t0 = time.perf_counter()
+        out = walker.run(bodies, None, up, stream_ids=mine)
+        eng.sync()
+        times.append(time.perf_counter() - t0)
+    barrier()
+    launches = eng.launch_count() - l0
+    sampler.stop()
+    # correctness of the timed configuration (not timed): served-by round == first non-failing attempt, bytes == the upstream's
+    kind = up.kind[:3, mine]
+    first_ok = np.where((kind == 0).any(axis=0), (kind == 0).argmax(axis=0), -1)
+    assert np.array_equal(out.served_round, first_ok.astype(np.int32)), "served-by round differs from the injected failure schedule"
+    b = up.batch; co = b.chunk_off.astype(np.int64)
+    for k in range(0, n, max(1, n // 64)):
+        if first_ok[k] >= 0:
+            s = int(mine[k]); lo, hi = int(co[b.seg_chunk[s]]), int(co[b.seg_chunk[s + 1]])
+            assert out.emitted(k) == b.data[lo:hi].tobytes()
+    step_s = max_over_ranks(float(np.mean(times)))
+    relayed = sum_over_ranks(float(out.chunks_relayed))
+    delta_events = sum_over_ranks(float((first_ok >= 0).sum() * E))
+    attempts = sum_over_ranks(float(out.attempts))
+    failed503 = sum_over_ranks(float((first_ok < 0).sum()))
+    per_gpu = delta_events / world / step_s
+    in_bytes = sum(int(a.data.size) for _, a in up.prepared.values()) + sum(len(x) for x in bodies)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = _peaks()
+    value = delta_events / step_s
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_s * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C4: 3-deep fallback rule chain, 20% injected upstream failure, 8192 concurrent streams sharded across the GPUs by shard_of(stream_id, N)",
+                       "streams_total": S, "streams_rank0": n, "events_per_stream": E, "p_fail": 0.2, "failure_kinds": ["http500+text", "first event error", "first event detail"],
+                       "counts": "chunks = the 64-B delta events of the streams that were served (the usage event and [DONE] of each are relayed too, not counted)",
+                       "l2": "inputs larger than L2 at N<=2 (270 MB per walk); host buffers every step, nothing cached on the device between steps",
+                       "parallelism": f"streams sharded x{world}, no collective"},
+            "chunks_relayed_incl_tail": relayed, "attempts": attempts, "exhausted_503": failed503, "per_gpu_chunks_per_s": per_gpu,
+            "json_gbs": value * EVENT_BYTES / 1e9, "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": value, "unit": UNIT, "ms_per_step": step_s * 1e3, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
+                    "note": "the walk is host-driven: `value` IS the end-to-end number (pinned host buffers -> device -> pinned host buffers every round)"},
+            "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                         "note": "host-driven walk: PCIe and Python control bound, see the C3 line for the kernel roofline"}}
+    _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c5(args):
+    """BASELINE configs[4]: usage-stats rollup of 10 M extracted usage records -> per-hour / per-day x model aggregation, 1 vs N GPUs.
+    Records are partitioned by contiguous row ranges over the ranks (strong scaling); every rank accumulates its records into a
+    dense (bucket x model) table of 64-bit integer cells, ONE all-reduce(sum) over that table is the exchange step,
+    rank 0 compacts the rows.  A step = the `hour` and the `day` rollup, each over the window the stats endpoint asks for
+    (stats.py:46-55: 24 h / 2 weeks) AND over the whole table (no window: the worst case for the table size)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from datetime import datetime, timedelta
+    import llmapigateway_b200 as L
+    from llmapigateway_b200 import usage as U
+    world, rank, local, dev, barrier, max_over_ranks, sum_over_ranks = _dist_setup()
+    n = args.records
+    W, K = max(args.warmup, 3), args.steps
+    end = datetime(2026, 9, 21, 6, 57, 17, 47518)
+    ts, models, tok, cost = U.synth_usage_columns(n, seed=5, end=end)
+    names = sorted({m for m in models if m is not None})
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    eng = L.Engine(device=local, max_streams=64, max_step_chunks=1024, max_step_bytes=1 << 20)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    tab = U.UsageTable(eng)
+    tab.load_columns(ts[lo:hi], list(models[lo:hi]), *[t[lo:hi] for t in tok], cost[lo:hi], names=names)
+    tab._upload()
+    t_min, t_max = int(ts.min()), int(ts.max())
+    nm = len(names) + 1
+    lib = tab._lib
+    queries = []
+    for period in ("hour", "day"):
+        s0, e0 = U.stats_window(period, end)
+        for label, start, stop in ((period + "_window", s0, e0), (period + "_all", None, None)):
+            p = U.PERIODS[period]
+            qlo = max(t_min, U.to_us(start)) if start is not None else t_min
+            qhi = min(t_max, U.to_us(stop)) if stop is not None else t_max
+            b0 = int(lib.lgw_rollup_bucket_of(qlo, p)); b1 = int(lib.lgw_rollup_bucket_of(qhi, p))
+            nb = b1 - b0 + 1 + (25 if period == "hour" else 1)
+            queries.append(dict(label=label, period=period, start=start, end=stop, b0=b0, nb=nb, groups=nb * nm,
+                                table=torch.zeros(nb * nm * U.ROLLUP_CELLS, dtype=torch.int64, device=dev),
+                                inexact=torch.zeros(nb * nm, dtype=torch.int32, device=dev), oob=torch.zeros(2, dtype=torch.int32, device=dev)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one(q, timed=None):
+        with torch.cuda.stream(stream):
+            q["table"].zero_(); q["inexact"].zero_(); q["oob"].zero_()
+            flush.fill_(1)                                 # evict L2 (not timed)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            tab.accumulate(q["period"], q["start"], q["end"], q["b0"], q["nb"], nm, C.c_void_p(q["table"].data_ptr()),
+                           C.c_void_p(q["inexact"].data_ptr()), C.c_void_p(q["oob"].data_ptr()))
+            e1.record(stream)
+            if world > 1:
+                dist.all_reduce(q["table"], op=dist.ReduceOp.SUM)
+                dist.all_reduce(q["inexact"], op=dist.ReduceOp.MAX)
+            rows = tab.emit(q["b0"], q["nb"], nm, C.c_void_p(q["table"].data_ptr()), C.c_void_p(q["inexact"].data_ptr())) if rank == 0 else None
+            e2.record(stream)
+        torch.cuda.synchronize(dev)
+        if timed is not None:
+            timed.append((e0.elapsed_time(e1), e0.elapsed_time(e2)))
+        return rows
+
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(W):
+        for q in queries:
+            one(q)
+    barrier()
+    l0 = eng.launch_count()
+    per_q = {q["label"]: [] for q in queries}
+    rows_of = {}
+    for _ in range(K):
+        for q in queries:
+            barrier()
+            rows_of[q["label"]] = one(q, per_q[q["label"]])
+    barrier()
+    launches = eng.launch_count() - l0
+    sampler.stop()
+    res = {}
+    for q in queries:
+        acc = max_over_ranks(float(np.mean([t[0] for t in per_q[q["label"]]])))
+        tot = max_over_ranks(float(np.mean([t[1] for t in per_q[q["label"]]])))
+        res[q["label"]] = dict(groups=q["groups"], accum_ms=acc, total_ms=tot, records_per_s=n / (tot / 1e3),
+                               accum_gbs_rank=40.0 * (hi - lo) / (acc / 1e3) / 1e9, path="privatised (shared memory)" if q["groups"] <= 2560 else "global 64-bit reductions")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # correctness of the timed configuration (not timed): conservation against the host columns
+    for q in queries:
+        rows = rows_of[q["label"]]
+        sel = np.ones(n, bool)
+        if q["start"] is not None:
+            sel = (ts >= U.to_us(q["start"])) & (ts <= U.to_us(q["end"]))
+        assert int(rows["count"].sum()) == int(sel.sum()), (q["label"], int(rows["count"].sum()), int(sel.sum()))
+        assert int(rows["prompt_tokens"].sum()) == int(tok[0][sel].astype(np.int64).sum())
+        assert int(rows["cached_tokens"].sum()) == int(tok[4][sel].astype(np.int64).sum())
+    peak, peak_src = _peaks()
+    step_ms = sum(r["total_ms"] for r in res.values())
+    head = res["day_window"]
+    value = n * len(res) / (step_ms / 1e3)
+    achieved = head["accum_gbs_rank"]
+    line = {"metric": "usage_rollup_records_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "C5: usage-stats rollup, 10M extracted usage records -> per-hour/day x model aggregation (SURVEY 8(d) C5: 400-day window, 64 models Zipf 1.1 + 1% NULL)",
+                       "records_total": n, "records_rank0": hi - lo, "step": "4 rollups: hour and day, each over the stats endpoint's window (24 h / 2 weeks) and over the whole table",
+                       "l2": "flushed: 256 MiB written on the stream before every rollup (not timed)", "parallelism": f"row ranges x{world}; one all-reduce(sum) of the dense table per rollup"},
+            "rollups": res, "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(sum(len(rows_of[q["label"]]) for q in queries) * U.ROW_DTYPE.itemsize),
+                    "note": "records are device-resident by design (ingested once, queried many times); the result rows are copied to the host inside the timed region"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_rollup_accum_smem + k_rollup_merge on the `day` window (40 B algorithmic per record, SURVEY 8(d)); the other rollups are in `rollups`"}}
+    _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _emit(line: dict) -> None:
@@ -199,6 +465,10 @@ def main():
     ap.add_argument("--events", type=int, default=N_EVENTS)
     ap.add_argument("--mode", type=int, default=0, help="0 bulk kernel (default), 1 exact sequential path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 (default): BASELINE configs[2], the headline; c4: 3-deep fallback chain with 20 %% injected failure, 8192 streams "
+                         "sharded over the GPUs (strong scaling); c5: usage rollup of 10 M records, 1 vs N GPUs")
+    ap.add_argument("--records", type=int, default=10_000_000)
     args = ap.parse_args()
     # stdout carries exactly one line, the JSON result: everything else that writes to fd 1 during the run (NCCL's
     # version banner, library chatter of child processes) is sent to stderr
@@ -207,7 +477,11 @@ def main():
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args) if args.config == "c3" else run_reference_side(args)
+    if args.config == "c4":
+        return run_c4(args)
+    if args.config == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist

@@ -226,6 +226,9 @@ int lgw_usage_rollup_emit(lgw_engine* e, const uint64_t* d_table, const uint32_t
 /* bucket index of one timestamp (host helper, same arithmetic as the kernel) */
 int64_t lgw_rollup_bucket_of(int64_t ts_us, int period);
 /* device time of the last accum / emit kernels, milliseconds */
+/* accumulate path: 0 (default) block-privatised shared-memory tables whenever bucket x model groups <= 2560 (every window
+ * the stats endpoint asks for, stats.py:46-55), global 64-bit reductions else; 1 forces the global path (tests, measurements) */
+int lgw_rollup_set_path(lgw_engine* e, int force_global);
 int lgw_rollup_last_ms(lgw_engine* e, float ms[2]);
 
 /* ---- request-body rewrite: SURVEY 8 rows a1, a3, a4 --------------------------------------------------

@@ -260,6 +260,16 @@ class ChainBatch:
         self.eng, self.plans, self.providers, self.rules = engine, plans, providers_config, fallback_rules
         self.rotation = rotation or ModelRotation()
         self._sched_cache: dict = {}
+        self._arenas: dict = {}                 # round -> pinned egress buffer (lgw_alloc_pinned), grown on demand, reused across runs
+
+    def _arena(self, rnd: int, nbytes: int):
+        alloc = getattr(self.eng, "alloc_pinned", None)
+        if alloc is None or nbytes == 0:
+            return None
+        a = self._arenas.get(rnd)
+        if a is None or a.size < nbytes:
+            a = self._arenas[rnd] = alloc(nbytes)
+        return a[:nbytes]
 
     def _schedule(self, requested_model: str, start: int):
         """The full attempt list of one request: [(plan index, url, rule, sub_provider)] in chat.py's order."""
@@ -372,7 +382,8 @@ class ChainBatch:
             if m:
                 slots = np.arange(m, dtype=np.uint32)
                 eng.open(slots, np.full(m, 200, np.int32))
-                r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots)
+                arena = self._arena(rnd, int(ans.data.size))
+                r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots, **({"out": arena} if arena is not None else {}))
                 out.steps += 1
                 out.round_out[-1] = r.out
                 phase, verdict, eb = r.segs["phase"], r.segs["verdict"], r.segs["emit_chunk_begin"].astype(np.int64)

@@ -44,6 +44,8 @@ struct lgw_engine {
     cudaEvent_t rev[4]{};
     float rms[2]{0, 0};
     RollupRow* d_rows = nullptr; uint64_t d_rows_cap = 0; unsigned long long* d_nrows = nullptr;
+    uint8_t* d_partial = nullptr; size_t d_partial_cap = 0; uint32_t* d_tiles = nullptr; uint32_t d_tiles_cap = 0;
+    bool rollup_attr_set = false, rollup_force_global = false;
     float ms[5]{0, 0, 0, 0, 0};     // prime, relay, commit, usage extract, whole host-buffer step
     bool timed = false;
     uint64_t launches = 0;
@@ -130,7 +132,7 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     scratch_free(e->scratch);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->rev) if (ev) cudaEventDestroy(ev);
-    cudaFree(e->d_rows); cudaFree(e->d_nrows);
+    cudaFree(e->d_rows); cudaFree(e->d_nrows); cudaFree(e->d_partial); cudaFree(e->d_tiles);
     cudaFree(e->d_plans); cudaFree(e->d_ops); cudaFree(e->d_blob);
     cudaFree(e->b_in); cudaFree(e->b_slots); cudaFree(e->b_out); cudaFree(e->b_models); cudaFree(e->b_off); cudaFree(e->b_out_off);
     cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans); cudaFree(e->b_redo);
@@ -420,8 +422,29 @@ extern "C" int lgw_usage_rollup_accum(lgw_engine* e, const int64_t* d_ts_us, con
     a.start_us = start_us; a.end_us = end_us; a.has_start = has_start; a.has_end = has_end;
     a.bucket0 = bucket0; a.n_buckets = n_buckets; a.n_models = n_models;
     a.table = (unsigned long long*)d_table; a.inexact = d_inexact; a.oob = d_oob;
+    const uint64_t groups = (uint64_t)n_buckets * n_models;
+    const bool privatised = groups <= LGW_ROLLUP_SMEM_GROUPS && n >= 65536 && !e->rollup_force_global;
+    if (privatised) {                     // scratch for the per-block partial tables (allocated outside the timed region)
+        const size_t need = (size_t)e->sm_count * groups * (LGW_ROLLUP_CELLS * 8 + 4);
+        if (need > e->d_partial_cap) {
+            cudaFree(e->d_partial); e->d_partial = nullptr; e->d_partial_cap = 0;
+            CK(e, cudaMalloc((void**)&e->d_partial, need));
+            e->d_partial_cap = need;
+        }
+        if (!e->rollup_attr_set) {
+            CK(e, cudaFuncSetAttribute(k_rollup_accum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollup_smem_bytes(LGW_ROLLUP_SMEM_GROUPS)));
+            e->rollup_attr_set = true;
+        }
+    }
     CK(e, cudaEventRecord(e->rev[0], e->stream));
-    if (n) {
+    if (n && privatised) {
+        const unsigned grid = (unsigned)e->sm_count;
+        unsigned long long* partial = (unsigned long long*)e->d_partial;
+        uint32_t* pflag = (uint32_t*)(e->d_partial + (size_t)grid * groups * LGW_ROLLUP_CELLS * 8);
+        k_rollup_accum_smem<<<grid, 1024, rollup_smem_bytes((uint32_t)groups), e->stream>>>(a, partial, pflag);
+        k_rollup_merge<<<(unsigned)((groups * LGW_ROLLUP_CELLS + 255) / 256), 256, 0, e->stream>>>(partial, pflag, grid, (uint32_t)groups, a.table, a.inexact);
+        e->launches += 2;
+    } else if (n) {
         const uint64_t want = (n + 255) / 256;
         const unsigned grid = (unsigned)(want < (uint64_t)e->sm_count * 16 ? want : (uint64_t)e->sm_count * 16);
         k_rollup_accum<<<grid, 256, 0, e->stream>>>(a);
@@ -445,9 +468,17 @@ extern "C" int lgw_usage_rollup_emit(lgw_engine* e, const uint64_t* d_table, con
         e->d_rows_cap = cap;
     }
     if (!e->d_nrows) CK(e, cudaMalloc((void**)&e->d_nrows, 8));
+    const uint32_t n_tiles = (uint32_t)((groups + 1023) / 1024);
+    if (n_tiles > e->d_tiles_cap) {
+        cudaFree(e->d_tiles); e->d_tiles = nullptr; e->d_tiles_cap = 0;
+        CK(e, cudaMalloc((void**)&e->d_tiles, (size_t)n_tiles * 4));
+        e->d_tiles_cap = n_tiles;
+    }
     CK(e, cudaEventRecord(e->rev[2], e->stream));
-    k_rollup_compact<<<1, 1024, 0, e->stream>>>((const unsigned long long*)d_table, d_inexact, n_buckets, n_models, bucket0, e->d_rows, cap, e->d_nrows);
-    ++e->launches;
+    k_rollup_count<<<n_tiles, 1024, 0, e->stream>>>((const unsigned long long*)d_table, n_buckets, n_models, e->d_tiles);
+    k_rollup_scan<<<1, 1024, 0, e->stream>>>(e->d_tiles, n_tiles, e->d_nrows);
+    k_rollup_write<<<n_tiles, 1024, 0, e->stream>>>((const unsigned long long*)d_table, d_inexact, n_buckets, n_models, bucket0, e->d_tiles, e->d_rows, cap);
+    e->launches += 3;
     CK(e, cudaEventRecord(e->rev[3], e->stream));
     CK(e, cudaGetLastError());
     unsigned long long cnt = 0;
@@ -457,6 +488,12 @@ extern "C" int lgw_usage_rollup_emit(lgw_engine* e, const uint64_t* d_table, con
     const uint64_t take = cnt < cap ? cnt : cap;
     if (take) CK(e, cudaMemcpyAsync(rows_out, e->d_rows, take * sizeof(RollupRow), cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_rollup_set_path(lgw_engine* e, int force_global) {   // 0 (default): privatised when the table fits; 1: global reductions only
+    if (!e) return LGW_ERR_ARG;
+    e->rollup_force_global = force_global != 0;
     return LGW_OK;
 }
 

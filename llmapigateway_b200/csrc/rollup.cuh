@@ -186,47 +186,135 @@ __global__ void __launch_bounds__(256) k_rollup_accum(RollupArgs a) {
     }
 }
 
-// groups with count > 0, in "time_period DESC, model ASC" order.  One block scans the table in
-// output order with a running offset (the table is small next to the record stream).
-__global__ void __launch_bounds__(1024) k_rollup_compact(const unsigned long long* table, const uint32_t* inexact, uint32_t n_buckets, uint32_t n_models,
-                                                         int64_t bucket0, RollupRow* rows, unsigned long long rows_cap, unsigned long long* n_rows) {
+// ---- block-privatised accumulation (tables that fit in shared memory: every window the stats endpoint asks for, stats.py:46-55) ----
+// Each block keeps the whole table in shared memory as 32-bit (lo, hi) halves, cell-major ([cell][group]: lanes of a warp that hit
+// different groups hit different banks).  A 64-bit add is one native 32-bit shared atomic on `lo` plus -- only on a carry or a
+// negative addend -- one on `hi`.  At the end the block stores its partial table to global scratch (plain coalesced stores) and
+// k_rollup_merge folds the partials into the caller's table: no global atomics at all.
+#define LGW_ROLLUP_SMEM_GROUPS 2560u                                  // 2560 x (10 x 8 + 4) B = 215 040 B
+LGW_RHD size_t rollup_smem_bytes(uint32_t groups) { return (size_t)groups * (LGW_ROLLUP_CELLS * 8 + 4); }
+
+__device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, uint32_t v, uint32_t sign_ext) {
+    const uint32_t old = atomicAdd(lo, v);
+    const uint32_t up = sign_ext + ((old + v) < old ? 1u : 0u);      // carry out of the low half + the addend's own high half
+    if (up) atomicAdd(hi, up);
+}
+
+__global__ void __launch_bounds__(1024, 1) k_rollup_accum_smem(RollupArgs a, unsigned long long* __restrict__ partial, uint32_t* __restrict__ partial_flag) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t G = a.n_buckets * a.n_models;
+    uint32_t* lo = sm;                                                // [CELLS][G]
+    uint32_t* hi = sm + (size_t)LGW_ROLLUP_CELLS * G;                 // [CELLS][G]
+    uint32_t* flag = hi + (size_t)LGW_ROLLUP_CELLS * G;               // [G]
+    for (uint32_t k = threadIdx.x; k < G * (2 * LGW_ROLLUP_CELLS + 1); k += blockDim.x) sm[k] = 0;
+    __syncthreads();
+    uint32_t oob = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t ts = __ldg(a.ts_us + i);
+        if ((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us)) continue;     // tokens_usage_db.py:255-266
+        const int64_t b = bucket_of(ts, a.period) - a.bucket0;
+        const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
+        if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) { ++oob; continue; }
+        const uint32_t g = (uint32_t)b * a.n_models + mr;
+        int32_t v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = __ldg(a.tok[k] + i);
+        const double cost = __ldg(a.cost + i);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) smem_add64(lo + k * G + g, hi + k * G + g, (uint32_t)v[k], v[k] < 0 ? 0xFFFFFFFFu : 0u);
+        smem_add64(lo + 5 * G + g, hi + 5 * G + g, 1u, 0u);
+        uint32_t limb[4];
+        if (!cost_to_limbs(cost, limb)) flag[g] = 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (limb[k]) smem_add64(lo + (6 + k) * G + g, hi + (6 + k) * G + g, limb[k], 0u);
+    }
+    if (oob) atomicAdd(a.oob, oob);
+    __syncthreads();
+    unsigned long long* mine = partial + (size_t)blockIdx.x * LGW_ROLLUP_CELLS * G;
+    for (uint32_t k = threadIdx.x; k < G * LGW_ROLLUP_CELLS; k += blockDim.x) mine[k] = (unsigned long long)lo[k] | ((unsigned long long)hi[k] << 32);
+    for (uint32_t k = threadIdx.x; k < G; k += blockDim.x) partial_flag[(size_t)blockIdx.x * G + k] = flag[k];
+}
+
+// table[g][cell] += sum over blocks of partial[block][cell][g] (64-bit wrap-around sums: exact two's complement)
+__global__ void __launch_bounds__(256) k_rollup_merge(const unsigned long long* __restrict__ partial, const uint32_t* __restrict__ partial_flag, uint32_t n_blocks,
+                                                      uint32_t G, unsigned long long* table, uint32_t* inexact) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;         // index into [cell][g]
+    if (k < G * LGW_ROLLUP_CELLS) {
+        unsigned long long s = 0;
+        for (uint32_t b = 0; b < n_blocks; ++b) s += partial[(size_t)b * LGW_ROLLUP_CELLS * G + k];
+        const uint32_t cell = k / G, g = k % G;
+        if (s) table[(size_t)g * LGW_ROLLUP_CELLS + cell] += s;
+    }
+    if (k < G) {
+        uint32_t f = 0;
+        for (uint32_t b = 0; b < n_blocks; ++b) f |= partial_flag[(size_t)b * G + k];
+        if (f) inexact[k] = 1;
+    }
+}
+
+// ---- compaction: groups with count > 0, in "time_period DESC, model ASC" order, over as many blocks as the table needs --------------
+// pass 1 counts the occupied groups of every 1024-position tile (output order), pass 2 scans the tile counts, pass 3 writes.
+LGW_RHD uint64_t rollup_group_at(uint64_t j, uint32_t n_buckets, uint32_t n_models) {
+    const uint64_t bdesc = j / n_models, mr = j % n_models;
+    return (uint64_t)(n_buckets - 1 - bdesc) * n_models + mr;
+}
+
+__global__ void __launch_bounds__(1024) k_rollup_count(const unsigned long long* __restrict__ table, uint32_t n_buckets, uint32_t n_models, uint32_t* __restrict__ tile_count) {
+    const uint64_t total = (uint64_t)n_buckets * n_models;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t has = j < total && table[rollup_group_at(j, n_buckets, n_models) * LGW_ROLLUP_CELLS + 5] != 0;
+    const uint32_t c = __syncthreads_count(has);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) k_rollup_scan(uint32_t* tile_count, uint32_t n_tiles, unsigned long long* n_rows) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ unsigned long long base;
+    __shared__ uint32_t base;
     if (threadIdx.x == 0) base = 0;
     __syncthreads();
-    const uint64_t total = (uint64_t)n_buckets * n_models;
-    for (uint64_t start = 0; start < total; start += blockDim.x) {
-        const uint64_t j = start + threadIdx.x;                       // output-order position
-        uint32_t has = 0; uint64_t g = 0;
-        if (j < total) {
-            const uint64_t bdesc = j / n_models, mr = j % n_models;
-            g = (uint64_t)(n_buckets - 1 - bdesc) * n_models + mr;
-            has = table[g * LGW_ROLLUP_CELLS + 5] != 0;
-        }
-        // block exclusive scan of `has`
+    for (uint32_t start = 0; start < n_tiles; start += blockDim.x) {
+        const uint32_t k = start + threadIdx.x;
+        const uint32_t v = k < n_tiles ? tile_count[k] : 0;
+        uint32_t x = v;                                               // inclusive warp scan
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
-        const uint32_t in_warp = __popc(ballot & ((1u << lane) - 1));
-        if (lane == 0) warp_sums[warp] = __popc(ballot);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) warp_sums[warp] = x;
         __syncthreads();
-        uint32_t before = 0, block_total = 0;
-        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) { const uint32_t s = warp_sums[w]; if (w < warp) before += s; block_total += s; }
-        const unsigned long long pos = base + before + in_warp;
-        if (has && pos < rows_cap) {
-            const unsigned long long* c = table + g * LGW_ROLLUP_CELLS;
-            RollupRow r;
-            r.bucket = bucket0 + (int64_t)(g / n_models); r.model_rank = (int32_t)(g % n_models); r.inexact = inexact[g];
-            r.prompt_tokens = (int64_t)c[0]; r.completion_tokens = (int64_t)c[1]; r.total_tokens = (int64_t)c[2];
-            r.reasoning_tokens = (int64_t)c[3]; r.cached_tokens = (int64_t)c[4]; r.count = (int64_t)c[5];
-            uint64_t cells[4] = {c[6], c[7], c[8], c[9]};
-            r.cost = limbs_to_cost(cells);
-            rows[pos] = r;
-        }
+        uint32_t before = 0, all = 0;
+        for (uint32_t w = 0; w < 32; ++w) { const uint32_t s = warp_sums[w]; if (w < warp) before += s; all += s; }
+        if (k < n_tiles) tile_count[k] = base + before + x - v;       // exclusive offset of the tile
         __syncthreads();
-        if (threadIdx.x == 0) base += block_total;
+        if (threadIdx.x == 0) base += all;
         __syncthreads();
     }
     if (threadIdx.x == 0) *n_rows = base;
+}
+
+__global__ void __launch_bounds__(1024) k_rollup_write(const unsigned long long* __restrict__ table, const uint32_t* __restrict__ inexact, uint32_t n_buckets, uint32_t n_models,
+                                                       int64_t bucket0, const uint32_t* __restrict__ tile_off, RollupRow* rows, unsigned long long rows_cap) {
+    __shared__ uint32_t warp_sums[32];
+    const uint64_t total = (uint64_t)n_buckets * n_models;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t g = 0; uint32_t has = 0;
+    if (j < total) { g = rollup_group_at(j, n_buckets, n_models); has = table[g * LGW_ROLLUP_CELLS + 5] != 0; }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
+    if (lane == 0) warp_sums[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sums[w];
+    const unsigned long long pos = (unsigned long long)tile_off[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1));
+    if (has && pos < rows_cap) {
+        const unsigned long long* c = table + g * LGW_ROLLUP_CELLS;
+        RollupRow r;
+        r.bucket = bucket0 + (int64_t)(g / n_models); r.model_rank = (int32_t)(g % n_models); r.inexact = inexact[g];
+        r.prompt_tokens = (int64_t)c[0]; r.completion_tokens = (int64_t)c[1]; r.total_tokens = (int64_t)c[2];
+        r.reasoning_tokens = (int64_t)c[3]; r.cached_tokens = (int64_t)c[4]; r.count = (int64_t)c[5];
+        uint64_t cells[4] = {c[6], c[7], c[8], c[9]};
+        r.cost = limbs_to_cost(cells);
+        rows[pos] = r;
+    }
 }
 #endif
 

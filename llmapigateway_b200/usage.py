@@ -99,8 +99,10 @@ class UsageTable:
         self._dev = None
         return True
 
-    def load_columns(self, ts_us, models, prompt, completion, total, reasoning, cached, cost):
-        """Bulk ingest of columns (models: sequence of str|None)."""
+    def load_columns(self, ts_us, models, prompt, completion, total, reasoning, cached, cost, names=None):
+        """Bulk ingest of columns (models: sequence of str|None).  `names`: the model dictionary to encode against when several
+        tables (one per GPU) are merged -- every rank must rank the models identically (sorted by UTF-8 bytes, NULL first)."""
+        self._fixed_names = sorted(set(names), key=lambda s: s.encode("utf-8")) if names is not None else None
         self._host = {"ts_us": np.ascontiguousarray(ts_us, np.int64), "model_rank": None,
                       "prompt_tokens": np.ascontiguousarray(prompt, np.int32), "completion_tokens": np.ascontiguousarray(completion, np.int32),
                       "total_tokens": np.ascontiguousarray(total, np.int32), "reasoning_tokens": np.ascontiguousarray(reasoning, np.int32),
@@ -122,7 +124,7 @@ class UsageTable:
             self._models = list(self._models) + list(cols[1])
             self._providers = list(self._providers) + list(cols[8])
             self._pending_rows = []
-        names = sorted({m for m in self._models if m is not None}, key=lambda s: s.encode("utf-8"))
+        names = getattr(self, "_fixed_names", None) or sorted({m for m in self._models if m is not None}, key=lambda s: s.encode("utf-8"))
         rank = {m: i + 1 for i, m in enumerate(names)}
         rank[None] = 0
         self._host["model_rank"] = np.fromiter((rank[m] for m in self._models), dtype=np.int32, count=len(self._models))
@@ -171,6 +173,21 @@ class UsageTable:
             ptr["reasoning_tokens"], ptr["cached_tokens"], ptr["cost"], n, PERIODS[period],
             int(start is not None), to_us(start) if start is not None else 0, int(end is not None), to_us(end) if end is not None else 0,
             bucket0, n_buckets, n_models, d_table, d_inexact, d_oob), "usage_rollup_accum")
+
+    def emit(self, bucket0: int, n_buckets: int, n_models: int, d_table, d_inexact) -> np.ndarray:
+        """Rows of a dense device table (this GPU's, or the all-reduced sum of every GPU's), time_period DESC, model ASC."""
+        groups = n_buckets * n_models
+        rows = np.zeros(groups, dtype=ROW_DTYPE)
+        n_rows = C.c_uint64(0)
+        self.eng._ck(self._lib.lgw_usage_rollup_emit(self.eng._h, d_table, d_inexact, bucket0, n_buckets, n_models,
+                                                     rows.ctypes.data_as(C.c_void_p), groups, C.byref(n_rows)), "usage_rollup_emit")
+        return rows[:n_rows.value]
+
+    def rows_to_dicts(self, period: str, rows) -> list[dict]:
+        return [{"time_period": period_label(period, int(r["bucket"])), "model": self._names[int(r["model_rank"])],
+                 "prompt_tokens": int(r["prompt_tokens"]), "completion_tokens": int(r["completion_tokens"]),
+                 "total_tokens": int(r["total_tokens"]), "reasoning_tokens": int(r["reasoning_tokens"]),
+                 "cached_tokens": int(r["cached_tokens"]), "cost": float(r["cost"]), "count": int(r["count"])} for r in rows]
 
     def rollup_rows(self, period: str, start: datetime | None = None, end: datetime | None = None) -> np.ndarray:
         """Rows (ROW_DTYPE) ordered time_period DESC, model ASC."""

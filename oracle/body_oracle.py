@@ -54,6 +54,7 @@ def rule_ops(rule: dict, provider_name: str, sub_provider=None, retry=False):
         ops.append(("usage", {"include": True}, True))                             # :114-115
     for k, v in (rule.get("custom_body_params") or {}).items():                    # :116-119
         ops.append((k, v, False))
+    ops.append(("model", rule.get("model"), False))                                # :135 / :160 re-assigned inside the retry loop
     order = rule.get("providers_order")
     if sub_provider is not None:                                                   # case 2, :164-168
         ops.append(("provider", {"order": [sub_provider]}, False))

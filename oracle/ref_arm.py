@@ -193,3 +193,145 @@ def run_config3(variant: str, procs: int, n_streams: int, n_events: int = 512, s
             times = pool.map(_worker, jobs)
     wall = time.perf_counter() - t0
     return n_streams * n_events / max(times), max(times), wall
+
+
+# ---- config 4: the reference's own endpoint body (chat.py:20 chat_completions) over the failure-injecting upstream --------------
+def load_chat(variant: str = "B2"):
+    """chat.py imported unmodified from oracle/_ref: ModelRotationDB's file redirected to a temp dir (model_rotation_db.py:15-22
+    hard-codes <root>/db), api/v1/models.py (loads config files at import; not on this path) replaced by an empty router."""
+    import types
+    load(variant)
+    import llm_gateway_core.db.model_rotation_db as mdb
+    tmp = Path(tempfile.mkdtemp(prefix="lgw_rot_")) / "rotation.db"
+
+    def _init(self, db_filename: str = "llmgateway_rotation.db"):
+        self.db_path = tmp
+        self._init_db()
+
+    mdb.ModelRotationDB.__init__ = _init
+    from fastapi import APIRouter
+    stub = types.ModuleType("llm_gateway_core.api.v1.models")
+    stub.router = APIRouter()
+    sys.modules["llm_gateway_core.api.v1.models"] = stub
+    import llm_gateway_core.api.v1.chat as chat
+    return chat
+
+
+def _c4_worker(args):
+    variant, ids, n_total, n_events = args
+    import types
+    import httpx
+    sys.path.insert(0, str(HERE.parent))
+    from llmapigateway_b200 import synth
+    chat = load_chat(variant)
+    rh, cl = _mods["rh"], _mods["cl"]
+    providers, rules, fallback_provider = synth.chain_world()
+    chat.settings.fallback_provider = fallback_provider
+    os.environ.setdefault("ALPHA_KEY_ENV", "sk-alpha-from-env")
+    loader = types.SimpleNamespace(providers_config=providers, fallback_rules=rules)
+    up = synth.ChainUpstream(n_total, n_events, seed=4, p_fail=0.2, lazy=True)
+    bodies = synth.chain_request_bodies(n_total, seed=4)
+    cl.write_log = lambda h, b, accum, usage: None
+    state = {"sid": 0, "attempt": 0}
+
+    class _Body(httpx.AsyncByteStream):
+        def __init__(self, chunks):
+            self.chunks = chunks
+
+        async def __aiter__(self):
+            for c in self.chunks:
+                yield c
+
+    def handler(request):
+        ans = up.stream_chunks(state["sid"], state["attempt"])
+        state["attempt"] += 1
+        if isinstance(ans, tuple):
+            return httpx.Response(ans[0], content=ans[1])
+        return httpx.Response(200, headers={"content-type": "text/event-stream"}, stream=_Body(ans))
+
+    real_client = httpx.AsyncClient
+    rh.httpx.AsyncClient = lambda **kw: real_client(transport=httpx.MockTransport(handler), **kw)
+    served = [0]
+
+    class Req:
+        def __init__(self, body):
+            self._b = body
+            self.headers = {}
+            self.app = types.SimpleNamespace(state=types.SimpleNamespace(config_loader=loader))
+
+        async def body(self):
+            return self._b
+
+    async def go():
+        from fastapi import HTTPException
+        for sid in ids:
+            state["sid"], state["attempt"] = int(sid), 0
+            try:
+                resp = await chat.chat_completions(Req(bodies[int(sid)]))
+            except HTTPException:
+                continue
+            out = []
+            try:
+                async for c in resp.body_iterator:
+                    out.append(c)
+            except UnboundLocalError:
+                pass
+            t = cl.ChunkProcessorThread({}, "", True)          # chat_logging.py tap of the relayed stream
+            t.queue = _NoWaitQueue()
+            for c in out:
+                t.enqueue_chunk(c)
+            t.run()
+            served[0] += 1
+
+    t0 = time.perf_counter()
+    try:
+        asyncio.run(go())
+    finally:
+        rh.httpx.AsyncClient = real_client
+    return time.perf_counter() - t0, served[0]
+
+
+def run_config4(variant: str, procs: int, ids, n_total: int = 8192, n_events: int = 512):
+    """The streams `ids` of config 4 through the unmodified chat_completions, split over `procs` processes.
+    -> (delta events relayed per second, slowest process seconds, served streams)."""
+    import multiprocessing as mp
+    ids = list(ids)
+    parts = [ids[i::procs] for i in range(procs)]
+    jobs = [(variant, p, n_total, n_events) for p in parts if p]
+    if len(jobs) == 1:
+        res = [_c4_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            res = pool.map(_c4_worker, jobs)
+    served = sum(r[1] for r in res)
+    slowest = max(r[0] for r in res)
+    return served * n_events / slowest, slowest, served
+
+
+# ---- config 5: TokensUsageDB.get_aggregated_usage (tokens_usage_db.py:222) on a SQLite file of the same records -----------------------
+def run_config5(n_rows: int, periods=("hour", "day")):
+    """-> dict(load_s, per query seconds).  The reference has one process and SQLite is single-threaded per connection."""
+    import sqlite3
+    from datetime import datetime, timedelta
+    sys.path.insert(0, str(HERE.parent))
+    from llmapigateway_b200 import usage as U
+    load("B2")
+    import llm_gateway_core.db.tokens_usage_db as tdb
+    db = tdb.TokensUsageDB()
+    end = datetime(2026, 9, 21, 6, 57, 17, 47518)
+    ts, models, tok, cost = U.synth_usage_columns(n_rows, seed=5, end=end)
+    epoch = datetime(1970, 1, 1)
+    t0 = time.perf_counter()
+    conn = sqlite3.connect(db.db_path)
+    conn.executemany("INSERT INTO tokens_usage (timestamp, prompt_tokens, completion_tokens, total_tokens, reasoning_tokens, cached_tokens, cost, model, provider)"
+                     " VALUES (?,?,?,?,?,?,?,?,NULL)",
+                     (((epoch + timedelta(microseconds=int(ts[i]))).isoformat(), int(tok[0][i]), int(tok[1][i]), int(tok[2][i]), int(tok[3][i]), int(tok[4][i]),
+                       float(cost[i]), models[i]) for i in range(n_rows)))
+    conn.commit(); conn.close()
+    out = {"load_s": time.perf_counter() - t0, "rows": n_rows}
+    for period in periods:
+        s0, e0 = U.stats_window(period, end)
+        t0 = time.perf_counter(); r1 = db.get_aggregated_usage(period, start_date=s0, end_date=e0); out[period + "_window_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); r2 = db.get_aggregated_usage(period); out[period + "_all_s"] = time.perf_counter() - t0
+        out[period + "_groups"] = (len(r1), len(r2))
+    return out

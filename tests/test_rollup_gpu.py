@@ -94,3 +94,37 @@ def test_rollup_full_size_properties(engine):
         assert order == sorted(order)                                  # time_period DESC, model ASC
     ms = t.last_ms()
     assert ms["accum"] > 0
+
+
+def test_privatised_and_global_paths_agree(engine):
+    """The shared-memory (block-privatised) accumulate path and the global-reduction path give the same rows, incl. negative
+    token counts (64-bit sign extension through the 32-bit shared halves) and costs with more than 53 bits of spread."""
+    n = 150_000
+    ts, models, tok, cost = synth_usage_columns(n, seed=21, end=NOW)
+    rng = np.random.default_rng(5)
+    tok[0][::7] = -tok[0][::7]
+    tok[1][:] = rng.integers(-2**31, 2**31 - 1, n, dtype=np.int64).astype(np.int32)
+    cost[::11] = -cost[::11] * 1e3
+    t = UsageTable(engine)
+    t.load_columns(ts, models, *tok, cost)
+    for period, s, e in (("hour", NOW - timedelta(hours=24), NOW), ("day", NOW - timedelta(weeks=2), NOW), ("week", NOW - timedelta(weeks=15), NOW), ("month", NOW - timedelta(days=365), NOW)):
+        engine._lib.lgw_rollup_set_path(engine._h, 0)
+        a = t.rollup_rows(period, s, e)
+        engine._lib.lgw_rollup_set_path(engine._h, 1)
+        b = t.rollup_rows(period, s, e)
+        engine._lib.lgw_rollup_set_path(engine._h, 0)
+        assert len(a) == len(b) > 0 and a.tobytes() == b.tobytes(), period
+        sel = (ts >= int((s - _EPOCH) / timedelta(microseconds=1))) & (ts <= int((e - _EPOCH) / timedelta(microseconds=1)))
+        assert int(a["completion_tokens"].sum()) == int(tok[1][sel].astype(np.int64).sum())
+
+
+def test_two_rank_rollup_merge_on_the_gpu():
+    """SURVEY 8(e): records partitioned over ranks, per-rank dense tables from the GPU kernels, one all-reduce(sum), rank 0 emits;
+    compared with SQLite over all records.  NCCL when the box has two GPUs, gloo over host copies of the device tables else."""
+    import os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(root / "tests" / "rollup_rank_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "ROLLUP_MERGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
