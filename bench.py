@@ -496,6 +496,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    from llmapigateway_b200 import numa
+    numa_info = numa.bind_to_gpu_node(local)        # pinned staging buffers on the GPU's own NUMA node (before anything is allocated)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -617,6 +619,9 @@ def main():
         if k >= 2:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
     e2e_step = float(np.mean(e2e_ms))
+    assert np.array_equal(h["out"].numpy(), h["data"].numpy()), "end-to-end: re-emitted host bytes differ from the input of committed streams"
+    assert _abi.usage_rec_to_dict(states[5].rec) == b.truths[5].expected_row()
+    e2e_direct = eng.last_step_direct()
     if world > 1:
         t = torch.tensor([e2e_step], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_step = float(t.item())
     e2e_value = events_total / (e2e_step / 1e3)
@@ -649,7 +654,10 @@ def main():
         "segments": counters,
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "json_gbs": e2e_value * EVENT_BYTES / 1e9},
+                "json_gbs": e2e_value * EVENT_BYTES / 1e9,
+                "path": ("direct: the bulk kernel's TMA loads/stores move the bytes over PCIe themselves (LGW_DIRECT)" if e2e_direct
+                         else "pinned host buffers, 8 slices: upload of slice k+1 | kernels of slice k | download of slice k-1 on three streams"),
+                "numa": numa_info, "pcie_peak_note": "copy engines alone, 134 MB each way at once: 2.78 ms (48.7 GB/s per direction; 55 GB/s one direction alone), measured with tools/exp_e2e.py on this pool"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(), "peak_source": peak_src,

@@ -189,6 +189,9 @@ int lgw_last_step_ms(lgw_engine* e, float ms[4]);
 int lgw_last_step_kernel_ms(lgw_engine* e, float ms[4]);
 int lgw_engine_set_kernel_timing(lgw_engine* e, int on);
 /* number of kernels launched by this engine since creation */
+/* 1 when the last lgw_sse_step ran in direct mode: both byte buffers were page-locked host memory and the bulk kernel moved
+ * them over PCIe itself (TMA loads from / stores to the host buffers), without the staged, sliced copies */
+int lgw_last_step_direct(lgw_engine* e);
 int lgw_launch_count(lgw_engine* e, uint64_t* out);
 
 /* ---- usage-stats rollup -----------------------------------------------------------------------------

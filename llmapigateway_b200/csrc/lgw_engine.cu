@@ -46,6 +46,7 @@ struct lgw_engine {
     RollupRow* d_rows = nullptr; uint64_t d_rows_cap = 0; unsigned long long* d_nrows = nullptr;
     uint8_t* d_partial = nullptr; size_t d_partial_cap = 0; uint32_t* d_tiles = nullptr; uint32_t d_tiles_cap = 0;
     bool rollup_attr_set = false, rollup_force_global = false;
+    bool last_direct = false;       // the last host-buffer step ran in direct mode (kernel-driven PCIe traffic)
     float ms[5]{0, 0, 0, 0, 0};     // prime, relay, commit, usage extract, whole host-buffer step
     bool timed = false;
     uint64_t launches = 0;
@@ -315,10 +316,31 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
     for (uint32_t s = 0; s < n_segs; ++s) if (seg_chunk[s] > seg_chunk[s + 1] || seg_slot[s] >= e->lim.max_streams) { e->err = "bad segment table"; return LGW_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaEventRecord(e->ev[5], e->stream));
-    // Pipelined: the step is cut at segment boundaries into up to 8 slices; the upload of slice k+1,
-    // the kernels of slice k and the download of slice k-1 overlap (PCIe is full duplex).
-    uint32_t n_slices = n_bytes >= (8u << 20) && n_segs >= 16 ? 4u : 1u;
-    if (const char* sl = getenv("LGW_SLICES")) { int v = atoi(sl); if (v >= 1 && v <= 16) n_slices = (uint32_t)v; }
+    // Host buffers that are page-locked (lgw_alloc_pinned, cudaHostAlloc, torch pin_memory) need no staging copy: the bulk kernel's
+    // TMA loads can read the packed chunks straight from the host buffer ("direct in") and its TMA stores can write the re-emitted
+    // bytes straight into the host output buffer ("direct out"); the parse of a tile then overlaps its own PCIe transfer.  The
+    // step is cut at segment boundaries into slices so that whatever still goes through the copy engines (the other direction)
+    // overlaps with the kernels: upload of slice k+1 | kernels of slice k | download of slice k-1 (PCIe is full duplex).
+    //   LGW_DIRECT = 0 (default) | in | out | both        LGW_SLICES = 1..14        LGW_TRACE = 1 prints the slice timeline
+    // Measured on the B200 box: the copy engines move 134 MB each way in 2.78 ms when nothing else runs; the direct
+    // modes are correct and save the device staging buffers, but SM-issued PCIe traffic and a copy-engine stream in the other
+    // direction slow each other down more than two copy-engine streams do, so the staged, sliced pipeline stays the default.
+    static const int allow = [] { const char* v = getenv("LGW_DIRECT"); if (!v || v[0] == '0') return 0; if (v[0] == 'b') return 3; if (v[0] == 'o') return 2; return 1; }();
+    static const bool trace = [] { const char* v = getenv("LGW_TRACE"); return v && v[0] == '1'; }();
+    const uint8_t* direct_in = nullptr; uint8_t* direct_out = nullptr;
+    {
+        cudaPointerAttributes pa{};
+        const bool big = e->mode == 0 && n_bytes >= (1u << 20);
+        if (big && (allow & 1) && ((uintptr_t)bytes & 15) == 0 && cudaPointerGetAttributes(&pa, bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            direct_in = (const uint8_t*)pa.devicePointer;
+        if (big && (allow & 2) && ((uintptr_t)out_bytes & 15) == 0 && cudaPointerGetAttributes(&pa, out_bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            direct_out = (uint8_t*)pa.devicePointer;
+        cudaGetLastError();                 // (cudaPointerGetAttributes on an unregistered pointer may leave an error behind)
+        e->last_direct = direct_in || direct_out;
+    }
+    uint32_t n_slices = n_bytes >= (8u << 20) && n_segs >= 16 ? 8u : 1u;
+    if (direct_in && direct_out) n_slices = 1;
+    if (const char* sl = getenv("LGW_SLICES")) { int v = atoi(sl); if (v >= 1 && v <= 14) n_slices = (uint32_t)v; }
     if (e->mode == 1 || n_segs < n_slices) n_slices = 1;
     uint32_t cut[18]; cut[0] = 0;
     for (uint32_t j = 1; j < n_slices; ++j) {           // segment index whose start byte is closest below j/n of the bytes
@@ -329,32 +351,63 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
     }
     cut[n_slices] = n_segs;
     CK(e, cudaMemsetAsync(e->d_rowq_count, 0, 4, e->stream));
+    const bool piped = n_slices > 1;
+    cudaStream_t sin = piped ? e->s_in : e->stream, sout = piped ? e->s_out : e->stream;
+    if (piped) { CK(e, cudaEventRecord(e->ev_k[15], e->stream)); CK(e, cudaStreamWaitEvent(sin, e->ev_k[15], 0)); }   // the copy stream starts after ev[5]
+    // offsets and segment tables: slice 0's part first (its kernels can start), everything else in one batch right behind it
+    {
+        const uint32_t s1 = cut[1], c1 = seg_chunk[s1];
+        CK(e, cudaMemcpyAsync(e->d_chunk_off, chunk_off, (size_t)(c1 + 1) * 4, cudaMemcpyHostToDevice, sin));
+        CK(e, cudaMemcpyAsync(e->d_seg_chunk, seg_chunk, (size_t)(n_segs + 1) * 4, cudaMemcpyHostToDevice, sin));
+        if (n_segs) CK(e, cudaMemcpyAsync(e->d_seg_slot, seg_slot, (size_t)n_segs * 4, cudaMemcpyHostToDevice, sin));
+    }
+    cudaEvent_t tr[3][16]; float tms[3][16];
+    if (trace) for (int k = 0; k < 3; ++k) for (uint32_t j = 0; j < n_slices; ++j) cudaEventCreate(&tr[k][j]);
     int rc = LGW_OK;
     for (uint32_t j = 0; j < n_slices; ++j) {
         const uint32_t s0 = cut[j], s1 = cut[j + 1];
-        if (s1 <= s0 && n_slices > 1) continue;
+        if (s1 <= s0 && piped) continue;
         const uint32_t c0 = seg_chunk[s0], c1 = seg_chunk[s1];
         const uint32_t b0 = chunk_off[c0]; const uint64_t b1 = chunk_off[c1];
-        cudaStream_t sin = n_slices > 1 ? e->s_in : e->stream, sout = n_slices > 1 ? e->s_out : e->stream;
-        if (b1 > b0) CK(e, cudaMemcpyAsync(e->d_in + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, sin));
-        CK(e, cudaMemcpyAsync(e->d_chunk_off + c0, chunk_off + c0, (size_t)(c1 - c0 + 1) * 4, cudaMemcpyHostToDevice, sin));
-        CK(e, cudaMemcpyAsync(e->d_seg_chunk + s0, seg_chunk + s0, (size_t)(s1 - s0 + 1) * 4, cudaMemcpyHostToDevice, sin));
-        if (s1 > s0) CK(e, cudaMemcpyAsync(e->d_seg_slot + s0, seg_slot + s0, (size_t)(s1 - s0) * 4, cudaMemcpyHostToDevice, sin));
-        if (n_slices > 1) { CK(e, cudaEventRecord(e->ev_in[j], sin)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[j], 0)); }
-        rc = step_device(e, e->d_in, n_bytes, e->d_chunk_off, n_chunks, e->d_seg_chunk, e->d_seg_slot, n_segs, e->d_out, e->d_seg_out,
-                         s0, s1, c0, c1, b0, b1, false);
+        if (!direct_in && b1 > b0) CK(e, cudaMemcpyAsync(e->d_in + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, sin));
+        if (piped && (j == 0 || !direct_in)) { CK(e, cudaEventRecord(e->ev_in[j], sin)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[j], 0)); }
+        if (trace) cudaEventRecord(tr[0][j], sin);
+        if (j == 0 && n_slices > 1 && n_chunks > seg_chunk[cut[1]]) {      // the rest of the chunk offsets, while slice 0 is at work
+            const uint32_t cc = seg_chunk[cut[1]];
+            CK(e, cudaMemcpyAsync(e->d_chunk_off + cc + 1, chunk_off + cc + 1, (size_t)(n_chunks - cc) * 4, cudaMemcpyHostToDevice, sin));
+            if (direct_in) { CK(e, cudaEventRecord(e->ev_in[1], sin)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[1], 0)); }
+        }
+        rc = step_device(e, direct_in ? direct_in : e->d_in, n_bytes, e->d_chunk_off, n_chunks, e->d_seg_chunk, e->d_seg_slot, n_segs,
+                         direct_out ? direct_out : e->d_out, e->d_seg_out, s0, s1, c0, c1, b0, b1, false);
         if (rc != LGW_OK) return rc;
-        if (n_slices > 1) { CK(e, cudaEventRecord(e->ev_k[j], e->stream)); CK(e, cudaStreamWaitEvent(sout, e->ev_k[j], 0)); }
-        if (b1 > b0) CK(e, cudaMemcpyAsync(out_bytes + b0, e->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, sout));
+        if (trace) cudaEventRecord(tr[1][j], e->stream);
+        if (!direct_out) {
+            if (piped) { CK(e, cudaEventRecord(e->ev_k[j], e->stream)); CK(e, cudaStreamWaitEvent(sout, e->ev_k[j], 0)); }
+            if (b1 > b0) CK(e, cudaMemcpyAsync(out_bytes + b0, e->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, sout));
+        }
+        if (trace) cudaEventRecord(tr[2][j], sout);
     }
     // per-segment results: one copy at the end (a copy into pageable host memory blocks the host thread,
     // which would serialise the pipeline if it were issued per slice)
     if (n_segs) CK(e, cudaMemcpyAsync(seg_out, e->d_seg_out, (size_t)n_segs * sizeof(SegResult), cudaMemcpyDeviceToHost, e->stream));
-    if (n_slices > 1) { CK(e, cudaStreamSynchronize(e->s_out)); CK(e, cudaStreamSynchronize(e->s_in)); }
+    if (piped) {                            // ev[6] closes the step on the engine stream: it has to see the downloads too
+        CK(e, cudaEventRecord(e->ev_k[14], sout)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_k[14], 0));
+        CK(e, cudaEventRecord(e->ev_in[15], sin)); CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[15], 0));
+    }
     CK(e, cudaEventRecord(e->ev[6], e->stream));
     rc = lgw_fetch_rows(e, rows_out, rows_cap, n_rows);
     if (rc != LGW_OK) return rc;
+    if (piped) { CK(e, cudaStreamSynchronize(e->s_out)); CK(e, cudaStreamSynchronize(e->s_in)); }
     float t = 0; if (cudaEventElapsedTime(&t, e->ev[5], e->ev[6]) == cudaSuccess) e->ms[4] = t;
+    if (trace) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[lgw trace] direct_in=%d direct_out=%d slices=%u total=%.3f ms; per slice (ms after step start): upload done | kernels done | download done\n", direct_in != nullptr, direct_out != nullptr, n_slices, t);
+        for (uint32_t j = 0; j < n_slices; ++j) {
+            for (int k = 0; k < 3; ++k) { tms[k][j] = -1; cudaEventElapsedTime(&tms[k][j], e->ev[5], tr[k][j]); cudaEventDestroy(tr[k][j]); }
+            fprintf(stderr, "[lgw trace]   %2u  %.3f | %.3f | %.3f\n", j, tms[0][j], tms[1][j], tms[2][j]);
+        }
+        cudaGetLastError();
+    }
     return LGW_OK;
 }
 
@@ -385,6 +438,8 @@ extern "C" int lgw_last_step_kernel_ms(lgw_engine* e, float ms[4]) {
     for (int i = 0; i < 4; ++i) ms[i] = e->ms[i];
     return LGW_OK;
 }
+
+extern "C" int lgw_last_step_direct(lgw_engine* e) { return e && e->last_direct ? 1 : 0; }
 
 extern "C" int lgw_launch_count(lgw_engine* e, uint64_t* out) {
     if (!e || !out) return LGW_ERR_ARG;
@@ -442,7 +497,7 @@ extern "C" int lgw_usage_rollup_accum(lgw_engine* e, const int64_t* d_ts_us, con
         unsigned long long* partial = (unsigned long long*)e->d_partial;
         uint32_t* pflag = (uint32_t*)(e->d_partial + (size_t)grid * groups * LGW_ROLLUP_CELLS * 8);
         k_rollup_accum_smem<<<grid, 1024, rollup_smem_bytes((uint32_t)groups), e->stream>>>(a, partial, pflag);
-        k_rollup_merge<<<(unsigned)((groups * LGW_ROLLUP_CELLS + 255) / 256), 256, 0, e->stream>>>(partial, pflag, grid, (uint32_t)groups, a.table, a.inexact);
+        k_rollup_merge<<<dim3((unsigned)((groups * LGW_ROLLUP_CELLS + 255) / 256), LGW_ROLLUP_MERGE_SLICES), 256, 0, e->stream>>>(partial, pflag, grid, (uint32_t)groups, a.table, a.inexact);
         e->launches += 2;
     } else if (n) {
         const uint64_t want = (n + 255) / 256;

@@ -209,24 +209,35 @@ __global__ void __launch_bounds__(1024, 1) k_rollup_accum_smem(RollupArgs a, uns
     for (uint32_t k = threadIdx.x; k < G * (2 * LGW_ROLLUP_CELLS + 1); k += blockDim.x) sm[k] = 0;
     __syncthreads();
     uint32_t oob = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const int64_t ts = __ldg(a.ts_us + i);
-        if ((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us)) continue;     // tokens_usage_db.py:255-266
-        const int64_t b = bucket_of(ts, a.period) - a.bucket0;
-        const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
-        if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) { ++oob; continue; }
-        const uint32_t g = (uint32_t)b * a.n_models + mr;
-        int32_t v[5];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // four timestamps per trip are requested before any is looked at: with a window most records end at the filter, and the loop
+    // would otherwise have one 8-byte load in flight per thread
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += 4 * stride) {
+        int64_t tsv[4];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) v[k] = __ldg(a.tok[k] + i);
-        const double cost = __ldg(a.cost + i);
+        for (int u = 0; u < 4; ++u) { const uint64_t i = i0 + u * stride; tsv[u] = i < a.n ? __ldg(a.ts_us + i) : INT64_MIN; }
 #pragma unroll
-        for (int k = 0; k < 5; ++k) smem_add64(lo + k * G + g, hi + k * G + g, (uint32_t)v[k], v[k] < 0 ? 0xFFFFFFFFu : 0u);
-        smem_add64(lo + 5 * G + g, hi + 5 * G + g, 1u, 0u);
-        uint32_t limb[4];
-        if (!cost_to_limbs(cost, limb)) flag[g] = 1;
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = i0 + u * stride;
+            const int64_t ts = tsv[u];
+            if (i >= a.n) continue;
+            if ((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us)) continue;     // tokens_usage_db.py:255-266
+            const int64_t b = bucket_of(ts, a.period) - a.bucket0;
+            const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
+            if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) { ++oob; continue; }
+            const uint32_t g = (uint32_t)b * a.n_models + mr;
+            int32_t v[5];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (limb[k]) smem_add64(lo + (6 + k) * G + g, hi + (6 + k) * G + g, limb[k], 0u);
+            for (int k = 0; k < 5; ++k) v[k] = __ldg(a.tok[k] + i);
+            const double cost = __ldg(a.cost + i);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) smem_add64(lo + k * G + g, hi + k * G + g, (uint32_t)v[k], v[k] < 0 ? 0xFFFFFFFFu : 0u);
+            smem_add64(lo + 5 * G + g, hi + 5 * G + g, 1u, 0u);
+            uint32_t limb[4];
+            if (!cost_to_limbs(cost, limb)) flag[g] = 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (limb[k]) smem_add64(lo + (6 + k) * G + g, hi + (6 + k) * G + g, limb[k], 0u);
+        }
     }
     if (oob) atomicAdd(a.oob, oob);
     __syncthreads();
@@ -235,19 +246,23 @@ __global__ void __launch_bounds__(1024, 1) k_rollup_accum_smem(RollupArgs a, uns
     for (uint32_t k = threadIdx.x; k < G; k += blockDim.x) partial_flag[(size_t)blockIdx.x * G + k] = flag[k];
 }
 
-// table[g][cell] += sum over blocks of partial[block][cell][g] (64-bit wrap-around sums: exact two's complement)
+// table[g][cell] += sum over blocks of partial[block][cell][g] (64-bit wrap-around sums: exact two's complement).  blockIdx.y picks
+// one of LGW_ROLLUP_MERGE_SLICES interleaved sets of blocks, so that the (independent, pipelined) loads of a thread stay few.
+#define LGW_ROLLUP_MERGE_SLICES 16u
 __global__ void __launch_bounds__(256) k_rollup_merge(const unsigned long long* __restrict__ partial, const uint32_t* __restrict__ partial_flag, uint32_t n_blocks,
                                                       uint32_t G, unsigned long long* table, uint32_t* inexact) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;         // index into [cell][g]
+    const uint32_t slice = blockIdx.y;
     if (k < G * LGW_ROLLUP_CELLS) {
         unsigned long long s = 0;
-        for (uint32_t b = 0; b < n_blocks; ++b) s += partial[(size_t)b * LGW_ROLLUP_CELLS * G + k];
+#pragma unroll 4
+        for (uint32_t b = slice; b < n_blocks; b += LGW_ROLLUP_MERGE_SLICES) s += partial[(size_t)b * LGW_ROLLUP_CELLS * G + k];
         const uint32_t cell = k / G, g = k % G;
-        if (s) table[(size_t)g * LGW_ROLLUP_CELLS + cell] += s;
+        if (s) atomicAdd(table + (size_t)g * LGW_ROLLUP_CELLS + cell, s);
     }
     if (k < G) {
         uint32_t f = 0;
-        for (uint32_t b = 0; b < n_blocks; ++b) f |= partial_flag[(size_t)b * G + k];
+        for (uint32_t b = slice; b < n_blocks; b += LGW_ROLLUP_MERGE_SLICES) f |= partial_flag[(size_t)b * G + k];
         if (f) inexact[k] = 1;
     }
 }

@@ -90,9 +90,11 @@ class Engine:
 
     def _states(self, fn, slots):
         slots = np.ascontiguousarray(slots, dtype=np.uint32)
-        out = (_abi.StreamState * max(1, len(slots)))()
+        if len(slots) == 0:
+            return []
+        out = (_abi.StreamState * len(slots))()
         self._ck(fn(self._h, _ptr(slots), len(slots), out), "streams_state")
-        return [out[i] for i in range(len(slots))]
+        return out                            # a ctypes array: len(), indexing and iteration like a list, no per-element views built
 
     def state(self, slots):
         return self._states(self._lib.lgw_streams_state, slots)
@@ -131,11 +133,13 @@ class Engine:
             out = np.empty(max(n_bytes, 1), dtype=np.uint8)
         segs = np.zeros(max(n_segs, 1), dtype=SEG_DTYPE)
         cap = self.limits.rowq_cap
-        rows = (_abi.RowEvent * max(cap, 1))()
+        rows = getattr(self, "_rows_buf", None)
+        if rows is None:
+            rows = self._rows_buf = (_abi.RowEvent * max(cap, 1))()       # reused from step to step; the events returned are copies
         n_rows = C.c_uint32(0)
         self._ck(self._lib.lgw_sse_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot),
                                         n_segs, _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows)), "sse_step")
-        return StepResult(out[:n_bytes], segs[:n_segs], [rows[i] for i in range(n_rows.value)])
+        return StepResult(out[:n_bytes], segs[:n_segs], [_abi.RowEvent.from_buffer_copy(rows[i]) for i in range(n_rows.value)])
 
     def step_device(self, d_data: int, n_bytes: int, d_chunk_off: int, n_chunks: int, d_seg_chunk: int, d_seg_slot: int,
                     n_segs: int, d_out: int, d_segs: int):
@@ -149,6 +153,10 @@ class Engine:
         n_rows = C.c_uint32(0)
         self._ck(self._lib.lgw_fetch_rows(self._h, rows, cap, C.byref(n_rows)), "fetch_rows")
         return [rows[i] for i in range(n_rows.value)]
+
+    def last_step_direct(self) -> bool:
+        """True when the last host-buffer step moved the bytes with the kernel itself (pinned host buffers, no staging copies)."""
+        return bool(self._lib.lgw_last_step_direct(self._h))
 
     def sync(self):
         self._ck(self._lib.lgw_sync(self._h), "sync")

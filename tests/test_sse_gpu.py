@@ -390,3 +390,37 @@ def test_openai_shaped_streams_vs_oracle(engine, mode, events_per_chunk, n_strea
             assert st.n_chunks_emitted == len(relay.emitted) and st.bytes_emitted == sum(map(len, relay.emitted))
     finally:
         engine.set_mode(0)
+
+
+@pytest.mark.parametrize("direct", ["out", "both", "0"])
+def test_pinned_host_buffers_direct_modes(direct):
+    """Host-buffer step with page-locked buffers: the bulk kernel's TMA stores (and, with LGW_DIRECT=both, its loads) go straight
+    to / from host memory.  Same bytes, same segment results, same final states as the staged path on pageable buffers."""
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, "tests")
+import llmapigateway_b200 as L
+from llmapigateway_b200 import _abi
+from llmapigateway_b200.synth import sse_batch
+b = sse_batch(256, 128, seed=17)
+eng = L.Engine(max_streams=256, max_step_chunks=256 * 130 + 8, max_step_bytes=int(b.data.size) + 4096)
+status = np.full(256, 200, np.int32)
+eng.open(b.seg_slot, status)
+ref = eng.step(b.data.copy(), b.chunk_off, b.seg_chunk, b.seg_slot)          # pageable: staged path
+assert not eng.last_step_direct()
+ref_states = [bytes(s) for s in eng.close(b.seg_slot)]
+pin_in, pin_out = eng.alloc_pinned(int(b.data.size)), eng.alloc_pinned(int(b.data.size))
+pin_in[:] = b.data; pin_out[:] = 0
+eng.open(b.seg_slot, status)
+got = eng.step(pin_in, b.chunk_off, b.seg_chunk, b.seg_slot, out=pin_out)
+assert eng.last_step_direct() == (sys.argv[1] != "0"), eng.last_step_direct()
+states = [bytes(s) for s in eng.close(b.seg_slot)]
+assert np.array_equal(got.out, ref.out) and np.array_equal(pin_out, b.data)
+assert got.segs.tobytes() == ref.segs.tobytes() and states == ref_states
+assert _abi.usage_rec_to_dict(_abi.StreamState.from_buffer_copy(states[3]).rec) == b.truths[3].expected_row()
+print("DIRECT_OK")
+'''
+    r = subprocess.run([sys.executable, "-c", code, direct], capture_output=True, text=True, timeout=300, env=dict(os.environ, LGW_DIRECT=direct),
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "DIRECT_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
