@@ -212,6 +212,8 @@ struct R2Ctx {
     uint32_t ready, free_slots;  // bit per slot: template usable / slot empty (refreshed by refresh_slots, the same in every lane)
     uint32_t last_ra;            // position of the last number re-anchor (a mismatch right there is final)
     uint32_t hits_d;             // events matched by the default slot
+    uint32_t single;             // the stream's events follow the default slot but not its period (value spans of varying length):
+                                 //   judge them one by one, span by span (match_single), instead of window passes that re-anchor
 };
 
 // Where bytes are read from: the resident tile in shared memory, global memory outside it.  A small value type: the
@@ -937,8 +939,8 @@ R2_DEV_NOINLINE PassOut pass_step(R2Io io, uint32_t lane, uint32_t slot, uint32_
 
 // the first eight bytes of the event at ps against the first eight of a template (literal positions only): true = they part
 R2_DEV bool head_differs(const R2Io& io, const Tpl2* tp, uint32_t lane, uint32_t ps, uint32_t ev_end) {
-    bool diff = false;
-    if (lane < 8u && tp->lit[lane]) diff = ps + lane >= ev_end || (uint32_t)io_byte(io, ps + lane) != (uint32_t)tp->text[lane];
+    bool diff = false;                  // one byte per lane over the template's first 32 bytes (events of different kinds share "data: {" and more)
+    if (lane < tp->m.len && tp->lit[lane]) diff = ps + lane >= ev_end || (uint32_t)io_byte(io, ps + lane) != (uint32_t)tp->text[lane];
     return __any_sync(R2_FULL, diff) != 0;
 }
 
@@ -955,6 +957,17 @@ R2_DEV_NOINLINE OddOut odd_event(const StepArgs* ap, R2Shared* sh, R2Io io, uint
     uint32_t ready = 0, free_slots = 0;
     if (lane == 0) for (uint32_t k = 0; k < R2_SLOTS; ++k) { const uint32_t st = *(volatile uint32_t*)&sh->slot_state[k]; if (st == 2u) ready |= 1u << k; else if (st == 0u) free_slots |= 1u << k; }
     ready = __shfl_sync(R2_FULL, ready, 0); free_slots = __shfl_sync(R2_FULL, free_slots, 0);
+    // the stream terminator `data: [DONE]` LF LF, byte for byte (not JSON: no class, nothing to account; chat_logging.py:116-121,
+    // request_handler.py:122-131 skip it) -- the one non-JSON event every stream has
+    {
+        const uint32_t want = lane < 14u ? (uint32_t)(uint8_t)"data: [DONE]\n\n"[lane] : 0u;
+        const bool fits = ps + 14u <= ev_end;
+        const bool same = lane >= 14u || (fits && (uint32_t)io_byte(io, ps + lane) == want);
+        if (__all_sync(R2_FULL, same)) {
+            const bool third_lf = ps + 14u < sub_end && io_byte(io, ps + 14u) == '\n';           // LF run >= 3: the sequential path's case
+            if (!third_lf) { o.e = ps + 12u; return o; }
+        }
+    }
     for (uint32_t slot = 0; slot < R2_SLOTS; ++slot) {
         if (!(ready & (1u << slot)) || slot == skip_slot) continue;
         if (head_differs(io, &sh->tpl[slot], lane, ps, ev_end)) continue;            // (most wrong slots part within the first bytes)
@@ -1037,14 +1050,28 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
             c.k = fo.k; c.tile_lo = fo.tile_lo; c.tile_hi = fo.tile_hi; c.buf = fo.buf;
             c.high |= fo.high;
             if (fo.nfast) {
+                c.single = 0u;
                 c.hits_d += fo.nfast; c.s_open = fo.s_open;
                 if (dm.cls == PC_DATA) c.ev_a += fo.nfast;
                 if (dm.flags & PF_VALID_B) c.ev_b += fo.nfast;
             }
             if (fo.pos != c.pos) { c.pos = fo.pos; c.t = fo.t; continue; }
         }
-        // ---- one pass with its boundary lanes, limits and re-anchoring (out of line) ----
+        // ---- events that follow the default slot but not its period: one event per step, span by span ----
         bool try_pass = have_dflt;
+        if (have_dflt && c.single && c.t == 0u && c.pos == c.s_open && c.in_kept != 2u) {
+            const SingleOut so = match_single(io_of(c), &sh->tpl[c.dflt], lane, c.pos, r2_min(sub_end, c.pos + c.a->t.carry_cap + 2u));
+            if (so.ok) {
+                const TplMeta& dm = sh->tpl[c.dflt].m;
+                c.high |= so.high; ++c.hits_d;
+                if (dm.cls == PC_DATA) { if (c.in_kept == 1u) c.primed = 1; else ++c.ev_a; }
+                if (dm.flags & PF_VALID_B) ++c.ev_b;
+                c.pos = c.s_open = so.e + 2u; c.last_ra = R2_NONE;
+                continue;
+            }
+            try_pass = false;                                                  // not a default event at all: the other slots / the recogniser
+        }
+        // ---- one pass with its boundary lanes, limits and re-anchoring (out of line) ----
         if (try_pass && c.t == 0u && c.pos == c.s_open && head_differs(io_of(c), &sh->tpl[c.dflt], lane, c.pos, sub_end)) try_pass = false;   // not a default event: no pass
         if (try_pass) {
             const PassOut po = pass_step(io_of(c), lane, c.dflt, c.fast, c.pos, c.t, c.s_open, c.last_ra, sub_end, range_hi, c.in_kept == 1u ? 1u : 0u, c.a->t.carry_cap);
@@ -1056,6 +1083,7 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
                 if (dm.flags & PF_VALID_B) c.ev_b += po.nwr;
             }
             c.pos = po.pos; c.t = po.t; c.s_open = po.s_open; c.last_ra = po.last_ra;
+            if (po.reanchored) c.single = 1u;                                  // a value span of another length than the template's
             if (c.in_kept == 2u && (po.kind || po.reanchored) && c.s_open < c.kept_end) {      // a surprise inside the kept chunk: walk it the careful way
                 c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE;
                 continue;
@@ -1135,7 +1163,7 @@ k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t b
     }
     __syncthreads();
 
-    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0;
+    c.dflt = sh->dflt; c.last_ra = R2_NONE; c.hits_d = 0; c.single = 0;
     refresh_slots(c);
     c.seg = R2_NONE; c.ev_a = c.ev_b = c.a_usage = 0; c.high = 0;
     c.t = 0; c.pos = c.s_open = 0;

@@ -162,6 +162,18 @@ def test_c3_full_size_properties(engine, mode):
         assert sum(st.n_events_b for st in states) == 4096 * 513   # 512 deltas + usage event; [DONE] is not JSON
         assert sum(st.n_chunks_emitted for st in states) == b.n_chunks
         assert all(st.flags & _abi.SF_A_USAGE_BOUND for st in states)
+        # 256 of the full-size streams (every 16th) through the oracle itself: relayed chunks, usage rows, end state
+        from oracle import sse_oracle
+        for s in range(0, 4096, 16):
+            chunks = b.stream_chunks(s)
+            relay, tap = sse_oracle.run_stream(chunks, 200)
+            c0, c1 = int(b.seg_chunk[s]), int(b.seg_chunk[s + 1])
+            assert not relay.failed and states[s].phase == _abi.PHASE_COMMITTED
+            got = [res.out[int(b.chunk_off[c]):int(b.chunk_off[c + 1])].tobytes() for c in range(int(res.segs["emit_chunk_begin"][s]), c1)]
+            assert got == relay.emitted, s
+            rows = [r for r in res.rows if r.slot == int(b.seg_slot[s])]
+            from stream_compare import rows_from_result
+            assert canon_rows(rows_from_result(states[s], rows)) == canon_rows(tap.rows), s
     finally:
         e.close_engine()
 
