@@ -386,7 +386,7 @@ def run_c5(args):
             if world > 1:
                 dist.all_reduce(q["table"], op=dist.ReduceOp.SUM)
                 dist.all_reduce(q["inexact"], op=dist.ReduceOp.MAX)
-            rows = tab.emit(q["b0"], q["nb"], nm, C.c_void_p(q["table"].data_ptr()), C.c_void_p(q["inexact"].data_ptr())) if rank == 0 else None
+            rows = tab.emit(q["b0"], q["nb"], nm, C.c_void_p(q["table"].data_ptr()), C.c_void_p(q["inexact"].data_ptr()), pinned=True) if rank == 0 else None
             e2.record(stream)
         torch.cuda.synchronize(dev)
         if timed is not None:
@@ -404,7 +404,8 @@ def run_c5(args):
     for _ in range(K):
         for q in queries:
             barrier()
-            rows_of[q["label"]] = one(q, per_q[q["label"]])
+            r = one(q, per_q[q["label"]])
+            rows_of[q["label"]] = r.copy() if r is not None else None      # (not timed: the pinned row buffer is reused by the next rollup)
     barrier()
     launches = eng.launch_count() - l0
     sampler.stop()
@@ -599,7 +600,7 @@ def main():
     counters = eng.debug_counters()
 
     # correctness spot check of the timed configuration (not timed)
-    b, h, d = sets[(K - 1) % 2]
+    b, h, d = sets[KB % 2]                              # the set of the last step that ran (the breakdown loop's last)
     torch.cuda.synchronize(dev)
     assert torch.equal(d["out"], d["data"]), "re-emitted bytes differ from the input of committed streams"
     st = eng.state(b.seg_slot[:4])
