@@ -277,7 +277,9 @@ def run_c4(args):
     eng.load_rules(plans)
     up.prepare(mine, 3, alloc=eng.alloc_pinned)
     walker = chat.ChainBatch(eng, plans, providers, rules)
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)
+    if rank == 0:                                   # (one poller for the box: nvidia-smi takes a driver lock every sample)
+        sampler.start()
     for _ in range(W):
         out = walker.run(bodies, None, up, stream_ids=mine)
     barrier()
@@ -291,7 +293,8 @@ def run_c4(args):
         times.append(time.perf_counter() - t0)
     barrier()
     launches = eng.launch_count() - l0
-    sampler.stop()
+    if rank == 0:
+        sampler.stop()
     # correctness of the timed configuration (not timed): served-by round == first non-failing attempt, bytes == the upstream's
     kind = up.kind[:3, mine]
     first_ok = np.where((kind == 0).any(axis=0), (kind == 0).argmax(axis=0), -1)
@@ -321,7 +324,7 @@ def run_c4(args):
                        "counts": "chunks = the 64-B delta events of the streams that were served (the usage event and [DONE] of each are relayed too, not counted)",
                        "l2": "inputs larger than L2 at N<=2 (270 MB per walk); host buffers every step, nothing cached on the device between steps",
                        "parallelism": f"streams sharded x{world}, no collective"},
-            "chunks_relayed_incl_tail": relayed, "attempts": attempts, "exhausted_503": failed503, "per_gpu_chunks_per_s": per_gpu,
+            "chunks_relayed_incl_tail": relayed, "attempts": attempts, "walk_phases_ms_rank0": {k: round(v * 1e3, 3) for k, v in out.timings.items()}, "exhausted_503": failed503, "per_gpu_chunks_per_s": per_gpu,
             "json_gbs": value * EVENT_BYTES / 1e9, "clocks": sampler.summary(), "gpu_launches": int(launches),
             "e2e": {"value": value, "unit": UNIT, "ms_per_step": step_s * 1e3, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
                     "note": "the walk is host-driven: `value` IS the end-to-end number (pinned host buffers -> device -> pinned host buffers every round)"},

@@ -233,6 +233,7 @@ class ChainOutcome:
     attempts: int = 0
     chunks_relayed: int = 0
     steps: int = 0
+    timings: dict = field(default_factory=dict)     # seconds per phase of the walk (host clock)
 
     def emitted(self, i: int) -> bytes:
         r = int(self.served_round[i])
@@ -240,8 +241,9 @@ class ChainOutcome:
 
     def usage_rows(self):
         """(request index, usage dict) of every served request: the last DB row of chat_logging.py:150."""
-        for idx, sts in self.states:
-            for i, st in zip(idx, sts):
+        for idx, sts, ok in self.states:
+            for i, k in zip(idx, ok):
+                st = sts[int(k)]
                 if st.flags & _abi.SF_EMITTED_ANY:
                     yield int(i), _abi.usage_rec_to_dict(st.rec)
 
@@ -296,11 +298,20 @@ class ChainBatch:
         return out
 
     def run(self, bodies: list, api_keys: list | None, upstream, stream_ids=None) -> ChainOutcome:
+        import time
         eng = self.eng
         n = len(bodies)
         ids = np.arange(n) if stream_ids is None else np.asarray(stream_ids)
+        tm = {"scan": 0.0, "schedule": 0.0, "rewrite": 0.0, "upstream": 0.0, "open": 0.0, "step": 0.0, "details": 0.0, "close": 0.0, "control": 0.0}
+        t_all = t0 = time.perf_counter()
+
+        def lap(key):
+            nonlocal t0
+            t1 = time.perf_counter(); tm[key] += t1 - t0; t0 = t1
+
         buf, off = rw.pack_bodies(bodies)
         scans, models = eng.scan_bodies(bodies)
+        lap("scan")
         out = ChainOutcome(np.full(n, -1, np.int32), [None] * n, np.zeros((n, 2), np.int64), [], [])
         # ---- schedules: one per distinct (model, rotation start) ---------------------------------------------------------------
         status = scans["status"]
@@ -344,6 +355,7 @@ class ChainBatch:
         slot_cap = (6 * longest + self.plans.max_growth() + 64 + 15) & ~15
         active = np.nonzero(sid >= 0)[0]
         rnd = 0
+        lap("schedule")
         while active.size:
             going = active[sched_len[sid[active]] > rnd]
             if not going.size:
@@ -357,9 +369,12 @@ class ChainBatch:
                 gather = np.repeat(off[going].astype(np.int64) - sub_off[:-1].astype(np.int64), lens) + np.arange(int(sub_off[-1]), dtype=np.int64)
                 sub_buf = buf[gather]
             plan_idx = plan_tab[sid[going], rnd]
+            lap("control")
             pay, pay_off, res = eng.rewrite_packed(sub_buf, sub_off, plan_idx, slot_cap)
+            lap("rewrite")
             urls = [sched_list[k][rnd][1] for k in sid[going]] if getattr(upstream, "wants_urls", True) else None
             ans: Answers = upstream(rnd, ids[going], urls, pay, pay_off)
+            lap("upstream")
             out.attempts += int(going.size)
             bad_body = res["status"] != rw.BODY_OK
             http_fail = (ans.http_status >= 400) & ~bad_body
@@ -381,15 +396,20 @@ class ChainBatch:
             out.round_out.append(None)
             if m:
                 slots = np.arange(m, dtype=np.uint32)
+                lap("control")
                 eng.open(slots, np.full(m, 200, np.int32))
                 arena = self._arena(rnd, int(ans.data.size))
+                lap("open")
                 r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots, **({"out": arena} if arena is not None else {}))
+                lap("step")
                 out.steps += 1
                 out.round_out[-1] = r.out
                 phase, verdict, eb = r.segs["phase"], r.segs["verdict"], r.segs["emit_chunk_begin"].astype(np.int64)
                 is_failed = phase == _abi.PHASE_FAILED
                 fidx = np.nonzero(is_failed)[0]
-                for d, k in zip(eng.details(slots[fidx]), fidx):
+                dets = eng.details(slots[fidx])
+                lap("details")
+                for d, k in zip(dets, fidx):
                     i = int(sreq[k])
                     text = d.decode("utf-8", errors="replace")
                     if verdict[k] == _abi.VERDICT_FAIL_PARSE:
@@ -404,8 +424,10 @@ class ChainBatch:
                 out.spans[sreq[ok], 1] = co[seg_end[ok]]
                 out.served_round[sreq[ok]] = rnd
                 out.chunks_relayed += int((seg_end[ok] - first[ok]).sum())
+                lap("control")
                 states = eng.close(slots)
-                out.states.append((sreq[ok], [states[int(k)] for k in ok]))
+                lap("close")
+                out.states.append((sreq[ok], states, ok))
             active = np.array(sorted(failed_now), dtype=np.int64)
             rnd += 1
         for i in np.nonzero(out.served_round == -1)[0]:                            # chat.py:197-198
@@ -416,4 +438,7 @@ class ChainBatch:
                 out.detail[i] = exhausted_text(req_model[i], failure_text(rule, sp, text))
             else:
                 out.detail[i] = exhausted_text(req_model[i], "No providers were attempted.")
+        lap("control")
+        tm["total"] = time.perf_counter() - t_all
+        out.timings = tm
         return out
