@@ -248,6 +248,35 @@ class ChainOutcome:
                     yield int(i), _abi.usage_rec_to_dict(st.rec)
 
 
+def _group_rows(rows: np.ndarray, lens: np.ndarray):
+    """Group equal (length, bytes) rows: (index of a first member per group, group of every row).  A 64-bit hash of every row
+    does the grouping (one pass, no 256-byte key sort); the groups are then verified byte for byte, and in the never-expected
+    case of a collision the exact structured sort is used instead."""
+    cap = rows.shape[1]
+    words = rows.view(np.uint64) if cap % 8 == 0 else rows.astype(np.uint64)
+    mult = (np.arange(words.shape[1], dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0xD6E8FEB86659FD93)) | np.uint64(1)
+    h = (words * mult).sum(axis=1, dtype=np.uint64) ^ (lens.astype(np.uint64) * np.uint64(0xFF51AFD7ED558CCD))
+    _, first, inverse = np.unique(h, return_index=True, return_inverse=True)
+    if ((rows == rows[first[inverse]]).all(axis=1) & (lens == lens[first[inverse]])).all():
+        return first, inverse
+    key = np.zeros(rows.shape[0], dtype=[("len", "<u8"), ("text", f"S{cap}")])
+    key["len"] = lens
+    key["text"] = rows.view(f"S{cap}").ravel()
+    _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+    return first, inverse
+
+
+class _NameView:
+    """request index -> requested model name, without a per-request Python list"""
+
+    def __init__(self, names, index):
+        self.names, self.index = names, index
+
+    def __getitem__(self, i):
+        k = int(self.index[i])
+        return self.names[k] if k >= 0 else None
+
+
 class ChainBatch:
     """Lock-step walker over `n` streaming requests that share one engine (one GPU).  `upstream(round, ids, urls, payload
     buffer, payload offsets) -> Answers` is the provider side (in the bench: the local synthetic SSE generator of the north star).
@@ -310,47 +339,56 @@ class ChainBatch:
             t1 = time.perf_counter(); tm[key] += t1 - t0; t0 = t1
 
         buf, off = rw.pack_bodies(bodies)
-        scans, models = eng.scan_bodies(bodies)
+        scans, model_rows = eng.scan_packed(buf, off)
         lap("scan")
         out = ChainOutcome(np.full(n, -1, np.int32), [None] * n, np.zeros((n, 2), np.int64), [], [])
-        # ---- schedules: one per distinct (model, rotation start) ---------------------------------------------------------------
+        # ---- schedules: one per distinct (model, rotation start); requests are grouped by their model bytes, not visited one by one ----
         status = scans["status"]
-        sched_list, sched_of = [], {}
+        sched_list = []
         sid = np.full(n, -1, np.int32)
-        req_model = [None] * n
-        for i in range(n):
-            st = int(status[i])
-            if st == rw.BODY_PARSE_ERROR:
-                pst, _, _, root = eng.rewrite_bodies([bodies[i]], [self.plans.plan_index(None)], with_matched=True)[0]
-                out.detail[i] = f"Error reading request body: {_request_error_text(bodies[i], (pst, root))}"; out.served_round[i] = -2
-                continue
-            if st == rw.BODY_NO_MODEL:
-                out.detail[i] = "Missing 'model' in request body"; out.served_round[i] = -2
-                continue
-            mb = models[i]
-            ent = sched_of.get(mb)
-            if ent is None:
-                name = mb.decode("utf-8")
+        req_name_of = np.full(n, -1, np.int32)                                     # request -> index into `names`
+        names = []
+        for i in np.nonzero(status == rw.BODY_PARSE_ERROR)[0]:
+            i = int(i)
+            pst, _, _, root = eng.rewrite_bodies([bodies[i]], [self.plans.plan_index(None)], with_matched=True)[0]
+            out.detail[i] = f"Error reading request body: {_request_error_text(bodies[i], (pst, root))}"; out.served_round[i] = -2
+        for i in np.nonzero(status == rw.BODY_NO_MODEL)[0]:
+            out.detail[int(i)] = "Missing 'model' in request body"; out.served_round[int(i)] = -2
+        okreq = np.nonzero(status == rw.BODY_OK)[0]
+        if okreq.size:
+            cap = model_rows.shape[1]
+            mlen = np.minimum(scans["model_len"][okreq], cap).astype(np.uint64)
+            rows = np.ascontiguousarray(model_rows[okreq])
+            first, inverse = _group_rows(rows, mlen)
+            for u in range(len(first)):
+                members = okreq[inverse == u]
+                i0 = int(okreq[first[u]])
+                name = bytes(model_rows[i0, :int(mlen[first[u]])]).decode("utf-8")
+                names.append(name)
+                req_name_of[members] = len(names) - 1
                 cfg = self.rules.get(name)
-                ent = sched_of[mb] = (name, bool(cfg and cfg["rotate_models"] and len(cfg["fallback_models"]) > 1), {})
-            name, rotates, by_start = ent
-            req_model[i] = name
-            start = 0
-            if rotates:                                                            # chat.py:65-78, serial per request
-                start = self.rotation.get_next_model_index(api_key=(api_keys[i] if api_keys else ""), gateway_model=name,
-                                                           total_models=len(self.rules[name]["fallback_models"]))
-            k = by_start.get(start)
-            if k is None:
-                k = by_start[start] = len(sched_list)
-                sched_list.append(self._schedule(name, start))
-            sid[i] = k
+                if cfg and cfg["rotate_models"] and len(cfg["fallback_models"]) > 1:   # chat.py:65-78: a serial read-modify-write per request, in request order
+                    by_start = {}
+                    for i in members:
+                        start = self.rotation.get_next_model_index(api_key=(api_keys[int(i)] if api_keys else ""), gateway_model=name,
+                                                                   total_models=len(cfg["fallback_models"]))
+                        k = by_start.get(start)
+                        if k is None:
+                            k = by_start[start] = len(sched_list)
+                            sched_list.append(self._schedule(name, start))
+                        sid[int(i)] = k
+                else:
+                    sid[members] = len(sched_list)
+                    sched_list.append(self._schedule(name, 0))
+        req_model = _NameView(names, req_name_of)
         depth = max((len(s) for s in sched_list), default=0)
         plan_tab = np.zeros((max(len(sched_list), 1), max(depth, 1)), np.uint32)
         sched_len = np.zeros(max(len(sched_list), 1), np.int32)
         for k, sc in enumerate(sched_list):
             sched_len[k] = len(sc)
             plan_tab[k, :len(sc)] = [a[0] for a in sc]
-        last_fail = {}                                                             # request -> (round, error_detail text)
+        fail_round = np.full(n, -1, np.int32)                                      # request -> round of its last failed attempt ...
+        fail_text = [None] * n                                                     # ... and that attempt's error detail (bytes or str; decoded only for the 503s)
         longest = max((len(b) for b in bodies), default=0)
         slot_cap = (6 * longest + self.plans.max_growth() + 64 + 15) & ~15
         active = np.nonzero(sid >= 0)[0]
@@ -379,17 +417,14 @@ class ChainBatch:
             bad_body = res["status"] != rw.BODY_OK
             http_fail = (ans.http_status >= 400) & ~bad_body
             streaming = ~(http_fail | bad_body)                                    # these sent a response stream, in order
-            failed_now = []
+            failed_now = [going[bad_body | http_fail]]
             for k in np.nonzero(bad_body)[0]:
                 i = int(going[k]); url = sched_list[sid[i]][rnd][1]
-                last_fail[i] = (rnd, f"Unexpected error during request to {url}: request body not modelled by the engine ({rw.STATUS_NAMES[int(res['status'][k])]})")
-                failed_now.append(i)
-            eb_iter = iter(ans.error_bodies)
-            for k in np.nonzero(ans.http_status >= 400)[0]:
-                body = next(eb_iter)
+                fail_text[i] = f"Unexpected error during request to {url}: request body not modelled by the engine ({rw.STATUS_NAMES[int(res['status'][k])]})"
+            for k, body in zip(np.nonzero(ans.http_status >= 400)[0], ans.error_bodies):
                 if not bad_body[k]:
-                    last_fail[int(going[k])] = (rnd, bytes(body).decode("utf-8"))
-                    failed_now.append(int(going[k]))
+                    fail_text[int(going[k])] = ("http", body)                      # (decoded at the end, for the requests that end in a 503)
+            fail_round[going[bad_body | http_fail]] = rnd
             # ---- everything the upstreams streamed back: one step --------------------------------------------------------------
             sreq = going[streaming]
             m = int(sreq.size)
@@ -411,30 +446,36 @@ class ChainBatch:
                 lap("details")
                 for d, k in zip(dets, fidx):
                     i = int(sreq[k])
-                    text = d.decode("utf-8", errors="replace")
                     if verdict[k] == _abi.VERDICT_FAIL_PARSE:
-                        text = f"Unexpected error during request to {sched_list[sid[i]][rnd][1]}: first event is not valid JSON: {text[:200]}"
-                    last_fail[i] = (rnd, text)
-                    failed_now.append(i)
+                        d = f"Unexpected error during request to {sched_list[sid[i]][rnd][1]}: first event is not valid JSON: {d.decode('utf-8', errors='replace')[:200]}"
+                    fail_text[i] = d
+                fail_round[sreq[fidx]] = rnd
+                failed_now.append(sreq[fidx])
                 ok = np.nonzero(~is_failed)[0]
                 seg_end = ans.seg_chunk[1:].astype(np.int64)
                 first = np.minimum(eb, seg_end)
-                co = ans.chunk_off.astype(np.int64)
-                out.spans[sreq[ok], 0] = co[first[ok]]
-                out.spans[sreq[ok], 1] = co[seg_end[ok]]
+                out.spans[sreq[ok], 0] = ans.chunk_off[first[ok]]                   # (indexing the offsets, not converting all of them)
+                out.spans[sreq[ok], 1] = ans.chunk_off[seg_end[ok]]
                 out.served_round[sreq[ok]] = rnd
                 out.chunks_relayed += int((seg_end[ok] - first[ok]).sum())
                 lap("control")
                 states = eng.close(slots)
                 lap("close")
                 out.states.append((sreq[ok], states, ok))
-            active = np.array(sorted(failed_now), dtype=np.int64)
+            active = np.sort(np.concatenate(failed_now)).astype(np.int64) if failed_now else np.zeros(0, np.int64)
             rnd += 1
         for i in np.nonzero(out.served_round == -1)[0]:                            # chat.py:197-198
             i = int(i)
-            if i in last_fail:
-                fr, text = last_fail[i]
-                _, _, rule, sp = sched_list[sid[i]][fr]
+            if fail_round[i] >= 0:
+                text = fail_text[i]
+                _, url, rule, sp = sched_list[sid[i]][int(fail_round[i])]
+                if isinstance(text, tuple):                                        # request_handler.py:27-30: body.decode("utf-8"); a decode error lands in :183-187
+                    try:
+                        text = bytes(text[1]).decode("utf-8")
+                    except UnicodeDecodeError as e:
+                        text = f"Unexpected error during request to {url}: {str(e)}"
+                elif not isinstance(text, str):
+                    text = bytes(text).decode("utf-8", errors="replace")
                 out.detail[i] = exhausted_text(req_model[i], failure_text(rule, sp, text))
             else:
                 out.detail[i] = exhausted_text(req_model[i], "No providers were attempted.")

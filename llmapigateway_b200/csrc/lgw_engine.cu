@@ -46,6 +46,7 @@ struct lgw_engine {
     RollupRow* d_rows = nullptr; uint64_t d_rows_cap = 0; unsigned long long* d_nrows = nullptr;
     uint8_t* d_partial = nullptr; size_t d_partial_cap = 0; uint32_t* d_tiles = nullptr; uint32_t d_tiles_cap = 0;
     bool rollup_attr_set = false, rollup_force_global = false;
+    uint8_t* d_details = nullptr; size_t d_details_cap = 0;      // staging of lgw_streams_details
     bool last_direct = false;       // the last host-buffer step ran in direct mode (kernel-driven PCIe traffic)
     float ms[5]{0, 0, 0, 0, 0};     // prime, relay, commit, usage extract, whole host-buffer step
     bool timed = false;
@@ -133,7 +134,7 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     scratch_free(e->scratch);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->rev) if (ev) cudaEventDestroy(ev);
-    cudaFree(e->d_rows); cudaFree(e->d_nrows); cudaFree(e->d_partial); cudaFree(e->d_tiles);
+    cudaFree(e->d_rows); cudaFree(e->d_nrows); cudaFree(e->d_partial); cudaFree(e->d_tiles); cudaFree(e->d_details);
     cudaFree(e->d_plans); cudaFree(e->d_ops); cudaFree(e->d_blob);
     cudaFree(e->b_in); cudaFree(e->b_slots); cudaFree(e->b_out); cudaFree(e->b_models); cudaFree(e->b_off); cudaFree(e->b_out_off);
     cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans); cudaFree(e->b_redo);
@@ -231,17 +232,20 @@ extern "C" int lgw_streams_details(lgw_engine* e, const uint32_t* slots, uint32_
     if (n == 0) return LGW_OK;
     for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->lim.max_streams) return LGW_ERR_ARG;
     CK(e, cudaSetDevice(e->device));
-    uint32_t* d_slots = nullptr; uint8_t* d_out = nullptr; uint32_t* d_lens = nullptr;
-    CK(e, cudaMallocAsync((void**)&d_slots, (size_t)n * 4, e->stream));
-    CK(e, cudaMallocAsync((void**)&d_lens, (size_t)n * 4, e->stream));
-    CK(e, cudaMallocAsync((void**)&d_out, (size_t)n * stride, e->stream));
+    // grow-only staging owned by the engine (a stream-ordered allocation per call gave memory back to the OS at every synchronisation)
+    const size_t need = (size_t)n * 8 + (size_t)n * stride;
+    if (need > e->d_details_cap) {
+        cudaFree(e->d_details); e->d_details = nullptr; e->d_details_cap = 0;
+        CK(e, cudaMalloc((void**)&e->d_details, need + need / 2));
+        e->d_details_cap = need + need / 2;
+    }
+    uint32_t* d_slots = (uint32_t*)e->d_details; uint32_t* d_lens = d_slots + n; uint8_t* d_out = e->d_details + (size_t)n * 8;
     CK(e, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     lgw::k_details_gather<<<(n * 32 + 255) / 256, 256, 0, e->stream>>>(e->t, d_slots, n, d_out, stride, d_lens);
     ++e->launches;
     CK(e, cudaMemcpyAsync(lens, d_lens, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaMemcpyAsync(buf, d_out, (size_t)n * stride, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    cudaFreeAsync(d_slots, e->stream); cudaFreeAsync(d_lens, e->stream); cudaFreeAsync(d_out, e->stream);
     return LGW_OK;
 }
 
@@ -478,7 +482,7 @@ extern "C" int lgw_usage_rollup_accum(lgw_engine* e, const int64_t* d_ts_us, con
     a.bucket0 = bucket0; a.n_buckets = n_buckets; a.n_models = n_models;
     a.table = (unsigned long long*)d_table; a.inexact = d_inexact; a.oob = d_oob;
     const uint64_t groups = (uint64_t)n_buckets * n_models;
-    const bool privatised = groups <= LGW_ROLLUP_SMEM_GROUPS && n >= 65536 && !e->rollup_force_global;
+    const bool privatised = groups <= LGW_ROLLUP_SMEM_GROUPS && n >= 65536 && n < 0xFFFFFFFFull && !e->rollup_force_global;
     if (privatised) {                     // scratch for the per-block partial tables (allocated outside the timed region)
         const size_t need = (size_t)e->sm_count * groups * (LGW_ROLLUP_CELLS * 8 + 4);
         if (need > e->d_partial_cap) {

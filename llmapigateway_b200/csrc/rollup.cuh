@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(256) k_rollup_accum(RollupArgs a) {
 // different groups hit different banks).  A 64-bit add is one native 32-bit shared atomic on `lo` plus -- only on a carry or a
 // negative addend -- one on `hi`.  At the end the block stores its partial table to global scratch (plain coalesced stores) and
 // k_rollup_merge folds the partials into the caller's table: no global atomics at all.
-#define LGW_ROLLUP_SMEM_GROUPS 2560u                                  // 2560 x (10 x 8 + 4) B = 215 040 B
-LGW_RHD size_t rollup_smem_bytes(uint32_t groups) { return (size_t)groups * (LGW_ROLLUP_CELLS * 8 + 4); }
+#define LGW_ROLLUP_SMEM_GROUPS 2560u                                  // 2560 x (10 x 8 + 4) B = 215 040 B (+ 8 KiB of queues; records are indexed with 32 bits)
+LGW_RHD size_t rollup_smem_bytes(uint32_t groups) { return (size_t)groups * (LGW_ROLLUP_CELLS * 8 + 4) + 32u * 64u * 4u; }   // + the warps' index queues
 
 __device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, uint32_t v, uint32_t sign_ext) {
     const uint32_t old = atomicAdd(lo, v);
@@ -200,19 +200,46 @@ __device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, uint32_t 
     if (up) atomicAdd(hi, up);
 }
 
+// one record into the block's table (all 32 lanes of the caller are expected to be here together: see the queue below)
+__device__ __forceinline__ uint32_t rollup_smem_record(const RollupArgs& a, uint64_t i, int64_t ts, uint32_t G, uint32_t* lo, uint32_t* hi, uint32_t* flag) {
+    const int64_t b = bucket_of(ts, a.period) - a.bucket0;
+    const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
+    if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) return 1u;
+    const uint32_t g = (uint32_t)b * a.n_models + mr;
+    int32_t v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = __ldg(a.tok[k] + i);
+    const double cost = __ldg(a.cost + i);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) smem_add64(lo + k * G + g, hi + k * G + g, (uint32_t)v[k], v[k] < 0 ? 0xFFFFFFFFu : 0u);
+    smem_add64(lo + 5 * G + g, hi + 5 * G + g, 1u, 0u);
+    uint32_t limb[4];
+    if (!cost_to_limbs(cost, limb)) flag[g] = 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (limb[k]) smem_add64(lo + (6 + k) * G + g, hi + (6 + k) * G + g, limb[k], 0u);
+    return 0u;
+}
+
+// Records that pass the window filter are first QUEUED per warp (their indices, 64-entry ring in shared memory, positions from a
+// ballot prefix) and handled 32 at a time by the whole warp: with a 2-week window over 400 days 3.5 % of the records pass, and
+// without the queue 68 % of the warp trips would run the bucket / load / atomics path for one or two lanes.
+#define LGW_ROLLUP_QUEUE 64u
 __global__ void __launch_bounds__(1024, 1) k_rollup_accum_smem(RollupArgs a, unsigned long long* __restrict__ partial, uint32_t* __restrict__ partial_flag) {
     extern __shared__ uint32_t sm[];
     const uint32_t G = a.n_buckets * a.n_models;
     uint32_t* lo = sm;                                                // [CELLS][G]
     uint32_t* hi = sm + (size_t)LGW_ROLLUP_CELLS * G;                 // [CELLS][G]
     uint32_t* flag = hi + (size_t)LGW_ROLLUP_CELLS * G;               // [G]
+    uint32_t* queue = flag + G + (threadIdx.x >> 5) * LGW_ROLLUP_QUEUE;   // this warp's ring of record indices
     for (uint32_t k = threadIdx.x; k < G * (2 * LGW_ROLLUP_CELLS + 1); k += blockDim.x) sm[k] = 0;
     __syncthreads();
-    uint32_t oob = 0;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    uint32_t oob = 0, head = 0, tail = 0;                             // (head, tail: the same in every lane of the warp)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    // four timestamps per trip are requested before any is looked at: with a window most records end at the filter, and the loop
-    // would otherwise have one 8-byte load in flight per thread
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += 4 * stride) {
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t trips = a.n > (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u) ? (a.n - ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) + 4 * stride - 1) / (4 * stride) : 0;
+    for (uint64_t t = 0; t < trips; ++t) {                            // (a warp-uniform trip count: the ballots below need all 32 lanes)
+        const uint64_t i0 = first + t * 4 * stride;
         int64_t tsv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { const uint64_t i = i0 + u * stride; tsv[u] = i < a.n ? __ldg(a.ts_us + i) : INT64_MIN; }
@@ -220,24 +247,22 @@ __global__ void __launch_bounds__(1024, 1) k_rollup_accum_smem(RollupArgs a, uns
         for (int u = 0; u < 4; ++u) {
             const uint64_t i = i0 + u * stride;
             const int64_t ts = tsv[u];
-            if (i >= a.n) continue;
-            if ((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us)) continue;     // tokens_usage_db.py:255-266
-            const int64_t b = bucket_of(ts, a.period) - a.bucket0;
-            const uint32_t mr = (uint32_t)__ldg(a.model_rank + i);
-            if (b < 0 || b >= (int64_t)a.n_buckets || mr >= a.n_models) { ++oob; continue; }
-            const uint32_t g = (uint32_t)b * a.n_models + mr;
-            int32_t v[5];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) v[k] = __ldg(a.tok[k] + i);
-            const double cost = __ldg(a.cost + i);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) smem_add64(lo + k * G + g, hi + k * G + g, (uint32_t)v[k], v[k] < 0 ? 0xFFFFFFFFu : 0u);
-            smem_add64(lo + 5 * G + g, hi + 5 * G + g, 1u, 0u);
-            uint32_t limb[4];
-            if (!cost_to_limbs(cost, limb)) flag[g] = 1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (limb[k]) smem_add64(lo + (6 + k) * G + g, hi + (6 + k) * G + g, limb[k], 0u);
+            const bool in = i < a.n && !((a.has_start && ts < a.start_us) || (a.has_end && ts > a.end_us));     // tokens_usage_db.py:255-266
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) queue[(tail + __popc(m & lt)) & (LGW_ROLLUP_QUEUE - 1u)] = (uint32_t)i;
+            tail += __popc(m);
+            __syncwarp();
+            if (tail - head >= 32u) {
+                const uint64_t j = queue[(head + lane) & (LGW_ROLLUP_QUEUE - 1u)];
+                oob += rollup_smem_record(a, j, __ldg(a.ts_us + j), G, lo, hi, flag);
+                head += 32u;
+                __syncwarp();
+            }
         }
+    }
+    if (lane < tail - head) {
+        const uint64_t j = queue[(head + lane) & (LGW_ROLLUP_QUEUE - 1u)];
+        oob += rollup_smem_record(a, j, __ldg(a.ts_us + j), G, lo, hi, flag);
     }
     if (oob) atomicAdd(a.oob, oob);
     __syncthreads();

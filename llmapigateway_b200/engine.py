@@ -114,11 +114,14 @@ class Engine:
         n = len(slots)
         if n == 0:
             return []
-        stride = stride or self.limits.detail_cap
+        stride = stride or min(self.limits.detail_cap, 1024)       # (a detail longer than the stride is cut: pass stride=detail_cap for the full text)
         buf = np.empty(n * stride, dtype=np.uint8)
         lens = np.zeros(n, dtype=np.uint32)
         self._ck(self._lib.lgw_streams_details(self._h, _ptr(slots), n, _ptr(buf), stride, _ptr(lens)), "streams_details")
-        return [bytes(buf[i * stride:i * stride + int(lens[i])]) for i in range(n)]
+        if int(lens.max()) >= stride and stride < self.limits.detail_cap:        # something was cut: once more with the full capacity
+            return self.details(slots, self.limits.detail_cap)
+        raw = buf.tobytes()
+        return [raw[i * stride:i * stride + int(lens[i])] for i in range(n)]
 
     # -- the hot path --------------------------------------------------------------------------------
     def step(self, data: np.ndarray, chunk_off: np.ndarray, seg_chunk: np.ndarray, seg_slot: np.ndarray,
@@ -194,16 +197,22 @@ class Engine:
                                           _ptr(blob), len(blob)), "rules_load")
         self._plan_growth = plans.max_growth()
 
+    def scan_packed(self, buf: np.ndarray, off: np.ndarray, model_cap: int = 256):
+        """chat.py:31-45 for n packed bodies: (SCAN_DTYPE[n], uint8 [n, model_cap] model bytes, zero padded)."""
+        from . import rewrite as rw
+        n = len(off) - 1
+        scans = np.zeros(max(n, 1), dtype=rw.SCAN_DTYPE)
+        models = np.zeros((max(n, 1), model_cap), dtype=np.uint8)
+        self._ck(self._lib.lgw_bodies_scan(self._h, _ptr(buf), _ptr(off), n, model_cap, _ptr(scans), _ptr(models)), "bodies_scan")
+        return scans[:n], models[:n]
+
     def scan_bodies(self, bodies, model_cap: int = 256):
         """chat.py:31-45 for a batch: (SCAN_DTYPE array, list of model bytes)."""
         from . import rewrite as rw
         buf, off = rw.pack_bodies(bodies)
-        n = len(bodies)
-        scans = np.zeros(max(n, 1), dtype=rw.SCAN_DTYPE)
-        models = np.zeros(max(n, 1) * model_cap, dtype=np.uint8)
-        self._ck(self._lib.lgw_bodies_scan(self._h, _ptr(buf), _ptr(off), n, model_cap, _ptr(scans), _ptr(models)), "bodies_scan")
-        texts = [bytes(models[i * model_cap:i * model_cap + min(int(scans["model_len"][i]), model_cap)]) for i in range(n)]
-        return scans[:n], texts
+        scans, models = self.scan_packed(buf, off, model_cap)
+        lens = np.minimum(scans["model_len"], model_cap)
+        return scans, [bytes(models[i, :int(lens[i])]) for i in range(len(bodies))]
 
     def rewrite_packed(self, buf: np.ndarray, off: np.ndarray, plan_idx: np.ndarray, slot_cap: int, out: np.ndarray | None = None):
         """One upstream attempt for n packed bodies -> (out bytes, out_off[n+1], RESULT_DTYPE[n])."""

@@ -95,3 +95,11 @@ class FakeEngine:
 
     def details(self, slots, stride=None):
         return [self.detail(s) for s in slots]
+
+    def scan_packed(self, buf, off, model_cap: int = 256):
+        bodies = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+        scans, texts = self.scan_bodies(bodies, model_cap)
+        models = np.zeros((len(bodies), model_cap), dtype=np.uint8)
+        for i, t in enumerate(texts):
+            models[i, :len(t)] = np.frombuffer(t, dtype=np.uint8)
+        return scans, models
