@@ -315,6 +315,21 @@ typedef struct lgw_doc_usage {
 /* host pointers; document i is docs[doc_off[i] .. doc_off[i+1]) */
 int lgw_documents_usage(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off /* n+1 */, uint32_t n, lgw_doc_usage* out);
 
+/* ---- error detail of a failing non-streaming upstream response (request_handler.py:167-169) ----
+ *     error_detail = response_json.get("error", {}).get("message") or response_json.get("detail")
+ * for documents that lgw_bodies_rewrite (response plan) reported as valid JSON with an object root and a top-level "error" or
+ * "detail" key.  result: 0 None, 1 a str (text[i*text_stride ..][0..text_len), UTF-8, unescaped), 2 True, 3 False,
+ * 4 "error" is not an object (`.get` raises AttributeError: the type name follows from error_kind; for a number the text holds
+ * its literal), 5 not modelled (a non-empty container wins, a lone surrogate, text longer than text_stride), 6 a number wins:
+ * the text holds its literal as spelt in the document.  kinds: 0 absent, 1 string, 2 null, 3 true, 4 false, 5 numeric zero, 6 number, 7 {}, 8 object, 9 [], 10 array. */
+typedef struct lgw_doc_error {
+    uint8_t result;
+    uint8_t error_kind, message_kind, detail_kind;
+    uint32_t text_len;
+} lgw_doc_error;
+int lgw_documents_error_detail(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off /* n+1 */, uint32_t n, lgw_doc_error* out,
+                               uint8_t* text, uint32_t text_stride);
+
 /* ---- device memory helpers for callers without their own CUDA allocator ----------------------------- */
 int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out);
 int lgw_device_free(lgw_engine* e, void* p);

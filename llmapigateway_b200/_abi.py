@@ -98,3 +98,11 @@ def usage_rec_to_dict(rec: UsageRec) -> dict:
         else:
             out[name] = _rec_text(rec, name, ln) if val.kind == KIND_STR else val_to_py(val)
     return out
+
+
+class DocError(C.Structure):          # == lgw_doc_error
+    _fields_ = [("result", C.c_uint8), ("error_kind", C.c_uint8), ("message_kind", C.c_uint8), ("detail_kind", C.c_uint8), ("text_len", C.c_uint32)]
+
+
+EDR_NONE, EDR_TEXT, EDR_TRUE, EDR_FALSE, EDR_ERROR_NOT_OBJECT, EDR_EXOTIC, EDR_ZERO = range(7)
+ED_TYPE_NAMES = {1: "str", 2: "NoneType", 3: "bool", 4: "bool", 5: "int", 6: "int", 9: "list", 10: "list"}   # (numbers: int or float, see responses.py)

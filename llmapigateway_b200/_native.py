@@ -13,7 +13,7 @@ EXPORTS = [
     "lgw_abi_version", "lgw_engine_create", "lgw_engine_destroy", "lgw_last_error", "lgw_engine_set_stream",
     "lgw_streams_open", "lgw_streams_state", "lgw_stream_detail", "lgw_streams_close",
     "lgw_sse_step", "lgw_sse_step_device", "lgw_fetch_rows", "lgw_sync", "lgw_last_step_ms", "lgw_last_step_kernel_ms", "lgw_engine_set_kernel_timing",
-    "lgw_launch_count", "lgw_last_step_direct", "lgw_rollup_set_path", "lgw_streams_details", "lgw_alloc_pinned", "lgw_free_pinned",
+    "lgw_launch_count", "lgw_documents_error_detail", "lgw_last_step_direct", "lgw_rollup_set_path", "lgw_streams_details", "lgw_alloc_pinned", "lgw_free_pinned",
     "lgw_usage_rollup_accum", "lgw_usage_rollup_emit", "lgw_rollup_bucket_of", "lgw_rollup_last_ms",
     "lgw_device_alloc", "lgw_device_free", "lgw_device_upload", "lgw_device_download", "lgw_device_zero",
     "lgw_documents_usage", "lgw_rules_load", "lgw_bodies_scan", "lgw_bodies_rewrite", "lgw_bodies_rewrite_device", "lgw_bodies_last_ms",
@@ -59,6 +59,7 @@ def load():
     lib.lgw_streams_details.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.lgw_rollup_set_path.argtypes = [C.c_void_p, C.c_int]
     lib.lgw_last_step_direct.argtypes = [C.c_void_p]
+    lib.lgw_documents_error_detail.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.lgw_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lgw_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
     lib.lgw_usage_rollup_accum.argtypes = [C.c_void_p] + [C.c_void_p] * 8 + [C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64,

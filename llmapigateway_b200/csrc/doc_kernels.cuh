@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "stream_machine.cuh"
+#include "error_detail.cuh"
 
 namespace lgw {
 
@@ -47,6 +48,24 @@ __global__ void __launch_bounds__(LGW_DOC_WARPS * 32) k_docs_usage(const uint8_t
                 }
             }
         }
+        __syncwarp();
+    }
+}
+
+// error detail of failing non-streaming responses (request_handler.py:167-169): one warp per document stages it, lane 0 walks it
+// (error_detail.cuh); documents longer than the stage are walked in global memory.  Failing responses are the rare case.
+__global__ void __launch_bounds__(LGW_DOC_WARPS * 32) k_docs_error_detail(const uint8_t* __restrict__ docs, const uint64_t* __restrict__ off, uint32_t n, DocError* __restrict__ out,
+                                                                          uint8_t* __restrict__ text, uint32_t text_stride) {
+    __shared__ __align__(16) uint8_t stage[LGW_DOC_WARPS][LGW_DOC_STAGE];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t i = blockIdx.x * LGW_DOC_WARPS + warp; i < n; i += gridDim.x * LGW_DOC_WARPS) {
+        const uint8_t* src = docs + off[i];
+        const uint64_t len64 = off[i + 1] - off[i];
+        const uint32_t len = len64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)len64;
+        const bool staged = len <= LGW_DOC_STAGE;
+        if (staged) for (uint32_t k = lane; k < len; k += 32) stage[warp][k] = src[k];
+        __syncwarp();
+        if (lane == 0) error_detail_of(staged ? stage[warp] : src, len, out[i], text + (size_t)i * text_stride, text_stride);
         __syncwarp();
     }
 }

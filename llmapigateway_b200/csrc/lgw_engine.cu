@@ -756,6 +756,30 @@ extern "C" int lgw_documents_usage(lgw_engine* e, const uint8_t* docs, const uin
     return LGW_OK;
 }
 
+// ---- error detail of failing non-streaming responses (row a12, request_handler.py:167-169) ---------------
+extern "C" int lgw_documents_error_detail(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off, uint32_t n, lgw_doc_error* out, uint8_t* text, uint32_t text_stride) {
+    if (!e || !doc_off || (!docs && n && doc_off[n]) || (n && (!out || !text)) || text_stride == 0) return LGW_ERR_ARG;
+    if (n == 0) return LGW_OK;
+    CK(e, cudaSetDevice(e->device));
+    int rc = bodies_stage_in(e, docs, doc_off, n);
+    if (rc != LGW_OK) return rc;
+    DocError* d_out = nullptr; uint8_t* d_text = nullptr;
+    CK(e, cudaMalloc((void**)&d_out, (size_t)n * sizeof(DocError)));
+    cudaError_t r = cudaMalloc((void**)&d_text, (size_t)n * text_stride);
+    if (r == cudaSuccess) {
+        const uint32_t grid = (n + LGW_DOC_WARPS - 1) / LGW_DOC_WARPS < (uint32_t)e->sm_count * 8u ? (n + LGW_DOC_WARPS - 1) / LGW_DOC_WARPS : (uint32_t)e->sm_count * 8u;
+        k_docs_error_detail<<<grid, LGW_DOC_WARPS * 32, 0, e->stream>>>(e->b_in, e->b_off, n, d_out, d_text, text_stride);
+        ++e->launches;
+        r = cudaGetLastError();
+    }
+    if (r == cudaSuccess) r = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(DocError), cudaMemcpyDeviceToHost, e->stream);
+    if (r == cudaSuccess) r = cudaMemcpyAsync(text, d_text, (size_t)n * text_stride, cudaMemcpyDeviceToHost, e->stream);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(e->stream);
+    cudaFree(d_out); cudaFree(d_text);
+    if (r != cudaSuccess) { e->err = std::string("lgw_documents_error_detail: ") + cudaGetErrorString(r); return LGW_ERR_CUDA; }
+    return LGW_OK;
+}
+
 extern "C" int lgw_bodies_last_ms(lgw_engine* e, float ms[3]) {
     if (!e || !ms) return LGW_ERR_ARG;
     CK(e, cudaSetDevice(e->device));

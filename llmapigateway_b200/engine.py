@@ -260,6 +260,16 @@ class Engine:
             res.append(([dict(row), row] if out[i].error_row else [row], bool(out[i].exotic)))
         return res
 
+    def documents_error_detail(self, docs, text_stride: int = 4096):
+        """request_handler.py:167-169 for failing non-streaming responses -> list of (DocError, text bytes)."""
+        from . import rewrite as rw
+        buf, off = rw.pack_bodies(docs)
+        n = len(docs)
+        out = (_abi.DocError * max(n, 1))()
+        text = np.zeros(max(n, 1) * text_stride, dtype=np.uint8)
+        self._ck(self._lib.lgw_documents_error_detail(self._h, _ptr(buf), _ptr(off), n, out, _ptr(text), text_stride), "documents_error_detail")
+        return [(out[i], bytes(text[i * text_stride:i * text_stride + out[i].text_len])) for i in range(n)]
+
     def bodies_last_ms(self):
         ms = (C.c_float * 3)()
         self._ck(self._lib.lgw_bodies_last_ms(self._h, C.byref(ms)), "bodies_last_ms")

@@ -103,3 +103,28 @@ def attempt_for_oracle(rule_idx, sub_idx, retry):
     rule = RULES["gw/chain"]["fallback_models"][rule_idx]
     sub = rule["providers_order"][sub_idx] if sub_idx >= 0 else None
     return rule, rule["provider"], sub, retry
+
+
+def error_detail_docs(rng, n):
+    """Documents whose top-level "error" / "detail" take every shape request_handler.py:167-169 can meet (shared by the CPU and GPU tests)."""
+    strings = ['"m"', '""', '"caf\\u00e9 \\ud83d\\ude00 \\"q\\" \\\\ \\/ \\n\\t"', '"中文"', '"x' + "y" * 300 + '"', '"\\u0041\\u0000z"']
+    scalars = ["null", "true", "false", "0", "-0", "0.0", "0e3", "-0.0E-2", "7", "-12", "1.5", "2e3", "{}", "[]", "{ }", "[ ]"]
+    containers = ['{"a":1}', '[1]', '{"message":"inner"}', '[[]]']
+    for it in range(n):
+        members = []
+        if rng.random() < 0.8:
+            ev = rng.choice(strings + scalars + containers + ['{"message":%s}' % rng.choice(strings + scalars + containers),
+                                                              '{"code":1,"message":%s,"type":"x"}' % rng.choice(strings + scalars),
+                                                              '{"message":"first","message":%s}' % rng.choice(strings + scalars)])
+            members.append((rng.choice(['"error"', '"\\u0065rror"', '"err\\u006fr"']), ev))
+        if rng.random() < 0.7:
+            members.append((rng.choice(['"detail"', '"deta\\u0069l"']), rng.choice(strings + scalars + containers)))
+        if rng.random() < 0.2:
+            members.append(('"error"', rng.choice(strings + scalars + ['{"message":"dup"}'])))
+        if not members:
+            continue
+        members += [('"other"', '{"error":{"message":"nested, not top level"},"detail":"no"}'), ('"errors"', '"x"'), ('"id"', "3")]
+        rng.shuffle(members)
+        ws = lambda: rng.choice(["", " ", "\n ", "\t"])
+        raw = ("{" + ",".join(ws() + k + ws() + ":" + ws() + v + ws() for k, v in members) + "}").encode("utf-8")
+        yield raw

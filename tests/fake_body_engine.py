@@ -20,3 +20,6 @@ class HostBodyEngine:
             out = out if st == 0 else b""
             rows.append((st, out, hm.last_matched(), hm.last_root_kind()) if with_matched else (st, out))
         return rows
+
+    def documents_error_detail(self, docs, text_stride: int = 4096):
+        return [hm.error_detail(bytes(d), text_stride) for d in docs]

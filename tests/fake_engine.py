@@ -103,3 +103,6 @@ class FakeEngine:
         for i, t in enumerate(texts):
             models[i, :len(t)] = np.frombuffer(t, dtype=np.uint8)
         return scans, models
+
+    def documents_error_detail(self, docs, text_stride: int = 4096):
+        return [hm.error_detail(bytes(d), text_stride) for d in docs]

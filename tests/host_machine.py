@@ -135,3 +135,13 @@ def rewrite_body_fast(raw: bytes, plans, ops, blob, plan_idx: int, cap: int = 1 
                                       sub.ctypes.data_as(C.c_void_p), C.c_uint32(len(sub)), blob.ctypes.data_as(C.c_void_p),
                                       out.ctypes.data_as(C.c_void_p), C.c_uint32(cap), C.byref(n), C.byref(_last_matched))
     return st, bytes(out[:min(n.value, cap)]) if st == 0 else b"", n.value
+
+
+def error_detail(raw: bytes, cap: int = 4096):
+    """(DocError, text bytes) of the host build of csrc/error_detail.cuh"""
+    from llmapigateway_b200 import _abi
+    out = _abi.DocError()
+    text = np.zeros(cap, dtype=np.uint8)
+    buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    lib().lgwt_error_detail(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.byref(out), text.ctypes.data_as(C.c_void_p), C.c_uint32(cap))
+    return out, bytes(text[:out.text_len])

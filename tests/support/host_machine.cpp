@@ -109,3 +109,10 @@ extern "C" uint32_t lgwt_rewrite_body_fast(const uint8_t* in, uint32_t n, int mo
     g_last_root_kind = KD_OBJ;
     return st;
 }
+
+// ---- error detail of failing non-streaming responses (error_detail.cuh) -----------------------------------
+#include "../../llmapigateway_b200/csrc/error_detail.cuh"
+static_assert(sizeof(lgw::DocError) == sizeof(lgw_doc_error), "DocError");
+extern "C" void lgwt_error_detail(const uint8_t* doc, uint32_t n, lgw_doc_error* out, uint8_t* text, uint32_t cap) {
+    lgw::error_detail_of(doc, n, *(lgw::DocError*)out, text, cap);
+}

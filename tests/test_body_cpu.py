@@ -368,3 +368,31 @@ def test_scan_matches_reference_parse_goldens():
         if want == 0 and p["is_streaming"] is not None:
             assert bool(sc["stream_truthy"]) == p["is_streaming"], raw
     assert seen == {0, 1, 2}
+
+
+def test_error_detail_walk_matches_cpython(plans028):
+    """csrc/error_detail.cuh (host build) against CPython's own evaluation of request_handler.py:167-169 on documents whose
+    "error" / "detail" values take every shape: escapes, surrogate pairs, escaped key names, whitespace, nested containers,
+    numbers of every spelling, duplicate keys (the last one wins in a dict)."""
+    from fake_body_engine import HostBodyEngine
+    from llmapigateway_b200.responses import _error_detail
+    from llmapigateway_b200 import rewrite as rw
+    rng = random.Random(99)
+    eng = HostBodyEngine(plans028, fast=True)
+    n_text = n_exotic = 0
+    for raw in bc.error_detail_docs(rng, 3000):
+        doc = json.loads(raw)
+        if not ("error" in doc or "detail" in doc):
+            continue
+        try:
+            want = doc.get("error", {}).get("message") or doc.get("detail")
+        except Exception as e:
+            want = f"Unexpected error during request to u: {str(e)}"
+        got, exotic = _error_detail(eng, raw, "u", rw.KIND_OBJ)
+        if exotic is not None:
+            assert isinstance(want, (dict, list)) or (isinstance(want, str) and any(0xD800 <= ord(ch) < 0xE000 for ch in want)), (raw, want, exotic)
+            n_exotic += 1
+            continue
+        assert type(got) is type(want) and got == want, (raw, got, want)
+        n_text += isinstance(want, str)
+    assert n_text > 800 and n_exotic > 50

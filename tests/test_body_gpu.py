@@ -296,3 +296,31 @@ def test_nonstream_response_tap(engine):
         assert canon_rows(rows) == canon_rows(tap_nonstream([t]).rows), t[:200]
         n_ok += 1
     assert n_ok > 1300
+
+
+def test_error_detail_on_the_device(engine):
+    """lgw_documents_error_detail through the C ABI against CPython's evaluation of request_handler.py:167-169."""
+    from llmapigateway_b200.responses import _error_detail
+    rng = random.Random(7)
+    docs = list(bc.error_detail_docs(rng, 1500)) + [b'{"error":{"message":"' + b"z" * 7000 + b'"},"pad":"' + b"p" * 3000 + b'"}']
+    docs = [d for d in docs if ("error" in json.loads(d) or "detail" in json.loads(d))]
+    got = engine.documents_error_detail(docs, 8192)
+    n_text = 0
+    for raw, (e, text) in zip(docs, got):
+        doc = json.loads(raw)
+        try:
+            want = doc.get("error", {}).get("message") or doc.get("detail")
+        except Exception as ex:
+            want = f"Unexpected error during request to u: {str(ex)}"
+
+        class One:                       # feed the already computed device answer to the host-side mapping
+            def documents_error_detail(self, _docs, text_stride=4096):
+                return [(e, text)]
+
+        mapped, exotic = _error_detail(One(), raw, "u", rw.KIND_OBJ)
+        if exotic is not None:
+            assert isinstance(want, (dict, list)) or (isinstance(want, str) and any(0xD800 <= ord(ch) < 0xE000 for ch in want)), (raw, want, exotic)
+            continue
+        assert type(mapped) is type(want) and mapped == want, (raw, mapped, want)
+        n_text += isinstance(want, str)
+    assert n_text > 400
