@@ -633,6 +633,31 @@ def main():
     h2d = n_bytes + 4 * (n_chunks + 1) + 4 * (S + 1) + 4 * S + 8 * S
     d2h = n_bytes + S * SEG_DTYPE.itemsize + S * 440
 
+    # ---- transcript tap, same C3 batch, device resident; a side measurement, not part of `value` -----------
+    text_tap = None
+    if world == 1:
+        try:
+            eng.enable_transcripts()
+            t_ms = []
+            for k in range(4):
+                b, h, d = sets[k % 2]
+                eng.open(b.seg_slot, status)
+                eng.step_device(d["data"].data_ptr(), int(b.data.size), d["chunk_off"].data_ptr(), n_chunks, d["seg_chunk"].data_ptr(),
+                                d["seg_slot"].data_ptr(), S, d["out"].data_ptr(), d["segs"].data_ptr())
+                eng.sync()
+                st_text = eng.step_transcript()
+                if k:
+                    t_ms.append(eng.transcript_last_ms())
+            raw = b.data.tobytes()[:E * EVENT_BYTES]              # stream 0 of the last set: its text is the 8 content bytes of every delta
+            want = b"".join(raw[i * EVENT_BYTES + 49:i * EVENT_BYTES + 57] for i in range(E))
+            assert st_text.segment(0) == want, "transcript of stream 0 differs from its content bytes"
+            assert int(st_text.seg_off[-1]) == S * E * 8 and not (st_text.flags & _abi.TF_SEQUENTIAL).any()
+            tm = float(np.mean(t_ms))
+            text_tap = {"ms": tm, "kernels": "k_text_extract + k_text_scan + k_text_pack", "text_bytes": int(st_text.seg_off[-1]),
+                        "input_gbs": int(b.data.size) / (tm / 1e3) / 1e9, "note": "every event parsed again with the full machine, one chunk per lane"}
+        except Exception as ex:
+            text_tap = {"error": repr(ex)}
+
     sampler.stop()
     if rank != 0:
         if world > 1:
@@ -670,6 +695,8 @@ def main():
                                "k_relay2 locates the fields of every stream's usage event, k_commit2 reads them out)"},
         "wall_s_timed_loop": t_wall,
     }
+    if text_tap is not None:
+        line["transcript_tap"] = text_tap
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_block(E)
     if world == 1 and not args.no_cpu_baseline:

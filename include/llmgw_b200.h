@@ -330,6 +330,34 @@ typedef struct lgw_doc_error {
 int lgw_documents_error_detail(lgw_engine* e, const uint8_t* docs, const uint64_t* doc_off /* n+1 */, uint32_t n, lgw_doc_error* out,
                                uint8_t* text, uint32_t text_stride);
 
+/* ---- transcript tap: SURVEY 8(f) rank 3, chat_logging.py:108-139 -------------------------------------------------------------------
+ * The other half of the response tap: the text ChunkProcessorThread accumulates in `llm_response_accum` -- for every parsed event, for
+ * every choice, `delta.content` else `message.content` when truthy (:124-133), JSON escapes decoded; a top-level "error" appends the
+ * event's own stripped text and calls write_log at once with the text so far (:137-139).  Optional, like the reference's tap
+ * (LOG_CHAT_ENABLED, :166-168): lgw_transcripts_enable allocates the per-stream tap state; streams opened afterwards are tapped.
+ *
+ * After each lgw_sse_step / lgw_sse_step_device (and before the next one) lgw_step_transcript_run walks the chunks that step RELAYED
+ * (seg_out[s].emit_chunk_begin onward) with the tap's own carry and leaves on the device: the text appended per segment, packed
+ * segment after segment (UTF-8; a lone surrogate escape is written in 'surrogatepass' form and flagged), and the marks -- mid-stream
+ * write_log calls: the transcript written at mark (slot, seq) is the stream's text up to byte text_pos (counted from the stream's
+ * start).  It returns the sizes; lgw_step_transcript_fetch copies them out: text_out[seg_text_off[s] .. seg_text_off[s+1]) is what
+ * segment s appended.  File naming, the header block and log pruning of write_log (:22-67) stay on the host
+ * (llmapigateway_b200/transcripts.py). */
+enum lgw_text_flag {
+    LGW_TF_LONE_SURROGATE = 1 << 0,  /* the stream's text holds a lone surrogate: the reference's f.write raises (no file, no DB row) */
+    LGW_TF_EXOTIC = 1 << 1,          /* an event shape whose Python behaviour the device does not model: text not authoritative */
+    LGW_TF_CARRY_OVERFLOW = 1 << 2,  /* an unterminated event outgrew carry_cap */
+    LGW_TF_MARKQ_OVERFLOW = 1 << 3,  /* more marks in one step than rowq_cap */
+    LGW_TF_SEQUENTIAL = 1 << 4       /* (this step) the segment took the sequential walk */
+};
+typedef struct lgw_text_mark { uint32_t slot, seq; uint64_t text_pos; } lgw_text_mark;
+int lgw_transcripts_enable(lgw_engine* e);
+int lgw_step_transcript_run(lgw_engine* e, uint64_t* text_bytes, uint32_t* n_marks);
+int lgw_step_transcript_fetch(lgw_engine* e, uint8_t* text_out /* text_bytes */, uint64_t* seg_text_off /* n_segs+1 */,
+                              uint32_t* seg_flags /* n_segs */, lgw_text_mark* marks_out /* n_marks */);
+/* device time of the last transcript pass (extract + scan + pack), milliseconds */
+int lgw_transcript_last_ms(lgw_engine* e, float* ms);
+
 /* ---- device memory helpers for callers without their own CUDA allocator ----------------------------- */
 int lgw_device_alloc(lgw_engine* e, uint64_t bytes, void** out);
 int lgw_device_free(lgw_engine* e, void* p);

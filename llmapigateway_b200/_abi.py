@@ -41,6 +41,14 @@ class RowEvent(C.Structure):
     _fields_ = [("slot", C.c_uint32), ("seq", C.c_uint32), ("rec", UsageRec)]
 
 
+class TextMark(C.Structure):
+    """lgw_text_mark: a mid-stream write_log call (chat_logging.py:139): the transcript written there is the stream's text[:text_pos]."""
+    _fields_ = [("slot", C.c_uint32), ("seq", C.c_uint32), ("text_pos", C.c_uint64)]
+
+
+TF_LONE_SURROGATE, TF_EXOTIC, TF_CARRY_OVERFLOW, TF_MARKQ_OVERFLOW, TF_SEQUENTIAL = 1, 2, 4, 8, 16
+
+
 class SegResult(C.Structure):
     _fields_ = [("emit_chunk_begin", C.c_uint32), ("phase", C.c_uint8), ("verdict", C.c_uint8),
                 ("flags", C.c_uint16), ("detail_len", C.c_uint32)]

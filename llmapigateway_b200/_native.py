@@ -16,6 +16,7 @@ EXPORTS = [
     "lgw_launch_count", "lgw_documents_error_detail", "lgw_last_step_direct", "lgw_rollup_set_path", "lgw_streams_details", "lgw_alloc_pinned", "lgw_free_pinned",
     "lgw_usage_rollup_accum", "lgw_usage_rollup_emit", "lgw_rollup_bucket_of", "lgw_rollup_last_ms",
     "lgw_device_alloc", "lgw_device_free", "lgw_device_upload", "lgw_device_download", "lgw_device_zero",
+    "lgw_transcripts_enable", "lgw_step_transcript_run", "lgw_step_transcript_fetch", "lgw_transcript_last_ms",
     "lgw_documents_usage", "lgw_rules_load", "lgw_bodies_scan", "lgw_bodies_rewrite", "lgw_bodies_rewrite_device", "lgw_bodies_last_ms",
 ]
 
@@ -81,6 +82,10 @@ def load():
                                               C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.lgw_bodies_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
     lib.lgw_documents_usage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.lgw_transcripts_enable.argtypes = [C.c_void_p]
+    lib.lgw_step_transcript_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    lib.lgw_step_transcript_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lgw_transcript_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     if hasattr(lib, "lgw_engine_set_mode"):
         lib.lgw_engine_set_mode.argtypes = [C.c_void_p, C.c_int]
     if lib.lgw_abi_version() != 1:

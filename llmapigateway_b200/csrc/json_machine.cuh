@@ -129,7 +129,9 @@ struct ValueTrack {
     LGW_HD void reset() { pos = 0; vstart = 0; dup = 0; seen = 0; choices_lo = choices_hi = 0xFFFFFFFFu; for (int i = 0; i < UF_N; ++i) { fstart[i] = fend[i] = 0xFFFFFFFFu; } }
 };
 
-template <bool EXTRACT>
+// TEXT (transcript tap, transcript.cuh): additionally reports WHERE the content strings the choices walk appends lie in the
+// text (chat_logging.py:127-133), so that the caller can decode them into llm_response_accum.
+template <bool EXTRACT, bool TEXT = false>
 struct JsonMachine {
     // syntax
     uint8_t st, depth, ctx, slot;
@@ -156,6 +158,11 @@ struct JsonMachine {
     UsageRaw* rec;
     char* cap; uint8_t* cap_len; uint8_t* cap_flags;
     ValueTrack* trk;           // optional (nullptr: no tracking)
+    // TEXT only: position of the byte being fed (set by the caller), raw extent of the last "content" string of the choice's
+    // delta [0] / message [1] (between its quotes), and what the byte just fed decided: `emit_pending` -- the walk appends
+    // text[emit_lo, emit_hi) (chat_logging.py:129,133); `rollback` -- a repeated "choices" key voids what an earlier one appended
+    uint32_t tpos, c_lo[2], c_hi[2], emit_lo, emit_hi;
+    uint8_t emit_pending, rollback;
 
     LGW_HD void track_field(int f, bool is_str) { if (EXTRACT && trk) { trk->fstart[f] = trk->vstart; trk->fend[f] = trk->pos + (is_str ? 1u : 0u); } }
 
@@ -165,6 +172,7 @@ struct JsonMachine {
         stack = 0; flags = 0; k0 = k1 = k2 = k3 = 0; klen = 0; key_bad = 0; ucode = 0; pending_high = 0;
         num.reset(); slen = 0; cd = ChoiceSide{0, 0, 0, 0, 0}; cm = cd; ch_stop = 0; ret_slots = 0;
         rec = r; cap = nullptr; cap_len = nullptr; cap_flags = nullptr; trk = nullptr;
+        if (TEXT) { tpos = 0; c_lo[0] = c_lo[1] = c_hi[0] = c_hi[1] = 0; emit_lo = emit_hi = 0; emit_pending = 0; rollback = 0; }
         if (EXTRACT && r) clear_usage(*r);
     }
 
@@ -263,7 +271,9 @@ struct JsonMachine {
             else if (sd.kind == KD_STR || sd.kind == KD_ARR) { flags |= PF_EXOTIC; ch_stop = 1; return; }
             else { flags |= PF_TYPE_ERROR; ch_stop = 1; return; }              // `"content" in None`
             if (!test) continue;
-            if (sd.content_kind == KD_STR) { if (sd.content_truthy) flags |= PF_CONTENT; }
+            if (sd.content_kind == KD_STR) {
+                if (sd.content_truthy) { flags |= PF_CONTENT; if (TEXT) { emit_lo = c_lo[pass]; emit_hi = c_hi[pass]; emit_pending = 1; } }
+            }
             else if (sd.content_truthy) { flags |= PF_TYPE_ERROR; ch_stop = 1; } // str += non-str
             return;                                                              // if / elif
         }
@@ -330,6 +340,7 @@ struct JsonMachine {
                 else if (LGW_KEYEQ("choices")) {
                     s = SL_CHOICES; flags |= TK_CHOICES;
                     flags &= ~(uint32_t)(PF_TYPE_ERROR | PF_EXOTIC | PF_CONTENT); ch_stop = 0;   // last duplicate wins
+                    if (TEXT) rollback = 1;
                 }
                 else if (LGW_KEYEQ("model")) { s = SL_MODEL; flags |= TK_MODEL; }
                 else if (LGW_KEYEQ("provider")) { s = SL_PROVIDER; flags |= TK_PROVIDER; }
@@ -412,10 +423,12 @@ struct JsonMachine {
             else if (ctx == X_TOP && slot == SL_PROVIDER) { cap = rec->provider; cap_len = &rec->provider_len; cap_flags = &rec->provider_flags; }
             if (cap) { *cap_len = 0; *cap_flags = 0; }
         }
+        if (TEXT && !key && slot == SL_CONTENT && (ctx == X_DELTA || ctx == X_MESSAGE)) c_lo[ctx == X_MESSAGE] = tpos + 1;
     }
     LGW_HD void end_string() {
         if (in_key) { end_key(); return; }
         if (EXTRACT && cap) { flush_high(); cap = nullptr; }
+        if (TEXT && slot == SL_CONTENT && (ctx == X_DELTA || ctx == X_MESSAGE)) c_hi[ctx == X_MESSAGE] = tpos;
         on_value(KD_STR, 0, slen != 0);
     }
 

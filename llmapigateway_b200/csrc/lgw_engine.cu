@@ -12,6 +12,7 @@
 #include "rollup.cuh"
 #include "body_kernels.cuh"
 #include "doc_kernels.cuh"
+#include "transcript.cuh"
 
 using namespace lgw;
 
@@ -22,6 +23,7 @@ static_assert(sizeof(RowEvent) == sizeof(lgw_row_event), "lgw_row_event layout")
 static_assert(sizeof(SegResult) == sizeof(lgw_seg_result), "lgw_seg_result layout");
 static_assert(sizeof(RollupRow) == sizeof(lgw_rollup_row), "lgw_rollup_row layout");
 static_assert(sizeof(DocUsage) == sizeof(lgw_doc_usage), "lgw_doc_usage layout");
+static_assert(sizeof(TextMark) == sizeof(lgw_text_mark), "lgw_text_mark layout");
 
 static thread_local std::string g_create_error;
 
@@ -64,6 +66,16 @@ struct lgw_engine {
     bool kernel_times_valid = false;
     int mode = 0;                   // 0: fast path + general fix-up, 1: general path only
     int sm_count = 148;
+    // transcript tap (transcript.cuh; off until lgw_transcripts_enable)
+    bool text_on = false, text_pending = false, text_ready = false;
+    TextTap* d_tap = nullptr; uint8_t* d_tcarry = nullptr; uint8_t* d_tsparse = nullptr; uint8_t* d_ttext = nullptr;
+    uint32_t *d_piece_len = nullptr, *d_tseg_len = nullptr, *d_tseg_flags = nullptr, *d_markq_count = nullptr;
+    unsigned long long* d_tseg_off = nullptr; TextMark* d_markq = nullptr;
+    uint64_t text_total = 0; uint32_t text_marks = 0;
+    cudaEvent_t tev[2]{}; float tms = 0;
+    // the arrays of the last step (device-visible): what lgw_step_transcript_run works on
+    const uint8_t* last_bytes = nullptr; const uint32_t *last_chunk_off = nullptr, *last_seg_chunk = nullptr, *last_seg_slot = nullptr;
+    const SegResult* last_seg_out = nullptr; uint32_t last_n_chunks = 0, last_n_segs = 0; uint64_t last_n_bytes = 0;
     std::string err;
 };
 
@@ -139,6 +151,9 @@ extern "C" int lgw_engine_destroy(lgw_engine* e) {
     cudaFree(e->b_in); cudaFree(e->b_slots); cudaFree(e->b_out); cudaFree(e->b_models); cudaFree(e->b_off); cudaFree(e->b_out_off);
     cudaFree(e->b_plan_idx); cudaFree(e->b_results); cudaFree(e->b_scans); cudaFree(e->b_redo);
     for (auto& ev : e->bev) if (ev) cudaEventDestroy(ev);
+    cudaFree(e->d_tap); cudaFree(e->d_tcarry); cudaFree(e->d_tsparse); cudaFree(e->d_ttext); cudaFree(e->d_piece_len); cudaFree(e->d_tseg_len);
+    cudaFree(e->d_tseg_flags); cudaFree(e->d_markq_count); cudaFree(e->d_tseg_off); cudaFree(e->d_markq);
+    for (auto& ev : e->tev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 16; ++i) { if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]); }
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -175,6 +190,7 @@ extern "C" int lgw_streams_open(lgw_engine* e, const uint32_t* slots, const int3
     CK(e, cudaMemcpyAsync(e->d_status, http_status, n * 4, cudaMemcpyHostToDevice, e->stream));
     k_streams_open<<<(n + 127) / 128, 128, 0, e->stream>>>(e->t, e->d_slots, e->d_status, n);
     ++e->launches;
+    if (e->text_on) { k_text_open<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_tap, e->d_slots, n); ++e->launches; }
     CK(e, cudaGetLastError());
     CK(e, cudaStreamSynchronize(e->stream));
     return LGW_OK;
@@ -283,6 +299,9 @@ extern "C" int lgw_sse_step_device(lgw_engine* e, const uint8_t* d_bytes, uint64
                                    uint8_t* d_out, lgw_seg_result* d_seg_out) {
     if (!e || (!d_bytes && n_bytes) || !d_chunk_off || !d_seg_chunk || !d_seg_slot || (!d_out && n_bytes) || !d_seg_out) return LGW_ERR_ARG;
     CK(e, cudaSetDevice(e->device));
+    e->last_bytes = d_bytes; e->last_n_bytes = n_bytes; e->last_chunk_off = d_chunk_off; e->last_n_chunks = n_chunks;
+    e->last_seg_chunk = d_seg_chunk; e->last_seg_slot = d_seg_slot; e->last_n_segs = n_segs; e->last_seg_out = (const SegResult*)d_seg_out;
+    e->text_pending = e->text_on; e->text_ready = false;
     return step_device(e, d_bytes, n_bytes, d_chunk_off, n_chunks, d_seg_chunk, d_seg_slot, n_segs, d_out, (SegResult*)d_seg_out);
 }
 
@@ -342,6 +361,9 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
         cudaGetLastError();                 // (cudaPointerGetAttributes on an unregistered pointer may leave an error behind)
         e->last_direct = direct_in || direct_out;
     }
+    e->last_bytes = direct_in ? direct_in : e->d_in; e->last_n_bytes = n_bytes; e->last_chunk_off = e->d_chunk_off; e->last_n_chunks = n_chunks;
+    e->last_seg_chunk = e->d_seg_chunk; e->last_seg_slot = e->d_seg_slot; e->last_n_segs = n_segs; e->last_seg_out = e->d_seg_out;
+    e->text_pending = e->text_on; e->text_ready = false;
     uint32_t n_slices = n_bytes >= (8u << 20) && n_segs >= 16 ? 8u : 1u;
     if (direct_in && direct_out) n_slices = 1;
     if (const char* sl = getenv("LGW_SLICES")) { int v = atoi(sl); if (v >= 1 && v <= 14) n_slices = (uint32_t)v; }
@@ -564,6 +586,80 @@ extern "C" int lgw_rollup_last_ms(lgw_engine* e, float ms[2]) {
     if (cudaEventElapsedTime(&t, e->rev[0], e->rev[1]) == cudaSuccess) e->rms[0] = t;
     if (cudaEventElapsedTime(&t, e->rev[2], e->rev[3]) == cudaSuccess) e->rms[1] = t;
     ms[0] = e->rms[0]; ms[1] = e->rms[1];
+    return LGW_OK;
+}
+
+// ---- transcript tap (chat_logging.py:108-139) ---------------------------------------------------------
+extern "C" int lgw_transcripts_enable(lgw_engine* e) {
+    if (!e) return LGW_ERR_ARG;
+    if (e->text_on) return LGW_OK;
+    CK(e, cudaSetDevice(e->device));
+    const size_t S = e->lim.max_streams, C = e->lim.max_step_chunks, B = e->lim.max_step_bytes, cc = e->lim.carry_cap;
+    CK(e, cudaMalloc((void**)&e->d_tap, S * sizeof(TextTap)));
+    CK(e, cudaMemset(e->d_tap, 0, S * sizeof(TextTap)));
+    CK(e, cudaMalloc((void**)&e->d_tcarry, S * cc));
+    CK(e, cudaMalloc((void**)&e->d_tsparse, B + S * cc + 64));        // per segment: room for its carry and its bytes
+    CK(e, cudaMalloc((void**)&e->d_ttext, B + S * cc + 64));
+    CK(e, cudaMalloc((void**)&e->d_piece_len, (C + 1) * 4));
+    CK(e, cudaMalloc((void**)&e->d_tseg_len, (S + 1) * 4));
+    CK(e, cudaMalloc((void**)&e->d_tseg_flags, (S + 1) * 4));
+    CK(e, cudaMalloc((void**)&e->d_tseg_off, (S + 2) * 8));
+    CK(e, cudaMalloc((void**)&e->d_markq, (size_t)(e->lim.rowq_cap + 1) * sizeof(TextMark)));
+    CK(e, cudaMalloc((void**)&e->d_markq_count, 16));
+    for (auto& ev : e->tev) CK(e, cudaEventCreate(&ev));
+    e->text_on = true;
+    return LGW_OK;
+}
+
+extern "C" int lgw_step_transcript_run(lgw_engine* e, uint64_t* text_bytes, uint32_t* n_marks) {
+    if (!e || !text_bytes || !n_marks) return LGW_ERR_ARG;
+    if (!e->text_on) { e->err = "transcripts are not enabled (lgw_transcripts_enable)"; return LGW_ERR_ARG; }
+    if (!e->text_pending) { e->err = "no step to tap (the transcript pass runs once after each lgw_sse_step / lgw_sse_step_device)"; return LGW_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    e->text_pending = false;
+    TextArgs a{};
+    a.data = e->last_bytes; a.chunk_off = e->last_chunk_off; a.seg_chunk = e->last_seg_chunk; a.seg_slot = e->last_seg_slot; a.n_segs = e->last_n_segs;
+    a.seg_res = e->last_seg_out; a.tap = e->d_tap; a.carry = e->d_tcarry; a.carry_cap = e->lim.carry_cap; a.sparse = e->d_tsparse;
+    a.piece_len = e->d_piece_len; a.seg_len = e->d_tseg_len; a.seg_flags = e->d_tseg_flags; a.seg_off = e->d_tseg_off; a.text = e->d_ttext;
+    a.markq = e->d_markq; a.markq_count = e->d_markq_count; a.markq_cap = e->lim.rowq_cap;
+    CK(e, cudaMemsetAsync(e->d_markq_count, 0, 4, e->stream));
+    CK(e, cudaEventRecord(e->tev[0], e->stream));
+    const uint32_t n = a.n_segs;
+    if (n) {
+        k_text_extract<<<(n + TX_WARPS - 1) / TX_WARPS, TX_WARPS * 32, 0, e->stream>>>(a);
+        k_text_scan<<<1, 1024, 0, e->stream>>>(a.seg_len, n, a.seg_off);
+        k_text_pack<<<(n + TX_WARPS - 1) / TX_WARPS, TX_WARPS * 32, 0, e->stream>>>(a);
+        e->launches += 3;
+    } else CK(e, cudaMemsetAsync(e->d_tseg_off, 0, 8, e->stream));
+    CK(e, cudaEventRecord(e->tev[1], e->stream));
+    CK(e, cudaGetLastError());
+    unsigned long long total = 0; uint32_t marks = 0;
+    CK(e, cudaMemcpyAsync(&total, e->d_tseg_off + n, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(&marks, e->d_markq_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (marks > e->lim.rowq_cap) marks = e->lim.rowq_cap;
+    e->text_total = total; e->text_marks = marks; e->text_ready = true;
+    float t = 0; if (cudaEventElapsedTime(&t, e->tev[0], e->tev[1]) == cudaSuccess) e->tms = t;
+    *text_bytes = total; *n_marks = marks;
+    return LGW_OK;
+}
+
+extern "C" int lgw_step_transcript_fetch(lgw_engine* e, uint8_t* text_out, uint64_t* seg_text_off, uint32_t* seg_flags, lgw_text_mark* marks_out) {
+    if (!e || !seg_text_off || !seg_flags || (!text_out && e->text_total) || (!marks_out && e->text_marks)) return LGW_ERR_ARG;
+    if (!e->text_ready) { e->err = "lgw_step_transcript_run has not run for the last step"; return LGW_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    const uint32_t n = e->last_n_segs;
+    if (e->text_total) CK(e, cudaMemcpyAsync(text_out, e->d_ttext, e->text_total, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(seg_text_off, e->d_tseg_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (n) CK(e, cudaMemcpyAsync(seg_flags, e->d_tseg_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (e->text_marks) CK(e, cudaMemcpyAsync(marks_out, e->d_markq, (size_t)e->text_marks * sizeof(TextMark), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return LGW_OK;
+}
+
+extern "C" int lgw_transcript_last_ms(lgw_engine* e, float* ms) {
+    if (!e || !ms) return LGW_ERR_ARG;
+    *ms = e->tms;
     return LGW_OK;
 }
 

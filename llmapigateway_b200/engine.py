@@ -37,6 +37,18 @@ class StepResult:
         return keep
 
 
+@dataclass
+class StepText:
+    """What the transcript tap appended in one step (chat_logging.py:124-139)."""
+    text: np.ndarray           # uint8: the appended text of every segment, packed in segment order (UTF-8, surrogates as 'surrogatepass')
+    seg_off: np.ndarray        # uint64 [n_segs + 1]: segment s appended text[seg_off[s]:seg_off[s+1]]
+    flags: np.ndarray          # uint32 per segment: _abi.TF_* bits
+    marks: list                # [(slot, seq, text_pos)] mid-stream write_log calls: transcript = stream text[:text_pos]
+
+    def segment(self, s: int) -> bytes:
+        return self.text[int(self.seg_off[s]):int(self.seg_off[s + 1])].tobytes()
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -140,6 +152,7 @@ class Engine:
         if rows is None:
             rows = self._rows_buf = (_abi.RowEvent * max(cap, 1))()       # reused from step to step; the events returned are copies
         n_rows = C.c_uint32(0)
+        self._last_n_segs = n_segs
         self._ck(self._lib.lgw_sse_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot),
                                         n_segs, _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows)), "sse_step")
         return StepResult(out[:n_bytes], segs[:n_segs], [_abi.RowEvent.from_buffer_copy(rows[i]) for i in range(n_rows.value)])
@@ -147,6 +160,7 @@ class Engine:
     def step_device(self, d_data: int, n_bytes: int, d_chunk_off: int, n_chunks: int, d_seg_chunk: int, d_seg_slot: int,
                     n_segs: int, d_out: int, d_segs: int):
         """Device-pointer step (asynchronous on the engine stream)."""
+        self._last_n_segs = n_segs
         self._ck(self._lib.lgw_sse_step_device(self._h, d_data, n_bytes, d_chunk_off, n_chunks, d_seg_chunk, d_seg_slot,
                                                n_segs, d_out, d_segs), "sse_step_device")
 
@@ -156,6 +170,30 @@ class Engine:
         n_rows = C.c_uint32(0)
         self._ck(self._lib.lgw_fetch_rows(self._h, rows, cap, C.byref(n_rows)), "fetch_rows")
         return [rows[i] for i in range(n_rows.value)]
+
+    # -- transcript tap -----------------------------------------------------------
+    def enable_transcripts(self):
+        """Allocate the per-stream transcript tap (the reference taps only with LOG_CHAT_ENABLED, chat_logging.py:166-168);
+        streams opened afterwards are tapped."""
+        self._ck(self._lib.lgw_transcripts_enable(self._h), "transcripts_enable")
+        self._text_on = True
+
+    def step_transcript(self) -> StepText:
+        """The text the tap appended for the chunks the LAST step relayed (run once per step, before the next one)."""
+        total, n_marks = C.c_uint64(0), C.c_uint32(0)
+        self._ck(self._lib.lgw_step_transcript_run(self._h, C.byref(total), C.byref(n_marks)), "step_transcript_run")
+        n_segs = self._last_n_segs
+        text = np.empty(max(total.value, 1), dtype=np.uint8)
+        seg_off = np.zeros(n_segs + 1, dtype=np.uint64)
+        flags = np.zeros(max(n_segs, 1), dtype=np.uint32)
+        marks = (_abi.TextMark * max(n_marks.value, 1))()
+        self._ck(self._lib.lgw_step_transcript_fetch(self._h, _ptr(text), _ptr(seg_off), _ptr(flags), marks), "step_transcript_fetch")
+        return StepText(text[:total.value], seg_off, flags[:n_segs], [(marks[i].slot, marks[i].seq, marks[i].text_pos) for i in range(n_marks.value)])
+
+    def transcript_last_ms(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self._lib.lgw_transcript_last_ms(self._h, C.byref(ms)), "transcript_last_ms")
+        return ms.value
 
     def last_step_direct(self) -> bool:
         """True when the last host-buffer step moved the bytes with the kernel itself (pinned host buffers, no staging copies)."""

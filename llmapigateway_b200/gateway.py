@@ -51,11 +51,22 @@ class StreamBatcher:
     request goes away (client disconnect cancels the awaiting feed()) can never be packed into the next stream that
     gets the slot, and a slot only returns to the free list once no step that contains it is in flight."""
 
-    def __init__(self, engine, window_s: float = 0.002, usage_sink=None, arena_bytes: int = 8 << 20):
+    def __init__(self, engine, window_s: float = 0.002, usage_sink=None, arena_bytes: int = 8 << 20, transcript_log=None):
         import collections
         self.eng = engine
         self.window_s = window_s
         self.usage_sink = usage_sink
+        # chat transcripts (SURVEY 8(f) rank 3): with a `transcripts.TranscriptLog` the engine's transcript tap runs after every
+        # step and every row goes through write_log (file, THEN the usage row, chat_logging.py:47-56) instead of straight to the sink
+        self.transcript_log = transcript_log
+        self._book = None
+        self._req: dict[int, tuple] = {}                      # slot -> (request headers, request body text) for the log file
+        if transcript_log is not None:
+            from .transcripts import TranscriptBook
+            engine.enable_transcripts()
+            self._book = TranscriptBook()
+            if transcript_log.usage_sink is None:
+                transcript_log.usage_sink = usage_sink
         self._free = collections.deque(range(engine.limits.max_streams))
         self._gen = [0] * engine.limits.max_streams
         self._pending: list[_Pending] = []
@@ -79,11 +90,14 @@ class StreamBatcher:
                 self._arena_in = self._arena_out = None
 
     # -- slots ---------------------------------------------------------------------------------------
-    async def open_stream(self, http_status: int = 200) -> int:
+    async def open_stream(self, http_status: int = 200, req_headers=None, req_body_str: str = "") -> int:
         if not self._free:
             raise RuntimeError("no free stream slot on this engine")
         slot = self._free.popleft()
         self._gen[slot] += 1
+        if self._book is not None:
+            self._book.open(slot)
+            self._req[slot] = (req_headers if req_headers is not None else {}, req_body_str)
         try:
             await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.open, [slot], [http_status])
         except BaseException:
@@ -105,9 +119,13 @@ class StreamBatcher:
         st = (await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.close, [slot]))[0]
         self._free.append(slot)
         usage = None
+        text = None
+        if self._book is not None:
+            text, _tflags = self._book.close(slot)
         if st.flags & _abi.SF_EMITTED_ANY:
             usage = _abi.usage_rec_to_dict(st.rec)
-            self._sink(usage)
+            self._row(slot, usage, text)                        # the final write_log (chat_logging.py:150)
+        self._req.pop(slot, None)
         return st, usage
 
     @staticmethod
@@ -115,6 +133,14 @@ class StreamBatcher:
         if not p.fut.done():
             p.fut.cancel()
         return False
+
+    def _row(self, slot: int, usage: dict, text):
+        """One write_log call of the tap (chat_logging.py:139,150): with transcripts on, the log file and then the row; else the row."""
+        if self.transcript_log is None or text is None:
+            self._sink(usage)
+            return
+        headers, body = self._req.get(slot, ({}, ""))
+        self.transcript_log.write_log(headers, body, text, usage)
 
     def _sink(self, usage: dict):
         if self.usage_sink is None:
@@ -195,9 +221,12 @@ class StreamBatcher:
             done = loop.create_future()
             for s in slots:
                 self._inflight[s] = done
+            def _step():
+                r = self.eng.step(data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32),
+                                  **({"out": out} if out is not None else {}))
+                return r, (self.eng.step_transcript() if self._book is not None else None)
             try:
-                res = await loop.run_in_executor(self._worker, lambda: self.eng.step(data, np.array(offs, np.uint32), np.array(segc, np.uint32),
-                                                                                    np.array(slots, np.uint32), **({"out": out} if out is not None else {})))
+                res, step_text = await loop.run_in_executor(self._worker, _step)
             except Exception as exc:                      # engine failure: the endpoint answers 500/503 like chat.py:26,198
                 for ps in by_slot.values():
                     for p in ps:
@@ -212,8 +241,11 @@ class StreamBatcher:
                     done.set_result(None)
             self.steps += 1
             try:
+                snaps = {}
+                if step_text is not None:                                       # what the tap appended this step + the text at each mark
+                    snaps = {(sl, seq): t for sl, seq, t in self._book.apply(slots, step_text)}
                 for ev in sorted(res.rows, key=lambda r: (r.slot, r.seq)):      # mid-stream rows, chat_logging.py:139
-                    self._sink(_abi.usage_rec_to_dict(ev.rec))
+                    self._row(ev.slot, _abi.usage_rec_to_dict(ev.rec), snaps.get((ev.slot, ev.seq)))
             except Exception:
                 pass
             for k, s in enumerate(slots):
@@ -236,12 +268,14 @@ class StreamBatcher:
 
 
 async def make_llm_request(target_url: str, headers: dict, payload: dict, is_streaming: bool, *, batcher: StreamBatcher,
-                           client_factory=None, exotic_fallback=None):
+                           client_factory=None, exotic_fallback=None, log_request: dict | None = None):
     """Drop-in for request_handler.py:8.  Returns (response, None) on success and (None, error_detail) on
     failure; never raises (request_handler.py:178-187).  `payload` is the attempt's body: the bytes
     `StreamBatcher.rewrite_bodies` produced (rows a3/a4) -- a dict is still accepted on the streaming branch
     and encoded by httpx as in the reference.  Non-streaming success is a ready `Response` whose body is
-    byte-identical to what FastAPI renders from the reference's returned dict (row a12)."""
+    byte-identical to what FastAPI renders from the reference's returned dict (row a12).
+    `log_request` = dict(req_headers=..., req_body_str=...) of the CLIENT request: what write_log prints above the transcript
+    (chat_logging.py:176-186) when the batcher keeps transcripts."""
     import httpx
     from fastapi.responses import Response, StreamingResponse
     client = (client_factory or (lambda **kw: httpx.AsyncClient(**kw)))(timeout=httpx.Timeout(300.0, connect=60.0))
@@ -276,7 +310,7 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
             body = await response.aread()
             await ctx.__aexit__(None, None, None)
             return None, body.decode("utf-8")
-        slot = await batcher.open_stream(response.status_code)
+        slot = await batcher.open_stream(response.status_code, **(log_request or {}))
         chunks = response.aiter_bytes()
         first_kept: list[bytes] = []
         committed = False

@@ -47,6 +47,10 @@ def lib():
         _lib.lgwt_bulk_detail.restype = C.c_uint32
         _lib.lgwt_bulk_templates.argtypes = [C.c_void_p, C.c_void_p]
         _lib.lgwt_bulk_counters.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.lgwt_bulk_transcripts_enable.argtypes = [C.c_void_p]
+        _lib.lgwt_bulk_transcript.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.lgwt_bulk_transcript.restype = C.c_uint32
     return _lib
 
 
@@ -109,7 +113,24 @@ class HostBulkEngine:
         n_rows = C.c_uint32(0)
         self._lib.lgwt_bulk_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot), n_segs,
                                  _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows), self.tiles_per_warp)
+        self._last = (data, chunk_off, seg_chunk, seg_slot, segs)
         return StepResult(out[:n_bytes], segs[:n_segs], [rows[i] for i in range(n_rows.value)])
+
+    def enable_transcripts(self):
+        self._lib.lgwt_bulk_transcripts_enable(self._h)
+
+    def step_transcript(self):
+        from llmapigateway_b200.engine import StepText
+        data, chunk_off, seg_chunk, seg_slot, segs = self._last
+        n_bytes, n_chunks, n_segs = data.size, chunk_off.size - 1, seg_slot.size
+        text = np.zeros(n_bytes + n_segs * self.limits.carry_cap + 1, dtype=np.uint8)
+        seg_off = np.zeros(n_segs + 1, dtype=np.uint64)
+        flags = np.zeros(max(n_segs, 1), dtype=np.uint32)
+        cap = self.limits.rowq_cap
+        marks = (_abi.TextMark * max(cap, 1))()
+        n = self._lib.lgwt_bulk_transcript(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot), n_segs, _ptr(segs),
+                                           _ptr(text), _ptr(seg_off), _ptr(flags), marks, cap)
+        return StepText(text[:int(seg_off[n_segs])], seg_off, flags[:n_segs], [(marks[i].slot, marks[i].seq, marks[i].text_pos) for i in range(n)])
 
     def counters(self):
         out = (C.c_uint32 * 4)()

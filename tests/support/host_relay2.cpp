@@ -14,6 +14,7 @@
 namespace lgw {
 #include "../../llmapigateway_b200/csrc/relay2.cuh"
 }
+#include "../../llmapigateway_b200/csrc/transcript.cuh"
 
 using namespace lgw;
 
@@ -28,6 +29,10 @@ struct HostEngine {
     std::vector<uint32_t> tile_seg;
     std::vector<RowEvent> rowq; uint32_t rowq_count;
     int mode;
+    // transcript tap (transcript.cuh)
+    std::vector<TextTap> tap; std::vector<uint8_t> tcarry, tsparse, ttext;
+    std::vector<uint32_t> piece_len, tseg_len, tseg_flags; std::vector<unsigned long long> tseg_off;
+    std::vector<TextMark> markq; uint32_t markq_count = 0;
 };
 
 extern "C" {
@@ -52,6 +57,45 @@ void lgwt_bulk_reset_templates(void* h) { HostEngine* e = (HostEngine*)h; memset
 void lgwt_bulk_open(void* h, const uint32_t* slots, const int32_t* status, uint32_t n) {
     HostEngine* e = (HostEngine*)h;
     for (uint32_t i = 0; i < n; ++i) init_stream(e->state[slots[i]], status[i]);
+    if (!e->tap.empty()) simt::launch((n + 127) / 128, 128, [&] { k_text_open(e->tap.data(), slots, n); });
+}
+
+void lgwt_bulk_transcripts_enable(void* h) {
+    HostEngine* e = (HostEngine*)h;
+    e->tap.assign(e->max_streams, TextTap{});
+    e->tcarry.assign((size_t)e->max_streams * e->carry_cap, 0);
+    e->markq.assign(e->rowq_cap + 1, TextMark{});
+}
+
+// the transcript pass over the arrays of the step that has just run (seg_res = that step's results); text_out has room for
+// n_bytes + n_segs * carry_cap bytes.  Returns the number of marks.
+uint32_t lgwt_bulk_transcript(void* h, const uint8_t* data, uint32_t n_bytes, const uint32_t* chunk_off, uint32_t n_chunks,
+                              const uint32_t* seg_chunk, const uint32_t* seg_slot, uint32_t n_segs, const lgw_seg_result* seg_res,
+                              uint8_t* text_out, uint64_t* seg_text_off, uint32_t* seg_flags, lgw_text_mark* marks_out, uint32_t marks_cap) {
+    HostEngine* e = (HostEngine*)h;
+    // exactly sized scratch: the emulated kernels must not touch a byte beyond it
+    e->tsparse.assign((size_t)n_bytes + (size_t)n_segs * e->carry_cap, 0xEE);
+    e->ttext.assign((size_t)n_bytes + (size_t)n_segs * e->carry_cap + 1, 0xEE);
+    e->piece_len.assign(n_chunks + 1, 0xEEEEEEEEu); e->tseg_len.assign(n_segs + 1, 0); e->tseg_flags.assign(n_segs + 1, 0); e->tseg_off.assign(n_segs + 2, 0);
+    e->markq_count = 0;
+    TextArgs a{};
+    a.data = data; a.chunk_off = chunk_off; a.seg_chunk = seg_chunk; a.seg_slot = seg_slot; a.n_segs = n_segs; a.seg_res = (const SegResult*)seg_res;
+    a.tap = e->tap.data(); a.carry = e->tcarry.data(); a.carry_cap = e->carry_cap; a.sparse = e->tsparse.data();
+    a.piece_len = e->piece_len.data(); a.seg_len = e->tseg_len.data(); a.seg_flags = e->tseg_flags.data(); a.seg_off = e->tseg_off.data(); a.text = e->ttext.data();
+    a.markq = e->markq.data(); a.markq_count = &e->markq_count; a.markq_cap = e->rowq_cap;
+    if (n_segs) {
+        simt::launch((n_segs + TX_WARPS - 1) / TX_WARPS, TX_WARPS * 32, [&] { k_text_extract(a); });
+        simt::launch(1, 1024, [&] { k_text_scan(a.seg_len, n_segs, a.seg_off); });
+        simt::launch((n_segs + TX_WARPS - 1) / TX_WARPS, TX_WARPS * 32, [&] { k_text_pack(a); });
+    }
+    const unsigned long long total = e->tseg_off[n_segs];
+    memcpy(text_out, e->ttext.data(), total);
+    for (uint32_t i = 0; i <= n_segs; ++i) seg_text_off[i] = e->tseg_off[i];
+    memcpy(seg_flags, e->tseg_flags.data(), (size_t)n_segs * 4);
+    uint32_t cnt = e->markq_count < e->rowq_cap ? e->markq_count : e->rowq_cap;
+    if (cnt > marks_cap) cnt = marks_cap;
+    memcpy(marks_out, e->markq.data(), (size_t)cnt * sizeof(TextMark));
+    return cnt;
 }
 
 static StepArgs make_args(HostEngine* e, const uint8_t* data, uint32_t n_bytes, const uint32_t* chunk_off, uint32_t n_chunks,
