@@ -598,8 +598,8 @@ extern "C" int lgw_transcripts_enable(lgw_engine* e) {
     CK(e, cudaMalloc((void**)&e->d_tap, S * sizeof(TextTap)));
     CK(e, cudaMemset(e->d_tap, 0, S * sizeof(TextTap)));
     CK(e, cudaMalloc((void**)&e->d_tcarry, S * cc));
-    CK(e, cudaMalloc((void**)&e->d_tsparse, B + S * cc + 64));        // per segment: room for its carry and its bytes
-    CK(e, cudaMalloc((void**)&e->d_ttext, B + S * cc + 64));
+    CK(e, cudaMalloc((void**)&e->d_tsparse, 2 * (B + S * cc) + 64));  // per segment: twice its carry and its bytes (content pieces + "error" event texts)
+    CK(e, cudaMalloc((void**)&e->d_ttext, 2 * (B + S * cc) + 64));
     CK(e, cudaMalloc((void**)&e->d_piece_len, (C + 1) * 4));
     CK(e, cudaMalloc((void**)&e->d_tseg_len, (S + 1) * 4));
     CK(e, cudaMalloc((void**)&e->d_tseg_flags, (S + 1) * 4));

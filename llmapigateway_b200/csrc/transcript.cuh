@@ -91,8 +91,10 @@ LGW_HD void text_unescape(const Rope& r, uint32_t lo, uint32_t hi, TextOut& o) {
 }
 
 // One classified part [s, e) through the tap's per-part code (chat_logging.py:120-139).  Appends to `o`; returns true when the
-// part makes the tap call write_log (a mark).
-LGW_HD_NOINLINE bool text_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, TextOut& o) {
+// part makes the tap call write_log (a mark).  Content pieces never outgrow the event's own bytes; the text of an "error" event
+// comes on top of them (an event can append up to twice its length), so the one-chunk-per-lane path, whose room is the chunk's own
+// footprint, passes with_error_text = false and leaves such events to the sequential walk.
+LGW_HD_NOINLINE bool text_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cls, TextOut& o, bool with_error_text) {
     const uint32_t ev_pos = o.pos, ev_flags = o.flags;
     JsonMachine<false, true> m;
     m.reset(nullptr, cls == PC_DATA);
@@ -109,6 +111,7 @@ LGW_HD_NOINLINE bool text_part(const Rope& r, uint32_t s, uint32_t e, uint8_t cl
     if (f & PF_EXOTIC) { o.flags |= TF_EXOTIC; return false; }
     if ((f & TK_CHOICES) && (f & PF_TYPE_ERROR)) return false;                          // :140-141, the pieces before the exception stay
     if (!(f & TK_ERROR)) return false;
+    if (!with_error_text) return true;
     uint32_t te = e;                                                                    // :121 .strip() (the text starts with '{')
     if (cls == PC_DATA) while (te > t0 && JsonMachine<false>::is_py_ws(r.at(te - 1))) --te;
     for (uint32_t i = t0; i < te; ++i) o.p[o.pos++] = (uint8_t)r.at(i);               // :138 accum += decoded_chunk
@@ -148,7 +151,7 @@ LGW_HD uint32_t text_walk(const TextIO& io, const uint8_t* data, const uint32_t*
         const uint32_t tail = split_scan(r, [&](uint32_t s, uint32_t e) {
             const uint8_t cls = classify_part(r, s, e);
             if (cls == PC_NONE) return true;
-            if (text_part(r, s, e, cls, o)) text_push_mark(io, tp.text_total + o.pos);
+            if (text_part(r, s, e, cls, o, true)) text_push_mark(io, tp.text_total + o.pos);
             return true; }, stopped);
         if (!store_carry(io.carry, tp.carry_len, io.carry_cap, r, tail)) tp.flags |= TF_CARRY_OVERFLOW;
     }
@@ -180,7 +183,8 @@ struct TextArgs {
     const uint32_t* seg_chunk; const uint32_t* seg_slot; uint32_t n_segs;
     const SegResult* seg_res;          // the relay step's results: emit_chunk_begin
     TextTap* tap; uint8_t* carry; uint32_t carry_cap;      // [max_streams], [max_streams][carry_cap]
-    uint8_t* sparse;                   // segment s writes from s * carry_cap + chunk_off[seg_chunk[s]]  (room: carry + segment bytes)
+    uint8_t* sparse;                   // segment s writes from 2 * (s * carry_cap + chunk_off[seg_chunk[s]]); room: 2 * (carry_cap + segment bytes)
+                                       //   (the sequential walk may append up to twice the bytes it reads: content pieces + "error" event texts)
     uint32_t* piece_len;               // [n_chunks] text bytes of the piece that starts at the chunk's footprint
     uint32_t* seg_len;                 // [n_segs]
     uint32_t* seg_flags;               // [n_segs] TextFlag bits of this step
@@ -205,7 +209,7 @@ TX_GLOBAL void k_text_extract(TextArgs a) {
     if (cb < c0) cb = c0;
     if (cb > c1) cb = c1;
     const uint32_t seg_byte0 = a.chunk_off[c0];
-    uint8_t* const region = a.sparse + (size_t)seg * a.carry_cap + seg_byte0;      // room for carry_cap + the segment's bytes
+    uint8_t* const region = a.sparse + 2 * ((size_t)seg * a.carry_cap + seg_byte0);   // room: 2 * (carry_cap + the segment's bytes)
     TextTap tp = a.tap[slot];
     for (uint32_t c = c0 + lane; c < cb; c += 32) a.piece_len[c] = 0;             // dropped chunks: the tap never sees them
     // ---- regular attempt: one chunk per lane -------------------------------------------------------------------------------
@@ -222,12 +226,12 @@ TX_GLOBAL void k_text_extract(TextArgs a) {
                     if (n < 2 || p[n - 1] != '\n' || p[n - 2] != '\n' || !utf8_valid(p, n)) bad = true;
                     else {
                         Rope r{nullptr, 0, p, n};
-                        TextOut o{region + a.carry_cap + (off - seg_byte0), 0, 0};
+                        TextOut o{region + 2 * (size_t)a.carry_cap + (off - seg_byte0), 0, 0};
                         bool stopped;
                         split_scan(r, [&](uint32_t s, uint32_t e) {
                             const uint8_t cls = classify_part(r, s, e);
                             if (cls == PC_NONE) return true;
-                            if (text_part(r, s, e, cls, o)) { bad = true; return false; }      // a mark: positions need the sequential walk
+                            if (text_part(r, s, e, cls, o, false)) { bad = true; return false; }   // a mark: position and room need the sequential walk
                             return true; }, stopped);
                         len = o.pos; flags |= o.flags;
                     }
@@ -305,7 +309,7 @@ TX_GLOBAL void k_text_pack(TextArgs a) {
     if (cb < c0) cb = c0;
     if (cb > c1) cb = c1;
     const uint32_t seg_byte0 = a.chunk_off[c0];
-    const uint8_t* const region = a.sparse + (size_t)seg * a.carry_cap + seg_byte0;
+    const uint8_t* const region = a.sparse + 2 * ((size_t)seg * a.carry_cap + seg_byte0);
     uint8_t* dst = a.text + a.seg_off[seg];
     if (a.seg_flags[seg] & TF_SEQUENTIAL) {                       // one piece at the start of the region
         const uint32_t n = a.seg_len[seg];
@@ -319,7 +323,7 @@ TX_GLOBAL void k_text_pack(TextArgs a) {
         uint32_t x = len;
         for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(TX_FULL, x, d); if (lane >= d) x += y; }
         if (len) {
-            const uint8_t* src = region + a.carry_cap + (a.chunk_off[c] - seg_byte0);
+            const uint8_t* src = region + 2 * (size_t)a.carry_cap + (a.chunk_off[c] - seg_byte0);
             uint8_t* q = dst + done + (x - len);
             for (uint32_t i = 0; i < len; ++i) q[i] = src[i];
         }

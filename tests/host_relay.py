@@ -123,7 +123,7 @@ class HostBulkEngine:
         from llmapigateway_b200.engine import StepText
         data, chunk_off, seg_chunk, seg_slot, segs = self._last
         n_bytes, n_chunks, n_segs = data.size, chunk_off.size - 1, seg_slot.size
-        text = np.zeros(n_bytes + n_segs * self.limits.carry_cap + 1, dtype=np.uint8)
+        text = np.zeros(2 * (n_bytes + n_segs * self.limits.carry_cap) + 1, dtype=np.uint8)
         seg_off = np.zeros(n_segs + 1, dtype=np.uint64)
         flags = np.zeros(max(n_segs, 1), dtype=np.uint32)
         cap = self.limits.rowq_cap

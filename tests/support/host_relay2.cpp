@@ -68,14 +68,14 @@ void lgwt_bulk_transcripts_enable(void* h) {
 }
 
 // the transcript pass over the arrays of the step that has just run (seg_res = that step's results); text_out has room for
-// n_bytes + n_segs * carry_cap bytes.  Returns the number of marks.
+// 2 * (n_bytes + n_segs * carry_cap) bytes.  Returns the number of marks.
 uint32_t lgwt_bulk_transcript(void* h, const uint8_t* data, uint32_t n_bytes, const uint32_t* chunk_off, uint32_t n_chunks,
                               const uint32_t* seg_chunk, const uint32_t* seg_slot, uint32_t n_segs, const lgw_seg_result* seg_res,
                               uint8_t* text_out, uint64_t* seg_text_off, uint32_t* seg_flags, lgw_text_mark* marks_out, uint32_t marks_cap) {
     HostEngine* e = (HostEngine*)h;
     // exactly sized scratch: the emulated kernels must not touch a byte beyond it
-    e->tsparse.assign((size_t)n_bytes + (size_t)n_segs * e->carry_cap, 0xEE);
-    e->ttext.assign((size_t)n_bytes + (size_t)n_segs * e->carry_cap + 1, 0xEE);
+    e->tsparse.assign(2 * ((size_t)n_bytes + (size_t)n_segs * e->carry_cap), 0xEE);
+    e->ttext.assign(2 * ((size_t)n_bytes + (size_t)n_segs * e->carry_cap) + 1, 0xEE);
     e->piece_len.assign(n_chunks + 1, 0xEEEEEEEEu); e->tseg_len.assign(n_segs + 1, 0); e->tseg_flags.assign(n_segs + 1, 0); e->tseg_off.assign(n_segs + 2, 0);
     e->markq_count = 0;
     TextArgs a{};
