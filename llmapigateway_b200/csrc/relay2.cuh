@@ -1315,6 +1315,11 @@ R2_DEV_NOINLINE void commit_usage_fields(const uint8_t* text, uint32_t ups, uint
 }
 
 R2_DEV_NOINLINE void commit_settle_pending(StepIO io) { resolve_pending(io); }
+#if !R2_HOST_EMU
+R2_DEV uint4 commit_ld16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+#else
+R2_DEV uint4 commit_ld16(const uint8_t* p) { uint4 v; memcpy(&v, p, 16); return v; }
+#endif
 
 R2_GLOBAL void
 #if !R2_HOST_EMU
@@ -1325,16 +1330,31 @@ k_commit2(StepArgs a) {
     __shared__ __align__(16) uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];           // the winning usage event's text
     __shared__ __align__(16) UsageRaw stage_raw[R2_CWARPS];                           // the record being assembled from it
 #else
-    static uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
+    alignas(16) static uint8_t stage[R2_CWARPS][LGW_PENDING_STRIDE];
     static UsageRaw stage_raw[R2_CWARPS];
 #endif
     const uint32_t seg = (R2_BID * R2_NTHR + R2_TID) >> 5, lane = R2_TID & 31u, warp = (R2_TID >> 5) % R2_CWARPS;
     if (seg >= a.n_segs) return;
-    const uint32_t c1 = __ldg(a.seg_chunk + seg + 1);
+    const uint32_t c0 = __ldg(a.seg_chunk + seg), c1 = __ldg(a.seg_chunk + seg + 1);
     const uint32_t slot = __ldg(a.seg_slot + seg);
-    griddep_wait();                                       // (the bulk kernel's findings from here on)
-    const SegPlan p = a.s.plan[seg];
+    // Everything that does not depend on the bulk kernel runs BEFORE the wait, while that kernel is still at work (this kernel's
+    // blocks become resident as soon as the bulk kernel's blocks have all started): the stream's state (written only by the
+    // commit of an earlier step) and the scan of the segment's chunk offsets for empty chunks.
     StreamHdr st = a.t.state[slot].h;                     // (every lane holds a copy; lane 0's is the one written back)
+    // an empty chunk is never yielded (request_handler.py:60-63): the concatenation argument does not cover it
+    bool empty = false;
+    if ((st.phase == PH_COMMITTED || st.phase == PH_PRIMING) && c0 < c1) {
+        for (uint32_t c = c0 + lane; c < c1; c += 32 * 8) {                 // eight independent trips in flight (a plain loop is one DRAM round trip per trip)
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) { const uint32_t cc = c + 32 * j; lo[j] = cc < c1 ? __ldg(a.chunk_off + cc) : 0u; hi[j] = cc < c1 ? __ldg(a.chunk_off + cc + 1) : 1u; }
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) if (lo[j] == hi[j]) empty = true;
+        }
+    }
+    const bool any_empty = __any_sync(R2_FULL, empty);
+    griddep_wait();                                       // (the bulk kernel's findings from here on)
+    const SegPlan p = a.s.plan[seg];                      // (resume_chunk is the segment's first chunk: k_prime2)
     const StepIO io = make_io(a, slot, &st);
     uint32_t emit_begin = p.emit_chunk_begin;
     const bool speculated = p.kept_chunk != 0xFFFFFFFFu;
@@ -1347,17 +1367,20 @@ k_commit2(StepArgs a) {
         const bool has_cand = staged && p.cand_ps == ups + 1u;
         uint2 fld = make_uint2(0u, 0xFFFFFFFFu), gf = make_uint2(0u, 0u);
         if (has_cand) { const uint2* uf = a.s.usage_fields + (size_t)seg * 9u; if (lane < 8u) fld = uf[lane]; gf = uf[8]; }
-        if (staged) for (uint32_t k = lane; k < ulen; k += 32) stage[warp][k] = __ldg(d + ups + k);
-        // an empty chunk is never yielded (request_handler.py:60-63): the concatenation argument does not cover it
-        bool empty = false;
-        for (uint32_t c = p.resume_chunk + lane; c < c1; c += 32 * 8) {          // eight independent trips in flight (a plain loop is one DRAM round trip per trip)
-            uint32_t lo[8], hi[8];
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) { const uint32_t cc = c + 32 * j; lo[j] = cc < c1 ? __ldg(a.chunk_off + cc) : 0u; hi[j] = cc < c1 ? __ldg(a.chunk_off + cc + 1) : 1u; }
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) if (lo[j] == hi[j]) empty = true;
+        // staged as whole 16-byte vectors around the text (the step's buffer is 16-byte aligned: the bulk kernel's TMA needs that too);
+        // a vector that would reach beyond the step's bytes is read byte by byte
+        const uint32_t ab = ups & ~15u, skew = ups - ab;
+        const bool d_aligned = (reinterpret_cast<uintptr_t>(d) & 15u) == 0u;
+        const uint8_t* const utext = stage[warp] + skew;
+        if (staged) {
+            const uint32_t nvec = (skew + ulen + 15u) >> 4;
+            for (uint32_t k = lane; k < nvec; k += 32) {
+                const uint32_t o = ab + (k << 4);
+                if (o + 16u <= a.n_bytes && d_aligned) *reinterpret_cast<uint4*>(stage[warp] + (k << 4)) = commit_ld16(d + o);
+                else for (uint32_t j = 0; j < 16u && o + j < a.n_bytes; ++j) stage[warp][(k << 4) + j] = __ldg(d + o + j);
+            }
         }
-        bool sequential = p.irregular || p.n_usage_b > 1 || __any_sync(R2_FULL, empty);   // several usage candidates: let the exact path count them
+        bool sequential = p.irregular || p.n_usage_b > 1 || any_empty;   // several usage candidates: let the exact path count them
         if (st.phase == PH_PRIMING && !(speculated && p.prime_ok)) sequential = true;
         if (!sequential && p.last_usage && !staged) sequential = true;
         if (!sequential && p.tail_start == 0xFFFFFFFFu) sequential = true;                        // (nobody reached the end of the text)
@@ -1382,14 +1405,14 @@ k_commit2(StepArgs a) {
                 __syncwarp();
                 if (has_cand) {
                     // the bulk kernel matched it against a usage template and noted where the eight fields sit: read them out
-                    commit_usage_fields(stage[warp], ups, ulen, gf.y, &a.s.tpl_cache2->raw[gf.x], &stage_raw[warp], io.rec, lane, fld.x, fld.y);
+                    commit_usage_fields(utext, ups, ulen, gf.y, &a.s.tpl_cache2->raw[gf.x], &stage_raw[warp], io.rec, lane, fld.x, fld.y);
                     __syncwarp();
                     st.flags |= SF_REC_VALID; ++st.n_usage_b;
                     if (io.rec->exotic) { ++st.n_exotic; st.flags |= SF_EXOTIC_SEEN; }
                     if (lane == 0) atomicAdd(a.s.counters + 2, 1u);
                 } else {
                     // no usage template: read the values out of the staged text with the full machine now
-                    if (lane == 0) { commit_usage_event(io, stage[warp], ulen); atomicAdd(a.s.counters + 3, 1u); }
+                    if (lane == 0) { commit_usage_event(io, utext, ulen); atomicAdd(a.s.counters + 3, 1u); }
                 }
             }
             // new carry = text after the last separator (both loops: SF_SYNCED)
