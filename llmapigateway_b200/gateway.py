@@ -7,8 +7,9 @@
   shard_of(stream_id, n)  <- SURVEY 8(e): stream -> GPU by hash, no cross-GPU dependency
 
 The upstream HTTP I/O stays httpx exactly as in the reference (request_handler.py:15,23); only the
-byte work moves to the GPU.  Non-streaming requests (rows a4/a12) are not accelerated in this round
-and are left to the reference's own code.
+byte work moves to the GPU.  Non-streaming requests go through the engine too: the attempt's body is the
+bytes `rewrite_bodies` rendered (rows a3/a4), the response is checked and re-rendered by the response plan
+(row a12) and tapped by `log_chat_completions` (row a8, non-streaming mode).
 """
 from __future__ import annotations
 
@@ -116,8 +117,10 @@ class StreamBatcher:
                 await asyncio.shield(fut)
             except Exception:
                 pass
-        st = (await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.close, [slot]))[0]
-        self._free.append(slot)
+        try:
+            st = (await asyncio.get_running_loop().run_in_executor(self._worker, self.eng.close, [slot]))[0]
+        finally:
+            self._free.append(slot)                            # (open() initialises the slot's state again: a failed close does not poison it)
         usage = None
         text = None
         if self._book is not None:
@@ -280,6 +283,31 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
     from fastapi.responses import Response, StreamingResponse
     client = (client_factory or (lambda **kw: httpx.AsyncClient(**kw)))(timeout=httpx.Timeout(300.0, connect=60.0))
     slot = None
+    ctx = None
+
+    async def _release(close_slot: bool = True):
+        """Give back whatever this attempt still holds -- the stream slot, the upstream response, the client (the reference
+        leaves its AsyncClient to the garbage collector, request_handler.py:15).  Every resource is released at most once and
+        no error of one release keeps the others from running."""
+        nonlocal slot, ctx
+        s_, c_ = slot, ctx
+        slot = ctx = None
+        try:
+            if s_ is not None and close_slot:
+                await batcher.close_stream(s_)
+        except Exception:
+            pass
+        try:
+            if c_ is not None:
+                await c_.__aexit__(None, None, None)
+        except Exception:
+            pass
+        try:
+            aclose = getattr(client, "aclose", None)
+            if aclose is not None:
+                await aclose()
+        except Exception:
+            pass
     body_kw = {"content": bytes(payload)} if isinstance(payload, (bytes, bytearray, memoryview)) else {"json": payload}
     if not is_streaming:                                                  # request_handler.py:152-176
         try:
@@ -303,13 +331,16 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
             return None, f"RequestError connecting to {target_url}: {str(e)}"
         except Exception as e:                                            # request_handler.py:183-187
             return None, f"Unexpected error during request to {target_url}: {str(e)}"
+        finally:
+            await _release()
     try:
         ctx = client.stream("POST", target_url, headers=headers, timeout=None, **body_kw)
         response = await ctx.__aenter__()
         if response.status_code >= 400:                                   # request_handler.py:25-30
             body = await response.aread()
-            await ctx.__aexit__(None, None, None)
-            return None, body.decode("utf-8")
+            detail = body.decode("utf-8")
+            await _release()
+            return None, detail
         slot = await batcher.open_stream(response.status_code, **(log_request or {}))
         chunks = response.aiter_bytes()
         first_kept: list[bytes] = []
@@ -320,8 +351,7 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
                 detail = await batcher.detail(slot)
                 if r.verdict == _abi.VERDICT_FAIL_PARSE:                  # :183-187 (message tail is the JSON library's text: unpinned)
                     detail = f"Unexpected error during request to {target_url}: first event is not valid JSON: {detail[:200]}"
-                await batcher.close_stream(slot)
-                await ctx.__aexit__(None, None, None)
+                await _release()
                 return None, detail
             if r.emitted is not None:
                 first_kept.append(r.emitted)
@@ -340,28 +370,20 @@ async def make_llm_request(target_url: str, headers: dict, payload: dict, is_str
                             yield r.emitted
             finally:
                 # (shielded: a client disconnect cancels this generator, the slot and the upstream connection must still be released)
-                await asyncio.shield(_cleanup())
-
-        async def _cleanup():
-            try:
-                await batcher.close_stream(slot)
-            finally:
-                await ctx.__aexit__(None, None, None)
+                await asyncio.shield(_release())
 
         resp = StreamingResponse(relay(), media_type="text/event-stream", headers={"Transfer-Encoding": "chunked", "X-Accel-Buffering": "no"})
         resp.lgw_tapped = True            # the engine's tap already saw every relayed chunk: log_chat_completions must not tap it again
         return resp, None
     except httpx.RequestError as e:                                       # request_handler.py:178-182
-        if slot is not None:
-            await batcher.close_stream(slot)
+        await _release()
         return None, f"RequestError connecting to {target_url}: {str(e)}"
     except Exception as e:                                                # request_handler.py:183-187
-        if slot is not None:
-            try:
-                await batcher.close_stream(slot)
-            except Exception:
-                pass
+        await _release()
         return None, f"Unexpected error during request to {target_url}: {str(e)}"
+    except BaseException:                                                 # cancelled while priming: the slot must not stay taken
+        await asyncio.shield(_release())
+        raise
 
 
 async def log_chat_completions(request, call_next, *, batcher: StreamBatcher):

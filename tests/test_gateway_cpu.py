@@ -347,3 +347,68 @@ def test_nonstream_responses_are_tapped_by_the_middleware_mirror():
         assert await log_chat_completions(other, call_next, batcher=b) is resp
         assert len(sink.rows) == 1
     asyncio.run(go())
+
+
+def test_every_attempt_gives_its_slot_back_exactly_once():
+    """Failed attempts, upstream errors while priming, a response whose close raises, a cancelled priming loop and a client that
+    walks away mid-stream: afterwards every slot is free again, once (a slot freed twice would be handed to two streams)."""
+    ok_case = next(c for c in CASES if not c["failed"] and len(c["chunks"]) > 3)
+    bad_case = next(c for c in CASES if c["failed"] and c["http_status"] < 400)
+
+    def factory(chunks, status=200, fail_after=None, close_raises=False, hang_after=None):
+        class _Body(httpx.AsyncByteStream):
+            async def __aiter__(self):
+                for k, c in enumerate(chunks):
+                    if fail_after is not None and k == fail_after:
+                        raise httpx.ReadError("upstream went away")
+                    if hang_after is not None and k == hang_after:
+                        await asyncio.sleep(3600)
+                    yield c
+
+            async def aclose(self):
+                if close_raises:
+                    raise httpx.ReadError("close failed")
+
+        return lambda **kw: httpx.AsyncClient(transport=httpx.MockTransport(
+            lambda request: httpx.Response(status, headers={"content-type": "text/event-stream"}, stream=_Body())), **kw)
+
+    async def go():
+        n = 8
+        batcher = StreamBatcher(FakeEngine(max_streams=n), window_s=0.0005, usage_sink=_Sink())
+        url = "http://upstream.test/v1/chat/completions"
+
+        async def attempt(f):
+            return await make_llm_request(url, {}, {"model": "m", "messages": []}, True, batcher=batcher, client_factory=f)
+
+        def all_free():
+            return sorted(batcher._free) == list(range(n))
+
+        for _ in range(3):
+            resp, err = await attempt(factory(bad_case["chunks"], close_raises=True))         # fails while priming; closing raises too
+            assert resp is None and err is not None and all_free()
+            resp, err = await attempt(factory(ok_case["chunks"], fail_after=0))                # upstream dies before the first chunk
+            assert resp is None and err.startswith("RequestError connecting to") and all_free()
+            resp, err = await attempt(factory([b"x"], status=502))                             # HTTP error: no slot is ever taken
+            assert resp is None and err == "x" and all_free()
+            resp, err = await attempt(factory(ok_case["chunks"]))                              # served in full
+            assert err is None
+            assert b"".join([bytes(c) async for c in resp.body_iterator]) == b"".join(ok_case["emitted"])
+            assert all_free()
+            resp, err = await attempt(factory(ok_case["chunks"], close_raises=True))           # served in full, then the upstream close raises
+            got = []                                                                           #   (the relay generator passes that on, as the
+            with pytest.raises(httpx.ReadError):                                               #   reference's does; the slot is free all the same)
+                async for c in resp.body_iterator:
+                    got.append(bytes(c))
+            assert b"".join(got) == b"".join(ok_case["emitted"]) and all_free()
+            resp, err = await attempt(factory(ok_case["chunks"]))                              # the client walks away mid-stream
+            it = resp.body_iterator
+            await it.__anext__()
+            await it.aclose()
+            assert all_free()
+            task = asyncio.ensure_future(attempt(factory([b": ping\n\n"] * 2, hang_after=1)))
+            await asyncio.sleep(0.05)                                                           # cancelled inside the priming loop
+            task.cancel()
+            with pytest.raises(asyncio.CancelledError):
+                await task
+            assert all_free()
+    asyncio.run(go())
