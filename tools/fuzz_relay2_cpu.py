@@ -1,0 +1,170 @@
+"""Differential fuzz campaign of the bulk SSE kernels on the CPU box (test aid, not a product path).
+
+The kernels of csrc/relay2.cuh are run through the SIMT emulator (tests/host_relay.py) in their bulk mode (mode 0) and in the
+exact sequential mode (mode 1) on streams from three generators -- the two of tests/test_sse_gpu.py with fresh seeds, and a
+third one aimed at the usage-field read-out (template-following usage events whose numbers and strings take every spelling
+JSON allows) -- and both are compared with the oracle (oracle/sse_oracle.py, the restatement of request_handler.py:21-150 and
+chat_logging.py:87-150,233-272).  Engine geometries (blocks, tiles per warp) and step counts vary per round.
+
+    python tools/fuzz_relay2_cpu.py --rounds 40 --procs 6 --seed 1000
+
+Prints one line per round; a divergence is reported with the generator, seed and stream so that it can be replayed
+(`--replay gen:seed:n_steps:geometry`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import random
+import sys
+import traceback
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+GEOMETRIES = [(2, 0), (3, 1), (1, 0), (5, 2), (4, 1)]
+
+NUMBERS = ["0", "7", "12", "123456", "2147483647", "2147483648", "4294967296", "9007199254740993", "18446744073709551616",
+           "-1", "-0", "0.0", "0.5", "1.25", "1e3", "1E3", "1e+3", "1e-3", "12.5e-2", "0.000001", "1.7976931348623157e308", "1e400",
+           "123456789012345678901234567890", "0.1234567890123456789", "3.0", "5e0", "100000000000000000000.0", "4.9e-324", "1e-400"]
+BAD_NUMBERS = ["01", "1.", ".5", "+1", "1e", "1e+", "--1", "0x10", "1_000", "NaN", "Infinity", "1.2.3", "1e1.5", ""]
+STRINGS = ["m", "gpt-4o", "openai/gpt-4o-mini", "", "x" * 63, "x" * 64, "x" * 65, "x" * 200, "café", "中文", "\U0001F600",
+           "a\\\"b", "tab\\there", "nl\\nx", "\\u0041\\u00e9", "\\ud83d\\ude00", "\\ud83d", "\\ude00x", "back\\\\slash", "sl\\/ash", "\\b\\f\\r"]
+BAD_STRINGS = ["a\\qb", "\\u12", "\\u12G4", "ctl\x01x", 'q"q']
+
+
+def usage_variant_streams(n_streams: int, seed: int):
+    """Streams whose usage events share ONE skeleton (so that after the first few the kernel holds a usage template) while the
+    values of the eight fields run through every number and string spelling; some events break the skeleton on purpose."""
+    import sse_cases as sc
+    rng = random.Random(seed)
+    out = []
+    for s in range(n_streams):
+        evs = [sc.delta(rng.choice(["a", "hello", "x" * rng.randrange(1, 90)])) for _ in range(rng.randrange(1, 24))]
+        n_usage = 1 if rng.random() < 0.8 else rng.randrange(0, 4)
+        for _ in range(n_usage):
+            def num():
+                r = rng.random()
+                return rng.choice(NUMBERS) if r < 0.85 else (rng.choice(BAD_NUMBERS) if r < 0.93 else rng.choice(["null", "true", '"7"', "[1]", "{}"]))
+
+            def text():
+                r = rng.random()
+                return '"' + (rng.choice(STRINGS) if r < 0.9 else rng.choice(BAD_STRINGS)) + '"' if r < 0.96 else rng.choice(["null", "12", "[]"])
+            shape = rng.random()
+            if shape < 0.75:         # the C3 skeleton: every field present
+                ev = ('{"choices":[],"usage":{"prompt_tokens":%s,"completion_tokens":%s,"total_tokens":%s,"cost":%s,'
+                      '"completion_tokens_details":{"reasoning_tokens":%s},"prompt_tokens_details":{"cached_tokens":%s}},"model":%s,"provider":%s}'
+                      % (num(), num(), num(), num(), num(), num(), text(), text()))
+            elif shape < 0.85:       # a second skeleton: no details, no provider
+                ev = '{"id":"u","choices":[],"usage":{"prompt_tokens":%s,"completion_tokens":%s,"total_tokens":%s},"model":%s}' % (num(), num(), num(), text())
+            elif shape < 0.92:       # usage beside a delta (the choices walk meets value spans)
+                ev = '{"choices":[{"index":0,"delta":{"content":%s}}],"usage":{"prompt_tokens":%s,"completion_tokens":%s,"total_tokens":%s,"cost":%s}}' % (text(), num(), num(), num(), num())
+            else:                    # details present but null / not objects
+                ev = '{"choices":[],"usage":{"prompt_tokens":%s,"completion_tokens":%s,"total_tokens":%s,"completion_tokens_details":%s,"prompt_tokens_details":%s},"model":%s}' % (
+                    num(), num(), num(), rng.choice(["null", "{}", '{"reasoning_tokens":3}', "5"]), rng.choice(["null", "{}", '{"cached_tokens":4}', '"x"']), text())
+            if rng.random() < 0.04:
+                i = rng.randrange(len(ev)); ev = ev[:i] + rng.choice(['"', "\\", "}", " ", "\n", ","]) + ev[i + 1:]
+            evs.append(("data: " + ev + "\n\n").encode("utf-8", errors="surrogatepass") if rng.random() < 0.97 else (ev + "\n\n").encode("utf-8", errors="surrogatepass"))
+            if rng.random() < 0.3:
+                evs.append(sc.delta("more"))
+        if rng.random() < 0.8:
+            evs.append(sc.DONE)
+        blob = b"".join(evs)
+        m = rng.random()
+        if m < 0.55:
+            chunks = evs
+        elif m < 0.8:
+            step = rng.randrange(5, 300)
+            chunks = sc.rechunk(blob, list(range(step, len(blob), step)))
+        else:
+            chunks = sc.rechunk(blob, [rng.randrange(1, max(2, len(blob))) for _ in range(rng.randrange(0, 9))])
+        out.append([c for c in chunks if c])
+    return out
+
+
+def make_streams(gen: str, n: int, seed: int):
+    import test_sse_gpu as G
+    if gen == "random":
+        return G._random_streams(n, seed)
+    if gen == "template":
+        return G._template_variant_streams(n, seed)
+    return usage_variant_streams(n, seed)
+
+
+def one_round(job):
+    gen, seed, n_steps, geo, n_streams, cold = job
+    import test_sse_gpu as G
+    from golden_io import canon_rows
+    from host_relay import HostBulkEngine
+    from llmapigateway_b200 import _abi
+    from oracle.sse_oracle import run_stream
+    tag = f"{gen}:{seed}:{n_steps}:{geo}"
+    try:
+        nb, tpw = GEOMETRIES[geo]
+        eng = HostBulkEngine(max_streams=2048, n_blocks=nb, tiles_per_warp=tpw)
+        try:
+            streams = make_streams(gen, n_streams, seed)
+            if not cold:                      # warm templates: a first batch of the same generator, other seed
+                G._run_all(eng, make_streams(gen, 64, seed + 1), 0, 1, seed=3)
+            s_fast, r_fast, e_fast = G._run_all(eng, streams, 0, n_steps, seed=seed)
+            counters = eng.counters()
+            s_seq, r_seq, e_seq = G._run_all(eng, streams, 1, n_steps, seed=seed)
+            n_ok = 0
+            for i, (a, b) in enumerate(zip(s_fast, s_seq)):
+                where = f"{tag} stream {i}"
+                assert e_fast[i] == e_seq[i], where + " emitted bytes: bulk != sequential"
+                assert bytes(a)[:64] == bytes(b)[:64], where + " state header: bulk != sequential"
+                if a.flags & _abi.SF_REC_VALID:
+                    assert a.rec.exotic == b.rec.exotic, where + " exotic flag"
+                    if not a.rec.exotic:
+                        assert canon_rows([_abi.usage_rec_to_dict(a.rec)]) == canon_rows([_abi.usage_rec_to_dict(b.rec)]), where + " usage record: bulk != sequential"
+                relay, tap = run_stream(streams[i])
+                assert e_fast[i] == relay.emitted, where + " emitted bytes != oracle"
+                assert (a.phase == _abi.PHASE_FAILED) == relay.failed, where + " verdict != oracle"
+                if not relay.failed and not a.n_exotic:
+                    got = [json.loads(r[2])[0] for r in r_fast if r[0] == i]
+                    if a.flags & _abi.SF_EMITTED_ANY:
+                        got.append(json.loads(canon_rows([_abi.usage_rec_to_dict(a.rec)]))[0])
+                    assert canon_rows(got) == canon_rows(tap.rows), where + " usage rows != oracle"
+                    assert (not (a.flags & _abi.SF_A_USAGE_BOUND)) == relay.end_raises, where + " end_raises != oracle"
+                    n_ok += 1
+            assert r_fast == r_seq, tag + " mid-stream rows: bulk != sequential"
+            return tag, True, f"{n_ok}/{n_streams} compared with the oracle; {counters}"
+        finally:
+            eng.close_engine()
+    except Exception:
+        return tag, False, traceback.format_exc(limit=3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rounds", type=int, default=20)
+    ap.add_argument("--procs", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=1000)
+    ap.add_argument("--streams", type=int, default=300)
+    ap.add_argument("--replay", default=None)
+    args = ap.parse_args()
+    if args.replay:
+        gen, seed, n_steps, geo = args.replay.split(":")
+        print(*one_round((gen, int(seed), int(n_steps), int(geo), args.streams, False)), sep="\n")
+        return 0
+    rng = random.Random(args.seed)
+    jobs = []
+    for r in range(args.rounds):
+        jobs.append((rng.choice(["random", "template", "usage", "usage"]), args.seed * 1000 + r, rng.choice([1, 1, 2, 3, 5]), rng.randrange(len(GEOMETRIES)), args.streams, rng.random() < 0.25))
+    from host_relay import lib
+    lib()                                   # build the emulator library once, before the workers start
+    bad = 0
+    with mp.get_context("fork").Pool(args.procs) as pool:
+        for tag, ok, msg in pool.imap_unordered(one_round, jobs):
+            print(("ok   " if ok else "FAIL ") + tag + "  " + msg, flush=True)
+            bad += 0 if ok else 1
+    print(f"{len(jobs) - bad}/{len(jobs)} rounds clean")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
