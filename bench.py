@@ -633,6 +633,34 @@ def main():
     h2d = n_bytes + 4 * (n_chunks + 1) + 4 * (S + 1) + 4 * S + 8 * S
     d2h = n_bytes + S * SEG_DTYPE.itemsize + S * 440
 
+    # ---- the same end-to-end call in "verdicts only" mode (out_bytes = NULL: the caller relays its own copy of the chunks, as
+    # StreamBatcher(relay_from="host") does); a side measurement -- the headline `e2e` above downloads the re-emitted bytes --------
+    e2e_vo = None
+    try:
+        vo_ms = []
+        for k in range(2 + min(K, 5)):
+            b, h, d = sets[k % 2]
+            barrier()
+            t0 = time.perf_counter()
+            eng.open(b.seg_slot, status)
+            res = eng.step(h["data"].numpy(), h["chunk_off"].numpy(), h["seg_chunk"].numpy(), h["seg_slot"].numpy(), relay_from_host=True)
+            states = eng.close(b.seg_slot)
+            barrier()
+            if k >= 2:
+                vo_ms.append((time.perf_counter() - t0) * 1e3)
+        vo_step = float(np.mean(vo_ms))
+        assert bool((res.segs["emit_chunk_begin"].astype(np.int64) == np.asarray(b.seg_chunk[:-1], dtype=np.int64)).all()), "verdicts-only: a committed stream does not relay from its first chunk"
+        assert res.out.ctypes.data == h["data"].numpy().ctypes.data, "verdicts-only: the relayed bytes must be the caller's own buffer"
+        assert _abi.usage_rec_to_dict(states[5].rec) == b.truths[5].expected_row()
+        if world > 1:
+            t = torch.tensor([vo_step], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); vo_step = float(t.item())
+        e2e_vo = {"value": events_total / (vo_step / 1e3), "unit": UNIT, "ms_per_step": vo_step, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": S * SEG_DTYPE.itemsize + S * 440,
+                  "note": "lgw_sse_step with out_bytes = NULL: the relayed bytes are the caller's own (request_handler.py:141-142 yields the original chunk); "
+                          "the kernels and the device-side re-emit are unchanged, only the download of the bytes is left out. NOT the headline e2e."}
+    except Exception as ex:
+        e2e_vo = {"error": repr(ex)}
+
     # ---- transcript tap, same C3 batch, device resident; a side measurement, not part of `value` -----------
     text_tap = None
     if world == 1:
@@ -695,6 +723,8 @@ def main():
                                "k_relay2 locates the fields of every stream's usage event, k_commit2 reads them out)"},
         "wall_s_timed_loop": t_wall,
     }
+    if e2e_vo is not None:
+        line["e2e_verdicts_only"] = e2e_vo
     if text_tap is not None:
         line["transcript_tap"] = text_tap
     if world == 1 and not args.no_cpu_baseline:

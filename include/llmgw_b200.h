@@ -161,6 +161,10 @@ int lgw_streams_close(lgw_engine* e, const uint32_t* slots, uint32_t n, lgw_stre
  * rows_out/n_rows: mid-stream row events of this step, in no particular order across streams
  * (seq orders them within a stream).
  *
+ * out_bytes may be NULL in lgw_sse_step ("verdicts only"): the relayed bytes are by construction the caller's own bytes at the
+ * same offsets, so a caller that keeps its chunks (the batcher does) can relay those and save the download; everything else
+ * (seg_out, rows, stream state, the device-side re-emit) is unchanged.
+ *
  * lgw_sse_step takes HOST pointers and performs the H2D/D2H copies itself (synchronous).
  * lgw_sse_step_device takes DEVICE pointers for the five input arrays and out_bytes/seg_out, is
  * asynchronous on the engine stream, and leaves row events on the device until lgw_fetch_rows. */

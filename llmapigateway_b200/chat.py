@@ -287,8 +287,12 @@ class ChainBatch:
     first event fails (request_handler.py:86-88) moves on to its next attempt, one that commits is relayed to its end in the
     same step.  The per-request control (which plan next, which error text last) is array arithmetic over the batch."""
 
-    def __init__(self, engine, plans: rw.RulePlans, providers_config: dict, fallback_rules: dict, rotation: ModelRotation | None = None):
+    def __init__(self, engine, plans: rw.RulePlans, providers_config: dict, fallback_rules: dict, rotation: ModelRotation | None = None,
+                 relay_from_host: bool = False):
         self.eng, self.plans, self.providers, self.rules = engine, plans, providers_config, fallback_rules
+        # True: "verdicts only" steps (lgw_sse_step with out_bytes = NULL): the served bytes are slices of the upstream answers the
+        # host already holds, the step downloads the per-segment results only (see StreamBatcher relay_from="host")
+        self.relay_from_host = relay_from_host
         self.rotation = rotation or ModelRotation()
         self._sched_cache: dict = {}
         self._arenas: dict = {}                 # round -> pinned egress buffer (lgw_alloc_pinned), grown on demand, reused across runs
@@ -433,9 +437,10 @@ class ChainBatch:
                 slots = np.arange(m, dtype=np.uint32)
                 lap("control")
                 eng.open(slots, np.full(m, 200, np.int32))
-                arena = self._arena(rnd, int(ans.data.size))
+                arena = None if self.relay_from_host else self._arena(rnd, int(ans.data.size))
                 lap("open")
-                r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots, **({"out": arena} if arena is not None else {}))
+                r = eng.step(ans.data, ans.chunk_off, ans.seg_chunk, slots,
+                             **({"relay_from_host": True} if self.relay_from_host else ({"out": arena} if arena is not None else {})))
                 lap("step")
                 out.steps += 1
                 out.round_out[-1] = r.out

@@ -164,7 +164,15 @@ struct JsonMachine {
     uint32_t tpos, c_lo[2], c_hi[2], emit_lo, emit_hi;
     uint8_t emit_pending, rollback;
 
-    LGW_HD void track_field(int f, bool is_str) { if (EXTRACT && trk) { trk->fstart[f] = trk->vstart; trk->fend[f] = trk->pos + (is_str ? 1u : 0u); } }
+    // (a container value -- "prompt_tokens":[1] -- has no extent of its own here: vstart is where its LAST inner value began, which
+    // would alias that inner value's span; it is recorded as 0xFFFFFFFE = "present, not a scalar" and the template builder
+    // refuses to read usage fields from such a template)
+    LGW_HD void track_field(int f, uint8_t kind) {
+        if (EXTRACT && trk) {
+            if (kind == KD_ARR || kind == KD_OBJ) { trk->fstart[f] = trk->fend[f] = 0xFFFFFFFEu; return; }
+            trk->fstart[f] = trk->vstart; trk->fend[f] = trk->pos + (kind == KD_STR ? 1u : 0u);
+        }
+    }
 
     LGW_HD void reset(UsageRaw* r, bool strip) {
         st = S_VALUE; depth = 0; ctx = X_TOP; slot = SL_NONE; other_ret = X_TOP; other_depth = 0;
@@ -208,8 +216,8 @@ struct JsonMachine {
         case X_TOP:
             if (EXTRACT && rec) {
                 if (s == SL_USAGE) rec->usage_kind = kind;
-                else if (s == SL_MODEL) { rec->model_kind = kind; rec->model_val.kind = kind; rec->model_val.bits = bits; track_field(UF_MODEL, kind == KD_STR); }
-                else if (s == SL_PROVIDER) { rec->provider_kind = kind; rec->provider_val.kind = kind; rec->provider_val.bits = bits; track_field(UF_PROVIDER, kind == KD_STR); }
+                else if (s == SL_MODEL) { rec->model_kind = kind; rec->model_val.kind = kind; rec->model_val.bits = bits; track_field(UF_MODEL, kind); }
+                else if (s == SL_PROVIDER) { rec->provider_kind = kind; rec->provider_val.kind = kind; rec->provider_val.bits = bits; track_field(UF_PROVIDER, kind); }
             }
             if (EXTRACT && trk && s == SL_CHOICES) trk->choices_hi = trk->pos;
             if (s == SL_CHOICES) {
@@ -222,19 +230,19 @@ struct JsonMachine {
         case X_USAGE:
             if (EXTRACT && rec) {
                 Val v; v.kind = kind; v.bits = bits;
-                if (s == SL_PROMPT) { rec->prompt = v; track_field(UF_PROMPT, kind == KD_STR); }
-                else if (s == SL_COMPLETION) { rec->completion = v; track_field(UF_COMPLETION, kind == KD_STR); }
-                else if (s == SL_TOTAL) { rec->total = v; track_field(UF_TOTAL, kind == KD_STR); }
-                else if (s == SL_COST) { rec->cost = v; track_field(UF_COST, kind == KD_STR); }
+                if (s == SL_PROMPT) { rec->prompt = v; track_field(UF_PROMPT, kind); }
+                else if (s == SL_COMPLETION) { rec->completion = v; track_field(UF_COMPLETION, kind); }
+                else if (s == SL_TOTAL) { rec->total = v; track_field(UF_TOTAL, kind); }
+                else if (s == SL_COST) { rec->cost = v; track_field(UF_COST, kind); }
                 else if (s == SL_CTD) rec->ctd_kind = kind;
                 else if (s == SL_PTD) rec->ptd_kind = kind;
             }
             break;
         case X_CTD:
-            if (EXTRACT && rec && s == SL_REASONING) { rec->reasoning.kind = kind; rec->reasoning.bits = bits; track_field(UF_REASONING, kind == KD_STR); }
+            if (EXTRACT && rec && s == SL_REASONING) { rec->reasoning.kind = kind; rec->reasoning.bits = bits; track_field(UF_REASONING, kind); }
             break;
         case X_PTD:
-            if (EXTRACT && rec && s == SL_CACHED) { rec->cached.kind = kind; rec->cached.bits = bits; track_field(UF_CACHED, kind == KD_STR); }
+            if (EXTRACT && rec && s == SL_CACHED) { rec->cached.kind = kind; rec->cached.bits = bits; track_field(UF_CACHED, kind); }
             break;
         case X_CHOICES:
             // a scalar / string / nested array element of the choices list (objects are

@@ -329,7 +329,9 @@ extern "C" int lgw_sync(lgw_engine* e) {
 extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_bytes, const uint32_t* chunk_off, uint32_t n_chunks,
                             const uint32_t* seg_chunk, const uint32_t* seg_slot, uint32_t n_segs,
                             uint8_t* out_bytes, lgw_seg_result* seg_out, lgw_row_event* rows_out, uint32_t rows_cap, uint32_t* n_rows) {
-    if (!e || (!bytes && n_bytes) || !chunk_off || !seg_chunk || !seg_slot || (!out_bytes && n_bytes) || !seg_out || !n_rows) return LGW_ERR_ARG;
+    if (!e || (!bytes && n_bytes) || !chunk_off || !seg_chunk || !seg_slot || !seg_out || !n_rows) return LGW_ERR_ARG;
+    // out_bytes == NULL: the caller relays its own copy of the chunk bytes (the relayed bytes ARE the original bytes, request_handler.py:141-142);
+    // the kernels run unchanged (the re-emit lands in the device staging buffer), only the download of the bytes is left out
     if (n_segs > e->lim.max_streams || n_chunks > e->lim.max_step_chunks || n_bytes > e->lim.max_step_bytes) {
         e->err = "step exceeds the limits given to lgw_engine_create"; return LGW_ERR_CAPACITY;
     }
@@ -356,7 +358,7 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
         const bool big = e->mode == 0 && n_bytes >= (1u << 20);
         if (big && (allow & 1) && ((uintptr_t)bytes & 15) == 0 && cudaPointerGetAttributes(&pa, bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
             direct_in = (const uint8_t*)pa.devicePointer;
-        if (big && (allow & 2) && ((uintptr_t)out_bytes & 15) == 0 && cudaPointerGetAttributes(&pa, out_bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+        if (big && out_bytes && (allow & 2) && ((uintptr_t)out_bytes & 15) == 0 && cudaPointerGetAttributes(&pa, out_bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
             direct_out = (uint8_t*)pa.devicePointer;
         cudaGetLastError();                 // (cudaPointerGetAttributes on an unregistered pointer may leave an error behind)
         e->last_direct = direct_in || direct_out;
@@ -409,7 +411,7 @@ extern "C" int lgw_sse_step(lgw_engine* e, const uint8_t* bytes, uint64_t n_byte
         if (trace) cudaEventRecord(tr[1][j], e->stream);
         if (!direct_out) {
             if (piped) { CK(e, cudaEventRecord(e->ev_k[j], e->stream)); CK(e, cudaStreamWaitEvent(sout, e->ev_k[j], 0)); }
-            if (b1 > b0) CK(e, cudaMemcpyAsync(out_bytes + b0, e->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, sout));
+            if (b1 > b0 && out_bytes) CK(e, cudaMemcpyAsync(out_bytes + b0, e->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, sout));
         }
         if (trace) cudaEventRecord(tr[2][j], sout);
     }

@@ -388,6 +388,7 @@ R2_DEV_NOINLINE bool build_template2(const RD& rd, Tpl2* tp, UsageRaw* raw_out, 
         if (ok && (ff & TK_CHOICES)) for (uint32_t k = 0; k < n_ids; ++k) if (m.send[k] >= trk.choices_lo && m.sstart[k] <= trk.choices_hi) ok = false;
         for (uint32_t fi = 0; ok && fi < UF_N; ++fi) {
             if (trk.fstart[fi] == 0xFFFFFFFFu) continue;                          // field absent: the template's (absent) value stands
+            if (trk.fstart[fi] == 0xFFFFFFFEu) { ok = false; break; }            // a container where a usage field goes: not read from spans
             uint32_t j = 0xff;
             for (uint32_t k = 0; k < n_ids; ++k) {
                 if (m.skind[k] == 1 && m.sstart[k] == trk.fstart[fi] && m.send[k] == trk.fend[fi]) j = k;

@@ -137,14 +137,18 @@ class Engine:
 
     # -- the hot path --------------------------------------------------------------------------------
     def step(self, data: np.ndarray, chunk_off: np.ndarray, seg_chunk: np.ndarray, seg_slot: np.ndarray,
-             out: np.ndarray | None = None) -> StepResult:
-        """Host-buffer step: H2D, kernels, D2H inside the call."""
+             out: np.ndarray | None = None, relay_from_host: bool = False) -> StepResult:
+        """Host-buffer step: H2D, kernels, D2H inside the call.  relay_from_host=True: "verdicts only" -- the re-emitted bytes are
+        not downloaded; `StepResult.out` is then the caller's own `data` (the relayed bytes are the original bytes at the same
+        offsets, request_handler.py:141-142), everything else is the same."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         chunk_off = np.ascontiguousarray(chunk_off, dtype=np.uint32)
         seg_chunk = np.ascontiguousarray(seg_chunk, dtype=np.uint32)
         seg_slot = np.ascontiguousarray(seg_slot, dtype=np.uint32)
         n_bytes, n_chunks, n_segs = data.size, chunk_off.size - 1, seg_slot.size
-        if out is None:
+        if relay_from_host:
+            out = None
+        elif out is None:
             out = np.empty(max(n_bytes, 1), dtype=np.uint8)
         segs = np.zeros(max(n_segs, 1), dtype=SEG_DTYPE)
         cap = self.limits.rowq_cap
@@ -154,8 +158,8 @@ class Engine:
         n_rows = C.c_uint32(0)
         self._last_n_segs = n_segs
         self._ck(self._lib.lgw_sse_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot),
-                                        n_segs, _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows)), "sse_step")
-        return StepResult(out[:n_bytes], segs[:n_segs], [_abi.RowEvent.from_buffer_copy(rows[i]) for i in range(n_rows.value)])
+                                        n_segs, _ptr(out) if out is not None else None, _ptr(segs), rows, cap, C.byref(n_rows)), "sse_step")
+        return StepResult((out if out is not None else data)[:n_bytes], segs[:n_segs], [_abi.RowEvent.from_buffer_copy(rows[i]) for i in range(n_rows.value)])
 
     def step_device(self, d_data: int, n_bytes: int, d_chunk_off: int, n_chunks: int, d_seg_chunk: int, d_seg_slot: int,
                     n_segs: int, d_out: int, d_segs: int):

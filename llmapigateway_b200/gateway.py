@@ -52,11 +52,19 @@ class StreamBatcher:
     request goes away (client disconnect cancels the awaiting feed()) can never be packed into the next stream that
     gets the slot, and a slot only returns to the free list once no step that contains it is in flight."""
 
-    def __init__(self, engine, window_s: float = 0.002, usage_sink=None, arena_bytes: int = 8 << 20, transcript_log=None):
+    def __init__(self, engine, window_s: float = 0.002, usage_sink=None, arena_bytes: int = 8 << 20, transcript_log=None,
+                 relay_from: str = "device"):
         import collections
         self.eng = engine
         self.window_s = window_s
         self.usage_sink = usage_sink
+        # relay_from="device": the bytes handed to the client are the ones the engine re-emitted (downloaded with the step).
+        # relay_from="host": "verdicts only" (lgw_sse_step with out_bytes = NULL) -- the relayed chunk is the very chunk object
+        # the upstream delivered, as in the reference (`yield chunk`, request_handler.py:141-142); the engine decides WHICH chunks
+        # are relayed and everything else, and the step's download shrinks to the per-segment results.
+        if relay_from not in ("device", "host"):
+            raise ValueError("relay_from must be 'device' or 'host'")
+        self.relay_from = relay_from
         # chat transcripts (SURVEY 8(f) rank 3): with a `transcripts.TranscriptLog` the engine's transcript tap runs after every
         # step and every row goes through write_log (file, THEN the usage row, chat_logging.py:47-56) instead of straight to the sink
         self.transcript_log = transcript_log
@@ -225,8 +233,8 @@ class StreamBatcher:
             for s in slots:
                 self._inflight[s] = done
             def _step():
-                r = self.eng.step(data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32),
-                                  **({"out": out} if out is not None else {}))
+                kw = {"relay_from_host": True} if self.relay_from == "host" else ({"out": out} if out is not None else {})
+                r = self.eng.step(data, np.array(offs, np.uint32), np.array(segc, np.uint32), np.array(slots, np.uint32), **kw)
                 return r, (self.eng.step_transcript() if self._book is not None else None)
             try:
                 res, step_text = await loop.run_in_executor(self._worker, _step)
@@ -261,7 +269,8 @@ class StreamBatcher:
                         c = segc[k] + j
                         emitted = None
                         if c >= eb and len(p.chunk):
-                            emitted = res.out[offs[c]:offs[c + 1]].tobytes()          # the re-emitted bytes
+                            # the re-emitted bytes (host mode: the upstream's own chunk object, no copy)
+                            emitted = p.chunk if self.relay_from == "host" else res.out[offs[c]:offs[c + 1]].tobytes()
                         if not p.fut.done():
                             p.fut.set_result(FeedResult(emitted, int(res.segs["phase"][k]), int(res.segs["verdict"][k]), flags))
                 except Exception as exc:                                         # never leave a future of the batch unresolved

@@ -29,7 +29,7 @@ class FakeEngine:
     def _run(self, h):
         return hm.run_stream(h["chunks"], h["steps"] or [0], h["status"])
 
-    def step(self, data, chunk_off, seg_chunk, seg_slot, out=None):
+    def step(self, data, chunk_off, seg_chunk, seg_slot, out=None, relay_from_host=False):
         data = np.asarray(data, dtype=np.uint8)
         segs = np.zeros(len(seg_slot), dtype=SEG_DTYPE)
         rows = []

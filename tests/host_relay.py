@@ -99,7 +99,7 @@ class HostBulkEngine:
         n = self._lib.lgwt_bulk_detail(self._h, slot, buf, self.limits.detail_cap)
         return buf.raw[:n]
 
-    def step(self, data, chunk_off, seg_chunk, seg_slot, out=None) -> StepResult:
+    def step(self, data, chunk_off, seg_chunk, seg_slot, out=None, relay_from_host=False) -> StepResult:
         data = np.ascontiguousarray(data, dtype=np.uint8)
         chunk_off = np.ascontiguousarray(chunk_off, dtype=np.uint32)
         seg_chunk = np.ascontiguousarray(seg_chunk, dtype=np.uint32)
@@ -114,7 +114,7 @@ class HostBulkEngine:
         self._lib.lgwt_bulk_step(self._h, _ptr(data), n_bytes, _ptr(chunk_off), n_chunks, _ptr(seg_chunk), _ptr(seg_slot), n_segs,
                                  _ptr(out), _ptr(segs), rows, cap, C.byref(n_rows), self.tiles_per_warp)
         self._last = (data, chunk_off, seg_chunk, seg_slot, segs)
-        return StepResult(out[:n_bytes], segs[:n_segs], [rows[i] for i in range(n_rows.value)])
+        return StepResult((data if relay_from_host else out)[:n_bytes], segs[:n_segs], [rows[i] for i in range(n_rows.value)])
 
     def enable_transcripts(self):
         self._lib.lgwt_bulk_transcripts_enable(self._h)

@@ -72,10 +72,13 @@ def test_make_llm_request_seam_matches_reference():
     asyncio.run(go())
 
 
-def test_batcher_interleaves_many_streams():
+@pytest.mark.parametrize("relay_from", ["device", "host"])
+def test_batcher_interleaves_many_streams(relay_from):
+    """relay_from="host" (verdicts-only steps): the relayed chunks are the upstream's own chunk objects, chosen by the engine's
+    per-segment results -- same bytes, same rows as with the downloaded re-emit."""
     async def go():
         sink = _Sink()
-        batcher = StreamBatcher(FakeEngine(max_streams=64), window_s=0.001, usage_sink=sink)
+        batcher = StreamBatcher(FakeEngine(max_streams=64), window_s=0.001, usage_sink=sink, relay_from=relay_from)
         picks = [c for c in CASES if not c["failed"] and c["chunks"]][:40]
         results = await asyncio.gather(*[_drive(c, batcher, _Sink()) for c in picks])
         for c, r in zip(picks, results):
@@ -162,7 +165,8 @@ def test_chain_walker_matches_the_reference_goldens():
         cc.check_against_golden(case, g)
 
 
-def test_chain_batch_matches_the_oracle():
+@pytest.mark.parametrize("relay_from_host", [False, True])
+def test_chain_batch_matches_the_oracle(relay_from_host):
     """ChainBatch (lock-step rounds) == the per-request oracle walk: served-by round, relayed bytes, 503 details, attempt count."""
     from fake_engine import FakeEngine
     from llmapigateway_b200 import chat, rewrite, synth
@@ -179,7 +183,7 @@ def test_chain_batch_matches_the_oracle():
     eng = FakeEngine(max_streams=n)
     plans = rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode())
     eng.load_rules(plans)
-    out = chat.ChainBatch(eng, plans, providers, rules).run(bodies, ["k"] * n, up)
+    out = chat.ChainBatch(eng, plans, providers, rules, relay_from_host=relay_from_host).run(bodies, ["k"] * n, up)
     rot = chain_oracle.Rotation()
     n_attempts = 0
     for i in range(n):

@@ -73,3 +73,11 @@ def test_usage_fields_come_from_the_template_spans(engine):
         relay, tap = run_stream(b.stream_chunks(s))
         assert canon_rows([_abi.usage_rec_to_dict(states[s].rec)]) == canon_rows(tap.rows)
     engine.close(b.seg_slot)
+
+
+def test_verdicts_only_step(engine):
+    G.test_verdicts_only_step_equals_the_full_step(engine)
+
+
+def test_container_valued_usage_fields(engine):
+    G.test_container_valued_usage_fields_are_never_read_from_a_span(engine)

@@ -268,8 +268,10 @@ def test_bulk_path_equals_sequential_path_and_oracle(engine, n_steps, n_streams=
     assert n_regular > min_regular
 
 
-def test_gateway_seam_on_the_real_engine(engine):
-    """make_llm_request + StreamBatcher over the CUDA engine against the reference goldens."""
+@pytest.mark.parametrize("relay_from", ["device", "host"])
+def test_gateway_seam_on_the_real_engine(engine, relay_from):
+    """make_llm_request + StreamBatcher over the CUDA engine against the reference goldens (relay_from="host": verdicts-only steps,
+    lgw_sse_step with out_bytes = NULL, the relayed chunks are the upstream's own)."""
     import asyncio
     from test_gateway_cpu import _Sink, _drive
     from llmapigateway_b200.gateway import StreamBatcher
@@ -277,7 +279,7 @@ def test_gateway_seam_on_the_real_engine(engine):
 
     async def go():
         sink = _Sink()
-        batcher = StreamBatcher(engine, window_s=0.0005, usage_sink=sink)
+        batcher = StreamBatcher(engine, window_s=0.0005, usage_sink=sink, relay_from=relay_from)
         picks = CASES[:150]
         results = await asyncio.gather(*[_drive(c, batcher, _Sink()) for c in picks])
         n_rows_ok = 0
@@ -436,3 +438,55 @@ print("DIRECT_OK")
     r = subprocess.run([sys.executable, "-c", code, direct], capture_output=True, text=True, timeout=300, env=dict(os.environ, LGW_DIRECT=direct),
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "DIRECT_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def test_verdicts_only_step_equals_the_full_step(engine):
+    """lgw_sse_step with out_bytes = NULL (no download of the re-emitted bytes): segment results, row events and final states equal
+    those of the ordinary step on the same streams, sliced pipeline (> 8 MiB) and single slice alike; the bytes the caller relays
+    from its own buffer are the bytes the engine re-emits."""
+    engine.set_mode(0)
+    for n_streams, n_events in [(96, 24), (2048, 80)]:
+        b = sse_batch(n_streams=n_streams, n_events=n_events, seed=31)
+        got = []
+        for host in (False, True):
+            engine.open(b.seg_slot)
+            half = [int(b.seg_chunk[s] + (b.seg_chunk[s + 1] - b.seg_chunk[s]) // 2) for s in range(n_streams)]
+            parts = []
+            for lo_of, hi_of in ((lambda s: int(b.seg_chunk[s]), lambda s: half[s]), (lambda s: half[s], lambda s: int(b.seg_chunk[s + 1]))):
+                pb = pack_streams([[b.data[int(b.chunk_off[c]):int(b.chunk_off[c + 1])].tobytes() for c in range(lo_of(s), hi_of(s))] for s in range(n_streams)],
+                                  slots=list(range(n_streams)))
+                r = engine.step(pb.data, pb.chunk_off, pb.seg_chunk, pb.seg_slot, relay_from_host=host)
+                emitted = [r.out[int(pb.chunk_off[int(r.segs["emit_chunk_begin"][s])]):int(pb.chunk_off[int(pb.seg_chunk[s + 1])])].tobytes() for s in range(n_streams)]
+                parts.append((r.segs.tobytes(), sorted((e.slot, e.seq, canon_rows([_abi.usage_rec_to_dict(e.rec)])) for e in r.rows), emitted))
+            states = engine.close(b.seg_slot)
+            # (header bytes + the record's values: the padding inside the record's value cells is not part of the contract)
+            got.append((parts, [(bytes(st)[:64], canon_rows([_abi.usage_rec_to_dict(st.rec)])) for st in states]))
+        assert got[0] == got[1]
+
+
+def test_container_valued_usage_fields_are_never_read_from_a_span(engine):
+    """Regression (found by tools/fuzz_relay2_cpu.py): `"prompt_tokens":[1]` / `"model":["x"]` -- the container's last inner scalar
+    used to be taken for the field's own value span, so a template learnt from such an event read `1` / "x" where the reference
+    stores the list itself (get_token_usage hands it on, chat_logging.py:237-267).  Bulk path == sequential path == oracle."""
+    from oracle.sse_oracle import run_stream
+    import sse_cases as sc
+    ev = ('data: {"choices":[],"usage":{"prompt_tokens":%s,"completion_tokens":%s,"total_tokens":3,"cost":0.5,'
+          '"completion_tokens_details":{"reasoning_tokens":%s},"prompt_tokens_details":{"cached_tokens":0}},"model":%s,"provider":"P"}\n\n')
+    shapes = [("[1]", "2", "0", '"m"'), ('{"a":7}', "2", "0", '"m"'), ("1", "[22]", "0", '"m"'), ("1", "2", "[5]", '"m"'), ("1", "2", "0", '["x"]'),
+              ("1", "2", "0", '{"k":"x"}'), ("[1]", "[2]", "[3]", '["x"]'), ("1", "2", "0", '"m"')]
+    streams = []
+    for rep in range(6):                       # the same skeletons again and again: later streams follow the templates the first ones left
+        for k, sh in enumerate(shapes):
+            tail = (ev % sh).replace("[1]", "[%d]" % (rep + 1)).replace('["x"]', '["y%d"]' % rep).encode()
+            streams.append([sc.delta("a"), sc.delta("hello %d" % k), tail, sc.DONE])
+    engine.reset_templates() if hasattr(engine, "reset_templates") else None
+    s_fast, r_fast, e_fast = _run_all(engine, streams, 0, 1, seed=1)
+    s_seq, r_seq, e_seq = _run_all(engine, streams, 1, 1, seed=1)
+    assert e_fast == e_seq and r_fast == r_seq
+    for i, (a, b) in enumerate(zip(s_fast, s_seq)):
+        assert bytes(a)[:64] == bytes(b)[:64], i
+        assert a.rec.exotic == b.rec.exotic and str(_abi.usage_rec_to_dict(a.rec)) == str(_abi.usage_rec_to_dict(b.rec)), (i, streams[i][2])
+        relay, tap = run_stream(streams[i])
+        assert e_fast[i] == relay.emitted
+        if not a.n_exotic:
+            assert canon_rows([_abi.usage_rec_to_dict(a.rec)]) == canon_rows(tap.rows), i

@@ -9,7 +9,7 @@ chat_logging.py:87-150,233-272).  Engine geometries (blocks, tiles per warp) and
     python tools/fuzz_relay2_cpu.py --rounds 40 --procs 6 --seed 1000
 
 Prints one line per round; a divergence is reported with the generator, seed and stream so that it can be replayed
-(`--replay gen:seed:n_steps:geometry`).
+(`--replay gen:seed:n_steps:geometry:cold`).
 """
 from __future__ import annotations
 
@@ -101,7 +101,7 @@ def one_round(job):
     from host_relay import HostBulkEngine
     from llmapigateway_b200 import _abi
     from oracle.sse_oracle import run_stream
-    tag = f"{gen}:{seed}:{n_steps}:{geo}"
+    tag = f"{gen}:{seed}:{n_steps}:{geo}:{int(cold)}"
     try:
         nb, tpw = GEOMETRIES[geo]
         eng = HostBulkEngine(max_streams=2048, n_blocks=nb, tiles_per_warp=tpw)
@@ -148,8 +148,8 @@ def main():
     ap.add_argument("--replay", default=None)
     args = ap.parse_args()
     if args.replay:
-        gen, seed, n_steps, geo = args.replay.split(":")
-        print(*one_round((gen, int(seed), int(n_steps), int(geo), args.streams, False)), sep="\n")
+        gen, seed, n_steps, geo, *cold = args.replay.split(":")
+        print(*one_round((gen, int(seed), int(n_steps), int(geo), args.streams, bool(cold and int(cold[0])))), sep="\n")
         return 0
     rng = random.Random(args.seed)
     jobs = []
