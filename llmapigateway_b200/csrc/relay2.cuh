@@ -619,7 +619,12 @@ R2_DEV bool enter_segment(R2Ctx& c, uint32_t seg, uint32_t from, uint32_t range_
     c.kept_end = kept;
     c.pos = te; c.walk_lo = te;
     c.t = 0;
-    if (pl->irregular || tb >= te) return false;
+    // `irregular` is the one plan field other warps write while this kernel runs (mark_irregular): one lane reads it and hands
+    // it to all -- lanes reading it on their own could see different values and part ways before the next collective
+    uint32_t irr = 0;
+    if (c.lane == 0) irr = *(volatile const uint32_t*)&pl->irregular;
+    irr = __shfl_sync(R2_FULL, irr, 0);
+    if (irr || tb >= te) return false;
     if (from <= tb) {
         if (tb >= range_hi) return false;
         if (kept) c.in_kept = 1u;                            // the kept chunk is walked by ONE warp, the one that owns its first byte (beyond its range if need be)

@@ -11,3 +11,20 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+# Fuzz campaigns: LGW_FUZZ_SALT=<anything> re-seeds every `random.Random(seed)` of the test suite (seed -> "seed/salt"), so that
+# the differential tests (device machines vs oracle / CPython / the sequential machine) see fresh inputs on every run:
+#     for s in 1 2 3; do LGW_FUZZ_SALT=$s python -m pytest tests -q -m "not gpu" -p no:cacheprovider; done
+# Unset (the default, and what the driver runs) the suite is deterministic.
+import os as _os
+
+_SALT = _os.environ.get("LGW_FUZZ_SALT")
+if _SALT:
+    import random as _random
+
+    class _SaltedRandom(_random.Random):
+        def seed(self, a=None, version=2):
+            super().seed(a if a is None else f"{a!r}/{_SALT}", version)
+
+    _random.Random = _SaltedRandom

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <ucontext.h>
+#include <dlfcn.h>
 #include <functional>
 #include <vector>
 
@@ -105,7 +106,10 @@ static inline uint64_t collective(int op, uint32_t mask, uint64_t val, uint32_t 
 #endif
     if (w.arrived == 0) { w.mask = mask; w.op = op; w.site = site; }
     else if (w.mask != mask || w.op != op) {
-        fprintf(stderr, "simt_emu: divergent collective in warp %u lane %u (op %d/%d mask %08x/%08x) sites %p / %p (arrived %08x)\n", t >> 5, lane, w.op, op, w.mask, mask, w.site, site, w.arrived);
+        Dl_info di0{}, di1{};                      // offsets inside the test library: `addr2line -e tests/support/_host_relay2.so <offset>`
+        dladdr(w.site, &di0); dladdr(site, &di1);
+        fprintf(stderr, "simt_emu: divergent collective in warp %u lane %u (op %d/%d mask %08x/%08x) sites +0x%zx / +0x%zx (arrived %08x)\n", t >> 5, lane, w.op, op, w.mask, mask,
+                (size_t)((char*)w.site - (char*)di0.dli_fbase), (size_t)((char*)site - (char*)di1.dli_fbase), w.arrived);
         abort();
     }
     w.in[lane] = val; w.aux[lane] = aux; w.arrived |= 1u << lane;

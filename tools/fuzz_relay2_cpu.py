@@ -157,9 +157,22 @@ def main():
         jobs.append((rng.choice(["random", "template", "usage", "usage"]), args.seed * 1000 + r, rng.choice([1, 1, 2, 3, 5]), rng.randrange(len(GEOMETRIES)), args.streams, rng.random() < 0.25))
     from host_relay import lib
     lib()                                   # build the emulator library once, before the workers start
+    # every round in a process of its own: the emulator ABORTS on a divergent collective or a deadlock (a finding, not a crash of
+    # the campaign), and a pool worker that dies takes its job with it
+    import subprocess
+    from concurrent.futures import ThreadPoolExecutor
+
+    def spawn(job):
+        gen, seed, n_steps, geo, n_streams, cold = job
+        tag = f"{gen}:{seed}:{n_steps}:{geo}:{int(cold)}"
+        r = subprocess.run([sys.executable, __file__, "--replay", tag, "--streams", str(n_streams)], capture_output=True, text=True)
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        if r.returncode != 0 or len(lines) < 3:
+            return tag, False, "process ended with status %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])
+        return tag, lines[1] == "True", "\n".join(lines[2:])
     bad = 0
-    with mp.get_context("fork").Pool(args.procs) as pool:
-        for tag, ok, msg in pool.imap_unordered(one_round, jobs):
+    with ThreadPoolExecutor(args.procs) as pool:
+        for tag, ok, msg in pool.map(spawn, jobs):
             print(("ok   " if ok else "FAIL ") + tag + "  " + msg, flush=True)
             bad += 0 if ok else 1
     print(f"{len(jobs) - bad}/{len(jobs)} rounds clean")
