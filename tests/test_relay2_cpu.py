@@ -81,3 +81,21 @@ def test_verdicts_only_step(engine):
 
 def test_container_valued_usage_fields(engine):
     G.test_container_valued_usage_fields_are_never_read_from_a_span(engine)
+
+
+def test_lanes_agree_on_a_segment_another_warp_flags():
+    """Regression (tools/fuzz_relay2_cpu.py): `plan[seg].irregular` is written by other warps of the launch; when every lane read
+    it on its own, lanes could see different values and part ways before the next collective (the emulator aborts the process on
+    that: "divergent collective").  This batch on this geometry is one the campaign found; it runs in a process of its own."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path[:0] = [%r, %r]
+        import test_sse_gpu as G
+        from host_relay import HostBulkEngine
+        eng = HostBulkEngine(max_streams=2048, n_blocks=3, tiles_per_warp=1)
+        G._run_all(eng, G._template_variant_streams(64, 11211), 0, 1, seed=3)
+        print("clean")
+    """) % (str(G.__file__).rsplit("/tests/", 1)[0], str(G.__file__).rsplit("/", 1)[0])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-500:]

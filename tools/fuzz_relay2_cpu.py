@@ -26,6 +26,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 GEOMETRIES = [(2, 0), (3, 1), (1, 0), (5, 2), (4, 1)]
+GENERATORS = ["random", "template", "usage", "usage", "openai", "c3"]
 
 NUMBERS = ["0", "7", "12", "123456", "2147483647", "2147483648", "4294967296", "9007199254740993", "18446744073709551616",
            "-1", "-0", "0.0", "0.5", "1.25", "1e3", "1E3", "1e+3", "1e-3", "12.5e-2", "0.000001", "1.7976931348623157e308", "1e400",
@@ -85,8 +86,44 @@ def usage_variant_streams(n_streams: int, seed: int):
     return out
 
 
+def _recut(rng, chunks):
+    """the same bytes in other network chunks: whole events, a fixed stride, or a few arbitrary cuts"""
+    import sse_cases as sc
+    m = rng.random()
+    if m < 0.5:
+        return chunks
+    blob = b"".join(chunks)
+    if m < 0.75:
+        step = rng.randrange(7, 700)
+        return [c for c in sc.rechunk(blob, list(range(step, len(blob), step))) if c]
+    return [c for c in sc.rechunk(blob, [rng.randrange(1, max(2, len(blob))) for _ in range(rng.randrange(1, 9))]) if c]
+
+
+def shaped_streams(gen: str, n: int, seed: int):
+    """`openai`: realistic OpenAI chunks (synth.openai_stream: id / created / model on every event, role and finish chunks, pieces
+    of varying length with escapes and raw UTF-8); `c3`: the benchmark's own 64-byte deltas (synth.sse_batch).  Both with the
+    usage event and [DONE], 1..k events per chunk or recut at arbitrary bytes."""
+    import numpy as np
+    from llmapigateway_b200 import synth
+    rng = random.Random(seed)
+    if gen == "openai":
+        nrng = np.random.default_rng(seed)
+        truths = synth._usage_truths(n, seed)
+        out = []
+        for s_ in range(n):
+            epc = rng.choice([(1, 1), (1, 4), (2, 2), (1, 9)])
+            out.append(_recut(rng, synth.openai_stream(nrng, rng.randrange(1, 60), truths[s_], "chatcmpl-%08x" % rng.randrange(2**32), epc)))
+        return out
+    n_events = rng.choice([8, 16, 48, 96])
+    b = synth.sse_batch(n_streams=n, n_events=n_events, seed=seed, events_per_chunk=rng.choice([1, 1, 2, 8]),
+                        with_usage=rng.random() < 0.9, with_done=rng.random() < 0.9)
+    return [_recut(rng, b.stream_chunks(s_)) for s_ in range(n)]
+
+
 def make_streams(gen: str, n: int, seed: int):
     import test_sse_gpu as G
+    if gen in ("openai", "c3"):
+        return shaped_streams(gen, n, seed)
     if gen == "random":
         return G._random_streams(n, seed)
     if gen == "template":
@@ -146,15 +183,18 @@ def main():
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--streams", type=int, default=300)
     ap.add_argument("--replay", default=None)
+    ap.add_argument("--gens", default=None, help="comma-separated subset of the generators")
     args = ap.parse_args()
     if args.replay:
         gen, seed, n_steps, geo, *cold = args.replay.split(":")
         print(*one_round((gen, int(seed), int(n_steps), int(geo), args.streams, bool(cold and int(cold[0])))), sep="\n")
         return 0
+    if args.gens:
+        GENERATORS[:] = args.gens.split(",")
     rng = random.Random(args.seed)
     jobs = []
     for r in range(args.rounds):
-        jobs.append((rng.choice(["random", "template", "usage", "usage"]), args.seed * 1000 + r, rng.choice([1, 1, 2, 3, 5]), rng.randrange(len(GEOMETRIES)), args.streams, rng.random() < 0.25))
+        jobs.append((rng.choice(GENERATORS), args.seed * 1000 + r, rng.choice([1, 1, 2, 3, 5]), rng.randrange(len(GEOMETRIES)), args.streams, rng.random() < 0.25))
     from host_relay import lib
     lib()                                   # build the emulator library once, before the workers start
     # every round in a process of its own: the emulator ABORTS on a divergent collective or a deadlock (a finding, not a crash of
