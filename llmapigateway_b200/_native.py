@@ -3,11 +3,14 @@ if the CUDA library is missing or no device is usable, importing/creating raises
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import _abi
 
 LIB_PATH = Path(__file__).resolve().parent / "_native" / "libllmgw_b200.so"
+if os.environ.get("LGW_NATIVE_LIB"):          # kernel-geometry experiments (tools/run_geometry_variants.sh): another build of the same library
+    LIB_PATH = Path(os.environ["LGW_NATIVE_LIB"]).resolve()
 
 EXPORTS = [
     "lgw_abi_version", "lgw_engine_create", "lgw_engine_destroy", "lgw_last_error", "lgw_engine_set_stream",

@@ -56,10 +56,16 @@
 #define R2_HOST_EMU 1
 #endif
 
+#ifndef R2_WARPS                        /* (overridable for geometry experiments: make EXTRA="-DR2_WARPS=24u -DR2_TILE=2048u") */
 #define R2_WARPS 16u
+#endif
 #define R2_THREADS (R2_WARPS * 32u)
-#define R2_TILE 3072u
+#ifndef R2_TILE
+#define R2_TILE 3072u                   /* a multiple of 512 (the fast loop walks whole 512-byte windows of a tile) */
+#endif
+#ifndef R2_NBUF
 #define R2_NBUF 3u
+#endif
 #define R2_SLOTS 4u
 #define R2_TPL_MAX 504u                 /* longest event kept as a template (text without its LF LF) */
 #define R2_TPL_MIN 16u

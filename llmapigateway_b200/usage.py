@@ -130,12 +130,25 @@ class UsageTable:
         self._host["model_rank"] = np.fromiter((rank[m] for m in self._models), dtype=np.int32, count=len(self._models))
         self._names = [None] + names
 
+    def _free_device(self):
+        """Give the device copy of the columns back (an insert makes it stale; without this every re-upload would leak the last one)."""
+        ptrs, self._dev_ptrs = getattr(self, "_dev_ptrs", None), None
+        self._dev = None
+        if ptrs and getattr(self.eng, "_h", None):
+            for p in ptrs.values():
+                self._lib.lgw_device_free(self.eng._h, p)
+
+    def close(self):
+        self._free_device()
+
     def _upload(self):
         if self._dev is not None:
             return
+        self._free_device()
         self._materialise()
         n = int(self._host["ts_us"].size)
         ptrs = {}
+        self._dev_ptrs = ptrs                     # (registered before the first allocation: a failed upload frees what it got)
         for c in self.COLS:
             a = self._host[c]
             p = C.c_void_p()
