@@ -3,7 +3,7 @@
 //
 // What changed against round 1 (relay_kernels.cuh, thread-per-chunk walk of a staged tile):
 //   * The re-emit is done by the TMA engine: every warp owns a contiguous byte range and runs its own ring of
-//     4 KiB shared-memory buffers -- cp.async.bulk global -> shared (mbarrier complete_tx), cp.async.bulk shared ->
+//     3 KiB shared-memory buffers -- cp.async.bulk global -> shared (mbarrier complete_tx), cp.async.bulk shared ->
 //     global straight from the same buffer.  No byte of the copy passes through a register.
 //   * The parse is warp-cooperative and driven by bytes, not by chunks: 16 bytes per lane, 512 bytes per pass.  SSE
 //     deltas of a stream are the same JSON skeleton over and over, so the event text is compared against a PERIODIC
@@ -64,7 +64,9 @@
 #define R2_TILE 3072u                   /* a multiple of 512 (the fast loop walks whole 512-byte windows of a tile) */
 #endif
 #ifndef R2_NBUF
-#define R2_NBUF 3u
+#define R2_NBUF 2u                      /* ring depth per warp.  2 x 3 KiB x 16 warps = 96 KiB: with the 28 KiB of tables the block takes the 132 KiB
+                                           carve-out and leaves ~96 KiB of L1 for the out-of-line paths' local memory (672 B of stack per thread);
+                                           a 3-deep ring (144 KiB, 32 KiB of L1 left) measured 140 us per C3 step against 124 us */
 #endif
 #define R2_SLOTS 4u
 #define R2_TPL_MAX 504u                 /* longest event kept as a template (text without its LF LF) */
@@ -1249,6 +1251,9 @@ R2_GLOBAL void k_prime2(StepArgs a) {
 
 // ---- k_commit2 (one warp per segment) ----------------------------------------------------------------------------------------------
 #define R2_CWARPS 8u
+#ifndef R2_CBLOCKS                      /* resident blocks per SM the commit kernel is compiled for: 6 -> 40 registers, 4 -> 64, 3 -> 80 */
+#define R2_CBLOCKS 6
+#endif
 // the exact sequential machine over a stream's chunks (streams the bulk kernel could not vouch for), out of line
 R2_DEV_NOINLINE uint32_t commit_sequential(StepIO io, const uint8_t* data, const uint32_t* chunk_off, uint32_t c_from, uint32_t c_to, uint32_t emit_begin) {
     run_chunks(io, data, chunk_off, c_from, c_to, emit_begin, false);
@@ -1335,7 +1340,7 @@ R2_DEV uint4 commit_ld16(const uint8_t* p) { uint4 v; memcpy(&v, p, 16); return 
 
 R2_GLOBAL void
 #if !R2_HOST_EMU
-__launch_bounds__(R2_CWARPS * 32, 6)      // (the full machine behind commit_usage_event / commit_sequential spills instead of costing every warp 142 registers)
+__launch_bounds__(R2_CWARPS * 32, R2_CBLOCKS)      // (the full machine behind commit_usage_event / commit_sequential spills instead of costing every warp 142 registers)
 #endif
 k_commit2(StepArgs a) {
 #if !R2_HOST_EMU
