@@ -200,7 +200,14 @@ TX_GLOBAL void k_text_open(TextTap* tap, const uint32_t* slots, uint32_t n) {
     tap[slots[i]] = z;
 }
 
-TX_GLOBAL void k_text_extract(TextArgs a) {
+#ifndef TX_BLOCKS                        /* resident 256-thread blocks per SM k_text_extract is compiled for (register budget 65536 / (256 * TX_BLOCKS)) */
+#define TX_BLOCKS 4                     /* 64 registers: 32 warps per SM, the 4 096 warps of a C3 step are one wave (2.27 -> 2.03 ms; 3 -> 2.57, 5 -> 2.46, 6 -> 2.44) */
+#endif
+TX_GLOBAL void
+#if defined(__CUDACC__)
+__launch_bounds__(TX_WARPS * 32, TX_BLOCKS)
+#endif
+k_text_extract(TextArgs a) {
     const uint32_t seg = TX_BID * TX_WARPS + (TX_TID >> 5), lane = TX_TID & 31u;
     if (seg >= a.n_segs) return;
     const uint32_t slot = a.seg_slot[seg];
