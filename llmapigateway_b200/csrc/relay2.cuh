@@ -1122,7 +1122,11 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
 
 R2_GLOBAL void
 #if !R2_HOST_EMU
+#ifdef R2_MAXREG                        /* experiment: a register cap below 65536 / R2_THREADS leaves room for the commit kernel's blocks beside this one */
+__maxnreg__(R2_MAXREG)
+#else
 __launch_bounds__(R2_THREADS, 1)
+#endif
 #endif
 k_relay2(StepArgs a, uint32_t n_tiles_total, uint32_t tiles_per_warp, uint32_t base0) {
     uint8_t* smem = smem_base();
