@@ -26,7 +26,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 GEOMETRIES = [(2, 0), (3, 1), (1, 0), (5, 2), (4, 1)]
-GENERATORS = ["random", "template", "usage", "usage", "openai", "c3"]
+GENERATORS = ["random", "template", "usage", "usage", "openai", "c3", "skeleton", "skeleton"]
 
 NUMBERS = ["0", "7", "12", "123456", "2147483647", "2147483648", "4294967296", "9007199254740993", "18446744073709551616",
            "-1", "-0", "0.0", "0.5", "1.25", "1e3", "1E3", "1e+3", "1e-3", "12.5e-2", "0.000001", "1.7976931348623157e308", "1e400",
@@ -120,10 +120,66 @@ def shaped_streams(gen: str, n: int, seed: int):
     return [_recut(rng, b.stream_chunks(s_)) for s_ in range(n)]
 
 
+SKELETONS = [   # %n = a number spelling, %s = a string value; every batch repeats a few of these so that they become templates
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"model":%s,"provider":%s}',
+    '{"choices": [], "usage": {"prompt_tokens": %n, "completion_tokens": %n, "total_tokens": %n, "cost": %n}, "model": %s}',
+    '{"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"cost":%n},"choices":[{"index":0,"delta":{"content":%s},"finish_reason":null}]}',
+    '{"id":%s,"choices":[{"index":0,"delta":{},"finish_reason":"stop","usage":{"prompt_tokens":%n}}],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n}}',
+    '{"x":{"usage":{"prompt_tokens":%n,"completion_tokens":%n}},"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"model":%s}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"model":%s}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"model":%s}',
+    '{"choices":[],"model":%s,"model":%s,"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n}}',
+    '{"choices":[],"usage":{"completion_tokens_details":{"reasoning_tokens":%n,"prompt_tokens":%n},"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"prompt_tokens_details":{"cached_tokens":%n,"cost":%n}},"model":%s}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"completion_tokens_details":null,"prompt_tokens_details":{"cached_tokens":%n}},"provider":%s}',
+    '{"choices":[],"usage":null,"model":%s,"provider":%s,"cost":%n}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"cost":%n,"cost_details":{"upstream_inference_cost":%n},"is_byok":false},"model":%s,"provider":%s}',
+    '{"choices":[{"index":0,"message":{"role":"assistant","content":%s}}],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n}}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"reasoning_tokens":%n,"cached_tokens":%n},"model":%s}',
+    '{"choices":[],"usage":{"total_tokens":%n,"completion_tokens":%n,"prompt_tokens":%n,"cost":%n},"provider":%s,"model":%s}',
+    '{"model":%s,"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n,"completion_tokens_details":{"reasoning_tokens":%n,"accepted_prediction_tokens":%n},"prompt_tokens_details":{"cached_tokens":%n,"audio_tokens":%n}},"choices":[],"provider":%s}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"model":{"name":%s},"provider":[%s]}',
+    '{"choices":[],"usage":[{"prompt_tokens":%n}],"model":%s}',
+    '{"choices":[],"usage":{"prompt_tokens":{"v":%n},"completion_tokens":[%n,%n],"total_tokens":%n},"model":%s}',
+    '{"error":{"message":%s,"code":%n},"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n}}',
+    '{"choices":[],"usage":{"prompt_tokens":%n,"completion_tokens":%n,"total_tokens":%n},"code":%n,"model":%s}',
+]
+
+
+def skeleton_streams(n_streams: int, seed: int):
+    """Usage events of odd shapes, each shape repeated across the batch with other values (so that it is learnt as a template and
+    then FOLLOWED): keys in other places and orders, repeated keys, usage-like keys where get_token_usage does not look, containers
+    and null where numbers go, spaces inside the event."""
+    import re
+    import sse_cases as sc
+    rng = random.Random(seed)
+    shapes = rng.sample(SKELETONS, rng.randrange(2, 5))
+    out = []
+    for s_ in range(n_streams):
+        evs = [sc.delta(rng.choice(["a", "hello", "x" * rng.randrange(1, 70)])) for _ in range(rng.randrange(1, 16))]
+        for _ in range(1 if rng.random() < 0.85 else 2):
+            shape = rng.choice(shapes) if rng.random() < 0.93 else rng.choice(SKELETONS)
+
+            def fill(m):
+                r = rng.random()
+                if m.group(0) == "%n":
+                    return rng.choice(NUMBERS) if r < 0.9 else (rng.choice(BAD_NUMBERS) if r < 0.94 else rng.choice(["null", "true", '"7"', "[1]", "{}"]))
+                return '"' + (rng.choice(STRINGS) if r < 0.93 else rng.choice(BAD_STRINGS)) + '"' if r < 0.97 else rng.choice(["null", "12", "[]"])
+            ev = re.sub(r"%[ns]", fill, shape)
+            evs.append(("data: " + ev + "\n\n").encode("utf-8", errors="surrogatepass"))
+            if rng.random() < 0.25:
+                evs.append(sc.delta("more"))
+        if rng.random() < 0.8:
+            evs.append(sc.DONE)
+        out.append(_recut(rng, evs))
+    return out
+
+
 def make_streams(gen: str, n: int, seed: int):
     import test_sse_gpu as G
     if gen in ("openai", "c3"):
         return shaped_streams(gen, n, seed)
+    if gen == "skeleton":
+        return skeleton_streams(n, seed)
     if gen == "random":
         return G._random_streams(n, seed)
     if gen == "template":
