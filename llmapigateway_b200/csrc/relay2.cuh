@@ -1102,6 +1102,10 @@ R2_DEV bool walk_segment(R2Ctx& c, const uint32_t range_hi) {
                 c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE;
                 continue;
             }
+            // single-event mode and the pass ran on into a LATER event before it met a value span of another length: that event is
+            // judged from its start by match_single (one step per event) -- going on from the re-anchor would keep the stream in
+            // pass mode for good, because every pass ends inside the next event and never at an event start
+            if (po.kind == 0 && po.reanchored && po.nwr && c.in_kept != 2u) { c.pos = c.s_open; c.t = 0u; c.last_ra = R2_NONE; continue; }
             if (po.kind == 0) continue;
         } else if (c.in_kept == 2u && c.s_open < c.kept_end) {
             c.in_kept = 1u; c.pos = c.s_open = c.tb; c.t = 0; c.ev_a = c.ev_b = c.a_usage = 0; c.primed = 0; c.last_ra = R2_NONE;

@@ -3,6 +3,7 @@ CPU-only helper: lets the CPU suite fuzz the exact device code paths without a G
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -31,7 +32,9 @@ def lib():
     global _lib
     if _lib is None:
         if _stale():
-            subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", str(LIB), str(SRC)])
+            tmp = LIB.with_suffix(".%d.tmp" % os.getpid())      # (built aside and moved into place: other processes may be loading the library)
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", str(tmp), str(SRC)])
+            os.replace(tmp, LIB)
         _lib = C.CDLL(str(LIB))
         _lib.lgwt_parse_part.restype = C.c_uint32
     return _lib

@@ -4,6 +4,7 @@ against the real engine on the GPU box and against the emulated kernels here.  N
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -32,7 +33,9 @@ def lib():
     global _lib
     if _lib is None:
         if _stale():
-            subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-shared", "-fPIC", "-o", str(LIB), str(SRC)])
+            tmp = LIB.with_suffix(".%d.tmp" % os.getpid())      # (built aside and moved into place: other processes may be loading the library)
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-shared", "-fPIC", "-o", str(tmp), str(SRC)])
+            os.replace(tmp, LIB)
         _lib = C.CDLL(str(LIB))
         _lib.lgwt_bulk_new.restype = C.c_void_p
         _lib.lgwt_bulk_new.argtypes = [C.c_uint32] * 5
