@@ -659,6 +659,8 @@ def main():
                   "note": "lgw_sse_step with out_bytes = NULL: the relayed bytes are the caller's own (request_handler.py:141-142 yields the original chunk); "
                           "the kernels and the device-side re-emit are unchanged, only the download of the bytes is left out. NOT the headline e2e."}
     except Exception as ex:
+        if world > 1:                       # (the loop above holds barriers: a rank that stopped early would hang the others -- fail loudly)
+            raise
         e2e_vo = {"error": repr(ex)}
 
     # ---- transcript tap, same C3 batch, device resident; a side measurement, not part of `value` -----------
