@@ -86,6 +86,7 @@ class StreamBatcher:
         self.steps = 0
         self.dropped_stale = 0
         self.overflowed = 0                                   # streams that reported SF_CARRY_OVERFLOW (logged, see feed())
+        self.rows_lost = 0                                    # segments that reported SF_ROWQ_OVERFLOW (raise Engine(rowq_cap=...))
         # the engine handle is not thread-safe: every call into it goes through this one worker thread
         self._worker = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="lgw-engine")
         # pinned ingress/egress arenas: chunks are packed straight into page-locked memory the engine
@@ -265,6 +266,8 @@ class StreamBatcher:
                     flags = int(res.segs["flags"][k])
                     if flags & _abi.SF_CARRY_OVERFLOW:
                         self.overflowed += 1
+                    if flags & getattr(_abi, "SF_ROWQ_OVERFLOW", 0):          # more mid-stream rows in one step than rowq_cap: rows were dropped
+                        self.rows_lost += 1
                     for j, p in enumerate(by_slot[s]):
                         c = segc[k] + j
                         emitted = None
