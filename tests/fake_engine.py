@@ -104,5 +104,14 @@ class FakeEngine:
             models[i, :len(t)] = np.frombuffer(t, dtype=np.uint8)
         return scans, models
 
+    def documents_usage(self, docs):
+        """same result shape as Engine.documents_usage, from the host build of the document tap"""
+        res = []
+        for d in docs:
+            o = hm.doc_usage(bytes(d))
+            row = _abi.usage_rec_to_dict(o.rec)
+            res.append(([dict(row), row] if o.error_row else [row], bool(o.exotic)))
+        return res
+
     def documents_error_detail(self, docs, text_stride: int = 4096):
         return [hm.error_detail(bytes(d), text_stride) for d in docs]

@@ -148,3 +148,12 @@ def error_detail(raw: bytes, cap: int = 4096):
     buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
     lib().lgwt_error_detail(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.byref(out), text.ctypes.data_as(C.c_void_p), C.c_uint32(cap))
     return out, bytes(text[:out.text_len])
+
+
+def doc_usage(raw: bytes):
+    """lgw_doc_usage of the host build of the document tap (the machine calls of k_docs_usage, csrc/doc_kernels.cuh)"""
+    from llmapigateway_b200 import _abi
+    out = _abi.DocUsage()
+    buf = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    lib().lgwt_doc_usage(buf.ctypes.data_as(C.c_void_p), C.c_uint32(len(raw)), C.byref(out))
+    return out

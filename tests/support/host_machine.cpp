@@ -116,3 +116,24 @@ static_assert(sizeof(lgw::DocError) == sizeof(lgw_doc_error), "DocError");
 extern "C" void lgwt_error_detail(const uint8_t* doc, uint32_t n, lgw_doc_error* out, uint8_t* text, uint32_t cap) {
     lgw::error_detail_of(doc, n, *(lgw::DocError*)out, text, cap);
 }
+
+// ---- response tap of a non-streaming response: what lane 0 of k_docs_usage does for one document (doc_kernels.cuh:32-50; the
+//      kernel itself holds __global__ code and is not included here -- the same machine calls in the same order) ---------------
+extern "C" void lgwt_doc_usage(const uint8_t* doc, uint32_t len, lgw_doc_usage* out) {
+    out->flags = 0; out->rec_valid = 0; out->error_row = 0; out->exotic = 0; out->_pad = 0;
+    UsageRec& rec = *(UsageRec*)&out->rec;
+    default_usage(rec);
+    Rope r{nullptr, 0, doc, len};
+    const uint8_t cls = classify_part(r, 0, len);                       // chat_logging.py:116-121
+    if (cls == PC_NONE) return;
+    UsageRaw raw;
+    const uint32_t f = parse_part<true>(r, 0, len, cls, &raw);          // :123
+    out->flags = f;
+    if ((f & PF_VALID_B) && (f & (TK_USAGE | TK_ERROR))) {
+        if (f & PF_EXOTIC) out->exotic = 1;
+        else if (!((f & TK_CHOICES) && (f & PF_TYPE_ERROR))) {
+            if (f & TK_USAGE) { normalise_usage(raw, f, rec); out->rec_valid = 1; if (rec.exotic) out->exotic = 1; }   // :134-135
+            if (f & TK_ERROR) out->error_row = 1;                        // :137-139
+        }
+    }
+}

@@ -396,3 +396,12 @@ def test_error_detail_walk_matches_cpython(plans028):
         assert type(got) is type(want) and got == want, (raw, got, want)
         n_text += isinstance(want, str)
     assert n_text > 800 and n_exotic > 50
+
+
+def test_nonstream_response_tap_host_machine():
+    """The document tap (row a8, non-streaming mode) on the CPU box: the body of the GPU test (tests/test_body_gpu.py) over the host
+    build of the same machine calls k_docs_usage makes -- the 20 + 9 reference-generated tap cases and 1 500 fuzzed documents
+    against the oracle."""
+    import test_body_gpu as G
+    from fake_engine import FakeEngine
+    G.test_nonstream_response_tap(FakeEngine(max_streams=2))
