@@ -232,6 +232,43 @@ def one_round(job):
         return tag, False, traceback.format_exc(limit=3)
 
 
+def transcript_round(job):
+    """The same generators through the transcript tap (k_text_extract / scan / pack on the emulator, TranscriptBook on the host)
+    against the oracle's llm_response_accum at every write_log call."""
+    gen, seed, n_steps, geo, n_streams, cold = job
+    import test_transcript_gpu as T
+    from host_relay import HostBulkEngine
+    from llmapigateway_b200 import _abi
+    from llmapigateway_b200.transcripts import decode_text
+    from oracle.sse_oracle import run_stream
+    tag = f"{gen}:{seed}:{n_steps}:{geo}:{int(cold)}"
+    try:
+        nb, tpw = GEOMETRIES[geo]
+        eng = HostBulkEngine(max_streams=2048, carry_cap=8192, n_blocks=nb, tiles_per_warp=tpw)
+        eng.enable_transcripts()
+        try:
+            streams = make_streams(gen, n_streams, seed)
+            rng = random.Random(seed)
+            scheds = [[0] + sorted(set(rng.randrange(1, max(2, len(c))) for _ in range(n_steps - 1))) if len(c) > 1 else [0] for c in streams]
+            res = T.run_streams(eng, streams, scheds)
+            n_cmp = 0
+            for i, (chunks, (snaps, flags, emitted_any, seq_steps)) in enumerate(zip(streams, res)):
+                relay, tap = run_stream(chunks)
+                where = f"{tag} stream {i}"
+                if relay.failed:
+                    assert snaps == [], where + " transcript of a failed stream"
+                    continue
+                if flags & _abi.TF_EXOTIC:
+                    continue
+                assert [decode_text(t) for t in snaps] == tap.transcripts, where + " transcripts != oracle"
+                n_cmp += 1
+            return tag, True, f"{n_cmp}/{n_streams} transcripts compared with the oracle"
+        finally:
+            eng.close_engine()
+    except Exception:
+        return tag, False, traceback.format_exc(limit=3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=20)
@@ -240,10 +277,12 @@ def main():
     ap.add_argument("--streams", type=int, default=300)
     ap.add_argument("--replay", default=None)
     ap.add_argument("--gens", default=None, help="comma-separated subset of the generators")
+    ap.add_argument("--transcripts", action="store_true", help="check the transcript tap instead of the relay / usage results")
     args = ap.parse_args()
     if args.replay:
         gen, seed, n_steps, geo, *cold = args.replay.split(":")
-        print(*one_round((gen, int(seed), int(n_steps), int(geo), args.streams, bool(cold and int(cold[0])))), sep="\n")
+        fn = transcript_round if args.transcripts else one_round
+        print(*fn((gen, int(seed), int(n_steps), int(geo), args.streams, bool(cold and int(cold[0])))), sep="\n")
         return 0
     if args.gens:
         GENERATORS[:] = args.gens.split(",")
@@ -261,7 +300,8 @@ def main():
     def spawn(job):
         gen, seed, n_steps, geo, n_streams, cold = job
         tag = f"{gen}:{seed}:{n_steps}:{geo}:{int(cold)}"
-        r = subprocess.run([sys.executable, __file__, "--replay", tag, "--streams", str(n_streams)], capture_output=True, text=True)
+        r = subprocess.run([sys.executable, __file__, "--replay", tag, "--streams", str(n_streams)] + (["--transcripts"] if args.transcripts else []),
+                           capture_output=True, text=True)
         lines = [l for l in r.stdout.splitlines() if l.strip()]
         if r.returncode != 0 or len(lines) < 3:
             return tag, False, "process ended with status %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])
