@@ -62,6 +62,27 @@ def _http_exception(status: int, detail: str):
     return HTTPException(status_code=status, detail=detail)
 
 
+try:
+    from fastapi import HTTPException as _HTTPException
+except ImportError:                                                        # (the walker is only ever used under FastAPI)
+    _HTTPException = Exception
+
+
+class RequestNotModelled(_HTTPException):
+    """The engine reports the request body but does not model it (duplicate keys, a float that needs 17 significant digits,
+    nesting beyond the machine's depth, a value the encoder rejects ...).  Raised BEFORE any upstream attempt, so that the
+    integrator can hand the whole request to the reference's own `chat_completions`; uncaught it answers
+    501 with the reason.  It must not be walked as a failed attempt: the retry plan of the next attempt drops `messages`
+    (chat.py:150's log scrub), the offending value with it, and a scrubbed body would go upstream as the FIRST real attempt."""
+
+    def __init__(self, reason: str):
+        self.reason = reason
+        if _HTTPException is Exception:
+            super().__init__(reason)
+        else:
+            super().__init__(status_code=501, detail=f"request body not modelled by the engine ({reason})")
+
+
 def attempt_headers(provider_cfg, rule: dict) -> dict:
     """chat.py:94-123: the headers of every attempt of one rule."""
     key_name = provider_cfg.apikey
@@ -139,6 +160,7 @@ async def chat_completions(request, *, batcher: StreamBatcher, rotation: ModelRo
     seq, gw_key = rule_sequence(fallback_rules, plans.fallback_provider, requested_model, api_key, rotation)
 
     last_error_detail = "No providers were attempted."                     # :82
+    attempted = False
     for rule_idx, rule in seq:                                             # :83
         provider_cfg = providers_config.get(rule.get("provider"))
         target_url = f"{provider_cfg.baseUrl.rstrip('/')}/chat/completions"           # :111
@@ -151,6 +173,9 @@ async def chat_completions(request, *, batcher: StreamBatcher, rotation: ModelRo
             for sub_idx, sub_provider in tries:
                 plan = plans.plan_index(gw_key, rule_idx, sub_idx, retry=scrubbed and sub_idx < 0, stream=is_streaming)
                 status, payload = (await batcher.rewrite_bodies([raw], [plan]))[0]
+                if status != rw.BODY_OK and not attempted:                 # nothing went upstream yet: hand the request back whole
+                    raise RequestNotModelled(rw.STATUS_NAMES[status])
+                attempted = True
                 if status != rw.BODY_OK:
                     response_data, error_detail = None, f"Unexpected error during request to {target_url}: request body not modelled by the engine ({rw.STATUS_NAMES[status]})"
                 else:
@@ -225,7 +250,8 @@ class Answers:
 
 @dataclass
 class ChainOutcome:
-    served_round: np.ndarray         # int32 per request: round (attempt number) that served it; -1 = all attempts failed (503); -2 = 400
+    served_round: np.ndarray         # int32 per request: round (attempt number) that served it; -1 = all attempts failed (503); -2 = 400;
+                                     #   -3 = handed back before any attempt (RequestNotModelled: detail holds the reason)
     detail: list                     # per request: None, or the HTTPException detail (503 / 400)
     spans: np.ndarray                # int64 [n, 2]: the relayed bytes of request i are round_out[served_round[i]][lo:hi]
     round_out: list                  # per round: the step's re-emitted byte buffer
@@ -414,21 +440,45 @@ class ChainBatch:
             lap("control")
             pay, pay_off, res = eng.rewrite_packed(sub_buf, sub_off, plan_idx, slot_cap)
             lap("rewrite")
+            late_bad = []
+            bad_body = res["status"] != rw.BODY_OK
+            if bad_body.any():
+                # bodies the engine reports but does not model never reach an upstream.  Before any attempt (round 0) the request is
+                # handed back whole (RequestNotModelled: a failed attempt would be followed by the retry plan, which drops
+                # `messages` and the offending value with it); later it is a failed attempt with that text.
+                for k in np.nonzero(bad_body)[0]:
+                    i = int(going[k]); reason = rw.STATUS_NAMES[int(res["status"][k])]
+                    if rnd == 0:
+                        out.served_round[i] = -3
+                        out.detail[i] = f"request body not modelled by the engine ({reason})"
+                    else:
+                        fail_text[i] = f"Unexpected error during request to {sched_list[sid[i]][rnd][1]}: request body not modelled by the engine ({reason})"
+                        fail_round[i] = rnd
+                        late_bad.append(i)
+                keep = ~bad_body
+                lens = (pay_off[1:] - pay_off[:-1]).astype(np.int64)
+                if int(lens[bad_body].sum()):                                      # (their slots hold bytes: close the gaps)
+                    starts = pay_off[:-1].astype(np.int64)[keep]
+                    kl = lens[keep]
+                    idx = np.repeat(starts - np.concatenate([[0], np.cumsum(kl)[:-1]]), kl) + np.arange(int(kl.sum()), dtype=np.int64)
+                    pay = pay[idx]
+                new_off = np.zeros(int(keep.sum()) + 1, np.uint64); np.cumsum(lens[keep], out=new_off[1:])
+                pay_off, going = new_off, going[keep]
+                if not going.size:
+                    out.round_out.append(None)
+                    active = np.array(sorted(late_bad), dtype=np.int64)
+                    rnd += 1
+                    continue
             urls = [sched_list[k][rnd][1] for k in sid[going]] if getattr(upstream, "wants_urls", True) else None
             ans: Answers = upstream(rnd, ids[going], urls, pay, pay_off)
             lap("upstream")
             out.attempts += int(going.size)
-            bad_body = res["status"] != rw.BODY_OK
-            http_fail = (ans.http_status >= 400) & ~bad_body
-            streaming = ~(http_fail | bad_body)                                    # these sent a response stream, in order
-            failed_now = [going[bad_body | http_fail]]
-            for k in np.nonzero(bad_body)[0]:
-                i = int(going[k]); url = sched_list[sid[i]][rnd][1]
-                fail_text[i] = f"Unexpected error during request to {url}: request body not modelled by the engine ({rw.STATUS_NAMES[int(res['status'][k])]})"
-            for k, body in zip(np.nonzero(ans.http_status >= 400)[0], ans.error_bodies):
-                if not bad_body[k]:
-                    fail_text[int(going[k])] = ("http", body)                      # (decoded at the end, for the requests that end in a 503)
-            fail_round[going[bad_body | http_fail]] = rnd
+            http_fail = ans.http_status >= 400
+            streaming = ~http_fail                                                 # these sent a response stream, in order
+            failed_now = [going[http_fail]] + ([np.array(late_bad, dtype=going.dtype)] if late_bad else [])
+            for k, body in zip(np.nonzero(http_fail)[0], ans.error_bodies):
+                fail_text[int(going[k])] = ("http", body)                          # (decoded at the end, for the requests that end in a 503)
+            fail_round[going[http_fail]] = rnd
             # ---- everything the upstreams streamed back: one step --------------------------------------------------------------
             sreq = going[streaming]
             m = int(sreq.size)

@@ -470,3 +470,48 @@ def test_config1_plumbing_matches_the_reference_golden():
     want_doc = json.loads(base64.b64decode(g["attempts"][0]["body"]))
     assert sent == bo.RENDERERS["json5"](want_doc)
     assert canon_rows(rows) == g["rows"]
+
+
+def test_a_request_body_the_engine_does_not_model_is_handed_back_before_any_attempt():
+    """Found by tools/fuzz_chain_live.py: a body with a value the engine reports but does not model (a float that needs 17
+    significant digits inside `messages`) used to be walked as a FAILED ATTEMPT -- and the next attempt's retry plan drops
+    `messages` (the log scrub of chat.py:150), the offending value with it, so a scrubbed body went upstream as the first real
+    attempt.  Now: chat_completions raises RequestNotModelled (501) with no upstream call made; ChainBatch reports the request as
+    handed back (served_round -3) and walks the others as before."""
+    import types
+    from fake_engine import FakeEngine
+    from llmapigateway_b200 import chat, rewrite, synth
+    import chain_cases as cc
+    providers, rules, fallback_provider = synth.chain_world()
+    odd = b'{"model":"gw/retrying","stream":true,"messages":[{"role":"user","content":"x","w":0.12345678901234567}]}'
+    calls = []
+
+    def handler(request):
+        calls.append(request.content)
+        return httpx.Response(500, content=b"never expected")
+
+    async def go():
+        batcher = StreamBatcher(FakeEngine(max_streams=4), window_s=0.0005)
+        batcher.load_rules(rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode()))
+        loader = types.SimpleNamespace(providers_config=providers, fallback_rules=rules)
+        with pytest.raises(chat.RequestNotModelled) as ei:
+            await chat.chat_completions(cc.FakeRequest(odd, {}, loader), batcher=batcher,
+                                        client_factory=lambda **kw: httpx.AsyncClient(transport=httpx.MockTransport(handler), **kw))
+        assert ei.value.status_code == 501 and "exotic" in ei.value.detail and calls == []
+    asyncio.run(go())
+
+    n = 12
+    up = synth.ChainUpstream(n, 4, seed=6, p_fail=0.5)
+    bodies = synth.chain_request_bodies(n, seed=6)
+    bodies[3] = odd
+    bodies[8] = odd.replace(b"gw/retrying", b"gw/chain3" if b"gw/chain3" in bodies[0] else b"gw/retrying")
+    eng = FakeEngine(max_streams=n)
+    plans = rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode())
+    eng.load_rules(plans)
+    ref = chat.ChainBatch(eng, plans, providers, rules).run([b for k, b in enumerate(bodies) if k not in (3, 8)], None, up,
+                                                             stream_ids=[k for k in range(n) if k not in (3, 8)])
+    out = chat.ChainBatch(eng, plans, providers, rules).run(bodies, None, up)
+    assert list(out.served_round[[3, 8]]) == [-3, -3] and all("not modelled by the engine (exotic)" in out.detail[k] for k in (3, 8))
+    others = [k for k in range(n) if k not in (3, 8)]
+    assert list(out.served_round[others]) == list(ref.served_round) and [out.emitted(k) for k in others] == [ref.emitted(j) for j in range(len(others))]
+    assert [out.detail[k] for k in others] == list(ref.detail) and out.attempts == ref.attempts

@@ -69,7 +69,14 @@ def run_world(seed: int, n_requests: int):
     reqs = []
     for sid in range(n_requests):
         model = rng.choice(models)
-        body = synth.chain_request_bodies(1, seed=seed * 1000 + sid, model=model, pad_to=rng.choice([120, 200, 256]))[0]
+        if run_world.rich and rng.random() < 0.7:        # rich bodies: random JSON (nested values, floats in odd spellings, escapes, odd keys)
+            import body_cases as bc
+            d = bc.rand_body(rng)
+            d["model"] = model
+            d["stream"] = True
+            body = bc.spell(rng, d).encode("utf-8")
+        else:
+            body = synth.chain_request_bodies(1, seed=seed * 1000 + sid, model=model, pad_to=rng.choice([120, 200, 256]))[0]
         key = rng.choice(["", "rot-key-0", "rot-key-1"])
         reqs.append((sid, body, {"Authorization": f"Bearer {key}"} if key else {}, key))
     # ---- the reference ----
@@ -93,8 +100,17 @@ def run_world(seed: int, n_requests: int):
         batcher = StreamBatcher(FakeEngine(max_streams=8), window_s=0.0002)
         batcher.load_rules(rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode()))
         rotation = our_chat.ModelRotation()
+        real_rewrite = batcher.rewrite_bodies
+        odd = []
+
+        async def watched(bodies, plan_idx):                       # a body the engine does not model (status != ok) at ANY attempt of the walk:
+            r = await real_rewrite(bodies, plan_idx)               #   before the first attempt the request is handed back (RequestNotModelled),
+            odd.extend(st for st, _ in r if st != rewrite.BODY_OK)  #   later it counts as a failed attempt -- a documented limit, not compared
+            return r
+        batcher.rewrite_bodies = watched
         for sid, body, headers, key in reqs:
             attempts = []
+            del odd[:]
 
             class _Body(httpx.AsyncByteStream):
                 def __init__(self, chunks):
@@ -123,11 +139,15 @@ def run_world(seed: int, n_requests: int):
             except HTTPException as e:
                 g = dict(kind="http_exception", status=e.status_code, detail=e.detail)
             g["attempts"] = attempts
+            g["not_modelled"] = bool(odd)
             got.append(g)
 
     asyncio.run(go())
     n_attempts = 0
     for case, g in zip(want, got):
+        if g["not_modelled"] or (g["kind"] == "http_exception" and "not modelled by the engine" in str(g.get("detail"))):
+            run_world.handed_back += 1            # a documented hand-back (duplicate keys, 17-digit floats, ...): the integrator's own path
+            continue
         cc.check_against_golden(case, g)
         n_attempts += len(case["attempts"])
     kinds = {}
@@ -142,7 +162,9 @@ def main():
     ap.add_argument("--worlds", type=int, default=20)
     ap.add_argument("--requests", type=int, default=30)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--rich-bodies", action="store_true", help="request bodies of random JSON instead of the padded chat shape")
     args = ap.parse_args()
+    run_world.rich, run_world.handed_back = args.rich_bodies, 0
     if not Path("/root/reference").exists():
         print("needs /root/reference (dev container)"); return 2
     import make_chain_golden as mcg
@@ -156,7 +178,7 @@ def main():
         except AssertionError as e:
             bad += 1
             print(f"FAIL world {seed}: {str(e)[:600]}", flush=True)
-    print(f"{args.worlds - bad}/{args.worlds} worlds agree with the unmodified endpoint")
+    print(f"{args.worlds - bad}/{args.worlds} worlds agree with the unmodified endpoint ({run_world.handed_back} requests handed back as not modelled)")
     return 1 if bad else 0
 
 
