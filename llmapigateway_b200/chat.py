@@ -218,7 +218,8 @@ def _request_error_text(raw: bytes, probe=None) -> str:
         bytes(raw).decode("utf-8")
     except UnicodeDecodeError as e:
         return str(e)
-    if probe is not None and probe[0] == rw.BODY_OK and probe[1] in _ROOT_ERRORS:
+    # (EXOTIC / ENCODE_ERROR: the document parsed -- it holds a value the engine does not re-render, which does not matter here)
+    if probe is not None and probe[0] in (rw.BODY_OK, rw.BODY_EXOTIC, rw.BODY_ENCODE_ERROR) and probe[1] in _ROOT_ERRORS:
         return _ROOT_ERRORS[probe[1]]
     return "request body is not valid JSON"
 

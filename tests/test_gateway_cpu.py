@@ -515,3 +515,30 @@ def test_a_request_body_the_engine_does_not_model_is_handed_back_before_any_atte
     others = [k for k in range(n) if k not in (3, 8)]
     assert list(out.served_round[others]) == list(ref.served_round) and [out.emitted(k) for k in others] == [ref.emitted(j) for j in range(len(others))]
     assert [out.detail[k] for k in others] == list(ref.detail) and out.attempts == ref.attempts
+
+
+def test_request_error_text_of_a_document_the_engine_does_not_render():
+    """Found by tools/fuzz_chain_live.py --broken: a valid JSON object WITHOUT a "model" key that also holds a value the engine does
+    not re-render (a float outside 1e+-290, a duplicate key, NaN) answered "request body is not valid JSON"; the reference's text is
+    the KeyError's, `'model'` (chat.py:35-39) -- and the TypeError texts for non-object roots of that kind."""
+    import types
+    from fake_engine import FakeEngine
+    from llmapigateway_b200 import chat, rewrite, synth
+    import chain_cases as cc
+    from fastapi import HTTPException
+    providers, rules, fallback_provider = synth.chain_world()
+    want = [(b'{"mode":"x","a":1.5e+300,"stream":true}', "Error reading request body: 'model'"),
+            (b'{"a":1,"a":2}', "Error reading request body: 'model'"),
+            (b'{"a":NaN}', "Error reading request body: 'model'"),
+            (b'[1.5e+300]', "Error reading request body: list indices must be integers or slices, not str"),
+            (b'1.5e+300', "Error reading request body: 'float' object does not support item assignment")]
+
+    async def go():
+        batcher = StreamBatcher(FakeEngine(max_streams=4), window_s=0.0005)
+        batcher.load_rules(rewrite.RulePlans(rules, fallback_provider=fallback_provider, stream_mode=cc.stream_mode()))
+        loader = types.SimpleNamespace(providers_config=providers, fallback_rules=rules)
+        for body, detail in want:
+            with pytest.raises(HTTPException) as ei:
+                await chat.chat_completions(cc.FakeRequest(body, {}, loader), batcher=batcher)
+            assert ei.value.status_code == 400 and ei.value.detail == detail, body
+    asyncio.run(go())
