@@ -55,13 +55,17 @@ def main():
         out = []
         for raw, status in docs:
             handler = lambda request, raw=raw, status=status: httpx.Response(status, headers={"content-type": "application/json"}, content=raw)
-            out.append(await make_llm_request(url, {}, payload, False, batcher=batcher,
-                                              client_factory=lambda handler=handler, **kw: httpx.AsyncClient(transport=httpx.MockTransport(handler), **kw)))
+            resp, err = await make_llm_request(url, {}, payload, False, batcher=batcher,
+                                               client_factory=lambda handler=handler, **kw: httpx.AsyncClient(transport=httpx.MockTransport(handler), **kw))
+            tap = (await batcher.documents_usage([bytes(resp.body)]))[0] if resp is not None else None     # what log_chat_completions stores for it
+            out.append((resp, err, tap))
         return out
 
     got = asyncio.run(ours())
     bad = n_ok = n_fail = n_exotic = 0
-    for it, ((raw, status), (resp, err)) in enumerate(zip(docs, got)):
+    from golden_io import canon_rows
+    n_rows = 0
+    for it, ((raw, status), (resp, err, tap)) in enumerate(zip(docs, got)):
         want = ref_driver.run_nonstream(raw, status, url)
         try:
             if resp is None and isinstance(err, str) and "not modelled by the engine" in err:
@@ -70,6 +74,11 @@ def main():
                 assert resp is not None and err is None, f"reference ok, ours failed: {err!r}"
                 assert bytes(resp.body) == want["body"], "rendered bytes"
                 n_ok += 1
+                rows, exotic = tap
+                if not exotic:                                  # the middleware's tap over the served body (chat_logging.py:98-150, non-streaming mode)
+                    ref_rows, _ = ref_driver.run_tap([want["body"]], is_real_streaming=False)
+                    assert canon_rows(rows) == canon_rows(ref_rows), f"tap rows {rows} != {ref_rows}"
+                    n_rows += len(ref_rows)
             elif want["kind"] == "raise":                      # Starlette's render raises (NaN ...): the engine must not serve it
                 assert resp is None, "reference cannot render this, ours served it"
             else:
@@ -82,7 +91,7 @@ def main():
         except AssertionError as e:
             bad += 1
             print(f"FAIL doc {it} status {status}: {e}; {raw[:260]!r}"[:900], flush=True)
-    print(f"{args.docs - bad}/{args.docs} documents: product non-streaming seam == unmodified reference ({n_ok} served, {n_fail} failed attempts, {n_exotic} reported as not modelled)")
+    print(f"{args.docs - bad}/{args.docs} documents: product non-streaming seam == unmodified reference ({n_ok} served with {n_rows} tap rows compared, {n_fail} failed attempts, {n_exotic} reported as not modelled)")
     return 1 if bad else 0
 
 
